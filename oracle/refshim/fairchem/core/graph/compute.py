@@ -1,0 +1,17 @@
+"""ORACLE stand-in for fairchem.core.graph.compute.generate_graph (call site
+equiformerv2_oc20.py:223-234).  fairchem is un-vendored and un-pinned; this brute-force
+restatement follows its documented semantics: all periodic images within `cutoff`,
+edge_index[0] = neighbour j, edge_index[1] = centre i, vec = pos[j] - pos[i] + offset,
+per-centre truncation to `max_neighbors` with a 0.01 A degeneracy tolerance when
+enforce_max_neighbors_strictly=False.  PARITY UNPINNED."""
+import torch
+
+from oracle.eqv2_oracle import radius_graph_pbc_fairchem
+
+
+def generate_graph(data, cutoff, max_neighbors, enforce_max_neighbors_strictly=False,
+                   radius_pbc_version=1, pbc=None):
+    ei, dist, vec = radius_graph_pbc_fairchem(
+        data.pos, data.cell, data.batch, data.natoms, cutoff, max_neighbors,
+        enforce_max_neighbors_strictly)
+    return {"edge_index": ei, "edge_distance": dist, "edge_distance_vec": vec}
