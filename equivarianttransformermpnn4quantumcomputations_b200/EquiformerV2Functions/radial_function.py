@@ -1,0 +1,32 @@
+"""RadialFunction (reference radial_function.py:5-30): Linear -> [LayerNorm -> SiLU -> Linear]*.
+Same `net.<i>` parameter names; the forward runs the grouped-GEMM engine and the fused
+LayerNorm+SiLU kernel instead of nn.Sequential."""
+import torch.nn as nn
+
+from .. import ops
+
+
+class RadialFunction(nn.Module):
+    def __init__(self, channels_list):
+        super().__init__()
+        mods = []
+        for i in range(1, len(channels_list)):
+            mods.append(nn.Linear(channels_list[i - 1], channels_list[i], bias=True))
+            if i < len(channels_list) - 1:
+                mods.append(nn.LayerNorm(channels_list[i]))
+                mods.append(nn.SiLU())
+        self.net = nn.Sequential(*mods)
+
+    def forward(self, inputs):
+        x = inputs
+        mods = list(self.net)
+        i = 0
+        while i < len(mods):
+            lin = mods[i]
+            x = ops.linear(x, lin.weight, lin.bias)
+            i += 1
+            if i < len(mods):
+                ln = mods[i]
+                x = ops.LnSiluFn.apply(x, ln.weight, ln.bias, ln.eps)
+                i += 2
+        return x

@@ -1,0 +1,139 @@
+"""ctypes binding of libeqv2_b200.so (C ABI declared in include/eqv2_b200.h).
+
+There is NO fallback: if the CUDA library is missing the package raises on first use.
+`use_library_for_testing()` exists only so the CPU test-suite can point the same Python
+host code at tests/emu/libeqv2_emu.so (the kernel *source* executed by a CPU emulator) --
+it is never selected automatically.
+"""
+import ctypes
+import os
+
+import torch
+
+_PKG = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_PKG, "libeqv2_b200.so")
+
+P = ctypes.c_void_p
+I = ctypes.c_int
+L = ctypes.c_longlong
+F = ctypes.c_float
+
+
+class GemmDesc(ctypes.Structure):
+    _fields_ = [
+        ("A", P), ("B", P), ("C", P), ("bias", P),
+        ("M", I), ("N", I), ("K", I), ("transA", I), ("transB", I),
+        ("a_rpb", L), ("a_bs", L), ("a_ld", L),
+        ("b_rpb", L), ("b_bs", L), ("b_ld", L),
+        ("c_rpb", L), ("c_bs", L), ("c_ld", L),
+        ("accumulate", I),
+    ]
+
+
+MAX_GEMM_GROUPS = 10
+
+_PROTOS = {
+    "eqv2_abi_version": [],
+    "eqv2_gemm_f32": [P, I, I, P],
+    "eqv2_wigner_from_rot": [P, P, P, L, I, P],
+    "eqv2_gather_rotate_fwd": [P, P, P, P, P, P, P, P, L, I, I, I, I, I, P],
+    "eqv2_gather_rotate_bwd": [P, P, P, P, P, P, P, P, P, P, P, P, L, I, I, I, I, I, P],
+    "eqv2_rotinv_reduce_fwd": [P, P, P, P, P, P, P, L, I, I, L, I, I, I, F, P],
+    "eqv2_rotinv_reduce_bwd": [P, P, P, P, P, P, P, P, L, I, I, L, I, I, I, F, P],
+    "eqv2_s2act_padded_rows": [I],
+    "eqv2_s2act_fwd": [P, L, P, L, P, L, P, P, L, I, I, I, I, I, P],
+    "eqv2_s2act_bwd": [P, L, P, L, P, L, P, L, P, L, P, P, L, I, I, I, I, I, P],
+    "eqv2_attn_alpha_fwd": [P, L, P, P, P, P, P, P, P, L, L, I, I, F, P],
+    "eqv2_attn_alpha_bwd": [P, L, P, P, P, P, P, P, P, P, P, L, P, P, P, L, L, I, I, F, P],
+    "eqv2_equiv_norm_fwd": [P, P, P, P, P, P, L, I, I, I, P, P, F, P],
+    "eqv2_equiv_norm_bwd": [P, P, P, P, P, P, P, P, L, I, I, I, P, P, P],
+    "eqv2_rbf_fwd": [P, P, L, I, P, F, P],
+    "eqv2_rbf_bwd": [P, P, P, L, I, P, F, P],
+    "eqv2_ln_silu_fwd": [P, P, P, P, L, I, F, P],
+    "eqv2_ln_silu_bwd": [P, P, P, P, P, P, P, L, I, F, P],
+}
+# entry points that only exist in the real (nvcc-built) library
+_OPTIONAL = set()
+
+_state = {"lib": None, "emu": False, "launches": 0}
+
+
+class Eqv2Error(RuntimeError):
+    pass
+
+
+def _bind(path):
+    lib = ctypes.CDLL(path)
+    lib.eqv2_last_error.restype = ctypes.c_char_p
+    for name, args in _PROTOS.items():
+        try:
+            fn = getattr(lib, name)
+        except AttributeError:
+            if name in _OPTIONAL:
+                continue
+            raise
+        fn.argtypes = args
+        fn.restype = I
+    return lib
+
+
+def lib():
+    if _state["lib"] is None:
+        if not os.path.exists(LIB_PATH):
+            raise Eqv2Error(
+                f"{LIB_PATH} is missing: build it with `python -m equivarianttransformermpnn4quantumcomputations_b200.build` "
+                "(nvcc, sm_100a). There is no CPU / PyTorch fallback for this package.")
+        _state["lib"] = _bind(LIB_PATH)
+        _state["emu"] = False
+    return _state["lib"]
+
+
+def use_library_for_testing(path):
+    """TEST HOOK: bind an alternative build of the same C ABI (the CPU emulator build)."""
+    _state["lib"] = _bind(path) if path is not None else None
+    _state["emu"] = path is not None
+
+
+def is_emulated():
+    return _state["emu"]
+
+
+def launch_count():
+    return _state["launches"]
+
+
+def reset_launch_count():
+    _state["launches"] = 0
+
+
+def check_device(*tensors):
+    """Product path: every tensor must live on a CUDA device (emulator hook: on CPU)."""
+    for t in tensors:
+        if t is None:
+            continue
+        if _state["emu"]:
+            if t.is_cuda:
+                raise Eqv2Error("emulated library bound but tensor is on CUDA")
+        elif not t.is_cuda:
+            raise Eqv2Error("eqv2_b200 kernels need CUDA tensors; there is no CPU fallback")
+
+
+def ptr(t):
+    if t is None:
+        return None
+    return t.data_ptr()
+
+
+def stream_ptr(ref=None):
+    if _state["emu"]:
+        return None
+    return torch.cuda.current_stream().cuda_stream
+
+
+def call(name, *args, n_kernels=1):
+    fn = getattr(lib(), name)
+    rc = fn(*args)
+    if rc != 0:
+        raise Eqv2Error(f"{name} failed ({rc}): {lib().eqv2_last_error().decode()}")
+    _state["launches"] += n_kernels
+    return rc

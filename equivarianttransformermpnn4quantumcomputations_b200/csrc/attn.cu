@@ -1,0 +1,231 @@
+// Attention logits + per-destination segment softmax (transformer_block.py:311-315,
+// activation.py:66-75, torch_geometric.utils.softmax semantics: max-shift, +1e-16 in the
+// denominator).  Edges of one destination node are visited through the dst-sorted CSR
+// (rowptr_dst / perm_dst), so the softmax needs no atomics and is deterministic.
+//
+//   logits : one warp per (edge, head): LayerNorm(alpha_ch) -> SmoothLeakyReLU(0.2) -> dot(alpha_dot[h])
+//   softmax: one thread per (node, head)
+// Backward recomputes the normalised activations instead of saving them.
+#include "common.cuh"
+
+namespace {
+
+constexpr int MAXPL = 4;  // alpha channels per lane (alpha_ch <= 128)
+constexpr float SLR_C1 = 0.6f, SLR_C2 = 0.4f;  // (1 +- 0.2) / 2
+
+__device__ __forceinline__ float slr(float x) { return SLR_C1 * x + SLR_C2 * x * (2.f * eqv2_sigmoid(x) - 1.f); }
+__device__ __forceinline__ float dslr(float x) {
+  const float s = eqv2_sigmoid(x);
+  return SLR_C1 + SLR_C2 * (2.f * s - 1.f) + SLR_C2 * x * 2.f * s * (1.f - s);
+}
+
+__global__ void attn_logits_kernel(const float* __restrict__ Y, long long y_rs, const float* __restrict__ ln_w,
+                                   const float* __restrict__ ln_b, const float* __restrict__ alpha_dot,
+                                   float* __restrict__ logits, long long E, int heads, int ach, float eps) {
+  const int lane = threadIdx.x & 31;
+  const long long warp = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const long long nwarps = ((long long)gridDim.x * blockDim.x) >> 5;
+  const long long items = E * heads;
+  for (long long it = warp; it < items; it += nwarps) {
+    const long long e = it / heads;
+    const int h = (int)(it % heads);
+    const float* xp = Y + e * y_rs + (long long)h * ach;
+    float x[MAXPL];
+    float s = 0.f;
+#pragma unroll
+    for (int k = 0; k < MAXPL; ++k) {
+      const int i = lane + 32 * k;
+      x[k] = (i < ach) ? xp[i] : 0.f;
+      s += x[k];
+    }
+    float mean = 0.f, rstd = 1.f;
+    if (ln_w) {
+      mean = eqv2_warp_sum(s) / ach;
+      float v = 0.f;
+#pragma unroll
+      for (int k = 0; k < MAXPL; ++k) {
+        const int i = lane + 32 * k;
+        const float d = (i < ach) ? x[k] - mean : 0.f;
+        v += d * d;
+      }
+      rstd = rsqrtf(eqv2_warp_sum(v) / ach + eps);
+    }
+    float dot = 0.f;
+#pragma unroll
+    for (int k = 0; k < MAXPL; ++k) {
+      const int i = lane + 32 * k;
+      if (i < ach) {
+        float y = x[k];
+        if (ln_w) y = (x[k] - mean) * rstd * ln_w[i] + ln_b[i];
+        dot = fmaf(slr(y), alpha_dot[h * ach + i], dot);
+      }
+    }
+    dot = eqv2_warp_sum(dot);
+    if (lane == 0) logits[it] = dot;
+  }
+}
+
+__global__ void segment_softmax_fwd_kernel(const float* __restrict__ logits, const int* __restrict__ rowptr,
+                                           const int* __restrict__ perm, float* __restrict__ alpha, long long N,
+                                           int heads) {
+  const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= N * heads) return;
+  const long long n = t / heads;
+  const int h = (int)(t % heads);
+  const int beg = rowptr[n], end = rowptr[n + 1];
+  float mx = -INFINITY;
+  for (int i = beg; i < end; ++i) mx = fmaxf(mx, logits[(long long)perm[i] * heads + h]);
+  float sum = 0.f;
+  for (int i = beg; i < end; ++i) sum += expf(logits[(long long)perm[i] * heads + h] - mx);
+  const float inv = 1.0f / (sum + 1e-16f);
+  for (int i = beg; i < end; ++i) {
+    const long long e = perm[i];
+    alpha[e * heads + h] = expf(logits[e * heads + h] - mx) * inv;
+  }
+}
+
+__global__ void segment_softmax_bwd_kernel(const float* __restrict__ alpha, const float* __restrict__ dalpha,
+                                           const int* __restrict__ rowptr, const int* __restrict__ perm,
+                                           float* __restrict__ dlogits, long long N, int heads) {
+  const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= N * heads) return;
+  const long long n = t / heads;
+  const int h = (int)(t % heads);
+  const int beg = rowptr[n], end = rowptr[n + 1];
+  float dot = 0.f;
+  for (int i = beg; i < end; ++i) {
+    const long long e = perm[i];
+    dot = fmaf(alpha[e * heads + h], dalpha[e * heads + h], dot);
+  }
+  for (int i = beg; i < end; ++i) {
+    const long long e = perm[i];
+    dlogits[e * heads + h] = alpha[e * heads + h] * (dalpha[e * heads + h] - dot);
+  }
+}
+
+// one warp owns one head and strides over edges, so the parameter gradients accumulate in registers
+__global__ void attn_logits_bwd_kernel(const float* __restrict__ Y, long long y_rs, const float* __restrict__ ln_w,
+                                       const float* __restrict__ ln_b, const float* __restrict__ alpha_dot,
+                                       const float* __restrict__ dlogits, float* __restrict__ dY, long long dy_rs,
+                                       float* __restrict__ d_ln_w, float* __restrict__ d_ln_b,
+                                       float* __restrict__ d_alpha_dot, long long E, int heads, int ach, float eps) {
+  const int lane = threadIdx.x & 31;
+  const long long warp = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const long long nwarps = ((long long)gridDim.x * blockDim.x) >> 5;   // multiple of heads (host guarantees)
+  const int h = (int)(warp % heads);
+  float gw[MAXPL], gb[MAXPL], gd[MAXPL];
+#pragma unroll
+  for (int k = 0; k < MAXPL; ++k) gw[k] = gb[k] = gd[k] = 0.f;
+  for (long long e = warp / heads; e < E; e += nwarps / heads) {
+    const float* xp = Y + e * y_rs + (long long)h * ach;
+    const float dl = dlogits[e * heads + h];
+    float x[MAXPL];
+    float s = 0.f;
+#pragma unroll
+    for (int k = 0; k < MAXPL; ++k) {
+      const int i = lane + 32 * k;
+      x[k] = (i < ach) ? xp[i] : 0.f;
+      s += x[k];
+    }
+    float mean = 0.f, rstd = 1.f;
+    if (ln_w) {
+      mean = eqv2_warp_sum(s) / ach;
+      float v = 0.f;
+#pragma unroll
+      for (int k = 0; k < MAXPL; ++k) {
+        const int i = lane + 32 * k;
+        const float d = (i < ach) ? x[k] - mean : 0.f;
+        v += d * d;
+      }
+      rstd = rsqrtf(eqv2_warp_sum(v) / ach + eps);
+    }
+    float dxh[MAXPL], xh[MAXPL];
+    float s1 = 0.f, s2 = 0.f;
+#pragma unroll
+    for (int k = 0; k < MAXPL; ++k) {
+      const int i = lane + 32 * k;
+      dxh[k] = 0.f;
+      xh[k] = 0.f;
+      if (i < ach) {
+        float y = x[k];
+        if (ln_w) {
+          xh[k] = (x[k] - mean) * rstd;
+          y = xh[k] * ln_w[i] + ln_b[i];
+        }
+        gd[k] = fmaf(dl, slr(y), gd[k]);
+        const float dy = dl * alpha_dot[h * ach + i] * dslr(y);
+        if (ln_w) {
+          gw[k] = fmaf(dy, xh[k], gw[k]);
+          gb[k] += dy;
+          dxh[k] = dy * ln_w[i];
+          s1 += dxh[k];
+          s2 = fmaf(dxh[k], xh[k], s2);
+        } else {
+          dxh[k] = dy;
+        }
+      }
+    }
+    if (ln_w) {
+      s1 = eqv2_warp_sum(s1) / ach;
+      s2 = eqv2_warp_sum(s2) / ach;
+    }
+    float* dp = dY + e * dy_rs + (long long)h * ach;
+#pragma unroll
+    for (int k = 0; k < MAXPL; ++k) {
+      const int i = lane + 32 * k;
+      if (i < ach) dp[i] = ln_w ? rstd * (dxh[k] - s1 - xh[k] * s2) : dxh[k];
+    }
+  }
+#pragma unroll
+  for (int k = 0; k < MAXPL; ++k) {
+    const int i = lane + 32 * k;
+    if (i < ach) {
+      atomicAdd(&d_alpha_dot[h * ach + i], gd[k]);
+      if (ln_w) {
+        atomicAdd(&d_ln_w[i], gw[k]);
+        atomicAdd(&d_ln_b[i], gb[k]);
+      }
+    }
+  }
+}
+
+}  // namespace
+
+extern "C" int eqv2_attn_alpha_fwd(const float* Y, long long y_rs, const float* ln_w, const float* ln_b,
+                                   const float* alpha_dot, const int* rowptr_dst, const int* perm_dst, float* logits,
+                                   float* alpha, long long E, long long N, int heads, int ach, float eps,
+                                   void* stream) {
+  if (E == 0 || N == 0) return 0;
+  EQV2_REQUIRE(ach > 0 && ach <= 32 * MAXPL, "attn_alpha_fwd: alpha channels %d > %d", ach, 32 * MAXPL);
+  const long long items = E * heads;
+  const int threads = 256;
+  long long blocks = (items * 32 + threads - 1) / threads;
+  if (blocks > 148 * 16) blocks = 148 * 16;
+  EQV2_LAUNCH(attn_logits_kernel, dim3((unsigned)blocks), dim3(threads), 0, stream, Y, y_rs, ln_w, ln_b, alpha_dot, logits, E, heads, ach, eps);
+  EQV2_CHECK_LAUNCH("eqv2_attn_alpha_fwd/logits");
+  const long long t = N * heads;
+  EQV2_LAUNCH(segment_softmax_fwd_kernel, dim3((unsigned)((t + 127) / 128)), dim3(128), 0, stream, logits, rowptr_dst, perm_dst, alpha, N, heads);
+  EQV2_CHECK_LAUNCH("eqv2_attn_alpha_fwd/softmax");
+  return 0;
+}
+
+extern "C" int eqv2_attn_alpha_bwd(const float* Y, long long y_rs, const float* ln_w, const float* ln_b,
+                                   const float* alpha_dot, const int* rowptr_dst, const int* perm_dst,
+                                   const float* alpha, const float* dalpha, float* dlogits, float* dY, long long dy_rs,
+                                   float* d_ln_w, float* d_ln_b, float* d_alpha_dot, long long E, long long N,
+                                   int heads, int ach, float eps, void* stream) {
+  if (E == 0 || N == 0) return 0;
+  EQV2_REQUIRE(ach > 0 && ach <= 32 * MAXPL, "attn_alpha_bwd: alpha channels %d > %d", ach, 32 * MAXPL);
+  const long long t = N * heads;
+  EQV2_LAUNCH(segment_softmax_bwd_kernel, dim3((unsigned)((t + 127) / 128)), dim3(128), 0, stream, alpha, dalpha, rowptr_dst, perm_dst, dlogits, N, heads);
+  EQV2_CHECK_LAUNCH("eqv2_attn_alpha_bwd/softmax");
+  // warps per launch must be a multiple of `heads`
+  const int wpb = 8;
+  long long want = (E * heads + wpb - 1) / wpb;
+  if (want > 148 * 8) want = 148 * 8;
+  long long blocks = ((want * wpb + heads - 1) / heads * heads + wpb - 1) / wpb;
+  while ((blocks * wpb) % heads != 0) ++blocks;
+  EQV2_LAUNCH(attn_logits_bwd_kernel, dim3((unsigned)blocks), dim3(wpb * 32), 0, stream, Y, y_rs, ln_w, ln_b, alpha_dot, dlogits, dY, dy_rs, d_ln_w, d_ln_b, d_alpha_dot, E, heads, ach, eps);
+  EQV2_CHECK_LAUNCH("eqv2_attn_alpha_bwd/logits");
+  return 0;
+}

@@ -1,0 +1,62 @@
+// Shared helpers for the sm_100a kernels behind the C-ABI of include/eqv2_b200.h.
+#pragma once
+#include <stdint.h>
+#include <stdio.h>
+#include <string.h>
+
+#ifdef EQV2_CPU_EMU
+#include "cpu_emu.h"
+#else
+#include <cuda_runtime.h>
+#define EQV2_LAUNCH(kernel, grid, block, smem, stream, ...) \
+  kernel<<<(grid), (block), (smem), (cudaStream_t)(stream)>>>(__VA_ARGS__)
+#define EQV2_DYN_SMEM(type, name)                              \
+  extern __shared__ __align__(16) unsigned char eqv2_dyn_smem_[]; \
+  type* name = reinterpret_cast<type*>(eqv2_dyn_smem_)
+#endif
+
+#include "../../include/eqv2_b200.h"
+
+#define EQV2_MAX_LMAX 8
+#define EQV2_MAX_K 81
+
+void eqv2_set_error(const char* fmt, ...);
+
+#define EQV2_CHECK_LAUNCH(name)                                                  \
+  do {                                                                           \
+    cudaError_t e_ = cudaGetLastError();                                         \
+    if (e_ != cudaSuccess) {                                                     \
+      eqv2_set_error("%s: launch failed: %s", name, cudaGetErrorString(e_));     \
+      return 2;                                                                  \
+    }                                                                            \
+  } while (0)
+
+#define EQV2_REQUIRE(cond, ...)        \
+  do {                                 \
+    if (!(cond)) {                     \
+      eqv2_set_error(__VA_ARGS__);     \
+      return 1;                        \
+    }                                  \
+  } while (0)
+
+__device__ __forceinline__ float eqv2_sigmoid(float x) { return 1.0f / (1.0f + __expf(-x)); }
+__device__ __forceinline__ float eqv2_silu(float x) { return x * eqv2_sigmoid(x); }
+// d/dx silu(x) = s (1 + x (1 - s))
+__device__ __forceinline__ float eqv2_dsilu(float x) {
+  float s = eqv2_sigmoid(x);
+  return s * (1.0f + x * (1.0f - s));
+}
+
+__device__ __forceinline__ float eqv2_warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+__device__ __forceinline__ float eqv2_warp_max(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
+  return v;
+}
+
+// offset of the (2l+1)x(2l+1) block of degree l inside a packed block-diagonal Wigner row
+__host__ __device__ __forceinline__ int eqv2_wig_off(int l) { return l * (4 * l * l - 1) / 3; }

@@ -1,0 +1,254 @@
+// Per-edge scalar-feature kernels:
+//   * Gaussian smearing of edge distances (equiformerv2_oc20.py:43-60) fwd / bwd-wrt-distance,
+//   * fused LayerNorm + SiLU of the radial MLP (radial_function.py:21-22) fwd / bwd,
+//   * Euler angles + Wigner-D blocks of the edge frames (so3.py:525-545, wigner.py:17-39),
+//     written block-diagonal [E, sum_l (2l+1)^2] instead of dense [E,K,K].
+#include "common.cuh"
+
+namespace {
+
+// ---------------------------------------------------------------------------------------- RBF
+__global__ void rbf_fwd_kernel(const float* __restrict__ d, float* __restrict__ out, long long E, int R,
+                               const float* __restrict__ offset, float coeff) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= E * R) return;
+  const long long e = i / R;
+  const int k = (int)(i % R);
+  const float t = d[e] - offset[k];
+  out[i] = expf(coeff * t * t);
+}
+
+// dd[e] = sum_k go[e,k] * 2 coeff (d - mu_k) exp(coeff (d - mu_k)^2)
+__global__ void rbf_bwd_kernel(const float* __restrict__ d, const float* __restrict__ go, float* __restrict__ dd,
+                               long long E, int R, const float* __restrict__ offset, float coeff) {
+  const int lane = threadIdx.x & 31;
+  const long long e = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  if (e >= E) return;   // whole warp exits together
+  const float de = d[e];
+  float s = 0.f;
+  for (int k = lane; k < R; k += 32) {
+    const float t = de - offset[k];
+    s = fmaf(go[e * R + k], 2.f * coeff * t * expf(coeff * t * t), s);
+  }
+  s = eqv2_warp_sum(s);
+  if (lane == 0) dd[e] = s;
+}
+
+// ---------------------------------------------------------------------------------------- LN + SiLU
+constexpr int LN_PL = 8;  // features per lane (width <= 256)
+
+__global__ void ln_silu_fwd_kernel(const float* __restrict__ x, const float* __restrict__ w,
+                                   const float* __restrict__ b, float* __restrict__ y, long long rows, int width,
+                                   float eps) {
+  const int lane = threadIdx.x & 31;
+  const long long r = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  if (r >= rows) return;
+  const float* xp = x + r * width;
+  float v[LN_PL];
+  float s = 0.f;
+#pragma unroll
+  for (int k = 0; k < LN_PL; ++k) {
+    const int i = lane + 32 * k;
+    v[k] = (i < width) ? xp[i] : 0.f;
+    s += v[k];
+  }
+  const float mean = eqv2_warp_sum(s) / width;
+  float q = 0.f;
+#pragma unroll
+  for (int k = 0; k < LN_PL; ++k) {
+    const int i = lane + 32 * k;
+    const float t = (i < width) ? v[k] - mean : 0.f;
+    q = fmaf(t, t, q);
+  }
+  const float rstd = rsqrtf(eqv2_warp_sum(q) / width + eps);
+#pragma unroll
+  for (int k = 0; k < LN_PL; ++k) {
+    const int i = lane + 32 * k;
+    if (i < width) y[r * width + i] = eqv2_silu((v[k] - mean) * rstd * w[i] + b[i]);
+  }
+}
+
+__global__ void ln_silu_bwd_kernel(const float* __restrict__ x, const float* __restrict__ w,
+                                   const float* __restrict__ b, const float* __restrict__ gy, float* __restrict__ gx,
+                                   float* __restrict__ gw, float* __restrict__ gb, long long rows, int width,
+                                   float eps) {
+  const int lane = threadIdx.x & 31;
+  const long long warp = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const long long nwarps = ((long long)gridDim.x * blockDim.x) >> 5;
+  float aw[LN_PL], ab[LN_PL];
+#pragma unroll
+  for (int k = 0; k < LN_PL; ++k) aw[k] = ab[k] = 0.f;
+  for (long long r = warp; r < rows; r += nwarps) {
+    const float* xp = x + r * width;
+    float v[LN_PL];
+    float s = 0.f;
+#pragma unroll
+    for (int k = 0; k < LN_PL; ++k) {
+      const int i = lane + 32 * k;
+      v[k] = (i < width) ? xp[i] : 0.f;
+      s += v[k];
+    }
+    const float mean = eqv2_warp_sum(s) / width;
+    float q = 0.f;
+#pragma unroll
+    for (int k = 0; k < LN_PL; ++k) {
+      const int i = lane + 32 * k;
+      const float t = (i < width) ? v[k] - mean : 0.f;
+      q = fmaf(t, t, q);
+    }
+    const float rstd = rsqrtf(eqv2_warp_sum(q) / width + eps);
+    float dxh[LN_PL], xh[LN_PL];
+    float s1 = 0.f, s2 = 0.f;
+#pragma unroll
+    for (int k = 0; k < LN_PL; ++k) {
+      const int i = lane + 32 * k;
+      dxh[k] = xh[k] = 0.f;
+      if (i < width) {
+        xh[k] = (v[k] - mean) * rstd;
+        const float u = xh[k] * w[i] + b[i];
+        const float du = gy[r * width + i] * eqv2_dsilu(u);
+        aw[k] = fmaf(du, xh[k], aw[k]);
+        ab[k] += du;
+        dxh[k] = du * w[i];
+        s1 += dxh[k];
+        s2 = fmaf(dxh[k], xh[k], s2);
+      }
+    }
+    s1 = eqv2_warp_sum(s1) / width;
+    s2 = eqv2_warp_sum(s2) / width;
+#pragma unroll
+    for (int k = 0; k < LN_PL; ++k) {
+      const int i = lane + 32 * k;
+      if (i < width) gx[r * width + i] = rstd * (dxh[k] - s1 - xh[k] * s2);
+    }
+  }
+#pragma unroll
+  for (int k = 0; k < LN_PL; ++k) {
+    const int i = lane + 32 * k;
+    if (i < width) {
+      atomicAdd(&gw[i], aw[k]);
+      atomicAdd(&gb[i], ab[k]);
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------- Wigner-D
+constexpr int WIG_WARPS = 4;
+constexpr int MAXN = 2 * EQV2_MAX_LMAX + 1;
+
+__global__ void wigner_kernel(const float* __restrict__ rot, const float* __restrict__ Jd, float* __restrict__ wig,
+                              long long E, int lmax, int WS) {
+  EQV2_DYN_SMEM(float, smem);
+  float* sJ = smem;                                           // [WS]
+  float* sA = sJ + WS;                                        // [WIG_WARPS][MAXN*MAXN]
+  float* sT = sA + WIG_WARPS * MAXN * MAXN;                   // [WIG_WARPS][3][2][MAXN]  (angle, sin/cos, f + lmax)
+  for (int i = threadIdx.x; i < WS; i += blockDim.x) sJ[i] = Jd[i];
+  __syncthreads();
+  const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+  const long long e = (long long)blockIdx.x * WIG_WARPS + wib;
+  if (e >= E) return;   // warp-uniform; no block barriers below
+  float* A = sA + wib * MAXN * MAXN;
+  float* T = sT + wib * 6 * MAXN;
+  const float* R = rot + e * 9;
+  // x = R @ (0,1,0) -> column 1, normalised and clamped (e3nn xyz_to_angles)
+  float x0 = R[1], x1 = R[4], x2 = R[7];
+  const float nrm = fmaxf(sqrtf(x0 * x0 + x1 * x1 + x2 * x2), 1e-12f);
+  x0 = fminf(fmaxf(x0 / nrm, -1.f), 1.f);
+  x1 = fminf(fmaxf(x1 / nrm, -1.f), 1.f);
+  x2 = fminf(fmaxf(x2 / nrm, -1.f), 1.f);
+  const float beta = acosf(x1);
+  const float alpha = atan2f(x0, x2);
+  const float ca = cosf(alpha), sa = sinf(alpha);
+  // first row of (R_y(alpha) R_x(beta))^T @ R
+  const float r00 = ca * R[0] - sa * R[6];
+  const float r02 = ca * R[2] - sa * R[8];
+  const float gamma = atan2f(r02, r00);
+  // trig tables for frequencies f = -lmax..lmax
+  if (lane <= 2 * lmax) {
+    const float f = (float)(lane - lmax);
+    T[0 * MAXN + lane] = sinf(f * alpha);
+    T[1 * MAXN + lane] = cosf(f * alpha);
+    T[2 * MAXN + lane] = sinf(f * beta);
+    T[3 * MAXN + lane] = cosf(f * beta);
+    T[4 * MAXN + lane] = sinf(f * gamma);
+    T[5 * MAXN + lane] = cosf(f * gamma);
+  }
+  __syncwarp();
+  float* out = wig + e * (long long)WS;
+  for (int l = 0; l <= lmax; ++l) {
+    const int n = 2 * l + 1;
+    const float* J = sJ + eqv2_wig_off(l);
+    // A = J @ (Z(beta) @ J);   row k of Z has frequency f_k = l - k
+    for (int idx = lane; idx < n * n; idx += 32) {
+      const int i = idx / n, j = idx % n;
+      float s = 0.f;
+      for (int k = 0; k < n; ++k) {
+        const int fi = (l - k) + lmax;
+        const float zj = T[3 * MAXN + fi] * J[k * n + j] + ((2 * k + 1 == n) ? 0.f : T[2 * MAXN + fi] * J[(n - 1 - k) * n + j]);
+        s = fmaf(J[i * n + k], zj, s);
+      }
+      A[idx] = s;
+    }
+    __syncwarp();
+    for (int idx = lane; idx < n * n; idx += 32) {
+      const int i = idx / n, j = idx % n;
+      const int fi = (l - i) + lmax, fj = (l - j) + lmax;
+      const float cai = T[1 * MAXN + fi], sai = (2 * i + 1 == n) ? 0.f : T[0 * MAXN + fi];
+      const float ccj = T[5 * MAXN + fj], scj = (2 * j + 1 == n) ? 0.f : T[4 * MAXN + fj];
+      const float y_i = A[i * n + j] * ccj - A[i * n + (n - 1 - j)] * scj;
+      const float y_r = A[(n - 1 - i) * n + j] * ccj - A[(n - 1 - i) * n + (n - 1 - j)] * scj;
+      out[eqv2_wig_off(l) + idx] = cai * y_i + sai * y_r;
+    }
+    __syncwarp();
+  }
+}
+
+}  // namespace
+
+extern "C" int eqv2_rbf_fwd(const float* d, float* out, long long E, int R, const float* offset, float coeff,
+                            void* stream) {
+  if (E == 0) return 0;
+  const long long n = E * R;
+  EQV2_LAUNCH(rbf_fwd_kernel, dim3((unsigned)((n + 255) / 256)), dim3(256), 0, stream, d, out, E, R, offset, coeff);
+  EQV2_CHECK_LAUNCH("eqv2_rbf_fwd");
+  return 0;
+}
+
+extern "C" int eqv2_rbf_bwd(const float* d, const float* go, float* dd, long long E, int R, const float* offset,
+                            float coeff, void* stream) {
+  if (E == 0) return 0;
+  EQV2_LAUNCH(rbf_bwd_kernel, dim3((unsigned)((E * 32 + 255) / 256)), dim3(256), 0, stream, d, go, dd, E, R, offset, coeff);
+  EQV2_CHECK_LAUNCH("eqv2_rbf_bwd");
+  return 0;
+}
+
+extern "C" int eqv2_ln_silu_fwd(const float* x, const float* w, const float* b, float* y, long long rows, int width,
+                                float eps, void* stream) {
+  if (rows == 0) return 0;
+  EQV2_REQUIRE(width > 0 && width <= 32 * LN_PL, "ln_silu_fwd: width %d > %d", width, 32 * LN_PL);
+  EQV2_LAUNCH(ln_silu_fwd_kernel, dim3((unsigned)((rows * 32 + 255) / 256)), dim3(256), 0, stream, x, w, b, y, rows, width, eps);
+  EQV2_CHECK_LAUNCH("eqv2_ln_silu_fwd");
+  return 0;
+}
+
+extern "C" int eqv2_ln_silu_bwd(const float* x, const float* w, const float* b, const float* gy, float* gx, float* gw,
+                                float* gb, long long rows, int width, float eps, void* stream) {
+  if (rows == 0) return 0;
+  EQV2_REQUIRE(width > 0 && width <= 32 * LN_PL, "ln_silu_bwd: width %d > %d", width, 32 * LN_PL);
+  long long blocks = (rows * 32 + 255) / 256;
+  if (blocks > 148 * 8) blocks = 148 * 8;
+  EQV2_LAUNCH(ln_silu_bwd_kernel, dim3((unsigned)blocks), dim3(256), 0, stream, x, w, b, gy, gx, gw, gb, rows, width, eps);
+  EQV2_CHECK_LAUNCH("eqv2_ln_silu_bwd");
+  return 0;
+}
+
+extern "C" int eqv2_wigner_from_rot(const float* rot, const float* Jd, float* wig, long long E, int lmax,
+                                    void* stream) {
+  if (E == 0) return 0;
+  EQV2_REQUIRE(lmax >= 0 && lmax <= EQV2_MAX_LMAX, "wigner_from_rot: lmax=%d out of range", lmax);
+  const int WS = eqv2_wig_off(lmax + 1);
+  const size_t smem = (size_t)(WS + WIG_WARPS * MAXN * MAXN + WIG_WARPS * 6 * MAXN) * sizeof(float);
+  EQV2_LAUNCH(wigner_kernel, dim3((unsigned)((E + WIG_WARPS - 1) / WIG_WARPS)), dim3(WIG_WARPS * 32), smem, stream, rot, Jd, wig, E, lmax, WS);
+  EQV2_CHECK_LAUNCH("eqv2_wigner_from_rot");
+  return 0;
+}

@@ -1,0 +1,681 @@
+"""torch.autograd.Function wrappers over the C ABI (include/eqv2_b200.h).
+
+Each Function's forward/backward launches hand-written kernels on the current CUDA stream;
+nothing here falls back to PyTorch math for the operators of SURVEY §8a.  Host-side tables
+(coefficient layouts, CSR edge plans, grid matrices) are built once and cached.
+"""
+import ctypes
+import math
+
+import numpy as np
+import torch
+
+from . import _lib, _so3_math
+
+_F32 = torch.float32
+
+
+# ----------------------------------------------------------------------------------------------
+# coefficient layout tables  (so3.py:45-199 CoefficientMappingModule, single resolution)
+# ----------------------------------------------------------------------------------------------
+class CoeffLayout:
+    _cache = {}
+
+    def __init__(self, lmax, mmax):
+        self.lmax, self.mmax = lmax, mmax
+        self.K = (lmax + 1) ** 2
+        self.WS = (lmax + 1) * (4 * (lmax + 1) ** 2 - 1) // 3
+        red = [(l, m) for l in range(lmax + 1) for m in range(-min(l, mmax), min(l, mmax) + 1)]
+        self.Kr = len(red)
+        self.full_of_red = [l * l + l + m for l, m in red]               # l-primary reduced -> full index
+        # m-primary order: m=0 rows (l=0..L), then for m=1..M: +m rows, -m rows
+        order = [(l, 0) for l in range(lmax + 1)]
+        self.m_sizes = [lmax + 1]
+        for m in range(1, mmax + 1):
+            order += [(l, m) for l in range(m, lmax + 1)]
+            order += [(l, -m) for l in range(m, lmax + 1)]
+            self.m_sizes.append(lmax - m + 1)
+        self.m_order = order
+        red_index = {lm: i for i, lm in enumerate(red)}
+        self.to_m = [red_index[lm] for lm in order]                      # m_primary[j] = l_primary[to_m[j]]
+        pos_of_full = [-1] * self.K
+        for p, (l, m) in enumerate(order):
+            pos_of_full[l * l + l + m] = p
+        self.pos_of_full_host = pos_of_full
+        # radial slot per m-primary row: slot * Cin + channel indexes the rad vector (so2_ops.py:100-133)
+        slot, base = [], 0
+        for m in range(mmax + 1):
+            n = lmax - m + 1
+            if m == 0:
+                slot += [base + i for i in range(n)]
+            else:
+                slot += [base + i for i in range(n)] * 2
+            base += n
+        self.rad_slot_host = slot
+        self.nslot = base
+        self.row_l = [l for l, _ in order]
+        self._dev = {}
+
+    @classmethod
+    def get(cls, lmax, mmax):
+        key = (lmax, mmax)
+        if key not in cls._cache:
+            cls._cache[key] = cls(lmax, mmax)
+        return cls._cache[key]
+
+    def dev(self, device):
+        key = str(device)
+        if key not in self._dev:
+            self._dev[key] = dict(
+                pos_of_full=torch.tensor(self.pos_of_full_host, dtype=torch.int32, device=device),
+                rad_slot=torch.tensor(self.rad_slot_host, dtype=torch.int32, device=device),
+                to_m=torch.tensor(self.to_m, dtype=torch.long, device=device),
+                jd=torch.from_numpy(_so3_math.jd_packed(self.lmax)).to(device),
+            )
+        return self._dev[key]
+
+    def conv_groups(self, c_in, c_out, extra):
+        """(a_off, k_g, c_off, n_g) of the m = 0..mmax blocks of one SO(2) convolution, operands in
+        m-primary order: A[E, Kr*c_in] -> Y[E, extra + Kr*c_out]."""
+        groups = []
+        a_off, c_off = 0, 0
+        for m, n in enumerate(self.m_sizes):
+            rows = n if m == 0 else 2 * n
+            k_g = rows * c_in
+            n_g = rows * c_out + (extra if m == 0 else 0)
+            groups.append((a_off, k_g, c_off, n_g))
+            a_off += k_g
+            c_off += n_g
+        return groups
+
+
+# ----------------------------------------------------------------------------------------------
+# edge plan: dst-sorted / src-sorted CSR over the (arbitrarily ordered) edge list
+# ----------------------------------------------------------------------------------------------
+class EdgePlan:
+    def __init__(self, edge_index, num_nodes):
+        _lib.check_device(edge_index)
+        self.E = int(edge_index.shape[1])
+        self.N = int(num_nodes)
+        self.src = edge_index[0].contiguous()
+        self.dst = edge_index[1].contiguous()
+        dev = edge_index.device
+        self.perm_dst, self.rowptr_dst = self._csr(self.dst, dev)
+        self.perm_src, self.rowptr_src = self._csr(self.src, dev)
+
+    def _csr(self, idx, dev):
+        if self.E == 0:
+            return (torch.zeros(0, dtype=torch.int32, device=dev), torch.zeros(self.N + 1, dtype=torch.int32, device=dev))
+        perm = torch.sort(idx, stable=True)[1].to(torch.int32)
+        counts = torch.bincount(idx, minlength=self.N)
+        rowptr = torch.zeros(self.N + 1, dtype=torch.int32, device=dev)
+        rowptr[1:] = torch.cumsum(counts, 0).to(torch.int32)
+        return perm.contiguous(), rowptr
+
+
+_plan_cache = {}
+
+
+def edge_plan(edge_index, num_nodes):
+    key = (edge_index.data_ptr(), tuple(edge_index.shape), edge_index._version, int(num_nodes), str(edge_index.device))
+    hit = _plan_cache.get("k")
+    if hit is not None and hit[0] == key:
+        return hit[1]
+    plan = EdgePlan(edge_index, num_nodes)
+    _plan_cache["k"] = (key, plan, edge_index)   # keep the tensor alive so data_ptr stays unique
+    return plan
+
+
+# ----------------------------------------------------------------------------------------------
+# GEMM engine
+# ----------------------------------------------------------------------------------------------
+_GEMM_MODE = {"mode": "fp32"}
+
+
+def set_gemm_mode(mode):
+    """'fp32' (exact FFMA engine, parity mode) | 'tf32x3' | 'tf32' | 'bf16' (tcgen05 engines)."""
+    assert mode in ("fp32", "tf32x3", "tf32", "bf16")
+    _GEMM_MODE["mode"] = mode
+
+
+def gemm_mode():
+    return _GEMM_MODE["mode"]
+
+
+def _desc(A, B, C, bias, M, N, K, transA, transB, a_addr, b_addr, c_addr, a_off=0, b_off=0, c_off=0, accumulate=0):
+    d = _lib.GemmDesc()
+    d.A = A.data_ptr() + 4 * a_off
+    d.B = B.data_ptr() + 4 * b_off
+    d.C = C.data_ptr() + 4 * c_off
+    d.bias = bias.data_ptr() if bias is not None else None
+    d.M, d.N, d.K = int(M), int(N), int(K)
+    d.transA, d.transB = int(transA), int(transB)
+    d.a_rpb, d.a_bs, d.a_ld = a_addr
+    d.b_rpb, d.b_bs, d.b_ld = b_addr
+    d.c_rpb, d.c_bs, d.c_ld = c_addr
+    d.accumulate = accumulate
+    return d
+
+
+_BIG = 1 << 40
+
+
+def _plain(ld):
+    return (_BIG, 0, int(ld))
+
+
+def _pick_split(descs, reduce_dim_large):
+    if not reduce_dim_large:
+        return 1
+    tiles = sum(((d.M + 127) // 128) * ((d.N + 127) // 128) for d in descs)
+    kmax = max(d.K for d in descs)
+    if tiles >= 148 or kmax < 2048:
+        return 1
+    return int(max(1, min(64, 296 // max(tiles, 1), kmax // 512)))
+
+
+def run_gemm(descs, split_k=1):
+    n = len(descs)
+    assert 1 <= n <= _lib.MAX_GEMM_GROUPS
+    arr = (_lib.GemmDesc * n)(*descs)
+    _lib.call("eqv2_gemm_f32", ctypes.cast(arr, ctypes.c_void_p), n, int(split_k), _lib.stream_ptr())
+
+
+class LinearFn(torch.autograd.Function):
+    """y = x @ W^T + b  (nn.Linear inside radial_function.py:29, transformer_block.py:420)."""
+
+    @staticmethod
+    def forward(ctx, x, W, b):
+        _lib.check_device(x, W, b)
+        x = x.contiguous()
+        W = W.contiguous()
+        M, K = x.shape
+        N = W.shape[0]
+        y = torch.empty(M, N, dtype=_F32, device=x.device)
+        run_gemm([_desc(x, W, y, b, M, N, K, 0, 1, _plain(K), _plain(K), _plain(N))])
+        ctx.save_for_backward(x, W)
+        ctx.has_bias = b is not None
+        return y
+
+    @staticmethod
+    def backward(ctx, gy):
+        x, W = ctx.saved_tensors
+        gy = gy.contiguous()
+        M, K = x.shape
+        N = W.shape[0]
+        gx = gW = gb = None
+        if ctx.needs_input_grad[0]:
+            gx = torch.empty(M, K, dtype=_F32, device=x.device)
+            run_gemm([_desc(gy, W, gx, None, M, K, N, 0, 0, _plain(N), _plain(K), _plain(K))])
+        if ctx.needs_input_grad[1]:
+            d = _desc(gy, x, x, None, N, K, M, 1, 0, _plain(N), _plain(K), _plain(K))
+            split = _pick_split([d], True)
+            gW = (torch.zeros if split > 1 else torch.empty)(N, K, dtype=_F32, device=x.device)
+            d.C = gW.data_ptr()
+            run_gemm([d], split)
+        if ctx.has_bias and ctx.needs_input_grad[2]:
+            gb = gy.sum(0)
+        return gx, gW, gb
+
+
+def linear(x, W, b=None):
+    return LinearFn.apply(x, W, b)
+
+
+class SO2ConvFn(torch.autograd.Function):
+    """All m-blocks of one SO(2) convolution as ONE grouped GEMM (so2_ops.py:150-185, :53-61).
+
+    A: [E, Kr*c_in] (m-primary, radial modulation already applied), weights[g]: [n_g, k_g]
+    (m = 0: fc_m0.weight; m > 0: the 2x2 real block form [[Wr, -Wi], [Wi, Wr]] of the complex
+    multiply), bias0: fc_m0.bias.  Y: [E, extra + Kr*c_out]."""
+
+    @staticmethod
+    def forward(ctx, A, bias0, groups, *weights):
+        _lib.check_device(A, bias0, *weights)
+        A = A.contiguous()
+        E, KA = A.shape
+        NC = sum(g[3] for g in groups)
+        Y = torch.empty(E, NC, dtype=_F32, device=A.device)
+        ws = [w.contiguous() for w in weights]
+        descs = []
+        for gi, (a_off, k_g, c_off, n_g) in enumerate(groups):
+            descs.append(_desc(A, ws[gi], Y, bias0 if gi == 0 else None, E, n_g, k_g, 0, 1,
+                               _plain(KA), _plain(k_g), _plain(NC), a_off=a_off, c_off=c_off))
+        run_gemm(descs)
+        ctx.save_for_backward(A, *ws)
+        ctx.groups = groups
+        ctx.has_bias = bias0 is not None
+        return Y
+
+    @staticmethod
+    def backward(ctx, gY):
+        A, *ws = ctx.saved_tensors
+        groups = ctx.groups
+        gY = gY.contiguous()
+        E, KA = A.shape
+        NC = gY.shape[1]
+        gA = gb = None
+        gws = [None] * len(ws)
+        if ctx.needs_input_grad[0]:
+            gA = torch.empty(E, KA, dtype=_F32, device=A.device)
+            descs = [_desc(gY, ws[gi], gA, None, E, k_g, n_g, 0, 0, _plain(NC), _plain(k_g), _plain(KA),
+                           a_off=c_off, c_off=a_off) for gi, (a_off, k_g, c_off, n_g) in enumerate(groups)]
+            run_gemm(descs)
+        if any(ctx.needs_input_grad[3:]):
+            descs = []
+            for gi, (a_off, k_g, c_off, n_g) in enumerate(groups):
+                descs.append(_desc(gY, A, A, None, n_g, k_g, E, 1, 0, _plain(NC), _plain(KA), _plain(k_g),
+                                   a_off=c_off, b_off=a_off))
+            split = _pick_split(descs, True)
+            for gi, (a_off, k_g, c_off, n_g) in enumerate(groups):
+                gws[gi] = (torch.zeros if split > 1 else torch.empty)(n_g, k_g, dtype=_F32, device=A.device)
+                descs[gi].C = gws[gi].data_ptr()
+            run_gemm(descs, split)
+        if ctx.has_bias and ctx.needs_input_grad[1]:
+            n0 = groups[0][3]
+            gb = gY[:, :n0].sum(0)
+        return (gA, gb, None, *gws)
+
+
+class SO3LinearFn(torch.autograd.Function):
+    """SO3_LinearV2 (so3.py:698-743): one GEMM per degree l over the slab x[:, l^2:(l+1)^2, :]."""
+
+    @staticmethod
+    def forward(ctx, x, W, b):
+        _lib.check_device(x, W, b)
+        x = x.contiguous()
+        W = W.contiguous()
+        N, K, Ci = x.shape
+        L1, Co, _ = W.shape
+        y = torch.empty(N, K, Co, dtype=_F32, device=x.device)
+        descs = []
+        for l in range(L1):
+            r = 2 * l + 1
+            descs.append(_desc(x, W, y, b if l == 0 else None, N * r, Co, Ci, 0, 1,
+                               (r, K * Ci, Ci), _plain(Ci), (r, K * Co, Co),
+                               a_off=l * l * Ci, b_off=l * Co * Ci, c_off=l * l * Co))
+        run_gemm(descs)
+        ctx.save_for_backward(x, W)
+        ctx.has_bias = b is not None
+        return y
+
+    @staticmethod
+    def backward(ctx, gy):
+        x, W = ctx.saved_tensors
+        gy = gy.contiguous()
+        N, K, Ci = x.shape
+        L1, Co, _ = W.shape
+        gx = gW = gb = None
+        if ctx.needs_input_grad[0]:
+            gx = torch.empty_like(x)
+            descs = []
+            for l in range(L1):
+                r = 2 * l + 1
+                descs.append(_desc(gy, W, gx, None, N * r, Ci, Co, 0, 0,
+                                   (r, K * Co, Co), _plain(Ci), (r, K * Ci, Ci),
+                                   a_off=l * l * Co, b_off=l * Co * Ci, c_off=l * l * Ci))
+            run_gemm(descs)
+        if ctx.needs_input_grad[1]:
+            descs = []
+            for l in range(L1):
+                r = 2 * l + 1
+                descs.append(_desc(gy, x, W, None, Co, Ci, N * r, 1, 0,
+                                   (r, K * Co, Co), (r, K * Ci, Ci), _plain(Ci),
+                                   a_off=l * l * Co, b_off=l * l * Ci))
+            split = _pick_split(descs, True)
+            gW = (torch.zeros if split > 1 else torch.empty)(L1, Co, Ci, dtype=_F32, device=x.device)
+            for l in range(L1):
+                descs[l].C = gW.data_ptr() + 4 * l * Co * Ci
+            run_gemm(descs, split)
+        if ctx.has_bias and ctx.needs_input_grad[2]:
+            gb = gy[:, 0, :].sum(0)
+        return gx, gW, gb
+
+
+def so3_linear(x, W, b):
+    return SO3LinearFn.apply(x, W, b)
+
+
+# ----------------------------------------------------------------------------------------------
+# Wigner-D
+# ----------------------------------------------------------------------------------------------
+def wigner_from_rot(rot, lmax):
+    """so3.py:525-545 -- block-diagonal packed [E, sum_l (2l+1)^2], no gradient (detached upstream)."""
+    _lib.check_device(rot)
+    rot = rot.detach().to(_F32).contiguous()
+    E = rot.shape[0]
+    lay = CoeffLayout.get(lmax, lmax)
+    wig = torch.empty(E, lay.WS, dtype=_F32, device=rot.device)
+    _lib.call("eqv2_wigner_from_rot", rot.data_ptr(), lay.dev(rot.device)["jd"].data_ptr(), wig.data_ptr(),
+              E, lmax, _lib.stream_ptr())
+    return wig
+
+
+def wigner_to_dense(wig, lmax):
+    """Expand the packed blocks to the reference's dense [E,K,K] layout (diagnostics / API parity)."""
+    E = wig.shape[0]
+    K = (lmax + 1) ** 2
+    out = wig.new_zeros(E, K, K)
+    off = 0
+    for l in range(lmax + 1):
+        n = 2 * l + 1
+        out[:, l * l:l * l + n, l * l:l * l + n] = wig[:, off:off + n * n].view(E, n, n)
+        off += n * n
+    return out
+
+
+class GatherRotateFn(torch.autograd.Function):
+    """x[src] | x[dst] -> Wigner rotate -> |m|<=mmax rows, m-primary -> * radial weights.
+    (transformer_block.py:250-275, so3.py:343-360, so3.py:322-334, so2_ops.py:150-175)"""
+
+    @staticmethod
+    def forward(ctx, x, rad, plan, wig, lmax, mmax):
+        _lib.check_device(x, rad, wig)
+        x = x.contiguous()
+        rad = rad.contiguous() if rad is not None else None
+        lay = CoeffLayout.get(lmax, mmax)
+        tabs = lay.dev(x.device)
+        N, K, C = x.shape
+        nrad = lay.nslot * 2 * C
+        if rad is not None:
+            assert rad.shape == (plan.E, nrad), (rad.shape, plan.E, nrad)
+        out = torch.empty(plan.E, lay.Kr * 2 * C, dtype=_F32, device=x.device)
+        _lib.call("eqv2_gather_rotate_fwd", x.data_ptr(), plan.src.data_ptr(), plan.dst.data_ptr(), wig.data_ptr(),
+                  _lib.ptr(rad), out.data_ptr(), tabs["pos_of_full"].data_ptr(), tabs["rad_slot"].data_ptr(),
+                  plan.E, C, lmax, mmax, lay.Kr, nrad, _lib.stream_ptr())
+        ctx.save_for_backward(x, rad, wig)
+        ctx.plan, ctx.lm = plan, (lmax, mmax)
+        return out
+
+    @staticmethod
+    def backward(ctx, gA):
+        x, rad, wig = ctx.saved_tensors
+        plan = ctx.plan
+        lmax, mmax = ctx.lm
+        lay = CoeffLayout.get(lmax, mmax)
+        tabs = lay.dev(x.device)
+        N, K, C = x.shape
+        nrad = lay.nslot * 2 * C
+        gA = gA.contiguous()
+        gx = torch.empty_like(x)
+        grad = torch.empty(plan.E, nrad, dtype=_F32, device=x.device) if rad is not None else None
+        _lib.call("eqv2_gather_rotate_bwd", x.data_ptr(), wig.data_ptr(), _lib.ptr(rad), gA.data_ptr(),
+                  plan.rowptr_src.data_ptr(), plan.perm_src.data_ptr(), plan.rowptr_dst.data_ptr(),
+                  plan.perm_dst.data_ptr(), gx.data_ptr(), _lib.ptr(grad), tabs["pos_of_full"].data_ptr(),
+                  tabs["rad_slot"].data_ptr(), N, C, lmax, mmax, lay.Kr, nrad, _lib.stream_ptr())
+        return gx, grad, None, None, None, None
+
+
+class RotInvReduceFn(torch.autograd.Function):
+    """(value * alpha) -> Wigner^T with l>mmax rescale -> deterministic dst-segmented sum.
+    (transformer_block.py:321-331, so3.py:367-387,516-521, so3.py:304-318; input_block.py:113-129)"""
+
+    @staticmethod
+    def forward(ctx, val, alpha, plan, wig, lmax, mmax, rows_used, heads, scale):
+        _lib.check_device(val, alpha, wig)
+        val = val.contiguous()
+        alpha = alpha.contiguous() if alpha is not None else None
+        lay = CoeffLayout.get(lmax, mmax)
+        tabs = lay.dev(val.device)
+        E = plan.E
+        Cv = val.shape[1] // rows_used
+        out = torch.empty(plan.N, lay.K, Cv, dtype=_F32, device=val.device)
+        _lib.call("eqv2_rotinv_reduce_fwd", val.data_ptr(), _lib.ptr(alpha), wig.data_ptr(),
+                  plan.rowptr_dst.data_ptr(), plan.perm_dst.data_ptr(), out.data_ptr(),
+                  tabs["pos_of_full"].data_ptr(), plan.N, Cv, rows_used, rows_used * Cv, heads, lmax, mmax,
+                  float(scale), _lib.stream_ptr())
+        ctx.save_for_backward(val, alpha, wig)
+        ctx.plan, ctx.meta = plan, (lmax, mmax, rows_used, heads, float(scale), Cv)
+        return out
+
+    @staticmethod
+    def backward(ctx, gout):
+        val, alpha, wig = ctx.saved_tensors
+        plan = ctx.plan
+        lmax, mmax, rows_used, heads, scale, Cv = ctx.meta
+        lay = CoeffLayout.get(lmax, mmax)
+        tabs = lay.dev(val.device)
+        gout = gout.contiguous()
+        gval = torch.empty_like(val)
+        galpha = torch.empty_like(alpha) if alpha is not None else None
+        _lib.call("eqv2_rotinv_reduce_bwd", gout.data_ptr(), val.data_ptr(), _lib.ptr(alpha), wig.data_ptr(),
+                  plan.dst.data_ptr(), gval.data_ptr(), _lib.ptr(galpha), tabs["pos_of_full"].data_ptr(),
+                  plan.E, Cv, rows_used, rows_used * Cv, heads, lmax, mmax, scale, _lib.stream_ptr())
+        return gval, galpha, None, None, None, None, None, None, None
+
+
+# ----------------------------------------------------------------------------------------------
+# S2 activation + attention weights
+# ----------------------------------------------------------------------------------------------
+class GridMats:
+    """Padded [G, KP] to/from-grid matrices in a given coefficient order (so3.py:584-622)."""
+
+    def __init__(self, T, Fm, Kr, KP, G):
+        self.T, self.F, self.Kr, self.KP, self.G = T, Fm, Kr, KP, G
+
+    @classmethod
+    def from_buffers(cls, to_grid, from_grid, lmax, mmax, order):
+        """to_grid / from_grid: [res_beta, res_alpha, Kr] buffers of SO3_Grid (l-primary reduced)."""
+        Kr = to_grid.shape[-1]
+        G = to_grid.shape[0] * to_grid.shape[1]
+        tg = to_grid.reshape(G, Kr).to(_F32)
+        fg = from_grid.reshape(G, Kr).to(_F32)
+        if order == "m":
+            perm = torch.tensor(CoeffLayout.get(lmax, mmax).to_m, dtype=torch.long, device=tg.device)
+            tg, fg = tg[:, perm], fg[:, perm]
+        KP = _lib.lib().eqv2_s2act_padded_rows(Kr)
+        if KP < 0:
+            raise _lib.Eqv2Error(f"S2 activation: {Kr} coefficients unsupported")
+        T = torch.zeros(G, KP, dtype=_F32, device=tg.device)
+        Fm = torch.zeros(G, KP, dtype=_F32, device=tg.device)
+        T[:, :Kr], Fm[:, :Kr] = tg, fg
+        return cls(T.contiguous(), Fm.contiguous(), Kr, KP, G)
+
+
+def _s2_blocks(R, C):
+    work = R * ((C + 63) // 64)
+    return int(max(1, min(work, 148 * 2)))
+
+
+class S2ActFn(torch.autograd.Function):
+    """SeparableS2Activation on a node tensor (transformer_block.py:442-447, activation.py:173-192):
+    x [N,K,C] (l-primary), gate [N,C] -> [N,K,C]."""
+
+    @staticmethod
+    def forward(ctx, x, gate, mats):
+        _lib.check_device(x, gate)
+        x = x.contiguous()
+        gate = gate.contiguous() if gate is not None else None
+        R, Kr, C = x.shape
+        assert Kr == mats.Kr
+        out = torch.empty_like(x)
+        _lib.call("eqv2_s2act_fwd", x.data_ptr(), Kr * C, _lib.ptr(gate), C, out.data_ptr(), Kr * C,
+                  mats.T.data_ptr(), mats.F.data_ptr(), R, C, Kr, mats.KP, mats.G, _s2_blocks(R, C),
+                  _lib.stream_ptr())
+        ctx.save_for_backward(x, gate)
+        ctx.mats = mats
+        return out
+
+    @staticmethod
+    def backward(ctx, go):
+        x, gate = ctx.saved_tensors
+        mats = ctx.mats
+        go = go.contiguous()
+        R, Kr, C = x.shape
+        gx = torch.empty_like(x)
+        gg = torch.empty_like(gate) if gate is not None else None
+        _lib.call("eqv2_s2act_bwd", x.data_ptr(), Kr * C, _lib.ptr(gate), C, go.data_ptr(), Kr * C, gx.data_ptr(),
+                  Kr * C, _lib.ptr(gg), C, mats.T.data_ptr(), mats.F.data_ptr(), R, C, Kr, mats.KP, mats.G,
+                  _s2_blocks(R, C), _lib.stream_ptr())
+        return gx, gg, None
+
+
+class EdgeActAlphaFn(torch.autograd.Function):
+    """Consumes the first SO(2) convolution's output Y[E, heads*ach + H + Kr*H] and produces
+      * Z[E, Kr*H]   = SeparableS2Activation(gate = Y[:, heads*ach : heads*ach+H], Y[:, extra:])
+      * alpha[E, heads] = segment_softmax_dst( alpha_dot . SmoothLeakyReLU(LayerNorm(Y[:, :heads*ach])) )
+    (transformer_block.py:289-315).  One backward fills one dY buffer -- no zero-fill, no adds."""
+
+    @staticmethod
+    def forward(ctx, Y, ln_w, ln_b, alpha_dot, plan, mats, heads, ach, H):
+        _lib.check_device(Y, ln_w, ln_b, alpha_dot)
+        Y = Y.contiguous()
+        E, W = Y.shape
+        extra = heads * ach + H
+        Kr = mats.Kr
+        assert W == extra + Kr * H
+        Z = torch.empty(E, Kr * H, dtype=_F32, device=Y.device)
+        yp = Y.data_ptr()
+        _lib.call("eqv2_s2act_fwd", yp + 4 * extra, W, yp + 4 * heads * ach, W, Z.data_ptr(), Kr * H,
+                  mats.T.data_ptr(), mats.F.data_ptr(), E, H, Kr, mats.KP, mats.G, _s2_blocks(E, H),
+                  _lib.stream_ptr())
+        logits = torch.empty(E, heads, dtype=_F32, device=Y.device)
+        alpha = torch.empty(E, heads, dtype=_F32, device=Y.device)
+        ln_w_c = ln_w.contiguous() if ln_w is not None else None
+        ln_b_c = ln_b.contiguous() if ln_b is not None else None
+        alpha_dot = alpha_dot.contiguous()
+        _lib.call("eqv2_attn_alpha_fwd", yp, W, _lib.ptr(ln_w_c), _lib.ptr(ln_b_c), alpha_dot.data_ptr(),
+                  plan.rowptr_dst.data_ptr(), plan.perm_dst.data_ptr(), logits.data_ptr(), alpha.data_ptr(),
+                  E, plan.N, heads, ach, 1e-5, _lib.stream_ptr(), n_kernels=2)
+        ctx.save_for_backward(Y, ln_w_c, ln_b_c, alpha_dot, alpha)
+        ctx.plan, ctx.mats, ctx.meta = plan, mats, (heads, ach, H)
+        return Z, alpha
+
+    @staticmethod
+    def backward(ctx, gZ, galpha):
+        Y, ln_w, ln_b, alpha_dot, alpha = ctx.saved_tensors
+        plan, mats = ctx.plan, ctx.mats
+        heads, ach, H = ctx.meta
+        E, W = Y.shape
+        extra = heads * ach + H
+        Kr = mats.Kr
+        dev = Y.device
+        gY = torch.empty_like(Y)
+        yp, gp = Y.data_ptr(), gY.data_ptr()
+        if gZ is None:
+            gZ = torch.zeros(E, Kr * H, dtype=_F32, device=dev)
+        gZ = gZ.contiguous()
+        _lib.call("eqv2_s2act_bwd", yp + 4 * extra, W, yp + 4 * heads * ach, W, gZ.data_ptr(), Kr * H,
+                  gp + 4 * extra, W, gp + 4 * heads * ach, W, mats.T.data_ptr(), mats.F.data_ptr(), E, H, Kr,
+                  mats.KP, mats.G, _s2_blocks(E, H), _lib.stream_ptr())
+        if galpha is None:
+            galpha = torch.zeros_like(alpha)
+        galpha = galpha.contiguous()
+        g_lnw = torch.zeros_like(ln_w) if ln_w is not None else None
+        g_lnb = torch.zeros_like(ln_b) if ln_b is not None else None
+        g_dot = torch.zeros_like(alpha_dot)
+        dlogits = torch.empty_like(alpha)
+        _lib.call("eqv2_attn_alpha_bwd", yp, W, _lib.ptr(ln_w), _lib.ptr(ln_b), alpha_dot.data_ptr(),
+                  plan.rowptr_dst.data_ptr(), plan.perm_dst.data_ptr(), alpha.data_ptr(), galpha.data_ptr(),
+                  dlogits.data_ptr(), gp, W, _lib.ptr(g_lnw), _lib.ptr(g_lnb), g_dot.data_ptr(), E, plan.N, heads,
+                  ach, 1e-5, _lib.stream_ptr(), n_kernels=2)
+        return gY, g_lnw, g_lnb, g_dot, None, None, None, None, None
+
+
+# ----------------------------------------------------------------------------------------------
+# equivariant norms, LN+SiLU, RBF
+# ----------------------------------------------------------------------------------------------
+def norm_groups(norm_type, lmax):
+    """(ngroups, group_of_l, bw_l) for layer_norm.py:38-108 / :112-201 / :265-351."""
+    if norm_type == "rms_norm_sh":
+        return 1, [0] * (lmax + 1), [1.0 / ((2 * l + 1) * (lmax + 1)) for l in range(lmax + 1)]
+    if norm_type == "layer_norm_sh":
+        return (2 if lmax > 0 else 1), [0] + [1] * lmax, [1.0] + [1.0 / ((2 * l + 1) * lmax) for l in range(1, lmax + 1)]
+    if norm_type == "layer_norm":
+        return lmax + 1, list(range(lmax + 1)), [1.0 / (2 * l + 1) for l in range(lmax + 1)]
+    raise ValueError(norm_type)
+
+
+class EquivNormFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, w, b, norm_type, lmax, eps):
+        _lib.check_device(x, w, b)
+        x = x.contiguous()
+        w = w.contiguous()
+        b = b.contiguous()
+        N, K, C = x.shape
+        ng, gol, bw = norm_groups(norm_type, lmax)
+        gol_c = (ctypes.c_int * len(gol))(*gol)
+        bw_c = (ctypes.c_float * len(bw))(*bw)
+        out = torch.empty_like(x)
+        inv = torch.empty(N, ng, dtype=_F32, device=x.device)
+        mean = torch.empty(N, dtype=_F32, device=x.device)
+        _lib.call("eqv2_equiv_norm_fwd", x.data_ptr(), w.data_ptr(), b.data_ptr(), out.data_ptr(), inv.data_ptr(),
+                  mean.data_ptr(), N, C, lmax, ng, ctypes.cast(gol_c, ctypes.c_void_p),
+                  ctypes.cast(bw_c, ctypes.c_void_p), float(eps), _lib.stream_ptr())
+        ctx.save_for_backward(x, w, inv, mean)
+        ctx.meta = (norm_type, lmax)
+        return out
+
+    @staticmethod
+    def backward(ctx, go):
+        x, w, inv, mean = ctx.saved_tensors
+        norm_type, lmax = ctx.meta
+        N, K, C = x.shape
+        ng, gol, bw = norm_groups(norm_type, lmax)
+        gol_c = (ctypes.c_int * len(gol))(*gol)
+        bw_c = (ctypes.c_float * len(bw))(*bw)
+        go = go.contiguous()
+        gx = torch.empty_like(x)
+        gw = torch.zeros_like(w)
+        gb = torch.zeros(C, dtype=_F32, device=x.device)
+        _lib.call("eqv2_equiv_norm_bwd", x.data_ptr(), w.data_ptr(), go.data_ptr(), inv.data_ptr(), mean.data_ptr(),
+                  gx.data_ptr(), gw.data_ptr(), gb.data_ptr(), N, C, lmax, ng, ctypes.cast(gol_c, ctypes.c_void_p),
+                  ctypes.cast(bw_c, ctypes.c_void_p), _lib.stream_ptr())
+        return gx, gw, gb, None, None, None
+
+
+class LnSiluFn(torch.autograd.Function):
+    """SiLU(LayerNorm(x)) of the radial MLP (radial_function.py:21-22)."""
+
+    @staticmethod
+    def forward(ctx, x, w, b, eps):
+        _lib.check_device(x, w, b)
+        x = x.contiguous()
+        w = w.contiguous()
+        b = b.contiguous()
+        rows, width = x.shape
+        y = torch.empty_like(x)
+        _lib.call("eqv2_ln_silu_fwd", x.data_ptr(), w.data_ptr(), b.data_ptr(), y.data_ptr(), rows, width, float(eps),
+                  _lib.stream_ptr())
+        ctx.save_for_backward(x, w, b)
+        ctx.eps = float(eps)
+        return y
+
+    @staticmethod
+    def backward(ctx, gy):
+        x, w, b = ctx.saved_tensors
+        rows, width = x.shape
+        gy = gy.contiguous()
+        gx = torch.empty_like(x)
+        gw = torch.zeros_like(w)
+        gb = torch.zeros_like(b)
+        _lib.call("eqv2_ln_silu_bwd", x.data_ptr(), w.data_ptr(), b.data_ptr(), gy.data_ptr(), gx.data_ptr(),
+                  gw.data_ptr(), gb.data_ptr(), rows, width, ctx.eps, _lib.stream_ptr())
+        return gx, gw, gb, None
+
+
+class RbfFn(torch.autograd.Function):
+    """GaussianSmearing (equiformerv2_oc20.py:43-60): exp(coeff * (d - offset_k)^2)."""
+
+    @staticmethod
+    def forward(ctx, d, offset, coeff):
+        _lib.check_device(d, offset)
+        d = d.contiguous().view(-1)
+        offset = offset.contiguous()
+        R = offset.shape[0]
+        out = torch.empty(d.shape[0], R, dtype=_F32, device=d.device)
+        _lib.call("eqv2_rbf_fwd", d.data_ptr(), out.data_ptr(), d.shape[0], R, offset.data_ptr(), float(coeff),
+                  _lib.stream_ptr())
+        ctx.save_for_backward(d, offset)
+        ctx.coeff = float(coeff)
+        return out
+
+    @staticmethod
+    def backward(ctx, go):
+        d, offset = ctx.saved_tensors
+        go = go.contiguous()
+        gd = torch.empty_like(d)
+        _lib.call("eqv2_rbf_bwd", d.data_ptr(), go.data_ptr(), gd.data_ptr(), d.shape[0], offset.shape[0],
+                  offset.data_ptr(), ctx.coeff, _lib.stream_ptr())
+        return gd, None, None

@@ -1,0 +1,118 @@
+/*
+ * eqv2_b200.h -- C ABI of libeqv2_b200.so: hand-written sm_100a kernels for the
+ * EquiformerV2 SO(2)-equivariant graph-attention block.
+ *
+ * The reference (johannebirkchristensen/EquivariantTransformerMPNN4QuantumComputations) has
+ * no FFI: its hot path is the Python package models/EquiformerV2Functions.  Each
+ * entry point below replaces the eager-PyTorch op sequence of the cited reference lines and
+ * is what a binding for that path would call.  Conventions:
+ *   - plain pointers to DEVICE memory, fp32 values, int64 node indices (as the reference),
+ *     int32 CSR tables; sizes as int / long long; `stream` is a cudaStream_t;
+ *   - no allocation inside: the caller passes outputs and workspaces;
+ *   - return 0 on success, non-zero otherwise with a thread-local message from
+ *     eqv2_last_error(); launches are asynchronous on `stream`.
+ */
+#ifndef EQV2_B200_H
+#define EQV2_B200_H
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+const char* eqv2_last_error(void);
+int eqv2_abi_version(void);
+
+/* ---- grouped GEMM engine ---------------------------------------------------------------
+ * C[i,j] (+)= sum_k opA(i,k) opB(k,j) (+ bias[j]);  row r of an operand lives at
+ * (r / rpb) * bs + (r % rpb) * ld  (two-level stride: degree-l slabs of [N,K,C] tensors).
+ * Replaces: F.linear in so2_ops.py:150-185 (SO2 convolution blocks), radial_function.py:29,
+ * the einsum of so3.py:722-727 (SO3_LinearV2) and their autograd backward. */
+#define EQV2_GEMM_MAX_GROUPS 10
+typedef struct {
+  const float* A;
+  const float* B;
+  float* C;
+  const float* bias; /* may be NULL */
+  int M, N, K;
+  int transA, transB;
+  long long a_rpb, a_bs, a_ld;
+  long long b_rpb, b_bs, b_ld;
+  long long c_rpb, c_bs, c_ld;
+  int accumulate; /* C += (ignored when split_k > 1: C must then be pre-initialised) */
+} eqv2_gemm_desc;
+
+/* exact fp32 (FFMA) engine */
+int eqv2_gemm_f32(const eqv2_gemm_desc* descs, int ngroups, int split_k, void* stream);
+
+/* ---- Wigner-D rotation (so3.py:343-387,499-545; transformer_block.py:250-275,321-331) ---- */
+int eqv2_wigner_from_rot(const float* rot /*[E,3,3]*/, const float* Jd /*packed blocks*/,
+                         float* wig /*[E, sum (2l+1)^2]*/, long long E, int lmax, void* stream);
+
+int eqv2_gather_rotate_fwd(const float* x /*[N,K,C]*/, const long long* src, const long long* dst,
+                           const float* wig, const float* rad /*[E,nrad] or NULL*/,
+                           float* out /*[E,Kr,2C] m-primary*/, const int* pos_of_full /*[K]*/,
+                           const int* rad_slot /*[Kr]*/, long long E, int C, int lmax, int mmax, int Kr,
+                           int nrad, void* stream);
+
+int eqv2_gather_rotate_bwd(const float* x, const float* wig, const float* rad, const float* dA /*[E,Kr,2C]*/,
+                           const int* rowptr_src, const int* perm_src, const int* rowptr_dst,
+                           const int* perm_dst, float* dx /*[N,K,C]*/, float* drad /*[E,nrad] or NULL*/,
+                           const int* pos_of_full, const int* rad_slot, long long N, int C, int lmax, int mmax,
+                           int Kr, int nrad, void* stream);
+
+int eqv2_rotinv_reduce_fwd(const float* val /*[E,rows,Cv]*/, const float* alpha /*[E,heads] or NULL*/,
+                           const float* wig, const int* rowptr_dst, const int* perm_dst,
+                           float* out /*[N,K,Cv]*/, const int* pos_of_full, long long N, int Cv, int rows_used,
+                           long long val_estride, int heads, int lmax, int mmax, float scale, void* stream);
+
+int eqv2_rotinv_reduce_bwd(const float* dout /*[N,K,Cv]*/, const float* val, const float* alpha,
+                           const float* wig, const long long* dst, float* dval, float* dalpha /*or NULL*/,
+                           const int* pos_of_full, long long E, int Cv, int rows_used, long long val_estride,
+                           int heads, int lmax, int mmax, float scale, void* stream);
+
+/* ---- separable S2 activation (activation.py:153-192, so3.py:552-646) --------------------- */
+int eqv2_s2act_padded_rows(int Kr);
+int eqv2_s2act_fwd(const float* X, long long x_rs, const float* gate /*or NULL*/, long long g_rs, float* O,
+                   long long o_rs, const float* to_grid /*[G,KP]*/, const float* from_grid /*[G,KP]*/,
+                   long long R, int C, int Kr, int KP, int G, int nblocks, void* stream);
+int eqv2_s2act_bwd(const float* X, long long x_rs, const float* gate, long long g_rs, const float* dO,
+                   long long o_rs, float* dX, long long dx_rs, float* dgate, long long dg_rs,
+                   const float* to_grid, const float* from_grid, long long R, int C, int Kr, int KP, int G,
+                   int nblocks, void* stream);
+
+/* ---- attention logits + segment softmax (transformer_block.py:311-315) ------------------- */
+int eqv2_attn_alpha_fwd(const float* Y, long long y_rs, const float* ln_w /*or NULL*/, const float* ln_b,
+                        const float* alpha_dot /*[heads,ach]*/, const int* rowptr_dst, const int* perm_dst,
+                        float* logits /*[E,heads]*/, float* alpha /*[E,heads]*/, long long E, long long N,
+                        int heads, int ach, float eps, void* stream);
+int eqv2_attn_alpha_bwd(const float* Y, long long y_rs, const float* ln_w, const float* ln_b,
+                        const float* alpha_dot, const int* rowptr_dst, const int* perm_dst, const float* alpha,
+                        const float* dalpha, float* dlogits, float* dY, long long dy_rs,
+                        float* d_ln_w /*zeroed*/, float* d_ln_b /*zeroed*/, float* d_alpha_dot /*zeroed*/,
+                        long long E, long long N, int heads, int ach, float eps, void* stream);
+
+/* ---- equivariant norms (layer_norm.py:38-108,112-201,265-351) ---------------------------- */
+int eqv2_equiv_norm_fwd(const float* x /*[N,K,C]*/, const float* w /*[lmax+1,C]*/, const float* b /*[C]*/,
+                        float* out, float* inv_out /*[N,ngroups]*/, float* mean_out /*[N]*/, long long N, int C,
+                        int lmax, int ngroups, const int* group_of_l /*host*/, const float* bw_l /*host*/,
+                        float eps, void* stream);
+int eqv2_equiv_norm_bwd(const float* x, const float* w, const float* go, const float* inv_in,
+                        const float* mean_in, float* dx, float* dw /*zeroed*/, float* db /*zeroed*/,
+                        long long N, int C, int lmax, int ngroups, const int* group_of_l /*host*/,
+                        const float* bw_l /*host*/, void* stream);
+
+/* ---- edge scalar features (equiformerv2_oc20.py:43-60, radial_function.py:21-22) --------- */
+int eqv2_rbf_fwd(const float* d, float* out /*[E,R]*/, long long E, int R, const float* offset /*[R]*/, float coeff,
+                 void* stream);
+int eqv2_rbf_bwd(const float* d, const float* go, float* dd, long long E, int R, const float* offset, float coeff,
+                 void* stream);
+int eqv2_ln_silu_fwd(const float* x, const float* w, const float* b, float* y, long long rows, int width,
+                     float eps, void* stream);
+int eqv2_ln_silu_bwd(const float* x, const float* w, const float* b, const float* gy, float* gx,
+                     float* gw /*zeroed*/, float* gb /*zeroed*/, long long rows, int width, float eps,
+                     void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* EQV2_B200_H */
