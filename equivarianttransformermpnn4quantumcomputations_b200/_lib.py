@@ -1,9 +1,7 @@
 """ctypes binding of libeqv2_b200.so (C ABI declared in include/eqv2_b200.h).
 
-There is NO fallback: if the CUDA library is missing the package raises on first use.
-`use_library_for_testing()` exists only so the CPU test-suite can point the same Python
-host code at tests/emu/libeqv2_emu.so (the kernel *source* executed by a CPU emulator) --
-it is never selected automatically.
+There is NO fallback: if the CUDA library is missing the package raises on first use, and
+every operator refuses tensors that do not live on a CUDA device.
 """
 import ctypes
 import os
@@ -17,6 +15,7 @@ P = ctypes.c_void_p
 I = ctypes.c_int
 L = ctypes.c_longlong
 F = ctypes.c_float
+D = ctypes.c_double
 
 
 class GemmDesc(ctypes.Structure):
@@ -51,11 +50,19 @@ _PROTOS = {
     "eqv2_rbf_bwd": [P, P, P, L, I, P, F, P],
     "eqv2_ln_silu_fwd": [P, P, P, P, L, I, F, P],
     "eqv2_ln_silu_bwd": [P, P, P, P, P, P, P, L, I, F, P],
+    "eqv2_graph_ptr": [P, P, I, P],
+    "eqv2_exclusive_scan": [P, P, I, P],
+    "eqv2_radius_graph": [P, P, P, L, F, I, I, P, P, P, P, P, P, P, P],
+    "eqv2_pbc_reps": [P, D, P, I, P],
+    "eqv2_radius_graph_pbc": [P, P, P, P, P, L, D, I, I, I, P, P, P, P, P, P, P, P],
+    "eqv2_csr_from_index": [P, L, L, P, P, P, P, P],
+    "eqv2_segment_sum_fwd": [P, L, P, P, L, I, P],
+    "eqv2_segment_sum_bwd": [P, P, P, L, P],
 }
 # entry points that only exist in the real (nvcc-built) library
 _OPTIONAL = set()
 
-_state = {"lib": None, "emu": False, "launches": 0}
+_state = {"lib": None, "launches": 0}
 
 
 class Eqv2Error(RuntimeError):
@@ -84,18 +91,7 @@ def lib():
                 f"{LIB_PATH} is missing: build it with `python -m equivarianttransformermpnn4quantumcomputations_b200.build` "
                 "(nvcc, sm_100a). There is no CPU / PyTorch fallback for this package.")
         _state["lib"] = _bind(LIB_PATH)
-        _state["emu"] = False
     return _state["lib"]
-
-
-def use_library_for_testing(path):
-    """TEST HOOK: bind an alternative build of the same C ABI (the CPU emulator build)."""
-    _state["lib"] = _bind(path) if path is not None else None
-    _state["emu"] = path is not None
-
-
-def is_emulated():
-    return _state["emu"]
 
 
 def launch_count():
@@ -107,14 +103,9 @@ def reset_launch_count():
 
 
 def check_device(*tensors):
-    """Product path: every tensor must live on a CUDA device (emulator hook: on CPU)."""
+    """Every tensor handed to a kernel must live on a CUDA device."""
     for t in tensors:
-        if t is None:
-            continue
-        if _state["emu"]:
-            if t.is_cuda:
-                raise Eqv2Error("emulated library bound but tensor is on CUDA")
-        elif not t.is_cuda:
+        if t is not None and not t.is_cuda:
             raise Eqv2Error("eqv2_b200 kernels need CUDA tensors; there is no CPU fallback")
 
 
@@ -124,9 +115,7 @@ def ptr(t):
     return t.data_ptr()
 
 
-def stream_ptr(ref=None):
-    if _state["emu"]:
-        return None
+def stream_ptr():
     return torch.cuda.current_stream().cuda_stream
 
 

@@ -1,0 +1,446 @@
+// Neighbour-list builders and per-graph reductions.
+//
+//  radius graph, isolated molecules (equiformerv2_qm9.py:423-525):
+//      candidates 0 < |p_j - p_i| < r_c inside one molecule (fp32, same operation order as
+//      torch.norm of the difference), per destination keep the `max_nb` nearest (ties by index).
+//  radius graph, periodic (fairchem generate_graph as called at equiformerv2_oc20.py:223-234; the
+//      semantics follow oracle/eqv2_oracle.py::radius_graph_pbc_fairchem -- UNPINNED upstream):
+//      fp64 image search over ceil(r_c / h_k) repeats per lattice direction, 1e-4 < d < r_c, per centre
+//      keep d <= d_(max_nb) + 0.01 (non-strict) or exactly the max_nb nearest (strict).
+//
+// Both builders are count -> exclusive scan -> fill, one CTA per destination atom, and emit the edges
+// SORTED BY DESTINATION (within a destination by source index, then image index).  The dst-CSR that
+// the segment softmax / segmented reduce kernels need is therefore the builder's own `rowptr`, for free.
+// The total edge count is the last element of rowptr (the only host read-back of a forward pass).
+//
+//  segment_sum: per-graph sum of per-atom scalars over a non-decreasing `batch` vector (readout
+//      reductions, equiformerv2_oc20.py:278-281, equiformerv2_qm9.py:679-684), deterministic.
+#include "common.cuh"
+
+namespace {
+
+constexpr int NB_THREADS = 128;
+constexpr int NB_CAP = 4096;   // candidates per destination held in shared memory (isolated molecules)
+constexpr int PBC_CAP = 2048;  // same, periodic builder (fp64 distances)
+
+__device__ __forceinline__ float dist_f32(float dx, float dy, float dz) {
+  // (dx*dx + dy*dy) + dz*dz without FMA contraction, then IEEE sqrt
+  const float s = __fadd_rn(__fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy)), __fmul_rn(dz, dz));
+  return __fsqrt_rn(s);
+}
+
+// ---------------------------------------------------------------------------------------------
+// Isolated molecules.  mode 0: write deg[i];  mode 1: write edges at rowptr[i].
+__global__ void __launch_bounds__(NB_THREADS)
+radius_graph_kernel(const float* __restrict__ pos, const int* __restrict__ graph_ptr,
+                    const long long* __restrict__ batch, float cutoff, int max_nb, int mode,
+                    int* __restrict__ deg, const int* __restrict__ rowptr, long long* __restrict__ src_out,
+                    long long* __restrict__ dst_out, float* __restrict__ dist_out, float* __restrict__ vec_out,
+                    int* __restrict__ err) {
+  __shared__ float sd[NB_CAP];
+  __shared__ int sj[NB_CAP];
+  __shared__ int scnt;
+  __shared__ int scratch[NB_THREADS / 32];
+  const int i = blockIdx.x;
+  const int g = (int)batch[i];
+  const int beg = graph_ptr[g], end = graph_ptr[g + 1];
+  const float xi = pos[3 * i], yi = pos[3 * i + 1], zi = pos[3 * i + 2];
+  if (threadIdx.x == 0) scnt = 0;
+  __syncthreads();
+  // candidate list in ascending j: chunked so that smem order == j order
+  for (int base = beg; base < end; base += NB_THREADS) {
+    const int j = base + threadIdx.x;
+    float d = 0.f;
+    bool ok = false;
+    if (j < end) {
+      d = dist_f32(xi - pos[3 * j], yi - pos[3 * j + 1], zi - pos[3 * j + 2]);
+      ok = (d < cutoff) && (d > 0.f);
+    }
+    // ordered compaction inside the chunk
+    const unsigned bal = __ballot_sync(0xffffffffu, ok);
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    __syncthreads();
+    if (lane == 0) scratch[warp] = __popc(bal);
+    __syncthreads();
+    int off = scnt;
+    for (int w = 0; w < warp; ++w) off += scratch[w];
+    off += __popc(bal & ((1u << lane) - 1u));
+    if (ok) {
+      if (off < NB_CAP) { sd[off] = d; sj[off] = j; }
+      else atomicExch(err, 1);
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      int t = 0;
+      for (int w = 0; w < NB_THREADS / 32; ++w) t += scratch[w];
+      scnt += t;
+    }
+    __syncthreads();
+  }
+  const int cnt = min(scnt, NB_CAP);
+  const bool trunc = (max_nb >= 0) && (cnt > max_nb);
+  if (mode == 0) {
+    if (threadIdx.x == 0) deg[i] = trunc ? max_nb : cnt;
+    return;
+  }
+  // CTA i is the DESTINATION; its candidates j are the sources (edge_vec = p[dst] - p[src]).
+  // keep candidate c iff rank(d_c, c) < max_nb; ordered compaction keeps ascending source order.
+  const int out0 = rowptr[i];
+  int written = 0;
+  for (int base = 0; base < cnt; base += NB_THREADS) {
+    const int c = base + threadIdx.x;
+    bool keep = false;
+    if (c < cnt) {
+      keep = true;
+      if (trunc) {
+        int rank = 0;
+        const float dc = sd[c];
+        for (int k = 0; k < cnt; ++k) rank += (sd[k] < dc) || (sd[k] == dc && k < c);
+        keep = rank < max_nb;
+      }
+    }
+    const unsigned bal = __ballot_sync(0xffffffffu, keep);
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    __syncthreads();
+    if (lane == 0) scratch[warp] = __popc(bal);
+    __syncthreads();
+    int off = written;
+    for (int w = 0; w < warp; ++w) off += scratch[w];
+    off += __popc(bal & ((1u << lane) - 1u));
+    int chunk = 0;
+    for (int w = 0; w < NB_THREADS / 32; ++w) chunk += scratch[w];
+    if (keep) {
+      const int o = out0 + off;
+      const int j = sj[c];
+      src_out[o] = j;
+      dst_out[o] = i;
+      dist_out[o] = sd[c];
+      vec_out[3 * o] = xi - pos[3 * j];
+      vec_out[3 * o + 1] = yi - pos[3 * j + 1];
+      vec_out[3 * o + 2] = zi - pos[3 * j + 2];
+    }
+    written += chunk;
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// Periodic.  One CTA per centre atom i; candidates (j, image s) in (j, s) order.
+__global__ void __launch_bounds__(NB_THREADS)
+radius_graph_pbc_kernel(const float* __restrict__ pos, const float* __restrict__ cell,
+                        const int* __restrict__ graph_ptr, const long long* __restrict__ batch,
+                        const int* __restrict__ reps /*[B,3]*/, double cutoff, int max_nb, int strict, int mode,
+                        int* __restrict__ deg, const int* __restrict__ rowptr, long long* __restrict__ nbr_out,
+                        long long* __restrict__ ctr_out, float* __restrict__ dist_out, float* __restrict__ vec_out,
+                        int* __restrict__ err) {
+  __shared__ double sd[PBC_CAP];
+  __shared__ int sj[PBC_CAP];
+  __shared__ int ss[PBC_CAP];
+  __shared__ int scnt;
+  __shared__ int scratch[NB_THREADS / 32];
+  __shared__ double sthr;
+  const int i = blockIdx.x;
+  const int g = (int)batch[i];
+  const int beg = graph_ptr[g], end = graph_ptr[g + 1];
+  double c[9];
+#pragma unroll
+  for (int k = 0; k < 9; ++k) c[k] = (double)cell[9 * g + k];
+  const int r0 = reps[3 * g], r1 = reps[3 * g + 1], r2 = reps[3 * g + 2];
+  const int n1 = 2 * r1 + 1, n2 = 2 * r2 + 1;
+  const int nimg = (2 * r0 + 1) * n1 * n2;
+  const double xi = pos[3 * i], yi = pos[3 * i + 1], zi = pos[3 * i + 2];
+  if (threadIdx.x == 0) scnt = 0;
+  __syncthreads();
+  const long long total = (long long)(end - beg) * nimg;
+  for (long long base = 0; base < total; base += NB_THREADS) {
+    const long long t = base + threadIdx.x;
+    double d = 0.0;
+    bool ok = false;
+    int j = 0, s = 0;
+    if (t < total) {
+      j = beg + (int)(t / nimg);
+      s = (int)(t % nimg);
+      const double a = (double)(s / (n1 * n2) - r0), b = (double)((s / n2) % n1 - r1), cc = (double)(s % n2 - r2);
+      // off = [a b cc] @ cell ; vec = (p_j + off) - p_i
+      const double ox = a * c[0] + b * c[3] + cc * c[6];
+      const double oy = a * c[1] + b * c[4] + cc * c[7];
+      const double oz = a * c[2] + b * c[5] + cc * c[8];
+      const double vx = ((double)pos[3 * j] + ox) - xi, vy = ((double)pos[3 * j + 1] + oy) - yi,
+                   vz = ((double)pos[3 * j + 2] + oz) - zi;
+      d = sqrt(vx * vx + vy * vy + vz * vz);
+      ok = (d < cutoff) && (d > 1e-4);
+    }
+    const unsigned bal = __ballot_sync(0xffffffffu, ok);
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    __syncthreads();
+    if (lane == 0) scratch[warp] = __popc(bal);
+    __syncthreads();
+    int off = scnt;
+    for (int w = 0; w < warp; ++w) off += scratch[w];
+    off += __popc(bal & ((1u << lane) - 1u));
+    if (ok) {
+      if (off < PBC_CAP) { sd[off] = d; sj[off] = j; ss[off] = s; }
+      else atomicExch(err, 1);
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      int tt = 0;
+      for (int w = 0; w < NB_THREADS / 32; ++w) tt += scratch[w];
+      scnt += tt;
+    }
+    __syncthreads();
+  }
+  const int cnt = min(scnt, PBC_CAP);
+  const bool trunc = cnt > max_nb;
+  // threshold: the max_nb-th smallest distance (rank max_nb-1 under (d, index) order)
+  if (trunc) {
+    for (int cidx = threadIdx.x; cidx < cnt; cidx += NB_THREADS) {
+      int rank = 0;
+      const double dc = sd[cidx];
+      for (int k = 0; k < cnt; ++k) rank += (sd[k] < dc) || (sd[k] == dc && k < cidx);
+      if (rank == max_nb - 1) sthr = dc;
+    }
+  }
+  __syncthreads();
+  const double thr = trunc ? (strict ? sthr : sthr + 0.01) : 0.0;
+  // keep flags + ordered positions (chunked ordered compaction again)
+  int written = 0;   // kept before this chunk (uniform across the CTA)
+  const int out0 = (mode == 1) ? rowptr[i] : 0;
+  for (int base = 0; base < cnt; base += NB_THREADS) {
+    const int cidx = base + threadIdx.x;
+    bool keep = false;
+    if (cidx < cnt) {
+      if (!trunc) keep = true;
+      else if (!strict) keep = !(sd[cidx] > thr);
+      else {
+        int rank = 0;
+        const double dc = sd[cidx];
+        for (int k = 0; k < cnt; ++k) rank += (sd[k] < dc) || (sd[k] == dc && k < cidx);
+        keep = rank < max_nb;
+      }
+    }
+    const unsigned bal = __ballot_sync(0xffffffffu, keep);
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    __syncthreads();
+    if (lane == 0) scratch[warp] = __popc(bal);
+    __syncthreads();
+    int off = written;
+    for (int w = 0; w < warp; ++w) off += scratch[w];
+    off += __popc(bal & ((1u << lane) - 1u));
+    int chunk = 0;
+    for (int w = 0; w < NB_THREADS / 32; ++w) chunk += scratch[w];
+    if (keep && mode == 1) {
+      const int o = out0 + off;
+      const int j = sj[cidx], s = ss[cidx];
+      const double a = (double)(s / (n1 * n2) - r0), b = (double)((s / n2) % n1 - r1), cc = (double)(s % n2 - r2);
+      const double ox = a * c[0] + b * c[3] + cc * c[6];
+      const double oy = a * c[1] + b * c[4] + cc * c[7];
+      const double oz = a * c[2] + b * c[5] + cc * c[8];
+      nbr_out[o] = j;
+      ctr_out[o] = i;
+      dist_out[o] = (float)sd[cidx];
+      vec_out[3 * o] = (float)(((double)pos[3 * j] + ox) - xi);
+      vec_out[3 * o + 1] = (float)(((double)pos[3 * j + 1] + oy) - yi);
+      vec_out[3 * o + 2] = (float)(((double)pos[3 * j + 2] + oz) - zi);
+    }
+    written += chunk;
+  }
+  if (mode == 0 && threadIdx.x == 0) deg[i] = written;
+}
+
+// reps[g,k] = ceil(cutoff / h_k), h_k = |det cell| / |a_{k+1} x a_{k+2}|  (fp64)
+__global__ void pbc_reps_kernel(const float* __restrict__ cell, double cutoff, int* __restrict__ reps, int B) {
+  const int g = blockIdx.x * blockDim.x + threadIdx.x;
+  if (g >= B) return;
+  double c[9];
+  for (int k = 0; k < 9; ++k) c[k] = (double)cell[9 * g + k];
+  const double det = c[0] * (c[4] * c[8] - c[5] * c[7]) - c[1] * (c[3] * c[8] - c[5] * c[6]) +
+                     c[2] * (c[3] * c[7] - c[4] * c[6]);
+  const double vol = fabs(det);
+  for (int k = 0; k < 3; ++k) {
+    const double* a = c + 3 * ((k + 1) % 3);
+    const double* b = c + 3 * ((k + 2) % 3);
+    const double cx = a[1] * b[2] - a[2] * b[1], cy = a[2] * b[0] - a[0] * b[2], cz = a[0] * b[1] - a[1] * b[0];
+    const double h = vol / sqrt(cx * cx + cy * cy + cz * cz);
+    reps[3 * g + k] = (int)ceil(cutoff / h);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// exclusive scan of int32 counts into rowptr[n+1] (single CTA; n is #atoms)
+__global__ void __launch_bounds__(1024) exclusive_scan_kernel(const int* __restrict__ in, int* __restrict__ out, int n) {
+  __shared__ int warp_tot[32];
+  __shared__ int carry;
+  if (threadIdx.x == 0) carry = 0;
+  __syncthreads();
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  for (int base = 0; base < n; base += 1024) {
+    const int i = base + threadIdx.x;
+    const int v = (i < n) ? in[i] : 0;
+    int x = v;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const int y = __shfl_up_sync(0xffffffffu, x, o);
+      if (lane >= o) x += y;
+    }
+    if (lane == 31) warp_tot[warp] = x;
+    __syncthreads();
+    if (warp == 0) {
+      int w = warp_tot[lane];
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) {
+        const int y = __shfl_up_sync(0xffffffffu, w, o);
+        if (lane >= o) w += y;
+      }
+      warp_tot[lane] = w;
+    }
+    __syncthreads();
+    const int prefix = carry + (warp > 0 ? warp_tot[warp - 1] : 0) + x - v;
+    if (i < n) out[i] = prefix;
+    __syncthreads();
+    if (threadIdx.x == 1023) carry = prefix + v;
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) out[n] = carry;
+}
+
+// graph_ptr[B+1] from natoms (int64)
+__global__ void graph_ptr_kernel(const long long* __restrict__ natoms, int* __restrict__ graph_ptr, int B) {
+  if (blockIdx.x == 0 && threadIdx.x == 0) {
+    int s = 0;
+    for (int g = 0; g < B; ++g) { graph_ptr[g] = s; s += (int)natoms[g]; }
+    graph_ptr[B] = s;
+  }
+}
+
+// CSR of an arbitrary index vector (used for the source-side walk of gather_rotate_bwd):
+// counting sort, stable in edge order.
+__global__ void hist_kernel(const long long* __restrict__ idx, int* __restrict__ cnt, long long E) {
+  const long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (e < E) atomicAdd(&cnt[idx[e]], 1);
+}
+// one thread per node walks nothing; instead one thread per edge computes its stable slot by counting
+// earlier edges with the same key inside the node's bucket -- O(E * deg) but deterministic, deg <= ~50.
+__global__ void csr_fill_kernel(const long long* __restrict__ idx, const int* __restrict__ rowptr,
+                                int* __restrict__ cursor, int* __restrict__ perm, long long E) {
+  // pass 1 (atomic) gives an arbitrary order inside a bucket; pass 2 (sort_bucket_kernel) sorts each bucket
+  const long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (e < E) {
+    const int k = (int)idx[e];
+    const int slot = atomicAdd(&cursor[k], 1);
+    perm[rowptr[k] + slot] = (int)e;
+  }
+}
+__global__ void sort_bucket_kernel(const int* __restrict__ rowptr, int* __restrict__ perm, long long N) {
+  const long long n = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (n >= N) return;
+  const int beg = rowptr[n], end = rowptr[n + 1];
+  for (int a = beg + 1; a < end; ++a) {   // insertion sort: buckets are short
+    const int v = perm[a];
+    int b = a - 1;
+    while (b >= beg && perm[b] > v) { perm[b + 1] = perm[b]; --b; }
+    perm[b + 1] = v;
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ long long lower_bound_ll(const long long* a, long long n, long long key) {
+  long long lo = 0, hi = n;
+  while (lo < hi) {
+    const long long mid = (lo + hi) >> 1;
+    if (a[mid] < key) lo = mid + 1; else hi = mid;
+  }
+  return lo;
+}
+
+__global__ void segment_sum_kernel(const float* __restrict__ v, long long v_stride, const long long* __restrict__ batch,
+                                   float* __restrict__ out, long long N, int B) {
+  const int g = blockIdx.x;
+  const long long beg = lower_bound_ll(batch, N, g), end = lower_bound_ll(batch, N, g + 1);
+  float s = 0.f;
+  for (long long i = beg + threadIdx.x; i < end; i += blockDim.x) s += v[i * v_stride];
+  s = eqv2_warp_sum(s);
+  if (threadIdx.x == 0) out[g] = s;   // blockDim.x == 32
+}
+
+__global__ void segment_bcast_kernel(const float* __restrict__ gout, const long long* __restrict__ batch,
+                                     float* __restrict__ gv, long long N) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < N) gv[i] = gout[batch[i]];
+}
+
+}  // namespace
+
+extern "C" int eqv2_graph_ptr(const long long* natoms, int* graph_ptr, int B, void* stream) {
+  EQV2_LAUNCH(graph_ptr_kernel, dim3(1), dim3(32), 0, stream, natoms, graph_ptr, B);
+  EQV2_CHECK_LAUNCH("eqv2_graph_ptr");
+  return 0;
+}
+
+extern "C" int eqv2_exclusive_scan(const int* in, int* out, int n, void* stream) {
+  EQV2_LAUNCH(exclusive_scan_kernel, dim3(1), dim3(1024), 0, stream, in, out, n);
+  EQV2_CHECK_LAUNCH("eqv2_exclusive_scan");
+  return 0;
+}
+
+extern "C" int eqv2_radius_graph(const float* pos, const int* graph_ptr, const long long* batch, long long N,
+                                 float cutoff, int max_nb, int mode, int* deg, const int* rowptr, long long* src,
+                                 long long* dst, float* dist, float* vec, int* err, void* stream) {
+  if (N == 0) return 0;
+  EQV2_LAUNCH(radius_graph_kernel, dim3((unsigned)N), dim3(NB_THREADS), 0, stream, pos, graph_ptr, batch, cutoff,
+              max_nb, mode, deg, rowptr, src, dst, dist, vec, err);
+  EQV2_CHECK_LAUNCH("eqv2_radius_graph");
+  return 0;
+}
+
+extern "C" int eqv2_pbc_reps(const float* cell, double cutoff, int* reps, int B, void* stream) {
+  if (B == 0) return 0;
+  EQV2_LAUNCH(pbc_reps_kernel, dim3((B + 63) / 64), dim3(64), 0, stream, cell, cutoff, reps, B);
+  EQV2_CHECK_LAUNCH("eqv2_pbc_reps");
+  return 0;
+}
+
+extern "C" int eqv2_radius_graph_pbc(const float* pos, const float* cell, const int* graph_ptr,
+                                     const long long* batch, const int* reps, long long N, double cutoff, int max_nb,
+                                     int strict, int mode, int* deg, const int* rowptr, long long* nbr,
+                                     long long* ctr, float* dist, float* vec, int* err, void* stream) {
+  if (N == 0) return 0;
+  EQV2_REQUIRE(max_nb >= 1, "radius_graph_pbc: max_neighbors must be >= 1");
+  EQV2_LAUNCH(radius_graph_pbc_kernel, dim3((unsigned)N), dim3(NB_THREADS), 0, stream, pos, cell, graph_ptr, batch,
+              reps, cutoff, max_nb, strict, mode, deg, rowptr, nbr, ctr, dist, vec, err);
+  EQV2_CHECK_LAUNCH("eqv2_radius_graph_pbc");
+  return 0;
+}
+
+extern "C" int eqv2_csr_from_index(const long long* idx, long long E, long long N, int* counts /*zeroed [N]*/,
+                                   int* rowptr /*[N+1]*/, int* cursor /*zeroed [N]*/, int* perm /*[E]*/,
+                                   void* stream) {
+  if (N == 0) return 0;
+  if (E > 0) {
+    EQV2_LAUNCH(hist_kernel, dim3((unsigned)((E + 255) / 256)), dim3(256), 0, stream, idx, counts, E);
+    EQV2_CHECK_LAUNCH("eqv2_csr_from_index/hist");
+  }
+  EQV2_LAUNCH(exclusive_scan_kernel, dim3(1), dim3(1024), 0, stream, counts, rowptr, (int)N);
+  EQV2_CHECK_LAUNCH("eqv2_csr_from_index/scan");
+  if (E > 0) {
+    EQV2_LAUNCH(csr_fill_kernel, dim3((unsigned)((E + 255) / 256)), dim3(256), 0, stream, idx, rowptr, cursor, perm, E);
+    EQV2_CHECK_LAUNCH("eqv2_csr_from_index/fill");
+    EQV2_LAUNCH(sort_bucket_kernel, dim3((unsigned)((N + 127) / 128)), dim3(128), 0, stream, rowptr, perm, N);
+    EQV2_CHECK_LAUNCH("eqv2_csr_from_index/sort");
+  }
+  return 0;
+}
+
+extern "C" int eqv2_segment_sum_fwd(const float* v, long long v_stride, const long long* batch, float* out,
+                                    long long N, int B, void* stream) {
+  if (B == 0) return 0;
+  EQV2_LAUNCH(segment_sum_kernel, dim3(B), dim3(32), 0, stream, v, v_stride, batch, out, N, B);
+  EQV2_CHECK_LAUNCH("eqv2_segment_sum_fwd");
+  return 0;
+}
+
+extern "C" int eqv2_segment_sum_bwd(const float* gout, const long long* batch, float* gv, long long N, void* stream) {
+  if (N == 0) return 0;
+  EQV2_LAUNCH(segment_bcast_kernel, dim3((unsigned)((N + 255) / 256)), dim3(256), 0, stream, gout, batch, gv, N);
+  EQV2_CHECK_LAUNCH("eqv2_segment_sum_bwd");
+  return 0;
+}

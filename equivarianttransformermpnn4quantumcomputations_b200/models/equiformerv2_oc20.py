@@ -1,0 +1,129 @@
+"""EquiformerV2_OC20 (reference models/equiformerv2_oc20.py:63-303): energy + direct forces for
+periodic slabs.  Same constructor arguments, forward(data) contract and state_dict keys.
+
+forward(data) accepts the reference batch dict {atomic_numbers, pos, batch, natoms, cell[, pbc]} and
+builds the periodic neighbour list on the GPU (`ops.radius_graph_pbc`, replacing the un-vendored
+fairchem `generate_graph` called at equiformerv2_oc20.py:223-234).  A caller that already has a graph
+may pass `edge_index`, `edge_distance`, `edge_distance_vec` in the dict to skip the builder.
+"""
+import torch
+import torch.nn as nn
+
+from .. import ops
+from ..EquiformerV2Functions.edge_rot_mat import init_edge_rot_mat
+from ..EquiformerV2Functions.input_block import EdgeDegreeEmbedding
+from ..EquiformerV2Functions.layer_norm import get_normalization_layer
+from ..EquiformerV2Functions.so3 import CoefficientMappingModule, SO3_Embedding, SO3_Rotation
+from ..EquiformerV2Functions.transformer_block import (FeedForwardNetwork, SO2EquivariantGraphAttention,
+                                                       TransBlockV2)
+from .common import GaussianSmearing, build_so3_grid, init_linear, segment_sum
+
+_AVG_NUM_NODES = 77.81317
+_AVG_DEGREE = 23.395238876342773
+
+
+class EquiformerV2_OC20(nn.Module):
+    def __init__(self, num_atoms=None, bond_feat_dim=None, num_targets=1, use_pbc=True, regress_forces=True,
+                 otf_graph=True, max_neighbors=20, max_radius=12.0, max_num_elements=90, num_layers=12,
+                 sphere_channels=128, attn_hidden_channels=64, num_heads=8, attn_alpha_channels=64,
+                 attn_value_channels=16, ffn_hidden_channels=128, norm_type="rms_norm_sh", lmax_list=[6],
+                 mmax_list=[2], grid_resolution=18, num_sphere_samples=128, edge_channels=128,
+                 use_atom_edge_embedding=True, share_atom_edge_embedding=False, use_m_share_rad=False,
+                 distance_function="gaussian", num_distance_basis=600, attn_activation="silu",
+                 use_s2_act_attn=False, use_attn_renorm=True, ffn_activation="silu", use_gate_act=False,
+                 use_grid_mlp=False, use_sep_s2_act=True, alpha_drop=0.1, drop_path_rate=0.05, proj_drop=0.0,
+                 weight_init="uniform"):
+        super().__init__()
+        self.use_pbc = use_pbc
+        self.regress_forces = regress_forces
+        self.otf_graph = otf_graph
+        self.max_neighbors = max_neighbors
+        self.max_radius = self.cutoff = max_radius
+        self.max_num_elements = max_num_elements
+        self.num_layers = num_layers
+        self.sphere_channels = sphere_channels
+        self.lmax_list, self.mmax_list = lmax_list, mmax_list
+        self.grid_resolution = grid_resolution
+        self.num_resolutions = len(lmax_list)
+        self.sphere_channels_all = self.num_resolutions * sphere_channels
+        self.edge_channels = edge_channels
+        self.use_atom_edge_embedding = use_atom_edge_embedding
+        self.share_atom_edge_embedding = share_atom_edge_embedding
+        self.weight_init = weight_init
+        self.block_use_atom_edge_embedding = False if share_atom_edge_embedding else use_atom_edge_embedding
+
+        self.sphere_embedding = nn.Embedding(max_num_elements, self.sphere_channels_all)
+        self.distance_expansion = GaussianSmearing(0.0, max_radius, num_distance_basis, 2.0)
+        self.edge_channels_list = [num_distance_basis, edge_channels, edge_channels]
+        if share_atom_edge_embedding and use_atom_edge_embedding:
+            self.source_embedding = nn.Embedding(max_num_elements, edge_channels)
+            self.target_embedding = nn.Embedding(max_num_elements, edge_channels)
+            self.edge_channels_list[0] = num_distance_basis + 2 * edge_channels
+        else:
+            self.source_embedding = self.target_embedding = None
+
+        self.SO3_rotation = nn.ModuleList([SO3_Rotation(l) for l in lmax_list])
+        self.mappingReduced = CoefficientMappingModule(lmax_list, mmax_list)
+        self.SO3_grid = build_so3_grid(lmax_list, grid_resolution)
+        self.edge_degree_embedding = EdgeDegreeEmbedding(
+            sphere_channels, lmax_list, mmax_list, self.SO3_rotation, self.mappingReduced, max_num_elements,
+            self.edge_channels_list, self.block_use_atom_edge_embedding, rescale_factor=_AVG_DEGREE)
+        self.blocks = nn.ModuleList([
+            TransBlockV2(sphere_channels, attn_hidden_channels, num_heads, attn_alpha_channels, attn_value_channels,
+                         ffn_hidden_channels, sphere_channels, lmax_list, mmax_list, self.SO3_rotation,
+                         self.mappingReduced, self.SO3_grid, max_num_elements, self.edge_channels_list,
+                         self.block_use_atom_edge_embedding, use_m_share_rad, attn_activation, use_s2_act_attn,
+                         use_attn_renorm, ffn_activation, use_gate_act, use_grid_mlp, use_sep_s2_act, norm_type,
+                         alpha_drop, drop_path_rate, proj_drop)
+            for _ in range(num_layers)])
+        self.norm = get_normalization_layer(norm_type, lmax=max(lmax_list), num_channels=sphere_channels)
+        self.energy_block = FeedForwardNetwork(sphere_channels, ffn_hidden_channels, 1, lmax_list, mmax_list,
+                                               self.SO3_grid, ffn_activation, use_gate_act, use_grid_mlp,
+                                               use_sep_s2_act)
+        if regress_forces:
+            self.force_block = SO2EquivariantGraphAttention(
+                sphere_channels, attn_hidden_channels, num_heads, attn_alpha_channels, attn_value_channels, 1,
+                lmax_list, mmax_list, self.SO3_rotation, self.mappingReduced, self.SO3_grid, max_num_elements,
+                self.edge_channels_list, self.block_use_atom_edge_embedding, use_m_share_rad, attn_activation,
+                use_s2_act_attn, use_attn_renorm, use_gate_act, use_sep_s2_act, alpha_drop=0.0)
+        # reference `_init_weights` (equiformerv2_oc20.py:294-303) re-draws for both modes
+        self.apply(lambda m: init_linear(m, "uniform" if weight_init == "uniform" else "normal"))
+
+    @property
+    def num_params(self):
+        return sum(p.numel() for p in self.parameters())
+
+    def generate_graph(self, data):
+        if "edge_index" in data:
+            return data["edge_index"], data["edge_distance"], data["edge_distance_vec"]
+        return ops.radius_graph_pbc(data["pos"], data["cell"], data["natoms"], data["batch"], self.cutoff,
+                                    self.max_neighbors)
+
+    def forward(self, data):
+        atomic_numbers = data["atomic_numbers"].long()
+        num_atoms = atomic_numbers.shape[0]
+        pos = data["pos"]
+        edge_index, edge_distance, edge_vec = self.generate_graph(data)
+
+        frames = init_edge_rot_mat(edge_vec)
+        for rot in self.SO3_rotation:
+            rot.set_wigner(frames)
+
+        x = SO3_Embedding(num_atoms, self.lmax_list, self.sphere_channels, pos.device, pos.dtype)
+        x.embedding[:, 0, :] = self.sphere_embedding(atomic_numbers)
+
+        rbf = self.distance_expansion(edge_distance)
+        if self.share_atom_edge_embedding and self.use_atom_edge_embedding:
+            rbf = torch.cat([rbf, self.source_embedding(atomic_numbers[edge_index[0]]),
+                             self.target_embedding(atomic_numbers[edge_index[1]])], dim=1)
+        x.embedding = x.embedding + self.edge_degree_embedding(atomic_numbers, rbf, edge_index).embedding
+        for block in self.blocks:
+            x = block(x, atomic_numbers, rbf, edge_index, batch=data["batch"])
+        x.embedding = self.norm(x.embedding)
+
+        node_energy = self.energy_block(x).embedding[:, 0, 0]
+        energy = segment_sum(node_energy, data["batch"], len(data["natoms"])) / _AVG_NUM_NODES
+        if self.regress_forces:
+            forces = self.force_block(x, atomic_numbers, rbf, edge_index).embedding[:, 1:4, 0]
+            return energy, forces
+        return energy

@@ -92,38 +92,172 @@ class CoeffLayout:
 # ----------------------------------------------------------------------------------------------
 # edge plan: dst-sorted / src-sorted CSR over the (arbitrarily ordered) edge list
 # ----------------------------------------------------------------------------------------------
+def _csr_from_index(idx, num_nodes):
+    """(perm int32 [E], rowptr int32 [N+1]): edges grouped by idx, stable in edge order
+    (`eqv2_csr_from_index`: histogram -> scan -> fill -> per-bucket sort)."""
+    dev = idx.device
+    E = int(idx.shape[0])
+    counts = torch.zeros(num_nodes, dtype=torch.int32, device=dev)
+    cursor = torch.zeros(num_nodes, dtype=torch.int32, device=dev)
+    rowptr = torch.empty(num_nodes + 1, dtype=torch.int32, device=dev)
+    perm = torch.empty(E, dtype=torch.int32, device=dev)
+    _lib.call("eqv2_csr_from_index", idx.data_ptr(), E, num_nodes, counts.data_ptr(), rowptr.data_ptr(),
+              cursor.data_ptr(), perm.data_ptr(), _lib.stream_ptr(), n_kernels=4)
+    return perm, rowptr
+
+
 class EdgePlan:
-    def __init__(self, edge_index, num_nodes):
+    """CSR views of one edge list.  `rowptr_dst`/`perm_dst` group edges by destination (segment softmax,
+    segmented reduce), `rowptr_src`/`perm_src` by source (node-centric backward of the gather)."""
+
+    def __init__(self, edge_index, num_nodes, dst_sorted_rowptr=None):
         _lib.check_device(edge_index)
         self.E = int(edge_index.shape[1])
         self.N = int(num_nodes)
         self.src = edge_index[0].contiguous()
         self.dst = edge_index[1].contiguous()
         dev = edge_index.device
-        self.perm_dst, self.rowptr_dst = self._csr(self.dst, dev)
-        self.perm_src, self.rowptr_src = self._csr(self.src, dev)
-
-    def _csr(self, idx, dev):
-        if self.E == 0:
-            return (torch.zeros(0, dtype=torch.int32, device=dev), torch.zeros(self.N + 1, dtype=torch.int32, device=dev))
-        perm = torch.sort(idx, stable=True)[1].to(torch.int32)
-        counts = torch.bincount(idx, minlength=self.N)
-        rowptr = torch.zeros(self.N + 1, dtype=torch.int32, device=dev)
-        rowptr[1:] = torch.cumsum(counts, 0).to(torch.int32)
-        return perm.contiguous(), rowptr
+        if dst_sorted_rowptr is not None:
+            # the neighbour-list builders emit edges already sorted by destination
+            self.rowptr_dst = dst_sorted_rowptr
+            self.perm_dst = torch.arange(self.E, dtype=torch.int32, device=dev)
+        else:
+            self.perm_dst, self.rowptr_dst = _csr_from_index(self.dst, self.N)
+        self.perm_src, self.rowptr_src = _csr_from_index(self.src, self.N)
 
 
 _plan_cache = {}
 
 
+def _plan_key(edge_index, num_nodes):
+    return (edge_index.data_ptr(), tuple(edge_index.shape), edge_index._version, int(num_nodes), str(edge_index.device))
+
+
 def edge_plan(edge_index, num_nodes):
-    key = (edge_index.data_ptr(), tuple(edge_index.shape), edge_index._version, int(num_nodes), str(edge_index.device))
+    key = _plan_key(edge_index, num_nodes)
     hit = _plan_cache.get("k")
     if hit is not None and hit[0] == key:
         return hit[1]
     plan = EdgePlan(edge_index, num_nodes)
     _plan_cache["k"] = (key, plan, edge_index)   # keep the tensor alive so data_ptr stays unique
     return plan
+
+
+def _register_plan(edge_index, num_nodes, rowptr_dst):
+    plan = EdgePlan(edge_index, num_nodes, dst_sorted_rowptr=rowptr_dst)
+    _plan_cache["k"] = (_plan_key(edge_index, num_nodes), plan, edge_index)
+    return plan
+
+
+# ----------------------------------------------------------------------------------------------
+# neighbour lists
+# ----------------------------------------------------------------------------------------------
+def _graph_ptr(natoms, dev):
+    B = int(natoms.shape[0])
+    natoms = natoms.to(device=dev, dtype=torch.long).contiguous()
+    gp = torch.empty(B + 1, dtype=torch.int32, device=dev)
+    _lib.call("eqv2_graph_ptr", natoms.data_ptr(), gp.data_ptr(), B, _lib.stream_ptr())
+    return gp
+
+
+def _count_scan_fill(N, dev, launch):
+    """count (mode 0) -> exclusive scan -> read E -> fill (mode 1).  `launch(mode, deg, rowptr, outs)`."""
+    deg = torch.empty(N, dtype=torch.int32, device=dev)
+    rowptr = torch.empty(N + 1, dtype=torch.int32, device=dev)
+    err = torch.zeros(1, dtype=torch.int32, device=dev)
+    launch(0, deg, rowptr, None, err)
+    _lib.call("eqv2_exclusive_scan", deg.data_ptr(), rowptr.data_ptr(), N, _lib.stream_ptr())
+    tail = torch.stack([rowptr[-1], err[0]]).tolist()          # the one host read-back of the builder
+    E = int(tail[0])
+    if tail[1] != 0:
+        raise _lib.Eqv2Error("neighbour list: a destination atom has more in-cutoff candidates than the kernel holds")
+    edge_index = torch.empty(2, E, dtype=torch.long, device=dev)
+    dist = torch.empty(E, dtype=_F32, device=dev)
+    vec = torch.empty(E, 3, dtype=_F32, device=dev)
+    if E > 0:
+        launch(1, deg, rowptr, (edge_index, dist, vec), err)
+    return edge_index, dist, vec, rowptr
+
+
+def radius_graph(pos, natoms, batch, cutoff, max_neighbors):
+    """Isolated-molecule radius graph (equiformerv2_qm9.py:423-525) -> (edge_index [2,E] int64 with
+    row 0 = source, row 1 = destination; edge_distance [E]; edge_vec [E,3] = pos[dst] - pos[src]),
+    edges sorted by (dst, src).  No gradient (the reference QM9/OC20 models never differentiate it)."""
+    _lib.check_device(pos, batch)
+    pos = pos.detach().to(_F32).contiguous()
+    batch = batch.contiguous()
+    N = int(pos.shape[0])
+    dev = pos.device
+    gp = _graph_ptr(natoms, dev)
+    mx = -1 if max_neighbors is None else int(max_neighbors)
+
+    def launch(mode, deg, rowptr, outs, err):
+        ei, d, v = outs if outs is not None else (None, None, None)
+        _lib.call("eqv2_radius_graph", pos.data_ptr(), gp.data_ptr(), batch.data_ptr(), N, float(cutoff), mx, mode,
+                  deg.data_ptr(), rowptr.data_ptr(), _lib.ptr(ei[0]) if ei is not None else None,
+                  _lib.ptr(ei[1]) if ei is not None else None, _lib.ptr(d), _lib.ptr(v), err.data_ptr(),
+                  _lib.stream_ptr())
+
+    ei, d, v, rowptr = _count_scan_fill(N, dev, launch)
+    _register_plan(ei, N, rowptr)
+    return ei, d, v
+
+
+def radius_graph_pbc(pos, cell, natoms, batch, cutoff, max_neighbors, strict=False):
+    """Periodic radius graph with the semantics of the fairchem `generate_graph` call at
+    equiformerv2_oc20.py:223-234 as restated in oracle/eqv2_oracle.py::radius_graph_pbc_fairchem
+    (row 0 = neighbour j, row 1 = centre i, vec = pos[j] + offset - pos[i]); edges sorted by (i, j, image)."""
+    _lib.check_device(pos, cell, batch)
+    pos = pos.detach().to(_F32).contiguous()
+    cell = cell.detach().to(_F32).contiguous()
+    batch = batch.contiguous()
+    N, B = int(pos.shape[0]), int(cell.shape[0])
+    dev = pos.device
+    gp = _graph_ptr(natoms, dev)
+    reps = torch.empty(B, 3, dtype=torch.int32, device=dev)
+    _lib.call("eqv2_pbc_reps", cell.data_ptr(), float(cutoff), reps.data_ptr(), B, _lib.stream_ptr())
+
+    def launch(mode, deg, rowptr, outs, err):
+        ei, d, v = outs if outs is not None else (None, None, None)
+        _lib.call("eqv2_radius_graph_pbc", pos.data_ptr(), cell.data_ptr(), gp.data_ptr(), batch.data_ptr(),
+                  reps.data_ptr(), N, float(cutoff), int(max_neighbors), int(bool(strict)), mode, deg.data_ptr(),
+                  rowptr.data_ptr(), _lib.ptr(ei[0]) if ei is not None else None,
+                  _lib.ptr(ei[1]) if ei is not None else None, _lib.ptr(d), _lib.ptr(v), err.data_ptr(),
+                  _lib.stream_ptr())
+
+    ei, d, v, rowptr = _count_scan_fill(N, dev, launch)
+    _register_plan(ei, N, rowptr)
+    return ei, d, v
+
+
+class SegmentSumFn(torch.autograd.Function):
+    """Per-graph sum of per-atom scalars; `batch` must be non-decreasing (every reference collate
+    function produces it that way).  Deterministic replacement of the index_add_ readouts."""
+
+    @staticmethod
+    def forward(ctx, values, batch, num_graphs):
+        _lib.check_device(values, batch)
+        values = values.contiguous()
+        batch = batch.contiguous()
+        N = int(values.shape[0])
+        out = torch.empty(num_graphs, dtype=_F32, device=values.device)
+        _lib.call("eqv2_segment_sum_fwd", values.data_ptr(), 1, batch.data_ptr(), out.data_ptr(), N, int(num_graphs),
+                  _lib.stream_ptr())
+        ctx.save_for_backward(batch)
+        return out
+
+    @staticmethod
+    def backward(ctx, gout):
+        (batch,) = ctx.saved_tensors
+        gout = gout.contiguous()
+        N = int(batch.shape[0])
+        gv = torch.empty(N, dtype=_F32, device=gout.device)
+        _lib.call("eqv2_segment_sum_bwd", gout.data_ptr(), batch.data_ptr(), gv.data_ptr(), N, _lib.stream_ptr())
+        return gv, None, None
+
+
+def segment_sum_nodes(values, batch, num_graphs):
+    return SegmentSumFn.apply(values, batch, num_graphs)
 
 
 # ----------------------------------------------------------------------------------------------

@@ -112,6 +112,29 @@ int eqv2_ln_silu_bwd(const float* x, const float* w, const float* b, const float
                      float* gw /*zeroed*/, float* gb /*zeroed*/, long long rows, int width, float eps,
                      void* stream);
 
+/* ---- neighbour lists and per-graph reductions -------------------------------------------
+ * Builders run count (mode 0: deg[N]) -> eqv2_exclusive_scan -> fill (mode 1) and emit edges sorted
+ * by destination; `err` is a device int set to 1 if a destination had more in-cutoff candidates
+ * than the kernel's shared-memory capacity.
+ * Replaces: equiformerv2_qm9.py:423-525 (generate_graph), the fairchem generate_graph call at
+ * equiformerv2_oc20.py:223-234, and the index_add_ readouts equiformerv2_oc20.py:278-281. */
+int eqv2_graph_ptr(const long long* natoms /*[B]*/, int* graph_ptr /*[B+1]*/, int B, void* stream);
+int eqv2_exclusive_scan(const int* in /*[n]*/, int* out /*[n+1]*/, int n, void* stream);
+int eqv2_radius_graph(const float* pos /*[N,3]*/, const int* graph_ptr, const long long* batch, long long N,
+                      float cutoff, int max_nb /* <0: unlimited */, int mode, int* deg, const int* rowptr,
+                      long long* src, long long* dst, float* dist, float* vec /*[E,3]*/, int* err, void* stream);
+int eqv2_pbc_reps(const float* cell /*[B,3,3]*/, double cutoff, int* reps /*[B,3]*/, int B, void* stream);
+int eqv2_radius_graph_pbc(const float* pos, const float* cell, const int* graph_ptr, const long long* batch,
+                          const int* reps, long long N, double cutoff, int max_nb, int strict, int mode, int* deg,
+                          const int* rowptr, long long* nbr, long long* ctr, float* dist, float* vec, int* err,
+                          void* stream);
+int eqv2_csr_from_index(const long long* idx /*[E]*/, long long E, long long N, int* counts /*zeroed [N]*/,
+                        int* rowptr /*[N+1]*/, int* cursor /*zeroed [N]*/, int* perm /*[E]*/, void* stream);
+int eqv2_segment_sum_fwd(const float* v, long long v_stride, const long long* batch /*non-decreasing [N]*/,
+                         float* out /*[B]*/, long long N, int B, void* stream);
+int eqv2_segment_sum_bwd(const float* gout /*[B]*/, const long long* batch, float* gv /*[N]*/, long long N,
+                         void* stream);
+
 #ifdef __cplusplus
 }
 #endif

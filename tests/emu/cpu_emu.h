@@ -94,6 +94,29 @@ static inline T __shfl_sync(unsigned, T v, int s, int width = 32) {
   return emu_shfl(v, (l / width) * width + (s % width));
 }
 
+template <typename T>
+static inline T __shfl_up_sync(unsigned, T v, int d, int width = 32) {
+  int l = emu_linear_tid() & 31;
+  int s = l - d;
+  if (s < (l / width) * width) s = l;
+  return emu_shfl(v, s);
+}
+static inline unsigned __ballot_sync(unsigned, int pred) {
+  int tid = emu_linear_tid();
+  int w = tid >> 5, l = tid & 31;
+  emu_shfl_buf[w][l] = pred ? 1u : 0u;
+  pthread_barrier_wait(&emu_warp_barrier[w]);
+  unsigned out = 0;
+  for (int i = 0; i < 32; ++i) out |= (emu_shfl_buf[w][i] & 1u) << i;
+  pthread_barrier_wait(&emu_warp_barrier[w]);
+  return out;
+}
+static inline int __popc(unsigned v) { return __builtin_popcount(v); }
+static inline float __fadd_rn(float a, float b) { volatile float r = a + b; return r; }
+static inline float __fmul_rn(float a, float b) { volatile float r = a * b; return r; }
+static inline float __fsqrt_rn(float a) { return sqrtf(a); }
+static inline int atomicExch(int* p, int v) { return reinterpret_cast<std::atomic<int>*>(p)->exchange(v); }
+
 static inline float atomicAdd(float* p, float v) {
   std::atomic<uint32_t>* a = reinterpret_cast<std::atomic<uint32_t>*>(p);
   uint32_t old = a->load();
