@@ -1,0 +1,294 @@
+#!/usr/bin/env python
+"""Headline benchmark: OC20 S2EF EquiformerV2 training step (BASELINE.json configs[1]).
+
+  python bench.py --gpus 1 --steps K --warmup W            # the CUDA path (this repo)
+  python bench.py --impl reference --steps K --warmup W    # the reference algorithm on the host CPU cores
+  torchrun --nproc-per-node N ... bench.py --gpus N ...    # data parallel, one rank per GPU (NCCL)
+
+A "step" = neighbour list + forward (energy + direct forces) + L1 losses + backward + AdamW update on a
+batch of synthetic ~80-atom periodic slabs (12 A cutoff, <= 20 neighbours), fp32, random-init weights of
+the reference architecture (equiformerv2_oc20.py ctor defaults: lmax 6, mmax 2, 12 blocks + force head).
+Prints ONE JSON line (rank 0).
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import tempfile
+import time
+
+import torch
+
+REPO = os.path.dirname(os.path.abspath(__file__))
+if REPO not in sys.path:
+    sys.path.insert(0, REPO)
+PKG = "equivarianttransformermpnn4quantumcomputations_b200"
+
+METRIC = "oc20_s2ef_train_structures_per_s"
+UNIT = "structures/s"
+
+MODEL_KW = dict(max_neighbors=20, max_radius=12.0, max_num_elements=90, num_layers=12, sphere_channels=128,
+                attn_hidden_channels=64, num_heads=8, attn_alpha_channels=64, attn_value_channels=16,
+                ffn_hidden_channels=128, norm_type="rms_norm_sh", lmax_list=[6], mmax_list=[2], grid_resolution=18,
+                edge_channels=128, alpha_drop=0.0, drop_path_rate=0.0, proj_drop=0.0)
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--structures", type=int, default=8, help="structures per GPU per step")
+    ap.add_argument("--layers", type=int, default=None, help="(debug) override the number of blocks")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    return ap.parse_args()
+
+
+def peaks():
+    path = os.path.join(REPO, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        p = json.load(open(path))
+        return dict(hbm=p["hbm_gbs"], tensor=p.get("bf16_tflops_sustained", p["bf16_tflops"]), src="measured")
+    return dict(hbm=6650.0, tensor=1400.0, src="fallback")
+
+
+class ClockSampler:
+    Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.f = tempfile.NamedTemporaryFile("w+", suffix=".csv", delete=False)
+        try:
+            self.p = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms",
+                                       "200", "-i", str(index)], stdout=self.f, stderr=subprocess.DEVNULL)
+        except OSError:
+            self.p = None
+
+    def stop(self):
+        if self.p is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.p.terminate()
+        self.p.wait()
+        self.f.flush()
+        rows = [r.strip().split(", ") for r in open(self.f.name) if r.strip()]
+        os.unlink(self.f.name)
+        sm = sorted(float(r[0]) for r in rows if r[0].replace(".", "").isdigit())
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = [n for i, n in enumerate(names) if any(len(r) > 2 + i and r[2 + i].strip() == "Active" for r in rows)]
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None,
+                "sm_max_mhz": float(rows[0][1]) if rows else None, "reasons": reasons, "samples": len(sm)}
+
+
+def losses(energy, forces, data):
+    return (energy - data["energy"]).abs().mean() + (forces - data["forces"]).abs().mean()
+
+
+# ------------------------------------------------------------------------------------------------
+def run_reference(args):
+    """The reference algorithm (CPU, all host threads) on a bounded sample of the same workload:
+    ONE structure per step through the oracle port of the reference's forward (oracle/eqv2_oracle.py),
+    torch autograd backward, AdamW update."""
+    rank = int(os.environ.get("RANK", 0))
+    if rank != 0:
+        return
+    import importlib
+    from oracle import eqv2_oracle as O
+    synthetic = importlib.import_module(PKG + ".synthetic")
+    oc20 = importlib.import_module(PKG + ".models.equiformerv2_oc20")
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    kw = dict(MODEL_KW)
+    if args.layers:
+        kw["num_layers"] = args.layers
+    torch.manual_seed(0)
+    model = oc20.EquiformerV2_OC20(**kw)            # parameter container only (reference state_dict keys)
+    P = dict(model.named_parameters())
+    hp = O.Hyper(lmax=6, mmax=2, C=128, H=64, heads=8, alpha_ch=64, value_ch=16, ffn_hidden=128, edge_ch=128,
+                 num_layers=kw["num_layers"], norm_type="rms_norm_sh", cutoff=12.0, max_neighbors=20)
+    opt = torch.optim.AdamW(model.parameters(), lr=1e-4)
+    n_struct = 1
+    times = []
+    edges = 0
+    for it in range(args.warmup + args.steps):
+        data = synthetic.oc20_batch(n_struct, seed=1000 + it)
+        t0 = time.perf_counter()
+        ei, dist, vec = O.radius_graph_pbc_fairchem(data["pos"], data["cell"], data["batch"], data["natoms"], 12.0, 20)
+        rand_vec = torch.rand(vec.shape) - 0.5
+        energy, forces = O.oc20_forward(P, hp, data["atomic_numbers"], data["batch"], n_struct, ei, dist, vec, rand_vec)
+        loss = losses(energy, forces, data)
+        opt.zero_grad(set_to_none=True)
+        loss.backward()
+        opt.step()
+        dt = time.perf_counter() - t0
+        if it >= args.warmup:
+            times.append(dt)
+            edges += ei.shape[1]
+    total = sum(times)
+    value = n_struct * len(times) / total
+    sample = f"{n_struct} structure/step (80 atoms, ~{edges // max(len(times), 1)} edges), oracle port of the reference forward + autograd backward + AdamW"
+    line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * total / len(times),
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": "OC20 S2EF EquiformerV2 (lmax 6, mmax 2, 12 blocks + force head) train step, "
+                                   "~80-atom slabs, 12 A cutoff, max 20 neighbours", "layers": kw["num_layers"]},
+            "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
+            "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "edge_msgs_per_s": edges * (kw["num_layers"] + 1) / total}
+    print(json.dumps(line), flush=True)
+
+
+# ------------------------------------------------------------------------------------------------
+def run_b200(args):
+    import importlib
+    rank = int(os.environ.get("RANK", 0))
+    world = int(os.environ.get("WORLD_SIZE", 1))
+    local = int(os.environ.get("LOCAL_RANK", 0))
+    assert torch.cuda.is_available(), "bench.py needs a CUDA device (no CPU fallback)"
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group(backend="nccl", init_method="env://", device_id=dev)
+    _lib = importlib.import_module(PKG + "._lib")
+    synthetic = importlib.import_module(PKG + ".synthetic")
+    oc20 = importlib.import_module(PKG + ".models.equiformerv2_oc20")
+    _lib.lib()
+
+    kw = dict(MODEL_KW)
+    if args.layers:
+        kw["num_layers"] = args.layers
+    torch.manual_seed(0)
+    model = oc20.EquiformerV2_OC20(**kw).to(dev)
+    net = model
+    if world > 1:
+        net = torch.nn.parallel.DistributedDataParallel(model, device_ids=[local], gradient_as_bucket_view=True)
+    opt = torch.optim.AdamW(model.parameters(), lr=1e-4, fused=True)
+
+    B = args.structures
+    host = synthetic.oc20_batch(B, seed=1000 + rank)
+    keys = ["atomic_numbers", "pos", "batch", "natoms", "cell", "energy", "forces"]
+    pinned = {k: host[k].pin_memory() for k in keys}
+    h2d_bytes = sum(pinned[k].numel() * pinned[k].element_size() for k in keys)
+    resident = {k: v.to(dev) for k, v in pinned.items()}
+    stats = {}
+
+    def step(data):
+        energy, forces = net(data)
+        loss = losses(energy, forces, data)
+        opt.zero_grad(set_to_none=True)
+        loss.backward()
+        opt.step()
+        return loss
+
+    def step_e2e():
+        data = {k: v.to(dev, non_blocking=True) for k, v in pinned.items()}
+        return float(step(data).item())          # device -> host read of the step's result
+
+    def barrier():
+        if dist is not None:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(fn, n):
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(n):
+            fn()
+        e1.record()
+        barrier()
+        ms = torch.tensor([e0.elapsed_time(e1)], device=dev)
+        if dist is not None:
+            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        return float(ms.item())
+
+    for _ in range(max(args.warmup, 3)):
+        step_e2e()
+    with torch.no_grad():
+        E = int(model.generate_graph(resident)[0].shape[1])
+    sampler = ClockSampler(local) if rank == 0 else None
+    _lib.reset_launch_count()
+    ms_dev = timed(lambda: step(resident), args.steps)
+    launches = _lib.launch_count()
+    ms_e2e = timed(step_e2e, args.steps)
+    clocks = sampler.stop() if sampler is not None else None
+
+    # per-entry-point device time (separate pass: event pairs around every C-ABI call)
+    barrier()
+    _lib.start_kernel_timing()
+    step(resident)
+    prof = _lib.stop_kernel_timing()
+
+    n_struct = B * world
+    value = n_struct * args.steps / (ms_dev / 1e3)
+    e2e = n_struct * args.steps / (ms_e2e / 1e3)
+    blocks = kw["num_layers"] + 1
+    if rank == 0:
+        pk = peaks()
+        tot = sum(r["ms"] for r in prof.values()) or 1.0
+        top = max(prof.items(), key=lambda kv: kv[1]["ms"])
+        name, r = top
+        shares = {k: round(v["ms"] / tot, 4) for k, v in sorted(prof.items(), key=lambda kv: -kv[1]["ms"])[:8]}
+        if r["flops"] > 0:
+            achieved = r["flops"] / (r["ms"] * 1e-3) / 1e12
+            roof = {"kernel": name, "bound": "tensor", "achieved": achieved, "peak": pk["tensor"], "unit": "TFLOP/s",
+                    "frac": achieved / pk["tensor"], "traffic": None, "peak_source": pk["src"] + " bf16 sustained",
+                    "launches_per_step": r["calls"], "avg_launch_ms": r["ms"] / r["calls"],
+                    "share_of_step_kernel_time": r["ms"] / tot}
+        else:
+            roof = {"kernel": name, "bound": "hbm", "achieved": None, "peak": pk["hbm"], "unit": "GB/s", "frac": None,
+                    "traffic": None, "peak_source": pk["src"], "share_of_step_kernel_time": r["ms"] / tot}
+        cpu = None
+        if world == 1 and not args.no_cpu_baseline:
+            cpu = cpu_baseline(kw)
+        line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+                "warmup": max(args.warmup, 3), "ms_per_step": ms_dev / args.steps, "higher_is_better": True,
+                "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+                "config": {"workload": "OC20 S2EF EquiformerV2 (lmax 6, mmax 2, 12 blocks + force head) train step "
+                                       "(graph build + fwd + L1 loss + bwd + AdamW), ~80-atom slabs, 12 A cutoff, "
+                                       "max 20 neighbours", "structures_per_gpu": B, "atoms_per_gpu": int(host["pos"].shape[0]),
+                           "edges_per_gpu": E, "layers": kw["num_layers"], "params": model.num_params,
+                           "parallelism": f"dp{world}", "gemm_engine": "fp32 FFMA",
+                           "l2": "step working set (330 MB weights + >1 GB activations) exceeds the 126 MB L2"},
+                "e2e": {"value": e2e, "unit": UNIT, "ms_per_step": ms_e2e / args.steps, "h2d_bytes_per_step": h2d_bytes,
+                        "d2h_bytes_per_step": 4},
+                "gpu_launches": launches, "edge_msgs_per_s": E * world * blocks * args.steps / (ms_dev / 1e3),
+                "roofline": roof, "kernel_time_shares": shares, "clocks": clocks, "cpu_baseline": cpu}
+        print(json.dumps(line), flush=True)
+    if dist is not None:
+        dist.destroy_process_group()
+
+
+def cpu_baseline(kw):
+    """Oracle port on the host cores, ONE structure fwd+bwd (bounded sample, ~10-30 s)."""
+    import importlib
+    from oracle import eqv2_oracle as O
+    synthetic = importlib.import_module(PKG + ".synthetic")
+    oc20 = importlib.import_module(PKG + ".models.equiformerv2_oc20")
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    torch.manual_seed(0)
+    model = oc20.EquiformerV2_OC20(**kw)
+    P = dict(model.named_parameters())
+    hp = O.Hyper(lmax=6, mmax=2, C=128, H=64, heads=8, alpha_ch=64, value_ch=16, ffn_hidden=128, edge_ch=128,
+                 num_layers=kw["num_layers"], norm_type="rms_norm_sh", cutoff=12.0, max_neighbors=20)
+    data = synthetic.oc20_batch(1, seed=999)
+    t0 = time.perf_counter()
+    ei, dist, vec = O.radius_graph_pbc_fairchem(data["pos"], data["cell"], data["batch"], data["natoms"], 12.0, 20)
+    energy, forces = O.oc20_forward(P, hp, data["atomic_numbers"], data["batch"], 1, ei, dist, vec,
+                                    torch.rand(vec.shape) - 0.5)
+    losses(energy, forces, data).backward()
+    dt = time.perf_counter() - t0
+    return {"value": 1.0 / dt, "unit": UNIT, "cores": cores, "kind": "port",
+            "sample": f"1 structure (80 atoms, {ei.shape[1]} edges) forward+backward through oracle/eqv2_oracle.py, {dt:.1f} s"}
+
+
+if __name__ == "__main__":
+    a = parse()
+    if a.impl == "reference":
+        run_reference(a)
+    else:
+        run_b200(a)

@@ -119,10 +119,42 @@ def stream_ptr():
     return torch.cuda.current_stream().cuda_stream
 
 
-def call(name, *args, n_kernels=1):
+_timing = {"on": False, "records": []}
+
+
+def start_kernel_timing():
+    """Measurement aid (bench.py): bracket every C-ABI call with CUDA events on the launching stream
+    and remember the algorithmic work the caller attached (`work=(flops, bytes)`)."""
+    _timing["on"] = True
+    _timing["records"] = []
+
+
+def stop_kernel_timing():
+    """-> {entry point: dict(ms, calls, flops, bytes)} (synchronises)."""
+    _timing["on"] = False
+    torch.cuda.synchronize()
+    out = {}
+    for name, e0, e1, work in _timing["records"]:
+        r = out.setdefault(name, dict(ms=0.0, calls=0, flops=0.0, bytes=0.0))
+        r["ms"] += e0.elapsed_time(e1)
+        r["calls"] += 1
+        if work is not None:
+            r["flops"] += work[0]
+            r["bytes"] += work[1]
+    _timing["records"] = []
+    return out
+
+
+def call(name, *args, n_kernels=1, work=None):
     fn = getattr(lib(), name)
+    if _timing["on"]:
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
     rc = fn(*args)
     if rc != 0:
         raise Eqv2Error(f"{name} failed ({rc}): {lib().eqv2_last_error().decode()}")
+    if _timing["on"]:
+        e1.record()
+        _timing["records"].append((name, e0, e1, work))
     _state["launches"] += n_kernels
     return rc

@@ -312,7 +312,10 @@ def run_gemm(descs, split_k=1):
     n = len(descs)
     assert 1 <= n <= _lib.MAX_GEMM_GROUPS
     arr = (_lib.GemmDesc * n)(*descs)
-    _lib.call("eqv2_gemm_f32", ctypes.cast(arr, ctypes.c_void_p), n, int(split_k), _lib.stream_ptr())
+    flops = sum(2.0 * d.M * d.N * d.K for d in descs)
+    nbytes = sum(4.0 * (d.M * d.K + d.K * d.N + d.M * d.N) for d in descs)
+    _lib.call("eqv2_gemm_f32", ctypes.cast(arr, ctypes.c_void_p), n, int(split_k), _lib.stream_ptr(),
+              work=(flops, nbytes))
 
 
 class LinearFn(torch.autograd.Function):
