@@ -34,6 +34,7 @@ MAX_GEMM_GROUPS = 10
 _PROTOS = {
     "eqv2_abi_version": [],
     "eqv2_gemm_f32": [P, I, I, P],
+    "eqv2_gemm_tc": [P, I, I, I, P],
     "eqv2_wigner_from_rot": [P, P, P, L, I, P],
     "eqv2_gather_rotate_fwd": [P, P, P, P, P, P, P, P, L, I, I, I, I, I, P],
     "eqv2_gather_rotate_bwd": [P, P, P, P, P, P, P, P, P, P, P, P, L, I, I, I, I, I, P],
@@ -60,7 +61,7 @@ _PROTOS = {
     "eqv2_segment_sum_bwd": [P, P, P, L, P],
 }
 # entry points that only exist in the real (nvcc-built) library
-_OPTIONAL = set()
+_OPTIONAL = {"eqv2_gemm_tc"}   # inline-PTX kernels: not part of the CPU emulator build
 
 _state = {"lib": None, "launches": 0}
 

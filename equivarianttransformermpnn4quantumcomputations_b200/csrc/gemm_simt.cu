@@ -25,8 +25,11 @@ struct GemmParams {
   int split_k;
 };
 
+// rows-per-block >= 2^31 marks a plain row-major operand: no 64-bit division on the hot path
 __device__ __forceinline__ long long row_off(long long r, long long rpb, long long bs, long long ld) {
-  return (r / rpb) * bs + (r % rpb) * ld;
+  if (rpb >= (1ll << 31)) return r * ld;
+  const int q = (int)r / (int)rpb;
+  return (long long)q * bs + (long long)((int)r - q * (int)rpb) * ld;
 }
 
 __global__ void __launch_bounds__(NT) gemm_simt_kernel(const GemmParams P) {
@@ -36,6 +39,7 @@ __global__ void __launch_bounds__(NT) gemm_simt_kernel(const GemmParams P) {
   const eqv2_gemm_desc& d = P.g[gi];
   const int m0 = blockIdx.y * BM, n0 = blockIdx.x * BN;
   const bool active = (m0 < d.M) && (n0 < d.N);
+  if (!active) return;   // CTA-uniform: the grid is sized for the largest group
 
   __shared__ float As[2][BK][BM + PAD];
   __shared__ float Bs[2][BK][BN + PAD];

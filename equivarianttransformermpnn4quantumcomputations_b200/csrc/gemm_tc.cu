@@ -1,0 +1,372 @@
+// Grouped GEMM on the 5th-generation tensor cores (tcgen05.mma kind::tf32, accumulators in TMEM)
+// for the dense contraction of the path: the SO(2) convolution blocks (so2_ops.py:150-185), their
+// dgrad / wgrad, and the radial-MLP linears (radial_function.py:29).
+//
+//   C[M,N] (+)= opA[M,K] * opB[K,N] (+ bias[N])         fp32 in, fp32 out
+//
+// Precision modes
+//   mode 0 "3xTF32": every operand value v is split in registers into hi = rna_tf32(v) and
+//           lo = rna_tf32(v - hi); the tensor core accumulates hi*hi + lo*hi + hi*lo in fp32 (TMEM).
+//           The dropped lo*lo term and the rounding of lo are O(2^-22) relative -- fp32-class accuracy,
+//           which is what the 1e-5 parity bound of the fp32 mode needs.
+//   mode 1 "1xTF32": hi*hi only (separately stated tolerance).
+//
+// CTA = one 128 x 128 output tile.  Warp roles (288 threads):
+//   warps 0-3  producers of the A tile (128 rows x 32 k per stage)        global -> registers -> split -> smem
+//   warps 4-7  producers of the B tile (128 rows x 32 k per stage)
+//   warp  8    TMEM allocation + single-thread tcgen05.mma issue + tcgen05.commit
+//   warps 0-7  epilogue after the main loop (tcgen05.ld -> bias / accumulate -> global)
+// Operands go through registers (not TMA) on purpose: the hi/lo split is an elementwise transform of
+// the tile, and both K-contiguous ([rows,K]) and row-contiguous ([K,rows]: dgrad weights, wgrad
+// operands) sources are written straight into the canonical SWIZZLE_128B shared-memory layouts
+// (K-major resp. MN-major) that the UMMA descriptors name -- no transposed copies in HBM.
+// 3-stage mbarrier ring: full[s] (producers -> MMA), empty[s] (tcgen05.commit -> producers),
+// accumulator-ready barrier (last commit -> epilogue).
+#include "common.cuh"
+
+#ifndef EQV2_CPU_EMU
+
+namespace {
+
+constexpr int BM = 128, BN = 128, BK = 32;         // BK fp32 = 128 bytes = one swizzle row
+constexpr int STAGES = 3;
+constexpr int TILE_BYTES = BM * BK * 4;            // 16 KB per operand tile
+constexpr int STAGE_BYTES = 4 * TILE_BYTES;        // A_hi, A_lo, B_hi, B_lo
+constexpr int NUM_PRODUCER_WARPS = 8;
+constexpr int NUM_THREADS = (NUM_PRODUCER_WARPS + 1) * 32;
+constexpr int TMEM_COLS = 128;
+constexpr size_t SMEM_BYTES = (size_t)STAGES * STAGE_BYTES + 1024 /*align*/ + 256 /*barriers*/;
+
+struct TcGroup {
+  const float* A;
+  const float* B;
+  float* C;
+  const float* bias;
+  int M, N, K;
+  long long lda, ldb, ldc;
+  int a_mn;        // 1: A stored [K,M] (row index contiguous)   0: [M,K]
+  int b_mn;        // 1: B stored [K,N]                          0: [N,K]
+  int accumulate;  // C += result
+  int tiles_m, tiles_n;
+  int tile_start;  // first linear tile of this group
+};
+
+struct TcParams {
+  TcGroup g[EQV2_GEMM_MAX_GROUPS];
+  int ngroups;
+  int split_k;
+  int mode;
+};
+
+// ---- PTX wrappers --------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n"
+      "WAIT_LOOP:\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+      "@p bra.uni WAIT_DONE;\n\t"
+      "bra.uni WAIT_LOOP;\n"
+      "WAIT_DONE:\n\t}\n" ::"r"(bar), "r"(parity)
+      : "memory");
+}
+__device__ __forceinline__ void fence_proxy_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+
+__device__ __forceinline__ void tmem_alloc(uint32_t dst_smem, uint32_t ncols) {
+  asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(dst_smem), "r"(ncols) : "memory");
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t ncols) {
+  asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
+}
+__device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t acc) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}\n" ::"r"(tmem_d),
+      "l"(adesc), "l"(bdesc), "r"(idesc), "r"(acc)
+      : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint32_t bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t* r) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
+        "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
+        "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+      : "r"(taddr)
+      : "memory");
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+
+__device__ __forceinline__ float tf32_rna(float v) {
+  uint32_t o;
+  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(o) : "f"(v));
+  return __uint_as_float(o);
+}
+
+// ---- descriptors ---------------------------------------------------------------------------------
+// SM100 shared-memory matrix descriptor: start>>4 [0,14) | LBO>>4 [16,30) | SBO>>4 [32,46) | version=1 [46,48)
+// | layout type [61,64) (2 = SWIZZLE_128B).
+// K-major tile  [rows][32 fp32]: 8-row groups are 1024 B apart (SBO); LBO unused (1).
+// MN-major tile: atom = 32 rows (128 B contiguous) x 8 k; atoms along rows are LBO = 1024 B apart,
+//               groups of 8 k are SBO = 4096 B apart.
+__device__ __forceinline__ uint64_t make_desc(uint32_t smem_addr, bool mn_major) {
+  const uint64_t lbo = mn_major ? (1024u >> 4) : 1u;
+  const uint64_t sbo = mn_major ? (4096u >> 4) : (1024u >> 4);
+  return (uint64_t)((smem_addr >> 4) & 0x3FFFu) | (lbo << 16) | (sbo << 32) | (1ull << 46) | (2ull << 61);
+}
+// instruction descriptor: D fp32 (1<<4), A/B tf32 (2<<7, 2<<10), majors (bits 15/16), N>>3 (17..22), M>>4 (24..28)
+__device__ __forceinline__ uint32_t make_idesc(bool a_mn, bool b_mn) {
+  return (1u << 4) | (2u << 7) | (2u << 10) | ((a_mn ? 1u : 0u) << 15) | ((b_mn ? 1u : 0u) << 16) |
+         ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
+}
+
+// ---- producer: one operand tile (128 rows x 32 k) into smem (hi and lo) ----------------------------
+// tid in [0,128).  src element (row, k) = mn ? src[k*ld + row] : src[row*ld + k].
+__device__ __forceinline__ void produce_tile(const float* __restrict__ src, long long ld, int mn, int row0, int rows,
+                                             int k0, int K, unsigned char* hi, unsigned char* lo, int tid, bool want_lo) {
+#pragma unroll
+  for (int it = 0; it < 8; ++it) {
+    const int idx = it * 128 + tid;
+    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+    uint32_t off;
+    if (!mn) {
+      const int r = idx >> 3, c = idx & 7;                  // 8 x 16 B chunks per row
+      const int gr = row0 + r, gk = k0 + c * 4;
+      if (gr < rows && gk < K) v = __ldg(reinterpret_cast<const float4*>(src + (long long)gr * ld + gk));
+      off = (uint32_t)(r * 128 + ((c ^ (r & 7)) << 4));
+    } else {
+      const int kk = idx >> 5, c32 = idx & 31;              // 32 x 16 B chunks (128 rows) per k
+      const int gr = row0 + c32 * 4, gk = k0 + kk;
+      if (gk < K) {
+        const float* p = src + (long long)gk * ld + gr;
+        if (gr + 3 < rows) v = __ldg(reinterpret_cast<const float4*>(p));
+        else {
+          if (gr < rows) v.x = __ldg(p);
+          if (gr + 1 < rows) v.y = __ldg(p + 1);
+          if (gr + 2 < rows) v.z = __ldg(p + 2);
+        }
+      }
+      // atom (rows/32, k/8): 1024 B; inside: k row (128 B) x 8 chunks, chunk ^= (k & 7)
+      const int rb = c32 >> 3, c = c32 & 7, k8 = kk & 7, kb = kk >> 3;
+      off = (uint32_t)(kb * 4096 + rb * 1024 + k8 * 128 + ((c ^ k8) << 4));
+    }
+    float4 h;
+    h.x = tf32_rna(v.x); h.y = tf32_rna(v.y); h.z = tf32_rna(v.z); h.w = tf32_rna(v.w);
+    *reinterpret_cast<float4*>(hi + off) = h;
+    if (want_lo) {
+      float4 l;
+      l.x = tf32_rna(v.x - h.x); l.y = tf32_rna(v.y - h.y); l.z = tf32_rna(v.z - h.z); l.w = tf32_rna(v.w - h.w);
+      *reinterpret_cast<float4*>(lo + off) = l;
+    }
+  }
+}
+
+__global__ void __launch_bounds__(NUM_THREADS, 1) gemm_tc_kernel(const __grid_constant__ TcParams P) {
+  extern __shared__ unsigned char smem_raw[];
+  const uint32_t raw_addr = smem_u32(smem_raw);
+  const uint32_t pad = (1024u - (raw_addr & 1023u)) & 1023u;
+  unsigned char* tiles = smem_raw + pad;                                    // STAGES * STAGE_BYTES, 1024-aligned
+  uint64_t* bars = reinterpret_cast<uint64_t*>(tiles + (size_t)STAGES * STAGE_BYTES);
+  // bars[0..S) full, bars[S..2S) empty, bars[2S] accumulator ready, then the TMEM base address word
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * STAGES + 1);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+  // ---- which tile ----
+  const int tile_lin = blockIdx.x / P.split_k;
+  const int ks = blockIdx.x % P.split_k;
+  int gi = 0;
+#pragma unroll 1
+  for (int i = 1; i < P.ngroups; ++i)
+    if (tile_lin >= P.g[i].tile_start) gi = i;
+  const TcGroup& G = P.g[gi];
+  const int t = tile_lin - G.tile_start;
+  const int tm = t % G.tiles_m, tn = t / G.tiles_m;      // m fastest: concurrent CTAs share the B tile
+  const int m0 = tm * BM, n0 = tn * BN;
+  const int nkb_all = (G.K + BK - 1) / BK;
+  const int per = (nkb_all + P.split_k - 1) / P.split_k;
+  const int kb0 = ks * per, kb1 = min(nkb_all, kb0 + per);
+  const int nkb = max(0, kb1 - kb0);
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < STAGES; ++s) {
+      mbar_init(smem_u32(&bars[s]), NUM_PRODUCER_WARPS);
+      mbar_init(smem_u32(&bars[STAGES + s]), 1);
+    }
+    mbar_init(smem_u32(&bars[2 * STAGES]), 1);
+    fence_barrier_init();
+  }
+  if (warp == NUM_PRODUCER_WARPS) tmem_alloc(smem_u32(tmem_slot), TMEM_COLS);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  const bool want_lo = (P.mode == 0);
+
+  if (warp < NUM_PRODUCER_WARPS) {
+    // ================= producers =================
+    const bool isB = warp >= 4;
+    const int tid = threadIdx.x & 127;
+    const float* src = isB ? G.B : G.A;
+    const long long ld = isB ? G.ldb : G.lda;
+    const int mn = isB ? G.b_mn : G.a_mn;
+    const int row0 = isB ? n0 : m0;
+    const int rows = isB ? G.N : G.M;
+    for (int i = 0; i < nkb; ++i) {
+      const int s = i % STAGES, round = i / STAGES;
+      mbar_wait(smem_u32(&bars[STAGES + s]), (uint32_t)((round & 1) ^ 1));
+      unsigned char* st = tiles + (size_t)s * STAGE_BYTES + (isB ? 2 * TILE_BYTES : 0);
+      produce_tile(src, ld, mn, row0, rows, (kb0 + i) * BK, G.K, st, st + TILE_BYTES, tid, want_lo);
+      fence_proxy_async_smem();      // generic-proxy stores -> visible to the tensor core (async proxy)
+      __syncwarp();
+      if (lane == 0) mbar_arrive(smem_u32(&bars[s]));
+    }
+  } else {
+    // ================= MMA issuer (one thread) =================
+    if (lane == 0) {
+      const uint32_t idesc = make_idesc(G.a_mn != 0, G.b_mn != 0);
+      const uint32_t a_step = G.a_mn ? 4096u : 32u;       // bytes per K=8 slice
+      const uint32_t b_step = G.b_mn ? 4096u : 32u;
+      for (int i = 0; i < nkb; ++i) {
+        const int s = i % STAGES, round = i / STAGES;
+        mbar_wait(smem_u32(&bars[s]), (uint32_t)(round & 1));
+        tc_fence_after();
+        const uint32_t base = smem_u32(tiles + (size_t)s * STAGE_BYTES);
+        const uint32_t a_hi = base, a_lo = base + TILE_BYTES, b_hi = base + 2 * TILE_BYTES, b_lo = base + 3 * TILE_BYTES;
+#pragma unroll
+        for (int k = 0; k < BK / 8; ++k) {
+          const uint64_t dah = make_desc(a_hi + k * a_step, G.a_mn != 0);
+          const uint64_t dbh = make_desc(b_hi + k * b_step, G.b_mn != 0);
+          umma_tf32(tmem_base, dah, dbh, idesc, (i > 0 || k > 0) ? 1u : 0u);
+          if (want_lo) {
+            const uint64_t dal = make_desc(a_lo + k * a_step, G.a_mn != 0);
+            const uint64_t dbl = make_desc(b_lo + k * b_step, G.b_mn != 0);
+            umma_tf32(tmem_base, dal, dbh, idesc, 1u);
+            umma_tf32(tmem_base, dah, dbl, idesc, 1u);
+          }
+        }
+        umma_commit(smem_u32(&bars[STAGES + s]));          // frees the stage when these MMAs retire
+      }
+      umma_commit(smem_u32(&bars[2 * STAGES]));            // accumulator complete
+    }
+    __syncwarp();
+  }
+
+  // ================= epilogue (warps 0-7) =================
+  if (warp < NUM_PRODUCER_WARPS && nkb > 0) {
+    mbar_wait(smem_u32(&bars[2 * STAGES]), 0u);
+    tc_fence_after();
+    const int q = warp & 3, half = warp >> 2;              // TMEM lane quarter; column half
+    const int row = m0 + q * 32 + lane;
+    const bool atomic = P.split_k > 1;
+#pragma unroll 1
+    for (int cc = 0; cc < 2; ++cc) {
+      const int col0 = half * 64 + cc * 32;
+      uint32_t r[32];
+      tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)col0, r);
+      if (row < G.M) {
+        float* crow = G.C + (long long)row * G.ldc + n0 + col0;
+        const int ncol = min(32, G.N - n0 - col0);
+        const bool vec = (ncol == 32) && ((reinterpret_cast<uintptr_t>(crow) & 15) == 0) && !atomic;
+        if (vec) {
+#pragma unroll
+          for (int c = 0; c < 32; c += 4) {
+            float4 o = make_float4(__uint_as_float(r[c]), __uint_as_float(r[c + 1]), __uint_as_float(r[c + 2]),
+                                   __uint_as_float(r[c + 3]));
+            if (G.bias != nullptr) {
+              const float4 b = __ldg(reinterpret_cast<const float4*>(G.bias + n0 + col0 + c));
+              o.x += b.x; o.y += b.y; o.z += b.z; o.w += b.w;
+            }
+            if (G.accumulate) {
+              const float4 p = *reinterpret_cast<const float4*>(crow + c);
+              o.x += p.x; o.y += p.y; o.z += p.z; o.w += p.w;
+            }
+            *reinterpret_cast<float4*>(crow + c) = o;
+          }
+        } else {
+#pragma unroll
+          for (int c = 0; c < 32; ++c) {
+            if (c < ncol) {
+              float o = __uint_as_float(r[c]);
+              if (G.bias != nullptr && ks == 0) o += __ldg(G.bias + n0 + col0 + c);
+              if (atomic) atomicAdd(crow + c, o);
+              else if (G.accumulate) crow[c] += o;
+              else crow[c] = o;
+            }
+          }
+        }
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == NUM_PRODUCER_WARPS) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, TMEM_COLS);
+  }
+}
+
+}  // namespace
+
+extern "C" int eqv2_gemm_tc(const eqv2_gemm_desc* descs, int ngroups, int split_k, int mode, void* stream) {
+  EQV2_REQUIRE(ngroups >= 1 && ngroups <= EQV2_GEMM_MAX_GROUPS, "eqv2_gemm_tc: ngroups=%d out of range", ngroups);
+  EQV2_REQUIRE(split_k >= 1 && (mode == 0 || mode == 1), "eqv2_gemm_tc: bad split_k/mode");
+  TcParams P;
+  memset(&P, 0, sizeof(P));
+  int tiles = 0;
+  for (int i = 0; i < ngroups; ++i) {
+    const eqv2_gemm_desc& d = descs[i];
+    EQV2_REQUIRE(d.A && d.B && d.C, "eqv2_gemm_tc: null operand in group %d", i);
+    EQV2_REQUIRE(d.a_rpb >= (1ll << 31) && d.b_rpb >= (1ll << 31) && d.c_rpb >= (1ll << 31),
+                 "eqv2_gemm_tc: two-level strided operands are served by eqv2_gemm_f32");
+    EQV2_REQUIRE((d.a_ld % 4) == 0 && (d.b_ld % 4) == 0 && (((uintptr_t)d.A | (uintptr_t)d.B) & 15) == 0,
+                 "eqv2_gemm_tc: operands must be 16-byte aligned with leading dimensions multiple of 4");
+    // the contiguous dimension is read in float4 units
+    EQV2_REQUIRE(d.transA ? true : (d.K % 4) == 0, "eqv2_gemm_tc: K must be a multiple of 4 for K-contiguous A");
+    EQV2_REQUIRE(d.transB ? (d.K % 4) == 0 : true, "eqv2_gemm_tc: K must be a multiple of 4 for K-contiguous B");
+    TcGroup& g = P.g[i];
+    g.A = d.A; g.B = d.B; g.C = d.C; g.bias = d.bias;
+    g.M = d.M; g.N = d.N; g.K = d.K;
+    g.lda = d.a_ld; g.ldb = d.b_ld; g.ldc = d.c_ld;
+    g.a_mn = d.transA ? 1 : 0;
+    g.b_mn = d.transB ? 0 : 1;
+    g.accumulate = d.accumulate;
+    g.tiles_m = (d.M + BM - 1) / BM;
+    g.tiles_n = (d.N + BN - 1) / BN;
+    g.tile_start = tiles;
+    tiles += g.tiles_m * g.tiles_n;
+  }
+  if (tiles == 0) return 0;
+  P.ngroups = ngroups;
+  P.split_k = split_k;
+  P.mode = mode;
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaError_t e = cudaFuncSetAttribute(gemm_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_BYTES);
+    EQV2_REQUIRE(e == cudaSuccess, "eqv2_gemm_tc: cannot reserve %zu B of shared memory: %s", SMEM_BYTES,
+                 cudaGetErrorString(e));
+    attr_set = true;
+  }
+  gemm_tc_kernel<<<dim3((unsigned)(tiles * split_k)), dim3(NUM_THREADS), SMEM_BYTES, (cudaStream_t)stream>>>(P);
+  EQV2_CHECK_LAUNCH("eqv2_gemm_tc");
+  return 0;
+}
+
+#endif  // EQV2_CPU_EMU

@@ -263,12 +263,17 @@ def segment_sum_nodes(values, batch, num_graphs):
 # ----------------------------------------------------------------------------------------------
 # GEMM engine
 # ----------------------------------------------------------------------------------------------
-_GEMM_MODE = {"mode": "fp32"}
+_GEMM_MODE = {"mode": "tf32x3"}
 
 
 def set_gemm_mode(mode):
-    """'fp32' (exact FFMA engine, parity mode) | 'tf32x3' | 'tf32' | 'bf16' (tcgen05 engines)."""
-    assert mode in ("fp32", "tf32x3", "tf32", "bf16")
+    """Engine for the dense edge-level contractions:
+      'tf32x3' (default): tcgen05 tensor cores with the 3xTF32 hi/lo split -- fp32-class accuracy,
+      'tf32'            : tcgen05, single TF32 pass (separately stated tolerance),
+      'fp32'            : exact FFMA engine for everything.
+    Problems the tensor-core engine cannot address (two-level strided degree slabs, unaligned
+    operands) always run on the FFMA engine."""
+    assert mode in ("fp32", "tf32x3", "tf32")
     _GEMM_MODE["mode"] = mode
 
 
@@ -308,14 +313,30 @@ def _pick_split(descs, reduce_dim_large):
     return int(max(1, min(64, 296 // max(tiles, 1), kmax // 512)))
 
 
+def _tc_ok(d):
+    """Can the tensor-core engine address this problem? (see eqv2_gemm_tc in include/eqv2_b200.h)"""
+    if min(d.a_rpb, d.b_rpb, d.c_rpb) < (1 << 31):
+        return False
+    if d.a_ld % 4 or d.b_ld % 4 or (d.A % 16) or (d.B % 16):
+        return False
+    if (not d.transA and d.K % 4) or (d.transB and d.K % 4):
+        return False
+    return d.M * d.N * d.K >= (1 << 21)      # tiny problems are launch-bound either way
+
+
 def run_gemm(descs, split_k=1):
     n = len(descs)
     assert 1 <= n <= _lib.MAX_GEMM_GROUPS
     arr = (_lib.GemmDesc * n)(*descs)
     flops = sum(2.0 * d.M * d.N * d.K for d in descs)
     nbytes = sum(4.0 * (d.M * d.K + d.K * d.N + d.M * d.N) for d in descs)
-    _lib.call("eqv2_gemm_f32", ctypes.cast(arr, ctypes.c_void_p), n, int(split_k), _lib.stream_ptr(),
-              work=(flops, nbytes))
+    mode = _GEMM_MODE["mode"]
+    if mode != "fp32" and all(_tc_ok(d) for d in descs):
+        _lib.call("eqv2_gemm_tc", ctypes.cast(arr, ctypes.c_void_p), n, int(split_k), 0 if mode == "tf32x3" else 1,
+                  _lib.stream_ptr(), work=(flops, nbytes))
+    else:
+        _lib.call("eqv2_gemm_f32", ctypes.cast(arr, ctypes.c_void_p), n, int(split_k), _lib.stream_ptr(),
+                  work=(flops, nbytes))
 
 
 class LinearFn(torch.autograd.Function):

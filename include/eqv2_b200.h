@@ -41,8 +41,12 @@ typedef struct {
   int accumulate; /* C += (ignored when split_k > 1: C must then be pre-initialised) */
 } eqv2_gemm_desc;
 
-/* exact fp32 (FFMA) engine */
+/* exact fp32 (FFMA) engine: any operand addressing */
 int eqv2_gemm_f32(const eqv2_gemm_desc* descs, int ngroups, int split_k, void* stream);
+/* tensor-core engine (tcgen05.mma kind::tf32, TMEM accumulators): plain row-major operands only
+ * (rpb >= 2^31), 16-byte aligned, leading dimensions multiple of 4.
+ * mode 0 = 3xTF32 split (fp32-class accuracy), mode 1 = 1xTF32. */
+int eqv2_gemm_tc(const eqv2_gemm_desc* descs, int ngroups, int split_k, int mode, void* stream);
 
 /* ---- Wigner-D rotation (so3.py:343-387,499-545; transformer_block.py:250-275,321-331) ---- */
 int eqv2_wigner_from_rot(const float* rot /*[E,3,3]*/, const float* Jd /*packed blocks*/,

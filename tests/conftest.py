@@ -50,16 +50,19 @@ def backend(request, monkeypatch):
         monkeypatch.setitem(_lib._state, "lib", _lib._bind(path))
         monkeypatch.setattr(_lib, "check_device", lambda *t: None)
         monkeypatch.setattr(_lib, "stream_ptr", lambda: None)
+        ops.set_gemm_mode("fp32")           # the tcgen05 engine is inline PTX: GPU only
     else:
         if not torch.cuda.is_available():
             pytest.skip("no CUDA device")
         monkeypatch.setitem(_lib._state, "lib", None)      # force the real library
         _lib.lib()
+        ops.set_gemm_mode("tf32x3")         # the product default
     ops._plan_cache.clear()
     for lay in ops.CoeffLayout._cache.values():
         lay._dev.clear()
     yield Backend(request.param)
     ops._plan_cache.clear()
+    ops.set_gemm_mode("tf32x3")
 
 
 def golden(name):

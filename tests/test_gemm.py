@@ -1,0 +1,80 @@
+"""GEMM engines vs an fp64 reference: the exact FFMA engine (emulator + GPU) and the tcgen05 tensor-core
+engine (GPU only; 3xTF32 must stay fp32-class, 1xTF32 within its stated 2e-3)."""
+import ctypes
+
+import pytest
+import torch
+
+from helpers import pkg
+
+
+def _run(ops, _lib, backend, M, N, K, transA, transB, engine, bias=False, accumulate=False, split_k=1, groups=1):
+    gen = torch.Generator().manual_seed(M * 7 + N * 3 + K + 2 * transA + transB)
+    descs, refs, outs = [], [], []
+    keep = []
+    for g in range(groups):
+        A = torch.randn((K, M) if transA else (M, K), generator=gen)
+        B = torch.randn((N, K) if transB else (K, N), generator=gen)
+        b = torch.randn(N, generator=gen) if bias else None
+        C0 = torch.randn(M, N, generator=gen) if accumulate else torch.zeros(M, N)
+        ref = (A.double().t() if transA else A.double()) @ (B.double().t() if transB else B.double())
+        if bias:
+            ref = ref + b.double()
+        if accumulate:
+            ref = ref + C0.double()
+        Ad, Bd, Cd = backend.to(A), backend.to(B), backend.to(C0.clone())
+        bd = backend.to(b) if bias else None
+        keep += [Ad, Bd, Cd, bd]
+        descs.append(ops._desc(Ad, Bd, Cd, bd, M, N, K, transA, transB, ops._plain(A.shape[1]), ops._plain(B.shape[1]),
+                               ops._plain(N), accumulate=int(accumulate and split_k == 1)))
+        refs.append(ref)
+        outs.append(Cd)
+    arr = (_lib.GemmDesc * groups)(*descs)
+    if engine == "fp32":
+        _lib.call("eqv2_gemm_f32", ctypes.cast(arr, ctypes.c_void_p), groups, split_k, _lib.stream_ptr())
+    else:
+        for d in descs:
+            assert ops._tc_ok(d) or d.M * d.N * d.K < (1 << 21)
+        _lib.call("eqv2_gemm_tc", ctypes.cast(arr, ctypes.c_void_p), groups, split_k, 0 if engine == "tf32x3" else 1,
+                  _lib.stream_ptr())
+    errs = []
+    for ref, out in zip(refs, outs):
+        errs.append(float((out.double().cpu() - ref).abs().max() / ref.abs().max()))
+    return max(errs)
+
+
+SHAPES = [(128, 128, 32), (256, 128, 64), (200, 136, 96), (77, 40, 36), (384, 256, 1792), (1000, 544, 960)]
+
+
+@pytest.mark.parametrize("M,N,K", SHAPES[:4])
+@pytest.mark.parametrize("tA,tB", [(0, 1), (0, 0), (1, 0), (1, 1)])
+def test_ffma_engine(backend, M, N, K, tA, tB):
+    ops, _lib = pkg("ops"), pkg("_lib")
+    assert _run(ops, _lib, backend, M, N, K, tA, tB, "fp32", bias=True) < 2e-6
+
+
+def test_ffma_engine_split_k_and_groups(backend):
+    ops, _lib = pkg("ops"), pkg("_lib")
+    assert _run(ops, _lib, backend, 96, 72, 300, 1, 0, "fp32", split_k=3, groups=2) < 2e-6
+    assert _run(ops, _lib, backend, 96, 72, 64, 0, 1, "fp32", accumulate=True) < 2e-6
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("M,N,K", SHAPES)
+@pytest.mark.parametrize("tA,tB", [(0, 1), (0, 0), (1, 0), (1, 1)])
+def test_tensor_core_engine_3xtf32(M, N, K, tA, tB):
+    from conftest import Backend
+    ops, _lib = pkg("ops"), pkg("_lib")
+    err = _run(ops, _lib, Backend("cuda"), M, N, K, tA, tB, "tf32x3", bias=True)
+    assert err < 3e-6, err
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("tA,tB", [(0, 1), (1, 0)])
+def test_tensor_core_engine_1xtf32_and_options(tA, tB):
+    from conftest import Backend
+    ops, _lib = pkg("ops"), pkg("_lib")
+    be = Backend("cuda")
+    assert _run(ops, _lib, be, 384, 256, 1792, tA, tB, "tf32") < 2e-3
+    assert _run(ops, _lib, be, 300, 200, 4096, tA, tB, "tf32x3", split_k=4, groups=3) < 3e-6
+    assert _run(ops, _lib, be, 300, 200, 512, tA, tB, "tf32x3", accumulate=True, bias=True) < 3e-6

@@ -60,3 +60,25 @@ def test_qm9_small_matches_reference(backend):
     w = torch.linspace(-1, 1, pred.numel(), device=pred.device).view_as(pred)
     (pred * w).sum().backward()
     _check_grads(model, fx)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("mode,tol", [("fp32", 1e-5), ("tf32", 5e-3)])
+def test_oc20_small_other_gemm_modes(mode, tol):
+    """fp32 = exact FFMA engine everywhere; tf32 = single-pass TF32 tensor cores (stated tolerance 5e-3)."""
+    from conftest import Backend
+    from helpers import pkg
+    ops = pkg("ops")
+    be = Backend("cuda")
+    fx = golden("oc20_small_rms_norm_sh.pt")
+    ops.set_gemm_mode(mode)
+    try:
+        model = build_oc20(fx["hyper"], be.device)
+        load_params(model, fx["params"])
+        data = _graph_inputs(fx, be)
+        with fixed_rand_like(fx["rand_vec"] + 0.5):
+            energy, forces = model(data)
+        assert rel_err(energy, fx["energy"]) < tol
+        assert rel_err(forces, fx["forces"]) < tol
+    finally:
+        ops.set_gemm_mode("tf32x3")
