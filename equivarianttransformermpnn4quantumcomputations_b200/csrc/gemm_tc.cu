@@ -6,22 +6,30 @@
 //
 // Precision modes
 //   mode 0 "3xTF32": every operand value v is split in registers into hi = rna_tf32(v) and
-//           lo = rna_tf32(v - hi); the tensor core accumulates hi*hi + lo*hi + hi*lo in fp32 (TMEM).
-//           The dropped lo*lo term and the rounding of lo are O(2^-22) relative -- fp32-class accuracy,
-//           which is what the 1e-5 parity bound of the fp32 mode needs.
-//   mode 1 "1xTF32": hi*hi only (separately stated tolerance).
+//           lo = rna_tf32(v - hi); the tensor core computes hi*hi, lo*hi and hi*lo (the dropped lo*lo term
+//           and the rounding of lo are O(2^-22) relative).
+//           MEASURED on B200 (scripts/gemm_accuracy.py): every tcgen05.mma accumulation into TMEM truncates
+//           (round-toward-zero at 24 bits, ~5e-8 relative per instruction, systematic), so a plain K-long
+//           chain is 1e-5 off at K ~ 2000.  The kernel therefore keeps the hi*hi chain short: it accumulates
+//           CHUNK k-blocks (8 instructions) into one of two ping-pong TMEM accumulators and dedicated
+//           promotion warps add each finished chunk into fp32 registers (round-to-nearest) while the tensor
+//           core works on the other buffer.  The small lo terms use a third TMEM accumulator for the whole K
+//           (their truncation is 2^-11 times smaller).  Result: fp32-class accuracy, as the 1e-5 parity
+//           bound of the fp32 mode needs.
+//   mode 1 "1xTF32": hi*hi only, one TMEM chain, no promotion (separately stated tolerance).
 //
-// CTA = one 128 x 128 output tile.  Warp roles (288 threads):
-//   warps 0-3  producers of the A tile (128 rows x 32 k per stage)        global -> registers -> split -> smem
-//   warps 4-7  producers of the B tile (128 rows x 32 k per stage)
-//   warp  8    TMEM allocation + single-thread tcgen05.mma issue + tcgen05.commit
-//   warps 0-7  epilogue after the main loop (tcgen05.ld -> bias / accumulate -> global)
+// CTA = one 128 x 128 output tile.  Warp roles (416 threads):
+//   warps 0-3   producers of the A and B tiles (128 rows x 32 k each per stage)
+//               global -> registers -> hi/lo split -> swizzled smem
+//   warps 4-11  promotion / epilogue: tcgen05.ld of finished chunks -> register accumulators -> bias /
+//               accumulate -> global
+//   warp  12    TMEM allocation + single-thread tcgen05.mma issue + tcgen05.commit
 // Operands go through registers (not TMA) on purpose: the hi/lo split is an elementwise transform of
 // the tile, and both K-contiguous ([rows,K]) and row-contiguous ([K,rows]: dgrad weights, wgrad
 // operands) sources are written straight into the canonical SWIZZLE_128B shared-memory layouts
 // (K-major resp. MN-major) that the UMMA descriptors name -- no transposed copies in HBM.
-// 3-stage mbarrier ring: full[s] (producers -> MMA), empty[s] (tcgen05.commit -> producers),
-// accumulator-ready barrier (last commit -> epilogue).
+// 3-stage mbarrier ring: full[s] (producers -> MMA), empty[s] (tcgen05.commit -> producers);
+// acc_full[b] (tcgen05.commit -> promoters), acc_empty[b] (promoters -> MMA).
 #include "common.cuh"
 
 #ifndef EQV2_CPU_EMU
@@ -32,9 +40,13 @@ constexpr int BM = 128, BN = 128, BK = 32;         // BK fp32 = 128 bytes = one 
 constexpr int STAGES = 3;
 constexpr int TILE_BYTES = BM * BK * 4;            // 16 KB per operand tile
 constexpr int STAGE_BYTES = 4 * TILE_BYTES;        // A_hi, A_lo, B_hi, B_lo
-constexpr int NUM_PRODUCER_WARPS = 8;
-constexpr int NUM_THREADS = (NUM_PRODUCER_WARPS + 1) * 32;
-constexpr int TMEM_COLS = 128;
+// 13 warps = (4,3,3,3) per scheduler partition -> 128 registers per thread without spills
+constexpr int NUM_PRODUCER_WARPS = 4;              // warps 0-3
+constexpr int NUM_EPI_WARPS = 8;                   // warps 4-11 (lane quarter = warp & 3)
+constexpr int MMA_WARP = NUM_PRODUCER_WARPS + NUM_EPI_WARPS;
+constexpr int NUM_THREADS = (NUM_PRODUCER_WARPS + NUM_EPI_WARPS + 1) * 32;
+constexpr int TMEM_COLS = 512;                     // D_hi[0], D_hi[1], D_lo (128 columns each); power of two
+constexpr int CHUNK_KB = 2;                        // k-blocks per promoted hi*hi chain (8 tcgen05.mma)
 constexpr size_t SMEM_BYTES = (size_t)STAGES * STAGE_BYTES + 1024 /*align*/ + 256 /*barriers*/;
 
 struct TcGroup {
@@ -184,8 +196,12 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) gemm_tc_kernel(const __grid_co
   const uint32_t pad = (1024u - (raw_addr & 1023u)) & 1023u;
   unsigned char* tiles = smem_raw + pad;                                    // STAGES * STAGE_BYTES, 1024-aligned
   uint64_t* bars = reinterpret_cast<uint64_t*>(tiles + (size_t)STAGES * STAGE_BYTES);
-  // bars[0..S) full, bars[S..2S) empty, bars[2S] accumulator ready, then the TMEM base address word
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * STAGES + 1);
+  // bars: [0,S) full | [S,2S) empty | 2S+b acc_full[b] | 2S+2+b acc_empty[b] ; then the TMEM base address word
+  uint64_t* full = bars;
+  uint64_t* empty = bars + STAGES;
+  uint64_t* acc_full = bars + 2 * STAGES;
+  uint64_t* acc_empty = bars + 2 * STAGES + 2;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * STAGES + 4);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
@@ -204,112 +220,141 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) gemm_tc_kernel(const __grid_co
   const int per = (nkb_all + P.split_k - 1) / P.split_k;
   const int kb0 = ks * per, kb1 = min(nkb_all, kb0 + per);
   const int nkb = max(0, kb1 - kb0);
+  const bool want_lo = (P.mode == 0);
+  const int chunk = want_lo ? CHUNK_KB : max(nkb, 1);
+  const int nchunks = (nkb + chunk - 1) / chunk;
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < STAGES; ++s) {
-      mbar_init(smem_u32(&bars[s]), NUM_PRODUCER_WARPS);
-      mbar_init(smem_u32(&bars[STAGES + s]), 1);
+      mbar_init(smem_u32(&full[s]), NUM_PRODUCER_WARPS);
+      mbar_init(smem_u32(&empty[s]), 1);
     }
-    mbar_init(smem_u32(&bars[2 * STAGES]), 1);
+    for (int b = 0; b < 2; ++b) {
+      mbar_init(smem_u32(&acc_full[b]), 1);
+      mbar_init(smem_u32(&acc_empty[b]), NUM_EPI_WARPS);
+    }
     fence_barrier_init();
   }
-  if (warp == NUM_PRODUCER_WARPS) tmem_alloc(smem_u32(tmem_slot), TMEM_COLS);
+  if (warp == MMA_WARP) tmem_alloc(smem_u32(tmem_slot), TMEM_COLS);
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
-  const bool want_lo = (P.mode == 0);
+  const uint32_t tmem_lo = tmem_base + 2 * BN;
 
   if (warp < NUM_PRODUCER_WARPS) {
     // ================= producers =================
-    const bool isB = warp >= 4;
-    const int tid = threadIdx.x & 127;
-    const float* src = isB ? G.B : G.A;
-    const long long ld = isB ? G.ldb : G.lda;
-    const int mn = isB ? G.b_mn : G.a_mn;
-    const int row0 = isB ? n0 : m0;
-    const int rows = isB ? G.N : G.M;
+    const int tid = threadIdx.x;          // 0..127
     for (int i = 0; i < nkb; ++i) {
       const int s = i % STAGES, round = i / STAGES;
-      mbar_wait(smem_u32(&bars[STAGES + s]), (uint32_t)((round & 1) ^ 1));
-      unsigned char* st = tiles + (size_t)s * STAGE_BYTES + (isB ? 2 * TILE_BYTES : 0);
-      produce_tile(src, ld, mn, row0, rows, (kb0 + i) * BK, G.K, st, st + TILE_BYTES, tid, want_lo);
+      mbar_wait(smem_u32(&empty[s]), (uint32_t)((round & 1) ^ 1));
+      unsigned char* st = tiles + (size_t)s * STAGE_BYTES;
+      const int k0 = (kb0 + i) * BK;
+      produce_tile(G.A, G.lda, G.a_mn, m0, G.M, k0, G.K, st, st + TILE_BYTES, tid, want_lo);
+      produce_tile(G.B, G.ldb, G.b_mn, n0, G.N, k0, G.K, st + 2 * TILE_BYTES, st + 3 * TILE_BYTES, tid, want_lo);
       fence_proxy_async_smem();      // generic-proxy stores -> visible to the tensor core (async proxy)
       __syncwarp();
-      if (lane == 0) mbar_arrive(smem_u32(&bars[s]));
+      if (lane == 0) mbar_arrive(smem_u32(&full[s]));
     }
-  } else {
+  } else if (warp == MMA_WARP) {
     // ================= MMA issuer (one thread) =================
     if (lane == 0) {
       const uint32_t idesc = make_idesc(G.a_mn != 0, G.b_mn != 0);
       const uint32_t a_step = G.a_mn ? 4096u : 32u;       // bytes per K=8 slice
       const uint32_t b_step = G.b_mn ? 4096u : 32u;
-      for (int i = 0; i < nkb; ++i) {
-        const int s = i % STAGES, round = i / STAGES;
-        mbar_wait(smem_u32(&bars[s]), (uint32_t)(round & 1));
+      int i = 0;
+      for (int j = 0; j < nchunks; ++j) {
+        const int b = j & 1;
+        mbar_wait(smem_u32(&acc_empty[b]), (uint32_t)(((j >> 1) & 1) ^ 1));   // promoters drained this buffer
         tc_fence_after();
-        const uint32_t base = smem_u32(tiles + (size_t)s * STAGE_BYTES);
-        const uint32_t a_hi = base, a_lo = base + TILE_BYTES, b_hi = base + 2 * TILE_BYTES, b_lo = base + 3 * TILE_BYTES;
+        const uint32_t d_hi = tmem_base + (uint32_t)(b * BN);
+        const int iend = min(nkb, i + chunk);
+        for (int i0 = i; i < iend; ++i) {
+          const int s = i % STAGES, round = i / STAGES;
+          mbar_wait(smem_u32(&full[s]), (uint32_t)(round & 1));
+          tc_fence_after();
+          const uint32_t base = smem_u32(tiles + (size_t)s * STAGE_BYTES);
+          const uint32_t a_hi = base, a_lo = base + TILE_BYTES, b_hi = base + 2 * TILE_BYTES, b_lo = base + 3 * TILE_BYTES;
 #pragma unroll
-        for (int k = 0; k < BK / 8; ++k) {
-          const uint64_t dah = make_desc(a_hi + k * a_step, G.a_mn != 0);
-          const uint64_t dbh = make_desc(b_hi + k * b_step, G.b_mn != 0);
-          umma_tf32(tmem_base, dah, dbh, idesc, (i > 0 || k > 0) ? 1u : 0u);
-          if (want_lo) {
-            const uint64_t dal = make_desc(a_lo + k * a_step, G.a_mn != 0);
-            const uint64_t dbl = make_desc(b_lo + k * b_step, G.b_mn != 0);
-            umma_tf32(tmem_base, dal, dbh, idesc, 1u);
-            umma_tf32(tmem_base, dah, dbl, idesc, 1u);
+          for (int k = 0; k < BK / 8; ++k) {
+            const uint64_t dah = make_desc(a_hi + k * a_step, G.a_mn != 0);
+            const uint64_t dbh = make_desc(b_hi + k * b_step, G.b_mn != 0);
+            umma_tf32(d_hi, dah, dbh, idesc, (i > i0 || k > 0) ? 1u : 0u);
+            if (want_lo) {
+              const uint64_t dal = make_desc(a_lo + k * a_step, G.a_mn != 0);
+              const uint64_t dbl = make_desc(b_lo + k * b_step, G.b_mn != 0);
+              umma_tf32(tmem_lo, dal, dbh, idesc, (i > 0 || k > 0) ? 1u : 0u);
+              umma_tf32(tmem_lo, dah, dbl, idesc, 1u);
+            }
           }
+          umma_commit(smem_u32(&empty[s]));                // frees the stage when these MMAs retire
         }
-        umma_commit(smem_u32(&bars[STAGES + s]));          // frees the stage when these MMAs retire
+        umma_commit(smem_u32(&acc_full[b]));               // chunk (and everything before it) complete
       }
-      umma_commit(smem_u32(&bars[2 * STAGES]));            // accumulator complete
     }
     __syncwarp();
-  }
-
-  // ================= epilogue (warps 0-7) =================
-  if (warp < NUM_PRODUCER_WARPS && nkb > 0) {
-    mbar_wait(smem_u32(&bars[2 * STAGES]), 0u);
-    tc_fence_after();
-    const int q = warp & 3, half = warp >> 2;              // TMEM lane quarter; column half
+  } else if (nkb > 0) {
+    // ================= promotion + epilogue =================
+    const int q = warp & 3;                                // TMEM lane quarter this warp may access
+    const int half = (warp - NUM_PRODUCER_WARPS) >> 2;     // column half
+    const uint32_t lane_col = ((uint32_t)(q * 32) << 16) + (uint32_t)(half * 64);
+    float acc[64];
+#pragma unroll
+    for (int c = 0; c < 64; ++c) acc[c] = 0.f;
+    for (int j = 0; j < nchunks; ++j) {
+      const int b = j & 1;
+      mbar_wait(smem_u32(&acc_full[b]), (uint32_t)((j >> 1) & 1));
+      tc_fence_after();
+      uint32_t r[32];
+#pragma unroll
+      for (int cc = 0; cc < 2; ++cc) {
+        tmem_ld32(tmem_base + (uint32_t)(b * BN) + lane_col + (uint32_t)(cc * 32), r);
+#pragma unroll
+        for (int c = 0; c < 32; ++c) acc[cc * 32 + c] += __uint_as_float(r[c]);
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(smem_u32(&acc_empty[b]));
+    }
+    if (want_lo) {
+      uint32_t r[32];
+#pragma unroll
+      for (int cc = 0; cc < 2; ++cc) {
+        tmem_ld32(tmem_lo + lane_col + (uint32_t)(cc * 32), r);
+#pragma unroll
+        for (int c = 0; c < 32; ++c) acc[cc * 32 + c] += __uint_as_float(r[c]);
+      }
+    }
     const int row = m0 + q * 32 + lane;
     const bool atomic = P.split_k > 1;
-#pragma unroll 1
-    for (int cc = 0; cc < 2; ++cc) {
-      const int col0 = half * 64 + cc * 32;
-      uint32_t r[32];
-      tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)col0, r);
-      if (row < G.M) {
-        float* crow = G.C + (long long)row * G.ldc + n0 + col0;
-        const int ncol = min(32, G.N - n0 - col0);
-        const bool vec = (ncol == 32) && ((reinterpret_cast<uintptr_t>(crow) & 15) == 0) && !atomic;
-        if (vec) {
+    if (row < G.M) {
+      const int col0 = half * 64;
+      float* crow = G.C + (long long)row * G.ldc + n0 + col0;
+      const int ncol = min(64, G.N - n0 - col0);
+      const bool vec = (ncol == 64) && ((reinterpret_cast<uintptr_t>(crow) & 15) == 0) && !atomic;
+      if (vec) {
 #pragma unroll
-          for (int c = 0; c < 32; c += 4) {
-            float4 o = make_float4(__uint_as_float(r[c]), __uint_as_float(r[c + 1]), __uint_as_float(r[c + 2]),
-                                   __uint_as_float(r[c + 3]));
-            if (G.bias != nullptr) {
-              const float4 b = __ldg(reinterpret_cast<const float4*>(G.bias + n0 + col0 + c));
-              o.x += b.x; o.y += b.y; o.z += b.z; o.w += b.w;
-            }
-            if (G.accumulate) {
-              const float4 p = *reinterpret_cast<const float4*>(crow + c);
-              o.x += p.x; o.y += p.y; o.z += p.z; o.w += p.w;
-            }
-            *reinterpret_cast<float4*>(crow + c) = o;
+        for (int c = 0; c < 64; c += 4) {
+          float4 o = make_float4(acc[c], acc[c + 1], acc[c + 2], acc[c + 3]);
+          if (G.bias != nullptr) {
+            const float4 bb = __ldg(reinterpret_cast<const float4*>(G.bias + n0 + col0 + c));
+            o.x += bb.x; o.y += bb.y; o.z += bb.z; o.w += bb.w;
           }
-        } else {
+          if (G.accumulate) {
+            const float4 p = *reinterpret_cast<const float4*>(crow + c);
+            o.x += p.x; o.y += p.y; o.z += p.z; o.w += p.w;
+          }
+          *reinterpret_cast<float4*>(crow + c) = o;
+        }
+      } else {
 #pragma unroll
-          for (int c = 0; c < 32; ++c) {
-            if (c < ncol) {
-              float o = __uint_as_float(r[c]);
-              if (G.bias != nullptr && ks == 0) o += __ldg(G.bias + n0 + col0 + c);
-              if (atomic) atomicAdd(crow + c, o);
-              else if (G.accumulate) crow[c] += o;
-              else crow[c] = o;
-            }
+        for (int c = 0; c < 64; ++c) {
+          if (c < ncol) {
+            float o = acc[c];
+            if (G.bias != nullptr && ks == 0) o += __ldg(G.bias + n0 + col0 + c);
+            if (atomic) atomicAdd(crow + c, o);
+            else if (G.accumulate) crow[c] += o;
+            else crow[c] = o;
           }
         }
       }
@@ -317,7 +362,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) gemm_tc_kernel(const __grid_co
   }
   tc_fence_before();
   __syncthreads();
-  if (warp == NUM_PRODUCER_WARPS) {
+  if (warp == MMA_WARP) {
     tc_fence_after();
     tmem_dealloc(tmem_base, TMEM_COLS);
   }
