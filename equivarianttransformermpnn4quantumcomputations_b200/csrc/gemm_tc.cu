@@ -18,18 +18,20 @@
 //           bound of the fp32 mode needs.
 //   mode 1 "1xTF32": hi*hi only, one TMEM chain, no promotion (separately stated tolerance).
 //
-// CTA = one 128 x 128 output tile.  Warp roles (416 threads):
-//   warps 0-3   producers of the A and B tiles (128 rows x 32 k each per stage)
-//               global -> registers -> hi/lo split -> swizzled smem
+// CTA = one 128 x 128 output tile.  Warp roles (416 threads, 13 warps -> 128 registers/thread):
+//   warps 0-3   producers: cp.async (LDGSTS, zero-filling out-of-range chunks) of the raw fp32 A and B tiles
+//               (128 rows x 32 k each) straight into their final swizzled position, LOOKAHEAD stages ahead;
+//               when a stage has landed (mbarrier completion of the cp.asyncs) they split it in place into
+//               hi (rounded) and lo tiles and hand it to the tensor core
 //   warps 4-11  promotion / epilogue: tcgen05.ld of finished chunks -> register accumulators -> bias /
 //               accumulate -> global
 //   warp  12    TMEM allocation + single-thread tcgen05.mma issue + tcgen05.commit
-// Operands go through registers (not TMA) on purpose: the hi/lo split is an elementwise transform of
-// the tile, and both K-contiguous ([rows,K]) and row-contiguous ([K,rows]: dgrad weights, wgrad
-// operands) sources are written straight into the canonical SWIZZLE_128B shared-memory layouts
-// (K-major resp. MN-major) that the UMMA descriptors name -- no transposed copies in HBM.
-// 3-stage mbarrier ring: full[s] (producers -> MMA), empty[s] (tcgen05.commit -> producers);
-// acc_full[b] (tcgen05.commit -> promoters), acc_empty[b] (promoters -> MMA).
+// Operands are staged by threads (not TMA) on purpose: every 16-byte chunk is addressed individually, so
+// K-contiguous ([rows,K]) sources land in the K-major SWIZZLE_128B layout and row-contiguous ([K,rows]:
+// dgrad weights, both wgrad operands) sources land in the MN-major SWIZZLE_128B_BASE32B layout that the
+// UMMA descriptors name -- no transposed copies in HBM -- with ragged M/N/K tails zero-filled.
+// 3-stage mbarrier ring: raw_full[s] (cp.async -> split), full[s] (split -> MMA), empty[s]
+// (tcgen05.commit -> producers); acc_full[b] (tcgen05.commit -> promoters), acc_empty[b] (promoters -> MMA).
 #include "common.cuh"
 
 #ifndef EQV2_CPU_EMU
@@ -46,8 +48,10 @@ constexpr int NUM_EPI_WARPS = 8;                   // warps 4-11 (lane quarter =
 constexpr int MMA_WARP = NUM_PRODUCER_WARPS + NUM_EPI_WARPS;
 constexpr int NUM_THREADS = (NUM_PRODUCER_WARPS + NUM_EPI_WARPS + 1) * 32;
 constexpr int TMEM_COLS = 512;                     // D_hi[0], D_hi[1], D_lo (128 columns each); power of two
+constexpr int LOOKAHEAD = 2;                       // stages of cp.async in flight ahead of the split
 constexpr int CHUNK_KB = 2;                        // k-blocks per promoted hi*hi chain (8 tcgen05.mma)
 constexpr size_t SMEM_BYTES = (size_t)STAGES * STAGE_BYTES + 1024 /*align*/ + 256 /*barriers*/;
+static_assert(LOOKAHEAD < STAGES, "the split works on a stage while LOOKAHEAD others are in flight");
 
 struct TcGroup {
   const float* A;
@@ -134,14 +138,17 @@ __device__ __forceinline__ float tf32_rna(float v) {
 
 // ---- descriptors ---------------------------------------------------------------------------------
 // SM100 shared-memory matrix descriptor: start>>4 [0,14) | LBO>>4 [16,30) | SBO>>4 [32,46) | version=1 [46,48)
-// | layout type [61,64) (2 = SWIZZLE_128B).
-// K-major tile  [rows][32 fp32]: 8-row groups are 1024 B apart (SBO); LBO unused (1).
-// MN-major tile: atom = 32 rows (128 B contiguous) x 8 k; atoms along rows are LBO = 1024 B apart,
-//               groups of 8 k are SBO = 4096 B apart.
+// | layout type [61,64).
+// K-major tile [rows][32 fp32], SWIZZLE_128B (type 2): 16-byte chunk index ^= (row & 7); 8-row groups are
+//   SBO = 1024 B apart; LBO unused (1).
+// MN-major tile (the row index is the contiguous one).  For 32-bit operands the only legal swizzle is
+//   SWIZZLE_128B_BASE32B (type 1): atom = 32 rows (128 B) x 4 k, 32-byte chunk index ^= (k & 3).
+//   Tile = [k/4 (8)][rows/32 (4)][k%4][128 B]  ->  LBO (next 32 rows) = 512 B, SBO (next 4 k) = 2048 B.
 __device__ __forceinline__ uint64_t make_desc(uint32_t smem_addr, bool mn_major) {
-  const uint64_t lbo = mn_major ? (1024u >> 4) : 1u;
-  const uint64_t sbo = mn_major ? (4096u >> 4) : (1024u >> 4);
-  return (uint64_t)((smem_addr >> 4) & 0x3FFFu) | (lbo << 16) | (sbo << 32) | (1ull << 46) | (2ull << 61);
+  const uint64_t lbo = mn_major ? (512u >> 4) : 1u;
+  const uint64_t sbo = mn_major ? (2048u >> 4) : (1024u >> 4);
+  const uint64_t type = mn_major ? 1ull : 2ull;
+  return (uint64_t)((smem_addr >> 4) & 0x3FFFu) | (lbo << 16) | (sbo << 32) | (1ull << 46) | (type << 61);
 }
 // instruction descriptor: D fp32 (1<<4), A/B tf32 (2<<7, 2<<10), majors (bits 15/16), N>>3 (17..22), M>>4 (24..28)
 __device__ __forceinline__ uint32_t make_idesc(bool a_mn, bool b_mn) {
@@ -149,44 +156,50 @@ __device__ __forceinline__ uint32_t make_idesc(bool a_mn, bool b_mn) {
          ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
 }
 
-// ---- producer: one operand tile (128 rows x 32 k) into smem (hi and lo) ----------------------------
-// tid in [0,128).  src element (row, k) = mn ? src[k*ld + row] : src[row*ld + k].
-__device__ __forceinline__ void produce_tile(const float* __restrict__ src, long long ld, int mn, int row0, int rows,
-                                             int k0, int K, unsigned char* hi, unsigned char* lo, int tid, bool want_lo) {
+// ---- producer: one operand tile (128 rows x 32 k) global -> smem with cp.async (LDGSTS) ------------------
+// tid in [0,128).  src element (row, k) = mn ? src[k*ld + row] : src[row*ld + k].  Out-of-range chunks are
+// zero-filled through the src-size operand.  The raw fp32 tile lands in the `hi` buffer in its final layout.
+__device__ __forceinline__ void cp_async16(uint32_t dst, const void* src, uint32_t src_bytes) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(src), "r"(src_bytes) : "memory");
+}
+__device__ __forceinline__ void cp_async_arrive_noinc(uint32_t bar) {
+  asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(bar) : "memory");
+}
+
+__device__ __forceinline__ void issue_tile(const float* __restrict__ src, long long ld, int mn, int row0, int rows,
+                                           int k0, int K, uint32_t hi, int tid) {
 #pragma unroll
   for (int it = 0; it < 8; ++it) {
     const int idx = it * 128 + tid;
-    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-    uint32_t off;
+    uint32_t off, nbytes = 0;
+    const float* p = src;
     if (!mn) {
       const int r = idx >> 3, c = idx & 7;                  // 8 x 16 B chunks per row
       const int gr = row0 + r, gk = k0 + c * 4;
-      if (gr < rows && gk < K) v = __ldg(reinterpret_cast<const float4*>(src + (long long)gr * ld + gk));
+      if (gr < rows && gk < K) { p = src + (long long)gr * ld + gk; nbytes = 16; }
       off = (uint32_t)(r * 128 + ((c ^ (r & 7)) << 4));
     } else {
       const int kk = idx >> 5, c32 = idx & 31;              // 32 x 16 B chunks (128 rows) per k
       const int gr = row0 + c32 * 4, gk = k0 + kk;
-      if (gk < K) {
-        const float* p = src + (long long)gk * ld + gr;
-        if (gr + 3 < rows) v = __ldg(reinterpret_cast<const float4*>(p));
-        else {
-          if (gr < rows) v.x = __ldg(p);
-          if (gr + 1 < rows) v.y = __ldg(p + 1);
-          if (gr + 2 < rows) v.z = __ldg(p + 2);
-        }
-      }
-      // atom (rows/32, k/8): 1024 B; inside: k row (128 B) x 8 chunks, chunk ^= (k & 7)
-      const int rb = c32 >> 3, c = c32 & 7, k8 = kk & 7, kb = kk >> 3;
-      off = (uint32_t)(kb * 4096 + rb * 1024 + k8 * 128 + ((c ^ k8) << 4));
+      if (gk < K && gr < rows) { p = src + (long long)gk * ld + gr; nbytes = (uint32_t)min(16, (rows - gr) * 4); }
+      const int rb = c32 >> 3, c = c32 & 7, k4 = kk & 3, kg = kk >> 2;
+      off = (uint32_t)(kg * 2048 + rb * 512 + k4 * 128 + (((((c >> 1) ^ k4) << 1) | (c & 1)) << 4));
     }
-    float4 h;
+    cp_async16(hi + off, p, nbytes);
+  }
+}
+
+// hi/lo split of a landed tile, elementwise and therefore layout-agnostic: chunk i of `hi` <-> chunk i of `lo`.
+__device__ __forceinline__ void split_tile(unsigned char* hi, unsigned char* lo, int tid) {
+#pragma unroll
+  for (int it = 0; it < 8; ++it) {
+    const uint32_t off = (uint32_t)(it * 128 + tid) << 4;
+    const float4 v = *reinterpret_cast<const float4*>(hi + off);
+    float4 h, l;
     h.x = tf32_rna(v.x); h.y = tf32_rna(v.y); h.z = tf32_rna(v.z); h.w = tf32_rna(v.w);
+    l.x = tf32_rna(v.x - h.x); l.y = tf32_rna(v.y - h.y); l.z = tf32_rna(v.z - h.z); l.w = tf32_rna(v.w - h.w);
     *reinterpret_cast<float4*>(hi + off) = h;
-    if (want_lo) {
-      float4 l;
-      l.x = tf32_rna(v.x - h.x); l.y = tf32_rna(v.y - h.y); l.z = tf32_rna(v.z - h.z); l.w = tf32_rna(v.w - h.w);
-      *reinterpret_cast<float4*>(lo + off) = l;
-    }
+    *reinterpret_cast<float4*>(lo + off) = l;
   }
 }
 
@@ -196,12 +209,13 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) gemm_tc_kernel(const __grid_co
   const uint32_t pad = (1024u - (raw_addr & 1023u)) & 1023u;
   unsigned char* tiles = smem_raw + pad;                                    // STAGES * STAGE_BYTES, 1024-aligned
   uint64_t* bars = reinterpret_cast<uint64_t*>(tiles + (size_t)STAGES * STAGE_BYTES);
-  // bars: [0,S) full | [S,2S) empty | 2S+b acc_full[b] | 2S+2+b acc_empty[b] ; then the TMEM base address word
+  // bars: [0,S) full | [S,2S) empty | [2S,3S) raw_full | 3S+b acc_full[b] | 3S+2+b acc_empty[b] ; TMEM base word
   uint64_t* full = bars;
   uint64_t* empty = bars + STAGES;
-  uint64_t* acc_full = bars + 2 * STAGES;
-  uint64_t* acc_empty = bars + 2 * STAGES + 2;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * STAGES + 4);
+  uint64_t* raw_full = bars + 2 * STAGES;
+  uint64_t* acc_full = bars + 3 * STAGES;
+  uint64_t* acc_empty = bars + 3 * STAGES + 2;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 3 * STAGES + 4);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
@@ -228,6 +242,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) gemm_tc_kernel(const __grid_co
     for (int s = 0; s < STAGES; ++s) {
       mbar_init(smem_u32(&full[s]), NUM_PRODUCER_WARPS);
       mbar_init(smem_u32(&empty[s]), 1);
+      mbar_init(smem_u32(&raw_full[s]), NUM_PRODUCER_WARPS * 32);   // one cp.async completion arrive per thread
     }
     for (int b = 0; b < 2; ++b) {
       mbar_init(smem_u32(&acc_full[b]), 1);
@@ -243,24 +258,37 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) gemm_tc_kernel(const __grid_co
   const uint32_t tmem_lo = tmem_base + 2 * BN;
 
   if (warp < NUM_PRODUCER_WARPS) {
-    // ================= producers =================
+    // ================= producers: async loads run LOOKAHEAD stages ahead of the split =================
     const int tid = threadIdx.x;          // 0..127
-    for (int i = 0; i < nkb; ++i) {
+    auto issue = [&](int i) {
       const int s = i % STAGES, round = i / STAGES;
       mbar_wait(smem_u32(&empty[s]), (uint32_t)((round & 1) ^ 1));
-      unsigned char* st = tiles + (size_t)s * STAGE_BYTES;
+      const uint32_t st = smem_u32(tiles + (size_t)s * STAGE_BYTES);
       const int k0 = (kb0 + i) * BK;
-      produce_tile(G.A, G.lda, G.a_mn, m0, G.M, k0, G.K, st, st + TILE_BYTES, tid, want_lo);
-      produce_tile(G.B, G.ldb, G.b_mn, n0, G.N, k0, G.K, st + 2 * TILE_BYTES, st + 3 * TILE_BYTES, tid, want_lo);
-      fence_proxy_async_smem();      // generic-proxy stores -> visible to the tensor core (async proxy)
-      __syncwarp();
-      if (lane == 0) mbar_arrive(smem_u32(&full[s]));
+      issue_tile(G.A, G.lda, G.a_mn, m0, G.M, k0, G.K, st, tid);
+      issue_tile(G.B, G.ldb, G.b_mn, n0, G.N, k0, G.K, st + 2 * TILE_BYTES, tid);
+      cp_async_arrive_noinc(smem_u32(&raw_full[s]));
+    };
+    for (int i = 0; i < min(LOOKAHEAD, nkb); ++i) issue(i);
+    for (int i = 0; i < nkb; ++i) {
+      if (want_lo) {
+        const int s = i % STAGES, round = i / STAGES;
+        mbar_wait(smem_u32(&raw_full[s]), (uint32_t)(round & 1));
+        unsigned char* st = tiles + (size_t)s * STAGE_BYTES;
+        split_tile(st, st + TILE_BYTES, tid);
+        split_tile(st + 2 * TILE_BYTES, st + 3 * TILE_BYTES, tid);
+        fence_proxy_async_smem();    // generic-proxy stores -> visible to the tensor core (async proxy)
+        __syncwarp();
+        if (lane == 0) mbar_arrive(smem_u32(&full[s]));
+      }
+      // the slot of block i+LOOKAHEAD is the one block i-1 used: by now its MMAs have had a split's time to retire
+      if (i + LOOKAHEAD < nkb) issue(i + LOOKAHEAD);
     }
   } else if (warp == MMA_WARP) {
     // ================= MMA issuer (one thread) =================
     if (lane == 0) {
       const uint32_t idesc = make_idesc(G.a_mn != 0, G.b_mn != 0);
-      const uint32_t a_step = G.a_mn ? 4096u : 32u;       // bytes per K=8 slice
+      const uint32_t a_step = G.a_mn ? 4096u : 32u;       // bytes per K=8 slice (MN-major: two 4-k groups)
       const uint32_t b_step = G.b_mn ? 4096u : 32u;
       int i = 0;
       for (int j = 0; j < nchunks; ++j) {
@@ -271,7 +299,12 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) gemm_tc_kernel(const __grid_co
         const int iend = min(nkb, i + chunk);
         for (int i0 = i; i < iend; ++i) {
           const int s = i % STAGES, round = i / STAGES;
-          mbar_wait(smem_u32(&full[s]), (uint32_t)(round & 1));
+          if (want_lo) {
+            mbar_wait(smem_u32(&full[s]), (uint32_t)(round & 1));
+          } else {                                         // 1xTF32: the raw fp32 tile feeds the tensor core as is
+            mbar_wait(smem_u32(&raw_full[s]), (uint32_t)(round & 1));
+            fence_proxy_async_smem();
+          }
           tc_fence_after();
           const uint32_t base = smem_u32(tiles + (size_t)s * STAGE_BYTES);
           const uint32_t a_hi = base, a_lo = base + TILE_BYTES, b_hi = base + 2 * TILE_BYTES, b_lo = base + 3 * TILE_BYTES;
