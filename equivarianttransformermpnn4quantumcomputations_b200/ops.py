@@ -313,7 +313,7 @@ def _pick_split(descs, reduce_dim_large):
     return int(max(1, min(64, 296 // max(tiles, 1), kmax // 512)))
 
 
-def _tc_ok(d):
+def _tc_addressable(d):
     """Can the tensor-core engine address this problem? (see eqv2_gemm_tc in include/eqv2_b200.h)"""
     if min(d.a_rpb, d.b_rpb, d.c_rpb) < (1 << 31):
         return False
@@ -321,7 +321,11 @@ def _tc_ok(d):
         return False
     if (not d.transA and d.K % 4) or (d.transB and d.K % 4):
         return False
-    return d.M * d.N * d.K >= (1 << 21)      # tiny problems are launch-bound either way
+    return True
+
+
+def _tc_ok(d):
+    return _tc_addressable(d) and d.M * d.N * d.K >= (1 << 21)      # tiny problems are launch-bound either way
 
 
 def run_gemm(descs, split_k=1):
