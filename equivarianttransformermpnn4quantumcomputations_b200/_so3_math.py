@@ -125,3 +125,34 @@ def s2_grid_matrices(lmax, mmax, res_beta, res_alpha):
         mm = min(l, mmax)
         keep += [l * l + l + m for m in range(-mm, mm + 1)]
     return np.ascontiguousarray(to_g[..., keep]), np.ascontiguousarray(fr_g[..., keep])
+
+
+@functools.lru_cache(maxsize=None)
+def s2_grid_factors(lmax, mmax, res):
+    """Latitude / longitude factors of `s2_grid_matrices(lmax, mmax, res, res)`:
+        to_grid[b,a,(l,m)]   = Pt[|m|,b,l] * trig[a,m]        from_grid[b,a,(l,m)] = Pf[|m|,b,l] * trig[a,m]
+    trig[a,m] = 1 (m=0) | sqrt2 cos(m alpha_a) (m>0) | sqrt2 sin(|m| alpha_a) (m<0).
+    Returns fp32 arrays Pt, Pf [7,res,7] (zero padded) and ct, st [res,7]."""
+    MAXL = 6
+    assert lmax <= MAXL and res % 2 == 0
+    betas = (np.arange(res) + 0.5) / res * math.pi
+    alphas = np.arange(res) / res * 2 * math.pi
+    P = _legendre_no_cs(lmax, np.cos(betas), np.sin(betas))
+    qw = _dh_weights(res // 2) * res ** 2 / res
+    Pt = np.zeros((MAXL + 1, res, MAXL + 1))
+    Pf = np.zeros((MAXL + 1, res, MAXL + 1))
+    for l in range(lmax + 1):
+        nt = math.sqrt(4 * math.pi) / math.sqrt(2 * l + 1) / math.sqrt(lmax + 1)
+        nf = math.sqrt(4 * math.pi) * math.sqrt(2 * l + 1) * math.sqrt(lmax + 1)
+        f = math.sqrt((2 * l + 1) / (2 * mmax + 1)) if (lmax != mmax and l > mmax) else 1.0
+        for m in range(0, min(l, mmax) + 1):
+            base = _norm(l, m) * P[(l, m)]
+            Pt[m, :, l] = base * nt * f
+            Pf[m, :, l] = base * nf * qw * f
+    ct = np.zeros((res, MAXL + 1))
+    st = np.zeros((res, MAXL + 1))
+    ct[:, 0] = 1.0
+    for m in range(1, mmax + 1):
+        ct[:, m] = math.sqrt(2.0) * np.cos(m * alphas)
+        st[:, m] = math.sqrt(2.0) * np.sin(m * alphas)
+    return tuple(np.ascontiguousarray(a.astype(np.float32)) for a in (Pt, Pf, ct, st))

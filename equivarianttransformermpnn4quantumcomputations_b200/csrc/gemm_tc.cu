@@ -48,10 +48,9 @@ constexpr int NUM_EPI_WARPS = 8;                   // warps 4-11 (lane quarter =
 constexpr int MMA_WARP = NUM_PRODUCER_WARPS + NUM_EPI_WARPS;
 constexpr int NUM_THREADS = (NUM_PRODUCER_WARPS + NUM_EPI_WARPS + 1) * 32;
 constexpr int TMEM_COLS = 512;                     // D_hi[0], D_hi[1], D_lo (128 columns each); power of two
-constexpr int LOOKAHEAD = 2;                       // stages of cp.async in flight ahead of the split
+constexpr int PROMOTE_LAG = 2;                     // blocks between the split of a chunk's last stage and its promotion
 constexpr int CHUNK_KB = 2;                        // k-blocks per promoted hi*hi chain (8 tcgen05.mma)
 constexpr size_t SMEM_BYTES = (size_t)STAGES * STAGE_BYTES + 1024 /*align*/ + 256 /*barriers*/;
-static_assert(LOOKAHEAD < STAGES, "the split works on a stage while LOOKAHEAD others are in flight");
 
 struct TcGroup {
   const float* A;
@@ -166,38 +165,59 @@ __device__ __forceinline__ void cp_async_arrive_noinc(uint32_t bar) {
   asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(bar) : "memory");
 }
 
-__device__ __forceinline__ void issue_tile(const float* __restrict__ src, long long ld, int mn, int row0, int rows,
-                                           int k0, int K, uint32_t hi, int tid) {
+// Per-thread view of its 8 chunks of one operand tile: everything that does not change along K.
+struct ChunkPlan {
+  const float* ptr[8];   // source of the chunk at k-block 0 (nullptr: row out of range)
+  uint32_t off[8];       // byte offset inside the tile (final swizzled position)
+  uint32_t bytes[8];     // 16, or fewer for a ragged row tail of a row-contiguous source
+  int kk[8];             // k of the chunk inside the k-block (first k for K-contiguous sources)
+};
+
+__device__ __forceinline__ void plan_tile(ChunkPlan& P, const float* __restrict__ src, long long ld, int mn, int row0,
+                                          int rows, int tid) {
 #pragma unroll
   for (int it = 0; it < 8; ++it) {
     const int idx = it * 128 + tid;
-    uint32_t off, nbytes = 0;
-    const float* p = src;
     if (!mn) {
       const int r = idx >> 3, c = idx & 7;                  // 8 x 16 B chunks per row
-      const int gr = row0 + r, gk = k0 + c * 4;
-      if (gr < rows && gk < K) { p = src + (long long)gr * ld + gk; nbytes = 16; }
-      off = (uint32_t)(r * 128 + ((c ^ (r & 7)) << 4));
+      const int gr = row0 + r;
+      P.ptr[it] = (gr < rows) ? src + (long long)gr * ld + c * 4 : nullptr;
+      P.bytes[it] = 16;
+      P.kk[it] = c * 4;
+      P.off[it] = (uint32_t)(r * 128 + ((c ^ (r & 7)) << 4));
     } else {
       const int kk = idx >> 5, c32 = idx & 31;              // 32 x 16 B chunks (128 rows) per k
-      const int gr = row0 + c32 * 4, gk = k0 + kk;
-      if (gk < K && gr < rows) { p = src + (long long)gk * ld + gr; nbytes = (uint32_t)min(16, (rows - gr) * 4); }
+      const int gr = row0 + c32 * 4;
+      P.ptr[it] = (gr < rows) ? src + (long long)kk * ld + gr : nullptr;
+      P.bytes[it] = (uint32_t)max(0, min(16, (rows - gr) * 4));
+      P.kk[it] = kk;
       const int rb = c32 >> 3, c = c32 & 7, k4 = kk & 3, kg = kk >> 2;
-      off = (uint32_t)(kg * 2048 + rb * 512 + k4 * 128 + (((((c >> 1) ^ k4) << 1) | (c & 1)) << 4));
+      P.off[it] = (uint32_t)(kg * 2048 + rb * 512 + k4 * 128 + (((((c >> 1) ^ k4) << 1) | (c & 1)) << 4));
     }
-    cp_async16(hi + off, p, nbytes);
+  }
+}
+
+__device__ __forceinline__ void issue_tile(const ChunkPlan& P, const float* __restrict__ base, long long kstep_elems,
+                                           int k0, int K, uint32_t hi) {
+#pragma unroll
+  for (int it = 0; it < 8; ++it) {
+    const bool ok = (P.ptr[it] != nullptr) && (k0 + P.kk[it] < K);
+    cp_async16(hi + P.off[it], ok ? P.ptr[it] + kstep_elems : base, ok ? P.bytes[it] : 0u);
   }
 }
 
 // hi/lo split of a landed tile, elementwise and therefore layout-agnostic: chunk i of `hi` <-> chunk i of `lo`.
-__device__ __forceinline__ void split_tile(unsigned char* hi, unsigned char* lo, int tid) {
+// 256 worker threads, 4 chunks each.
+__device__ __forceinline__ void split_tile(unsigned char* hi, unsigned char* lo, int wt) {
+  float4 v[4];
 #pragma unroll
-  for (int it = 0; it < 8; ++it) {
-    const uint32_t off = (uint32_t)(it * 128 + tid) << 4;
-    const float4 v = *reinterpret_cast<const float4*>(hi + off);
+  for (int it = 0; it < 4; ++it) v[it] = *reinterpret_cast<const float4*>(hi + ((uint32_t)(it * 256 + wt) << 4));
+#pragma unroll
+  for (int it = 0; it < 4; ++it) {
+    const uint32_t off = (uint32_t)(it * 256 + wt) << 4;
     float4 h, l;
-    h.x = tf32_rna(v.x); h.y = tf32_rna(v.y); h.z = tf32_rna(v.z); h.w = tf32_rna(v.w);
-    l.x = tf32_rna(v.x - h.x); l.y = tf32_rna(v.y - h.y); l.z = tf32_rna(v.z - h.z); l.w = tf32_rna(v.w - h.w);
+    h.x = tf32_rna(v[it].x); h.y = tf32_rna(v[it].y); h.z = tf32_rna(v[it].z); h.w = tf32_rna(v[it].w);
+    l.x = tf32_rna(v[it].x - h.x); l.y = tf32_rna(v[it].y - h.y); l.z = tf32_rna(v[it].z - h.z); l.w = tf32_rna(v[it].w - h.w);
     *reinterpret_cast<float4*>(hi + off) = h;
     *reinterpret_cast<float4*>(lo + off) = l;
   }
@@ -240,7 +260,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) gemm_tc_kernel(const __grid_co
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < STAGES; ++s) {
-      mbar_init(smem_u32(&full[s]), NUM_PRODUCER_WARPS);
+      mbar_init(smem_u32(&full[s]), NUM_EPI_WARPS);                 // one arrive per worker warp after the split
       mbar_init(smem_u32(&empty[s]), 1);
       mbar_init(smem_u32(&raw_full[s]), NUM_PRODUCER_WARPS * 32);   // one cp.async completion arrive per thread
     }
@@ -258,31 +278,20 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) gemm_tc_kernel(const __grid_co
   const uint32_t tmem_lo = tmem_base + 2 * BN;
 
   if (warp < NUM_PRODUCER_WARPS) {
-    // ================= producers: async loads run LOOKAHEAD stages ahead of the split =================
+    // ================= producers: cp.async only, up to STAGES blocks ahead of the tensor core =================
     const int tid = threadIdx.x;          // 0..127
-    auto issue = [&](int i) {
+    ChunkPlan pa, pb;
+    plan_tile(pa, G.A, G.lda, G.a_mn, m0, G.M, tid);
+    plan_tile(pb, G.B, G.ldb, G.b_mn, n0, G.N, tid);
+    const long long a_kstride = G.a_mn ? G.lda : 1, b_kstride = G.b_mn ? G.ldb : 1;
+    for (int i = 0; i < nkb; ++i) {
       const int s = i % STAGES, round = i / STAGES;
       mbar_wait(smem_u32(&empty[s]), (uint32_t)((round & 1) ^ 1));
       const uint32_t st = smem_u32(tiles + (size_t)s * STAGE_BYTES);
       const int k0 = (kb0 + i) * BK;
-      issue_tile(G.A, G.lda, G.a_mn, m0, G.M, k0, G.K, st, tid);
-      issue_tile(G.B, G.ldb, G.b_mn, n0, G.N, k0, G.K, st + 2 * TILE_BYTES, tid);
+      issue_tile(pa, G.A, (long long)k0 * a_kstride, k0, G.K, st);
+      issue_tile(pb, G.B, (long long)k0 * b_kstride, k0, G.K, st + 2 * TILE_BYTES);
       cp_async_arrive_noinc(smem_u32(&raw_full[s]));
-    };
-    for (int i = 0; i < min(LOOKAHEAD, nkb); ++i) issue(i);
-    for (int i = 0; i < nkb; ++i) {
-      if (want_lo) {
-        const int s = i % STAGES, round = i / STAGES;
-        mbar_wait(smem_u32(&raw_full[s]), (uint32_t)(round & 1));
-        unsigned char* st = tiles + (size_t)s * STAGE_BYTES;
-        split_tile(st, st + TILE_BYTES, tid);
-        split_tile(st + 2 * TILE_BYTES, st + 3 * TILE_BYTES, tid);
-        fence_proxy_async_smem();    // generic-proxy stores -> visible to the tensor core (async proxy)
-        __syncwarp();
-        if (lane == 0) mbar_arrive(smem_u32(&full[s]));
-      }
-      // the slot of block i+LOOKAHEAD is the one block i-1 used: by now its MMAs have had a split's time to retire
-      if (i + LOOKAHEAD < nkb) issue(i + LOOKAHEAD);
     }
   } else if (warp == MMA_WARP) {
     // ================= MMA issuer (one thread) =================
@@ -327,14 +336,15 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) gemm_tc_kernel(const __grid_co
     }
     __syncwarp();
   } else if (nkb > 0) {
-    // ================= promotion + epilogue =================
+    // ================= workers: hi/lo split of landed stages + promotion of finished chunks + epilogue ==========
     const int q = warp & 3;                                // TMEM lane quarter this warp may access
     const int half = (warp - NUM_PRODUCER_WARPS) >> 2;     // column half
+    const int wt = threadIdx.x - NUM_PRODUCER_WARPS * 32;  // 0..255
     const uint32_t lane_col = ((uint32_t)(q * 32) << 16) + (uint32_t)(half * 64);
     float acc[64];
 #pragma unroll
     for (int c = 0; c < 64; ++c) acc[c] = 0.f;
-    for (int j = 0; j < nchunks; ++j) {
+    auto promote = [&](int j) {
       const int b = j & 1;
       mbar_wait(smem_u32(&acc_full[b]), (uint32_t)((j >> 1) & 1));
       tc_fence_after();
@@ -348,7 +358,23 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) gemm_tc_kernel(const __grid_co
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(smem_u32(&acc_empty[b]));
+    };
+    int promoted = 0;
+    if (want_lo) {
+      for (int i = 0; i < nkb; ++i) {
+        const int s = i % STAGES, round = i / STAGES;
+        mbar_wait(smem_u32(&raw_full[s]), (uint32_t)(round & 1));
+        unsigned char* st = tiles + (size_t)s * STAGE_BYTES;
+        split_tile(st, st + TILE_BYTES, wt);
+        split_tile(st + 2 * TILE_BYTES, st + 3 * TILE_BYTES, wt);
+        fence_proxy_async_smem();    // generic-proxy stores -> visible to the tensor core (async proxy)
+        __syncwarp();
+        if (lane == 0) mbar_arrive(smem_u32(&full[s]));
+        // promote a chunk whose MMAs were issued >= PROMOTE_LAG blocks ago (it has very likely retired)
+        if (promoted < nchunks && (promoted + 1) * chunk + PROMOTE_LAG <= i + 1) promote(promoted++);
+      }
     }
+    while (promoted < nchunks) promote(promoted++);
     if (want_lo) {
       uint32_t r[32];
 #pragma unroll

@@ -1,0 +1,251 @@
+// Separable S2 activation (activation.py:153-192 on the grids of so3.py:552-646), latitude/longitude
+// factorised.  The reference multiplies by dense [18,18,Kr] matrices; those matrices are products
+//     to_grid[b,a,(l,m)]   = Pt[|m|][b][l] * trig[a][m]
+//     from_grid[b,a,(l,m)] = Pf[|m|][b][l] * trig[a][m]          trig = 1 | sqrt2 cos(m alpha_a) | sqrt2 sin(|m| alpha_a)
+// (e3nn ToS2Grid / FromS2Grid `shb`/`sha`, so3.py:584-608), so per latitude ring b
+//     u[m]   = sum_l Pt[|m|][b][l] x[l,m]                       (Kr FMAs)
+//     g[a]   = sum_m trig[a][m] u[m]  ->  s = SiLU(g[a])  ->  v[m] += trig[a][m] s      (2 (2M+1) FMAs per grid point)
+//     o[l,m] += Pf[|m|][b][l] v[m]                              (Kr FMAs)
+// = 18 (2 Kr + 36 (2M+1)) FMAs instead of 2*324*Kr: 4.8x fewer at (L,M) = (6,2), 3.1x at (6,6).
+// The factor tables live in __constant__ memory (uniform operands of the FMAs, no shared-memory traffic);
+// the host checks them against the module's to_grid/from_grid buffers before use.
+// One thread per (row, channel); x / o stay in registers; coefficient order (l- or m-primary) is a
+// compile-time index map.
+#include "common.cuh"
+
+namespace {
+
+constexpr int S2_MAXL = 6;
+constexpr int S2_RES = 18;
+constexpr int S2_THREADS = 128;
+
+struct S2Tables {
+  float Pt[S2_MAXL + 1][S2_RES][S2_MAXL + 1];   // [|m|][b][l]
+  float Pf[S2_MAXL + 1][S2_RES][S2_MAXL + 1];
+  float ct[S2_RES][S2_MAXL + 1];                // sqrt2 cos(m alpha_a)  (m = 0: 1)
+  float st[S2_RES][S2_MAXL + 1];                // sqrt2 sin(m alpha_a)  (m = 0: unused)
+};
+
+#ifdef EQV2_CPU_EMU
+static S2Tables g_tab[2];
+#else
+__constant__ S2Tables g_tab[2];
+#endif
+
+// position of coefficient (l, +-mi) in the reduced tensor
+template <int L, int M, bool MPRIMARY>
+__host__ __device__ constexpr int coef_pos(int l, int mi, bool neg) {
+  if (MPRIMARY) {
+    if (mi == 0) return l;
+    int base = L + 1;
+    for (int j = 1; j < mi; ++j) base += 2 * (L - j + 1);
+    return base + (neg ? (L - mi + 1) : 0) + (l - mi);
+  }
+  int base = 0;
+  for (int j = 0; j < l; ++j) base += (2 * j + 1 < 2 * M + 1) ? 2 * j + 1 : 2 * M + 1;
+  const int mm = l < M ? l : M;
+  return base + mm + (neg ? -mi : mi);
+}
+
+template <int L, int M>
+struct KrOf {
+  static constexpr int value() {
+    int s = 0;
+    for (int l = 0; l <= L; ++l) s += (2 * l + 1 < 2 * M + 1) ? 2 * l + 1 : 2 * M + 1;
+    return s;
+  }
+};
+
+// latitude transform of ring b: u_p[mi] / u_n[mi] from coefficient registers
+template <int L, int M, bool MP>
+__device__ __forceinline__ void lat_fwd(const float (&x)[KrOf<L, M>::value()], const float (*P)[S2_RES][S2_MAXL + 1], int b,
+                                        float (&up)[M + 1], float (&un)[M + 1]) {
+#pragma unroll
+  for (int mi = 0; mi <= M; ++mi) {
+    float sp = 0.f, sn = 0.f;
+#pragma unroll
+    for (int l = mi; l <= L; ++l) {
+      const float p = P[mi][b][l];
+      sp = fmaf(p, x[coef_pos<L, M, MP>(l, mi, false)], sp);
+      if (mi > 0) sn = fmaf(p, x[coef_pos<L, M, MP>(l, mi, true)], sn);
+    }
+    up[mi] = sp;
+    un[mi] = sn;
+  }
+}
+template <int L, int M, bool MP>
+__device__ __forceinline__ void lat_bwd(float (&o)[KrOf<L, M>::value()], const float (*P)[S2_RES][S2_MAXL + 1], int b,
+                                        const float (&vp)[M + 1], const float (&vn)[M + 1]) {
+#pragma unroll
+  for (int mi = 0; mi <= M; ++mi) {
+#pragma unroll
+    for (int l = mi; l <= L; ++l) {
+      const float p = P[mi][b][l];
+      o[coef_pos<L, M, MP>(l, mi, false)] = fmaf(p, vp[mi], o[coef_pos<L, M, MP>(l, mi, false)]);
+      if (mi > 0) o[coef_pos<L, M, MP>(l, mi, true)] = fmaf(p, vn[mi], o[coef_pos<L, M, MP>(l, mi, true)]);
+    }
+  }
+}
+
+template <int L, int M, bool MP>
+__global__ void __launch_bounds__(S2_THREADS)
+s2sep_fwd_kernel(const float* __restrict__ X, long long x_rs, const float* __restrict__ gate, long long g_rs,
+                 float* __restrict__ O, long long o_rs, long long R, int C, int slot) {
+  constexpr int Kr = KrOf<L, M>::value();
+  const S2Tables& T = g_tab[slot];
+  const long long total = R * C;
+  for (long long w = (long long)blockIdx.x * blockDim.x + threadIdx.x; w < total; w += (long long)gridDim.x * blockDim.x) {
+    const long long r = w / C;
+    const int c = (int)(w % C);
+    float x[Kr], o[Kr];
+#pragma unroll
+    for (int p = 0; p < Kr; ++p) {
+      x[p] = __ldg(X + r * x_rs + (long long)p * C + c);
+      o[p] = 0.f;
+    }
+#pragma unroll 1
+    for (int b = 0; b < S2_RES; ++b) {
+      float up[M + 1], un[M + 1], vp[M + 1], vn[M + 1];
+      lat_fwd<L, M, MP>(x, T.Pt, b, up, un);
+#pragma unroll
+      for (int mi = 0; mi <= M; ++mi) vp[mi] = vn[mi] = 0.f;
+#pragma unroll
+      for (int a = 0; a < S2_RES; ++a) {
+        float g = up[0];
+#pragma unroll
+        for (int mi = 1; mi <= M; ++mi) g = fmaf(T.ct[a][mi], up[mi], fmaf(T.st[a][mi], un[mi], g));
+        const float s = eqv2_silu(g);
+        vp[0] += s;
+#pragma unroll
+        for (int mi = 1; mi <= M; ++mi) {
+          vp[mi] = fmaf(T.ct[a][mi], s, vp[mi]);
+          vn[mi] = fmaf(T.st[a][mi], s, vn[mi]);
+        }
+      }
+      lat_bwd<L, M, MP>(o, T.Pf, b, vp, vn);
+    }
+    if (gate != nullptr) o[0] = eqv2_silu(__ldg(gate + r * g_rs + c));
+#pragma unroll
+    for (int p = 0; p < Kr; ++p) O[r * o_rs + (long long)p * C + c] = o[p];
+  }
+}
+
+template <int L, int M, bool MP>
+__global__ void __launch_bounds__(S2_THREADS)
+s2sep_bwd_kernel(const float* __restrict__ X, long long x_rs, const float* __restrict__ gate, long long g_rs,
+                 const float* __restrict__ dO, long long o_rs, float* __restrict__ dX, long long dx_rs,
+                 float* __restrict__ dgate, long long dg_rs, long long R, int C, int slot) {
+  constexpr int Kr = KrOf<L, M>::value();
+  const S2Tables& T = g_tab[slot];
+  const long long total = R * C;
+  for (long long w = (long long)blockIdx.x * blockDim.x + threadIdx.x; w < total; w += (long long)gridDim.x * blockDim.x) {
+    const long long r = w / C;
+    const int c = (int)(w % C);
+    float x[Kr], go[Kr], dx[Kr];
+#pragma unroll
+    for (int p = 0; p < Kr; ++p) {
+      x[p] = __ldg(X + r * x_rs + (long long)p * C + c);
+      // the l = 0 output row is overwritten by the gate path -> no gradient through the grid
+      go[p] = (p > 0 || gate == nullptr) ? __ldg(dO + r * o_rs + (long long)p * C + c) : 0.f;
+      dx[p] = 0.f;
+    }
+#pragma unroll 1
+    for (int b = 0; b < S2_RES; ++b) {
+      float up[M + 1], un[M + 1], hp[M + 1], hn[M + 1], wp[M + 1], wn[M + 1];
+      lat_fwd<L, M, MP>(x, T.Pt, b, up, un);     // grid values of x on ring b
+      lat_fwd<L, M, MP>(go, T.Pf, b, hp, hn);    // from_grid^T applied to dO on ring b
+#pragma unroll
+      for (int mi = 0; mi <= M; ++mi) wp[mi] = wn[mi] = 0.f;
+#pragma unroll
+      for (int a = 0; a < S2_RES; ++a) {
+        float g = up[0], h = hp[0];
+#pragma unroll
+        for (int mi = 1; mi <= M; ++mi) {
+          g = fmaf(T.ct[a][mi], up[mi], fmaf(T.st[a][mi], un[mi], g));
+          h = fmaf(T.ct[a][mi], hp[mi], fmaf(T.st[a][mi], hn[mi], h));
+        }
+        const float t = h * eqv2_dsilu(g);
+        wp[0] += t;
+#pragma unroll
+        for (int mi = 1; mi <= M; ++mi) {
+          wp[mi] = fmaf(T.ct[a][mi], t, wp[mi]);
+          wn[mi] = fmaf(T.st[a][mi], t, wn[mi]);
+        }
+      }
+      lat_bwd<L, M, MP>(dx, T.Pt, b, wp, wn);
+    }
+#pragma unroll
+    for (int p = 0; p < Kr; ++p) dX[r * dx_rs + (long long)p * C + c] = dx[p];
+    if (gate != nullptr) {
+      const float gv = __ldg(gate + r * g_rs + c);
+      dgate[r * dg_rs + c] = __ldg(dO + r * o_rs + c) * eqv2_dsilu(gv);
+    }
+  }
+}
+
+inline unsigned s2_grid_blocks(long long total) {
+  long long b = (total + S2_THREADS - 1) / S2_THREADS;
+  const long long cap = 148LL * 16;
+  return (unsigned)(b < cap ? (b > 0 ? b : 1) : cap);
+}
+
+}  // namespace
+
+#define EQV2_S2_CONFIGS(X) X(2, 2) X(3, 2) X(3, 3) X(4, 2) X(4, 4) X(6, 2) X(6, 6) X(1, 1) X(2, 1) X(5, 2) X(5, 5)
+
+extern "C" int eqv2_s2sep_supported(int lmax, int mmax) {
+#define X(L_, M_) if (lmax == L_ && mmax == M_) return 1;
+  EQV2_S2_CONFIGS(X)
+#undef X
+  return 0;
+}
+
+// tables: host pointer to an S2Tables-shaped float block (see ops.py::S2Factors), copied into constant slot 0/1
+extern "C" int eqv2_s2sep_set_tables(const float* host_tables, int nfloats, int slot, void* stream) {
+  EQV2_REQUIRE(slot == 0 || slot == 1, "s2sep_set_tables: slot must be 0 or 1");
+  EQV2_REQUIRE(nfloats == (int)(sizeof(S2Tables) / sizeof(float)), "s2sep_set_tables: expected %d floats, got %d",
+               (int)(sizeof(S2Tables) / sizeof(float)), nfloats);
+#ifdef EQV2_CPU_EMU
+  memcpy(&g_tab[slot], host_tables, sizeof(S2Tables));
+#else
+  cudaError_t e = cudaMemcpyToSymbolAsync(g_tab, host_tables, sizeof(S2Tables), (size_t)slot * sizeof(S2Tables),
+                                          cudaMemcpyHostToDevice, (cudaStream_t)stream);
+  EQV2_REQUIRE(e == cudaSuccess, "s2sep_set_tables: %s", cudaGetErrorString(e));
+#endif
+  return 0;
+}
+
+extern "C" int eqv2_s2sep_fwd(const float* Xp, long long x_rs, const float* gate, long long g_rs, float* O, long long o_rs,
+                              long long R, int C, int lmax, int mmax, int m_primary, int slot, void* stream) {
+  if (R == 0) return 0;
+  const unsigned blocks = s2_grid_blocks(R * C);
+#define X(L_, M_)                                                                                                        \
+  if (lmax == L_ && mmax == M_) {                                                                                        \
+    auto kfn = m_primary ? s2sep_fwd_kernel<L_, M_, true> : s2sep_fwd_kernel<L_, M_, false>;                             \
+    EQV2_LAUNCH(kfn, dim3(blocks), dim3(S2_THREADS), 0, stream, Xp, x_rs, gate, g_rs, O, o_rs, R, C, slot);               \
+    EQV2_CHECK_LAUNCH("eqv2_s2sep_fwd");                                                                                 \
+    return 0;                                                                                                            \
+  }
+  EQV2_S2_CONFIGS(X)
+#undef X
+  eqv2_set_error("s2sep_fwd: (lmax, mmax) = (%d, %d) not instantiated", lmax, mmax);
+  return 1;
+}
+
+extern "C" int eqv2_s2sep_bwd(const float* Xp, long long x_rs, const float* gate, long long g_rs, const float* dO,
+                              long long o_rs, float* dX, long long dx_rs, float* dgate, long long dg_rs, long long R, int C,
+                              int lmax, int mmax, int m_primary, int slot, void* stream) {
+  if (R == 0) return 0;
+  const unsigned blocks = s2_grid_blocks(R * C);
+#define X(L_, M_)                                                                                                        \
+  if (lmax == L_ && mmax == M_) {                                                                                        \
+    auto kfn = m_primary ? s2sep_bwd_kernel<L_, M_, true> : s2sep_bwd_kernel<L_, M_, false>;                             \
+    EQV2_LAUNCH(kfn, dim3(blocks), dim3(S2_THREADS), 0, stream, Xp, x_rs, gate, g_rs, dO, o_rs, dX, dx_rs, dgate, dg_rs, R, C, slot); \
+    EQV2_CHECK_LAUNCH("eqv2_s2sep_bwd");                                                                                 \
+    return 0;                                                                                                            \
+  }
+  EQV2_S2_CONFIGS(X)
+#undef X
+  eqv2_set_error("s2sep_bwd: (lmax, mmax) = (%d, %d) not instantiated", lmax, mmax);
+  return 1;
+}

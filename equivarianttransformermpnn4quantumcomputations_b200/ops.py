@@ -304,13 +304,21 @@ def _plain(ld):
 
 
 def _pick_split(descs, reduce_dim_large):
+    """Split-K factor for reduction-heavy problems (weight gradients: K = #edges): choose the factor that
+    fills whole waves of 148 CTAs best, keeping >= 32 k-blocks per split."""
     if not reduce_dim_large:
         return 1
     tiles = sum(((d.M + 127) // 128) * ((d.N + 127) // 128) for d in descs)
     kmax = max(d.K for d in descs)
-    if tiles >= 148 or kmax < 2048:
-        return 1
-    return int(max(1, min(64, 296 // max(tiles, 1), kmax // 512)))
+    best, best_eff = 1, 0.0
+    for s in range(1, 9):
+        if s > 1 and kmax // (32 * s) < 32:
+            break
+        ctas = tiles * s
+        eff = ctas / (148.0 * ((ctas + 147) // 148))
+        if eff > best_eff + 0.04:
+            best, best_eff = s, eff
+    return best
 
 
 def _tc_addressable(d):
@@ -610,10 +618,13 @@ class RotInvReduceFn(torch.autograd.Function):
 # S2 activation + attention weights
 # ----------------------------------------------------------------------------------------------
 class GridMats:
-    """Padded [G, KP] to/from-grid matrices in a given coefficient order (so3.py:584-622)."""
+    """Kernel-side form of one SO3_Grid: padded dense [G, KP] to/from-grid matrices in a given coefficient
+    order (so3.py:584-622) and, when the grid is the resolution-18 one every config uses, the
+    latitude/longitude factor tables of the separable kernel (csrc/s2act_sep.cu)."""
 
-    def __init__(self, T, Fm, Kr, KP, G):
+    def __init__(self, T, Fm, Kr, KP, G, lmax, mmax, order, factors):
         self.T, self.F, self.Kr, self.KP, self.G = T, Fm, Kr, KP, G
+        self.lmax, self.mmax, self.order, self.factors = lmax, mmax, order, factors
 
     @classmethod
     def from_buffers(cls, to_grid, from_grid, lmax, mmax, order):
@@ -631,7 +642,59 @@ class GridMats:
         T = torch.zeros(G, KP, dtype=_F32, device=tg.device)
         Fm = torch.zeros(G, KP, dtype=_F32, device=tg.device)
         T[:, :Kr], Fm[:, :Kr] = tg, fg
-        return cls(T.contiguous(), Fm.contiguous(), Kr, KP, G)
+        factors = cls._factor_tables(to_grid, from_grid, lmax, mmax)
+        return cls(T.contiguous(), Fm.contiguous(), Kr, KP, G, lmax, mmax, order, factors)
+
+    @staticmethod
+    def _factor_tables(to_grid, from_grid, lmax, mmax):
+        """Flat fp32 block [Pt | Pf | cos | sin] if the buffers are the separable resolution-18 matrices
+        (verified to 2e-6 against the buffers themselves), else None -> dense kernel."""
+        res = to_grid.shape[0]
+        if res != 18 or to_grid.shape[1] != 18 or lmax > 6 or not _lib.lib().eqv2_s2sep_supported(lmax, mmax):
+            return None
+        Pt, Pf, ct, st = _so3_math.s2_grid_factors(lmax, mmax, res)
+        red = [(l, m) for l in range(lmax + 1) for m in range(-min(l, mmax), min(l, mmax) + 1)]
+        tg, fg = to_grid.detach().cpu().numpy(), from_grid.detach().cpu().numpy()
+        for i, (l, m) in enumerate(red):
+            trig = ct[:, m] if m >= 0 else st[:, -m]
+            if (np.abs(Pt[abs(m), :, l][:, None] * trig[None, :] - tg[:, :, i]).max() > 2e-6 or
+                    np.abs(Pf[abs(m), :, l][:, None] * trig[None, :] - fg[:, :, i]).max() > 2e-6 * max(1.0, np.abs(fg).max())):
+                return None
+        return np.ascontiguousarray(np.concatenate([a.reshape(-1) for a in (Pt, Pf, ct, st)]).astype(np.float32))
+
+
+_s2_slots = {}
+
+
+def _s2_bind_tables(mats, device):
+    """Make sure the constant-memory slot of this coefficient order holds `mats`' factor tables."""
+    slot = 0 if mats.order == "m" else 1
+    key = (str(device), slot)
+    if _s2_slots.get(key, (None,))[0] != (mats.lmax, mats.mmax):
+        _lib.call("eqv2_s2sep_set_tables", mats.factors.ctypes.data, int(mats.factors.size), slot, _lib.stream_ptr(),
+                  n_kernels=0)
+        _s2_slots[key] = ((mats.lmax, mats.mmax), mats.factors)     # keep the host block alive
+    return slot
+
+
+def _s2_fwd(mats, xp, x_rs, gp, g_rs, op, o_rs, R, C, device):
+    if mats.factors is not None:
+        slot = _s2_bind_tables(mats, device)
+        _lib.call("eqv2_s2sep_fwd", xp, x_rs, gp, g_rs, op, o_rs, R, C, mats.lmax, mats.mmax, int(mats.order == "m"), slot,
+                  _lib.stream_ptr())
+    else:
+        _lib.call("eqv2_s2act_fwd", xp, x_rs, gp, g_rs, op, o_rs, mats.T.data_ptr(), mats.F.data_ptr(), R, C, mats.Kr,
+                  mats.KP, mats.G, _s2_blocks(R, C), _lib.stream_ptr())
+
+
+def _s2_bwd(mats, xp, x_rs, gp, g_rs, dop, o_rs, dxp, dx_rs, dgp, dg_rs, R, C, device):
+    if mats.factors is not None:
+        slot = _s2_bind_tables(mats, device)
+        _lib.call("eqv2_s2sep_bwd", xp, x_rs, gp, g_rs, dop, o_rs, dxp, dx_rs, dgp, dg_rs, R, C, mats.lmax, mats.mmax,
+                  int(mats.order == "m"), slot, _lib.stream_ptr())
+    else:
+        _lib.call("eqv2_s2act_bwd", xp, x_rs, gp, g_rs, dop, o_rs, dxp, dx_rs, dgp, dg_rs, mats.T.data_ptr(),
+                  mats.F.data_ptr(), R, C, mats.Kr, mats.KP, mats.G, _s2_blocks(R, C), _lib.stream_ptr())
 
 
 def _s2_blocks(R, C):
@@ -651,9 +714,7 @@ class S2ActFn(torch.autograd.Function):
         R, Kr, C = x.shape
         assert Kr == mats.Kr
         out = torch.empty_like(x)
-        _lib.call("eqv2_s2act_fwd", x.data_ptr(), Kr * C, _lib.ptr(gate), C, out.data_ptr(), Kr * C,
-                  mats.T.data_ptr(), mats.F.data_ptr(), R, C, Kr, mats.KP, mats.G, _s2_blocks(R, C),
-                  _lib.stream_ptr())
+        _s2_fwd(mats, x.data_ptr(), Kr * C, _lib.ptr(gate), C, out.data_ptr(), Kr * C, R, C, x.device)
         ctx.save_for_backward(x, gate)
         ctx.mats = mats
         return out
@@ -666,9 +727,8 @@ class S2ActFn(torch.autograd.Function):
         R, Kr, C = x.shape
         gx = torch.empty_like(x)
         gg = torch.empty_like(gate) if gate is not None else None
-        _lib.call("eqv2_s2act_bwd", x.data_ptr(), Kr * C, _lib.ptr(gate), C, go.data_ptr(), Kr * C, gx.data_ptr(),
-                  Kr * C, _lib.ptr(gg), C, mats.T.data_ptr(), mats.F.data_ptr(), R, C, Kr, mats.KP, mats.G,
-                  _s2_blocks(R, C), _lib.stream_ptr())
+        _s2_bwd(mats, x.data_ptr(), Kr * C, _lib.ptr(gate), C, go.data_ptr(), Kr * C, gx.data_ptr(), Kr * C,
+                _lib.ptr(gg), C, R, C, x.device)
         return gx, gg, None
 
 
@@ -688,9 +748,7 @@ class EdgeActAlphaFn(torch.autograd.Function):
         assert W == extra + Kr * H
         Z = torch.empty(E, Kr * H, dtype=_F32, device=Y.device)
         yp = Y.data_ptr()
-        _lib.call("eqv2_s2act_fwd", yp + 4 * extra, W, yp + 4 * heads * ach, W, Z.data_ptr(), Kr * H,
-                  mats.T.data_ptr(), mats.F.data_ptr(), E, H, Kr, mats.KP, mats.G, _s2_blocks(E, H),
-                  _lib.stream_ptr())
+        _s2_fwd(mats, yp + 4 * extra, W, yp + 4 * heads * ach, W, Z.data_ptr(), Kr * H, E, H, Y.device)
         logits = torch.empty(E, heads, dtype=_F32, device=Y.device)
         alpha = torch.empty(E, heads, dtype=_F32, device=Y.device)
         ln_w_c = ln_w.contiguous() if ln_w is not None else None
@@ -717,9 +775,8 @@ class EdgeActAlphaFn(torch.autograd.Function):
         if gZ is None:
             gZ = torch.zeros(E, Kr * H, dtype=_F32, device=dev)
         gZ = gZ.contiguous()
-        _lib.call("eqv2_s2act_bwd", yp + 4 * extra, W, yp + 4 * heads * ach, W, gZ.data_ptr(), Kr * H,
-                  gp + 4 * extra, W, gp + 4 * heads * ach, W, mats.T.data_ptr(), mats.F.data_ptr(), E, H, Kr,
-                  mats.KP, mats.G, _s2_blocks(E, H), _lib.stream_ptr())
+        _s2_bwd(mats, yp + 4 * extra, W, yp + 4 * heads * ach, W, gZ.data_ptr(), Kr * H, gp + 4 * extra, W,
+                gp + 4 * heads * ach, W, E, H, dev)
         if galpha is None:
             galpha = torch.zeros_like(alpha)
         galpha = galpha.contiguous()

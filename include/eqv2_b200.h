@@ -84,6 +84,17 @@ int eqv2_s2act_bwd(const float* X, long long x_rs, const float* gate, long long 
                    const float* to_grid, const float* from_grid, long long R, int C, int Kr, int KP, int G,
                    int nblocks, void* stream);
 
+/* latitude/longitude-factorised version of the same operator (csrc/s2act_sep.cu): resolution-18 grids,
+ * factor tables (float block laid out as [7][18][7] Pt | [7][18][7] Pf | [18][7] cos | [18][7] sin) in one
+ * of two __constant__ slots; m_primary selects the coefficient order of X / O. */
+int eqv2_s2sep_supported(int lmax, int mmax);
+int eqv2_s2sep_set_tables(const float* host_tables, int nfloats, int slot, void* stream);
+int eqv2_s2sep_fwd(const float* X, long long x_rs, const float* gate, long long g_rs, float* O, long long o_rs,
+                   long long R, int C, int lmax, int mmax, int m_primary, int slot, void* stream);
+int eqv2_s2sep_bwd(const float* X, long long x_rs, const float* gate, long long g_rs, const float* dO, long long o_rs,
+                   float* dX, long long dx_rs, float* dgate, long long dg_rs, long long R, int C, int lmax, int mmax,
+                   int m_primary, int slot, void* stream);
+
 /* ---- attention logits + segment softmax (transformer_block.py:311-315) ------------------- */
 int eqv2_attn_alpha_fwd(const float* Y, long long y_rs, const float* ln_w /*or NULL*/, const float* ln_b,
                         const float* alpha_dot /*[heads,ach]*/, const int* rowptr_dst, const int* perm_dst,
