@@ -59,6 +59,10 @@ struct TcGroup {
   const float* bias;
   int M, N, K;
   long long lda, ldb, ldc;
+  // two-level addressing of the NON-contiguous index r of an operand (degree slabs of [N,K,C] node tensors):
+  // offset(r) = (r / rpb) * bs + (r % rpb) * ld ; rpb == 0 means plain r * ld
+  int a_rpb, b_rpb, c_rpb;
+  long long a_bs, b_bs, c_bs;
   int a_mn;        // 1: A stored [K,M] (row index contiguous)   0: [M,K]
   int b_mn;        // 1: B stored [K,N]                          0: [N,K]
   int accumulate;  // C += result
@@ -165,30 +169,36 @@ __device__ __forceinline__ void cp_async_arrive_noinc(uint32_t bar) {
   asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(bar) : "memory");
 }
 
+__device__ __forceinline__ long long strided_off(int r, int rpb, long long bs, long long ld) {
+  if (rpb == 0) return (long long)r * ld;
+  const int q = r / rpb;
+  return (long long)q * bs + (long long)(r - q * rpb) * ld;
+}
+
 // Per-thread view of its 8 chunks of one operand tile: everything that does not change along K.
 struct ChunkPlan {
-  const float* ptr[8];   // source of the chunk at k-block 0 (nullptr: row out of range)
+  long long rowoff[8];   // element offset of the chunk's row part (-1: row out of range)
   uint32_t off[8];       // byte offset inside the tile (final swizzled position)
   uint32_t bytes[8];     // 16, or fewer for a ragged row tail of a row-contiguous source
-  int kk[8];             // k of the chunk inside the k-block (first k for K-contiguous sources)
+  int kk[8];             // k of the chunk inside the k-block (first of 4 for K-contiguous sources)
 };
 
-__device__ __forceinline__ void plan_tile(ChunkPlan& P, const float* __restrict__ src, long long ld, int mn, int row0,
-                                          int rows, int tid) {
+__device__ __forceinline__ void plan_tile(ChunkPlan& P, long long ld, int rpb, long long bs, int mn, int row0, int rows,
+                                          int tid) {
 #pragma unroll
   for (int it = 0; it < 8; ++it) {
     const int idx = it * 128 + tid;
     if (!mn) {
       const int r = idx >> 3, c = idx & 7;                  // 8 x 16 B chunks per row
       const int gr = row0 + r;
-      P.ptr[it] = (gr < rows) ? src + (long long)gr * ld + c * 4 : nullptr;
+      P.rowoff[it] = (gr < rows) ? strided_off(gr, rpb, bs, ld) : -1;
       P.bytes[it] = 16;
       P.kk[it] = c * 4;
       P.off[it] = (uint32_t)(r * 128 + ((c ^ (r & 7)) << 4));
     } else {
       const int kk = idx >> 5, c32 = idx & 31;              // 32 x 16 B chunks (128 rows) per k
       const int gr = row0 + c32 * 4;
-      P.ptr[it] = (gr < rows) ? src + (long long)kk * ld + gr : nullptr;
+      P.rowoff[it] = (gr < rows) ? (long long)gr : -1;
       P.bytes[it] = (uint32_t)max(0, min(16, (rows - gr) * 4));
       P.kk[it] = kk;
       const int rb = c32 >> 3, c = c32 & 7, k4 = kk & 3, kg = kk >> 2;
@@ -197,12 +207,14 @@ __device__ __forceinline__ void plan_tile(ChunkPlan& P, const float* __restrict_
   }
 }
 
-__device__ __forceinline__ void issue_tile(const ChunkPlan& P, const float* __restrict__ base, long long kstep_elems,
-                                           int k0, int K, uint32_t hi) {
+__device__ __forceinline__ void issue_tile(const ChunkPlan& P, const float* __restrict__ base, long long ld, int rpb,
+                                           long long bs, int mn, int k0, int K, uint32_t hi) {
 #pragma unroll
   for (int it = 0; it < 8; ++it) {
-    const bool ok = (P.ptr[it] != nullptr) && (k0 + P.kk[it] < K);
-    cp_async16(hi + P.off[it], ok ? P.ptr[it] + kstep_elems : base, ok ? P.bytes[it] : 0u);
+    const int gk = k0 + P.kk[it];
+    const bool ok = (P.rowoff[it] >= 0) && (gk < K);
+    const long long koff = mn ? strided_off(gk, rpb, bs, ld) : (long long)gk;
+    cp_async16(hi + P.off[it], ok ? base + P.rowoff[it] + koff : base, ok ? P.bytes[it] : 0u);
   }
 }
 
@@ -281,16 +293,15 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) gemm_tc_kernel(const __grid_co
     // ================= producers: cp.async only, up to STAGES blocks ahead of the tensor core =================
     const int tid = threadIdx.x;          // 0..127
     ChunkPlan pa, pb;
-    plan_tile(pa, G.A, G.lda, G.a_mn, m0, G.M, tid);
-    plan_tile(pb, G.B, G.ldb, G.b_mn, n0, G.N, tid);
-    const long long a_kstride = G.a_mn ? G.lda : 1, b_kstride = G.b_mn ? G.ldb : 1;
+    plan_tile(pa, G.lda, G.a_rpb, G.a_bs, G.a_mn, m0, G.M, tid);
+    plan_tile(pb, G.ldb, G.b_rpb, G.b_bs, G.b_mn, n0, G.N, tid);
     for (int i = 0; i < nkb; ++i) {
       const int s = i % STAGES, round = i / STAGES;
       mbar_wait(smem_u32(&empty[s]), (uint32_t)((round & 1) ^ 1));
       const uint32_t st = smem_u32(tiles + (size_t)s * STAGE_BYTES);
       const int k0 = (kb0 + i) * BK;
-      issue_tile(pa, G.A, (long long)k0 * a_kstride, k0, G.K, st);
-      issue_tile(pb, G.B, (long long)k0 * b_kstride, k0, G.K, st + 2 * TILE_BYTES);
+      issue_tile(pa, G.A, G.lda, G.a_rpb, G.a_bs, G.a_mn, k0, G.K, st);
+      issue_tile(pb, G.B, G.ldb, G.b_rpb, G.b_bs, G.b_mn, k0, G.K, st + 2 * TILE_BYTES);
       cp_async_arrive_noinc(smem_u32(&raw_full[s]));
     }
   } else if (warp == MMA_WARP) {
@@ -388,7 +399,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) gemm_tc_kernel(const __grid_co
     const bool atomic = P.split_k > 1;
     if (row < G.M) {
       const int col0 = half * 64;
-      float* crow = G.C + (long long)row * G.ldc + n0 + col0;
+      float* crow = G.C + strided_off(row, G.c_rpb, G.c_bs, G.ldc) + n0 + col0;
       const int ncol = min(64, G.N - n0 - col0);
       const bool vec = (ncol == 64) && ((reinterpret_cast<uintptr_t>(crow) & 15) == 0) && !atomic;
       if (vec) {
@@ -438,10 +449,10 @@ extern "C" int eqv2_gemm_tc(const eqv2_gemm_desc* descs, int ngroups, int split_
   for (int i = 0; i < ngroups; ++i) {
     const eqv2_gemm_desc& d = descs[i];
     EQV2_REQUIRE(d.A && d.B && d.C, "eqv2_gemm_tc: null operand in group %d", i);
-    EQV2_REQUIRE(d.a_rpb >= (1ll << 31) && d.b_rpb >= (1ll << 31) && d.c_rpb >= (1ll << 31),
-                 "eqv2_gemm_tc: two-level strided operands are served by eqv2_gemm_f32");
     EQV2_REQUIRE((d.a_ld % 4) == 0 && (d.b_ld % 4) == 0 && (((uintptr_t)d.A | (uintptr_t)d.B) & 15) == 0,
                  "eqv2_gemm_tc: operands must be 16-byte aligned with leading dimensions multiple of 4");
+    EQV2_REQUIRE((d.a_rpb >= (1ll << 31) || d.a_bs % 4 == 0) && (d.b_rpb >= (1ll << 31) || d.b_bs % 4 == 0),
+                 "eqv2_gemm_tc: block strides of two-level operands must be multiples of 4");
     // the contiguous dimension is read in float4 units
     EQV2_REQUIRE(d.transA ? true : (d.K % 4) == 0, "eqv2_gemm_tc: K must be a multiple of 4 for K-contiguous A");
     EQV2_REQUIRE(d.transB ? (d.K % 4) == 0 : true, "eqv2_gemm_tc: K must be a multiple of 4 for K-contiguous B");
@@ -449,6 +460,9 @@ extern "C" int eqv2_gemm_tc(const eqv2_gemm_desc* descs, int ngroups, int split_
     g.A = d.A; g.B = d.B; g.C = d.C; g.bias = d.bias;
     g.M = d.M; g.N = d.N; g.K = d.K;
     g.lda = d.a_ld; g.ldb = d.b_ld; g.ldc = d.c_ld;
+    g.a_rpb = d.a_rpb >= (1ll << 31) ? 0 : (int)d.a_rpb; g.a_bs = d.a_bs;
+    g.b_rpb = d.b_rpb >= (1ll << 31) ? 0 : (int)d.b_rpb; g.b_bs = d.b_bs;
+    g.c_rpb = d.c_rpb >= (1ll << 31) ? 0 : (int)d.c_rpb; g.c_bs = d.c_bs;
     g.a_mn = d.transA ? 1 : 0;
     g.b_mn = d.transB ? 0 : 1;
     g.accumulate = d.accumulate;

@@ -323,9 +323,9 @@ def _pick_split(descs, reduce_dim_large):
 
 def _tc_addressable(d):
     """Can the tensor-core engine address this problem? (see eqv2_gemm_tc in include/eqv2_b200.h)"""
-    if min(d.a_rpb, d.b_rpb, d.c_rpb) < (1 << 31):
-        return False
     if d.a_ld % 4 or d.b_ld % 4 or (d.A % 16) or (d.B % 16):
+        return False
+    if (d.a_rpb < (1 << 31) and d.a_bs % 4) or (d.b_rpb < (1 << 31) and d.b_bs % 4):
         return False
     if (not d.transA and d.K % 4) or (d.transB and d.K % 4):
         return False

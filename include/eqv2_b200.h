@@ -43,8 +43,8 @@ typedef struct {
 
 /* exact fp32 (FFMA) engine: any operand addressing */
 int eqv2_gemm_f32(const eqv2_gemm_desc* descs, int ngroups, int split_k, void* stream);
-/* tensor-core engine (tcgen05.mma kind::tf32, TMEM accumulators): plain row-major operands only
- * (rpb >= 2^31), 16-byte aligned, leading dimensions multiple of 4.
+/* tensor-core engine (tcgen05.mma kind::tf32, TMEM accumulators): operands 16-byte aligned, leading
+ * dimensions and block strides multiples of 4 (the two-level stride applies to the non-contiguous index).
  * mode 0 = 3xTF32 split (fp32-class accuracy), mode 1 = 1xTF32. */
 int eqv2_gemm_tc(const eqv2_gemm_desc* descs, int ngroups, int split_k, int mode, void* stream);
 

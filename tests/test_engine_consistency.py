@@ -1,0 +1,50 @@
+"""GPU only: a mid-size OC20-shaped model (large enough that every dense contraction runs on the tcgen05
+engine, including the two-level strided SO3_LinearV2 problems) must give the same energies / forces /
+parameter gradients in 3xTF32 mode as with the exact FFMA engine -- the 1e-5 bound of the fp32 mode."""
+import pytest
+import torch
+
+from helpers import pkg, rel_err
+
+
+def _run(mode, data, seed_frames):
+    ops = pkg("ops")
+    oc20 = pkg("models.equiformerv2_oc20")
+    ops.set_gemm_mode(mode)
+    try:
+        torch.manual_seed(0)
+        model = oc20.EquiformerV2_OC20(num_layers=2, sphere_channels=64, attn_hidden_channels=32, num_heads=4,
+                                       attn_alpha_channels=32, attn_value_channels=16, ffn_hidden_channels=64,
+                                       lmax_list=[4], mmax_list=[2], edge_channels=64, alpha_drop=0.0, drop_path_rate=0.0,
+                                       max_radius=8.0).cuda()
+        gen = torch.Generator().manual_seed(1)
+        with torch.no_grad():
+            for p in model.parameters():
+                p.add_(0.02 * torch.randn(p.shape, generator=gen).cuda())
+        torch.manual_seed(seed_frames)
+        energy, forces = model(data)
+        w = torch.linspace(-1, 1, forces.numel(), device="cuda").view_as(forces)
+        (energy.sum() + (forces * w).sum()).backward()
+        return energy.detach(), forces.detach(), {k: p.grad.clone() for k, p in model.named_parameters()}
+    finally:
+        ops.set_gemm_mode("tf32x3")
+
+
+@pytest.mark.gpu
+def test_tensor_core_mode_matches_ffma_mode():
+    if not torch.cuda.is_available():
+        pytest.skip("no CUDA device")
+    _lib = pkg("_lib")
+    _lib._state["lib"] = None
+    syn = pkg("synthetic")
+    data = {k: (v.cuda() if torch.is_tensor(v) else v) for k, v in syn.oc20_batch(4, seed=5).items()}
+    e0, f0, g0 = _run("fp32", data, 7)
+    _lib.start_kernel_timing()
+    e1, f1, g1 = _run("tf32x3", data, 7)
+    prof = _lib.stop_kernel_timing()
+    assert prof.get("eqv2_gemm_tc", {}).get("calls", 0) >= 20, "the tensor-core engine did not run"
+    assert rel_err(e1, e0) < 1e-5 and rel_err(f1, f0) < 1e-5
+    bad = [(k, rel_err(g1[k], g0[k])) for k in g0 if rel_err(g1[k], g0[k]) > 1e-4]
+    assert not bad, bad
+    e2, f2, _ = _run("tf32", data, 7)
+    assert rel_err(e2, e0) < 5e-3 and rel_err(f2, f0) < 5e-3
