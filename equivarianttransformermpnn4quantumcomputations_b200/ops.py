@@ -333,7 +333,12 @@ def _tc_addressable(d):
 
 
 def _tc_ok(d):
-    return _tc_addressable(d) and d.M * d.N * d.K >= (1 << 21)      # tiny problems are launch-bound either way
+    """Engine choice (measured, profiles/r01_bench_e): one CTA per 128x128 tile pays a fixed TMEM-allocation /
+    pipeline-fill / epilogue cost, so short reductions (K < 256, i.e. < 8 k-blocks) with few output columns
+    run faster on the FFMA engine."""
+    if not _tc_addressable(d) or d.M * d.N * d.K < (1 << 21):
+        return False
+    return d.K >= 256 or d.N >= 1024
 
 
 def run_gemm(descs, split_k=1):
