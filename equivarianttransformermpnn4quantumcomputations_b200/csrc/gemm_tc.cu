@@ -209,17 +209,30 @@ __device__ __forceinline__ void plan_tile(ChunkPlan& P, long long ld, int rpb, l
 
 __device__ __forceinline__ void issue_tile(const ChunkPlan& P, const float* __restrict__ base, long long ld, int rpb,
                                            long long bs, int mn, int k0, int K, uint32_t hi) {
+  if (!mn || rpb == 0) {          // common case: the k offset is a plain multiple -> no division in the loop
+    const long long kmul = mn ? ld : 1;
 #pragma unroll
-  for (int it = 0; it < 8; ++it) {
-    const int gk = k0 + P.kk[it];
-    const bool ok = (P.rowoff[it] >= 0) && (gk < K);
-    const long long koff = mn ? strided_off(gk, rpb, bs, ld) : (long long)gk;
-    cp_async16(hi + P.off[it], ok ? base + P.rowoff[it] + koff : base, ok ? P.bytes[it] : 0u);
+    for (int it = 0; it < 8; ++it) {
+      const int gk = k0 + P.kk[it];
+      const bool ok = (P.rowoff[it] >= 0) && (gk < K);
+      cp_async16(hi + P.off[it], ok ? base + P.rowoff[it] + (long long)gk * kmul : base, ok ? P.bytes[it] : 0u);
+    }
+  } else {
+#pragma unroll
+    for (int it = 0; it < 8; ++it) {
+      const int gk = k0 + P.kk[it];
+      const bool ok = (P.rowoff[it] >= 0) && (gk < K);
+      cp_async16(hi + P.off[it], ok ? base + P.rowoff[it] + strided_off(gk, rpb, bs, ld) : base, ok ? P.bytes[it] : 0u);
+    }
   }
 }
 
 // hi/lo split of a landed tile, elementwise and therefore layout-agnostic: chunk i of `hi` <-> chunk i of `lo`.
+// hi = v rounded to tf32 (ties away: add half an ulp to the magnitude bits, clear the low 13 bits),
+// lo = v - hi exactly (fp32); the tensor core reads lo's upper 19 bits, i.e. drops O(2^-21 |v|).
 // 256 worker threads, 4 chunks each.
+__device__ __forceinline__ float tf32_hi(float v) { return __uint_as_float((__float_as_uint(v) + 0x1000u) & 0xFFFFE000u); }
+
 __device__ __forceinline__ void split_tile(unsigned char* hi, unsigned char* lo, int wt) {
   float4 v[4];
 #pragma unroll
@@ -228,8 +241,8 @@ __device__ __forceinline__ void split_tile(unsigned char* hi, unsigned char* lo,
   for (int it = 0; it < 4; ++it) {
     const uint32_t off = (uint32_t)(it * 256 + wt) << 4;
     float4 h, l;
-    h.x = tf32_rna(v[it].x); h.y = tf32_rna(v[it].y); h.z = tf32_rna(v[it].z); h.w = tf32_rna(v[it].w);
-    l.x = tf32_rna(v[it].x - h.x); l.y = tf32_rna(v[it].y - h.y); l.z = tf32_rna(v[it].z - h.z); l.w = tf32_rna(v[it].w - h.w);
+    h.x = tf32_hi(v[it].x); h.y = tf32_hi(v[it].y); h.z = tf32_hi(v[it].z); h.w = tf32_hi(v[it].w);
+    l.x = v[it].x - h.x; l.y = v[it].y - h.y; l.z = v[it].z - h.z; l.w = v[it].w - h.w;
     *reinterpret_cast<float4*>(hi + off) = h;
     *reinterpret_cast<float4*>(lo + off) = l;
   }
@@ -260,7 +273,9 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) gemm_tc_kernel(const __grid_co
     if (tile_lin >= P.g[i].tile_start) gi = i;
   const TcGroup& G = P.g[gi];
   const int t = tile_lin - G.tile_start;
-  const int tm = t % G.tiles_m, tn = t / G.tiles_m;      // m fastest: concurrent CTAs share the B tile
+  // n fastest: CTAs that run together share the (large, streamed) A row panel through L2; the B panels are
+  // weights and stay L2-resident anyway (ncu r01c: m-fastest re-read A 5x from DRAM)
+  const int tn = t % G.tiles_n, tm = t / G.tiles_n;
   const int m0 = tm * BM, n0 = tn * BN;
   const int nkb_all = (G.K + BK - 1) / BK;
   const int per = (nkb_all + P.split_k - 1) / P.split_k;
