@@ -25,6 +25,10 @@ if REPO not in sys.path:
     sys.path.insert(0, REPO)
 PKG = "equivarianttransformermpnn4quantumcomputations_b200"
 
+# dram__bytes_read.sum + dram__bytes_write.sum per launch of the dominant kernel's largest launch (conv1 forward,
+# 153 GFLOP), from the committed `ncu --set full` capture (profiles/r01c_ncu_gemm_tc_summary.txt)
+TRAFFIC = {"eqv2_gemm_tc": 2.18e9}
+
 METRIC = "oc20_s2ef_train_structures_per_s"
 UNIT = "structures/s"
 
@@ -235,7 +239,9 @@ def run_b200(args):
         if r["flops"] > 0:
             achieved = r["flops"] / (r["ms"] * 1e-3) / 1e12
             roof = {"kernel": name, "bound": "tensor", "achieved": achieved, "peak": pk["tensor"], "unit": "TFLOP/s",
-                    "frac": achieved / pk["tensor"], "traffic": None, "peak_source": pk["src"] + " bf16 sustained",
+                    "frac": achieved / pk["tensor"], "traffic": TRAFFIC.get(name), "peak_source": pk["src"] + " bf16 sustained",
+                    "note": "fp32-accurate 3xTF32: 3 tensor-core passes at the TF32 rate (1/2 of bf16) -> ceiling = peak/6; "
+                            "cuBLAS TF32 measured 744 TFLOP/s on this pool -> 3x ceiling 248 TFLOP/s",
                     "launches_per_step": r["calls"], "avg_launch_ms": r["ms"] / r["calls"],
                     "share_of_step_kernel_time": r["ms"] / tot}
         else:
@@ -251,7 +257,9 @@ def run_b200(args):
                                        "(graph build + fwd + L1 loss + bwd + AdamW), ~80-atom slabs, 12 A cutoff, "
                                        "max 20 neighbours", "structures_per_gpu": B, "atoms_per_gpu": int(host["pos"].shape[0]),
                            "edges_per_gpu": E, "layers": kw["num_layers"], "params": model.num_params,
-                           "parallelism": f"dp{world}", "gemm_engine": "fp32 FFMA",
+                           "parallelism": f"dp{world}",
+                           "gemm_engine": "tcgen05 kind::tf32, 3xTF32 split with fp32 promotion (fp32-class accuracy); "
+                                          "short reductions and degree slabs on the FFMA engine",
                            "l2": "step working set (330 MB weights + >1 GB activations) exceeds the 126 MB L2"},
                 "e2e": {"value": e2e, "unit": UNIT, "ms_per_step": ms_e2e / args.steps, "h2d_bytes_per_step": h2d_bytes,
                         "d2h_bytes_per_step": 4},

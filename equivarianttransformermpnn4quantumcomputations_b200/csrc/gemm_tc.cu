@@ -281,8 +281,9 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) gemm_tc_kernel(const __grid_co
   const int per = (nkb_all + P.split_k - 1) / P.split_k;
   const int kb0 = ks * per, kb1 = min(nkb_all, kb0 + per);
   const int nkb = max(0, kb1 - kb0);
-  const bool want_lo = (P.mode == 0);
-  const int chunk = want_lo ? CHUNK_KB : max(nkb, 1);
+  const bool want_lo = ((P.mode & 1) == 0);
+  // bit 1 of mode (diagnostics): one long TMEM chain even in 3xTF32 mode -> isolates the cost of promotion
+  const int chunk = (want_lo && !(P.mode & 2)) ? CHUNK_KB : max(nkb, 1);
   const int nchunks = (nkb + chunk - 1) / chunk;
 
   if (threadIdx.x == 0) {
@@ -457,7 +458,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) gemm_tc_kernel(const __grid_co
 
 extern "C" int eqv2_gemm_tc(const eqv2_gemm_desc* descs, int ngroups, int split_k, int mode, void* stream) {
   EQV2_REQUIRE(ngroups >= 1 && ngroups <= EQV2_GEMM_MAX_GROUPS, "eqv2_gemm_tc: ngroups=%d out of range", ngroups);
-  EQV2_REQUIRE(split_k >= 1 && (mode == 0 || mode == 1), "eqv2_gemm_tc: bad split_k/mode");
+  EQV2_REQUIRE(split_k >= 1 && mode >= 0 && mode <= 3, "eqv2_gemm_tc: bad split_k/mode");
   TcParams P;
   memset(&P, 0, sizeof(P));
   int tiles = 0;
