@@ -60,6 +60,7 @@ _PROTOS = {
     "eqv2_radius_graph": [P, P, P, L, F, I, I, P, P, P, P, P, P, P, P],
     "eqv2_pbc_reps": [P, D, P, I, P],
     "eqv2_radius_graph_pbc": [P, P, P, P, P, L, D, I, I, I, P, P, P, P, P, P, P, P],
+    "eqv2_radius_graph_pbc27": [P, P, P, P, L, F, I, I, I, P, P, P, P, P, P, P, P, P],
     "eqv2_csr_from_index": [P, L, L, P, P, P, P, P],
     "eqv2_segment_sum_fwd": [P, L, P, P, L, I, P],
     "eqv2_segment_sum_bwd": [P, P, P, L, P],

@@ -247,6 +247,124 @@ radius_graph_pbc_kernel(const float* __restrict__ pos, const float* __restrict__
   if (mode == 0 && threadIdx.x == 0) deg[i] = written;
 }
 
+// ---------------------------------------------------------------------------------------------
+// MatPES builders (equiformerv2_MatPES.py:258-340 "v1", equiformerv2_MatPESv2.py:177-240 "v2"): fixed 27 images
+// (-1..1)^3 in meshgrid('ij') order, fp32 arithmetic in the reference's operation order:
+//   off_s = frac_s @ cell ; diff = (pos[dst] + off_s) - pos[src] ; keep |diff| < r_c (zero image: also > 1e-6).
+// One CTA per DESTINATION atom j; candidates (src i, image s) in (i, s) order.
+//   v1: ranking distance = |diff| ; emitted vector = diff.
+//   v2: ranking distance = |pos[dst] - pos[src]| (no offset!) ; emitted vector = pos[dst] - pos[src].
+// The image index is emitted too, so the caller can rebuild differentiable vectors from pos / cell.
+__global__ void __launch_bounds__(NB_THREADS)
+radius_graph_pbc27_kernel(const float* __restrict__ pos, const float* __restrict__ cell,
+                          const int* __restrict__ graph_ptr, const long long* __restrict__ batch, float cutoff,
+                          int max_nb, int version, int mode, int* __restrict__ deg, const int* __restrict__ rowptr,
+                          long long* __restrict__ src_out, long long* __restrict__ dst_out, int* __restrict__ img_out,
+                          float* __restrict__ dist_out, float* __restrict__ vec_out, int* __restrict__ err) {
+  __shared__ float sd[NB_CAP];      // ranking distance
+  __shared__ int sc[NB_CAP];        // candidate code: (i - beg) * 27 + s
+  __shared__ int scnt;
+  __shared__ int scratch[NB_THREADS / 32];
+  const int j = blockIdx.x;
+  const int g = (int)batch[j];
+  const int beg = graph_ptr[g], end = graph_ptr[g + 1];
+  const float* c = cell + 9 * g;
+  const float xj = pos[3 * j], yj = pos[3 * j + 1], zj = pos[3 * j + 2];
+  if (threadIdx.x == 0) scnt = 0;
+  __syncthreads();
+  const int total = (end - beg) * 27;
+  for (int base = 0; base < total; base += NB_THREADS) {
+    const int t = base + threadIdx.x;
+    float d = 0.f;
+    bool ok = false;
+    if (t < total) {
+      const int i = beg + t / 27, s = t % 27;
+      const float a = (float)(s / 9 - 1), b = (float)((s / 3) % 3 - 1), cc = (float)(s % 3 - 1);
+      // frac @ cell, accumulated k = 0, 1, 2 without contraction
+      const float ox = __fadd_rn(__fadd_rn(__fmul_rn(a, c[0]), __fmul_rn(b, c[3])), __fmul_rn(cc, c[6]));
+      const float oy = __fadd_rn(__fadd_rn(__fmul_rn(a, c[1]), __fmul_rn(b, c[4])), __fmul_rn(cc, c[7]));
+      const float oz = __fadd_rn(__fadd_rn(__fmul_rn(a, c[2]), __fmul_rn(b, c[5])), __fmul_rn(cc, c[8]));
+      const float dx = __fadd_rn(__fadd_rn(xj, ox), -pos[3 * i]), dy = __fadd_rn(__fadd_rn(yj, oy), -pos[3 * i + 1]),
+                  dz = __fadd_rn(__fadd_rn(zj, oz), -pos[3 * i + 2]);
+      const float dtrue = dist_f32(dx, dy, dz);
+      ok = (dtrue < cutoff) && (s != 13 || dtrue > 1e-6f);
+      d = (version == 1) ? dtrue : dist_f32(xj - pos[3 * i], yj - pos[3 * i + 1], zj - pos[3 * i + 2]);
+    }
+    const unsigned bal = __ballot_sync(0xffffffffu, ok);
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    __syncthreads();
+    if (lane == 0) scratch[warp] = __popc(bal);
+    __syncthreads();
+    int off = scnt;
+    for (int w = 0; w < warp; ++w) off += scratch[w];
+    off += __popc(bal & ((1u << lane) - 1u));
+    if (ok) {
+      if (off < NB_CAP) { sd[off] = d; sc[off] = t; }
+      else atomicExch(err, 1);
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      int tt = 0;
+      for (int w = 0; w < NB_THREADS / 32; ++w) tt += scratch[w];
+      scnt += tt;
+    }
+    __syncthreads();
+  }
+  const int cnt = min(scnt, NB_CAP);
+  const bool trunc = (max_nb >= 0) && (cnt > max_nb);
+  if (mode == 0) {
+    if (threadIdx.x == 0) deg[j] = trunc ? max_nb : cnt;
+    return;
+  }
+  const int out0 = rowptr[j];
+  int written = 0;
+  for (int base = 0; base < cnt; base += NB_THREADS) {
+    const int q = base + threadIdx.x;
+    bool keep = false;
+    if (q < cnt) {
+      keep = true;
+      if (trunc) {
+        int rank = 0;
+        const float dq = sd[q];
+        for (int k = 0; k < cnt; ++k) rank += (sd[k] < dq) || (sd[k] == dq && k < q);
+        keep = rank < max_nb;
+      }
+    }
+    const unsigned bal = __ballot_sync(0xffffffffu, keep);
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    __syncthreads();
+    if (lane == 0) scratch[warp] = __popc(bal);
+    __syncthreads();
+    int off = written;
+    for (int w = 0; w < warp; ++w) off += scratch[w];
+    off += __popc(bal & ((1u << lane) - 1u));
+    int chunk = 0;
+    for (int w = 0; w < NB_THREADS / 32; ++w) chunk += scratch[w];
+    if (keep) {
+      const int o = out0 + off;
+      const int i = beg + sc[q] / 27, s = sc[q] % 27;
+      float vx, vy, vz;
+      if (version == 1) {
+        const float a = (float)(s / 9 - 1), b = (float)((s / 3) % 3 - 1), cc = (float)(s % 3 - 1);
+        const float ox = __fadd_rn(__fadd_rn(__fmul_rn(a, c[0]), __fmul_rn(b, c[3])), __fmul_rn(cc, c[6]));
+        const float oy = __fadd_rn(__fadd_rn(__fmul_rn(a, c[1]), __fmul_rn(b, c[4])), __fmul_rn(cc, c[7]));
+        const float oz = __fadd_rn(__fadd_rn(__fmul_rn(a, c[2]), __fmul_rn(b, c[5])), __fmul_rn(cc, c[8]));
+        vx = __fadd_rn(__fadd_rn(xj, ox), -pos[3 * i]);
+        vy = __fadd_rn(__fadd_rn(yj, oy), -pos[3 * i + 1]);
+        vz = __fadd_rn(__fadd_rn(zj, oz), -pos[3 * i + 2]);
+      } else {
+        vx = xj - pos[3 * i]; vy = yj - pos[3 * i + 1]; vz = zj - pos[3 * i + 2];
+      }
+      src_out[o] = i;
+      dst_out[o] = j;
+      img_out[o] = s;
+      dist_out[o] = dist_f32(vx, vy, vz);
+      vec_out[3 * o] = vx; vec_out[3 * o + 1] = vy; vec_out[3 * o + 2] = vz;
+    }
+    written += chunk;
+  }
+}
+
 // reps[g,k] = ceil(cutoff / h_k), h_k = |det cell| / |a_{k+1} x a_{k+2}|  (fp64)
 __global__ void pbc_reps_kernel(const float* __restrict__ cell, double cutoff, int* __restrict__ reps, int B) {
   const int g = blockIdx.x * blockDim.x + threadIdx.x;
@@ -408,6 +526,18 @@ extern "C" int eqv2_radius_graph_pbc(const float* pos, const float* cell, const 
   EQV2_LAUNCH(radius_graph_pbc_kernel, dim3((unsigned)N), dim3(NB_THREADS), 0, stream, pos, cell, graph_ptr, batch,
               reps, cutoff, max_nb, strict, mode, deg, rowptr, nbr, ctr, dist, vec, err);
   EQV2_CHECK_LAUNCH("eqv2_radius_graph_pbc");
+  return 0;
+}
+
+extern "C" int eqv2_radius_graph_pbc27(const float* pos, const float* cell, const int* graph_ptr, const long long* batch,
+                                       long long N, float cutoff, int max_nb, int version, int mode, int* deg,
+                                       const int* rowptr, long long* src, long long* dst, int* img, float* dist,
+                                       float* vec, int* err, void* stream) {
+  if (N == 0) return 0;
+  EQV2_REQUIRE(version == 1 || version == 2, "radius_graph_pbc27: version must be 1 or 2");
+  EQV2_LAUNCH(radius_graph_pbc27_kernel, dim3((unsigned)N), dim3(NB_THREADS), 0, stream, pos, cell, graph_ptr, batch,
+              cutoff, max_nb, version, mode, deg, rowptr, src, dst, img, dist, vec, err);
+  EQV2_CHECK_LAUNCH("eqv2_radius_graph_pbc27");
   return 0;
 }
 

@@ -230,6 +230,38 @@ def radius_graph_pbc(pos, cell, natoms, batch, cutoff, max_neighbors, strict=Fal
     return ei, d, v
 
 
+def radius_graph_matpes(pos, cell, natoms, batch, cutoff, max_neighbors, version):
+    """MatPES periodic builders (27 images).  version 1: equiformerv2_MatPES.py:258-340; version 2:
+    equiformerv2_MatPESv2.py:177-240.  Returns (edge_index [2,E] row 0 = src, row 1 = dst, edge_distance,
+    edge_vec, image index int32 [E]); topology only -- no gradient (the reference builds it on detached
+    positions in v2; differentiable vectors are rebuilt from pos/cell by the model wrapper)."""
+    _lib.check_device(pos, cell, batch)
+    pos = pos.detach().to(_F32).contiguous()
+    cell = cell.detach().to(_F32).contiguous()
+    batch = batch.contiguous()
+    N = int(pos.shape[0])
+    dev = pos.device
+    gp = _graph_ptr(natoms, dev)
+    mx = -1 if max_neighbors is None else int(max_neighbors)
+    holder = {}
+
+    def launch(mode, deg, rowptr, outs, err):
+        ei, d, v = outs if outs is not None else (None, None, None)
+        img = torch.empty(ei.shape[1], dtype=torch.int32, device=dev) if ei is not None else None
+        holder["img"] = img
+        _lib.call("eqv2_radius_graph_pbc27", pos.data_ptr(), cell.data_ptr(), gp.data_ptr(), batch.data_ptr(), N,
+                  float(cutoff), mx, int(version), mode, deg.data_ptr(), rowptr.data_ptr(),
+                  _lib.ptr(ei[0]) if ei is not None else None, _lib.ptr(ei[1]) if ei is not None else None,
+                  _lib.ptr(img), _lib.ptr(d), _lib.ptr(v), err.data_ptr(), _lib.stream_ptr())
+
+    ei, d, v, rowptr = _count_scan_fill(N, dev, launch)
+    img = holder.get("img")
+    if img is None:
+        img = torch.empty(0, dtype=torch.int32, device=dev)
+    _register_plan(ei, N, rowptr)
+    return ei, d, v, img
+
+
 class SegmentSumFn(torch.autograd.Function):
     """Per-graph sum of per-atom scalars; `batch` must be non-decreasing (every reference collate
     function produces it that way).  Deterministic replacement of the index_add_ readouts."""

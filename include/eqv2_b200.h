@@ -143,6 +143,12 @@ int eqv2_radius_graph_pbc(const float* pos, const float* cell, const int* graph_
                           const int* reps, long long N, double cutoff, int max_nb, int strict, int mode, int* deg,
                           const int* rowptr, long long* nbr, long long* ctr, float* dist, float* vec, int* err,
                           void* stream);
+/* MatPES builders: 27 images, fp32; version 1 = equiformerv2_MatPES.py:258-340 (true image vectors),
+ * version 2 = equiformerv2_MatPESv2.py:177-240 / equiformerv2_MatPES_GATAV2.py:285-349 (ranking and vectors
+ * without the image offset).  row src = i, row dst = j of diff[i,j] = pos[j] + offset - pos[i]. */
+int eqv2_radius_graph_pbc27(const float* pos, const float* cell, const int* graph_ptr, const long long* batch,
+                            long long N, float cutoff, int max_nb, int version, int mode, int* deg, const int* rowptr,
+                            long long* src, long long* dst, int* img, float* dist, float* vec, int* err, void* stream);
 int eqv2_csr_from_index(const long long* idx /*[E]*/, long long E, long long N, int* counts /*zeroed [N]*/,
                         int* rowptr /*[N+1]*/, int* cursor /*zeroed [N]*/, int* perm /*[E]*/, void* stream);
 int eqv2_segment_sum_fwd(const float* v, long long v_stride, const long long* batch /*non-decreasing [N]*/,

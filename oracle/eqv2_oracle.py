@@ -494,3 +494,92 @@ def canonical_edge_order(edge_index, num_nodes, tiebreak=None):
         order = np.lexsort((tiebreak.numpy(), key.numpy()))
         return torch.from_numpy(order)
     return torch.argsort(key, stable=True)
+
+
+def _pbc27_candidates(pos_b, cell_b, cutoff):
+    """27-image candidate search shared by the MatPES builders (equiformerv2_MatPES.py:270-290,
+    equiformerv2_MatPESv2.py:186-201): image order = meshgrid(-1..1, indexing='ij'); for image offset o,
+    diff[i, j] = (pos[j] + o) - pos[i]; keep dist < cutoff (and > 1e-6 for the zero image).
+    Returns src (=i), dst (=j), image index, and the true image vectors."""
+    rng = torch.arange(-1, 2, dtype=torch.float32)
+    gx, gy, gz = torch.meshgrid(rng, rng, rng, indexing="ij")
+    offs = torch.stack([gx.reshape(-1), gy.reshape(-1), gz.reshape(-1)], dim=1) @ cell_b
+    src_l, dst_l, img_l, vec_l = [], [], [], []
+    for s, o in enumerate(offs):
+        diff = (pos_b + o.unsqueeze(0)).unsqueeze(0) - pos_b.unsqueeze(1)
+        dist = torch.norm(diff, dim=2)
+        within = (dist < cutoff) & (dist > 1e-6) if o.abs().sum() < 1e-6 else (dist < cutoff)
+        src, dst = torch.where(within)
+        src_l.append(src)
+        dst_l.append(dst)
+        img_l.append(torch.full_like(src, s))
+        vec_l.append(diff[src, dst])
+    return torch.cat(src_l), torch.cat(dst_l), torch.cat(img_l), torch.cat(vec_l)
+
+
+def radius_graph_matpes(pos, cell, batch, cutoff, max_neighbors, version):
+    """version 1: equiformerv2_MatPES.py:258-340 -- vectors keep the periodic image offset, per-destination
+    ranking by the true image distance.
+    version 2: equiformerv2_MatPESv2.py:177-240 (also equiformerv2_MatPES_GATAV2.py:285-349) -- candidates as
+    in v1, but the ranking distance and the returned vector are pos[dst] - pos[src] WITHOUT the image offset
+    (duplicates and zero-length self-image edges are kept).
+    Returns edge_index [2,E] (row 0 = src, row 1 = dst), distance, vector, image index."""
+    ei, dd, vv, im = [], [], [], []
+    for g in range(cell.shape[0]):
+        nodes = torch.where(batch == g)[0]
+        pb = pos[nodes]
+        src, dst, img, vec = _pbc27_candidates(pb, cell[g], cutoff)
+        if len(src) == 0:
+            continue
+        if version == 2:
+            vec = pb[dst] - pb[src]
+        dist = torch.norm(vec, dim=1)
+        if max_neighbors is not None:
+            keep = torch.zeros(len(src), dtype=torch.bool)
+            for d in torch.unique(dst):
+                ids = torch.where(dst == d)[0]
+                if len(ids) > max_neighbors:
+                    order = torch.sort(dist[ids], stable=True)[1]
+                    keep[ids[order[:max_neighbors]]] = True
+                else:
+                    keep[ids] = True
+            src, dst, img, vec, dist = src[keep], dst[keep], img[keep], vec[keep], dist[keep]
+        ei.append(torch.stack([nodes[src], nodes[dst]]))
+        dd.append(dist)
+        vv.append(vec)
+        im.append(img)
+    return torch.cat(ei, dim=1), torch.cat(dd), torch.cat(vv), torch.cat(im)
+
+
+def edge_rot_mat_deterministic(edge_vec):
+    """equiformerv2_MatPESv2.py:41-66: helper axis = cardinal axis of the smallest |component|."""
+    ev = edge_vec.detach()
+    dist = torch.sqrt(torch.sum(ev ** 2, dim=1, keepdim=True)).clamp(min=1e-8)
+    nx = ev / dist
+    ref = torch.eye(3, dtype=ev.dtype)[torch.argmin(torch.abs(nx), dim=1)]
+    nz = torch.cross(nx, ref, dim=1)
+    nz = nz / torch.sqrt(torch.sum(nz ** 2, dim=1, keepdim=True)).clamp(min=1e-8)
+    ny = torch.cross(nx, nz, dim=1)
+    ny = ny / torch.sqrt(torch.sum(ny ** 2, dim=1, keepdim=True)).clamp(min=1e-8)
+    inv = torch.stack([nz, nx, -ny], dim=2)
+    return inv.transpose(1, 2)
+
+
+def matpes_v2_forward(P, hp, Z, batch, natoms, pos, edge_index):
+    """equiformerv2_MatPESv2.py:242-300: energy only; differentiable w.r.t. `pos` through
+    dvec = pos[dst] - pos[src] -> distance -> RBF -> radial MLPs (frames / Wigner-D detached).
+    Returns energy_total [B]."""
+    dvec = pos[edge_index[1]] - pos[edge_index[0]]
+    dist = torch.norm(dvec, dim=1)
+    R = edge_rot_mat_deterministic(dvec)
+    W = rotation_to_wigner(R, hp.lmax)
+    N = Z.shape[0]
+    x = torch.zeros(N, hp.lay.K, hp.C)
+    x = torch.cat([P["sphere_embedding.weight"][Z].unsqueeze(1), x[:, 1:]], dim=1)
+    rbf = gaussian_smearing(dist, hp.cutoff, hp.num_rbf, 2.0)
+    x = x + edge_degree_embedding(P, "edge_degree_embedding.", hp, Z, rbf, edge_index, W, N, hp.avg_degree)
+    for i in range(hp.num_layers):
+        x = trans_block(P, f"blocks.{i}.", hp, x, Z, rbf, edge_index, W)
+    x = equivariant_norm(P, "norm.", x, hp.norm_type, hp.lmax)
+    node_e = feed_forward(P, "energy_block.", hp, x)[:, 0, 0]
+    return torch.zeros(len(natoms), dtype=node_e.dtype).index_add_(0, batch, node_e)

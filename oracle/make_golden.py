@@ -185,9 +185,51 @@ def golden_components():
     print("components ok")
 
 
+def golden_matpes():
+    """MatPES v1/v2 graphs and the v2 model's train-step quantities (train_MatPES_GATAWandB.py:67-91 pattern:
+    forces by autograd.grad(create_graph=True), loss on energy + forces, loss.backward())."""
+    import importlib
+    v1 = importlib.import_module("equiformerv2_MatPES")
+    v2 = importlib.import_module("equiformerv2_MatPESv2")
+    gen = torch.Generator().manual_seed(13)
+    Z, pos, batch, natoms, cell = synth_cells(gen, 2, 7, vol_per_atom=14.0, zmax=89)
+    data = dict(atomic_numbers=Z, pos=pos, batch=batch, natoms=natoms, cell=cell)
+    hp = dict(lmax=3, mmax=2, C=16, H=8, heads=2, alpha_ch=8, value_ch=4, ffn_hidden=16, edge_ch=16, num_layers=2,
+              norm_type="rms_norm_sh", grid_res=18, num_rbf=600, cutoff=4.5, max_elements=100, max_neighbors=8)
+    kw = dict(max_neighbors=hp["max_neighbors"], max_radius=hp["cutoff"], max_num_elements=100, num_layers=2,
+              sphere_channels=16, attn_hidden_channels=8, num_heads=2, attn_alpha_channels=8, attn_value_channels=4,
+              ffn_hidden_channels=16, lmax_list=[3], mmax_list=[2], grid_resolution=18, edge_channels=16,
+              alpha_drop=0.0, drop_path_rate=0.0, proj_drop=0.0)
+    torch.manual_seed(4)
+    m1 = v1.EquiformerV2_MatPES(regress_forces=False, regress_stress=False, **kw)
+    ei1, d1, vec1, *_ = m1.generate_graph(data)
+    torch.manual_seed(4)
+    model = v2.EquiformerV2_MatPES(**kw)
+    with torch.no_grad():
+        for p in model.parameters():
+            p.add_(0.05 * torch.randn(p.shape, generator=gen))
+    ei2, d2, vec2 = model.generate_graph(pos, batch, cell)
+    posg = pos.clone().requires_grad_(True)
+    out = model(dict(data, pos=posg))
+    forces = -torch.autograd.grad(out["energy_total"].sum(), posg, create_graph=True, retain_graph=True)[0]
+    wf = torch.linspace(-1, 1, forces.numel()).view_as(forces)
+    we = torch.linspace(0.5, 1.5, out["energy"].numel()).view_as(out["energy"])
+    loss = (out["energy"] * we).sum() + (forces * wf).sum()
+    loss.backward()
+    fx = dict(hyper=hp, params=params_of(model),
+              grads={k: p.grad.clone() for k, p in model.named_parameters() if p.grad is not None},
+              inputs=data, v1_edge_index=ei1, v1_edge_distance=d1.detach(), v1_edge_vec=vec1.detach(),
+              edge_index=ei2, edge_distance=d2.detach(), edge_vec=vec2.detach(),
+              energy=out["energy"].detach(), energy_total=out["energy_total"].detach(), forces=forces.detach())
+    torch.save(fx, os.path.join(OUT, "matpes_v2_small.pt"))
+    print("matpes E1", ei1.shape[1], "E2", ei2.shape[1], out["energy"].detach().view(-1), forces.abs().max().item(),
+          "self edges", int((ei2[0] == ei2[1]).sum()))
+
+
 if __name__ == "__main__":
     ref_loader.install()
     os.makedirs(OUT, exist_ok=True)
     golden_components()
     golden_oc20()
     golden_qm9()
+    golden_matpes()

@@ -108,3 +108,39 @@ def test_edge_plan_csr(backend):
         assert torch.equal(perm.cpu().long(), order)
         counts = torch.bincount(idx, minlength=9)
         assert torch.equal(rowptr.cpu().long(), torch.cat([torch.zeros(1, dtype=torch.long), counts.cumsum(0)]))
+
+
+@pytest.mark.parametrize("version", [1, 2])
+def test_radius_graph_matpes_matches_reference_graph(backend, version):
+    fx = golden("matpes_v2_small.pt")
+    ops = pkg("ops")
+    inp = backend.to(fx["inputs"])
+    hp = fx["hyper"]
+    pre = "v1_" if version == 1 else ""
+    ei, d, v, img = ops.radius_graph_matpes(inp["pos"], inp["cell"], inp["natoms"], inp["batch"], hp["cutoff"],
+                                            hp["max_neighbors"], version)
+    n = inp["pos"].shape[0]
+    a = _canon(ei, d, v, n)
+    b = _canon(fx[pre + "edge_index"], fx[pre + "edge_distance"], fx[pre + "edge_vec"], n)
+    assert a[0].shape == b[0].shape and torch.equal(a[0], b[0])
+    assert torch.allclose(a[1], b[1], atol=2e-6)
+    if version == 2:                      # v1 duplicates of one (src, dst) pair differ only by image: compare as sets
+        assert torch.allclose(a[2], b[2], atol=2e-6)
+    assert int(img.min()) >= 0 and int(img.max()) <= 26
+
+
+@pytest.mark.parametrize("version", [1, 2])
+def test_radius_graph_matpes_matches_oracle_random_cells(backend, version):
+    ops = pkg("ops")
+    gen = torch.Generator().manual_seed(31)
+    cells = torch.stack([3.5 * torch.eye(3) + 0.3 * torch.randn(3, 3, generator=gen) for _ in range(3)])
+    natoms = torch.tensor([4, 9, 1])
+    pos = torch.cat([torch.rand(int(k), 3, generator=gen) @ cells[g] for g, k in enumerate(natoms)])
+    batch = torch.repeat_interleave(torch.arange(3), natoms)
+    for max_nb in (None, 5, 12):
+        ref = O.radius_graph_matpes(pos, cells, batch, 4.0, max_nb, version)
+        ei, d, v, img = ops.radius_graph_matpes(backend.to(pos), backend.to(cells), backend.to(natoms), backend.to(batch),
+                                                4.0, max_nb, version)
+        a, b = _canon(ei, d, v, len(pos)), _canon(ref[0], ref[1], ref[2], len(pos))
+        assert a[0].shape == b[0].shape and torch.equal(a[0], b[0]), (version, max_nb)
+        assert torch.allclose(a[1], b[1], atol=2e-6)

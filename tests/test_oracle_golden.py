@@ -68,3 +68,36 @@ def test_oracle_components_match_reference():
         tg, fg = O.s2_grid_mats(l, m, 18)
         assert torch.allclose(tg, c[f"to_grid_{l}_{m}"], atol=1e-6)
         assert torch.allclose(fg, c[f"from_grid_{l}_{m}"], atol=1e-6)
+
+
+def test_oracle_matpes_builders_match_reference_graphs():
+    fx = golden("matpes_v2_small.pt")
+    inp, hp = fx["inputs"], fx["hyper"]
+    for version, pre in ((1, "v1_"), (2, "")):
+        ei, d, v, _ = O.radius_graph_matpes(inp["pos"], inp["cell"], inp["batch"], hp["cutoff"], hp["max_neighbors"], version)
+        n = inp["pos"].shape[0]
+        oa = O.canonical_edge_order(ei, n, tiebreak=d)
+        ob = O.canonical_edge_order(fx[pre + "edge_index"], n, tiebreak=fx[pre + "edge_distance"])
+        assert torch.equal(ei[:, oa], fx[pre + "edge_index"][:, ob]), version
+        assert torch.allclose(d[oa], fx[pre + "edge_distance"][ob], atol=1e-6)
+
+
+def test_oracle_matpes_v2_train_step_matches_reference():
+    """energy, autograd forces (create_graph) and the parameter gradients of a loss on both."""
+    fx = golden("matpes_v2_small.pt")
+    h = fx["hyper"]
+    hp = _hyper(h)
+    hp.avg_degree = 12.0                      # _AVG_DEGREE_MATPES (equiformerv2_MatPESv2.py:68)
+    P = {k: v.clone().requires_grad_(True) for k, v in fx["params"].items()}
+    inp = fx["inputs"]
+    pos = inp["pos"].clone().requires_grad_(True)
+    e_tot = O.matpes_v2_forward(P, hp, inp["atomic_numbers"], inp["batch"], inp["natoms"], pos, fx["edge_index"])
+    assert _rel(e_tot, fx["energy_total"]) < 2e-6
+    forces = -torch.autograd.grad(e_tot.sum(), pos, create_graph=True)[0]
+    assert _rel(forces, fx["forces"]) < 1e-5
+    energy = (e_tot / inp["natoms"].float()).unsqueeze(1)
+    wf = torch.linspace(-1, 1, forces.numel()).view_as(forces)
+    we = torch.linspace(0.5, 1.5, energy.numel()).view_as(energy)
+    ((energy * we).sum() + (forces * wf).sum()).backward()
+    for k, g in fx["grads"].items():
+        assert _rel(P[k].grad, g) < 1e-4, k
