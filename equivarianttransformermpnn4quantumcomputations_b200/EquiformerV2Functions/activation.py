@@ -104,7 +104,7 @@ class S2Activation(nn.Module):
 
     def forward(self, inputs, SO3_grid):
         mats = SO3_grid[self.lmax][self.mmax].kernel_mats("l")
-        return ops.S2ActFn.apply(inputs, None, mats)
+        return ops.s2_act(inputs, None, mats)
 
 
 class SeparableS2Activation(nn.Module):
@@ -120,4 +120,4 @@ class SeparableS2Activation(nn.Module):
     def forward(self, input_scalars, input_tensors, SO3_grid):
         mats = SO3_grid[self.lmax][self.mmax].kernel_mats("l")
         scalars = input_scalars.reshape(input_scalars.shape[0], input_scalars.shape[-1])
-        return ops.S2ActFn.apply(input_tensors, scalars, mats)
+        return ops.s2_act(input_tensors, scalars, mats)

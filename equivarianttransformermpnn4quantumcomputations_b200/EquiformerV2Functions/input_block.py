@@ -52,7 +52,7 @@ class EdgeDegreeEmbedding(nn.Module):
             raise RuntimeError("SO3_Rotation.set_wigner must be called with this graph's edge frames first")
         x_edge = edge_scalar_features(self, atomic_numbers, edge_distance, edge_index)
         m0 = self.rad_func(x_edge)                                            # [E, (lmax+1)*C]
-        out = ops.RotInvReduceFn.apply(m0, None, plan, wig, lmax, mmax, self.m_0_num_coefficients, 0,
+        out = ops.rotinv_reduce(m0, None, plan, wig, lmax, mmax, self.m_0_num_coefficients, 0,
                                        1.0 / float(self.rescale_factor))
         res = SO3_Embedding(0, self.lmax_list.copy(), self.sphere_channels, device=out.device, dtype=out.dtype)
         res.set_embedding(out)

@@ -42,7 +42,7 @@ class EquivariantLayerNormArray(nn.Module):
         return f"{self.__class__.__name__}(lmax={self.lmax}, num_channels={self.num_channels}, eps={self.eps})"
 
     def forward(self, node_input):
-        return ops.EquivNormFn.apply(node_input.float(), self.affine_weight, self.affine_bias,
+        return ops.equiv_norm(node_input.float(), self.affine_weight, self.affine_bias,
                                      "layer_norm", self.lmax, self.eps)
 
 
@@ -71,7 +71,7 @@ class EquivariantLayerNormArraySphericalHarmonics(nn.Module):
 
     def forward(self, node_input):
         w = torch.cat([self.norm_l0.weight.view(1, -1), self.affine_weight], dim=0)
-        return ops.EquivNormFn.apply(node_input.float(), w, self.norm_l0.bias, "layer_norm_sh", self.lmax, self.eps)
+        return ops.equiv_norm(node_input.float(), w, self.norm_l0.bias, "layer_norm_sh", self.lmax, self.eps)
 
 
 class EquivariantRMSNormArraySphericalHarmonics(nn.Module):
@@ -109,5 +109,5 @@ class EquivariantRMSNormArraySphericalHarmonicsV2(nn.Module):
                 f"centering={self.centering}, std_balance_degrees={self.std_balance_degrees})")
 
     def forward(self, node_input):
-        return ops.EquivNormFn.apply(node_input.float(), self.affine_weight, self.affine_bias,
+        return ops.equiv_norm(node_input.float(), self.affine_weight, self.affine_bias,
                                      "rms_norm_sh", self.lmax, self.eps)

@@ -27,6 +27,6 @@ class RadialFunction(nn.Module):
             i += 1
             if i < len(mods):
                 ln = mods[i]
-                x = ops.LnSiluFn.apply(x, ln.weight, ln.bias, ln.eps)
+                x = ops.ln_silu(x, ln.weight, ln.bias, ln.eps)
                 i += 2
         return x

@@ -49,7 +49,7 @@ class SO2_m_Convolution(nn.Module):
         E = x_m.shape[0]
         Wb = self.block_weight()
         k2, o2 = Wb.shape[1], Wb.shape[0]
-        y = ops.SO2ConvFn.apply(x_m.reshape(E, k2), None, ((0, k2, 0, o2),), Wb)
+        y = ops.so2_conv(x_m.reshape(E, k2), None, ((0, k2, 0, o2),), [Wb])
         return y.view(E, 2, o2 // 2)
 
 
@@ -98,7 +98,7 @@ class SO2_Convolution(nn.Module):
         groups = tuple(self.layout().conv_groups(self.sphere_channels, self.m_output_channels,
                                                  self.extra_m0_output_channels or 0))
         weights = [self.fc_m0.weight] + [mc.block_weight() for mc in self.so2_m_conv]
-        return ops.SO2ConvFn.apply(A, self.fc_m0.bias, groups, *weights)
+        return ops.so2_conv(A, self.fc_m0.bias, groups, weights)
 
     # -- reference-shaped entry point -------------------------------------------------------
     def forward(self, x, x_edge):

@@ -118,17 +118,27 @@ class SO2EquivariantGraphAttention(nn.Module):
 
         x_edge = edge_scalar_features(self, atomic_numbers, edge_distance, edge_index)
         rad = self.so2_conv_1.radial_weights(x_edge)                          # [E, n_rad]
-        A = ops.GatherRotateFn.apply(emb, rad, plan, wig, lmax, mmax)         # [E, Kr*2C]  m-primary
+        A = ops.gather_rotate(emb, rad, plan, wig, lmax, mmax)         # [E, Kr*2C]  m-primary
         Y = self.so2_conv_1.conv_m_primary(A)                                 # [E, h*a + H + Kr*H]
         mats = self.SO3_grid[lmax][mmax].kernel_mats("m")
         ln_w = self.alpha_norm.weight if self.use_attn_renorm else None
         ln_b = self.alpha_norm.bias if self.use_attn_renorm else None
-        Zm, alpha = ops.EdgeActAlphaFn.apply(Y, ln_w, ln_b, self.alpha_dot, plan, mats, self.num_heads,
-                                             self.attn_alpha_channels, self.hidden_channels)
+        if torch.is_grad_enabled() and edge_distance.requires_grad:
+            # positions are being differentiated (forces by autograd, train_MatPES_GATAWandB.py:72-77): use the
+            # operators whose backward passes are themselves differentiable
+            ha = self.num_heads * self.attn_alpha_channels
+            extra = ha + self.hidden_channels
+            alpha = ops.attn_alpha(Y[:, :ha], ln_w, ln_b, self.alpha_dot, plan, self.num_heads,
+                                          self.attn_alpha_channels)
+            Zm = ops.s2_act(Y[:, extra:].reshape(plan.E, lay.Kr, self.hidden_channels), Y[:, ha:extra], mats)
+            Zm = Zm.reshape(plan.E, lay.Kr * self.hidden_channels)
+        else:
+            Zm, alpha = ops.edge_act_alpha(Y, ln_w, ln_b, self.alpha_dot, plan, mats, self.num_heads,
+                                                 self.attn_alpha_channels, self.hidden_channels)
         if self.alpha_dropout is not None:
             alpha = self.alpha_dropout(alpha)
         V = self.so2_conv_2.conv_m_primary(Zm)                                # [E, Kr*h*v]
-        out = ops.RotInvReduceFn.apply(V, alpha, plan, wig, lmax, mmax, lay.Kr, self.num_heads, 1.0)
+        out = ops.rotinv_reduce(V, alpha, plan, wig, lmax, mmax, lay.Kr, self.num_heads, 1.0)
         msg = SO3_Embedding(0, x.lmax_list.copy(), self.num_heads * self.attn_value_channels,
                             device=x.device, dtype=x.dtype)
         msg.set_embedding(out)

@@ -47,6 +47,7 @@ _PROTOS = {
     "eqv2_s2sep_set_tables": [P, I, I, P],
     "eqv2_s2sep_fwd": [P, L, P, L, P, L, L, I, I, I, I, I, P],
     "eqv2_s2sep_bwd": [P, L, P, L, P, L, P, L, P, L, L, I, I, I, I, I, P],
+    "eqv2_s2sep_bwd2": [P, L, P, L, P, L, P, L, P, L, P, L, P, L, P, L, L, I, I, I, I, I, P],
     "eqv2_attn_alpha_fwd": [P, L, P, P, P, P, P, P, P, L, L, I, I, F, P],
     "eqv2_attn_alpha_bwd": [P, L, P, P, P, P, P, P, P, P, P, L, P, P, P, L, L, I, I, F, P],
     "eqv2_equiv_norm_fwd": [P, P, P, P, P, P, L, I, I, I, P, P, F, P],

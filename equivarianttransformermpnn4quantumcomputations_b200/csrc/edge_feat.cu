@@ -151,7 +151,9 @@ __global__ void wigner_kernel(const float* __restrict__ rot, const float* __rest
   float* T = sT + wib * 6 * MAXN;
   const float* R = rot + e * 9;
   // x = R @ (0,1,0) -> column 1, normalised and clamped (e3nn xyz_to_angles)
-  float x0 = R[1], x1 = R[4], x2 = R[7];
+  // (a matmul accumulates from +0: a degenerate frame's -0 entries become +0, which decides atan2(0, +-0);
+  //  zero-length self-image edges of the MatPES v2 builder hit exactly this case)
+  float x0 = __fadd_rn(R[1], 0.f), x1 = __fadd_rn(R[4], 0.f), x2 = __fadd_rn(R[7], 0.f);
   const float nrm = fmaxf(sqrtf(x0 * x0 + x1 * x1 + x2 * x2), 1e-12f);
   x0 = fminf(fmaxf(x0 / nrm, -1.f), 1.f);
   x1 = fminf(fmaxf(x1 / nrm, -1.f), 1.f);
@@ -160,8 +162,8 @@ __global__ void wigner_kernel(const float* __restrict__ rot, const float* __rest
   const float alpha = atan2f(x0, x2);
   const float ca = cosf(alpha), sa = sinf(alpha);
   // first row of (R_y(alpha) R_x(beta))^T @ R
-  const float r00 = ca * R[0] - sa * R[6];
-  const float r02 = ca * R[2] - sa * R[8];
+  const float r00 = __fadd_rn(ca * R[0] - sa * R[6], 0.f);
+  const float r02 = __fadd_rn(ca * R[2] - sa * R[8], 0.f);
   const float gamma = atan2f(r02, r00);
   // trig tables for frequencies f = -lmax..lmax
   if (lane <= 2 * lmax) {

@@ -183,6 +183,86 @@ s2sep_bwd_kernel(const float* __restrict__ X, long long x_rs, const float* __res
   }
 }
 
+// d/dz of SiLU'(z):  s (1 - s) (2 + z (1 - 2 s))
+__device__ __forceinline__ float eqv2_d2silu(float z) {
+  const float sg = eqv2_sigmoid(z);
+  return sg * (1.f - sg) * (2.f + z * (1.f - 2.f * sg));
+}
+
+// Derivative of the BACKWARD pass (needed when forces = -dE/dpos are themselves trained on).
+// Backward computed  dx = T^t[ SiLU'(T x) . (F go') ],  dgate = go_0 SiLU'(gate)   (go' = go without row 0 if gated).
+// With cotangents u (of dx) and w (of dgate):   S = <u, dx> + <w, dgate>
+//   dS/dx    = T^t[ (T u) . SiLU''(T x) . (F go') ]
+//   dS/dgo'  = F^t[ (T u) . SiLU'(T x) ]             dS/dgo_0 = w SiLU'(gate)      (gated)
+//   dS/dgate = w go_0 SiLU''(gate)
+template <int L, int M, bool MP>
+__global__ void __launch_bounds__(S2_THREADS)
+s2sep_bwd2_kernel(const float* __restrict__ X, long long x_rs, const float* __restrict__ gate, long long g_rs,
+                  const float* __restrict__ dO, long long o_rs, const float* __restrict__ U, long long u_rs,
+                  const float* __restrict__ Wg, long long w_rs, float* __restrict__ d2X, long long d2x_rs,
+                  float* __restrict__ d2gate, long long d2g_rs, float* __restrict__ d2O, long long d2o_rs, long long R,
+                  int C, int slot) {
+  constexpr int Kr = KrOf<L, M>::value();
+  const S2Tables& T = g_tab[slot];
+  const long long total = R * C;
+  for (long long w = (long long)blockIdx.x * blockDim.x + threadIdx.x; w < total; w += (long long)gridDim.x * blockDim.x) {
+    const long long r = w / C;
+    const int c = (int)(w % C);
+    float x[Kr], go[Kr], u[Kr], ax[Kr], ao[Kr];
+#pragma unroll
+    for (int p = 0; p < Kr; ++p) {
+      x[p] = __ldg(X + r * x_rs + (long long)p * C + c);
+      go[p] = (p > 0 || gate == nullptr) ? __ldg(dO + r * o_rs + (long long)p * C + c) : 0.f;
+      u[p] = (U != nullptr) ? __ldg(U + r * u_rs + (long long)p * C + c) : 0.f;
+      ax[p] = 0.f;
+      ao[p] = 0.f;
+    }
+#pragma unroll 1
+    for (int b = 0; b < S2_RES; ++b) {
+      float xp[M + 1], xn[M + 1], hp[M + 1], hn[M + 1], qp[M + 1], qn[M + 1], ap[M + 1], an[M + 1], bp[M + 1], bn[M + 1];
+      lat_fwd<L, M, MP>(x, T.Pt, b, xp, xn);
+      lat_fwd<L, M, MP>(go, T.Pf, b, hp, hn);
+      lat_fwd<L, M, MP>(u, T.Pt, b, qp, qn);
+#pragma unroll
+      for (int mi = 0; mi <= M; ++mi) ap[mi] = an[mi] = bp[mi] = bn[mi] = 0.f;
+#pragma unroll
+      for (int a = 0; a < S2_RES; ++a) {
+        float g = xp[0], h = hp[0], q = qp[0];
+#pragma unroll
+        for (int mi = 1; mi <= M; ++mi) {
+          g = fmaf(T.ct[a][mi], xp[mi], fmaf(T.st[a][mi], xn[mi], g));
+          h = fmaf(T.ct[a][mi], hp[mi], fmaf(T.st[a][mi], hn[mi], h));
+          q = fmaf(T.ct[a][mi], qp[mi], fmaf(T.st[a][mi], qn[mi], q));
+        }
+        const float t1 = q * h * eqv2_d2silu(g);
+        const float t2 = q * eqv2_dsilu(g);
+        ap[0] += t1;
+        bp[0] += t2;
+#pragma unroll
+        for (int mi = 1; mi <= M; ++mi) {
+          ap[mi] = fmaf(T.ct[a][mi], t1, ap[mi]);
+          an[mi] = fmaf(T.st[a][mi], t1, an[mi]);
+          bp[mi] = fmaf(T.ct[a][mi], t2, bp[mi]);
+          bn[mi] = fmaf(T.st[a][mi], t2, bn[mi]);
+        }
+      }
+      lat_bwd<L, M, MP>(ax, T.Pt, b, ap, an);
+      lat_bwd<L, M, MP>(ao, T.Pf, b, bp, bn);
+    }
+    if (gate != nullptr) {
+      const float gv = __ldg(gate + r * g_rs + c);
+      const float wv = (Wg != nullptr) ? __ldg(Wg + r * w_rs + c) : 0.f;
+      ao[0] = wv * eqv2_dsilu(gv);
+      d2gate[r * d2g_rs + c] = wv * __ldg(dO + r * o_rs + c) * eqv2_d2silu(gv);
+    }
+#pragma unroll
+    for (int p = 0; p < Kr; ++p) {
+      d2X[r * d2x_rs + (long long)p * C + c] = ax[p];
+      d2O[r * d2o_rs + (long long)p * C + c] = ao[p];
+    }
+  }
+}
+
 inline unsigned s2_grid_blocks(long long total) {
   long long b = (total + S2_THREADS - 1) / S2_THREADS;
   const long long cap = 148LL * 16;
@@ -247,5 +327,25 @@ extern "C" int eqv2_s2sep_bwd(const float* Xp, long long x_rs, const float* gate
   EQV2_S2_CONFIGS(X)
 #undef X
   eqv2_set_error("s2sep_bwd: (lmax, mmax) = (%d, %d) not instantiated", lmax, mmax);
+  return 1;
+}
+
+extern "C" int eqv2_s2sep_bwd2(const float* Xp, long long x_rs, const float* gate, long long g_rs, const float* dO,
+                               long long o_rs, const float* U, long long u_rs, const float* Wg, long long w_rs,
+                               float* d2X, long long d2x_rs, float* d2gate, long long d2g_rs, float* d2O, long long d2o_rs,
+                               long long R, int C, int lmax, int mmax, int m_primary, int slot, void* stream) {
+  if (R == 0) return 0;
+  const unsigned blocks = s2_grid_blocks(R * C);
+#define X(L_, M_)                                                                                                        \
+  if (lmax == L_ && mmax == M_) {                                                                                        \
+    auto kfn = m_primary ? s2sep_bwd2_kernel<L_, M_, true> : s2sep_bwd2_kernel<L_, M_, false>;                           \
+    EQV2_LAUNCH(kfn, dim3(blocks), dim3(S2_THREADS), 0, stream, Xp, x_rs, gate, g_rs, dO, o_rs, U, u_rs, Wg, w_rs, d2X,  \
+                d2x_rs, d2gate, d2g_rs, d2O, d2o_rs, R, C, slot);                                                        \
+    EQV2_CHECK_LAUNCH("eqv2_s2sep_bwd2");                                                                                \
+    return 0;                                                                                                            \
+  }
+  EQV2_S2_CONFIGS(X)
+#undef X
+  eqv2_set_error("s2sep_bwd2: (lmax, mmax) = (%d, %d) not instantiated", lmax, mmax);
   return 1;
 }

@@ -26,7 +26,7 @@ class GaussianSmearing(nn.Module):
         return self.num_gaussians
 
     def forward(self, dist):
-        return ops.RbfFn.apply(dist.reshape(-1), self.offset, self.coeff)
+        return ops.rbf(dist.reshape(-1), self.offset, self.coeff)
 
 
 def build_so3_grid(lmax_list, grid_resolution):

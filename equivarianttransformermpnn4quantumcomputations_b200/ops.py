@@ -269,27 +269,42 @@ class SegmentSumFn(torch.autograd.Function):
     @staticmethod
     def forward(ctx, values, batch, num_graphs):
         _lib.check_device(values, batch)
-        values = values.contiguous()
-        batch = batch.contiguous()
+        assert values.is_contiguous() and batch.is_contiguous()
         N = int(values.shape[0])
         out = torch.empty(num_graphs, dtype=_F32, device=values.device)
         _lib.call("eqv2_segment_sum_fwd", values.data_ptr(), 1, batch.data_ptr(), out.data_ptr(), N, int(num_graphs),
                   _lib.stream_ptr())
         ctx.save_for_backward(batch)
+        ctx.num_graphs = int(num_graphs)
         return out
 
     @staticmethod
     def backward(ctx, gout):
         (batch,) = ctx.saved_tensors
-        gout = gout.contiguous()
+        return SegmentBcastFn.apply(gout.contiguous(), batch, ctx.num_graphs), None, None
+
+
+class SegmentBcastFn(torch.autograd.Function):
+    """gv[n] = gout[batch[n]] -- the adjoint of SegmentSumFn (and vice versa)."""
+
+    @staticmethod
+    def forward(ctx, gout, batch, num_graphs):
+        assert gout.is_contiguous()
         N = int(batch.shape[0])
         gv = torch.empty(N, dtype=_F32, device=gout.device)
         _lib.call("eqv2_segment_sum_bwd", gout.data_ptr(), batch.data_ptr(), gv.data_ptr(), N, _lib.stream_ptr())
-        return gv, None, None
+        ctx.save_for_backward(batch)
+        ctx.num_graphs = num_graphs
+        return gv
+
+    @staticmethod
+    def backward(ctx, ggv):
+        (batch,) = ctx.saved_tensors
+        return SegmentSumFn.apply(ggv.contiguous(), batch, ctx.num_graphs), None, None
 
 
 def segment_sum_nodes(values, batch, num_graphs):
-    return SegmentSumFn.apply(values, batch, num_graphs)
+    return SegmentSumFn.apply(values.contiguous(), batch.contiguous(), num_graphs)
 
 
 # ----------------------------------------------------------------------------------------------
@@ -388,159 +403,188 @@ def run_gemm(descs, split_k=1):
                   work=(flops, nbytes))
 
 
-class LinearFn(torch.autograd.Function):
-    """y = x @ W^T + b  (nn.Linear inside radial_function.py:29, transformer_block.py:420)."""
+# The dense contractions are four primitives that are CLOSED UNDER DIFFERENTIATION: the backward of each is
+# a combination of the same primitives applied through autograd, so a backward pass run with
+# create_graph=True (forces = -dE/dpos, train_MatPES_GATAWandB.py:72-77) can itself be differentiated
+# (loss.backward() through the force computation) without any eager fallback.
+#   SliceMm    : Y[:, ys_g] = X[:, xs_g] @ (W_g^T | W_g)      column-sliced operands (SO(2) blocks, nn.Linear)
+#   SliceOuter : W_g = U[:, us_g]^T @ V[:, vs_g]               (weight gradients; split-K over the edge dimension)
+#   SlabMm     : y[:, slab_l, :] = x[:, slab_l, :] @ (W_l^T | W_l)   degree slabs of [N, K, C] (SO3_LinearV2)
+#   SlabOuter  : W_l = U[:, slab_l, :]^T @ V[:, slab_l, :]
+def _covers(slices, width):
+    pos = 0
+    for off, w in sorted(slices):
+        if off != pos:
+            return False
+        pos = off + w
+    return pos == width
 
+
+class SliceMm(torch.autograd.Function):
     @staticmethod
-    def forward(ctx, x, W, b):
-        _lib.check_device(x, W, b)
-        x = x.contiguous()
-        W = W.contiguous()
-        M, K = x.shape
-        N = W.shape[0]
-        y = torch.empty(M, N, dtype=_F32, device=x.device)
-        run_gemm([_desc(x, W, y, b, M, N, K, 0, 1, _plain(K), _plain(K), _plain(N))])
-        ctx.save_for_backward(x, W)
-        ctx.has_bias = b is not None
-        return y
-
-    @staticmethod
-    def backward(ctx, gy):
-        x, W = ctx.saved_tensors
-        gy = gy.contiguous()
-        M, K = x.shape
-        N = W.shape[0]
-        gx = gW = gb = None
-        if ctx.needs_input_grad[0]:
-            gx = torch.empty(M, K, dtype=_F32, device=x.device)
-            run_gemm([_desc(gy, W, gx, None, M, K, N, 0, 0, _plain(N), _plain(K), _plain(K))])
-        if ctx.needs_input_grad[1]:
-            d = _desc(gy, x, x, None, N, K, M, 1, 0, _plain(N), _plain(K), _plain(K))
-            split = _pick_split([d], True)
-            gW = (torch.zeros if split > 1 else torch.empty)(N, K, dtype=_F32, device=x.device)
-            d.C = gW.data_ptr()
-            run_gemm([d], split)
-        if ctx.has_bias and ctx.needs_input_grad[2]:
-            gb = gy.sum(0)
-        return gx, gW, gb
-
-
-def linear(x, W, b=None):
-    return LinearFn.apply(x, W, b)
-
-
-class SO2ConvFn(torch.autograd.Function):
-    """All m-blocks of one SO(2) convolution as ONE grouped GEMM (so2_ops.py:150-185, :53-61).
-
-    A: [E, Kr*c_in] (m-primary, radial modulation already applied), weights[g]: [n_g, k_g]
-    (m = 0: fc_m0.weight; m > 0: the 2x2 real block form [[Wr, -Wi], [Wi, Wr]] of the complex
-    multiply), bias0: fc_m0.bias.  Y: [E, extra + Kr*c_out]."""
-
-    @staticmethod
-    def forward(ctx, A, bias0, groups, *weights):
-        _lib.check_device(A, bias0, *weights)
-        A = A.contiguous()
-        E, KA = A.shape
-        NC = sum(g[3] for g in groups)
-        Y = torch.empty(E, NC, dtype=_F32, device=A.device)
-        ws = [w.contiguous() for w in weights]
+    def forward(ctx, X, bias, xs, ys, y_width, transW, *Ws):
+        _lib.check_device(X, bias, *Ws)
+        assert X.is_contiguous() and all(w.is_contiguous() for w in Ws)
+        rows, xw = X.shape
+        Y = (torch.empty if _covers(ys, y_width) else torch.zeros)(rows, y_width, dtype=_F32, device=X.device)
         descs = []
-        for gi, (a_off, k_g, c_off, n_g) in enumerate(groups):
-            descs.append(_desc(A, ws[gi], Y, bias0 if gi == 0 else None, E, n_g, k_g, 0, 1,
-                               _plain(KA), _plain(k_g), _plain(NC), a_off=a_off, c_off=c_off))
-        run_gemm(descs)
-        ctx.save_for_backward(A, *ws)
-        ctx.groups = groups
-        ctx.has_bias = bias0 is not None
+        for g, ((xo, k), (yo, n)) in enumerate(zip(xs, ys)):
+            assert tuple(Ws[g].shape) == ((n, k) if transW else (k, n)), (Ws[g].shape, n, k, transW)
+            descs.append(_desc(X, Ws[g], Y, bias if g == 0 else None, rows, n, k, 0, 1 if transW else 0,
+                               _plain(xw), _plain(Ws[g].shape[1]), _plain(y_width), a_off=xo, c_off=yo))
+        if rows > 0:
+            run_gemm(descs)
+        ctx.save_for_backward(X, *Ws)
+        ctx.spec = (xs, ys, y_width, transW, bias is not None)
         return Y
 
     @staticmethod
     def backward(ctx, gY):
-        A, *ws = ctx.saved_tensors
-        groups = ctx.groups
-        gY = gY.contiguous()
-        E, KA = A.shape
-        NC = gY.shape[1]
-        gA = gb = None
-        gws = [None] * len(ws)
+        X, *Ws = ctx.saved_tensors
+        xs, ys, y_width, transW, has_bias = ctx.spec
+        gX = gb = None
+        gWs = [None] * len(Ws)
         if ctx.needs_input_grad[0]:
-            gA = torch.empty(E, KA, dtype=_F32, device=A.device)
-            descs = [_desc(gY, ws[gi], gA, None, E, k_g, n_g, 0, 0, _plain(NC), _plain(k_g), _plain(KA),
-                           a_off=c_off, c_off=a_off) for gi, (a_off, k_g, c_off, n_g) in enumerate(groups)]
-            run_gemm(descs)
-        if any(ctx.needs_input_grad[3:]):
-            descs = []
-            for gi, (a_off, k_g, c_off, n_g) in enumerate(groups):
-                descs.append(_desc(gY, A, A, None, n_g, k_g, E, 1, 0, _plain(NC), _plain(KA), _plain(k_g),
-                                   a_off=c_off, b_off=a_off))
-            split = _pick_split(descs, True)
-            for gi, (a_off, k_g, c_off, n_g) in enumerate(groups):
-                gws[gi] = (torch.zeros if split > 1 else torch.empty)(n_g, k_g, dtype=_F32, device=A.device)
-                descs[gi].C = gws[gi].data_ptr()
+            gX = SliceMm.apply(gY.contiguous(), None, ys, xs, X.shape[1], not transW, *Ws)
+        if any(ctx.needs_input_grad[6:]):
+            if transW:      # W_g [n,k]: gW = gY_g^T X_g
+                outs = SliceOuter.apply(gY.contiguous(), X, ys, xs)
+            else:           # W_g [k,n]: gW = X_g^T gY_g
+                outs = SliceOuter.apply(X, gY.contiguous(), xs, ys)
+            gWs = list(outs) if isinstance(outs, tuple) else [outs]
+        if has_bias and ctx.needs_input_grad[1]:
+            yo, n = ys[0]
+            gb = gY[:, yo:yo + n].sum(0)
+        return (gX, gb, None, None, None, None, *gWs)
+
+
+class SliceOuter(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, U, V, us, vs):
+        _lib.check_device(U, V)
+        assert U.is_contiguous() and V.is_contiguous()
+        rows = U.shape[0]
+        descs = []
+        for (uo, m), (vo, n) in zip(us, vs):
+            descs.append(_desc(U, V, U, None, m, n, rows, 1, 0, _plain(U.shape[1]), _plain(V.shape[1]), _plain(n),
+                               a_off=uo, b_off=vo))
+        split = _pick_split(descs, True) if rows > 0 else 1
+        outs = []
+        for d, ((uo, m), (vo, n)) in zip(descs, zip(us, vs)):
+            W = (torch.zeros if (split > 1 or rows == 0) else torch.empty)(m, n, dtype=_F32, device=U.device)
+            d.C = W.data_ptr()
+            outs.append(W)
+        if rows > 0:
             run_gemm(descs, split)
-        if ctx.has_bias and ctx.needs_input_grad[1]:
-            n0 = groups[0][3]
-            gb = gY[:, :n0].sum(0)
-        return (gA, gb, None, *gws)
-
-
-class SO3LinearFn(torch.autograd.Function):
-    """SO3_LinearV2 (so3.py:698-743): one GEMM per degree l over the slab x[:, l^2:(l+1)^2, :]."""
+        ctx.save_for_backward(U, V)
+        ctx.spec = (us, vs)
+        return tuple(outs)
 
     @staticmethod
-    def forward(ctx, x, W, b):
-        _lib.check_device(x, W, b)
-        x = x.contiguous()
-        W = W.contiguous()
+    def backward(ctx, *gWs):
+        U, V = ctx.saved_tensors
+        us, vs = ctx.spec
+        gWs = [g.contiguous() if g is not None else torch.zeros(m, n, dtype=_F32, device=U.device)
+               for g, ((_, m), (_, n)) in zip(gWs, zip(us, vs))]
+        gU = gV = None
+        if ctx.needs_input_grad[0]:     # gU_g = V_g @ gW_g^T
+            gU = SliceMm.apply(V, None, vs, us, U.shape[1], True, *gWs)
+        if ctx.needs_input_grad[1]:     # gV_g = U_g @ gW_g
+            gV = SliceMm.apply(U, None, us, vs, V.shape[1], False, *gWs)
+        return gU, gV, None, None
+
+
+class SlabMm(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, W, bias, transW):
+        _lib.check_device(x, W, bias)
+        assert x.is_contiguous() and W.is_contiguous()
         N, K, Ci = x.shape
-        L1, Co, _ = W.shape
+        L1, Wo, Wi = W.shape
+        Co = Wo if transW else Wi
+        assert Ci == (Wi if transW else Wo)
         y = torch.empty(N, K, Co, dtype=_F32, device=x.device)
         descs = []
         for l in range(L1):
             r = 2 * l + 1
-            descs.append(_desc(x, W, y, b if l == 0 else None, N * r, Co, Ci, 0, 1,
-                               (r, K * Ci, Ci), _plain(Ci), (r, K * Co, Co),
-                               a_off=l * l * Ci, b_off=l * Co * Ci, c_off=l * l * Co))
-        run_gemm(descs)
+            descs.append(_desc(x, W, y, bias if l == 0 else None, N * r, Co, Ci, 0, 1 if transW else 0,
+                               (r, K * Ci, Ci), _plain(Wi), (r, K * Co, Co),
+                               a_off=l * l * Ci, b_off=l * Wo * Wi, c_off=l * l * Co))
+        if N > 0:
+            run_gemm(descs)
         ctx.save_for_backward(x, W)
-        ctx.has_bias = b is not None
+        ctx.spec = (transW, bias is not None)
         return y
 
     @staticmethod
     def backward(ctx, gy):
         x, W = ctx.saved_tensors
-        gy = gy.contiguous()
-        N, K, Ci = x.shape
-        L1, Co, _ = W.shape
+        transW, has_bias = ctx.spec
         gx = gW = gb = None
         if ctx.needs_input_grad[0]:
-            gx = torch.empty_like(x)
-            descs = []
-            for l in range(L1):
-                r = 2 * l + 1
-                descs.append(_desc(gy, W, gx, None, N * r, Ci, Co, 0, 0,
-                                   (r, K * Co, Co), _plain(Ci), (r, K * Ci, Ci),
-                                   a_off=l * l * Co, b_off=l * Co * Ci, c_off=l * l * Ci))
-            run_gemm(descs)
+            gx = SlabMm.apply(gy.contiguous(), W, None, not transW)
         if ctx.needs_input_grad[1]:
-            descs = []
-            for l in range(L1):
-                r = 2 * l + 1
-                descs.append(_desc(gy, x, W, None, Co, Ci, N * r, 1, 0,
-                                   (r, K * Co, Co), (r, K * Ci, Ci), _plain(Ci),
-                                   a_off=l * l * Co, b_off=l * l * Ci))
-            split = _pick_split(descs, True)
-            gW = (torch.zeros if split > 1 else torch.empty)(L1, Co, Ci, dtype=_F32, device=x.device)
-            for l in range(L1):
-                descs[l].C = gW.data_ptr() + 4 * l * Co * Ci
-            run_gemm(descs, split)
-        if ctx.has_bias and ctx.needs_input_grad[2]:
+            gW = SlabOuter.apply(gy.contiguous(), x) if transW else SlabOuter.apply(x, gy.contiguous())
+        if has_bias and ctx.needs_input_grad[2]:
             gb = gy[:, 0, :].sum(0)
-        return gx, gW, gb
+        return gx, gW, gb, None
+
+
+class SlabOuter(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, U, V):
+        _lib.check_device(U, V)
+        assert U.is_contiguous() and V.is_contiguous()
+        N, K, Cu = U.shape
+        Cv = V.shape[2]
+        L1 = int(round(math.sqrt(K)))
+        descs = []
+        for l in range(L1):
+            r = 2 * l + 1
+            descs.append(_desc(U, V, U, None, Cu, Cv, N * r, 1, 0, (r, K * Cu, Cu), (r, K * Cv, Cv), _plain(Cv),
+                               a_off=l * l * Cu, b_off=l * l * Cv))
+        split = _pick_split(descs, True) if N > 0 else 1
+        W = (torch.zeros if (split > 1 or N == 0) else torch.empty)(L1, Cu, Cv, dtype=_F32, device=U.device)
+        for l in range(L1):
+            descs[l].C = W.data_ptr() + 4 * l * Cu * Cv
+        if N > 0:
+            run_gemm(descs, split)
+        ctx.save_for_backward(U, V)
+        return W
+
+    @staticmethod
+    def backward(ctx, gW):
+        U, V = ctx.saved_tensors
+        gU = gV = None
+        if ctx.needs_input_grad[0]:     # gU_l = V_l @ gW_l^T
+            gU = SlabMm.apply(V, gW.contiguous(), None, True)
+        if ctx.needs_input_grad[1]:     # gV_l = U_l @ gW_l
+            gV = SlabMm.apply(U, gW.contiguous(), None, False)
+        return gU, gV
+
+
+# Public entry points.  `.contiguous()` is applied HERE, as a differentiable torch op outside the Functions, so
+# that the tensors a Function saves are the graph-connected ones (needed by the differentiable backward passes).
+def linear(x, W, b=None):
+    """y = x @ W^T + b  (nn.Linear inside radial_function.py:29, transformer_block.py:420)."""
+    n, k = W.shape
+    return SliceMm.apply(x.contiguous(), b, ((0, k),), ((0, n),), n, True, W.contiguous())
+
+
+def so2_conv(A, bias0, groups, weights):
+    """All m-blocks of one SO(2) convolution as ONE grouped GEMM (so2_ops.py:150-185, :53-61).
+    A: [E, Kr*c_in] (m-primary, radial modulation already applied), weights[g]: [n_g, k_g] (m = 0: fc_m0.weight;
+    m > 0: the 2x2 real block form [[Wr, -Wi], [Wi, Wr]] of the complex multiply), bias0: fc_m0.bias.
+    groups[g] = (a_off, k_g, c_off, n_g).  Returns Y [E, extra + Kr*c_out]."""
+    xs = tuple((a_off, k_g) for a_off, k_g, _, _ in groups)
+    ys = tuple((c_off, n_g) for _, _, c_off, n_g in groups)
+    width = sum(n for _, n in ys)
+    return SliceMm.apply(A.contiguous(), bias0, xs, ys, width, True, *[w.contiguous() for w in weights])
 
 
 def so3_linear(x, W, b):
-    return SO3LinearFn.apply(x, W, b)
+    """SO3_LinearV2 (so3.py:698-743): one GEMM per degree l over the slab x[:, l^2:(l+1)^2, :], bias on l = 0."""
+    return SlabMm.apply(x.contiguous(), W.contiguous(), b, True)
 
 
 # ----------------------------------------------------------------------------------------------
@@ -571,25 +615,46 @@ def wigner_to_dense(wig, lmax):
     return out
 
 
+def _gr_fwd(x, rad, plan, wig, lmax, mmax):
+    lay = CoeffLayout.get(lmax, mmax)
+    tabs = lay.dev(x.device)
+    N, K, C = x.shape
+    nrad = lay.nslot * 2 * C
+    if rad is not None:
+        assert rad.shape == (plan.E, nrad), (rad.shape, plan.E, nrad)
+    out = torch.empty(plan.E, lay.Kr * 2 * C, dtype=_F32, device=x.device)
+    _lib.call("eqv2_gather_rotate_fwd", x.data_ptr(), plan.src.data_ptr(), plan.dst.data_ptr(), wig.data_ptr(),
+              _lib.ptr(rad), out.data_ptr(), tabs["pos_of_full"].data_ptr(), tabs["rad_slot"].data_ptr(),
+              plan.E, C, lmax, mmax, lay.Kr, nrad, _lib.stream_ptr())
+    return out
+
+
+def _gr_bwd(x, rad, gA, plan, wig, lmax, mmax, want_dx=True, want_drad=True):
+    """(dx, drad) of T(x, rad, g) = <g, rad * (W x)>:  dx = sum_e W^t (g*rad) uses (rad, g);  drad = g*(W x) uses (x, g)."""
+    lay = CoeffLayout.get(lmax, mmax)
+    tabs = lay.dev(x.device)
+    N, K, C = x.shape
+    nrad = lay.nslot * 2 * C
+    gx = torch.empty_like(x)
+    grad = torch.empty(plan.E, nrad, dtype=_F32, device=x.device) if want_drad else None
+    _lib.call("eqv2_gather_rotate_bwd", x.data_ptr(), wig.data_ptr(), _lib.ptr(rad), gA.data_ptr(),
+              plan.rowptr_src.data_ptr(), plan.perm_src.data_ptr(), plan.rowptr_dst.data_ptr(),
+              plan.perm_dst.data_ptr(), gx.data_ptr(), _lib.ptr(grad), tabs["pos_of_full"].data_ptr(),
+              tabs["rad_slot"].data_ptr(), N, C, lmax, mmax, lay.Kr, nrad, _lib.stream_ptr())
+    return (gx if want_dx else None), grad
+
+
 class GatherRotateFn(torch.autograd.Function):
     """x[src] | x[dst] -> Wigner rotate -> |m|<=mmax rows, m-primary -> * radial weights.
-    (transformer_block.py:250-275, so3.py:343-360, so3.py:322-334, so2_ops.py:150-175)"""
+    (transformer_block.py:250-275, so3.py:343-360, so3.py:322-334, so2_ops.py:150-175)
+    Trilinear form T(x, rad, g); forward = dT/dg, backward = (dT/dx, dT/drad), and the derivative of the
+    backward is again made of the same two kernels (GatherRotateBwdFn)."""
 
     @staticmethod
     def forward(ctx, x, rad, plan, wig, lmax, mmax):
         _lib.check_device(x, rad, wig)
-        x = x.contiguous()
-        rad = rad.contiguous() if rad is not None else None
-        lay = CoeffLayout.get(lmax, mmax)
-        tabs = lay.dev(x.device)
-        N, K, C = x.shape
-        nrad = lay.nslot * 2 * C
-        if rad is not None:
-            assert rad.shape == (plan.E, nrad), (rad.shape, plan.E, nrad)
-        out = torch.empty(plan.E, lay.Kr * 2 * C, dtype=_F32, device=x.device)
-        _lib.call("eqv2_gather_rotate_fwd", x.data_ptr(), plan.src.data_ptr(), plan.dst.data_ptr(), wig.data_ptr(),
-                  _lib.ptr(rad), out.data_ptr(), tabs["pos_of_full"].data_ptr(), tabs["rad_slot"].data_ptr(),
-                  plan.E, C, lmax, mmax, lay.Kr, nrad, _lib.stream_ptr())
+        assert x.is_contiguous() and (rad is None or rad.is_contiguous())
+        out = _gr_fwd(x, rad, plan, wig, lmax, mmax)
         ctx.save_for_backward(x, rad, wig)
         ctx.plan, ctx.lm = plan, (lmax, mmax)
         return out
@@ -597,58 +662,114 @@ class GatherRotateFn(torch.autograd.Function):
     @staticmethod
     def backward(ctx, gA):
         x, rad, wig = ctx.saved_tensors
-        plan = ctx.plan
-        lmax, mmax = ctx.lm
-        lay = CoeffLayout.get(lmax, mmax)
-        tabs = lay.dev(x.device)
-        N, K, C = x.shape
-        nrad = lay.nslot * 2 * C
-        gA = gA.contiguous()
-        gx = torch.empty_like(x)
-        grad = torch.empty(plan.E, nrad, dtype=_F32, device=x.device) if rad is not None else None
-        _lib.call("eqv2_gather_rotate_bwd", x.data_ptr(), wig.data_ptr(), _lib.ptr(rad), gA.data_ptr(),
-                  plan.rowptr_src.data_ptr(), plan.perm_src.data_ptr(), plan.rowptr_dst.data_ptr(),
-                  plan.perm_dst.data_ptr(), gx.data_ptr(), _lib.ptr(grad), tabs["pos_of_full"].data_ptr(),
-                  tabs["rad_slot"].data_ptr(), N, C, lmax, mmax, lay.Kr, nrad, _lib.stream_ptr())
+        gx, grad = GatherRotateBwdFn.apply(x, rad, gA.contiguous(), ctx.plan, wig, *ctx.lm)
         return gx, grad, None, None, None, None
+
+
+class GatherRotateBwdFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, rad, gA, plan, wig, lmax, mmax):
+        assert gA.is_contiguous()
+        gx, grad = _gr_bwd(x, rad, gA, plan, wig, lmax, mmax, want_drad=rad is not None)
+        ctx.save_for_backward(x, rad, gA, wig)
+        ctx.plan, ctx.lm = plan, (lmax, mmax)
+        if grad is None:
+            ctx.mark_non_differentiable()
+        return gx, grad
+
+    @staticmethod
+    @torch.autograd.function.once_differentiable
+    def backward(ctx, u, r):
+        """cotangents u (of gx), r (of grad):  S = T(u, rad, g) + T(x, r, g)."""
+        x, rad, gA, wig = ctx.saved_tensors
+        plan, (lmax, mmax) = ctx.plan, ctx.lm
+        d_x = d_rad = d_g = None
+        if r is not None and rad is not None:
+            r = r.contiguous()
+            d_x, _ = _gr_bwd(x, r, gA, plan, wig, lmax, mmax, want_drad=False)
+            d_g = _gr_fwd(x, r, plan, wig, lmax, mmax)
+        if u is not None:
+            u = u.contiguous()
+            if rad is not None:
+                _, d_rad = _gr_bwd(u, rad, gA, plan, wig, lmax, mmax, want_dx=False, want_drad=True)
+            t = _gr_fwd(u, rad, plan, wig, lmax, mmax)
+            d_g = t if d_g is None else d_g + t
+        return d_x, d_rad, d_g, None, None, None, None
+
+
+def _rir_fwd(val, alpha, plan, wig, lmax, mmax, rows_used, heads, scale, Cv):
+    lay = CoeffLayout.get(lmax, mmax)
+    tabs = lay.dev(val.device)
+    out = torch.empty(plan.N, lay.K, Cv, dtype=_F32, device=val.device)
+    _lib.call("eqv2_rotinv_reduce_fwd", val.data_ptr(), _lib.ptr(alpha), wig.data_ptr(),
+              plan.rowptr_dst.data_ptr(), plan.perm_dst.data_ptr(), out.data_ptr(),
+              tabs["pos_of_full"].data_ptr(), plan.N, Cv, rows_used, rows_used * Cv, heads, lmax, mmax,
+              float(scale), _lib.stream_ptr())
+    return out
+
+
+def _rir_bwd(gout, val, alpha, plan, wig, lmax, mmax, rows_used, heads, scale, Cv):
+    """(dval, dalpha) of T(val, alpha, g):  dval = alpha * (W g) uses (alpha, g);  dalpha = <W g, val> uses (val, g)."""
+    lay = CoeffLayout.get(lmax, mmax)
+    tabs = lay.dev(val.device)
+    gval = torch.empty_like(val)
+    galpha = torch.empty_like(alpha) if alpha is not None else None
+    _lib.call("eqv2_rotinv_reduce_bwd", gout.data_ptr(), val.data_ptr(), _lib.ptr(alpha), wig.data_ptr(),
+              plan.dst.data_ptr(), gval.data_ptr(), _lib.ptr(galpha), tabs["pos_of_full"].data_ptr(),
+              plan.E, Cv, rows_used, rows_used * Cv, heads, lmax, mmax, float(scale), _lib.stream_ptr())
+    return gval, galpha
 
 
 class RotInvReduceFn(torch.autograd.Function):
     """(value * alpha) -> Wigner^T with l>mmax rescale -> deterministic dst-segmented sum.
-    (transformer_block.py:321-331, so3.py:367-387,516-521, so3.py:304-318; input_block.py:113-129)"""
+    (transformer_block.py:321-331, so3.py:367-387,516-521, so3.py:304-318; input_block.py:113-129)
+    Trilinear form T(val, alpha, g) like GatherRotateFn."""
 
     @staticmethod
     def forward(ctx, val, alpha, plan, wig, lmax, mmax, rows_used, heads, scale):
         _lib.check_device(val, alpha, wig)
-        val = val.contiguous()
-        alpha = alpha.contiguous() if alpha is not None else None
-        lay = CoeffLayout.get(lmax, mmax)
-        tabs = lay.dev(val.device)
-        E = plan.E
+        assert val.is_contiguous() and (alpha is None or alpha.is_contiguous())
         Cv = val.shape[1] // rows_used
-        out = torch.empty(plan.N, lay.K, Cv, dtype=_F32, device=val.device)
-        _lib.call("eqv2_rotinv_reduce_fwd", val.data_ptr(), _lib.ptr(alpha), wig.data_ptr(),
-                  plan.rowptr_dst.data_ptr(), plan.perm_dst.data_ptr(), out.data_ptr(),
-                  tabs["pos_of_full"].data_ptr(), plan.N, Cv, rows_used, rows_used * Cv, heads, lmax, mmax,
-                  float(scale), _lib.stream_ptr())
+        meta = (lmax, mmax, rows_used, heads, float(scale), Cv)
+        out = _rir_fwd(val, alpha, plan, wig, *meta)
         ctx.save_for_backward(val, alpha, wig)
-        ctx.plan, ctx.meta = plan, (lmax, mmax, rows_used, heads, float(scale), Cv)
+        ctx.plan, ctx.meta = plan, meta
         return out
 
     @staticmethod
     def backward(ctx, gout):
         val, alpha, wig = ctx.saved_tensors
-        plan = ctx.plan
-        lmax, mmax, rows_used, heads, scale, Cv = ctx.meta
-        lay = CoeffLayout.get(lmax, mmax)
-        tabs = lay.dev(val.device)
-        gout = gout.contiguous()
-        gval = torch.empty_like(val)
-        galpha = torch.empty_like(alpha) if alpha is not None else None
-        _lib.call("eqv2_rotinv_reduce_bwd", gout.data_ptr(), val.data_ptr(), _lib.ptr(alpha), wig.data_ptr(),
-                  plan.dst.data_ptr(), gval.data_ptr(), _lib.ptr(galpha), tabs["pos_of_full"].data_ptr(),
-                  plan.E, Cv, rows_used, rows_used * Cv, heads, lmax, mmax, scale, _lib.stream_ptr())
+        gval, galpha = RotInvReduceBwdFn.apply(gout.contiguous(), val, alpha, ctx.plan, wig, ctx.meta)
         return gval, galpha, None, None, None, None, None, None, None
+
+
+class RotInvReduceBwdFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, gout, val, alpha, plan, wig, meta):
+        assert gout.is_contiguous()
+        gval, galpha = _rir_bwd(gout, val, alpha, plan, wig, *meta)
+        ctx.save_for_backward(gout, val, alpha, wig)
+        ctx.plan, ctx.meta = plan, meta
+        return gval, galpha
+
+    @staticmethod
+    @torch.autograd.function.once_differentiable
+    def backward(ctx, u, a):
+        """cotangents u (of gval), a (of galpha):  S = T(u, alpha, g) + T(val, a, g)."""
+        gout, val, alpha, wig = ctx.saved_tensors
+        plan, meta = ctx.plan, ctx.meta
+        d_g = d_val = d_alpha = None
+        if u is not None:
+            u = u.contiguous()
+            d_g = _rir_fwd(u, alpha, plan, wig, *meta)
+            if alpha is not None:
+                _, d_alpha = _rir_bwd(gout, u, alpha, plan, wig, *meta)
+        if a is not None and alpha is not None:
+            a = a.contiguous()
+            t = _rir_fwd(val, a, plan, wig, *meta)
+            d_g = t if d_g is None else d_g + t
+            d_val, _ = _rir_bwd(gout, val, a, plan, wig, *meta)
+        return d_g, d_val, d_alpha, None, None, None
 
 
 # ----------------------------------------------------------------------------------------------
@@ -739,15 +860,22 @@ def _s2_blocks(R, C):
     return int(max(1, min(work, 148 * 2)))
 
 
+def _s2_bwd2(mats, xp, x_rs, gp, g_rs, dop, o_rs, up, u_rs, wp, w_rs, d2xp, d2x_rs, d2gp, d2g_rs, d2op, d2o_rs, R, C, device):
+    if mats.factors is None:
+        raise _lib.Eqv2Error("S2 activation: second-order terms need the resolution-18 factorised grid")
+    slot = _s2_bind_tables(mats, device)
+    _lib.call("eqv2_s2sep_bwd2", xp, x_rs, gp, g_rs, dop, o_rs, up, u_rs, wp, w_rs, d2xp, d2x_rs, d2gp, d2g_rs, d2op,
+              d2o_rs, R, C, mats.lmax, mats.mmax, int(mats.order == "m"), slot, _lib.stream_ptr())
+
+
 class S2ActFn(torch.autograd.Function):
-    """SeparableS2Activation on a node tensor (transformer_block.py:442-447, activation.py:173-192):
-    x [N,K,C] (l-primary), gate [N,C] -> [N,K,C]."""
+    """SeparableS2Activation (transformer_block.py:442-447, activation.py:173-192):
+    x [R,Kr,C], gate [R,C] (or None: plain S2Activation) -> [R,Kr,C]."""
 
     @staticmethod
     def forward(ctx, x, gate, mats):
         _lib.check_device(x, gate)
-        x = x.contiguous()
-        gate = gate.contiguous() if gate is not None else None
+        assert x.is_contiguous() and (gate is None or gate.is_contiguous())
         R, Kr, C = x.shape
         assert Kr == mats.Kr
         out = torch.empty_like(x)
@@ -759,26 +887,52 @@ class S2ActFn(torch.autograd.Function):
     @staticmethod
     def backward(ctx, go):
         x, gate = ctx.saved_tensors
-        mats = ctx.mats
-        go = go.contiguous()
+        gx, gg = S2ActBwdFn.apply(x, gate, go.contiguous(), ctx.mats)
+        return gx, gg, None
+
+
+class S2ActBwdFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, gate, go, mats):
+        assert go.is_contiguous()
         R, Kr, C = x.shape
         gx = torch.empty_like(x)
         gg = torch.empty_like(gate) if gate is not None else None
         _s2_bwd(mats, x.data_ptr(), Kr * C, _lib.ptr(gate), C, go.data_ptr(), Kr * C, gx.data_ptr(), Kr * C,
                 _lib.ptr(gg), C, R, C, x.device)
-        return gx, gg, None
+        ctx.save_for_backward(x, gate, go)
+        ctx.mats = mats
+        return gx, gg
+
+    @staticmethod
+    @torch.autograd.function.once_differentiable
+    def backward(ctx, u, w):
+        x, gate, go = ctx.saved_tensors
+        mats = ctx.mats
+        R, Kr, C = x.shape
+        u = u.contiguous() if u is not None else None
+        w = w.contiguous() if (w is not None and gate is not None) else None
+        d_x = torch.empty_like(x)
+        d_go = torch.empty_like(go)
+        d_gate = torch.empty_like(gate) if gate is not None else None
+        _s2_bwd2(mats, x.data_ptr(), Kr * C, _lib.ptr(gate), C, go.data_ptr(), Kr * C, _lib.ptr(u), Kr * C, _lib.ptr(w), C,
+                 d_x.data_ptr(), Kr * C, _lib.ptr(d_gate), C, d_go.data_ptr(), Kr * C, R, C, x.device)
+        return d_x, d_gate, d_go, None
 
 
 class EdgeActAlphaFn(torch.autograd.Function):
-    """Consumes the first SO(2) convolution's output Y[E, heads*ach + H + Kr*H] and produces
+    """FIRST-ORDER fused path (no position gradients, configs 1-2).  Consumes the first SO(2) convolution's
+    output Y[E, heads*ach + H + Kr*H] and produces
       * Z[E, Kr*H]   = SeparableS2Activation(gate = Y[:, heads*ach : heads*ach+H], Y[:, extra:])
       * alpha[E, heads] = segment_softmax_dst( alpha_dot . SmoothLeakyReLU(LayerNorm(Y[:, :heads*ach])) )
-    (transformer_block.py:289-315).  One backward fills one dY buffer -- no zero-fill, no adds."""
+    (transformer_block.py:289-315).  One backward fills one dY buffer -- no zero-fill, no adds.
+    When edge distances carry gradient (forces by autograd) the block uses S2ActFn + AttnAlphaFn instead,
+    whose backward passes are differentiable."""
 
     @staticmethod
     def forward(ctx, Y, ln_w, ln_b, alpha_dot, plan, mats, heads, ach, H):
         _lib.check_device(Y, ln_w, ln_b, alpha_dot)
-        Y = Y.contiguous()
+        assert Y.is_contiguous()
         E, W = Y.shape
         extra = heads * ach + H
         Kr = mats.Kr
@@ -799,6 +953,7 @@ class EdgeActAlphaFn(torch.autograd.Function):
         return Z, alpha
 
     @staticmethod
+    @torch.autograd.function.once_differentiable
     def backward(ctx, gZ, galpha):
         Y, ln_w, ln_b, alpha_dot, alpha = ctx.saved_tensors
         plan, mats = ctx.plan, ctx.mats
@@ -829,8 +984,86 @@ class EdgeActAlphaFn(torch.autograd.Function):
 
 
 # ----------------------------------------------------------------------------------------------
-# equivariant norms, LN+SiLU, RBF
+# small per-row operators.  Forward and first-order backward are kernels.  When the backward pass itself is
+# being recorded (create_graph=True: forces by autograd), its derivative is obtained by re-expressing the
+# operator with torch primitives on the saved inputs and differentiating that expression -- these
+# operators are a negligible share of the step and their second derivatives are lengthy (LayerNorm of
+# LayerNorm-gradient terms); the heavy operators (GEMMs, rotations, S2 grids) differentiate through kernels.
 # ----------------------------------------------------------------------------------------------
+def _second_order(fn, inputs, gout):
+    """Gradients of fn(*inputs) w.r.t. the inputs that require grad, as differentiable functions of
+    (inputs, gout).  Called from a backward running under create_graph=True."""
+    with torch.enable_grad():
+        out = fn(*inputs)
+        idx = [i for i, t in enumerate(inputs) if t is not None and t.requires_grad]
+        grads = torch.autograd.grad(out, [inputs[i] for i in idx], gout, create_graph=True, allow_unused=True)
+    res = [None] * len(inputs)
+    for i, g in zip(idx, grads):
+        res[i] = g
+    return res
+
+
+def _recording(*tensors):
+    return torch.is_grad_enabled() and any(t is not None and t.requires_grad for t in tensors)
+
+
+def _slr(x):
+    return 0.6 * x + 0.4 * x * (2.0 * torch.sigmoid(x) - 1.0)
+
+
+def _alpha_expr(heads, ach, eps, dst, N):
+    def fn(Ya, ln_w, ln_b, alpha_dot):
+        a = Ya.reshape(-1, heads, ach)
+        if ln_w is not None:
+            a = torch.nn.functional.layer_norm(a, (ach,), ln_w, ln_b, eps)
+        logits = (_slr(a) * alpha_dot.unsqueeze(0)).sum(-1)
+        idx = dst.view(-1, 1).expand_as(logits)
+        mx = torch.full((N, heads), float("-inf"), dtype=logits.dtype, device=logits.device)
+        mx = mx.scatter_reduce(0, idx, logits.detach(), reduce="amax", include_self=True)
+        e = (logits - mx.gather(0, idx)).exp()
+        ssum = torch.zeros(N, heads, dtype=logits.dtype, device=logits.device).scatter_add(0, idx, e)
+        return e / (ssum.gather(0, idx) + 1e-16)
+    return fn
+
+
+class AttnAlphaFn(torch.autograd.Function):
+    """alpha[E, heads] = segment_softmax_dst(alpha_dot . SmoothLeakyReLU(LayerNorm(Ya)))  (transformer_block.py:311-315)."""
+
+    @staticmethod
+    def forward(ctx, Ya, ln_w, ln_b, alpha_dot, plan, heads, ach):
+        _lib.check_device(Ya, ln_w, ln_b, alpha_dot)
+        assert Ya.is_contiguous() and alpha_dot.is_contiguous()
+        E = Ya.shape[0]
+        logits = torch.empty(E, heads, dtype=_F32, device=Ya.device)
+        alpha = torch.empty(E, heads, dtype=_F32, device=Ya.device)
+        _lib.call("eqv2_attn_alpha_fwd", Ya.data_ptr(), heads * ach, _lib.ptr(ln_w), _lib.ptr(ln_b), alpha_dot.data_ptr(),
+                  plan.rowptr_dst.data_ptr(), plan.perm_dst.data_ptr(), logits.data_ptr(), alpha.data_ptr(),
+                  E, plan.N, heads, ach, 1e-5, _lib.stream_ptr(), n_kernels=2)
+        ctx.save_for_backward(Ya, ln_w, ln_b, alpha_dot, alpha)
+        ctx.plan, ctx.meta = plan, (heads, ach)
+        return alpha
+
+    @staticmethod
+    def backward(ctx, galpha):
+        Ya, ln_w, ln_b, alpha_dot, alpha = ctx.saved_tensors
+        plan, (heads, ach) = ctx.plan, ctx.meta
+        if _recording(Ya, ln_w, ln_b, alpha_dot, galpha):
+            g = _second_order(_alpha_expr(heads, ach, 1e-5, plan.dst, plan.N), [Ya, ln_w, ln_b, alpha_dot], galpha)
+            return g[0], g[1], g[2], g[3], None, None, None
+        E = Ya.shape[0]
+        galpha = galpha.contiguous()
+        gY = torch.empty_like(Ya)
+        g_lnw = torch.zeros_like(ln_w) if ln_w is not None else None
+        g_lnb = torch.zeros_like(ln_b) if ln_b is not None else None
+        g_dot = torch.zeros_like(alpha_dot)
+        dlogits = torch.empty_like(alpha)
+        _lib.call("eqv2_attn_alpha_bwd", Ya.data_ptr(), heads * ach, _lib.ptr(ln_w), _lib.ptr(ln_b), alpha_dot.data_ptr(),
+                  plan.rowptr_dst.data_ptr(), plan.perm_dst.data_ptr(), alpha.data_ptr(), galpha.data_ptr(),
+                  dlogits.data_ptr(), gY.data_ptr(), heads * ach, _lib.ptr(g_lnw), _lib.ptr(g_lnb), g_dot.data_ptr(),
+                  E, plan.N, heads, ach, 1e-5, _lib.stream_ptr(), n_kernels=2)
+        return gY, g_lnw, g_lnb, g_dot, None, None, None
+
+
 def norm_groups(norm_type, lmax):
     """(ngroups, group_of_l, bw_l) for layer_norm.py:38-108 / :112-201 / :265-351."""
     if norm_type == "rms_norm_sh":
@@ -842,13 +1075,29 @@ def norm_groups(norm_type, lmax):
     raise ValueError(norm_type)
 
 
+def _equiv_norm_expr(norm_type, lmax, eps):
+    ng, gol, bw = norm_groups(norm_type, lmax)
+
+    def fn(x, w, b):
+        N, K, C = x.shape
+        dev = x.device
+        lk = torch.tensor([l for l in range(lmax + 1) for _ in range(2 * l + 1)], device=dev)
+        bwk = torch.tensor(bw, dtype=x.dtype, device=dev)[lk]
+        gk = torch.tensor(gol, device=dev)[lk]
+        f = torch.cat([x[:, :1] - x[:, :1].mean(dim=2, keepdim=True), x[:, 1:]], dim=1)
+        onehot = torch.nn.functional.one_hot(gk, ng).to(x.dtype)
+        s = torch.einsum("nkc,k,kg->ng", f * f, bwk, onehot) / C
+        inv = (s + eps).rsqrt()[:, gk]
+        out = f * inv.unsqueeze(-1) * w[lk].unsqueeze(0)
+        return torch.cat([out[:, :1] + b.view(1, 1, C), out[:, 1:]], dim=1)
+    return fn
+
+
 class EquivNormFn(torch.autograd.Function):
     @staticmethod
     def forward(ctx, x, w, b, norm_type, lmax, eps):
         _lib.check_device(x, w, b)
-        x = x.contiguous()
-        w = w.contiguous()
-        b = b.contiguous()
+        assert x.is_contiguous() and w.is_contiguous() and b.is_contiguous()
         N, K, C = x.shape
         ng, gol, bw = norm_groups(norm_type, lmax)
         gol_c = (ctypes.c_int * len(gol))(*gol)
@@ -859,14 +1108,17 @@ class EquivNormFn(torch.autograd.Function):
         _lib.call("eqv2_equiv_norm_fwd", x.data_ptr(), w.data_ptr(), b.data_ptr(), out.data_ptr(), inv.data_ptr(),
                   mean.data_ptr(), N, C, lmax, ng, ctypes.cast(gol_c, ctypes.c_void_p),
                   ctypes.cast(bw_c, ctypes.c_void_p), float(eps), _lib.stream_ptr())
-        ctx.save_for_backward(x, w, inv, mean)
-        ctx.meta = (norm_type, lmax)
+        ctx.save_for_backward(x, w, b, inv, mean)
+        ctx.meta = (norm_type, lmax, float(eps))
         return out
 
     @staticmethod
     def backward(ctx, go):
-        x, w, inv, mean = ctx.saved_tensors
-        norm_type, lmax = ctx.meta
+        x, w, b, inv, mean = ctx.saved_tensors
+        norm_type, lmax, eps = ctx.meta
+        if _recording(x, w, b, go):
+            g = _second_order(_equiv_norm_expr(norm_type, lmax, eps), [x, w, b], go)
+            return g[0], g[1], g[2], None, None, None
         N, K, C = x.shape
         ng, gol, bw = norm_groups(norm_type, lmax)
         gol_c = (ctypes.c_int * len(gol))(*gol)
@@ -887,9 +1139,7 @@ class LnSiluFn(torch.autograd.Function):
     @staticmethod
     def forward(ctx, x, w, b, eps):
         _lib.check_device(x, w, b)
-        x = x.contiguous()
-        w = w.contiguous()
-        b = b.contiguous()
+        assert x.is_contiguous() and w.is_contiguous() and b.is_contiguous()
         rows, width = x.shape
         y = torch.empty_like(x)
         _lib.call("eqv2_ln_silu_fwd", x.data_ptr(), w.data_ptr(), b.data_ptr(), y.data_ptr(), rows, width, float(eps),
@@ -901,13 +1151,18 @@ class LnSiluFn(torch.autograd.Function):
     @staticmethod
     def backward(ctx, gy):
         x, w, b = ctx.saved_tensors
+        eps = ctx.eps
+        if _recording(x, w, b, gy):
+            Fn = torch.nn.functional
+            g = _second_order(lambda x_, w_, b_: Fn.silu(Fn.layer_norm(x_, x_.shape[-1:], w_, b_, eps)), [x, w, b], gy)
+            return g[0], g[1], g[2], None
         rows, width = x.shape
         gy = gy.contiguous()
         gx = torch.empty_like(x)
         gw = torch.zeros_like(w)
         gb = torch.zeros_like(b)
         _lib.call("eqv2_ln_silu_bwd", x.data_ptr(), w.data_ptr(), b.data_ptr(), gy.data_ptr(), gx.data_ptr(),
-                  gw.data_ptr(), gb.data_ptr(), rows, width, ctx.eps, _lib.stream_ptr())
+                  gw.data_ptr(), gb.data_ptr(), rows, width, eps, _lib.stream_ptr())
         return gx, gw, gb, None
 
 
@@ -917,8 +1172,7 @@ class RbfFn(torch.autograd.Function):
     @staticmethod
     def forward(ctx, d, offset, coeff):
         _lib.check_device(d, offset)
-        d = d.contiguous().view(-1)
-        offset = offset.contiguous()
+        assert d.dim() == 1 and d.is_contiguous() and offset.is_contiguous()
         R = offset.shape[0]
         out = torch.empty(d.shape[0], R, dtype=_F32, device=d.device)
         _lib.call("eqv2_rbf_fwd", d.data_ptr(), out.data_ptr(), d.shape[0], R, offset.data_ptr(), float(coeff),
@@ -930,8 +1184,45 @@ class RbfFn(torch.autograd.Function):
     @staticmethod
     def backward(ctx, go):
         d, offset = ctx.saved_tensors
+        coeff = ctx.coeff
+        if _recording(d, go):
+            g = _second_order(lambda d_: torch.exp(coeff * (d_.view(-1, 1) - offset.view(1, -1)) ** 2), [d], go)
+            return g[0], None, None
         go = go.contiguous()
         gd = torch.empty_like(d)
         _lib.call("eqv2_rbf_bwd", d.data_ptr(), go.data_ptr(), gd.data_ptr(), d.shape[0], offset.shape[0],
-                  offset.data_ptr(), ctx.coeff, _lib.stream_ptr())
+                  offset.data_ptr(), coeff, _lib.stream_ptr())
         return gd, None, None
+
+
+def gather_rotate(x, rad, plan, wig, lmax, mmax):
+    return GatherRotateFn.apply(x.contiguous(), rad.contiguous() if rad is not None else None, plan, wig, lmax, mmax)
+
+
+def rotinv_reduce(val, alpha, plan, wig, lmax, mmax, rows_used, heads, scale):
+    return RotInvReduceFn.apply(val.contiguous(), alpha.contiguous() if alpha is not None else None, plan, wig, lmax, mmax,
+                                rows_used, heads, scale)
+
+
+def s2_act(x, gate, mats):
+    return S2ActFn.apply(x.contiguous(), gate.contiguous() if gate is not None else None, mats)
+
+
+def attn_alpha(Ya, ln_w, ln_b, alpha_dot, plan, heads, ach):
+    return AttnAlphaFn.apply(Ya.contiguous(), ln_w, ln_b, alpha_dot.contiguous(), plan, heads, ach)
+
+
+def edge_act_alpha(Y, ln_w, ln_b, alpha_dot, plan, mats, heads, ach, H):
+    return EdgeActAlphaFn.apply(Y.contiguous(), ln_w, ln_b, alpha_dot.contiguous(), plan, mats, heads, ach, H)
+
+
+def equiv_norm(x, w, b, norm_type, lmax, eps):
+    return EquivNormFn.apply(x.contiguous(), w.contiguous(), b.contiguous(), norm_type, lmax, eps)
+
+
+def ln_silu(x, w, b, eps):
+    return LnSiluFn.apply(x.contiguous(), w.contiguous(), b.contiguous(), eps)
+
+
+def rbf(d, offset, coeff):
+    return RbfFn.apply(d.reshape(-1).contiguous(), offset.contiguous(), coeff)

@@ -95,6 +95,13 @@ int eqv2_s2sep_bwd(const float* X, long long x_rs, const float* gate, long long 
                    float* dX, long long dx_rs, float* dgate, long long dg_rs, long long R, int C, int lmax, int mmax,
                    int m_primary, int slot, void* stream);
 
+/* derivative of eqv2_s2sep_bwd w.r.t. (X, gate, dO) for cotangents U (of dX) and Wg (of dgate): the second-order
+ * term needed when forces = -dE/dpos are trained on (train_MatPES_GATAWandB.py:72-91). */
+int eqv2_s2sep_bwd2(const float* X, long long x_rs, const float* gate, long long g_rs, const float* dO, long long o_rs,
+                    const float* U, long long u_rs, const float* Wg, long long w_rs, float* d2X, long long d2x_rs,
+                    float* d2gate, long long d2g_rs, float* d2O, long long d2o_rs, long long R, int C, int lmax, int mmax,
+                    int m_primary, int slot, void* stream);
+
 /* ---- attention logits + segment softmax (transformer_block.py:311-315) ------------------- */
 int eqv2_attn_alpha_fwd(const float* Y, long long y_rs, const float* ln_w /*or NULL*/, const float* ln_b,
                         const float* alpha_dot /*[heads,ach]*/, const int* rowptr_dst, const int* perm_dst,

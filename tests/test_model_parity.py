@@ -82,3 +82,23 @@ def test_oc20_small_other_gemm_modes(mode, tol):
         assert rel_err(forces, fx["forces"]) < tol
     finally:
         ops.set_gemm_mode("tf32x3")
+
+
+def test_matpes_v2_train_step_matches_reference(backend):
+    """MatPES pattern (train_MatPES_GATAWandB.py:67-91): energy, forces = -autograd.grad(E, pos, create_graph=True),
+    then the gradient of a loss on energy AND forces w.r.t. every parameter (double backward), against the golden
+    vectors of the unmodified reference.  The graph is built by the CUDA 27-image builder."""
+    from helpers import build_matpes_v2
+    fx = golden("matpes_v2_small.pt")
+    model = build_matpes_v2(fx["hyper"], backend.device)
+    load_params(model, fx["params"])
+    data = backend.to(dict(fx["inputs"]))
+    pos = data["pos"].clone().requires_grad_(True)
+    out = model(dict(data, pos=pos))
+    assert rel_err(out["energy"], fx["energy"]) < OUT_TOL
+    forces = -torch.autograd.grad(out["energy_total"].sum(), pos, create_graph=True, retain_graph=True)[0]
+    assert rel_err(forces, fx["forces"]) < 2e-5
+    wf = torch.linspace(-1, 1, forces.numel(), device=forces.device).view_as(forces)
+    we = torch.linspace(0.5, 1.5, out["energy"].numel(), device=forces.device).view_as(out["energy"])
+    ((out["energy"] * we).sum() + (forces * wf).sum()).backward()
+    _check_grads(model, fx)
