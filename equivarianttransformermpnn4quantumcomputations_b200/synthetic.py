@@ -70,3 +70,34 @@ def qm9_batch(num_molecules, seed, nmin=9, nmax=29):
                 pos=torch.from_numpy(np.concatenate(pos)).float(),
                 batch=torch.from_numpy(np.concatenate(batch)).long(),
                 natoms=torch.tensor(natoms, dtype=torch.long))
+
+
+def matpes_batch(num_cells, seed, n_atoms=30, vol_per_atom=15.0):
+    """Bulk cells of `n_atoms` atoms at 15 A^3/atom, lattice = L*I + 5 % Gaussian shear, Z ~ U{1..89}
+    (cfg 3/4); structures with a pair closer than 0.7 A (any of the 27 images) are resampled."""
+    rng = np.random.default_rng(seed)
+    Z, pos, cell, batch, natoms = [], [], [], [], []
+    side = (vol_per_atom * n_atoms) ** (1.0 / 3.0)
+    shifts = np.array([[a, b, c] for a in (-1, 0, 1) for b in (-1, 0, 1) for c in (-1, 0, 1)], dtype=float)
+    for g in range(num_cells):
+        lat = side * np.eye(3) + 0.05 * side * rng.normal(size=(3, 3))
+        pts = []
+        while len(pts) < n_atoms:
+            p = rng.uniform(0, 1, 3) @ lat
+            ok = True
+            if pts:
+                d = (np.array(pts)[:, None, :] + (shifts @ lat)[None, :, :]) - p
+                ok = np.sqrt((d ** 2).sum(-1)).min() > 0.7
+            if ok:
+                pts.append(p)
+        Z.append(rng.integers(1, 90, n_atoms)); pos.append(np.array(pts)); cell.append(lat)
+        batch.append(np.full(n_atoms, g)); natoms.append(n_atoms)
+    data = dict(atomic_numbers=torch.from_numpy(np.concatenate(Z)).long(),
+                pos=torch.from_numpy(np.concatenate(pos)).float(),
+                batch=torch.from_numpy(np.concatenate(batch)).long(),
+                natoms=torch.tensor(natoms, dtype=torch.long),
+                cell=torch.from_numpy(np.stack(cell)).float())
+    g2 = torch.Generator().manual_seed(seed + 1)
+    data["energy"] = torch.randn(num_cells, 1, generator=g2)
+    data["forces"] = 0.1 * torch.randn(num_cells * n_atoms, 3, generator=g2)
+    return data
