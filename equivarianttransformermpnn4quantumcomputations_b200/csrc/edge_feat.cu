@@ -205,6 +205,54 @@ __global__ void wigner_kernel(const float* __restrict__ rot, const float* __rest
   }
 }
 
+// ---------------------------------------------------------------------------------------- edge SH
+// Real spherical harmonics of the edge direction for l = 1..lmax ("norm" normalisation: |Y_l| = 1), as
+// e3nn o3.SphericalHarmonics(normalize=False, normalization='norm') is used at
+// equiformerv2_MatPES_GATAV2.py:137-140,232-241 on unit = vec / max(|vec|, 1e-8).  Basis of SURVEY App. B.1
+// (polar axis y, azimuth atan2(x, z), no Condon-Shortley phase), evaluated pole-free as Cartesian polynomials:
+//   A_m + i B_m = (z + i x)^m ,  Q_l^m(y) = P_l^m(y) / sin^m(beta)  (upward recurrences in y).
+// One thread per edge; output [E, (lmax+1)^2 - 1].
+constexpr int SH_MAXL = 6;
+
+__global__ void edge_sh_kernel(const float* __restrict__ vec, float* __restrict__ out, long long E, int lmax) {
+  const long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= E) return;
+  float x = vec[3 * e], y = vec[3 * e + 1], z = vec[3 * e + 2];
+  const float inv = 1.0f / fmaxf(sqrtf(x * x + y * y + z * z), 1e-8f);
+  x *= inv; y *= inv; z *= inv;
+  float A[SH_MAXL + 1], B[SH_MAXL + 1];
+  A[0] = 1.f; B[0] = 0.f;
+  for (int m = 1; m <= lmax; ++m) {
+    A[m] = A[m - 1] * z - B[m - 1] * x;
+    B[m] = B[m - 1] * z + A[m - 1] * x;
+  }
+  const int K1 = (lmax + 1) * (lmax + 1) - 1;
+  float* o = out + e * K1;
+  for (int m = 0; m <= lmax; ++m) {
+    float dfact = 1.f;
+    for (int k = 1; k < 2 * m; k += 2) dfact *= (float)k;
+    float qm2 = 0.f, qm1 = 0.f;          // Q_{l-2}^m, Q_{l-1}^m
+    for (int l = m; l <= lmax; ++l) {
+      float q;
+      if (l == m) q = dfact;
+      else if (l == m + 1) q = (float)(2 * m + 1) * y * qm1;
+      else q = ((float)(2 * l - 1) * y * qm1 - (float)(l + m - 1) * qm2) / (float)(l - m);
+      qm2 = qm1; qm1 = q;
+      if (l == 0) continue;
+      // N_l^m * sqrt(4 pi / (2l+1)) = sqrt((l-m)! / (l+m)!)
+      float ratio = 1.f;
+      for (int k = l - m + 1; k <= l + m; ++k) ratio /= (float)k;
+      const float n = sqrtf(ratio);
+      const int base = l * l - 1 + l;    // index of (l, m=0) in the output (l = 0 dropped)
+      if (m == 0) o[base] = n * q;
+      else {
+        o[base + m] = n * 1.41421356237309515f * q * A[m];
+        o[base - m] = n * 1.41421356237309515f * q * B[m];
+      }
+    }
+  }
+}
+
 }  // namespace
 
 extern "C" int eqv2_rbf_fwd(const float* d, float* out, long long E, int R, const float* offset, float coeff,
@@ -252,5 +300,13 @@ extern "C" int eqv2_wigner_from_rot(const float* rot, const float* Jd, float* wi
   const size_t smem = (size_t)(WS + WIG_WARPS * MAXN * MAXN + WIG_WARPS * 6 * MAXN) * sizeof(float);
   EQV2_LAUNCH(wigner_kernel, dim3((unsigned)((E + WIG_WARPS - 1) / WIG_WARPS)), dim3(WIG_WARPS * 32), smem, stream, rot, Jd, wig, E, lmax, WS);
   EQV2_CHECK_LAUNCH("eqv2_wigner_from_rot");
+  return 0;
+}
+
+extern "C" int eqv2_edge_sh(const float* vec, float* out, long long E, int lmax, void* stream) {
+  if (E == 0) return 0;
+  EQV2_REQUIRE(lmax >= 1 && lmax <= SH_MAXL, "edge_sh: lmax=%d out of range (1..%d)", lmax, SH_MAXL);
+  EQV2_LAUNCH(edge_sh_kernel, dim3((unsigned)((E + 127) / 128)), dim3(128), 0, stream, vec, out, E, lmax);
+  EQV2_CHECK_LAUNCH("eqv2_edge_sh");
   return 0;
 }

@@ -602,6 +602,16 @@ def wigner_from_rot(rot, lmax):
     return wig
 
 
+def edge_sh(edge_vec, lmax):
+    """Edge spherical harmonics l = 1..lmax in the original frame, detached (equiformerv2_MatPES_GATAV2.py:232-241)."""
+    _lib.check_device(edge_vec)
+    vec = edge_vec.detach().to(_F32).contiguous()
+    E = vec.shape[0]
+    out = torch.empty(E, (lmax + 1) ** 2 - 1, dtype=_F32, device=vec.device)
+    _lib.call("eqv2_edge_sh", vec.data_ptr(), out.data_ptr(), E, lmax, _lib.stream_ptr())
+    return out
+
+
 def wigner_to_dense(wig, lmax):
     """Expand the packed blocks to the reference's dense [E,K,K] layout (diagnostics / API parity)."""
     E = wig.shape[0]

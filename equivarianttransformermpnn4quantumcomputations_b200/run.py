@@ -16,6 +16,14 @@ def install_alias():
     sys.modules["EquiformerV2Functions"] = pkg
     for sub in _SUBMODULES:
         sys.modules["EquiformerV2Functions." + sub] = importlib.import_module(pkg.__name__ + "." + sub)
+    # forks used by the GATA models: `from NewFunctions.Gotennet_morethaninspired.transformer_block import ...`
+    # (models/equiformerv2_MatPES_GATAV2.py:49)
+    nf = importlib.import_module(__package__ + ".NewFunctions")
+    sys.modules["NewFunctions"] = nf
+    for fork in ("Gotennet_morethaninspired",):
+        sys.modules["NewFunctions." + fork] = importlib.import_module(nf.__name__ + "." + fork)
+        for sub in ("transformer_block", "activation"):
+            sys.modules[f"NewFunctions.{fork}.{sub}"] = importlib.import_module(f"{nf.__name__}.{fork}.{sub}")
     return pkg
 
 

@@ -226,6 +226,39 @@ def golden_matpes():
           "self edges", int((ei2[0] == ei2[1]).sum()))
 
 
+def golden_gata():
+    """BASELINE config 4 family: equiformerv2_MatPES_GATAV2.py (HTR + GATA value activation), train-step pattern."""
+    import importlib
+    mod = importlib.import_module("equiformerv2_MatPES_GATAV2")
+    gen = torch.Generator().manual_seed(17)
+    Z, pos, batch, natoms, cell = synth_cells(gen, 2, 6, vol_per_atom=14.0, zmax=89)
+    data = dict(atomic_numbers=Z, pos=pos, batch=batch, natoms=natoms, cell=cell)
+    hp = dict(lmax=3, mmax=3, C=16, H=8, heads=2, alpha_ch=8, value_ch=4, ffn_hidden=16, edge_ch=16, num_layers=2,
+              norm_type="rms_norm_sh", grid_res=18, num_rbf=600, cutoff=4.5, max_elements=100, max_neighbors=8)
+    torch.manual_seed(8)
+    model = mod.EquiformerV2_MatPES(
+        max_neighbors=8, max_radius=4.5, max_num_elements=100, num_layers=2, sphere_channels=16, attn_hidden_channels=8,
+        num_heads=2, attn_alpha_channels=8, attn_value_channels=4, ffn_hidden_channels=16, lmax_list=[3], mmax_list=[3],
+        grid_resolution=18, edge_channels=16, alpha_drop=0.0, drop_path_rate=0.0, proj_drop=0.0)
+    with torch.no_grad():
+        for p in model.parameters():
+            p.add_(0.05 * torch.randn(p.shape, generator=gen))
+    ei, d, vec = model.generate_graph(pos, batch, cell)
+    posg = pos.clone().requires_grad_(True)
+    out = model(dict(data, pos=posg))
+    forces = -torch.autograd.grad(out["energy_total"].sum(), posg, create_graph=True, retain_graph=True)[0]
+    wf = torch.linspace(-1, 1, forces.numel()).view_as(forces)
+    we = torch.linspace(0.5, 1.5, out["energy"].numel()).view_as(out["energy"])
+    ((out["energy"] * we).sum() + (forces * wf).sum()).backward()
+    fx = dict(hyper=hp, params=params_of(model),
+              grads={k: p.grad.clone() for k, p in model.named_parameters() if p.grad is not None},
+              inputs=data, edge_index=ei, edge_distance=d.detach(), edge_vec=vec.detach(),
+              energy=out["energy"].detach(), energy_total=out["energy_total"].detach(), forces=forces.detach())
+    torch.save(fx, os.path.join(OUT, "matpes_gatav2_small.pt"))
+    nograd = [k for k, p in model.named_parameters() if p.grad is None]
+    print("gata E", ei.shape[1], out["energy"].detach().view(-1), "params without grad:", len(nograd))
+
+
 if __name__ == "__main__":
     ref_loader.install()
     os.makedirs(OUT, exist_ok=True)
@@ -233,3 +266,4 @@ if __name__ == "__main__":
     golden_oc20()
     golden_qm9()
     golden_matpes()
+    golden_gata()

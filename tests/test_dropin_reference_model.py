@@ -19,7 +19,8 @@ pytestmark = pytest.mark.skipif(not os.path.isdir(REF), reason="reference tree n
 @pytest.fixture
 def reference_on_dropin(backend):
     saved = {k: v for k, v in sys.modules.items()
-             if k.split(".")[0] in ("EquiformerV2Functions", "equiformerv2_qm9", "equiformerv2_oc20", "e3nn", "fairchem",
+             if k.split(".")[0] in ("EquiformerV2Functions", "NewFunctions", "equiformerv2_qm9", "equiformerv2_oc20",
+                                    "equiformerv2_MatPESv2", "equiformerv2_MatPES_GATAV2", "e3nn", "fairchem",
                                     "torch_geometric")}
     for k in saved:
         del sys.modules[k]
@@ -30,7 +31,8 @@ def reference_on_dropin(backend):
     pkg("run").install_alias()
     yield backend
     for k in list(sys.modules):
-        if k.split(".")[0] in ("EquiformerV2Functions", "equiformerv2_qm9", "equiformerv2_oc20"):
+        if k.split(".")[0] in ("EquiformerV2Functions", "NewFunctions", "equiformerv2_qm9", "equiformerv2_oc20",
+                               "equiformerv2_MatPESv2", "equiformerv2_MatPES_GATAV2"):
             del sys.modules[k]
     sys.modules.update(saved)
     for p in added:
@@ -83,3 +85,37 @@ def test_reference_oc20_model_file_runs_on_dropin(reference_on_dropin):
     with fixed_rand_like(fx["rand_vec"] + 0.5):
         energy, forces = model(data)
     assert rel_err(energy, fx["energy"]) < 1e-5 and rel_err(forces, fx["forces"]) < 1e-5
+
+
+@pytest.mark.parametrize("modname,fixture", [("equiformerv2_MatPESv2", "matpes_v2_small.pt"),
+                                             ("equiformerv2_MatPES_GATAV2", "matpes_gatav2_small.pt")])
+def test_reference_matpes_model_files_run_on_dropin(reference_on_dropin, modname, fixture):
+    """The unmodified MatPES v2 / GATAV2 model files (their own Python graph builder, HTR/GATA blocks from the
+    drop-in `NewFunctions`) with the reference train-step pattern: forces by autograd, double backward."""
+    be = reference_on_dropin
+    mod = importlib.import_module(modname)
+    assert mod.__file__.startswith(REF)
+    fx = golden(fixture)
+    hp = fx["hyper"]
+    model = mod.EquiformerV2_MatPES(
+        max_neighbors=hp["max_neighbors"], max_radius=hp["cutoff"], max_num_elements=100, num_layers=hp["num_layers"],
+        sphere_channels=hp["C"], attn_hidden_channels=hp["H"], num_heads=hp["heads"], attn_alpha_channels=hp["alpha_ch"],
+        attn_value_channels=hp["value_ch"], ffn_hidden_channels=hp["ffn_hidden"], lmax_list=[hp["lmax"]],
+        mmax_list=[hp["mmax"]], grid_resolution=18, edge_channels=hp["edge_ch"], alpha_drop=0.0, drop_path_rate=0.0,
+        proj_drop=0.0).to(be.device)
+    own = dict(model.named_parameters())
+    assert set(own) == set(fx["params"])
+    with torch.no_grad():
+        for k, v in fx["params"].items():
+            own[k].copy_(v)
+    data = be.to(dict(fx["inputs"]))
+    pos = data["pos"].clone().requires_grad_(True)
+    out = model(dict(data, pos=pos))
+    assert rel_err(out["energy"], fx["energy"]) < 1e-5
+    forces = -torch.autograd.grad(out["energy_total"].sum(), pos, create_graph=True, retain_graph=True)[0]
+    assert rel_err(forces, fx["forces"]) < 2e-5
+    wf = torch.linspace(-1, 1, forces.numel(), device=forces.device).view_as(forces)
+    we = torch.linspace(0.5, 1.5, out["energy"].numel(), device=forces.device).view_as(out["energy"])
+    ((out["energy"] * we).sum() + (forces * wf).sum()).backward()
+    worst = max(rel_err(p.grad, fx["grads"][k]) for k, p in model.named_parameters() if k in fx["grads"])
+    assert worst < 2e-4

@@ -102,3 +102,24 @@ def test_matpes_v2_train_step_matches_reference(backend):
     we = torch.linspace(0.5, 1.5, out["energy"].numel(), device=forces.device).view_as(out["energy"])
     ((out["energy"] * we).sum() + (forces * wf).sum()).backward()
     _check_grads(model, fx)
+
+
+def test_matpes_gatav2_train_step_matches_reference(backend):
+    """BASELINE config 4 family (equiformerv2_MatPES_GATAV2.py: HTR edge stream + GATA value activation): energy,
+    autograd forces and double-backward parameter gradients against the unmodified reference; parameters the
+    reference leaves without gradient (so2_conv_1.so2_m_conv.*) must stay without gradient."""
+    from helpers import build_gatav2
+    fx = golden("matpes_gatav2_small.pt")
+    model = build_gatav2(fx["hyper"], backend.device)
+    load_params(model, fx["params"])
+    data = backend.to(dict(fx["inputs"]))
+    pos = data["pos"].clone().requires_grad_(True)
+    out = model(dict(data, pos=pos))
+    assert rel_err(out["energy"], fx["energy"]) < OUT_TOL
+    forces = -torch.autograd.grad(out["energy_total"].sum(), pos, create_graph=True, retain_graph=True)[0]
+    assert rel_err(forces, fx["forces"]) < 2e-5
+    wf = torch.linspace(-1, 1, forces.numel(), device=forces.device).view_as(forces)
+    we = torch.linspace(0.5, 1.5, out["energy"].numel(), device=forces.device).view_as(out["energy"])
+    ((out["energy"] * we).sum() + (forces * wf).sum()).backward()
+    _check_grads(model, fx)
+    assert any(k not in fx["grads"] for k, _ in model.named_parameters())
