@@ -67,22 +67,28 @@ class GATAValueActivation(nn.Module):
     """combined = attn_output + W_rs(t_ij) * gamma_s(h_j) -> (o_s | o_d^l | o_t^l);
     out_0 = SiLU(o_s); out_l = o_d^l * r^l + o_t^l * (xj_proj X_j)^l on the first min(2l+1, 2 mmax+1) rows."""
 
-    def __init__(self, sphere_channels, hidden_channels, edge_channels, lmax, mmax):
+    def __init__(self, sphere_channels, hidden_channels, edge_channels, lmax, mmax, num_rbf=None):
         super().__init__()
         self.lmax = lmax
         self.mmax = mmax
         self.hidden_channels = hidden_channels
         self.S = 1 + 2 * lmax
         self.W_rs = nn.Linear(edge_channels, self.S * hidden_channels)
+        if num_rbf is not None:
+            # `Gotennets_GATA_phi_refined_every_layer` variant (activation.py:314,352): extra factor phi_proj(phi_r)
+            self.phi_proj = nn.Linear(num_rbf, self.S * hidden_channels, bias=False)
         self.gamma_s = nn.Sequential(nn.Linear(sphere_channels, self.S * hidden_channels), nn.SiLU())
         self.xj_proj = nn.Linear(sphere_channels, hidden_channels, bias=False)
         self.scalar_act = nn.SiLU()
         self.full_degree_sizes = [2 * l + 1 for l in range(1, lmax + 1)]
         self.reduced_degree_sizes = [min(2 * l + 1, 2 * mmax + 1) for l in range(1, lmax + 1)]
 
-    def forward(self, attn_output, t_ij, h_j, X_j, rl_ij):
+    def forward(self, attn_output, t_ij, h_j, X_j, rl_ij, phi_r=None):
         C = self.hidden_channels
-        combined = attn_output + _lin(self.W_rs, t_ij) * F.silu(_lin(self.gamma_s[0], h_j))
+        bias = _lin(self.W_rs, t_ij) * F.silu(_lin(self.gamma_s[0], h_j))
+        if phi_r is not None:
+            bias = bias * _lin(self.phi_proj, phi_r)
+        combined = attn_output + bias
         chunks = combined.split(C, dim=-1)
         out = [F.silu(chunks[0]).unsqueeze(1)]
         Xp = _lin(self.xj_proj, X_j)

@@ -25,8 +25,9 @@ class SO2EquivariantGraphAttention(nn.Module):
                  output_channels, lmax_list, mmax_list, SO3_rotation, mappingReduced, SO3_grid, max_num_elements,
                  edge_channels_list, edge_channels, use_atom_edge_embedding=True, use_m_share_rad=False,
                  activation="scaled_silu", use_s2_act_attn=False, use_attn_renorm=True, use_gate_act=False,
-                 use_sep_s2_act=True, alpha_drop=0.0):
+                 use_sep_s2_act=True, alpha_drop=0.0, num_rbf=None):
         super().__init__()
+        self.num_rbf = num_rbf
         self.sphere_channels = sphere_channels
         self.hidden_channels = hidden_channels
         self.num_heads = num_heads
@@ -68,13 +69,14 @@ class SO2EquivariantGraphAttention(nn.Module):
         nn.init.uniform_(self.alpha_dot, -bound, bound)
         self.alpha_dropout = nn.Dropout(alpha_drop) if alpha_drop != 0.0 else None
         self.value_act = GATAValueActivation(sphere_channels=sphere_channels, hidden_channels=hidden_channels,
-                                             edge_channels=edge_channels, lmax=self.lmax, mmax=max(mmax_list))
+                                             edge_channels=edge_channels, lmax=self.lmax, mmax=max(mmax_list),
+                                             num_rbf=num_rbf)
         self.so2_conv_2 = SO2_Convolution(hidden_channels, num_heads * attn_value_channels, lmax_list, mmax_list,
                                           mappingReduced, internal_weights=True, edge_channels_list=None,
                                           extra_m0_output_channels=None)
         self.proj = SO3_LinearV2(num_heads * attn_value_channels, output_channels, lmax=lmax_list[0])
 
-    def forward(self, x, atomic_numbers, edge_distance, edge_index, t_ij, rl_ij):
+    def forward(self, x, atomic_numbers, edge_distance, edge_index, t_ij, rl_ij, phi_r=None):
         lmax, mmax = self.lmax_list[0], self.mmax_list[0]
         lay = ops.CoeffLayout.get(lmax, mmax)
         emb = x.embedding
@@ -97,7 +99,8 @@ class SO2EquivariantGraphAttention(nn.Module):
         alpha = ops.attn_alpha(Y0[:, :ha], ln_w, ln_b, self.alpha_dot, plan, self.num_heads, self.attn_alpha_channels)
         attn_output = alpha.mean(dim=1, keepdim=True) * Y0[:, ha:]
         x_dst = emb[edge_index[1]]                                           # un-rotated neighbour features
-        msg = self.value_act(attn_output=attn_output, t_ij=t_ij, h_j=x_dst[:, 0, :], X_j=x_dst[:, 1:, :], rl_ij=rl_ij)
+        msg = self.value_act(attn_output=attn_output, t_ij=t_ij, h_j=x_dst[:, 0, :], X_j=x_dst[:, 1:, :], rl_ij=rl_ij,
+                             phi_r=phi_r if self.num_rbf is not None else None)
         tabs = lay.dev(emb.device)
         Zm = msg.index_select(1, tabs["to_m"]).reshape(plan.E, lay.Kr * self.hidden_channels)   # l- -> m-primary
         V = self.so2_conv_2.conv_m_primary(Zm)
@@ -116,7 +119,7 @@ class TransBlockV2(nn.Module):
                  max_num_elements, edge_channels_list, edge_channels, use_atom_edge_embedding=True,
                  use_m_share_rad=False, attn_activation="silu", use_s2_act_attn=False, use_attn_renorm=True,
                  ffn_activation="silu", use_gate_act=False, use_grid_mlp=False, use_sep_s2_act=True,
-                 norm_type="rms_norm_sh", alpha_drop=0.0, drop_path_rate=0.0, proj_drop=0.0):
+                 norm_type="rms_norm_sh", alpha_drop=0.0, drop_path_rate=0.0, proj_drop=0.0, num_rbf=None):
         super().__init__()
         max_lmax = max(lmax_list)
         self.norm_1 = get_normalization_layer(norm_type, lmax=max_lmax, num_channels=sphere_channels)
@@ -129,7 +132,7 @@ class TransBlockV2(nn.Module):
             edge_channels_list=edge_channels_list, edge_channels=edge_channels,
             use_atom_edge_embedding=use_atom_edge_embedding, use_m_share_rad=use_m_share_rad,
             activation=attn_activation, use_s2_act_attn=use_s2_act_attn, use_attn_renorm=use_attn_renorm,
-            use_gate_act=use_gate_act, use_sep_s2_act=use_sep_s2_act, alpha_drop=alpha_drop)
+            use_gate_act=use_gate_act, use_sep_s2_act=use_sep_s2_act, alpha_drop=alpha_drop, num_rbf=num_rbf)
         self.drop_path = GraphDropPath(drop_path_rate) if drop_path_rate > 0.0 else None
         self.proj_drop = EquivariantDropoutArraySphericalHarmonics(proj_drop, drop_graph=False) if proj_drop > 0.0 else None
         self.norm_2 = get_normalization_layer(norm_type, lmax=max_lmax, num_channels=sphere_channels)
@@ -147,13 +150,13 @@ class TransBlockV2(nn.Module):
             t = self.proj_drop(t, batch)
         return t
 
-    def forward(self, x, atomic_numbers, edge_distance, edge_index, batch, t_ij, rl_ij):
+    def forward(self, x, atomic_numbers, edge_distance, edge_index, batch, t_ij, rl_ij, phi_r=None):
         out = x
         X_all = x.embedding[:, 1:, :]
         t_ij = self.htr(t_ij, X_all[edge_index[0]], X_all[edge_index[1]], rl_ij)    # edge stream update (un-normed x)
         res = out.embedding
         out.embedding = self.norm_1(out.embedding)
-        out = self.ga(out, atomic_numbers, edge_distance, edge_index, t_ij=t_ij, rl_ij=rl_ij)
+        out = self.ga(out, atomic_numbers, edge_distance, edge_index, t_ij=t_ij, rl_ij=rl_ij, phi_r=phi_r)
         out.embedding = self._drop(out.embedding, batch) + res
         res = out.embedding
         out.embedding = self.norm_2(out.embedding)

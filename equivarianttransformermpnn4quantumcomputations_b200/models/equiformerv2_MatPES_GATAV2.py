@@ -19,6 +19,11 @@ _AVG_DEGREE_MATPES = 12.0
 
 
 class EquiformerV2_MatPES(nn.Module):
+    # hooks for the phi-at-every-iteration twin (equiformerv2_MatPES_GATAV2_phi_at_every_iteration_like_gata.py)
+    _avg_degree = _AVG_DEGREE_MATPES
+    _phi_every_layer = False
+    _block_cls = TransBlockV2
+
     def __init__(self, use_pbc=True, regress_forces=True, regress_stress=False, otf_graph=True, max_neighbors=20,
                  max_radius=6.0, max_num_elements=100, num_layers=6, sphere_channels=128, attn_hidden_channels=128,
                  num_heads=8, attn_alpha_channels=32, attn_value_channels=16, ffn_hidden_channels=512,
@@ -57,9 +62,10 @@ class EquiformerV2_MatPES(nn.Module):
         self.SO3_grid = build_so3_grid(lmax_list, grid_resolution)
         self.edge_degree_embedding = EdgeDegreeEmbedding(
             sphere_channels, lmax_list, mmax_list, self.SO3_rotation, self.mappingReduced, max_num_elements,
-            self.edge_channels_list, self.block_use_atom_edge_embedding, rescale_factor=_AVG_DEGREE_MATPES)
+            self.edge_channels_list, self.block_use_atom_edge_embedding, rescale_factor=self._avg_degree)
+        extra_kw = dict(num_rbf=num_rbf) if self._phi_every_layer else {}
         self.blocks = nn.ModuleList([
-            TransBlockV2(sphere_channels=sphere_channels, attn_hidden_channels=attn_hidden_channels, num_heads=num_heads,
+            self._block_cls(sphere_channels=sphere_channels, attn_hidden_channels=attn_hidden_channels, num_heads=num_heads,
                          attn_alpha_channels=attn_alpha_channels, attn_value_channels=attn_value_channels,
                          ffn_hidden_channels=ffn_hidden_channels, output_channels=sphere_channels, lmax_list=lmax_list,
                          mmax_list=mmax_list, SO3_rotation=self.SO3_rotation, mappingReduced=self.mappingReduced,
@@ -69,7 +75,7 @@ class EquiformerV2_MatPES(nn.Module):
                          attn_activation=attn_activation, use_s2_act_attn=use_s2_act_attn,
                          use_attn_renorm=use_attn_renorm, ffn_activation=ffn_activation, use_gate_act=use_gate_act,
                          use_grid_mlp=use_grid_mlp, use_sep_s2_act=use_sep_s2_act, norm_type=norm_type,
-                         alpha_drop=alpha_drop, drop_path_rate=drop_path_rate, proj_drop=proj_drop)
+                         alpha_drop=alpha_drop, drop_path_rate=drop_path_rate, proj_drop=proj_drop, **extra_kw)
             for _ in range(num_layers)])
         self.norm = get_normalization_layer(norm_type, lmax=max(lmax_list), num_channels=sphere_channels)
         self.energy_block = FeedForwardNetwork(sphere_channels, ffn_hidden_channels, 1, lmax_list, mmax_list,
@@ -126,8 +132,10 @@ class EquiformerV2_MatPES(nn.Module):
                                    self.target_embedding(atomic_numbers[edge_index[1]])), dim=1)
         x.embedding = x.embedding + self.edge_degree_embedding(atomic_numbers, edge_feat, edge_index).embedding
         t_ij = self._init_t_ij(x.embedding, rbf, edge_index)
+        phi_kw = dict(phi_r=edge_feat) if self._phi_every_layer else {}
         for block in self.blocks:
-            x, t_ij = block(x, atomic_numbers, edge_feat, edge_index, batch=data["batch"], t_ij=t_ij, rl_ij=rl_ij)
+            x, t_ij = block(x, atomic_numbers, edge_feat, edge_index, batch=data["batch"], t_ij=t_ij, rl_ij=rl_ij,
+                            **phi_kw)
         x.embedding = self.norm(x.embedding)
         node_energy = self.energy_block(x).embedding[:, 0, 0]
         energy_total = segment_sum(node_energy, data["batch"], self.batch_size)

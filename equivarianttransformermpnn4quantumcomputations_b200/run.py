@@ -20,7 +20,7 @@ def install_alias():
     # (models/equiformerv2_MatPES_GATAV2.py:49)
     nf = importlib.import_module(__package__ + ".NewFunctions")
     sys.modules["NewFunctions"] = nf
-    for fork in ("Gotennet_morethaninspired",):
+    for fork in ("Gotennet_morethaninspired", "Gotennets_GATA_phi_refined_every_layer"):
         sys.modules["NewFunctions." + fork] = importlib.import_module(nf.__name__ + "." + fork)
         for sub in ("transformer_block", "activation"):
             sys.modules[f"NewFunctions.{fork}.{sub}"] = importlib.import_module(f"{nf.__name__}.{fork}.{sub}")

@@ -226,10 +226,11 @@ def golden_matpes():
           "self edges", int((ei2[0] == ei2[1]).sum()))
 
 
-def golden_gata():
-    """BASELINE config 4 family: equiformerv2_MatPES_GATAV2.py (HTR + GATA value activation), train-step pattern."""
+def golden_gata(modname="equiformerv2_MatPES_GATAV2", out_name="matpes_gatav2_small.pt"):
+    """BASELINE config 4 family: equiformerv2_MatPES_GATAV2.py (HTR + GATA value activation) and its
+    phi-at-every-iteration twin, train-step pattern."""
     import importlib
-    mod = importlib.import_module("equiformerv2_MatPES_GATAV2")
+    mod = importlib.import_module(modname)
     gen = torch.Generator().manual_seed(17)
     Z, pos, batch, natoms, cell = synth_cells(gen, 2, 6, vol_per_atom=14.0, zmax=89)
     data = dict(atomic_numbers=Z, pos=pos, batch=batch, natoms=natoms, cell=cell)
@@ -254,7 +255,7 @@ def golden_gata():
               grads={k: p.grad.clone() for k, p in model.named_parameters() if p.grad is not None},
               inputs=data, edge_index=ei, edge_distance=d.detach(), edge_vec=vec.detach(),
               energy=out["energy"].detach(), energy_total=out["energy_total"].detach(), forces=forces.detach())
-    torch.save(fx, os.path.join(OUT, "matpes_gatav2_small.pt"))
+    torch.save(fx, os.path.join(OUT, out_name))
     nograd = [k for k, p in model.named_parameters() if p.grad is None]
     print("gata E", ei.shape[1], out["energy"].detach().view(-1), "params without grad:", len(nograd))
 
@@ -267,3 +268,4 @@ if __name__ == "__main__":
     golden_qm9()
     golden_matpes()
     golden_gata()
+    golden_gata("equiformerv2_MatPES_GATAV2_phi_at_every_iteration_like_gata", "matpes_gatav2_phi_small.pt")

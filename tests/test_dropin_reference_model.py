@@ -20,7 +20,8 @@ pytestmark = pytest.mark.skipif(not os.path.isdir(REF), reason="reference tree n
 def reference_on_dropin(backend):
     saved = {k: v for k, v in sys.modules.items()
              if k.split(".")[0] in ("EquiformerV2Functions", "NewFunctions", "equiformerv2_qm9", "equiformerv2_oc20",
-                                    "equiformerv2_MatPESv2", "equiformerv2_MatPES_GATAV2", "e3nn", "fairchem",
+                                    "equiformerv2_MatPESv2", "equiformerv2_MatPES_GATAV2",
+                                    "equiformerv2_MatPES_GATAV2_phi_at_every_iteration_like_gata", "e3nn", "fairchem",
                                     "torch_geometric")}
     for k in saved:
         del sys.modules[k]
@@ -32,7 +33,8 @@ def reference_on_dropin(backend):
     yield backend
     for k in list(sys.modules):
         if k.split(".")[0] in ("EquiformerV2Functions", "NewFunctions", "equiformerv2_qm9", "equiformerv2_oc20",
-                               "equiformerv2_MatPESv2", "equiformerv2_MatPES_GATAV2"):
+                               "equiformerv2_MatPESv2", "equiformerv2_MatPES_GATAV2",
+                               "equiformerv2_MatPES_GATAV2_phi_at_every_iteration_like_gata"):
             del sys.modules[k]
     sys.modules.update(saved)
     for p in added:
@@ -88,7 +90,9 @@ def test_reference_oc20_model_file_runs_on_dropin(reference_on_dropin):
 
 
 @pytest.mark.parametrize("modname,fixture", [("equiformerv2_MatPESv2", "matpes_v2_small.pt"),
-                                             ("equiformerv2_MatPES_GATAV2", "matpes_gatav2_small.pt")])
+                                             ("equiformerv2_MatPES_GATAV2", "matpes_gatav2_small.pt"),
+                                             ("equiformerv2_MatPES_GATAV2_phi_at_every_iteration_like_gata",
+                                              "matpes_gatav2_phi_small.pt")])
 def test_reference_matpes_model_files_run_on_dropin(reference_on_dropin, modname, fixture):
     """The unmodified MatPES v2 / GATAV2 model files (their own Python graph builder, HTR/GATA blocks from the
     drop-in `NewFunctions`) with the reference train-step pattern: forces by autograd, double backward."""

@@ -104,13 +104,14 @@ def test_matpes_v2_train_step_matches_reference(backend):
     _check_grads(model, fx)
 
 
-def test_matpes_gatav2_train_step_matches_reference(backend):
+@pytest.mark.parametrize("variant", ["gatav2", "gatav2_phi"])
+def test_matpes_gatav2_train_step_matches_reference(backend, variant):
     """BASELINE config 4 family (equiformerv2_MatPES_GATAV2.py: HTR edge stream + GATA value activation): energy,
     autograd forces and double-backward parameter gradients against the unmodified reference; parameters the
     reference leaves without gradient (so2_conv_1.so2_m_conv.*) must stay without gradient."""
-    from helpers import build_gatav2
-    fx = golden("matpes_gatav2_small.pt")
-    model = build_gatav2(fx["hyper"], backend.device)
+    from helpers import build_gatav2, build_gatav2_phi
+    fx = golden("matpes_gatav2_small.pt" if variant == "gatav2" else "matpes_gatav2_phi_small.pt")
+    model = (build_gatav2 if variant == "gatav2" else build_gatav2_phi)(fx["hyper"], backend.device)
     load_params(model, fx["params"])
     data = backend.to(dict(fx["inputs"]))
     pos = data["pos"].clone().requires_grad_(True)
