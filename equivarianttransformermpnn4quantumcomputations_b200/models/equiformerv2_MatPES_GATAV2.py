@@ -137,6 +137,8 @@ class EquiformerV2_MatPES(nn.Module):
             x, t_ij = block(x, atomic_numbers, edge_feat, edge_index, batch=data["batch"], t_ij=t_ij, rl_ij=rl_ij,
                             **phi_kw)
         x.embedding = self.norm(x.embedding)
+        if getattr(self, "global_attn", None) is not None:          # config-5 twin: all-to-all attention after the norm
+            x.embedding = self.global_attn(x.embedding, data["batch"], pos)
         node_energy = self.energy_block(x).embedding[:, 0, 0]
         energy_total = segment_sum(node_energy, data["batch"], self.batch_size)
         energy_out = (energy_total / data["natoms"].to(node_energy.dtype)).unsqueeze(1)

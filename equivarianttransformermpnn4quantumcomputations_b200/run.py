@@ -20,10 +20,13 @@ def install_alias():
     # (models/equiformerv2_MatPES_GATAV2.py:49)
     nf = importlib.import_module(__package__ + ".NewFunctions")
     sys.modules["NewFunctions"] = nf
-    for fork in ("Gotennet_morethaninspired", "Gotennets_GATA_phi_refined_every_layer"):
+    for fork in ("Gotennet_morethaninspired", "Gotennets_GATA_phi_refined_every_layer", "GATA_and_all2all"):
         sys.modules["NewFunctions." + fork] = importlib.import_module(nf.__name__ + "." + fork)
         for sub in ("transformer_block", "activation"):
-            sys.modules[f"NewFunctions.{fork}.{sub}"] = importlib.import_module(f"{nf.__name__}.{fork}.{sub}")
+            try:
+                sys.modules[f"NewFunctions.{fork}.{sub}"] = importlib.import_module(f"{nf.__name__}.{fork}.{sub}")
+            except ModuleNotFoundError:
+                pass        # GATA_and_all2all ships only `activation` (its transformer_block is unused)
     return pkg
 
 

@@ -269,3 +269,5 @@ if __name__ == "__main__":
     golden_matpes()
     golden_gata()
     golden_gata("equiformerv2_MatPES_GATAV2_phi_at_every_iteration_like_gata", "matpes_gatav2_phi_small.pt")
+    golden_gata("equiformerv2_MatPES_GATAV2_GLOBALALLATTENTION_HTR_phi_at_every_iteration_like_gata_with_DISTANCE",
+                "matpes_gatav2_global_small.pt")

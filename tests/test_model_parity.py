@@ -22,13 +22,22 @@ def _graph_inputs(fx, backend):
 
 def _check_grads(model, fx):
     bad = []
+    # gradients that are mathematically zero (e.g. a key bias under softmax) are rounding noise in both paths:
+    # measure them against the overall gradient scale, not against themselves
+    floor = 1e-7 * max(float(g.abs().max()) for g in fx["grads"].values())
+    # softmax is invariant to a bias on the keys: d/d(k_proj.bias) is EXACTLY zero mathematically and pure rounding
+    # noise (1e-8) numerically in both implementations
+    zero_by_construction = ("global_attn.k_proj.bias",)
     for k, p in model.named_parameters():
         g_ref = fx["grads"].get(k)
         if g_ref is None:
             assert p.grad is None or float(p.grad.abs().max()) == 0.0, k
             continue
         assert p.grad is not None, k
-        e = rel_err(p.grad, g_ref)
+        if k.endswith(zero_by_construction):
+            assert float(p.grad.abs().max()) < 1e-5 * floor / 1e-7 * 1e-2, k
+            continue
+        e = float((p.grad.detach().double().cpu() - g_ref.double()).abs().max() / max(float(g_ref.abs().max()), floor))
         if e > GRAD_TOL:
             bad.append((k, e))
     assert not bad, bad
@@ -104,14 +113,16 @@ def test_matpes_v2_train_step_matches_reference(backend):
     _check_grads(model, fx)
 
 
-@pytest.mark.parametrize("variant", ["gatav2", "gatav2_phi"])
+@pytest.mark.parametrize("variant", ["gatav2", "gatav2_phi", "gatav2_global"])
 def test_matpes_gatav2_train_step_matches_reference(backend, variant):
     """BASELINE config 4 family (equiformerv2_MatPES_GATAV2.py: HTR edge stream + GATA value activation): energy,
     autograd forces and double-backward parameter gradients against the unmodified reference; parameters the
     reference leaves without gradient (so2_conv_1.so2_m_conv.*) must stay without gradient."""
-    from helpers import build_gatav2, build_gatav2_phi
-    fx = golden("matpes_gatav2_small.pt" if variant == "gatav2" else "matpes_gatav2_phi_small.pt")
-    model = (build_gatav2 if variant == "gatav2" else build_gatav2_phi)(fx["hyper"], backend.device)
+    import helpers
+    name = {"gatav2": "matpes_gatav2_small.pt", "gatav2_phi": "matpes_gatav2_phi_small.pt",
+            "gatav2_global": "matpes_gatav2_global_small.pt"}[variant]      # the last one is BASELINE config 5
+    fx = golden(name)
+    model = getattr(helpers, "build_" + variant)(fx["hyper"], backend.device)
     load_params(model, fx["params"])
     data = backend.to(dict(fx["inputs"]))
     pos = data["pos"].clone().requires_grad_(True)
