@@ -1,53 +1,129 @@
-// Wigner-D edge-frame rotation kernels (HBM-bound gather / scatter side of the block).
+// Wigner-D edge-frame rotation kernels (HBM / L2-bound gather / scatter side of the block).
 //
 //  gather_rotate_fwd : x[src] | x[dst] -> rotate into the edge frame, keep |m| <= mmax, emit rows in
 //                      m-primary order and (optionally) apply the radial modulation.
 //                      Replaces transformer_block.py:250-275 + so3.py:343-360,509-512 + so3.py:322-334
 //                      + the `x * x_edge` products of so2_ops.py:150-175 in one pass.
 //  gather_rotate_bwd : node-centric, deterministic (no atomics): for every node, walk its outgoing
-//                      (src half) and incoming (dst half) edges in CSR order.
+//                      (src half) and incoming (dst half) edges in CSR order -- the two halves run
+//                      concurrently in two thread groups and are summed through shared memory.
 //  rotinv_reduce_fwd : value * alpha -> rotate back (Wigner^T with the l > mmax rescale of
 //                      so3.py:175-195) -> dst-sorted segmented sum.  Replaces
 //                      transformer_block.py:321-331 + so3.py:367-387,516-521 + so3.py:304-318
 //                      (index_add_) deterministically; also serves input_block.py:113-129.
+//                      Two thread groups take alternate edges of the node's segment.
 //  rotinv_reduce_bwd : edge-parallel gather of the node gradient, rotate, split into d(value), d(alpha).
 //
 // Wigner matrices are stored block-diagonal: [E, sum_l (2l+1)^2] (so3.py:537 stores dense [E,K,K]).
-// One CTA per edge (or node), one thread per channel; the per-thread coefficient column lives in
-// registers (LMAX is a template parameter), the edge's Wigner blocks are broadcast from shared memory.
+// (LMAX, MMAX) are template parameters: every coefficient index (l-major position, m-primary position,
+// radial slot) is a compile-time constant, the per-thread coefficient column lives in registers, and the
+// edge's Wigner blocks sit in shared memory with rows padded to a multiple of 4 floats so that a row is
+// read with broadcast 128-bit loads (one LDS.128 per 4 FMAs instead of one LDS.32 per FMA).
+#include <type_traits>
+
 #include "common.cuh"
 
 namespace {
 
-template <int LMAX>
-struct KDim { static constexpr int K = (LMAX + 1) * (LMAX + 1); static constexpr int WS = (LMAX + 1) * (4 * (LMAX + 1) * (LMAX + 1) - 1) / 3; };
+template <int L>
+struct Dim {
+  static constexpr int K = (L + 1) * (L + 1);
+  static constexpr int WS = (L + 1) * (4 * (L + 1) * (L + 1) - 1) / 3;
+};
+__host__ __device__ constexpr int pad4(int n) { return (n + 3) & ~3; }
+// offset of degree l inside the padded shared-memory copy (rows of 2l+1 floats padded to a multiple of 4)
+__host__ __device__ constexpr int wpad_off(int l) {
+  int s = 0;
+  for (int j = 0; j < l; ++j) s += (2 * j + 1) * pad4(2 * j + 1);
+  return s;
+}
+// m-primary position of coefficient (l, m), |m| <= min(l, M)      (so3.py:97-109)
+template <int L, int M>
+__host__ __device__ constexpr int mpos(int l, int m) {
+  if (m == 0) return l;
+  const int am = m < 0 ? -m : m;
+  int base = L + 1;
+  for (int j = 1; j < am; ++j) base += 2 * (L - j + 1);
+  return base + (m < 0 ? (L - am + 1) : 0) + (l - am);
+}
+// radial-weight slot of rows (l, +-am): slot * C_in + channel indexes the rad vector (so2_ops.py:100-133)
+template <int L, int M>
+__host__ __device__ constexpr int rslot(int l, int am) {
+  if (am == 0) return l;
+  int base = L + 1;
+  for (int j = 1; j < am; ++j) base += (L - j + 1);
+  return base + (l - am);
+}
+__host__ __device__ constexpr float rescale_l(int l, int mmax) {
+  // sqrt((2l+1)/(2 mmax+1)) for l > mmax, evaluated at run time where needed (sqrtf is not constexpr)
+  return (l > mmax) ? (float)(2 * l + 1) / (float)(2 * mmax + 1) : 1.0f;
+}
 
-__device__ __forceinline__ float rescale_l(int l, int mmax) {
-  return (l > mmax) ? sqrtf((float)(2 * l + 1) / (float)(2 * mmax + 1)) : 1.0f;
+// cooperative copy of one edge's packed Wigner blocks into the padded shared layout
+template <int L>
+__device__ __forceinline__ void stage_wigner(float* __restrict__ sw, const float* __restrict__ wig_e, int tid, int nthreads) {
+#pragma unroll
+  for (int l = 0; l <= L; ++l) {
+    const int n = 2 * l + 1, ns = pad4(n);
+    const float* src = wig_e + eqv2_wig_off(l);
+    float* dst = sw + wpad_off(l);
+    for (int i = tid; i < n * n; i += nthreads) dst[(i / n) * ns + (i % n)] = src[i];
+  }
+}
+
+// acc = sum_j w[row][j] * v[j]   (row of degree l, padded smem, 128-bit broadcast loads)
+template <int LDEG>
+__device__ __forceinline__ float row_dot(const float* __restrict__ sw, int row, const float* v /* n values */) {
+  constexpr int n = 2 * LDEG + 1, ns = pad4(n);
+  const float4* wr = reinterpret_cast<const float4*>(sw + wpad_off(LDEG) + row * ns);
+  float acc = 0.f;
+#pragma unroll
+  for (int q = 0; q < ns / 4; ++q) {
+    const float4 w = wr[q];
+    acc = fmaf(w.x, v[4 * q], acc);
+    if (4 * q + 1 < n) acc = fmaf(w.y, v[4 * q + 1], acc);
+    if (4 * q + 2 < n) acc = fmaf(w.z, v[4 * q + 2], acc);
+    if (4 * q + 3 < n) acc = fmaf(w.w, v[4 * q + 3], acc);
+  }
+  return acc;
+}
+// v[j] += w[row][j] * s
+template <int LDEG>
+__device__ __forceinline__ void row_axpy(const float* __restrict__ sw, int row, float s, float* v) {
+  constexpr int n = 2 * LDEG + 1, ns = pad4(n);
+  const float4* wr = reinterpret_cast<const float4*>(sw + wpad_off(LDEG) + row * ns);
+#pragma unroll
+  for (int q = 0; q < ns / 4; ++q) {
+    const float4 w = wr[q];
+    v[4 * q] = fmaf(w.x, s, v[4 * q]);
+    if (4 * q + 1 < n) v[4 * q + 1] = fmaf(w.y, s, v[4 * q + 1]);
+    if (4 * q + 2 < n) v[4 * q + 2] = fmaf(w.z, s, v[4 * q + 2]);
+    if (4 * q + 3 < n) v[4 * q + 3] = fmaf(w.w, s, v[4 * q + 3]);
+  }
+}
+
+// compile-time loop over degrees
+template <int LDEG, int L, int M, typename F>
+__device__ __forceinline__ void for_each_degree(F&& f) {
+  f(std::integral_constant<int, LDEG>{});
+  if constexpr (LDEG < L) for_each_degree<LDEG + 1, L, M>(static_cast<F&&>(f));
 }
 
 // ------------------------------------------------------------------------------------------
-template <int LMAX>
-__global__ void gather_rotate_fwd_kernel(const float* __restrict__ x, const long long* __restrict__ src,
-                                         const long long* __restrict__ dst, const float* __restrict__ wig,
-                                         const float* __restrict__ rad, float* __restrict__ out,
-                                         const int* __restrict__ pos_of_full, const int* __restrict__ rad_slot,
-                                         int C, int Kr, int mmax, int nrad) {
-  constexpr int K = KDim<LMAX>::K, WS = KDim<LMAX>::WS;
-  __shared__ float sw[WS];
-  __shared__ int spos[K];
-  __shared__ int sslot[K];
+template <int L, int M>
+__global__ void __launch_bounds__(256)
+gather_rotate_fwd_kernel(const float* __restrict__ x, const long long* __restrict__ src,
+                         const long long* __restrict__ dst, const float* __restrict__ wig,
+                         const float* __restrict__ rad, float* __restrict__ out, int C, int Kr, int nrad) {
+  constexpr int K = Dim<L>::K, WS = Dim<L>::WS;
+  __shared__ __align__(16) float sw[wpad_off(L + 1)];
   const long long e = blockIdx.x;
-  for (int i = threadIdx.x; i < WS; i += blockDim.x) sw[i] = wig[e * WS + i];
-  for (int i = threadIdx.x; i < K; i += blockDim.x) {
-    spos[i] = pos_of_full[i];
-    sslot[i] = (i < Kr) ? rad_slot[i] : 0;
-  }
+  stage_wigner<L>(sw, wig + e * WS, threadIdx.x, blockDim.x);
   __syncthreads();
-  const long long ns = src[e], nd = dst[e];
+  const long long ns_ = src[e], nd_ = dst[e];
   const int C2 = 2 * C;
   for (int ch = threadIdx.x; ch < C2; ch += blockDim.x) {
-    const long long node = (ch < C) ? ns : nd;
+    const long long node = (ch < C) ? ns_ : nd_;
     const int c = (ch < C) ? ch : ch - C;
     const float* xp = x + node * (long long)K * C + c;
     float xc[K];
@@ -55,169 +131,165 @@ __global__ void gather_rotate_fwd_kernel(const float* __restrict__ x, const long
     for (int k = 0; k < K; ++k) xc[k] = __ldg(xp + (long long)k * C);
     const float* rp = rad ? rad + e * (long long)nrad + ch : nullptr;
     float* op = out + e * (long long)Kr * C2 + ch;
+    for_each_degree<0, L, M>([&](auto ld) {
+      constexpr int l = decltype(ld)::value;
+      constexpr int mm = l < M ? l : M;
 #pragma unroll
-    for (int l = 0; l <= LMAX; ++l) {
-      const int n = 2 * l + 1;
-      const int mm = (l < mmax) ? l : mmax;
-      const float* wl = sw + eqv2_wig_off(l);
       for (int m = -mm; m <= mm; ++m) {
-        const int row = l + m;
-        float acc = 0.f;
-#pragma unroll
-        for (int j = 0; j < n; ++j) acc = fmaf(wl[row * n + j], xc[l * l + j], acc);
-        const int p = spos[l * l + row];
-        if (rp) acc *= rp[(long long)sslot[p] * C2];
+        float acc = row_dot<l>(sw, l + m, xc + l * l);
+        const int p = mpos<L, M>(l, m);
+        if (rp) acc *= __ldg(rp + (long long)rslot<L, M>(l, m < 0 ? -m : m) * C2);
         op[(long long)p * C2] = acc;
       }
-    }
+    });
   }
 }
 
 // ------------------------------------------------------------------------------------------
-template <int LMAX>
-__global__ void gather_rotate_bwd_kernel(const float* __restrict__ x, const float* __restrict__ wig,
-                                         const float* __restrict__ rad, const float* __restrict__ dA,
-                                         const int* __restrict__ rowptr_src, const int* __restrict__ perm_src,
-                                         const int* __restrict__ rowptr_dst, const int* __restrict__ perm_dst,
-                                         float* __restrict__ dx, float* __restrict__ drad,
-                                         const int* __restrict__ pos_of_full, const int* __restrict__ rad_slot,
-                                         int C, int Kr, int mmax, int nrad) {
-  constexpr int K = KDim<LMAX>::K, WS = KDim<LMAX>::WS;
-  __shared__ float sw[WS];
-  __shared__ int spos[K];
-  __shared__ int sslot[K];
+// CTA = one node; thread group h (0: edges where the node is the source, 1: where it is the destination)
+template <int L, int M>
+__global__ void __launch_bounds__(256)
+gather_rotate_bwd_kernel(const float* __restrict__ x, const float* __restrict__ wig, const float* __restrict__ rad,
+                         const float* __restrict__ dA, const int* __restrict__ rowptr_src,
+                         const int* __restrict__ perm_src, const int* __restrict__ rowptr_dst,
+                         const int* __restrict__ perm_dst, float* __restrict__ dx, float* __restrict__ drad, int C,
+                         int CP /* C rounded to 32 */, int Kr, int nrad) {
+  constexpr int K = Dim<L>::K, WS = Dim<L>::WS, WP = wpad_off(L + 1);
+  __shared__ __align__(16) float sw[2][WP];
+  EQV2_DYN_SMEM(float, sred);     // [K][CP]: partial dx of group 1
   const long long node = blockIdx.x;
-  for (int i = threadIdx.x; i < K; i += blockDim.x) {
-    spos[i] = pos_of_full[i];
-    sslot[i] = (i < Kr) ? rad_slot[i] : 0;
-  }
-  const int c = threadIdx.x;
+  const int half = threadIdx.x / CP, c = threadIdx.x % CP;
   const bool live = c < C;
   const int C2 = 2 * C;
+  const int* rowptr = half ? rowptr_dst : rowptr_src;
+  const int* perm = half ? perm_dst : perm_src;
+  const int beg = rowptr[node], len = rowptr[node + 1] - beg;
+  const int len_other = (half ? rowptr_src : rowptr_dst)[node + 1] - (half ? rowptr_src : rowptr_dst)[node];
+  const int maxlen = len > len_other ? len : len_other;
+  const int ch = half * C + c;
   float xc[K], acc[K];
 #pragma unroll
   for (int k = 0; k < K; ++k) {
-    xc[k] = live ? __ldg(x + (node * K + k) * (long long)C + c) : 0.f;
+    xc[k] = (live && drad) ? __ldg(x + (node * K + k) * (long long)C + c) : 0.f;
     acc[k] = 0.f;
   }
-  for (int half = 0; half < 2; ++half) {
-    const int* rowptr = half ? rowptr_dst : rowptr_src;
-    const int* perm = half ? perm_dst : perm_src;
-    const int beg = rowptr[node], end = rowptr[node + 1];
-    const int ch = half * C + c;
-    for (int idx = beg; idx < end; ++idx) {
-      const long long e = perm[idx];
-      __syncthreads();
-      for (int i = threadIdx.x; i < WS; i += blockDim.x) sw[i] = wig[e * WS + i];
-      __syncthreads();
-      if (!live) continue;
-      const float* gp = dA + e * (long long)Kr * C2 + ch;
-      const float* rp = rad ? rad + e * (long long)nrad + ch : nullptr;
-      float* drp = drad ? drad + e * (long long)nrad + ch : nullptr;
-#pragma unroll
-      for (int l = 0; l <= LMAX; ++l) {
-        const int n = 2 * l + 1;
-        const int mm = (l < mmax) ? l : mmax;
-        const float* wl = sw + eqv2_wig_off(l);
-        for (int m = 0; m <= mm; ++m) {
-          // rows (l, +m) and (l, -m) share one radial weight (so2_ops.py:170-175)
-          const int rowp = l + m, rown = l - m;
-          const int pp = spos[l * l + rowp], pn = spos[l * l + rown];
-          const float r = rp ? rp[(long long)sslot[pp] * C2] : 1.0f;
-          const float gpv = gp[(long long)pp * C2];
-          const float gnv = (m > 0) ? gp[(long long)pn * C2] : 0.f;
-          if (drp) {
-            float xrp = 0.f, xrn = 0.f;
-#pragma unroll
-            for (int j = 0; j < n; ++j) {
-              xrp = fmaf(wl[rowp * n + j], xc[l * l + j], xrp);
-              xrn = fmaf(wl[rown * n + j], xc[l * l + j], xrn);
-            }
-            drp[(long long)sslot[pp] * C2] = (m > 0) ? (gpv * xrp + gnv * xrn) : gpv * xrp;
-          }
-          const float gmp = gpv * r, gmn = gnv * r;
-#pragma unroll
-          for (int j = 0; j < n; ++j) {
-            float t = fmaf(wl[rowp * n + j], gmp, acc[l * l + j]);
-            acc[l * l + j] = (m > 0) ? fmaf(wl[rown * n + j], gmn, t) : t;
-          }
-        }
-      }
+  for (int it = 0; it < maxlen; ++it) {
+    __syncthreads();
+    const bool has = it < len;
+    long long e = 0;
+    if (has) {
+      e = perm[beg + it];
+      stage_wigner<L>(sw[half], wig + e * WS, c, CP);
     }
-  }
-  if (live) {
+    __syncthreads();
+    if (!has || !live) continue;
+    const float* gp = dA + e * (long long)Kr * C2 + ch;
+    const float* rp = rad ? rad + e * (long long)nrad + ch : nullptr;
+    float* drp = drad ? drad + e * (long long)nrad + ch : nullptr;
+    const float* w = sw[half];
+    for_each_degree<0, L, M>([&](auto ld) {
+      constexpr int l = decltype(ld)::value;
+      constexpr int mm = l < M ? l : M;
 #pragma unroll
-    for (int k = 0; k < K; ++k) dx[(node * K + k) * (long long)C + c] = acc[k];
+      for (int m = 0; m <= mm; ++m) {
+        // rows (l, +m) and (l, -m) share one radial weight (so2_ops.py:170-175)
+        const int pp = mpos<L, M>(l, m), pn = mpos<L, M>(l, -m);
+        const int slot = rslot<L, M>(l, m);
+        const float r = rp ? __ldg(rp + (long long)slot * C2) : 1.0f;
+        const float gpv = __ldg(gp + (long long)pp * C2);
+        const float gnv = (m > 0) ? __ldg(gp + (long long)pn * C2) : 0.f;
+        if (drp) {
+          float d = gpv * row_dot<l>(w, l + m, xc + l * l);
+          if (m > 0) d = fmaf(gnv, row_dot<l>(w, l - m, xc + l * l), d);
+          drp[(long long)slot * C2] = d;
+        }
+        row_axpy<l>(w, l + m, gpv * r, acc + l * l);
+        if (m > 0) row_axpy<l>(w, l - m, gnv * r, acc + l * l);
+      }
+    });
+  }
+  __syncthreads();
+  if (half == 1 && live) {
+#pragma unroll
+    for (int k = 0; k < K; ++k) sred[k * CP + c] = acc[k];
+  }
+  __syncthreads();
+  if (half == 0 && live) {
+#pragma unroll
+    for (int k = 0; k < K; ++k) dx[(node * K + k) * (long long)C + c] = acc[k] + sred[k * CP + c];
   }
 }
 
 // ------------------------------------------------------------------------------------------
-template <int LMAX>
-__global__ void rotinv_reduce_fwd_kernel(const float* __restrict__ val, const float* __restrict__ alpha,
-                                         const float* __restrict__ wig, const int* __restrict__ rowptr_dst,
-                                         const int* __restrict__ perm_dst, float* __restrict__ out,
-                                         const int* __restrict__ pos_of_full, int Cv, int rows_used,
-                                         long long val_estride, int heads, int mmax, float scale) {
-  constexpr int K = KDim<LMAX>::K, WS = KDim<LMAX>::WS;
-  __shared__ float sw[WS];
-  __shared__ int spos[K];
+// CTA = one destination node; two thread groups take alternate edges of its segment
+template <int L, int M>
+__global__ void __launch_bounds__(256)
+rotinv_reduce_fwd_kernel(const float* __restrict__ val, const float* __restrict__ alpha, const float* __restrict__ wig,
+                         const int* __restrict__ rowptr_dst, const int* __restrict__ perm_dst, float* __restrict__ out,
+                         int Cv, int CP, int rows_used, long long val_estride, int heads, float scale) {
+  constexpr int K = Dim<L>::K, WS = Dim<L>::WS, WP = wpad_off(L + 1);
+  __shared__ __align__(16) float sw[2][WP];
+  EQV2_DYN_SMEM(float, sred);     // [K][CP]
   const long long node = blockIdx.x;
-  for (int i = threadIdx.x; i < K; i += blockDim.x) spos[i] = pos_of_full[i];
-  const int c = threadIdx.x;
+  const int grp = threadIdx.x / CP, c = threadIdx.x % CP;
   const bool live = c < Cv;
   const int vch = heads > 0 ? Cv / heads : Cv;
   float acc[K];
 #pragma unroll
   for (int k = 0; k < K; ++k) acc[k] = 0.f;
   const int beg = rowptr_dst[node], end = rowptr_dst[node + 1];
-  for (int idx = beg; idx < end; ++idx) {
-    const long long e = perm_dst[idx];
+  for (int idx0 = beg; idx0 < end; idx0 += 2) {
+    const int idx = idx0 + grp;
+    const bool has = idx < end;
+    long long e = 0;
     __syncthreads();
-    for (int i = threadIdx.x; i < WS; i += blockDim.x) sw[i] = wig[e * WS + i];
+    if (has) {
+      e = perm_dst[idx];
+      stage_wigner<L>(sw[grp], wig + e * WS, c, CP);
+    }
     __syncthreads();
-    if (!live) continue;
-    const float a = alpha ? alpha[e * heads + c / vch] : 1.0f;
+    if (!has || !live) continue;
+    const float a = alpha ? __ldg(alpha + e * heads + c / vch) : 1.0f;
     const float* vp = val + e * val_estride + c;
+    const float* w = sw[grp];
+    for_each_degree<0, L, M>([&](auto ld) {
+      constexpr int l = decltype(ld)::value;
+      constexpr int mm = l < M ? l : M;
 #pragma unroll
-    for (int l = 0; l <= LMAX; ++l) {
-      const int n = 2 * l + 1;
-      const int mm = (l < mmax) ? l : mmax;
-      const float* wl = sw + eqv2_wig_off(l);
       for (int m = -mm; m <= mm; ++m) {
-        const int row = l + m;
-        const int p = spos[l * l + row];
-        if (p >= rows_used) continue;
-        const float v = vp[(long long)p * Cv] * a;
-#pragma unroll
-        for (int j = 0; j < n; ++j) acc[l * l + j] = fmaf(wl[row * n + j], v, acc[l * l + j]);
+        const int p = mpos<L, M>(l, m);
+        if (p < rows_used) row_axpy<l>(w, l + m, __ldg(vp + (long long)p * Cv) * a, acc + l * l);
       }
-    }
+    });
   }
-  if (live) {
+  __syncthreads();
+  if (grp == 1 && live) {
 #pragma unroll
-    for (int l = 0; l <= LMAX; ++l) {
-      const float f = rescale_l(l, mmax) * scale;
+    for (int k = 0; k < K; ++k) sred[k * CP + c] = acc[k];
+  }
+  __syncthreads();
+  if (grp == 0 && live) {
+    for_each_degree<0, L, M>([&](auto ld) {
+      constexpr int l = decltype(ld)::value;
+      const float f = (l > M ? sqrtf(rescale_l(l, M)) : 1.0f) * scale;
 #pragma unroll
-      for (int j = 0; j < 2 * l + 1; ++j) out[(node * K + l * l + j) * (long long)Cv + c] = acc[l * l + j] * f;
-    }
+      for (int j = 0; j < 2 * l + 1; ++j)
+        out[(node * K + l * l + j) * (long long)Cv + c] = (acc[l * l + j] + sred[(l * l + j) * CP + c]) * f;
+    });
   }
 }
 
 // ------------------------------------------------------------------------------------------
-template <int LMAX>
-__global__ void rotinv_reduce_bwd_kernel(const float* __restrict__ dout, const float* __restrict__ val,
-                                         const float* __restrict__ alpha, const float* __restrict__ wig,
-                                         const long long* __restrict__ dst, float* __restrict__ dval,
-                                         float* __restrict__ dalpha, const int* __restrict__ pos_of_full,
-                                         int Cv, int rows_used, long long val_estride, int heads, int mmax,
-                                         float scale) {
-  constexpr int K = KDim<LMAX>::K, WS = KDim<LMAX>::WS;
-  __shared__ float sw[WS];
-  __shared__ int spos[K];
+template <int L, int M>
+__global__ void __launch_bounds__(256)
+rotinv_reduce_bwd_kernel(const float* __restrict__ dout, const float* __restrict__ val, const float* __restrict__ alpha,
+                         const float* __restrict__ wig, const long long* __restrict__ dst, float* __restrict__ dval,
+                         float* __restrict__ dalpha, int Cv, int rows_used, long long val_estride, int heads, float scale) {
+  constexpr int K = Dim<L>::K, WS = Dim<L>::WS;
+  __shared__ __align__(16) float sw[wpad_off(L + 1)];
   EQV2_DYN_SMEM(float, spart);   // [blockDim.x] partial d(alpha)
   const long long e = blockIdx.x;
-  for (int i = threadIdx.x; i < WS; i += blockDim.x) sw[i] = wig[e * WS + i];
-  for (int i = threadIdx.x; i < K; i += blockDim.x) spos[i] = pos_of_full[i];
+  stage_wigner<L>(sw, wig + e * WS, threadIdx.x, blockDim.x);
   __syncthreads();
   const int c = threadIdx.x;
   const bool live = c < Cv;
@@ -226,31 +298,28 @@ __global__ void rotinv_reduce_bwd_kernel(const float* __restrict__ dout, const f
   float da = 0.f;
   if (live) {
     float g[K];
-#pragma unroll
-    for (int l = 0; l <= LMAX; ++l) {
-      const float f = rescale_l(l, mmax) * scale;
+    for_each_degree<0, L, M>([&](auto ld) {
+      constexpr int l = decltype(ld)::value;
+      const float f = (l > M ? sqrtf(rescale_l(l, M)) : 1.0f) * scale;
 #pragma unroll
       for (int j = 0; j < 2 * l + 1; ++j) g[l * l + j] = __ldg(dout + (node * K + l * l + j) * (long long)Cv + c) * f;
-    }
-    const float a = alpha ? alpha[e * heads + c / vch] : 1.0f;
+    });
+    const float a = alpha ? __ldg(alpha + e * heads + c / vch) : 1.0f;
     const float* vp = val + e * val_estride + c;
     float* dvp = dval + e * val_estride + c;
+    for_each_degree<0, L, M>([&](auto ld) {
+      constexpr int l = decltype(ld)::value;
+      constexpr int mm = l < M ? l : M;
 #pragma unroll
-    for (int l = 0; l <= LMAX; ++l) {
-      const int n = 2 * l + 1;
-      const int mm = (l < mmax) ? l : mmax;
-      const float* wl = sw + eqv2_wig_off(l);
       for (int m = -mm; m <= mm; ++m) {
-        const int row = l + m;
-        const int p = spos[l * l + row];
-        if (p >= rows_used) continue;
-        float t = 0.f;
-#pragma unroll
-        for (int j = 0; j < n; ++j) t = fmaf(wl[row * n + j], g[l * l + j], t);
-        if (alpha) da = fmaf(t, vp[(long long)p * Cv], da);
-        dvp[(long long)p * Cv] = t * a;
+        const int p = mpos<L, M>(l, m);
+        if (p < rows_used) {
+          const float t = row_dot<l>(sw, l + m, g + l * l);
+          if (alpha) da = fmaf(t, __ldg(vp + (long long)p * Cv), da);
+          dvp[(long long)p * Cv] = t * a;
+        }
       }
-    }
+    });
   }
   if (dalpha) {
     spart[threadIdx.x] = da;
@@ -267,28 +336,30 @@ inline int round32(int v) { return (v + 31) / 32 * 32; }
 
 }  // namespace
 
-#define EQV2_DISPATCH_LMAX(lmax, CALL)                                          \
-  switch (lmax) {                                                               \
-    case 1: { CALL(1); } break;                                                 \
-    case 2: { CALL(2); } break;                                                 \
-    case 3: { CALL(3); } break;                                                 \
-    case 4: { CALL(4); } break;                                                 \
-    case 5: { CALL(5); } break;                                                 \
-    case 6: { CALL(6); } break;                                                 \
-    default: eqv2_set_error("lmax=%d unsupported (1..6)", lmax); return 1;      \
-  }
+// (lmax, mmax) pairs with kernels: every reference config and the test fixtures
+#define EQV2_ROT_CONFIGS(X) X(1, 1) X(2, 1) X(2, 2) X(3, 2) X(3, 3) X(4, 2) X(4, 4) X(5, 2) X(6, 2) X(6, 4) X(6, 6)
+
+#define EQV2_ROT_DISPATCH(NAME, BODY)                                                    \
+  EQV2_ROT_CONFIGS(BODY)                                                                 \
+  eqv2_set_error(NAME ": (lmax, mmax) = (%d, %d) has no kernel instance", lmax, mmax);   \
+  return 1;
 
 extern "C" int eqv2_gather_rotate_fwd(const float* x, const long long* src, const long long* dst, const float* wig,
                                       const float* rad, float* out, const int* pos_of_full, const int* rad_slot,
                                       long long E, int C, int lmax, int mmax, int Kr, int nrad, void* stream) {
+  (void)pos_of_full; (void)rad_slot;   // index maps are compile-time now; kept in the ABI for the host tables
   if (E == 0) return 0;
   EQV2_REQUIRE(C > 0 && Kr > 0, "gather_rotate_fwd: bad sizes");
   const int threads = min(256, round32(2 * C));
-#define CALL(L) EQV2_LAUNCH(gather_rotate_fwd_kernel<L>, dim3((unsigned)E), dim3(threads), 0, stream, x, src, dst, wig, rad, out, pos_of_full, rad_slot, C, Kr, mmax, nrad)
-  EQV2_DISPATCH_LMAX(lmax, CALL)
-#undef CALL
-  EQV2_CHECK_LAUNCH("eqv2_gather_rotate_fwd");
-  return 0;
+#define X(L_, M_)                                                                                              \
+  if (lmax == L_ && mmax == M_) {                                                                              \
+    auto kfn = gather_rotate_fwd_kernel<L_, M_>;                                                                                    \
+    EQV2_LAUNCH(kfn, dim3((unsigned)E), dim3(threads), 0, stream, x, src, dst, wig, rad, out, C, Kr, nrad); \
+    EQV2_CHECK_LAUNCH("eqv2_gather_rotate_fwd");                                                               \
+    return 0;                                                                                                  \
+  }
+  EQV2_ROT_DISPATCH("gather_rotate_fwd", X)
+#undef X
 }
 
 extern "C" int eqv2_gather_rotate_bwd(const float* x, const float* wig, const float* rad, const float* dA,
@@ -296,42 +367,59 @@ extern "C" int eqv2_gather_rotate_bwd(const float* x, const float* wig, const fl
                                       const int* perm_dst, float* dx, float* drad, const int* pos_of_full,
                                       const int* rad_slot, long long N, int C, int lmax, int mmax, int Kr, int nrad,
                                       void* stream) {
+  (void)pos_of_full; (void)rad_slot;
   if (N == 0) return 0;
-  EQV2_REQUIRE(C > 0 && C <= 1024, "gather_rotate_bwd: C=%d out of range", C);
-  const int threads = round32(C);
-#define CALL(L) EQV2_LAUNCH(gather_rotate_bwd_kernel<L>, dim3((unsigned)N), dim3(threads), 0, stream, x, wig, rad, dA, rowptr_src, perm_src, rowptr_dst, perm_dst, dx, drad, pos_of_full, rad_slot, C, Kr, mmax, nrad)
-  EQV2_DISPATCH_LMAX(lmax, CALL)
-#undef CALL
-  EQV2_CHECK_LAUNCH("eqv2_gather_rotate_bwd");
-  return 0;
+  EQV2_REQUIRE(C > 0 && C <= 128, "gather_rotate_bwd: C=%d out of range (1..128)", C);
+  const int CP = round32(C);
+  const size_t smem = (size_t)(lmax + 1) * (lmax + 1) * CP * sizeof(float);
+#define X(L_, M_)                                                                                              \
+  if (lmax == L_ && mmax == M_) {                                                                              \
+    auto kfn = gather_rotate_bwd_kernel<L_, M_>;                                                                                    \
+    EQV2_LAUNCH(kfn, dim3((unsigned)N), dim3(2 * CP), smem, stream, x, wig, rad, dA, rowptr_src, perm_src, rowptr_dst, perm_dst, dx, drad, C, CP, Kr, nrad); \
+    EQV2_CHECK_LAUNCH("eqv2_gather_rotate_bwd");                                                               \
+    return 0;                                                                                                  \
+  }
+  EQV2_ROT_DISPATCH("gather_rotate_bwd", X)
+#undef X
 }
 
 extern "C" int eqv2_rotinv_reduce_fwd(const float* val, const float* alpha, const float* wig, const int* rowptr_dst,
                                       const int* perm_dst, float* out, const int* pos_of_full, long long N, int Cv,
                                       int rows_used, long long val_estride, int heads, int lmax, int mmax, float scale,
                                       void* stream) {
+  (void)pos_of_full;
   if (N == 0) return 0;
-  EQV2_REQUIRE(Cv > 0 && Cv <= 1024, "rotinv_reduce_fwd: Cv=%d out of range", Cv);
+  EQV2_REQUIRE(Cv > 0 && Cv <= 128, "rotinv_reduce_fwd: Cv=%d out of range (1..128)", Cv);
   EQV2_REQUIRE(alpha == nullptr || (heads > 0 && Cv % heads == 0), "rotinv_reduce_fwd: heads must divide Cv");
-  const int threads = round32(Cv);
-#define CALL(L) EQV2_LAUNCH(rotinv_reduce_fwd_kernel<L>, dim3((unsigned)N), dim3(threads), 0, stream, val, alpha, wig, rowptr_dst, perm_dst, out, pos_of_full, Cv, rows_used, val_estride, heads, mmax, scale)
-  EQV2_DISPATCH_LMAX(lmax, CALL)
-#undef CALL
-  EQV2_CHECK_LAUNCH("eqv2_rotinv_reduce_fwd");
-  return 0;
+  const int CP = round32(Cv);
+  const size_t smem = (size_t)(lmax + 1) * (lmax + 1) * CP * sizeof(float);
+#define X(L_, M_)                                                                                              \
+  if (lmax == L_ && mmax == M_) {                                                                              \
+    auto kfn = rotinv_reduce_fwd_kernel<L_, M_>;                                                                                    \
+    EQV2_LAUNCH(kfn, dim3((unsigned)N), dim3(2 * CP), smem, stream, val, alpha, wig, rowptr_dst, perm_dst, out, Cv, CP, rows_used, val_estride, heads, scale); \
+    EQV2_CHECK_LAUNCH("eqv2_rotinv_reduce_fwd");                                                               \
+    return 0;                                                                                                  \
+  }
+  EQV2_ROT_DISPATCH("rotinv_reduce_fwd", X)
+#undef X
 }
 
 extern "C" int eqv2_rotinv_reduce_bwd(const float* dout, const float* val, const float* alpha, const float* wig,
                                       const long long* dst, float* dval, float* dalpha, const int* pos_of_full,
                                       long long E, int Cv, int rows_used, long long val_estride, int heads, int lmax,
                                       int mmax, float scale, void* stream) {
+  (void)pos_of_full;
   if (E == 0) return 0;
-  EQV2_REQUIRE(Cv > 0 && Cv <= 1024, "rotinv_reduce_bwd: Cv=%d out of range", Cv);
+  EQV2_REQUIRE(Cv > 0 && Cv <= 256, "rotinv_reduce_bwd: Cv=%d out of range", Cv);
   EQV2_REQUIRE(alpha == nullptr || (heads > 0 && Cv % heads == 0), "rotinv_reduce_bwd: heads must divide Cv");
   const int threads = round32(max(Cv, heads));
-#define CALL(L) EQV2_LAUNCH(rotinv_reduce_bwd_kernel<L>, dim3((unsigned)E), dim3(threads), threads * sizeof(float), stream, dout, val, alpha, wig, dst, dval, dalpha, pos_of_full, Cv, rows_used, val_estride, heads, mmax, scale)
-  EQV2_DISPATCH_LMAX(lmax, CALL)
-#undef CALL
-  EQV2_CHECK_LAUNCH("eqv2_rotinv_reduce_bwd");
-  return 0;
+#define X(L_, M_)                                                                                              \
+  if (lmax == L_ && mmax == M_) {                                                                              \
+    auto kfn = rotinv_reduce_bwd_kernel<L_, M_>;                                                                                    \
+    EQV2_LAUNCH(kfn, dim3((unsigned)E), dim3(threads), threads * sizeof(float), stream, dout, val, alpha, wig, dst, dval, dalpha, Cv, rows_used, val_estride, heads, scale); \
+    EQV2_CHECK_LAUNCH("eqv2_rotinv_reduce_bwd");                                                               \
+    return 0;                                                                                                  \
+  }
+  EQV2_ROT_DISPATCH("rotinv_reduce_bwd", X)
+#undef X
 }

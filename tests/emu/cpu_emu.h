@@ -26,6 +26,7 @@
 #define __shared__ static
 #define __launch_bounds__(...)
 #define __constant__ static
+#define __align__(n) __attribute__((aligned(n)))
 
 struct uint3 { unsigned x, y, z; };
 struct dim3 {
