@@ -5,33 +5,38 @@
 //   C[M,N] (+)= opA[M,K] * opB[K,N] (+ bias[N])         fp32 in, fp32 out
 //
 // Precision modes
-//   mode 0 "3xTF32": every operand value v is split in registers into hi = rna_tf32(v) and
-//           lo = rna_tf32(v - hi); the tensor core computes hi*hi, lo*hi and hi*lo (the dropped lo*lo term
-//           and the rounding of lo are O(2^-22) relative).
+//   mode 0 "3xTF32": every operand value v is split into hi = v rounded to tf32 and lo = v - hi (exact in fp32; the
+//           tensor core reads lo's upper 19 bits); the tensor core computes hi*hi, lo*hi and hi*lo (the dropped
+//           lo*lo term and the truncation of lo are O(2^-21) relative).
 //           MEASURED on B200 (scripts/gemm_accuracy.py): every tcgen05.mma accumulation into TMEM truncates
 //           (round-toward-zero at 24 bits, ~5e-8 relative per instruction, systematic), so a plain K-long
 //           chain is 1e-5 off at K ~ 2000.  The kernel therefore keeps the hi*hi chain short: it accumulates
-//           CHUNK k-blocks (8 instructions) into one of two ping-pong TMEM accumulators and dedicated
-//           promotion warps add each finished chunk into fp32 registers (round-to-nearest) while the tensor
-//           core works on the other buffer.  The small lo terms use a third TMEM accumulator for the whole K
-//           (their truncation is 2^-11 times smaller).  Result: fp32-class accuracy, as the 1e-5 parity
-//           bound of the fp32 mode needs.
-//   mode 1 "1xTF32": hi*hi only, one TMEM chain, no promotion (separately stated tolerance).
+//           CHUNK_KB k-blocks (16 instructions) into one of two ping-pong TMEM accumulators and the worker warps
+//           add each finished chunk into fp32 registers (round-to-nearest) while the tensor core works on the
+//           other buffer.  The small lo terms use a third TMEM accumulator for the whole K (their truncation is
+//           2^-11 times smaller).  Result: 4e-7 max-normalised error at K = 2048..8192 -- fp32-class accuracy, as
+//           the 1e-5 parity bound of the fp32 mode needs (the FFMA engine and cuBLAS fp32 give 5e-7..2.7e-6).
+//   mode 1 "1xTF32": raw fp32 tiles straight to the tensor core, one TMEM chain (separately stated tolerance).
 //
-// CTA = one 128 x 128 output tile.  Warp roles (416 threads, 13 warps -> 128 registers/thread):
+// CTA = one 128 x 128 output tile, 4-stage mbarrier ring.  Warp roles (416 threads, 13 warps -> 128 regs/thread):
 //   warps 0-3   producers: cp.async (LDGSTS, zero-filling out-of-range chunks) of the raw fp32 A and B tiles
-//               (128 rows x 32 k each) straight into their final swizzled position, LOOKAHEAD stages ahead;
-//               when a stage has landed (mbarrier completion of the cp.asyncs) they split it in place into
-//               hi (rounded) and lo tiles and hand it to the tensor core
-//   warps 4-11  promotion / epilogue: tcgen05.ld of finished chunks -> register accumulators -> bias /
-//               accumulate -> global
-//   warp  12    TMEM allocation + single-thread tcgen05.mma issue + tcgen05.commit
-// Operands are staged by threads (not TMA) on purpose: every 16-byte chunk is addressed individually, so
-// K-contiguous ([rows,K]) sources land in the K-major SWIZZLE_128B layout and row-contiguous ([K,rows]:
-// dgrad weights, both wgrad operands) sources land in the MN-major SWIZZLE_128B_BASE32B layout that the
-// UMMA descriptors name -- no transposed copies in HBM -- with ragged M/N/K tails zero-filled.
-// 3-stage mbarrier ring: raw_full[s] (cp.async -> split), full[s] (split -> MMA), empty[s]
-// (tcgen05.commit -> producers); acc_full[b] (tcgen05.commit -> promoters), acc_empty[b] (promoters -> MMA).
+//               (128 rows x 32 k each) straight into their final swizzled position, up to 4 k-blocks ahead.
+//               Every 16-byte chunk is addressed individually, so K-contiguous ([rows,K]) sources land in the
+//               K-major SWIZZLE_128B layout and row-contiguous ([K,rows]: dgrad weights, both wgrad operands)
+//               sources in the MN-major SWIZZLE_128B_BASE32B layout (the only legal one for 32-bit MN-major
+//               operands) -- no transposed copies in HBM -- with ragged M/N/K tails zero-filled; two-level row
+//               strides address the degree slabs of [N,K,C] node tensors.
+//   warps 4-11  workers, two groups of four on ALTERNATE k-blocks:
+//               B: split the landed tile in shared memory (hi in place, lo tile);
+//               A: shared memory -> registers -> hi/lo -> TENSOR MEMORY (tcgen05.st): the A operand of all three
+//                  MMAs is read from TMEM, so no A_hi/A_lo tiles are written to or re-read from shared memory
+//                  (shared-memory bandwidth was the first bound: 224 KB of traffic per k-block in r01 v3);
+//               promotion of finished hi*hi chunks (tcgen05.ld -> register accumulators) and the epilogue
+//               (bias / accumulate / split-K atomics -> global).
+//   warp  12    TMEM allocation (512 columns: D_hi[2] | D_lo | A ring 2 x (hi 32 | lo 32)) + single-thread
+//               tcgen05.mma issue (A from TMEM, B from smem descriptors) + tcgen05.commit.
+// Barriers: raw_full[s] (cp.async completion -> workers), full[s] (workers -> MMA), empty[s] (commit ->
+// producers), a_empty[g] (commit -> workers: TMEM A slot free), acc_full[b] / acc_empty[b] (promotion).
 #include "common.cuh"
 
 #ifndef EQV2_CPU_EMU
@@ -39,17 +44,18 @@
 namespace {
 
 constexpr int BM = 128, BN = 128, BK = 32;         // BK fp32 = 128 bytes = one swizzle row
-constexpr int STAGES = 3;
+constexpr int STAGES = 4;
 constexpr int TILE_BYTES = BM * BK * 4;            // 16 KB per operand tile
-constexpr int STAGE_BYTES = 4 * TILE_BYTES;        // A_hi, A_lo, B_hi, B_lo
+constexpr int STAGE_BYTES = 3 * TILE_BYTES;        // A raw | B hi (raw lands here) | B lo
+constexpr int A_SLOTS = 2;                         // TMEM ring of split A tiles: per slot hi (32 columns) + lo (32)
 // 13 warps = (4,3,3,3) per scheduler partition -> 128 registers per thread without spills
 constexpr int NUM_PRODUCER_WARPS = 4;              // warps 0-3
 constexpr int NUM_EPI_WARPS = 8;                   // warps 4-11 (lane quarter = warp & 3)
 constexpr int MMA_WARP = NUM_PRODUCER_WARPS + NUM_EPI_WARPS;
 constexpr int NUM_THREADS = (NUM_PRODUCER_WARPS + NUM_EPI_WARPS + 1) * 32;
-constexpr int TMEM_COLS = 512;                     // D_hi[0], D_hi[1], D_lo (128 columns each); power of two
-constexpr int PROMOTE_LAG = 2;                     // blocks between the split of a chunk's last stage and its promotion
-constexpr int CHUNK_KB = 2;                        // k-blocks per promoted hi*hi chain (8 tcgen05.mma)
+constexpr int TMEM_COLS = 512;                     // D_hi[0] | D_hi[1] | D_lo (128 columns each) | A ring (2 x 64)
+constexpr int PROMOTE_LAG = 3;                     // blocks between the split of a chunk's last stage and its promotion
+constexpr int CHUNK_KB = 4;                        // k-blocks per promoted hi*hi chain (16 tcgen05.mma)
 constexpr size_t SMEM_BYTES = (size_t)STAGES * STAGE_BYTES + 1024 /*align*/ + 256 /*barriers*/;
 
 struct TcGroup {
@@ -116,6 +122,26 @@ __device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t adesc, uint6
       "l"(adesc), "l"(bdesc), "r"(idesc), "r"(acc)
       : "memory");
 }
+// A operand from tensor memory (128 lanes = rows, 8 columns = the K=8 slice), B from shared memory
+__device__ __forceinline__ void umma_tf32_ts(uint32_t tmem_d, uint32_t tmem_a, uint64_t bdesc, uint32_t idesc, uint32_t acc) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::tf32 [%0], [%1], %2, %3, {%5, %5, %5, %5}, p;\n\t}\n" ::"r"(tmem_d),
+      "r"(tmem_a), "l"(bdesc), "r"(idesc), "r"(acc), "r"(0u)
+      : "memory");
+}
+// 32 lanes x 16 columns: lane i of the warp writes its 16 registers to columns [col, col+16) of TMEM lane (base + i)
+__device__ __forceinline__ void tmem_st16(uint32_t taddr, const uint32_t* r) {
+  asm volatile(
+      "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], "
+      "{%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16};" ::"r"(taddr),
+      "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]), "r"(r[8]), "r"(r[9]),
+      "r"(r[10]), "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15])
+      : "memory");
+}
+__device__ __forceinline__ void tmem_wait_st() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
+
 __device__ __forceinline__ void umma_commit(uint32_t bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
 }
@@ -230,16 +256,16 @@ __device__ __forceinline__ void issue_tile(const ChunkPlan& P, const float* __re
 // hi/lo split of a landed tile, elementwise and therefore layout-agnostic: chunk i of `hi` <-> chunk i of `lo`.
 // hi = v rounded to tf32 (ties away: add half an ulp to the magnitude bits, clear the low 13 bits),
 // lo = v - hi exactly (fp32); the tensor core reads lo's upper 19 bits, i.e. drops O(2^-21 |v|).
-// 256 worker threads, 4 chunks each.
+// 128 threads of one worker group, 4 chunks each over an 8 KB half tile (called twice per tile).
 __device__ __forceinline__ float tf32_hi(float v) { return __uint_as_float((__float_as_uint(v) + 0x1000u) & 0xFFFFE000u); }
 
 __device__ __forceinline__ void split_tile(unsigned char* hi, unsigned char* lo, int wt) {
   float4 v[4];
 #pragma unroll
-  for (int it = 0; it < 4; ++it) v[it] = *reinterpret_cast<const float4*>(hi + ((uint32_t)(it * 256 + wt) << 4));
+  for (int it = 0; it < 4; ++it) v[it] = *reinterpret_cast<const float4*>(hi + ((uint32_t)(it * 128 + wt) << 4));
 #pragma unroll
   for (int it = 0; it < 4; ++it) {
-    const uint32_t off = (uint32_t)(it * 256 + wt) << 4;
+    const uint32_t off = (uint32_t)(it * 128 + wt) << 4;
     float4 h, l;
     h.x = tf32_hi(v[it].x); h.y = tf32_hi(v[it].y); h.z = tf32_hi(v[it].z); h.w = tf32_hi(v[it].w);
     l.x = v[it].x - h.x; l.y = v[it].y - h.y; l.z = v[it].z - h.z; l.w = v[it].w - h.w;
@@ -248,19 +274,56 @@ __device__ __forceinline__ void split_tile(unsigned char* hi, unsigned char* lo,
   }
 }
 
+// A tile (raw fp32 in shared memory, K-major SWIZZLE_128B or MN-major SWIZZLE_128B_BASE32B) -> hi / lo halves in
+// TENSOR MEMORY: the worker thread of TMEM lane r reads 16 of row r's 32 k-values, splits them and stores
+// hi to columns [k, k+16) and lo to columns [32 + k, ...) of the slot.  The tensor core then reads A from TMEM:
+// no A_hi / A_lo tiles are written to or re-read from shared memory (the kernel is shared-memory-bandwidth bound).
+__device__ __forceinline__ void split_a_to_tmem(const unsigned char* a_raw, int mn, int q, int half, int lane,
+                                                uint32_t tmem_slot_addr) {
+  const int r = q * 32 + lane;
+  float v[16];
+  if (!mn) {
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int c = 4 * half + j;
+      const float4 f = *reinterpret_cast<const float4*>(a_raw + r * 128 + ((c ^ (r & 7)) << 4));
+      v[4 * j] = f.x; v[4 * j + 1] = f.y; v[4 * j + 2] = f.z; v[4 * j + 3] = f.w;
+    }
+  } else {
+    const int c16 = lane >> 2;
+#pragma unroll
+    for (int t = 0; t < 16; ++t) {
+      const int kk = 16 * half + t, k4 = kk & 3, kg = kk >> 2;
+      const int cs = ((((c16 >> 1) ^ k4) << 1) | (c16 & 1));
+      v[t] = *reinterpret_cast<const float*>(a_raw + kg * 2048 + q * 512 + k4 * 128 + cs * 16 + (lane & 3) * 4);
+    }
+  }
+  uint32_t h[16], l[16];
+#pragma unroll
+  for (int t = 0; t < 16; ++t) {
+    const float hv = tf32_hi(v[t]);
+    h[t] = __float_as_uint(hv);
+    l[t] = __float_as_uint(v[t] - hv);
+  }
+  const uint32_t ta = tmem_slot_addr + ((uint32_t)(q * 32) << 16) + (uint32_t)(16 * half);
+  tmem_st16(ta, h);
+  tmem_st16(ta + 32u, l);     // the caller issues tcgen05.wait::st once for the whole tile
+}
+
 __global__ void __launch_bounds__(NUM_THREADS, 1) gemm_tc_kernel(const __grid_constant__ TcParams P) {
   extern __shared__ unsigned char smem_raw[];
   const uint32_t raw_addr = smem_u32(smem_raw);
   const uint32_t pad = (1024u - (raw_addr & 1023u)) & 1023u;
   unsigned char* tiles = smem_raw + pad;                                    // STAGES * STAGE_BYTES, 1024-aligned
   uint64_t* bars = reinterpret_cast<uint64_t*>(tiles + (size_t)STAGES * STAGE_BYTES);
-  // bars: [0,S) full | [S,2S) empty | [2S,3S) raw_full | 3S+b acc_full[b] | 3S+2+b acc_empty[b] ; TMEM base word
+  // bars: [0,S) full | [S,2S) empty | [2S,3S) raw_full | 3S+b acc_full | 3S+2+b acc_empty | 3S+4+a a_empty ; TMEM base
   uint64_t* full = bars;
   uint64_t* empty = bars + STAGES;
   uint64_t* raw_full = bars + 2 * STAGES;
   uint64_t* acc_full = bars + 3 * STAGES;
   uint64_t* acc_empty = bars + 3 * STAGES + 2;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 3 * STAGES + 4);
+  uint64_t* a_empty = bars + 3 * STAGES + 4;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 3 * STAGES + 4 + A_SLOTS);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
@@ -288,13 +351,14 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) gemm_tc_kernel(const __grid_co
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < STAGES; ++s) {
-      mbar_init(smem_u32(&full[s]), NUM_EPI_WARPS);                 // one arrive per worker warp after the split
+      mbar_init(smem_u32(&full[s]), NUM_EPI_WARPS / 2);             // one arrive per warp of the owning worker group
       mbar_init(smem_u32(&empty[s]), 1);
       mbar_init(smem_u32(&raw_full[s]), NUM_PRODUCER_WARPS * 32);   // one cp.async completion arrive per thread
     }
     for (int b = 0; b < 2; ++b) {
       mbar_init(smem_u32(&acc_full[b]), 1);
       mbar_init(smem_u32(&acc_empty[b]), NUM_EPI_WARPS);
+      mbar_init(smem_u32(&a_empty[b]), 1);
     }
     fence_barrier_init();
   }
@@ -304,6 +368,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) gemm_tc_kernel(const __grid_co
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
   const uint32_t tmem_lo = tmem_base + 2 * BN;
+  const uint32_t tmem_a = tmem_base + 3 * BN;            // + slot * 64: hi [0,32), lo [32,64)
 
   if (warp < NUM_PRODUCER_WARPS) {
     // ================= producers: cp.async only, up to STAGES blocks ahead of the tensor core =================
@@ -317,13 +382,14 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) gemm_tc_kernel(const __grid_co
       const uint32_t st = smem_u32(tiles + (size_t)s * STAGE_BYTES);
       const int k0 = (kb0 + i) * BK;
       issue_tile(pa, G.A, G.lda, G.a_rpb, G.a_bs, G.a_mn, k0, G.K, st);
-      issue_tile(pb, G.B, G.ldb, G.b_rpb, G.b_bs, G.b_mn, k0, G.K, st + 2 * TILE_BYTES);
+      issue_tile(pb, G.B, G.ldb, G.b_rpb, G.b_bs, G.b_mn, k0, G.K, st + TILE_BYTES);
       cp_async_arrive_noinc(smem_u32(&raw_full[s]));
     }
   } else if (warp == MMA_WARP) {
     // ================= MMA issuer (one thread) =================
     if (lane == 0) {
       const uint32_t idesc = make_idesc(G.a_mn != 0, G.b_mn != 0);
+      const uint32_t idesc_ts = make_idesc(false, G.b_mn != 0);   // A from TMEM is always K-major (row per lane)
       const uint32_t a_step = G.a_mn ? 4096u : 32u;       // bytes per K=8 slice (MN-major: two 4-k groups)
       const uint32_t b_step = G.b_mn ? 4096u : 32u;
       int i = 0;
@@ -343,17 +409,25 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) gemm_tc_kernel(const __grid_co
           }
           tc_fence_after();
           const uint32_t base = smem_u32(tiles + (size_t)s * STAGE_BYTES);
-          const uint32_t a_hi = base, a_lo = base + TILE_BYTES, b_hi = base + 2 * TILE_BYTES, b_lo = base + 3 * TILE_BYTES;
+          const uint32_t a_raw = base, b_hi = base + TILE_BYTES, b_lo = base + 2 * TILE_BYTES;
+          if (want_lo) {
+            // A (hi | lo) from tensor memory slot i % 2, B (hi, lo) from shared memory
+            const uint32_t ah = tmem_a + (uint32_t)((i % A_SLOTS) * 64), al = ah + 32u;
 #pragma unroll
-          for (int k = 0; k < BK / 8; ++k) {
-            const uint64_t dah = make_desc(a_hi + k * a_step, G.a_mn != 0);
-            const uint64_t dbh = make_desc(b_hi + k * b_step, G.b_mn != 0);
-            umma_tf32(d_hi, dah, dbh, idesc, (i > i0 || k > 0) ? 1u : 0u);
-            if (want_lo) {
-              const uint64_t dal = make_desc(a_lo + k * a_step, G.a_mn != 0);
+            for (int k = 0; k < BK / 8; ++k) {
+              const uint64_t dbh = make_desc(b_hi + k * b_step, G.b_mn != 0);
               const uint64_t dbl = make_desc(b_lo + k * b_step, G.b_mn != 0);
-              umma_tf32(tmem_lo, dal, dbh, idesc, (i > 0 || k > 0) ? 1u : 0u);
-              umma_tf32(tmem_lo, dah, dbl, idesc, 1u);
+              umma_tf32_ts(d_hi, ah + 8u * k, dbh, idesc_ts, (i > i0 || k > 0) ? 1u : 0u);
+              umma_tf32_ts(tmem_lo, al + 8u * k, dbh, idesc_ts, (i > 0 || k > 0) ? 1u : 0u);
+              umma_tf32_ts(tmem_lo, ah + 8u * k, dbl, idesc_ts, 1u);
+            }
+            umma_commit(smem_u32(&a_empty[i % A_SLOTS]));  // the A slot may be overwritten when these retire
+          } else {
+#pragma unroll
+            for (int k = 0; k < BK / 8; ++k) {
+              const uint64_t da = make_desc(a_raw + k * a_step, G.a_mn != 0);
+              const uint64_t db = make_desc(b_hi + k * b_step, G.b_mn != 0);
+              umma_tf32(d_hi, da, db, idesc, (i > i0 || k > 0) ? 1u : 0u);
             }
           }
           umma_commit(smem_u32(&empty[s]));                // frees the stage when these MMAs retire
@@ -388,17 +462,30 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) gemm_tc_kernel(const __grid_co
     };
     int promoted = 0;
     if (want_lo) {
-      for (int i = 0; i < nkb; ++i) {
+      // The split of one k-block is a chain of long-latency steps (LDS -> STTM -> wait::st -> LDS -> STS -> proxy
+      // fence -> arrive; ncu r01 v4: the MMA thread waited on `full` 140 polls per block).  Two groups of four warps
+      // therefore work on ALTERNATE k-blocks (group g owns blocks i = g mod 2 and TMEM A slot g), so two chains are
+      // in flight; both groups promote every finished chunk (their own 64 accumulator columns).
+      const int grp = half, gt = wt & 127;
+      for (int i = grp; i < nkb; i += 2) {
         const int s = i % STAGES, round = i / STAGES;
         mbar_wait(smem_u32(&raw_full[s]), (uint32_t)(round & 1));
         unsigned char* st = tiles + (size_t)s * STAGE_BYTES;
-        split_tile(st, st + TILE_BYTES, wt);
-        split_tile(st + 2 * TILE_BYTES, st + 3 * TILE_BYTES, wt);
-        fence_proxy_async_smem();    // generic-proxy stores -> visible to the tensor core (async proxy)
+        // B first (it does not depend on the tensor core): split in place (hi) + lo tile, 128 threads x 8 chunks
+        split_tile(st + TILE_BYTES, st + 2 * TILE_BYTES, gt);
+        split_tile(st + TILE_BYTES + 8192, st + 2 * TILE_BYTES + 8192, gt);
+        // A: shared memory (raw) -> registers -> hi/lo -> tensor memory slot g (free once block i-2 retired)
+        mbar_wait(smem_u32(&a_empty[grp]), (uint32_t)((((i >> 1) & 1) ^ 1)));
+        tc_fence_after();
+        split_a_to_tmem(st, G.a_mn, q, 0, lane, tmem_a + (uint32_t)(grp * 64));
+        split_a_to_tmem(st, G.a_mn, q, 1, lane, tmem_a + (uint32_t)(grp * 64));
+        fence_proxy_async_smem();    // generic-proxy stores of B -> visible to the tensor core (async proxy)
+        tmem_wait_st();
+        tc_fence_before();
         __syncwarp();
         if (lane == 0) mbar_arrive(smem_u32(&full[s]));
-        // promote a chunk whose MMAs were issued >= PROMOTE_LAG blocks ago (it has very likely retired)
-        if (promoted < nchunks && (promoted + 1) * chunk + PROMOTE_LAG <= i + 1) promote(promoted++);
+        // promote chunks whose MMAs were issued >= PROMOTE_LAG blocks ago (they have very likely retired)
+        while (promoted < nchunks && (promoted + 1) * chunk + PROMOTE_LAG <= i + 1) promote(promoted++);
       }
     }
     while (promoted < nchunks) promote(promoted++);
