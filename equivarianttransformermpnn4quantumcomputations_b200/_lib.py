@@ -37,7 +37,8 @@ _PROTOS = {
     "eqv2_gemm_tc": [P, I, I, I, P],
     "eqv2_wigner_from_rot": [P, P, P, L, I, P],
     "eqv2_gather_rotate_fwd": [P, P, P, P, P, P, P, P, L, I, I, I, I, I, P],
-    "eqv2_gather_rotate_bwd": [P, P, P, P, P, P, P, P, P, P, P, P, L, I, I, I, I, I, P],
+    "eqv2_gather_rotate_dx": [P, P, P, P, P, P, P, P, L, I, I, I, I, I, P],
+    "eqv2_gather_rotate_drad": [P, P, P, P, P, P, L, I, I, I, I, I, P],
     "eqv2_rotinv_reduce_fwd": [P, P, P, P, P, P, P, L, I, I, L, I, I, I, F, P],
     "eqv2_rotinv_reduce_bwd": [P, P, P, P, P, P, P, P, L, I, I, L, I, I, I, F, P],
     "eqv2_s2act_padded_rows": [I],

@@ -146,14 +146,50 @@ gather_rotate_fwd_kernel(const float* __restrict__ x, const long long* __restric
 }
 
 // ------------------------------------------------------------------------------------------
-// CTA = one node; thread group h (0: edges where the node is the source, 1: where it is the destination)
+// d(rad): edge-parallel (same shape as the forward).  drad[e, slot, ch] = sum over the rows (l, +-m) sharing the
+// slot of  dA[e, row, ch] * (W_e x)[row, ch]   (so2_ops.py:170-175: rows +m and -m share one radial weight).
 template <int L, int M>
 __global__ void __launch_bounds__(256)
-gather_rotate_bwd_kernel(const float* __restrict__ x, const float* __restrict__ wig, const float* __restrict__ rad,
-                         const float* __restrict__ dA, const int* __restrict__ rowptr_src,
-                         const int* __restrict__ perm_src, const int* __restrict__ rowptr_dst,
-                         const int* __restrict__ perm_dst, float* __restrict__ dx, float* __restrict__ drad, int C,
-                         int CP /* C rounded to 32 */, int Kr, int nrad) {
+gather_rotate_drad_kernel(const float* __restrict__ x, const long long* __restrict__ src,
+                          const long long* __restrict__ dst, const float* __restrict__ wig,
+                          const float* __restrict__ dA, float* __restrict__ drad, int C, int Kr, int nrad) {
+  constexpr int K = Dim<L>::K, WS = Dim<L>::WS;
+  __shared__ __align__(16) float sw[wpad_off(L + 1)];
+  const long long e = blockIdx.x;
+  stage_wigner<L>(sw, wig + e * WS, threadIdx.x, blockDim.x);
+  __syncthreads();
+  const long long ns_ = src[e], nd_ = dst[e];
+  const int C2 = 2 * C;
+  for (int ch = threadIdx.x; ch < C2; ch += blockDim.x) {
+    const long long node = (ch < C) ? ns_ : nd_;
+    const int c = (ch < C) ? ch : ch - C;
+    const float* xp = x + node * (long long)K * C + c;
+    float xc[K];
+#pragma unroll
+    for (int k = 0; k < K; ++k) xc[k] = __ldg(xp + (long long)k * C);
+    const float* gp = dA + e * (long long)Kr * C2 + ch;
+    float* drp = drad + e * (long long)nrad + ch;
+    for_each_degree<0, L, M>([&](auto ld) {
+      constexpr int l = decltype(ld)::value;
+      constexpr int mm = l < M ? l : M;
+#pragma unroll
+      for (int m = 0; m <= mm; ++m) {
+        float d = __ldg(gp + (long long)mpos<L, M>(l, m) * C2) * row_dot<l>(sw, l + m, xc + l * l);
+        if (m > 0) d = fmaf(__ldg(gp + (long long)mpos<L, M>(l, -m) * C2), row_dot<l>(sw, l - m, xc + l * l), d);
+        drp[(long long)rslot<L, M>(l, m) * C2] = d;
+      }
+    });
+  }
+}
+
+// d(x): node-centric and deterministic.  CTA = one node; thread group h (0: edges where the node is the source,
+// 1: where it is the destination) walks its CSR segment; the two partial sums meet in shared memory.
+template <int L, int M>
+__global__ void __launch_bounds__(256, 2)
+gather_rotate_dx_kernel(const float* __restrict__ wig, const float* __restrict__ rad, const float* __restrict__ dA,
+                        const int* __restrict__ rowptr_src, const int* __restrict__ perm_src,
+                        const int* __restrict__ rowptr_dst, const int* __restrict__ perm_dst, float* __restrict__ dx,
+                        int C, int CP /* C rounded to 32 */, int Kr, int nrad) {
   constexpr int K = Dim<L>::K, WS = Dim<L>::WS, WP = wpad_off(L + 1);
   __shared__ __align__(16) float sw[2][WP];
   EQV2_DYN_SMEM(float, sred);     // [K][CP]: partial dx of group 1
@@ -167,12 +203,9 @@ gather_rotate_bwd_kernel(const float* __restrict__ x, const float* __restrict__ 
   const int len_other = (half ? rowptr_src : rowptr_dst)[node + 1] - (half ? rowptr_src : rowptr_dst)[node];
   const int maxlen = len > len_other ? len : len_other;
   const int ch = half * C + c;
-  float xc[K], acc[K];
+  float acc[K];
 #pragma unroll
-  for (int k = 0; k < K; ++k) {
-    xc[k] = (live && drad) ? __ldg(x + (node * K + k) * (long long)C + c) : 0.f;
-    acc[k] = 0.f;
-  }
+  for (int k = 0; k < K; ++k) acc[k] = 0.f;
   for (int it = 0; it < maxlen; ++it) {
     __syncthreads();
     const bool has = it < len;
@@ -185,26 +218,15 @@ gather_rotate_bwd_kernel(const float* __restrict__ x, const float* __restrict__ 
     if (!has || !live) continue;
     const float* gp = dA + e * (long long)Kr * C2 + ch;
     const float* rp = rad ? rad + e * (long long)nrad + ch : nullptr;
-    float* drp = drad ? drad + e * (long long)nrad + ch : nullptr;
     const float* w = sw[half];
     for_each_degree<0, L, M>([&](auto ld) {
       constexpr int l = decltype(ld)::value;
       constexpr int mm = l < M ? l : M;
 #pragma unroll
       for (int m = 0; m <= mm; ++m) {
-        // rows (l, +m) and (l, -m) share one radial weight (so2_ops.py:170-175)
-        const int pp = mpos<L, M>(l, m), pn = mpos<L, M>(l, -m);
-        const int slot = rslot<L, M>(l, m);
-        const float r = rp ? __ldg(rp + (long long)slot * C2) : 1.0f;
-        const float gpv = __ldg(gp + (long long)pp * C2);
-        const float gnv = (m > 0) ? __ldg(gp + (long long)pn * C2) : 0.f;
-        if (drp) {
-          float d = gpv * row_dot<l>(w, l + m, xc + l * l);
-          if (m > 0) d = fmaf(gnv, row_dot<l>(w, l - m, xc + l * l), d);
-          drp[(long long)slot * C2] = d;
-        }
-        row_axpy<l>(w, l + m, gpv * r, acc + l * l);
-        if (m > 0) row_axpy<l>(w, l - m, gnv * r, acc + l * l);
+        const float r = rp ? __ldg(rp + (long long)rslot<L, M>(l, m) * C2) : 1.0f;
+        row_axpy<l>(w, l + m, __ldg(gp + (long long)mpos<L, M>(l, m) * C2) * r, acc + l * l);
+        if (m > 0) row_axpy<l>(w, l - m, __ldg(gp + (long long)mpos<L, M>(l, -m) * C2) * r, acc + l * l);
       }
     });
   }
@@ -362,24 +384,40 @@ extern "C" int eqv2_gather_rotate_fwd(const float* x, const long long* src, cons
 #undef X
 }
 
-extern "C" int eqv2_gather_rotate_bwd(const float* x, const float* wig, const float* rad, const float* dA,
-                                      const int* rowptr_src, const int* perm_src, const int* rowptr_dst,
-                                      const int* perm_dst, float* dx, float* drad, const int* pos_of_full,
-                                      const int* rad_slot, long long N, int C, int lmax, int mmax, int Kr, int nrad,
-                                      void* stream) {
-  (void)pos_of_full; (void)rad_slot;
+// dx[N,K,C] = sum over the node's edges of W_e^T (dA * rad)     (deterministic, node-centric)
+extern "C" int eqv2_gather_rotate_dx(const float* wig, const float* rad, const float* dA, const int* rowptr_src,
+                                     const int* perm_src, const int* rowptr_dst, const int* perm_dst, float* dx,
+                                     long long N, int C, int lmax, int mmax, int Kr, int nrad, void* stream) {
   if (N == 0) return 0;
-  EQV2_REQUIRE(C > 0 && C <= 128, "gather_rotate_bwd: C=%d out of range (1..128)", C);
+  EQV2_REQUIRE(C > 0 && C <= 128, "gather_rotate_dx: C=%d out of range (1..128)", C);
   const int CP = round32(C);
   const size_t smem = (size_t)(lmax + 1) * (lmax + 1) * CP * sizeof(float);
 #define X(L_, M_)                                                                                              \
   if (lmax == L_ && mmax == M_) {                                                                              \
-    auto kfn = gather_rotate_bwd_kernel<L_, M_>;                                                                                    \
-    EQV2_LAUNCH(kfn, dim3((unsigned)N), dim3(2 * CP), smem, stream, x, wig, rad, dA, rowptr_src, perm_src, rowptr_dst, perm_dst, dx, drad, C, CP, Kr, nrad); \
-    EQV2_CHECK_LAUNCH("eqv2_gather_rotate_bwd");                                                               \
+    auto kfn = gather_rotate_dx_kernel<L_, M_>;                                                                \
+    EQV2_LAUNCH(kfn, dim3((unsigned)N), dim3(2 * CP), smem, stream, wig, rad, dA, rowptr_src, perm_src, rowptr_dst, perm_dst, dx, C, CP, Kr, nrad); \
+    EQV2_CHECK_LAUNCH("eqv2_gather_rotate_dx");                                                                \
     return 0;                                                                                                  \
   }
-  EQV2_ROT_DISPATCH("gather_rotate_bwd", X)
+  EQV2_ROT_DISPATCH("gather_rotate_dx", X)
+#undef X
+}
+
+// drad[E,nrad] = per-edge gradient of the radial weights          (edge-parallel)
+extern "C" int eqv2_gather_rotate_drad(const float* x, const long long* src, const long long* dst, const float* wig,
+                                       const float* dA, float* drad, long long E, int C, int lmax, int mmax, int Kr,
+                                       int nrad, void* stream) {
+  if (E == 0) return 0;
+  EQV2_REQUIRE(C > 0 && Kr > 0, "gather_rotate_drad: bad sizes");
+  const int threads = min(256, round32(2 * C));
+#define X(L_, M_)                                                                                              \
+  if (lmax == L_ && mmax == M_) {                                                                              \
+    auto kfn = gather_rotate_drad_kernel<L_, M_>;                                                              \
+    EQV2_LAUNCH(kfn, dim3((unsigned)E), dim3(threads), 0, stream, x, src, dst, wig, dA, drad, C, Kr, nrad);     \
+    EQV2_CHECK_LAUNCH("eqv2_gather_rotate_drad");                                                              \
+    return 0;                                                                                                  \
+  }
+  EQV2_ROT_DISPATCH("gather_rotate_drad", X)
 #undef X
 }
 

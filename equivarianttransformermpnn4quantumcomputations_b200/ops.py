@@ -642,16 +642,19 @@ def _gr_fwd(x, rad, plan, wig, lmax, mmax):
 def _gr_bwd(x, rad, gA, plan, wig, lmax, mmax, want_dx=True, want_drad=True):
     """(dx, drad) of T(x, rad, g) = <g, rad * (W x)>:  dx = sum_e W^t (g*rad) uses (rad, g);  drad = g*(W x) uses (x, g)."""
     lay = CoeffLayout.get(lmax, mmax)
-    tabs = lay.dev(x.device)
     N, K, C = x.shape
     nrad = lay.nslot * 2 * C
-    gx = torch.empty_like(x)
-    grad = torch.empty(plan.E, nrad, dtype=_F32, device=x.device) if want_drad else None
-    _lib.call("eqv2_gather_rotate_bwd", x.data_ptr(), wig.data_ptr(), _lib.ptr(rad), gA.data_ptr(),
-              plan.rowptr_src.data_ptr(), plan.perm_src.data_ptr(), plan.rowptr_dst.data_ptr(),
-              plan.perm_dst.data_ptr(), gx.data_ptr(), _lib.ptr(grad), tabs["pos_of_full"].data_ptr(),
-              tabs["rad_slot"].data_ptr(), N, C, lmax, mmax, lay.Kr, nrad, _lib.stream_ptr())
-    return (gx if want_dx else None), grad
+    gx = grad = None
+    if want_dx:
+        gx = torch.empty_like(x)
+        _lib.call("eqv2_gather_rotate_dx", wig.data_ptr(), _lib.ptr(rad), gA.data_ptr(), plan.rowptr_src.data_ptr(),
+                  plan.perm_src.data_ptr(), plan.rowptr_dst.data_ptr(), plan.perm_dst.data_ptr(), gx.data_ptr(), N, C,
+                  lmax, mmax, lay.Kr, nrad, _lib.stream_ptr())
+    if want_drad:
+        grad = torch.empty(plan.E, nrad, dtype=_F32, device=x.device)
+        _lib.call("eqv2_gather_rotate_drad", x.data_ptr(), plan.src.data_ptr(), plan.dst.data_ptr(), wig.data_ptr(),
+                  gA.data_ptr(), grad.data_ptr(), plan.E, C, lmax, mmax, lay.Kr, nrad, _lib.stream_ptr())
+    return gx, grad
 
 
 class GatherRotateFn(torch.autograd.Function):

@@ -58,11 +58,16 @@ int eqv2_gather_rotate_fwd(const float* x /*[N,K,C]*/, const long long* src, con
                            const int* rad_slot /*[Kr]*/, long long E, int C, int lmax, int mmax, int Kr,
                            int nrad, void* stream);
 
-int eqv2_gather_rotate_bwd(const float* x, const float* wig, const float* rad, const float* dA /*[E,Kr,2C]*/,
-                           const int* rowptr_src, const int* perm_src, const int* rowptr_dst,
-                           const int* perm_dst, float* dx /*[N,K,C]*/, float* drad /*[E,nrad] or NULL*/,
-                           const int* pos_of_full, const int* rad_slot, long long N, int C, int lmax, int mmax,
-                           int Kr, int nrad, void* stream);
+/* backward of the gather/rotate, split by its two outputs:
+ *   dx   [N,K,C]   = sum over the node's outgoing (src half) and incoming (dst half) edges of W_e^T (dA * rad)
+ *                    -- node-centric over the two CSR views, deterministic (no atomics);
+ *   drad [E,nrad]  = dA * (W_e x) summed over the rows that share a radial weight -- edge-parallel. */
+int eqv2_gather_rotate_dx(const float* wig, const float* rad /*or NULL*/, const float* dA /*[E,Kr,2C]*/,
+                          const int* rowptr_src, const int* perm_src, const int* rowptr_dst, const int* perm_dst,
+                          float* dx, long long N, int C, int lmax, int mmax, int Kr, int nrad, void* stream);
+int eqv2_gather_rotate_drad(const float* x, const long long* src, const long long* dst, const float* wig,
+                            const float* dA, float* drad, long long E, int C, int lmax, int mmax, int Kr, int nrad,
+                            void* stream);
 
 int eqv2_rotinv_reduce_fwd(const float* val /*[E,rows,Cv]*/, const float* alpha /*[E,heads] or NULL*/,
                            const float* wig, const int* rowptr_dst, const int* perm_dst,
