@@ -226,6 +226,41 @@ def golden_matpes():
           "self edges", int((ei2[0] == ei2[1]).sum()))
 
 
+def golden_matpes_v1():
+    """BASELINE config 3 as named: equiformerv2_MatPES.py (v1), forces pass and stress pass separately (the combined
+    default crashes in the reference)."""
+    import importlib
+    v1 = importlib.import_module("equiformerv2_MatPES")
+    gen = torch.Generator().manual_seed(23)
+    Z, pos, batch, natoms, cell = synth_cells(gen, 2, 6, vol_per_atom=14.0, zmax=89)
+    data = dict(atomic_numbers=Z, pos=pos, batch=batch, natoms=natoms, cell=cell)
+    hp = dict(lmax=3, mmax=2, C=16, H=8, heads=2, alpha_ch=8, value_ch=4, ffn_hidden=16, edge_ch=16, num_layers=2,
+              norm_type="rms_norm_sh", grid_res=18, num_rbf=600, cutoff=4.5, max_elements=100, max_neighbors=8)
+    kw = dict(max_neighbors=8, max_radius=4.5, max_num_elements=100, num_layers=2, sphere_channels=16,
+              attn_hidden_channels=8, num_heads=2, attn_alpha_channels=8, attn_value_channels=4, ffn_hidden_channels=16,
+              lmax_list=[3], mmax_list=[2], grid_resolution=18, edge_channels=16, alpha_drop=0.0, drop_path_rate=0.0,
+              proj_drop=0.0)
+    torch.manual_seed(6)
+    mf = v1.EquiformerV2_MatPES(regress_forces=True, regress_stress=False, **kw)
+    with torch.no_grad():
+        for p in mf.parameters():
+            p.add_(0.05 * torch.randn(p.shape, generator=gen))
+    ms = v1.EquiformerV2_MatPES(regress_forces=False, regress_stress=True, **kw)
+    ms.load_state_dict(mf.state_dict())
+    ms.eval()
+    torch.manual_seed(77)
+    with RandRecorder() as rr:
+        of = mf(dict(data, pos=pos.clone()))
+    torch.manual_seed(77)
+    os_ = ms(dict(data, pos=pos.clone()))
+    ei, d, vec, *_ = mf.generate_graph(data)
+    fx = dict(hyper=hp, params=params_of(mf), inputs=data, edge_index=ei, edge_distance=d.detach(), edge_vec=vec.detach(),
+              rand_vec=rr.draws[0] - 0.5, energy=of["energy"].detach(), forces=of["forces"].detach(),
+              energy_stress_pass=os_["energy"].detach(), stress=os_["stress"].detach())
+    torch.save(fx, os.path.join(OUT, "matpes_v1_small.pt"))
+    print("matpes v1 E", ei.shape[1], of["energy"].detach().view(-1), os_["stress"].detach()[0])
+
+
 def golden_gata(modname="equiformerv2_MatPES_GATAV2", out_name="matpes_gatav2_small.pt"):
     """BASELINE config 4 family: equiformerv2_MatPES_GATAV2.py (HTR + GATA value activation) and its
     phi-at-every-iteration twin, train-step pattern."""
@@ -267,6 +302,7 @@ if __name__ == "__main__":
     golden_oc20()
     golden_qm9()
     golden_matpes()
+    golden_matpes_v1()
     golden_gata()
     golden_gata("equiformerv2_MatPES_GATAV2_phi_at_every_iteration_like_gata", "matpes_gatav2_phi_small.pt")
     golden_gata("equiformerv2_MatPES_GATAV2_GLOBALALLATTENTION_HTR_phi_at_every_iteration_like_gata_with_DISTANCE",

@@ -73,6 +73,16 @@ def build_matpes_v2(hp, device):
     return m.to(device)
 
 
+def build_matpes_v1(hp, device, **flags):
+    m = pkg("models.equiformerv2_MatPES").EquiformerV2_MatPES(
+        max_neighbors=hp["max_neighbors"], max_radius=hp["cutoff"], max_num_elements=hp["max_elements"],
+        num_layers=hp["num_layers"], sphere_channels=hp["C"], attn_hidden_channels=hp["H"], num_heads=hp["heads"],
+        attn_alpha_channels=hp["alpha_ch"], attn_value_channels=hp["value_ch"], ffn_hidden_channels=hp["ffn_hidden"],
+        lmax_list=[hp["lmax"]], mmax_list=[hp["mmax"]], grid_resolution=hp["grid_res"], edge_channels=hp["edge_ch"],
+        alpha_drop=0.0, drop_path_rate=0.0, proj_drop=0.0, **flags)
+    return m.to(device)
+
+
 def build_gatav2(hp, device):
     m = pkg("models.equiformerv2_MatPES_GATAV2").EquiformerV2_MatPES(
         max_neighbors=hp["max_neighbors"], max_radius=hp["cutoff"], max_num_elements=hp["max_elements"],

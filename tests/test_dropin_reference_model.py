@@ -20,7 +20,7 @@ pytestmark = pytest.mark.skipif(not os.path.isdir(REF), reason="reference tree n
 def reference_on_dropin(backend):
     saved = {k: v for k, v in sys.modules.items()
              if k.split(".")[0] in ("EquiformerV2Functions", "NewFunctions", "equiformerv2_qm9", "equiformerv2_oc20",
-                                    "equiformerv2_MatPESv2", "equiformerv2_MatPES_GATAV2",
+                                    "equiformerv2_MatPESv2", "equiformerv2_MatPES", "equiformerv2_MatPES_GATAV2",
                                     "equiformerv2_MatPES_GATAV2_phi_at_every_iteration_like_gata",
                                     "equiformerv2_MatPES_GATAV2_GLOBALALLATTENTION_HTR_phi_at_every_iteration_like_gata_with_DISTANCE",
                                     "e3nn", "fairchem",
@@ -35,7 +35,7 @@ def reference_on_dropin(backend):
     yield backend
     for k in list(sys.modules):
         if k.split(".")[0] in ("EquiformerV2Functions", "NewFunctions", "equiformerv2_qm9", "equiformerv2_oc20",
-                               "equiformerv2_MatPESv2", "equiformerv2_MatPES_GATAV2",
+                               "equiformerv2_MatPESv2", "equiformerv2_MatPES", "equiformerv2_MatPES_GATAV2",
                                "equiformerv2_MatPES_GATAV2_phi_at_every_iteration_like_gata",
                                "equiformerv2_MatPES_GATAV2_GLOBALALLATTENTION_HTR_phi_at_every_iteration_like_gata_with_DISTANCE"):
             del sys.modules[k]
@@ -140,3 +140,34 @@ def test_reference_matpes_model_files_run_on_dropin(reference_on_dropin, modname
                       / max(float(fx["grads"][k].abs().max()), floor))
                 for k, p in model.named_parameters() if k in fx["grads"] and not k.endswith(zero_by_construction))
     assert worst < 2e-4
+
+
+def test_reference_matpes_v1_model_file_runs_on_dropin(reference_on_dropin):
+    """The unmodified equiformerv2_MatPES.py (v1, BASELINE config 3 as named): its own Python 27-image builder, forces
+    inside forward (regress_stress off -- the combined default raises in the reference), then the stress
+    pass."""
+    be = reference_on_dropin
+    mod = importlib.import_module("equiformerv2_MatPES")
+    assert mod.__file__.startswith(REF)
+    fx = golden("matpes_v1_small.pt")
+    hp = fx["hyper"]
+    kw = dict(max_neighbors=hp["max_neighbors"], max_radius=hp["cutoff"], max_num_elements=100,
+              num_layers=hp["num_layers"], sphere_channels=hp["C"], attn_hidden_channels=hp["H"], num_heads=hp["heads"],
+              attn_alpha_channels=hp["alpha_ch"], attn_value_channels=hp["value_ch"],
+              ffn_hidden_channels=hp["ffn_hidden"], lmax_list=[hp["lmax"]], mmax_list=[hp["mmax"]], grid_resolution=18,
+              edge_channels=hp["edge_ch"], alpha_drop=0.0, drop_path_rate=0.0, proj_drop=0.0)
+    data = be.to(dict(fx["inputs"]))
+    for flags, keys in ((dict(regress_forces=True, regress_stress=False), ("energy", "forces")),
+                        (dict(regress_forces=False, regress_stress=True), ("energy_stress_pass", "stress"))):
+        model = mod.EquiformerV2_MatPES(**flags, **kw).to(be.device)
+        if not flags["regress_forces"]:
+            model.eval()
+        own = dict(model.named_parameters())
+        assert set(own) == set(fx["params"])
+        with torch.no_grad():
+            for k, v in fx["params"].items():
+                own[k].copy_(v)
+        with fixed_rand_like(fx["rand_vec"] + 0.5):
+            out = model(dict(data, pos=data["pos"].clone()))
+        assert rel_err(out["energy"], fx[keys[0]]) < 1e-5
+        assert rel_err(out[keys[1]], fx[keys[1]]) < 2e-5

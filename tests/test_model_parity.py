@@ -113,6 +113,34 @@ def test_matpes_v2_train_step_matches_reference(backend):
     _check_grads(model, fx)
 
 
+def test_matpes_v1_forces_and_stress_match_reference(backend):
+    """BASELINE config 3 as named (equiformerv2_MatPES.py:373-488): forces and Voigt stress computed inside forward by
+    autograd (strain applied to positions and cell), graph from the CUDA 27-image builder (version 1).  The reference
+    can only run the two passes separately; each is compared with its own golden output, and the
+    combined call -- which the reference cannot make -- must reproduce both."""
+    from helpers import build_matpes_v1
+    fx = golden("matpes_v1_small.pt")
+    data = backend.to(dict(fx["inputs"]))
+    draw = fx["rand_vec"] + 0.5
+    mf = build_matpes_v1(fx["hyper"], backend.device, regress_forces=True, regress_stress=False)
+    load_params(mf, fx["params"])
+    with fixed_rand_like(draw):
+        of = mf(dict(data, pos=data["pos"].clone()))
+    assert rel_err(of["energy"], fx["energy"]) < OUT_TOL
+    assert rel_err(of["forces"], fx["forces"]) < 2e-5
+    ms = build_matpes_v1(fx["hyper"], backend.device, regress_forces=False, regress_stress=True).eval()
+    load_params(ms, fx["params"])
+    with fixed_rand_like(draw):
+        os_ = ms(dict(data, pos=data["pos"].clone()))
+    assert rel_err(os_["energy"], fx["energy_stress_pass"]) < OUT_TOL
+    assert rel_err(os_["stress"], fx["stress"]) < 2e-5
+    mb = build_matpes_v1(fx["hyper"], backend.device).eval()
+    load_params(mb, fx["params"])
+    with fixed_rand_like(draw):
+        ob = mb(dict(data, pos=data["pos"].clone()))
+    assert rel_err(ob["forces"], fx["forces"]) < 2e-5 and rel_err(ob["stress"], fx["stress"]) < 2e-5
+
+
 @pytest.mark.parametrize("variant", ["gatav2", "gatav2_phi", "gatav2_global"])
 def test_matpes_gatav2_train_step_matches_reference(backend, variant):
     """BASELINE config 4 family (equiformerv2_MatPES_GATAV2.py: HTR edge stream + GATA value activation): energy,
