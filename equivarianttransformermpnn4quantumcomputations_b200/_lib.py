@@ -29,12 +29,27 @@ class GemmDesc(ctypes.Structure):
     ]
 
 
+class SplitDesc(ctypes.Structure):
+    _fields_ = [("src", P), ("dst", P), ("absmax", P), ("rows", L), ("cols", L), ("rows_pad", L), ("cols_pad", L)]
+
+
+class Gemm16Desc(ctypes.Structure):
+    _fields_ = [
+        ("A", P), ("B", P), ("C", P), ("bias", P), ("a_absmax", P), ("b_absmax", P),
+        ("a_ld", L), ("a_plane", L), ("b_ld", L), ("b_plane", L), ("c_ld", L),
+        ("M", I), ("N", I), ("K", I), ("transA", I), ("transB", I), ("accumulate", I),
+    ]
+
+
 MAX_GEMM_GROUPS = 10
+MAX_SPLIT_ITEMS = 16
 
 _PROTOS = {
     "eqv2_abi_version": [],
     "eqv2_gemm_f32": [P, I, I, P],
     "eqv2_gemm_tc": [P, I, I, I, P],
+    "eqv2_split_f16": [P, I, P],
+    "eqv2_gemm_f16": [P, I, I, P],
     "eqv2_wigner_from_rot": [P, P, P, L, I, P],
     "eqv2_gather_rotate_fwd": [P, P, P, P, P, P, P, P, L, I, I, I, I, I, P],
     "eqv2_gather_rotate_dx": [P, P, P, P, P, P, P, P, L, I, I, I, I, I, P],
@@ -69,7 +84,7 @@ _PROTOS = {
     "eqv2_segment_sum_bwd": [P, P, P, L, P],
 }
 # entry points that only exist in the real (nvcc-built) library
-_OPTIONAL = {"eqv2_gemm_tc"}   # inline-PTX kernels: not part of the CPU emulator build
+_OPTIONAL = {"eqv2_gemm_tc", "eqv2_split_f16", "eqv2_gemm_f16"}   # inline-PTX kernels: not part of the CPU emulator build
 
 _state = {"lib": None, "launches": 0}
 

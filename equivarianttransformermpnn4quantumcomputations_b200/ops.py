@@ -315,12 +315,14 @@ _GEMM_MODE = {"mode": "tf32x3"}
 
 def set_gemm_mode(mode):
     """Engine for the dense edge-level contractions:
-      'tf32x3' (default): tcgen05 tensor cores with the 3xTF32 hi/lo split -- fp32-class accuracy,
+      'f16x3'           : tcgen05 kind::f16 on operands pre-split into scaled fp16 hi/lo planes (three passes at
+                          twice the TF32 rate, TMA operands, persistent CTAs) -- fp32-class accuracy,
+      'tf32x3'          : tcgen05 kind::tf32 with the 3xTF32 hi/lo split done in the kernel -- fp32-class accuracy,
       'tf32'            : tcgen05, single TF32 pass (separately stated tolerance),
       'fp32'            : exact FFMA engine for everything.
-    Problems the tensor-core engine cannot address (two-level strided degree slabs, unaligned
-    operands) always run on the FFMA engine."""
-    assert mode in ("fp32", "tf32x3", "tf32")
+    Problems a tensor-core engine cannot address (two-level strided degree slabs, unaligned operands) run on the
+    next engine down the list."""
+    assert mode in ("fp32", "tf32x3", "tf32", "f16x3")
     _GEMM_MODE["mode"] = mode
 
 
@@ -340,6 +342,7 @@ def _desc(A, B, C, bias, M, N, K, transA, transB, a_addr, b_addr, c_addr, a_off=
     d.b_rpb, d.b_bs, d.b_ld = b_addr
     d.c_rpb, d.c_bs, d.c_ld = c_addr
     d.accumulate = accumulate
+    d.src = (A, int(a_off), B, int(b_off))      # python-side only: the tensors behind the raw pointers
     return d
 
 
@@ -388,19 +391,136 @@ def _tc_ok(d):
     return d.K >= 256 or d.N >= 1024
 
 
+# ---- f16x3 engine: operand splits --------------------------------------------------------------------------
+class SplitF16:
+    """Scaled fp16 hi/lo planes [2, rows, cols_pad] of a contiguous fp32 matrix + its absolute maximum (device)."""
+    __slots__ = ("buf", "absmax", "rows", "cols", "cols_pad", "version")
+
+    def __init__(self, t):
+        self.rows, self.cols = int(t.shape[0]), int(t.shape[1])
+        self.cols_pad = (self.cols + 63) // 64 * 64
+        self.buf = torch.empty(2, self.rows, self.cols_pad, dtype=torch.float16, device=t.device)
+        self.absmax = torch.empty(1, dtype=_F32, device=t.device)
+        self.version = t._version
+
+    @property
+    def plane(self):
+        return self.rows * self.cols_pad
+
+
+_SPLIT_SCOPES = []        # stack of {id(tensor): (tensor, SplitF16)}: splits that are valid while a backward pass runs
+_PARAM_SPLITS = {}        # id(parameter) -> (weakref, version, SplitF16): weights are split once per optimizer step
+
+
+class split_scope:
+    """While active, GEMM calls find the splits of `pairs` [(tensor, SplitF16 | None)] by tensor identity and add the
+    splits they make themselves (an output gradient is split once for its dgrad and its wgrad product)."""
+
+    def __init__(self, pairs):
+        self.d = {id(t): (t, sp) for t, sp in pairs if sp is not None and t is not None}
+
+    def __enter__(self):
+        _SPLIT_SCOPES.append(self.d)
+        return self
+
+    def __exit__(self, *exc):
+        _SPLIT_SCOPES.pop()
+        return False
+
+
+def _find_split(t):
+    for d in reversed(_SPLIT_SCOPES):
+        hit = d.get(id(t))
+        if hit is not None and hit[0] is t and hit[1].version == t._version:
+            return hit[1]
+    if t.is_leaf and t.requires_grad:
+        hit = _PARAM_SPLITS.get(id(t))
+        if hit is not None and hit[0]() is t and hit[1] == t._version:
+            return hit[2]
+    return None
+
+
+def _splits_for(tensors):
+    """-> {id(t): SplitF16} for contiguous fp32 matrices; the missing ones are made by ONE eqv2_split_f16 call."""
+    import weakref
+    out, missing = {}, []
+    for t in tensors:
+        if id(t) in out:
+            continue
+        sp = _find_split(t)
+        if sp is None:
+            sp = SplitF16(t)
+            missing.append((t, sp))
+        out[id(t)] = sp
+    for i in range(0, len(missing), _lib.MAX_SPLIT_ITEMS):
+        part = missing[i:i + _lib.MAX_SPLIT_ITEMS]
+        arr = (_lib.SplitDesc * len(part))()
+        for a, (t, sp) in zip(arr, part):
+            a.src, a.dst, a.absmax = t.data_ptr(), sp.buf.data_ptr(), sp.absmax.data_ptr()
+            a.rows, a.cols, a.rows_pad, a.cols_pad = sp.rows, sp.cols, sp.rows, sp.cols_pad
+        nb = sum(12.0 * sp.rows * sp.cols for _, sp in part)
+        _lib.call("eqv2_split_f16", ctypes.cast(arr, ctypes.c_void_p), len(part), _lib.stream_ptr(), n_kernels=2,
+                  work=(0.0, nb))
+    for t, sp in missing:
+        if t.is_leaf and t.requires_grad:
+            _PARAM_SPLITS[id(t)] = (weakref.ref(t), t._version, sp)
+        elif _SPLIT_SCOPES:
+            _SPLIT_SCOPES[-1][id(t)] = (t, sp)
+    return out
+
+
+def _f16_ok(d):
+    """Should the f16x3 engine take this problem?  Same size rule as `_tc_ok`."""
+    return _f16_addressable(d) and d.M * d.N * d.K >= (1 << 21) and (d.K >= 256 or d.N >= 1024)
+
+
+def _f16_addressable(d):
+    """Plain row-major operands whose sub-block starts at a column offset that keeps TMA's 16-byte alignment."""
+    if min(d.a_rpb, d.b_rpb, d.c_rpb) < (1 << 31):
+        return False
+    A, a_off, B, b_off = d.src
+    for t, off in ((A, a_off), (B, b_off)):
+        if t.dim() != 2 or not t.is_contiguous() or t.dtype != _F32 or off % 8 or off >= max(t.shape[1], 1):
+            return False
+    return True
+
+
+def _run_gemm_f16(descs, split_k, flops, nbytes):
+    splits = _splits_for([t for d in descs for t in (d.src[0], d.src[2])])
+    n = len(descs)
+    arr = (_lib.Gemm16Desc * n)()
+    for a, d in zip(arr, descs):
+        A, a_off, B, b_off = d.src
+        sa, sb = splits[id(A)], splits[id(B)]
+        a.A, a.B = sa.buf.data_ptr() + 2 * a_off, sb.buf.data_ptr() + 2 * b_off
+        a.C, a.bias = d.C, d.bias
+        a.a_absmax, a.b_absmax = sa.absmax.data_ptr(), sb.absmax.data_ptr()
+        a.a_ld, a.a_plane, a.b_ld, a.b_plane, a.c_ld = sa.cols_pad, sa.plane, sb.cols_pad, sb.plane, d.c_ld
+        a.M, a.N, a.K, a.transA, a.transB, a.accumulate = d.M, d.N, d.K, d.transA, d.transB, d.accumulate
+    _lib.call("eqv2_gemm_f16", ctypes.cast(arr, ctypes.c_void_p), n, int(split_k), _lib.stream_ptr(),
+              work=(flops, nbytes))
+    return splits
+
+
 def run_gemm(descs, split_k=1):
+    """-> {id(tensor): SplitF16} of the operand splits the f16x3 engine used ({} on the other engines)."""
     n = len(descs)
     assert 1 <= n <= _lib.MAX_GEMM_GROUPS
-    arr = (_lib.GemmDesc * n)(*descs)
     flops = sum(2.0 * d.M * d.N * d.K for d in descs)
     nbytes = sum(4.0 * (d.M * d.K + d.K * d.N + d.M * d.N) for d in descs)
     mode = _GEMM_MODE["mode"]
+    if mode == "f16x3":
+        if all(_f16_ok(d) for d in descs):
+            return _run_gemm_f16(descs, split_k, flops, nbytes)
+        mode = "tf32x3"
+    arr = (_lib.GemmDesc * n)(*descs)
     if mode != "fp32" and all(_tc_ok(d) for d in descs):
         _lib.call("eqv2_gemm_tc", ctypes.cast(arr, ctypes.c_void_p), n, int(split_k), 0 if mode == "tf32x3" else 1,
                   _lib.stream_ptr(), work=(flops, nbytes))
     else:
         _lib.call("eqv2_gemm_f32", ctypes.cast(arr, ctypes.c_void_p), n, int(split_k), _lib.stream_ptr(),
                   work=(flops, nbytes))
+    return {}
 
 
 # The dense contractions are four primitives that are CLOSED UNDER DIFFERENTIATION: the backward of each is
@@ -432,10 +552,10 @@ class SliceMm(torch.autograd.Function):
             assert tuple(Ws[g].shape) == ((n, k) if transW else (k, n)), (Ws[g].shape, n, k, transW)
             descs.append(_desc(X, Ws[g], Y, bias if g == 0 else None, rows, n, k, 0, 1 if transW else 0,
                                _plain(xw), _plain(Ws[g].shape[1]), _plain(y_width), a_off=xo, c_off=yo))
-        if rows > 0:
-            run_gemm(descs)
+        sp = run_gemm(descs) if rows > 0 else {}
         ctx.save_for_backward(X, *Ws)
         ctx.spec = (xs, ys, y_width, transW, bias is not None)
+        ctx.splits = [sp.get(id(X))] + [sp.get(id(w)) for w in Ws]
         return Y
 
     @staticmethod
@@ -444,14 +564,16 @@ class SliceMm(torch.autograd.Function):
         xs, ys, y_width, transW, has_bias = ctx.spec
         gX = gb = None
         gWs = [None] * len(Ws)
-        if ctx.needs_input_grad[0]:
-            gX = SliceMm.apply(gY.contiguous(), None, ys, xs, X.shape[1], not transW, *Ws)
-        if any(ctx.needs_input_grad[6:]):
-            if transW:      # W_g [n,k]: gW = gY_g^T X_g
-                outs = SliceOuter.apply(gY.contiguous(), X, ys, xs)
-            else:           # W_g [k,n]: gW = X_g^T gY_g
-                outs = SliceOuter.apply(X, gY.contiguous(), xs, ys)
-            gWs = list(outs) if isinstance(outs, tuple) else [outs]
+        gY = gY.contiguous()
+        with split_scope(zip([X, *Ws], ctx.splits)):      # forward splits of X / W; gY's is made once and shared
+            if ctx.needs_input_grad[0]:
+                gX = SliceMm.apply(gY, None, ys, xs, X.shape[1], not transW, *Ws)
+            if any(ctx.needs_input_grad[6:]):
+                if transW:      # W_g [n,k]: gW = gY_g^T X_g
+                    outs = SliceOuter.apply(gY, X, ys, xs)
+                else:           # W_g [k,n]: gW = X_g^T gY_g
+                    outs = SliceOuter.apply(X, gY, xs, ys)
+                gWs = list(outs) if isinstance(outs, tuple) else [outs]
         if has_bias and ctx.needs_input_grad[1]:
             yo, n = ys[0]
             gb = gY[:, yo:yo + n].sum(0)
@@ -474,10 +596,10 @@ class SliceOuter(torch.autograd.Function):
             W = (torch.zeros if (split > 1 or rows == 0) else torch.empty)(m, n, dtype=_F32, device=U.device)
             d.C = W.data_ptr()
             outs.append(W)
-        if rows > 0:
-            run_gemm(descs, split)
+        sp = run_gemm(descs, split) if rows > 0 else {}
         ctx.save_for_backward(U, V)
         ctx.spec = (us, vs)
+        ctx.splits = [sp.get(id(U)), sp.get(id(V))]
         return tuple(outs)
 
     @staticmethod
@@ -487,10 +609,11 @@ class SliceOuter(torch.autograd.Function):
         gWs = [g.contiguous() if g is not None else torch.zeros(m, n, dtype=_F32, device=U.device)
                for g, ((_, m), (_, n)) in zip(gWs, zip(us, vs))]
         gU = gV = None
-        if ctx.needs_input_grad[0]:     # gU_g = V_g @ gW_g^T
-            gU = SliceMm.apply(V, None, vs, us, U.shape[1], True, *gWs)
-        if ctx.needs_input_grad[1]:     # gV_g = U_g @ gW_g
-            gV = SliceMm.apply(U, None, us, vs, V.shape[1], False, *gWs)
+        with split_scope(zip([U, V], ctx.splits)):
+            if ctx.needs_input_grad[0]:     # gU_g = V_g @ gW_g^T
+                gU = SliceMm.apply(V, None, vs, us, U.shape[1], True, *gWs)
+            if ctx.needs_input_grad[1]:     # gV_g = U_g @ gW_g
+                gV = SliceMm.apply(U, None, us, vs, V.shape[1], False, *gWs)
         return gU, gV, None, None
 
 

@@ -48,6 +48,37 @@ int eqv2_gemm_f32(const eqv2_gemm_desc* descs, int ngroups, int split_k, void* s
  * mode 0 = 3xTF32 split (fp32-class accuracy), mode 1 = 1xTF32. */
 int eqv2_gemm_tc(const eqv2_gemm_desc* descs, int ngroups, int split_k, int mode, void* stream);
 
+/* second tensor-core engine (tcgen05.mma kind::f16, TMA operands, persistent CTAs): fp32-class accuracy from three
+ * fp16 passes over PRE-SPLIT operands.
+ *   eqv2_split_f16: for each contiguous fp32 tensor [rows, cols] write the planes hi = fp16(s v), lo = fp16(s v - hi)
+ *     into dst[2][rows_pad][cols_pad] (fp16, zero padding; cols_pad % 64 == 0) with s the power of two that puts
+ *     max |s v| into [2^14, 2^15); *absmax receives max |v| (the GEMM derives 1/s from it on the device).
+ *   eqv2_gemm_f16: A / B point at the hi plane of the operand's sub-block (lo plane `*_plane` elements further,
+ *     leading dimension `*_ld`; both multiples of 8 elements, pointers 16-byte aligned).
+ *     transA = 0: A(m,k) at A[m*a_ld + k]; 1: A[k*a_ld + m].  transB = 1: B(k,n) at B[n*b_ld + k]; 0: B[k*b_ld + n].
+ *     C is fp32 [M, c_ld]; accumulate / split_k / bias as for eqv2_gemm_f32. */
+#define EQV2_SPLIT_MAX_ITEMS 16
+typedef struct {
+  const float* src;
+  void* dst;       /* fp16 [2][rows_pad][cols_pad] */
+  float* absmax;   /* one float, written by the call */
+  long long rows, cols, rows_pad, cols_pad;
+} eqv2_split_desc;
+typedef struct {
+  const void* A;
+  const void* B;
+  float* C;
+  const float* bias; /* may be NULL */
+  const float* a_absmax;
+  const float* b_absmax;
+  long long a_ld, a_plane, b_ld, b_plane, c_ld;
+  int M, N, K;
+  int transA, transB;
+  int accumulate;
+} eqv2_gemm16_desc;
+int eqv2_split_f16(const eqv2_split_desc* descs, int n, void* stream);
+int eqv2_gemm_f16(const eqv2_gemm16_desc* descs, int ngroups, int split_k, void* stream);
+
 /* ---- Wigner-D rotation (so3.py:343-387,499-545; transformer_block.py:250-275,321-331) ---- */
 int eqv2_wigner_from_rot(const float* rot /*[E,3,3]*/, const float* Jd /*packed blocks*/,
                          float* wig /*[E, sum (2l+1)^2]*/, long long E, int lmax, void* stream);

@@ -1,5 +1,5 @@
 """GEMM engines vs an fp64 reference: the exact FFMA engine (emulator + GPU) and the tcgen05 tensor-core
-engine (GPU only; 3xTF32 must stay fp32-class, 1xTF32 within its stated 2e-3)."""
+engines (GPU only; 3xTF32 and the fp16-split f16x3 engine must stay fp32-class, 1xTF32 within its stated 2e-3)."""
 import ctypes
 
 import pytest
@@ -30,7 +30,10 @@ def _run(ops, _lib, backend, M, N, K, transA, transB, engine, bias=False, accumu
         refs.append(ref)
         outs.append(Cd)
     arr = (_lib.GemmDesc * groups)(*descs)
-    if engine == "fp32":
+    if engine == "f16x3":
+        assert all(ops._f16_addressable(d) for d in descs)
+        ops._run_gemm_f16(descs, split_k, 0.0, 0.0)
+    elif engine == "fp32":
         _lib.call("eqv2_gemm_f32", ctypes.cast(arr, ctypes.c_void_p), groups, split_k, _lib.stream_ptr())
     else:
         if not all(ops._tc_addressable(d) for d in descs):
@@ -79,3 +82,49 @@ def test_tensor_core_engine_1xtf32_and_options(tA, tB):
     assert _run(ops, _lib, be, 384, 256, 1792, tA, tB, "tf32") < 2e-3
     assert _run(ops, _lib, be, 300, 200, 4096, tA, tB, "tf32x3", split_k=4, groups=3) < 3e-6
     assert _run(ops, _lib, be, 300, 200, 512, tA, tB, "tf32x3", accumulate=True, bias=True) < 3e-6
+
+
+F16_SHAPES = SHAPES + [(130, 260, 520), (64, 8, 8), (13120 // 8, 384, 1280)]
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("M,N,K", F16_SHAPES)
+@pytest.mark.parametrize("tA,tB", [(0, 1), (0, 0), (1, 0), (1, 1)])
+def test_f16x3_engine(M, N, K, tA, tB):
+    from conftest import Backend
+    ops, _lib = pkg("ops"), pkg("_lib")
+    err = _run(ops, _lib, Backend("cuda"), M, N, K, tA, tB, "f16x3", bias=True)
+    assert err < 3e-6, err
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("tA,tB", [(0, 1), (1, 0)])
+def test_f16x3_engine_options(tA, tB):
+    from conftest import Backend
+    ops, _lib = pkg("ops"), pkg("_lib")
+    be = Backend("cuda")
+    assert _run(ops, _lib, be, 300, 200, 4096, tA, tB, "f16x3", split_k=4, groups=3) < 3e-6
+    assert _run(ops, _lib, be, 300, 200, 1000, tA, tB, "f16x3", accumulate=True, groups=2) < 3e-6
+    assert _run(ops, _lib, be, 2000, 1100, 9000, tA, tB, "f16x3", bias=True) < 3e-6      # 144 tiles < 148 CTAs, 141 k-blocks
+
+
+@pytest.mark.gpu
+def test_f16x3_wide_dynamic_range():
+    """Rows 2^-20 .. 2^10 apart in magnitude: the per-tensor power-of-two scale keeps the max-normalised error of every
+    output row fp32-class down to 2^-18 of the tensor maximum (documented bound of the split)."""
+    from conftest import Backend
+    ops, _lib = pkg("ops"), pkg("_lib")
+    be = Backend("cuda")
+    gen = torch.Generator().manual_seed(5)
+    M, N, K = 512, 256, 1024
+    A = torch.randn(M, K, generator=gen) * torch.logspace(-5, 3, M).view(-1, 1)
+    B = torch.randn(N, K, generator=gen)
+    C = torch.zeros(M, N)
+    Ad, Bd, Cd = be.to(A), be.to(B), be.to(C)
+    d = ops._desc(Ad, Bd, Cd, None, M, N, K, 0, 1, ops._plain(K), ops._plain(K), ops._plain(N))
+    ops._run_gemm_f16([d], 1, 0.0, 0.0)
+    ref = A.double() @ B.double().t()
+    row_err = (Cd.double().cpu() - ref).abs().max(1).values / ref.abs().max(1).values
+    big = A.abs().max(1).values >= A.abs().max() * 2.0 ** -18
+    assert float(row_err[big].max()) < 3e-6
+    assert float(row_err.max()) < 1e-3
