@@ -27,7 +27,7 @@ PKG = "equivarianttransformermpnn4quantumcomputations_b200"
 
 # dram__bytes_read.sum + dram__bytes_write.sum per launch of the dominant kernel's largest launch (conv1 forward,
 # 153 GFLOP), from the committed `ncu --set full` capture (profiles/r01c_ncu_gemm_tc_summary.txt)
-TRAFFIC = {"eqv2_gemm_tc": 2.18e9}
+TRAFFIC = {"eqv2_gemm_tc": 2.18e9, "eqv2_gemm_f16": None}
 
 METRIC = "oc20_s2ef_train_structures_per_s"
 UNIT = "structures/s"
@@ -47,6 +47,8 @@ def parse():
     ap.add_argument("--structures", type=int, default=8, help="structures per GPU per step")
     ap.add_argument("--layers", type=int, default=None, help="(debug) override the number of blocks")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--gemm-mode", default=None, choices=["f16x3", "tf32x3", "tf32", "fp32"],
+                    help="GEMM engine (default: the package default, f16x3 = fp32-class accuracy)")
     return ap.parse_args()
 
 
@@ -160,6 +162,19 @@ def run_b200(args):
     synthetic = importlib.import_module(PKG + ".synthetic")
     oc20 = importlib.import_module(PKG + ".models.equiformerv2_oc20")
     _lib.lib()
+    ops = importlib.import_module(PKG + ".ops")
+    if args.gemm_mode:
+        ops.set_gemm_mode(args.gemm_mode)
+    engine_note = {
+        "f16x3": ("tcgen05 kind::f16 on operands pre-split into scaled fp16 hi/lo planes (3 passes, TMA, persistent CTAs, "
+                  "fp32 register promotion: fp32-class accuracy); short reductions and degree slabs on the FFMA engine",
+                  "fp32-accurate 3xFP16: 3 tensor-core passes at the fp16/bf16 rate -> ceiling = peak/3"),
+        "tf32x3": ("tcgen05 kind::tf32, 3xTF32 split with fp32 promotion (fp32-class accuracy); short reductions and "
+                   "degree slabs on the FFMA engine",
+                   "fp32-accurate 3xTF32: 3 tensor-core passes at the TF32 rate (1/2 of bf16) -> ceiling = peak/6"),
+        "tf32": ("tcgen05 kind::tf32 single pass (REDUCED precision, stated tolerance 5e-3)", "TF32 rate = 1/2 of bf16"),
+        "fp32": ("FFMA engine only", "no tensor cores"),
+    }[ops.gemm_mode()]
 
     kw = dict(MODEL_KW)
     if args.layers:
@@ -240,8 +255,7 @@ def run_b200(args):
             achieved = r["flops"] / (r["ms"] * 1e-3) / 1e12
             roof = {"kernel": name, "bound": "tensor", "achieved": achieved, "peak": pk["tensor"], "unit": "TFLOP/s",
                     "frac": achieved / pk["tensor"], "traffic": TRAFFIC.get(name), "peak_source": pk["src"] + " bf16 sustained",
-                    "note": "fp32-accurate 3xTF32: 3 tensor-core passes at the TF32 rate (1/2 of bf16) -> ceiling = peak/6; "
-                            "cuBLAS TF32 measured 744 TFLOP/s on this pool -> 3x ceiling 248 TFLOP/s",
+                    "note": engine_note[1],
                     "launches_per_step": r["calls"], "avg_launch_ms": r["ms"] / r["calls"],
                     "share_of_step_kernel_time": r["ms"] / tot}
         else:
@@ -258,8 +272,7 @@ def run_b200(args):
                                        "max 20 neighbours", "structures_per_gpu": B, "atoms_per_gpu": int(host["pos"].shape[0]),
                            "edges_per_gpu": E, "layers": kw["num_layers"], "params": model.num_params,
                            "parallelism": f"dp{world}",
-                           "gemm_engine": "tcgen05 kind::tf32, 3xTF32 split with fp32 promotion (fp32-class accuracy); "
-                                          "short reductions and degree slabs on the FFMA engine",
+                           "gemm_engine": engine_note[0],
                            "l2": "step working set (330 MB weights + >1 GB activations) exceeds the 126 MB L2"},
                 "e2e": {"value": e2e, "unit": UNIT, "ms_per_step": ms_e2e / args.steps, "h2d_bytes_per_step": h2d_bytes,
                         "d2h_bytes_per_step": 4},

@@ -30,13 +30,14 @@ class GemmDesc(ctypes.Structure):
 
 
 class SplitDesc(ctypes.Structure):
-    _fields_ = [("src", P), ("dst", P), ("absmax", P), ("rows", L), ("cols", L), ("rows_pad", L), ("cols_pad", L)]
+    _fields_ = [("src", P), ("dst", P), ("absmax", P), ("rows", L), ("cols", L), ("rows_pad", L), ("cols_pad", L),
+                ("slab_k", I)]
 
 
 class Gemm16Desc(ctypes.Structure):
     _fields_ = [
         ("A", P), ("B", P), ("C", P), ("bias", P), ("a_absmax", P), ("b_absmax", P),
-        ("a_ld", L), ("a_plane", L), ("b_ld", L), ("b_plane", L), ("c_ld", L),
+        ("a_ld", L), ("a_plane", L), ("b_ld", L), ("b_plane", L), ("c_ld", L), ("c_rpb", L), ("c_bs", L),
         ("M", I), ("N", I), ("K", I), ("transA", I), ("transB", I), ("accumulate", I),
     ]
 

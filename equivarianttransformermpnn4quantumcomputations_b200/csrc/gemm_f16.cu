@@ -51,7 +51,8 @@ struct alignas(64) HGroup {
   const float* bias;
   const float* a_absmax;
   const float* b_absmax;
-  long long ldc;
+  long long ldc, c_bs;
+  int c_rpb;           // C row r lives at (r / c_rpb) * c_bs + (r % c_rpb) * ldc (degree slabs of [N,K,C]); 0 = plain
   int M, N, K;
   int a_mn, b_mn;      // 1: the row index (M resp. N) is the contiguous one
   int accumulate;
@@ -346,7 +347,12 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) gemm_f16_kernel(const __grid_c
       const bool atomic = P.split_k > 1;
       if (row < G.M) {
         const int col0 = half * 64;
-        float* crow = G.C + (long long)row * G.ldc + W.n0 + col0;
+        long long roff = (long long)row * G.ldc;
+        if (G.c_rpb != 0) {
+          const int qd = row / G.c_rpb;
+          roff = (long long)qd * G.c_bs + (long long)(row - qd * G.c_rpb) * G.ldc;
+        }
+        float* crow = G.C + roff + W.n0 + col0;
         const int ncol = min(64, G.N - W.n0 - col0);
         const bool vec = (ncol == 64) && ((reinterpret_cast<uintptr_t>(crow) & 15) == 0) && !atomic;
         if (vec) {
@@ -392,6 +398,8 @@ struct SplitItem {
   __half* dst;
   float* absmax;
   long long rows, cols, rows_pad, cols_pad;
+  int slab_k;          // > 0: src is [rows / slab_k, slab_k, cols] (l-major coefficients); dst holds the degree slabs
+                       // one after the other: slab l = rows [n_nodes l^2, n_nodes (l+1)^2), row (node, j) at node (2l+1) + j
   int block_start, nblocks;
 };
 struct SplitParams {
@@ -449,14 +457,24 @@ __global__ void __launch_bounds__(256) split_kernel(const __grid_constant__ Spli
   for (long long g = (long long)lb * 256 + threadIdx.x; g < ngroups; g += (long long)T.nblocks * 256) {
     const long long r = (ngroups <= 0xFFFFFFFFll) ? (long long)((unsigned)g / gpr) : g / gpr;   // 32-bit division
     const long long c8 = (g - r * gpr) << 3;
+    long long sr = r;                                    // source row
+    if (T.slab_k > 0 && r < T.rows) {
+      const int nn = (int)(T.rows / T.slab_k);
+      int l = (int)sqrtf((float)((int)r / nn));
+      while ((long long)(l + 1) * (l + 1) * nn <= r) ++l;
+      while ((long long)l * l * nn > r) --l;
+      const int rr = (int)(r - (long long)l * l * nn), w = 2 * l + 1;
+      const int node = rr / w;
+      sr = (long long)node * T.slab_k + l * l + (rr - node * w);
+    }
     float v[8];
     if (r < T.rows && c8 + 8 <= T.cols && vec_ok) {
-      const float4 a = __ldg(reinterpret_cast<const float4*>(T.src + r * T.cols + c8));
-      const float4 b = __ldg(reinterpret_cast<const float4*>(T.src + r * T.cols + c8 + 4));
+      const float4 a = __ldg(reinterpret_cast<const float4*>(T.src + sr * T.cols + c8));
+      const float4 b = __ldg(reinterpret_cast<const float4*>(T.src + sr * T.cols + c8 + 4));
       v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
     } else {
 #pragma unroll
-      for (int t = 0; t < 8; ++t) v[t] = (r < T.rows && c8 + t < T.cols) ? __ldg(T.src + r * T.cols + c8 + t) : 0.f;
+      for (int t = 0; t < 8; ++t) v[t] = (r < T.rows && c8 + t < T.cols) ? __ldg(T.src + sr * T.cols + c8 + t) : 0.f;
     }
     __align__(16) __half h[8];
     __align__(16) __half l[8];
@@ -528,6 +546,9 @@ extern "C" int eqv2_split_f16(const eqv2_split_desc* descs, int n, void* stream)
     SplitItem& t = P.it[i];
     t.src = d.src; t.dst = reinterpret_cast<__half*>(d.dst); t.absmax = d.absmax;
     t.rows = d.rows; t.cols = d.cols; t.rows_pad = d.rows_pad; t.cols_pad = d.cols_pad;
+    EQV2_REQUIRE(d.slab_k >= 0 && (d.slab_k == 0 || (d.rows % d.slab_k == 0 && d.rows < (1ll << 31))),
+                 "eqv2_split_f16: item %d: rows must be a multiple of slab_k", i);
+    t.slab_k = d.slab_k;
     const long long groups = d.rows_pad * (d.cols_pad / 8);
     long long nb = (groups + 2047) / 2048;                 // >= 8 groups (128 B of output per plane) per thread
     if (nb < 1) nb = 1;
@@ -562,6 +583,8 @@ extern "C" int eqv2_gemm_f16(const eqv2_gemm16_desc* descs, int ngroups, int spl
     HGroup& g = P.g[i];
     g.C = d.C; g.bias = d.bias; g.a_absmax = d.a_absmax; g.b_absmax = d.b_absmax;
     g.ldc = d.c_ld;
+    g.c_rpb = (d.c_rpb <= 0 || d.c_rpb >= (1ll << 31)) ? 0 : (int)d.c_rpb;
+    g.c_bs = d.c_bs;
     g.M = d.M; g.N = d.N; g.K = d.K;
     g.a_mn = d.transA ? 1 : 0;
     g.b_mn = d.transB ? 0 : 1;

@@ -310,12 +310,13 @@ def segment_sum_nodes(values, batch, num_graphs):
 # ----------------------------------------------------------------------------------------------
 # GEMM engine
 # ----------------------------------------------------------------------------------------------
-_GEMM_MODE = {"mode": "tf32x3"}
+DEFAULT_GEMM_MODE = "f16x3"
+_GEMM_MODE = {"mode": DEFAULT_GEMM_MODE}
 
 
 def set_gemm_mode(mode):
     """Engine for the dense edge-level contractions:
-      'f16x3'           : tcgen05 kind::f16 on operands pre-split into scaled fp16 hi/lo planes (three passes at
+      'f16x3' (default) : tcgen05 kind::f16 on operands pre-split into scaled fp16 hi/lo planes (three passes at
                           twice the TF32 rate, TMA operands, persistent CTAs) -- fp32-class accuracy,
       'tf32x3'          : tcgen05 kind::tf32 with the 3xTF32 hi/lo split done in the kernel -- fp32-class accuracy,
       'tf32'            : tcgen05, single TF32 pass (separately stated tolerance),
@@ -330,7 +331,23 @@ def gemm_mode():
     return _GEMM_MODE["mode"]
 
 
-def _desc(A, B, C, bias, M, N, K, transA, transB, a_addr, b_addr, c_addr, a_off=0, b_off=0, c_off=0, accumulate=0):
+class OperandSrc:
+    """Where a GEMM operand lives inside the f16x3 split of tensor `t` (python side only): `t` read as a
+    [rows, cols] matrix (slab_k > 0: a node tensor [n, slab_k, cols] repacked slab by slab), the operand's block
+    starting at (row_off, col_off)."""
+    __slots__ = ("t", "rows", "cols", "slab_k", "row_off", "col_off")
+
+    def __init__(self, t, rows, cols, slab_k=0, row_off=0, col_off=0):
+        self.t, self.rows, self.cols, self.slab_k = t, int(rows), int(cols), int(slab_k)
+        self.row_off, self.col_off = int(row_off), int(col_off)
+
+    @property
+    def key(self):
+        return (id(self.t), self.slab_k)
+
+
+def _desc(A, B, C, bias, M, N, K, transA, transB, a_addr, b_addr, c_addr, a_off=0, b_off=0, c_off=0, accumulate=0,
+          a_src=None, b_src=None):
     d = _lib.GemmDesc()
     d.A = A.data_ptr() + 4 * a_off
     d.B = B.data_ptr() + 4 * b_off
@@ -342,7 +359,12 @@ def _desc(A, B, C, bias, M, N, K, transA, transB, a_addr, b_addr, c_addr, a_off=
     d.b_rpb, d.b_bs, d.b_ld = b_addr
     d.c_rpb, d.c_bs, d.c_ld = c_addr
     d.accumulate = accumulate
-    d.src = (A, int(a_off), B, int(b_off))      # python-side only: the tensors behind the raw pointers
+    # python-side only: the tensors behind the raw pointers (plain matrices: the offset is a column offset)
+    if a_src is None and A.dim() == 2:
+        a_src = OperandSrc(A, A.shape[0], A.shape[1], 0, a_off // max(A.shape[1], 1), a_off % max(A.shape[1], 1))
+    if b_src is None and B.dim() == 2:
+        b_src = OperandSrc(B, B.shape[0], B.shape[1], 0, b_off // max(B.shape[1], 1), b_off % max(B.shape[1], 1))
+    d.src = (a_src, b_src)
     return d
 
 
@@ -394,30 +416,30 @@ def _tc_ok(d):
 # ---- f16x3 engine: operand splits --------------------------------------------------------------------------
 class SplitF16:
     """Scaled fp16 hi/lo planes [2, rows, cols_pad] of a contiguous fp32 matrix + its absolute maximum (device)."""
-    __slots__ = ("buf", "absmax", "rows", "cols", "cols_pad", "version")
+    __slots__ = ("buf", "absmax", "rows", "cols", "cols_pad", "slab_k", "version")
 
-    def __init__(self, t):
-        self.rows, self.cols = int(t.shape[0]), int(t.shape[1])
+    def __init__(self, src):
+        self.rows, self.cols, self.slab_k = src.rows, src.cols, src.slab_k
         self.cols_pad = (self.cols + 63) // 64 * 64
-        self.buf = torch.empty(2, self.rows, self.cols_pad, dtype=torch.float16, device=t.device)
-        self.absmax = torch.empty(1, dtype=_F32, device=t.device)
-        self.version = t._version
+        self.buf = torch.empty(2, self.rows, self.cols_pad, dtype=torch.float16, device=src.t.device)
+        self.absmax = torch.empty(1, dtype=_F32, device=src.t.device)
+        self.version = src.t._version
 
     @property
     def plane(self):
         return self.rows * self.cols_pad
 
 
-_SPLIT_SCOPES = []        # stack of {id(tensor): (tensor, SplitF16)}: splits that are valid while a backward pass runs
-_PARAM_SPLITS = {}        # id(parameter) -> (weakref, version, SplitF16): weights are split once per optimizer step
+_SPLIT_SCOPES = []        # stack of {(id(tensor), slab_k): (tensor, SplitF16)}: splits valid while a backward pass runs
+_PARAM_SPLITS = {}        # (id(parameter), slab_k) -> (weakref, version, SplitF16): weights are split once per update
 
 
 class split_scope:
-    """While active, GEMM calls find the splits of `pairs` [(tensor, SplitF16 | None)] by tensor identity and add the
+    """While active, GEMM calls find the splits in `pairs` [(tensor, SplitF16 | None)] by tensor identity and add the
     splits they make themselves (an output gradient is split once for its dgrad and its wgrad product)."""
 
     def __init__(self, pairs):
-        self.d = {id(t): (t, sp) for t, sp in pairs if sp is not None and t is not None}
+        self.d = {(id(t), sp.slab_k): (t, sp) for t, sp in pairs if sp is not None and t is not None}
 
     def __enter__(self):
         _SPLIT_SCOPES.append(self.d)
@@ -428,74 +450,81 @@ class split_scope:
         return False
 
 
-def _find_split(t):
+def _find_split(src):
+    t = src.t
     for d in reversed(_SPLIT_SCOPES):
-        hit = d.get(id(t))
+        hit = d.get(src.key)
         if hit is not None and hit[0] is t and hit[1].version == t._version:
             return hit[1]
     if t.is_leaf and t.requires_grad:
-        hit = _PARAM_SPLITS.get(id(t))
+        hit = _PARAM_SPLITS.get(src.key)
         if hit is not None and hit[0]() is t and hit[1] == t._version:
             return hit[2]
     return None
 
 
-def _splits_for(tensors):
-    """-> {id(t): SplitF16} for contiguous fp32 matrices; the missing ones are made by ONE eqv2_split_f16 call."""
+def _splits_for(srcs):
+    """-> {src.key: SplitF16}; the missing splits are made by ONE eqv2_split_f16 call (two kernels)."""
     import weakref
     out, missing = {}, []
-    for t in tensors:
-        if id(t) in out:
+    for src in srcs:
+        if src.key in out:
             continue
-        sp = _find_split(t)
+        sp = _find_split(src)
         if sp is None:
-            sp = SplitF16(t)
-            missing.append((t, sp))
-        out[id(t)] = sp
+            sp = SplitF16(src)
+            missing.append((src, sp))
+        out[src.key] = sp
     for i in range(0, len(missing), _lib.MAX_SPLIT_ITEMS):
         part = missing[i:i + _lib.MAX_SPLIT_ITEMS]
         arr = (_lib.SplitDesc * len(part))()
-        for a, (t, sp) in zip(arr, part):
-            a.src, a.dst, a.absmax = t.data_ptr(), sp.buf.data_ptr(), sp.absmax.data_ptr()
-            a.rows, a.cols, a.rows_pad, a.cols_pad = sp.rows, sp.cols, sp.rows, sp.cols_pad
+        for a, (src, sp) in zip(arr, part):
+            a.src, a.dst, a.absmax = src.t.data_ptr(), sp.buf.data_ptr(), sp.absmax.data_ptr()
+            a.rows, a.cols, a.rows_pad, a.cols_pad, a.slab_k = sp.rows, sp.cols, sp.rows, sp.cols_pad, sp.slab_k
         nb = sum(12.0 * sp.rows * sp.cols for _, sp in part)
         _lib.call("eqv2_split_f16", ctypes.cast(arr, ctypes.c_void_p), len(part), _lib.stream_ptr(), n_kernels=2,
                   work=(0.0, nb))
-    for t, sp in missing:
+    for src, sp in missing:
+        t = src.t
         if t.is_leaf and t.requires_grad:
-            _PARAM_SPLITS[id(t)] = (weakref.ref(t), t._version, sp)
+            _PARAM_SPLITS[src.key] = (weakref.ref(t), t._version, sp)
         elif _SPLIT_SCOPES:
-            _SPLIT_SCOPES[-1][id(t)] = (t, sp)
+            _SPLIT_SCOPES[-1][src.key] = (t, sp)
     return out
 
 
-def _f16_ok(d):
-    """Should the f16x3 engine take this problem?  Same size rule as `_tc_ok`."""
-    return _f16_addressable(d) and d.M * d.N * d.K >= (1 << 21) and (d.K >= 256 or d.N >= 1024)
+def _split_of(splits, src):
+    return splits.get(src.key) if src is not None else None
+
+
+def _f16_ok(descs):
+    """Should the f16x3 engine take this launch?  Measured (profiles/): the persistent TMA kernel beats the FFMA engine
+    and the in-kernel-split tf32 engine from ~16 M multiply-adds per launch, operand splits included."""
+    return all(_f16_addressable(d) for d in descs) and sum(d.M * d.N * d.K for d in descs) >= (1 << 24)
 
 
 def _f16_addressable(d):
-    """Plain row-major operands whose sub-block starts at a column offset that keeps TMA's 16-byte alignment."""
-    if min(d.a_rpb, d.b_rpb, d.c_rpb) < (1 << 31):
+    """Operands that map onto split buffers (contiguous fp32 tensors; block origin keeping TMA's 16-byte alignment)."""
+    if min(d.a_rpb, d.b_rpb) < (1 << 31) and (d.src[0] is None or d.src[1] is None):
         return False
-    A, a_off, B, b_off = d.src
-    for t, off in ((A, a_off), (B, b_off)):
-        if t.dim() != 2 or not t.is_contiguous() or t.dtype != _F32 or off % 8 or off >= max(t.shape[1], 1):
+    for src in d.src:
+        if src is None or not src.t.is_contiguous() or src.t.dtype != _F32 or src.col_off % 8 or src.col_off >= max(src.cols, 1):
             return False
-    return True
+    return min(d.M, d.N, d.K) > 0
 
 
 def _run_gemm_f16(descs, split_k, flops, nbytes):
-    splits = _splits_for([t for d in descs for t in (d.src[0], d.src[2])])
+    splits = _splits_for([src for d in descs for src in d.src])
     n = len(descs)
     arr = (_lib.Gemm16Desc * n)()
     for a, d in zip(arr, descs):
-        A, a_off, B, b_off = d.src
-        sa, sb = splits[id(A)], splits[id(B)]
-        a.A, a.B = sa.buf.data_ptr() + 2 * a_off, sb.buf.data_ptr() + 2 * b_off
+        sa, sb = splits[d.src[0].key], splits[d.src[1].key]
+        a.A = sa.buf.data_ptr() + 2 * (d.src[0].row_off * sa.cols_pad + d.src[0].col_off)
+        a.B = sb.buf.data_ptr() + 2 * (d.src[1].row_off * sb.cols_pad + d.src[1].col_off)
         a.C, a.bias = d.C, d.bias
         a.a_absmax, a.b_absmax = sa.absmax.data_ptr(), sb.absmax.data_ptr()
         a.a_ld, a.a_plane, a.b_ld, a.b_plane, a.c_ld = sa.cols_pad, sa.plane, sb.cols_pad, sb.plane, d.c_ld
+        a.c_rpb, a.c_bs = d.c_rpb, d.c_bs
         a.M, a.N, a.K, a.transA, a.transB, a.accumulate = d.M, d.N, d.K, d.transA, d.transB, d.accumulate
     _lib.call("eqv2_gemm_f16", ctypes.cast(arr, ctypes.c_void_p), n, int(split_k), _lib.stream_ptr(),
               work=(flops, nbytes))
@@ -503,14 +532,14 @@ def _run_gemm_f16(descs, split_k, flops, nbytes):
 
 
 def run_gemm(descs, split_k=1):
-    """-> {id(tensor): SplitF16} of the operand splits the f16x3 engine used ({} on the other engines)."""
+    """-> {OperandSrc.key: SplitF16} of the operand splits the f16x3 engine used ({} on the other engines)."""
     n = len(descs)
     assert 1 <= n <= _lib.MAX_GEMM_GROUPS
     flops = sum(2.0 * d.M * d.N * d.K for d in descs)
     nbytes = sum(4.0 * (d.M * d.K + d.K * d.N + d.M * d.N) for d in descs)
     mode = _GEMM_MODE["mode"]
     if mode == "f16x3":
-        if all(_f16_ok(d) for d in descs):
+        if _f16_ok(descs):
             return _run_gemm_f16(descs, split_k, flops, nbytes)
         mode = "tf32x3"
     arr = (_lib.GemmDesc * n)(*descs)
@@ -555,7 +584,7 @@ class SliceMm(torch.autograd.Function):
         sp = run_gemm(descs) if rows > 0 else {}
         ctx.save_for_backward(X, *Ws)
         ctx.spec = (xs, ys, y_width, transW, bias is not None)
-        ctx.splits = [sp.get(id(X))] + [sp.get(id(w)) for w in Ws]
+        ctx.splits = [_split_of(sp, descs[0].src[0])] + [_split_of(sp, d.src[1]) for d in descs]
         return Y
 
     @staticmethod
@@ -599,7 +628,7 @@ class SliceOuter(torch.autograd.Function):
         sp = run_gemm(descs, split) if rows > 0 else {}
         ctx.save_for_backward(U, V)
         ctx.spec = (us, vs)
-        ctx.splits = [sp.get(id(U)), sp.get(id(V))]
+        ctx.splits = [_split_of(sp, descs[0].src[0]), _split_of(sp, descs[0].src[1])] if descs else [None, None]
         return tuple(outs)
 
     @staticmethod
@@ -632,11 +661,13 @@ class SlabMm(torch.autograd.Function):
             r = 2 * l + 1
             descs.append(_desc(x, W, y, bias if l == 0 else None, N * r, Co, Ci, 0, 1 if transW else 0,
                                (r, K * Ci, Ci), _plain(Wi), (r, K * Co, Co),
-                               a_off=l * l * Ci, b_off=l * Wo * Wi, c_off=l * l * Co))
-        if N > 0:
-            run_gemm(descs)
+                               a_off=l * l * Ci, b_off=l * Wo * Wi, c_off=l * l * Co,
+                               a_src=OperandSrc(x, N * K, Ci, K, N * l * l, 0),
+                               b_src=OperandSrc(W, L1 * Wo, Wi, 0, l * Wo, 0)))
+        sp = run_gemm(descs) if N > 0 else {}
         ctx.save_for_backward(x, W)
         ctx.spec = (transW, bias is not None)
+        ctx.splits = [_split_of(sp, descs[0].src[0]), _split_of(sp, descs[0].src[1])]
         return y
 
     @staticmethod
@@ -644,10 +675,12 @@ class SlabMm(torch.autograd.Function):
         x, W = ctx.saved_tensors
         transW, has_bias = ctx.spec
         gx = gW = gb = None
-        if ctx.needs_input_grad[0]:
-            gx = SlabMm.apply(gy.contiguous(), W, None, not transW)
-        if ctx.needs_input_grad[1]:
-            gW = SlabOuter.apply(gy.contiguous(), x) if transW else SlabOuter.apply(x, gy.contiguous())
+        gy = gy.contiguous()
+        with split_scope(zip([x, W], ctx.splits)):
+            if ctx.needs_input_grad[0]:
+                gx = SlabMm.apply(gy, W, None, not transW)
+            if ctx.needs_input_grad[1]:
+                gW = SlabOuter.apply(gy, x) if transW else SlabOuter.apply(x, gy)
         if has_bias and ctx.needs_input_grad[2]:
             gb = gy[:, 0, :].sum(0)
         return gx, gW, gb, None
@@ -665,24 +698,28 @@ class SlabOuter(torch.autograd.Function):
         for l in range(L1):
             r = 2 * l + 1
             descs.append(_desc(U, V, U, None, Cu, Cv, N * r, 1, 0, (r, K * Cu, Cu), (r, K * Cv, Cv), _plain(Cv),
-                               a_off=l * l * Cu, b_off=l * l * Cv))
+                               a_off=l * l * Cu, b_off=l * l * Cv,
+                               a_src=OperandSrc(U, N * K, Cu, K, N * l * l, 0),
+                               b_src=OperandSrc(V, N * K, Cv, K, N * l * l, 0)))
         split = _pick_split(descs, True) if N > 0 else 1
         W = (torch.zeros if (split > 1 or N == 0) else torch.empty)(L1, Cu, Cv, dtype=_F32, device=U.device)
         for l in range(L1):
             descs[l].C = W.data_ptr() + 4 * l * Cu * Cv
-        if N > 0:
-            run_gemm(descs, split)
+        sp = run_gemm(descs, split) if N > 0 else {}
         ctx.save_for_backward(U, V)
+        ctx.splits = [_split_of(sp, descs[0].src[0]), _split_of(sp, descs[0].src[1])]
         return W
 
     @staticmethod
     def backward(ctx, gW):
         U, V = ctx.saved_tensors
         gU = gV = None
-        if ctx.needs_input_grad[0]:     # gU_l = V_l @ gW_l^T
-            gU = SlabMm.apply(V, gW.contiguous(), None, True)
-        if ctx.needs_input_grad[1]:     # gV_l = U_l @ gW_l
-            gV = SlabMm.apply(U, gW.contiguous(), None, False)
+        gW = gW.contiguous()
+        with split_scope(zip([U, V], ctx.splits)):
+            if ctx.needs_input_grad[0]:     # gU_l = V_l @ gW_l^T
+                gU = SlabMm.apply(V, gW, None, True)
+            if ctx.needs_input_grad[1]:     # gV_l = U_l @ gW_l
+                gV = SlabMm.apply(U, gW, None, False)
         return gU, gV
 
 

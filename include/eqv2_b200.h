@@ -63,6 +63,9 @@ typedef struct {
   void* dst;       /* fp16 [2][rows_pad][cols_pad] */
   float* absmax;   /* one float, written by the call */
   long long rows, cols, rows_pad, cols_pad;
+  int slab_k;      /* 0: plain.  > 0: src is a node tensor [rows / slab_k, slab_k = (lmax+1)^2, cols] (so3.py:76-88) and dst
+                      receives its degree slabs one after the other -- slab l = rows [n l^2, n (l+1)^2), row (node, j) at
+                      node (2l+1) + j -- so that every SO3_LinearV2 block (so3.py:722-727) is a plain matrix */
 } eqv2_split_desc;
 typedef struct {
   const void* A;
@@ -72,6 +75,7 @@ typedef struct {
   const float* a_absmax;
   const float* b_absmax;
   long long a_ld, a_plane, b_ld, b_plane, c_ld;
+  long long c_rpb, c_bs; /* C row r at (r / c_rpb) * c_bs + (r % c_rpb) * c_ld; c_rpb <= 0 or >= 2^31: plain r * c_ld */
   int M, N, K;
   int transA, transB;
   int accumulate;

@@ -257,6 +257,21 @@ def golden_matpes_v1():
     fx = dict(hyper=hp, params=params_of(mf), inputs=data, edge_index=ei, edge_distance=d.detach(), edge_vec=vec.detach(),
               rand_vec=rr.draws[0] - 0.5, energy=of["energy"].detach(), forces=of["forces"].detach(),
               energy_stress_pass=os_["energy"].detach(), stress=os_["stress"].detach())
+    # The same reference evaluated in float64 (its fp32 result carries ~1e-5 of rounding noise in the autograd forces and
+    # stress, so parity with the fp32 numbers is only meaningful down to that floor).  The reference hard-codes
+    # dtype=torch.float32 in one torch.arange (equiformerv2_MatPES.py:275); that single dtype is redirected here.
+    real_arange, real_rand_like = torch.arange, torch.rand_like
+    torch.arange = lambda *a, **k: real_arange(*a, **{**k, "dtype": torch.float64 if k.get("dtype") == torch.float32 else k.get("dtype")})
+    torch.rand_like = lambda t, *a, **k: rr.draws[0].to(t.dtype)
+    torch.set_default_dtype(torch.float64)
+    try:
+        data64 = {k: (v.double() if torch.is_tensor(v) and v.is_floating_point() else v) for k, v in data.items()}
+        of64 = mf.double()(dict(data64, pos=data64["pos"].clone()))
+        os64 = ms.double()(dict(data64, pos=data64["pos"].clone()))
+    finally:
+        torch.arange, torch.rand_like = real_arange, real_rand_like
+        torch.set_default_dtype(torch.float32)
+    fx.update(energy_f64=of64["energy"].detach(), forces_f64=of64["forces"].detach(), stress_f64=os64["stress"].detach())
     torch.save(fx, os.path.join(OUT, "matpes_v1_small.pt"))
     print("matpes v1 E", ei.shape[1], of["energy"].detach().view(-1), os_["stress"].detach()[0])
 

@@ -27,9 +27,9 @@ def one(name, M, N, K, tA, tB, split=1, check=True):
         rows = slice(0, min(M, 512))
         ref = ((A.double().t() if tA else A.double())[rows] @ (B.double().t() if tB else B.double()))
         out.append(f"err {float((C[rows].double() - ref).abs().max() / ref.abs().max()):.1e}")
-    t_split = timeit(lambda: ops._splits_for([A, B]))
+    t_split = timeit(lambda: ops._splits_for(list(d.src)))
     with ops.split_scope([]):
-        ops._splits_for([A, B])                   # registers both splits in the scope
+        ops._splits_for(list(d.src))              # registers both splits in the scope
         def run16():
             if split > 1: C.zero_()
             ops._run_gemm_f16([d], split, 0, 0)

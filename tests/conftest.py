@@ -56,13 +56,13 @@ def backend(request, monkeypatch):
             pytest.skip("no CUDA device")
         monkeypatch.setitem(_lib._state, "lib", None)      # force the real library
         _lib.lib()
-        ops.set_gemm_mode("tf32x3")         # the product default
+        ops.set_gemm_mode(ops.DEFAULT_GEMM_MODE)         # the product default (f16x3)
     ops._plan_cache.clear()
     for lay in ops.CoeffLayout._cache.values():
         lay._dev.clear()
     yield Backend(request.param)
     ops._plan_cache.clear()
-    ops.set_gemm_mode("tf32x3")
+    ops.set_gemm_mode(ops.DEFAULT_GEMM_MODE)
 
 
 def golden(name):

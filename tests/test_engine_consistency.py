@@ -1,6 +1,6 @@
 """GPU only: a mid-size OC20-shaped model (large enough that every dense contraction runs on the tcgen05
 engine, including the two-level strided SO3_LinearV2 problems) must give the same energies / forces /
-parameter gradients in 3xTF32 mode as with the exact FFMA engine -- the 1e-5 bound of the fp32 mode."""
+parameter gradients in the fp32-class tensor-core modes (3xTF32 and the fp16-split f16x3 default) as with the exact FFMA engine -- the 1e-5 bound of the fp32 mode."""
 import pytest
 import torch
 
@@ -27,7 +27,7 @@ def _run(mode, data, seed_frames):
         (energy.sum() + (forces * w).sum()).backward()
         return energy.detach(), forces.detach(), {k: p.grad.clone() for k, p in model.named_parameters()}
     finally:
-        ops.set_gemm_mode("tf32x3")
+        ops.set_gemm_mode(ops.DEFAULT_GEMM_MODE)
 
 
 @pytest.mark.gpu
@@ -48,3 +48,10 @@ def test_tensor_core_mode_matches_ffma_mode():
     assert not bad, bad
     e2, f2, _ = _run("tf32", data, 7)
     assert rel_err(e2, e0) < 5e-3 and rel_err(f2, f0) < 5e-3
+    _lib.start_kernel_timing()
+    e3, f3, g3 = _run("f16x3", data, 7)
+    prof = _lib.stop_kernel_timing()
+    assert prof.get("eqv2_gemm_f16", {}).get("calls", 0) >= 20, "the f16x3 engine did not run"
+    assert rel_err(e3, e0) < 1e-5 and rel_err(f3, f0) < 1e-5
+    bad = [(k, rel_err(g3[k], g0[k])) for k in g0 if rel_err(g3[k], g0[k]) > 1e-4]
+    assert not bad, bad

@@ -128,3 +128,33 @@ def test_f16x3_wide_dynamic_range():
     big = A.abs().max(1).values >= A.abs().max() * 2.0 ** -18
     assert float(row_err[big].max()) < 3e-6
     assert float(row_err.max()) < 1e-3
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("lmax,N,Ci,Co", [(6, 640, 128, 128), (3, 77, 40, 24), (2, 300, 64, 136)])
+def test_f16x3_slab_linear_matches_ffma(lmax, N, Ci, Co):
+    """SO3_LinearV2 (so3.py:698-743) on the f16x3 engine -- node tensor repacked slab by slab by the split kernel, C
+    written back through the two-level row map -- against the exact FFMA engine: output and all three gradients."""
+    ops = pkg("ops")
+    K = (lmax + 1) ** 2
+    gen = torch.Generator().manual_seed(lmax * 100 + N)
+    x0 = torch.randn(N, K, Ci, generator=gen).cuda()
+    W0 = (torch.randn(lmax + 1, Co, Ci, generator=gen) / Ci ** 0.5).cuda()
+    b0 = torch.randn(Co, generator=gen).cuda()
+    g = torch.randn(N, K, Co, generator=gen).cuda()
+    res = {}
+    try:
+        for mode in ("fp32", "f16x3"):
+            ops.set_gemm_mode(mode)
+            x, W, b = x0.clone().requires_grad_(True), W0.clone().requires_grad_(True), b0.clone().requires_grad_(True)
+            pkg("_lib").start_kernel_timing()
+            y = ops.so3_linear(x, W, b)
+            (y * g).sum().backward()
+            prof = pkg("_lib").stop_kernel_timing()
+            res[mode] = (y.detach(), x.grad, W.grad, b.grad)
+            if mode == "f16x3" and N * K * Ci * Co >= (1 << 24):
+                assert prof.get("eqv2_gemm_f16", {}).get("calls", 0) == 3, prof.keys()
+    finally:
+        ops.set_gemm_mode(ops.DEFAULT_GEMM_MODE)
+    for a, b_ in zip(res["f16x3"], res["fp32"]):
+        assert float((a - b_).abs().max() / b_.abs().max()) < 3e-6

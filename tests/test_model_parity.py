@@ -72,7 +72,7 @@ def test_qm9_small_matches_reference(backend):
 
 
 @pytest.mark.gpu
-@pytest.mark.parametrize("mode,tol", [("fp32", 1e-5), ("tf32", 5e-3)])
+@pytest.mark.parametrize("mode,tol", [("fp32", 1e-5), ("tf32x3", 1e-5), ("tf32", 5e-3)])
 def test_oc20_small_other_gemm_modes(mode, tol):
     """fp32 = exact FFMA engine everywhere; tf32 = single-pass TF32 tensor cores (stated tolerance 5e-3)."""
     from conftest import Backend
@@ -90,7 +90,7 @@ def test_oc20_small_other_gemm_modes(mode, tol):
         assert rel_err(energy, fx["energy"]) < tol
         assert rel_err(forces, fx["forces"]) < tol
     finally:
-        ops.set_gemm_mode("tf32x3")
+        ops.set_gemm_mode(ops.DEFAULT_GEMM_MODE)
 
 
 def test_matpes_v2_train_step_matches_reference(backend):
@@ -117,28 +117,43 @@ def test_matpes_v1_forces_and_stress_match_reference(backend):
     """BASELINE config 3 as named (equiformerv2_MatPES.py:373-488): forces and Voigt stress computed inside forward by
     autograd (strain applied to positions and cell), graph from the CUDA 27-image builder (version 1).  The reference
     can only run the two passes separately; each is compared with its own golden output, and the
-    combined call -- which the reference cannot make -- must reproduce both."""
+    combined call -- which the reference cannot make -- must reproduce both.
+    Tolerance: the reference's fp32 forces / stress are themselves 1.2e-5 / 1.6e-5 away from the same reference evaluated
+    in float64 (fixture fields *_f64), so the check is made against the float64 values with a bound of twice the
+    reference's own fp32 deviation (never tighter than the 1e-5 of north_star), plus a 5e-5 sanity bound on the
+    fp32-vs-fp32 difference."""
     from helpers import build_matpes_v1
     fx = golden("matpes_v1_small.pt")
     data = backend.to(dict(fx["inputs"]))
     draw = fx["rand_vec"] + 0.5
+    tol_f = max(1e-5, 2 * rel_err(fx["forces"], fx["forces_f64"]))
+    tol_s = max(1e-5, 2 * rel_err(fx["stress"], fx["stress_f64"]))
+
+    def check(out, forces, stress):
+        if forces:
+            assert rel_err(out["forces"], fx["forces_f64"]) < tol_f
+            assert rel_err(out["forces"], fx["forces"]) < 5e-5
+        if stress:
+            assert rel_err(out["stress"], fx["stress_f64"]) < tol_s
+            assert rel_err(out["stress"], fx["stress"]) < 5e-5
+
     mf = build_matpes_v1(fx["hyper"], backend.device, regress_forces=True, regress_stress=False)
     load_params(mf, fx["params"])
     with fixed_rand_like(draw):
         of = mf(dict(data, pos=data["pos"].clone()))
-    assert rel_err(of["energy"], fx["energy"]) < OUT_TOL
-    assert rel_err(of["forces"], fx["forces"]) < 2e-5
+    assert rel_err(of["energy"], fx["energy"]) < OUT_TOL and rel_err(of["energy"], fx["energy_f64"]) < OUT_TOL
+    check(of, True, False)
     ms = build_matpes_v1(fx["hyper"], backend.device, regress_forces=False, regress_stress=True).eval()
     load_params(ms, fx["params"])
     with fixed_rand_like(draw):
         os_ = ms(dict(data, pos=data["pos"].clone()))
     assert rel_err(os_["energy"], fx["energy_stress_pass"]) < OUT_TOL
-    assert rel_err(os_["stress"], fx["stress"]) < 2e-5
+    check(os_, False, True)
     mb = build_matpes_v1(fx["hyper"], backend.device).eval()
     load_params(mb, fx["params"])
     with fixed_rand_like(draw):
         ob = mb(dict(data, pos=data["pos"].clone()))
-    assert rel_err(ob["forces"], fx["forces"]) < 2e-5 and rel_err(ob["stress"], fx["stress"]) < 2e-5
+    check(ob, True, True)
 
 
 @pytest.mark.parametrize("variant", ["gatav2", "gatav2_phi", "gatav2_global"])
