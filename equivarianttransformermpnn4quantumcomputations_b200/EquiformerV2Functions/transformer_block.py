@@ -45,9 +45,15 @@ def edge_scalar_features(module, atomic_numbers, edge_distance, edge_index):
     (transformer_block.py:241-248, input_block.py:93-100)."""
     if not module.use_atom_edge_embedding:
         return edge_distance
-    return torch.cat((edge_distance,
-                      module.source_embedding(atomic_numbers[edge_index[0]]),
-                      module.target_embedding(atomic_numbers[edge_index[1]])), dim=1)
+    src_w, dst_w = module.source_embedding.weight, module.target_embedding.weight
+    if src_w.shape[0] != dst_w.shape[0] or module.source_embedding.padding_idx is not None:
+        return torch.cat((edge_distance, module.source_embedding(atomic_numbers[edge_index[0]]),
+                          module.target_embedding(atomic_numbers[edge_index[1]])), dim=1)
+    # same lookups through the row-gather kernel: its backward is a deterministic segmented column sum over a CSR of
+    # the element types that is built once per graph (F.embedding's backward sorts the indices on every call)
+    plan = ops.edge_plan(edge_index, atomic_numbers.shape[0])
+    zs, csr_s, zd, csr_d = plan.element_types(atomic_numbers, src_w.shape[0])
+    return torch.cat((edge_distance, ops.embed_rows(src_w, zs, csr_s), ops.embed_rows(dst_w, zd, csr_d)), dim=1)
 
 
 class SO2EquivariantGraphAttention(nn.Module):

@@ -31,7 +31,7 @@ class GemmDesc(ctypes.Structure):
 
 class SplitDesc(ctypes.Structure):
     _fields_ = [("src", P), ("dst", P), ("absmax", P), ("rows", L), ("cols", L), ("rows_pad", L), ("cols_pad", L),
-                ("slab_k", I)]
+                ("absmax_given", I), ("slab_k", I)]
 
 
 class Gemm16Desc(ctypes.Structure):
@@ -52,11 +52,11 @@ _PROTOS = {
     "eqv2_split_f16": [P, I, P],
     "eqv2_gemm_f16": [P, I, I, P],
     "eqv2_wigner_from_rot": [P, P, P, L, I, P],
-    "eqv2_gather_rotate_fwd": [P, P, P, P, P, P, P, P, L, I, I, I, I, I, P],
+    "eqv2_gather_rotate_fwd": [P, P, P, P, P, P, P, P, L, I, I, I, I, I, P, P],
     "eqv2_gather_rotate_dx": [P, P, P, P, P, P, P, P, L, I, I, I, I, I, P],
-    "eqv2_gather_rotate_drad": [P, P, P, P, P, P, L, I, I, I, I, I, P],
+    "eqv2_gather_rotate_drad": [P, P, P, P, P, P, L, I, I, I, I, I, P, P],
     "eqv2_rotinv_reduce_fwd": [P, P, P, P, P, P, P, L, I, I, L, I, I, I, F, P],
-    "eqv2_rotinv_reduce_bwd": [P, P, P, P, P, P, P, P, L, I, I, L, I, I, I, F, P],
+    "eqv2_rotinv_reduce_bwd": [P, P, P, P, P, P, P, P, L, I, I, L, I, I, I, F, P, P],
     "eqv2_s2act_padded_rows": [I],
     "eqv2_s2act_fwd": [P, L, P, L, P, L, P, P, L, I, I, I, I, I, P],
     "eqv2_s2act_bwd": [P, L, P, L, P, L, P, L, P, L, P, P, L, I, I, I, I, I, P],
@@ -83,6 +83,8 @@ _PROTOS = {
     "eqv2_csr_from_index": [P, L, L, P, P, P, P, P],
     "eqv2_segment_sum_fwd": [P, L, P, P, L, I, P],
     "eqv2_segment_sum_bwd": [P, P, P, L, P],
+    "eqv2_embed_rows": [P, P, P, L, I, P],
+    "eqv2_seg_colsum": [P, L, P, P, L, I, I, I, P, P, P],
 }
 # entry points that only exist in the real (nvcc-built) library
 _OPTIONAL = {"eqv2_gemm_tc", "eqv2_split_f16", "eqv2_gemm_f16"}   # inline-PTX kernels: not part of the CPU emulator build

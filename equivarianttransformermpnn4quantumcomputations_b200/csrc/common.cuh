@@ -61,3 +61,19 @@ __device__ __forceinline__ float eqv2_warp_max(float v) {
 
 // offset of the (2l+1)x(2l+1) block of degree l inside a packed block-diagonal Wigner row
 __host__ __device__ __forceinline__ int eqv2_wig_off(int l) { return l * (4 * l * l - 1) / 3; }
+
+// Running max |v| of everything a launch writes (for the f16x3 GEMM engine's operand scale, csrc/gemm_f16.cu): block
+// reduction, then ONE conditional atomic per block -- same-address atomics serialise, so a block whose maximum does not
+// raise the running value only reads it.  Every thread of the block must call (contains __syncthreads).
+__device__ __forceinline__ void eqv2_commit_absmax(float m, float* slot) {
+  __shared__ float eqv2_absmax_red[32];
+  m = eqv2_warp_max(m);
+  if ((threadIdx.x & 31) == 0) eqv2_absmax_red[threadIdx.x >> 5] = m;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    const int nw = (blockDim.x + 31) >> 5;
+    for (int i = 1; i < nw; ++i) m = fmaxf(m, eqv2_absmax_red[i]);
+    const unsigned bits = __float_as_uint(m);           // non-negative floats order like their bit patterns
+    if (bits > *reinterpret_cast<volatile unsigned*>(slot)) atomicMax(reinterpret_cast<unsigned*>(slot), bits);
+  }
+}

@@ -398,6 +398,7 @@ struct SplitItem {
   __half* dst;
   float* absmax;
   long long rows, cols, rows_pad, cols_pad;
+  int absmax_given;    // the producer already wrote max |src| into *absmax
   int slab_k;          // > 0: src is [rows / slab_k, slab_k, cols] (l-major coefficients); dst holds the degree slabs
                        // one after the other: slab l = rows [n_nodes l^2, n_nodes (l+1)^2), row (node, j) at node (2l+1) + j
   int block_start, nblocks;
@@ -417,6 +418,7 @@ __device__ __forceinline__ const SplitItem& find_item(const SplitParams& P, int 
 
 __global__ void __launch_bounds__(256) absmax_kernel(const __grid_constant__ SplitParams P) {
   const SplitItem& T = find_item(P, blockIdx.x);
+  if (T.absmax_given) return;
   const int lb = blockIdx.x - T.block_start;
   const long long n = T.rows * T.cols;
   float m = 0.f;
@@ -537,6 +539,7 @@ extern "C" int eqv2_split_f16(const eqv2_split_desc* descs, int n, void* stream)
   SplitParams P;
   memset(&P, 0, sizeof(P));
   int blocks = 0;
+  bool need_pass = false;
   for (int i = 0; i < n; ++i) {
     const eqv2_split_desc& d = descs[i];
     EQV2_REQUIRE(d.src && d.dst && d.absmax, "eqv2_split_f16: null pointer in item %d", i);
@@ -549,6 +552,7 @@ extern "C" int eqv2_split_f16(const eqv2_split_desc* descs, int n, void* stream)
     EQV2_REQUIRE(d.slab_k >= 0 && (d.slab_k == 0 || (d.rows % d.slab_k == 0 && d.rows < (1ll << 31))),
                  "eqv2_split_f16: item %d: rows must be a multiple of slab_k", i);
     t.slab_k = d.slab_k;
+    t.absmax_given = d.absmax_given ? 1 : 0;
     const long long groups = d.rows_pad * (d.cols_pad / 8);
     long long nb = (groups + 2047) / 2048;                 // >= 8 groups (128 B of output per plane) per thread
     if (nb < 1) nb = 1;
@@ -556,12 +560,17 @@ extern "C" int eqv2_split_f16(const eqv2_split_desc* descs, int n, void* stream)
     t.block_start = blocks;
     t.nblocks = (int)nb;
     blocks += (int)nb;
-    cudaError_t e = cudaMemsetAsync(d.absmax, 0, sizeof(float), (cudaStream_t)stream);
-    EQV2_REQUIRE(e == cudaSuccess, "eqv2_split_f16: memset failed: %s", cudaGetErrorString(e));
+    if (!d.absmax_given) {
+      need_pass = true;
+      cudaError_t e = cudaMemsetAsync(d.absmax, 0, sizeof(float), (cudaStream_t)stream);
+      EQV2_REQUIRE(e == cudaSuccess, "eqv2_split_f16: memset failed: %s", cudaGetErrorString(e));
+    }
   }
   P.n = n;
-  absmax_kernel<<<dim3((unsigned)blocks), dim3(256), 0, (cudaStream_t)stream>>>(P);
-  EQV2_CHECK_LAUNCH("eqv2_split_f16 (absmax)");
+  if (need_pass) {
+    absmax_kernel<<<dim3((unsigned)blocks), dim3(256), 0, (cudaStream_t)stream>>>(P);
+    EQV2_CHECK_LAUNCH("eqv2_split_f16 (absmax)");
+  }
   split_kernel<<<dim3((unsigned)blocks), dim3(256), 0, (cudaStream_t)stream>>>(P);
   EQV2_CHECK_LAUNCH("eqv2_split_f16 (split)");
   return 0;

@@ -114,7 +114,8 @@ template <int L, int M>
 __global__ void __launch_bounds__(256)
 gather_rotate_fwd_kernel(const float* __restrict__ x, const long long* __restrict__ src,
                          const long long* __restrict__ dst, const float* __restrict__ wig,
-                         const float* __restrict__ rad, float* __restrict__ out, int C, int Kr, int nrad) {
+                         const float* __restrict__ rad, float* __restrict__ out, int C, int Kr, int nrad,
+                         float* __restrict__ absmax) {
   constexpr int K = Dim<L>::K, WS = Dim<L>::WS;
   __shared__ __align__(16) float sw[wpad_off(L + 1)];
   const long long e = blockIdx.x;
@@ -122,6 +123,7 @@ gather_rotate_fwd_kernel(const float* __restrict__ x, const long long* __restric
   __syncthreads();
   const long long ns_ = src[e], nd_ = dst[e];
   const int C2 = 2 * C;
+  float amax = 0.f;
   for (int ch = threadIdx.x; ch < C2; ch += blockDim.x) {
     const long long node = (ch < C) ? ns_ : nd_;
     const int c = (ch < C) ? ch : ch - C;
@@ -140,9 +142,11 @@ gather_rotate_fwd_kernel(const float* __restrict__ x, const long long* __restric
         const int p = mpos<L, M>(l, m);
         if (rp) acc *= __ldg(rp + (long long)rslot<L, M>(l, m < 0 ? -m : m) * C2);
         op[(long long)p * C2] = acc;
+        amax = fmaxf(amax, fabsf(acc));
       }
     });
   }
+  if (absmax != nullptr) eqv2_commit_absmax(amax, absmax);
 }
 
 // ------------------------------------------------------------------------------------------
@@ -152,7 +156,8 @@ template <int L, int M>
 __global__ void __launch_bounds__(256)
 gather_rotate_drad_kernel(const float* __restrict__ x, const long long* __restrict__ src,
                           const long long* __restrict__ dst, const float* __restrict__ wig,
-                          const float* __restrict__ dA, float* __restrict__ drad, int C, int Kr, int nrad) {
+                          const float* __restrict__ dA, float* __restrict__ drad, int C, int Kr, int nrad,
+                          float* __restrict__ absmax) {
   constexpr int K = Dim<L>::K, WS = Dim<L>::WS;
   __shared__ __align__(16) float sw[wpad_off(L + 1)];
   const long long e = blockIdx.x;
@@ -160,6 +165,7 @@ gather_rotate_drad_kernel(const float* __restrict__ x, const long long* __restri
   __syncthreads();
   const long long ns_ = src[e], nd_ = dst[e];
   const int C2 = 2 * C;
+  float amax = 0.f;
   for (int ch = threadIdx.x; ch < C2; ch += blockDim.x) {
     const long long node = (ch < C) ? ns_ : nd_;
     const int c = (ch < C) ? ch : ch - C;
@@ -177,9 +183,11 @@ gather_rotate_drad_kernel(const float* __restrict__ x, const long long* __restri
         float d = __ldg(gp + (long long)mpos<L, M>(l, m) * C2) * row_dot<l>(sw, l + m, xc + l * l);
         if (m > 0) d = fmaf(__ldg(gp + (long long)mpos<L, M>(l, -m) * C2), row_dot<l>(sw, l - m, xc + l * l), d);
         drp[(long long)rslot<L, M>(l, m) * C2] = d;
+        amax = fmaxf(amax, fabsf(d));
       }
     });
   }
+  if (absmax != nullptr) eqv2_commit_absmax(amax, absmax);
 }
 
 // d(x): node-centric and deterministic.  CTA = one node; thread group h (0: edges where the node is the source,
@@ -306,7 +314,8 @@ template <int L, int M>
 __global__ void __launch_bounds__(256)
 rotinv_reduce_bwd_kernel(const float* __restrict__ dout, const float* __restrict__ val, const float* __restrict__ alpha,
                          const float* __restrict__ wig, const long long* __restrict__ dst, float* __restrict__ dval,
-                         float* __restrict__ dalpha, int Cv, int rows_used, long long val_estride, int heads, float scale) {
+                         float* __restrict__ dalpha, int Cv, int rows_used, long long val_estride, int heads, float scale,
+                         float* __restrict__ absmax) {
   constexpr int K = Dim<L>::K, WS = Dim<L>::WS;
   __shared__ __align__(16) float sw[wpad_off(L + 1)];
   EQV2_DYN_SMEM(float, spart);   // [blockDim.x] partial d(alpha)
@@ -317,7 +326,7 @@ rotinv_reduce_bwd_kernel(const float* __restrict__ dout, const float* __restrict
   const bool live = c < Cv;
   const int vch = heads > 0 ? Cv / heads : Cv;
   const long long node = dst[e];
-  float da = 0.f;
+  float da = 0.f, amax = 0.f;
   if (live) {
     float g[K];
     for_each_degree<0, L, M>([&](auto ld) {
@@ -339,6 +348,7 @@ rotinv_reduce_bwd_kernel(const float* __restrict__ dout, const float* __restrict
           const float t = row_dot<l>(sw, l + m, g + l * l);
           if (alpha) da = fmaf(t, __ldg(vp + (long long)p * Cv), da);
           dvp[(long long)p * Cv] = t * a;
+          amax = fmaxf(amax, fabsf(t * a));
         }
       }
     });
@@ -352,6 +362,7 @@ rotinv_reduce_bwd_kernel(const float* __restrict__ dout, const float* __restrict
       dalpha[e * heads + threadIdx.x] = s;
     }
   }
+  if (absmax != nullptr) eqv2_commit_absmax(amax, absmax);
 }
 
 inline int round32(int v) { return (v + 31) / 32 * 32; }
@@ -368,7 +379,8 @@ inline int round32(int v) { return (v + 31) / 32 * 32; }
 
 extern "C" int eqv2_gather_rotate_fwd(const float* x, const long long* src, const long long* dst, const float* wig,
                                       const float* rad, float* out, const int* pos_of_full, const int* rad_slot,
-                                      long long E, int C, int lmax, int mmax, int Kr, int nrad, void* stream) {
+                                      long long E, int C, int lmax, int mmax, int Kr, int nrad, float* absmax,
+                                      void* stream) {
   (void)pos_of_full; (void)rad_slot;   // index maps are compile-time now; kept in the ABI for the host tables
   if (E == 0) return 0;
   EQV2_REQUIRE(C > 0 && Kr > 0, "gather_rotate_fwd: bad sizes");
@@ -376,7 +388,7 @@ extern "C" int eqv2_gather_rotate_fwd(const float* x, const long long* src, cons
 #define X(L_, M_)                                                                                              \
   if (lmax == L_ && mmax == M_) {                                                                              \
     auto kfn = gather_rotate_fwd_kernel<L_, M_>;                                                                                    \
-    EQV2_LAUNCH(kfn, dim3((unsigned)E), dim3(threads), 0, stream, x, src, dst, wig, rad, out, C, Kr, nrad); \
+    EQV2_LAUNCH(kfn, dim3((unsigned)E), dim3(threads), 0, stream, x, src, dst, wig, rad, out, C, Kr, nrad, absmax); \
     EQV2_CHECK_LAUNCH("eqv2_gather_rotate_fwd");                                                               \
     return 0;                                                                                                  \
   }
@@ -406,14 +418,14 @@ extern "C" int eqv2_gather_rotate_dx(const float* wig, const float* rad, const f
 // drad[E,nrad] = per-edge gradient of the radial weights          (edge-parallel)
 extern "C" int eqv2_gather_rotate_drad(const float* x, const long long* src, const long long* dst, const float* wig,
                                        const float* dA, float* drad, long long E, int C, int lmax, int mmax, int Kr,
-                                       int nrad, void* stream) {
+                                       int nrad, float* absmax, void* stream) {
   if (E == 0) return 0;
   EQV2_REQUIRE(C > 0 && Kr > 0, "gather_rotate_drad: bad sizes");
   const int threads = min(256, round32(2 * C));
 #define X(L_, M_)                                                                                              \
   if (lmax == L_ && mmax == M_) {                                                                              \
     auto kfn = gather_rotate_drad_kernel<L_, M_>;                                                              \
-    EQV2_LAUNCH(kfn, dim3((unsigned)E), dim3(threads), 0, stream, x, src, dst, wig, dA, drad, C, Kr, nrad);     \
+    EQV2_LAUNCH(kfn, dim3((unsigned)E), dim3(threads), 0, stream, x, src, dst, wig, dA, drad, C, Kr, nrad, absmax);     \
     EQV2_CHECK_LAUNCH("eqv2_gather_rotate_drad");                                                              \
     return 0;                                                                                                  \
   }
@@ -445,7 +457,7 @@ extern "C" int eqv2_rotinv_reduce_fwd(const float* val, const float* alpha, cons
 extern "C" int eqv2_rotinv_reduce_bwd(const float* dout, const float* val, const float* alpha, const float* wig,
                                       const long long* dst, float* dval, float* dalpha, const int* pos_of_full,
                                       long long E, int Cv, int rows_used, long long val_estride, int heads, int lmax,
-                                      int mmax, float scale, void* stream) {
+                                      int mmax, float scale, float* absmax, void* stream) {
   (void)pos_of_full;
   if (E == 0) return 0;
   EQV2_REQUIRE(Cv > 0 && Cv <= 256, "rotinv_reduce_bwd: Cv=%d out of range", Cv);
@@ -454,7 +466,7 @@ extern "C" int eqv2_rotinv_reduce_bwd(const float* dout, const float* val, const
 #define X(L_, M_)                                                                                              \
   if (lmax == L_ && mmax == M_) {                                                                              \
     auto kfn = rotinv_reduce_bwd_kernel<L_, M_>;                                                                                    \
-    EQV2_LAUNCH(kfn, dim3((unsigned)E), dim3(threads), threads * sizeof(float), stream, dout, val, alpha, wig, dst, dval, dalpha, Cv, rows_used, val_estride, heads, scale); \
+    EQV2_LAUNCH(kfn, dim3((unsigned)E), dim3(threads), threads * sizeof(float), stream, dout, val, alpha, wig, dst, dval, dalpha, Cv, rows_used, val_estride, heads, scale, absmax); \
     EQV2_CHECK_LAUNCH("eqv2_rotinv_reduce_bwd");                                                               \
     return 0;                                                                                                  \
   }

@@ -1,0 +1,94 @@
+"""CUDA-graph replay of a training step.
+
+A train step of this path is ~3 900 kernel launches of 5-500 us: enqueueing them from Python costs the host about as long
+as the GPU needs to run them (bench.py reports both), so the step is captured once per problem signature
+(atoms, edges, structures) and replayed.  Only the data-dependent head stays eager -- the neighbour list (its edge count
+is read back to size the edge tensors) and the edge frames (`model.prepare`) -- and the optimizer update, which runs
+eagerly on the gradients the replay leaves in place (its state and step count behave exactly as without graphs).
+A batch with a new signature is captured again (or runs eagerly with `max_graphs=0`)."""
+import torch
+
+from . import ops
+
+
+class GraphedTrainStep:
+    def __init__(self, model, loss_fn, optimizer, max_graphs=8, warmup=2):
+        """model(data) -> outputs; loss_fn(outputs, data) -> scalar; `model.prepare(data)` must exist (see
+        models/equiformerv2_oc20.py) and `model` accept its results under the keys below."""
+        self.model, self.loss_fn, self.optimizer = model, loss_fn, optimizer
+        self.max_graphs, self.warmup = max_graphs, warmup
+        self.graphs = {}            # signature -> (graph, static inputs, static loss, gradient tensors, launches)
+        self.params = [p for g in optimizer.param_groups for p in g["params"]]
+        self.pool = None
+        self.stream = None          # warm-up and every capture run on this one side stream (AccumulateGrad nodes bind to it)
+        self.active = None          # signature whose gradient tensors are currently bound to the parameters
+        self.replays = 0
+
+    PREPARED_KEYS = ("edge_index", "edge_distance", "edge_distance_vec", "edge_frames")
+
+    def _with_prepared(self, data):
+        with torch.no_grad():
+            prepared = self.model.prepare(data)
+        out = dict(data)
+        out.update(zip(self.PREPARED_KEYS, prepared))
+        return out
+
+    def _eager(self, full):
+        loss = self.loss_fn(self.model(full), full)
+        self.optimizer.zero_grad(set_to_none=True)
+        loss.backward()
+        return loss
+
+    def _capture(self, full, sig):
+        static = {k: (v.clone() if torch.is_tensor(v) else v) for k, v in full.items()}
+        if self.stream is None:
+            self.stream = torch.cuda.Stream()
+        side = self.stream
+        side.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(side):               # warm-up off the capture: lazy tables, kernel attributes, allocator
+            for _ in range(self.warmup):
+                self._eager(static)
+        torch.cuda.current_stream().wait_stream(side)
+        self.optimizer.zero_grad(set_to_none=True)  # the captured backward then ASSIGNS the .grad tensors it allocates
+        ops.reset_caches()
+        from . import _lib
+        n0 = _lib.launch_count()
+        graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(graph, pool=self.pool, stream=side):
+            loss = self.loss_fn(self.model(static), static)
+            loss.backward()
+        ops.reset_caches()
+        if self.pool is None:
+            self.pool = graph.pool()
+        self.graphs[sig] = (graph, static, loss, [p.grad for p in self.params], _lib.launch_count() - n0)
+        self.active = sig
+
+    def __call__(self, data):
+        full = self._with_prepared(data)
+        sig = (int(full["pos"].shape[0]), int(full["edge_index"].shape[1]), len(full["natoms"]))
+        hit = self.graphs.get(sig)
+        if hit is None:
+            if len(self.graphs) >= self.max_graphs:
+                loss = self._eager(full)
+                self.active = None
+                self.optimizer.step()
+                return loss
+            self._capture(full, sig)
+            hit = self.graphs[sig]
+        graph, static, loss, grads, _ = hit
+        for k, v in full.items():
+            if torch.is_tensor(v):
+                static[k].copy_(v, non_blocking=True)
+        graph.replay()
+        self.replays += 1
+        if self.active != sig:          # another signature (or an eager step) ran since: re-bind this graph's gradients
+            for p, g in zip(self.params, grads):
+                p.grad = g
+            self.active = sig
+        self.optimizer.step()
+        return loss
+
+    def captured_launches(self, sig=None):
+        """C-ABI kernel launches inside the captured step (the library's own count at capture time)."""
+        hit = self.graphs.get(sig if sig is not None else self.active)
+        return hit[4] if hit else 0

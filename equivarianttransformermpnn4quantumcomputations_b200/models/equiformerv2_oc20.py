@@ -99,13 +99,22 @@ class EquiformerV2_OC20(nn.Module):
         return ops.radius_graph_pbc(data["pos"], data["cell"], data["natoms"], data["batch"], self.cutoff,
                                     self.max_neighbors)
 
+    def prepare(self, data):
+        """The data-dependent, host-synchronising head of a forward pass: neighbour list (one read-back of the edge
+        count) and edge frames (the reference's host-side checks, edge_rot_mat.py:24,46).  Everything after it has
+        shapes fixed by (atoms, edges) and can be replayed from a CUDA graph (graphs.GraphedTrainStep)."""
+        edge_index, edge_distance, edge_vec = self.generate_graph(data)
+        return edge_index, edge_distance, edge_vec, init_edge_rot_mat(edge_vec)
+
     def forward(self, data):
         atomic_numbers = data["atomic_numbers"].long()
         num_atoms = atomic_numbers.shape[0]
         pos = data["pos"]
-        edge_index, edge_distance, edge_vec = self.generate_graph(data)
-
-        frames = init_edge_rot_mat(edge_vec)
+        if "edge_frames" in data:
+            edge_index, edge_distance, edge_vec, frames = (data["edge_index"], data["edge_distance"],
+                                                           data["edge_distance_vec"], data["edge_frames"])
+        else:
+            edge_index, edge_distance, edge_vec, frames = self.prepare(data)
         for rot in self.SO3_rotation:
             rot.set_wigner(frames)
 

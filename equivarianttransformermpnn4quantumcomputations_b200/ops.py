@@ -106,6 +106,15 @@ def _csr_from_index(idx, num_nodes):
     return perm, rowptr
 
 
+def _csr_few_buckets(idx, num_buckets):
+    """(perm, rowptr) like `_csr_from_index` for FEW, LARGE buckets (element types: thousands of edges each; the
+    per-bucket ordering pass of eqv2_csr_from_index is sized for node degrees).  Once per graph: a stable sort."""
+    perm = torch.argsort(idx, stable=True).to(torch.int32)
+    counts = torch.zeros(num_buckets + 1, dtype=torch.int32, device=idx.device)
+    counts.scatter_add_(0, idx + 1, torch.ones_like(idx, dtype=torch.int32))     # (torch.bincount reads back the max)
+    return perm, torch.cumsum(counts, 0, dtype=torch.int32)
+
+
 class EdgePlan:
     """CSR views of one edge list.  `rowptr_dst`/`perm_dst` group edges by destination (segment softmax,
     segmented reduce), `rowptr_src`/`perm_src` by source (node-centric backward of the gather)."""
@@ -124,6 +133,16 @@ class EdgePlan:
         else:
             self.perm_dst, self.rowptr_dst = _csr_from_index(self.dst, self.N)
         self.perm_src, self.rowptr_src = _csr_from_index(self.src, self.N)
+        self._z = None
+
+    def element_types(self, atomic_numbers, num_elements):
+        """(Z[src], csr, Z[dst], csr): per-edge element types and their CSR over the embedding rows, shared by every
+        block of a forward pass (the reference recomputes atomic_numbers[edge_index[i]] per block)."""
+        key = (atomic_numbers.data_ptr(), atomic_numbers._version, int(num_elements))
+        if self._z is None or self._z[0] != key:
+            zs, zd = atomic_numbers[self.src].contiguous(), atomic_numbers[self.dst].contiguous()
+            self._z = (key, (zs, _csr_few_buckets(zs, num_elements), zd, _csr_few_buckets(zd, num_elements)), atomic_numbers)
+        return self._z[1]
 
 
 _plan_cache = {}
@@ -308,6 +327,88 @@ def segment_sum_nodes(values, batch, num_graphs):
 
 
 # ----------------------------------------------------------------------------------------------
+# row gathers / deterministic segmented column sums (embedding lookups and their gradients, bias gradients)
+# ----------------------------------------------------------------------------------------------
+def _seg_colsum(src, ld, col_off, rows, C, V, rowptr, perm, S):
+    partial = torch.empty(V * S * C, dtype=_F32, device=src.device)
+    out = torch.empty(V, C, dtype=_F32, device=src.device)
+    _lib.call("eqv2_seg_colsum", src.data_ptr() + 4 * col_off, int(ld), _lib.ptr(rowptr), _lib.ptr(perm), int(rows),
+              int(V), int(C), int(S), partial.data_ptr(), out.data_ptr(), _lib.stream_ptr(), n_kernels=2,
+              work=(0.0, 4.0 * rows * C))
+    return out
+
+
+class EmbedRowsFn(torch.autograd.Function):
+    """out[e] = table[idx[e]]; `csr` = (perm, rowptr) of idx over the table rows (for the deterministic backward)."""
+
+    @staticmethod
+    def forward(ctx, table, idx, csr):
+        _lib.check_device(table, idx)
+        assert table.is_contiguous() and idx.is_contiguous() and idx.dtype == torch.long
+        E, C = int(idx.shape[0]), int(table.shape[1])
+        out = torch.empty(E, C, dtype=_F32, device=table.device)
+        _lib.call("eqv2_embed_rows", table.data_ptr(), idx.data_ptr(), out.data_ptr(), E, C, _lib.stream_ptr(),
+                  work=(0.0, 8.0 * E * C))
+        ctx.save_for_backward(idx)
+        ctx.csr, ctx.V = csr, int(table.shape[0])
+        return out
+
+    @staticmethod
+    def backward(ctx, g):
+        (idx,) = ctx.saved_tensors
+        return EmbedRowsBwdFn.apply(g.contiguous(), idx, ctx.csr, ctx.V), None, None
+
+
+class EmbedRowsBwdFn(torch.autograd.Function):
+    """gtable[v] = sum_{e: idx[e] = v} g[e] in a fixed order -- the adjoint of EmbedRowsFn (and vice versa)."""
+
+    @staticmethod
+    def forward(ctx, g, idx, csr, V):
+        _lib.check_device(g, idx)
+        perm, rowptr = csr
+        ctx.save_for_backward(idx)
+        ctx.csr = csr
+        # few element types occur in a batch -> few non-empty segments: split each into many row groups
+        S = max(1, min(128, int(g.shape[0]) // 32))
+        return _seg_colsum(g, g.shape[1], 0, g.shape[0], g.shape[1], V, rowptr, perm, S)
+
+    @staticmethod
+    def backward(ctx, gg):
+        (idx,) = ctx.saved_tensors
+        return EmbedRowsFn.apply(gg.contiguous(), idx, ctx.csr), None, None, None
+
+
+def embed_rows(table, idx, csr):
+    return EmbedRowsFn.apply(table.contiguous(), idx.contiguous(), csr)
+
+
+class ColsumFn(torch.autograd.Function):
+    """X[:, off:off+n].sum(0) for a contiguous matrix, fixed summation order (bias gradients)."""
+
+    @staticmethod
+    def forward(ctx, X, off, n):
+        _lib.check_device(X)
+        assert X.is_contiguous() and X.dim() == 2
+        ctx.spec = (tuple(X.shape), off, n)
+        rows = int(X.shape[0])
+        if rows == 0:
+            return torch.zeros(n, dtype=_F32, device=X.device)
+        S = max(1, min(rows // 16, -(-592 // ((n + 127) // 128))))       # ~4 CTAs per SM
+        return _seg_colsum(X, X.shape[1], off, rows, n, 1, None, None, S).view(n)
+
+    @staticmethod
+    def backward(ctx, g):
+        shape, off, n = ctx.spec
+        gX = g.new_zeros(shape)
+        gX[:, off:off + n] = g
+        return gX, None, None
+
+
+def colsum(X, off, n):
+    return ColsumFn.apply(X, off, n)
+
+
+# ----------------------------------------------------------------------------------------------
 # GEMM engine
 # ----------------------------------------------------------------------------------------------
 DEFAULT_GEMM_MODE = "f16x3"
@@ -430,8 +531,39 @@ class SplitF16:
         return self.rows * self.cols_pad
 
 
+_ABSMAX = {}             # storage pointer -> (weakref(tensor), slot, version): max |v| written by the producing kernel
+
+
+def _absmax_slot(device):
+    """Zero-initialised device float for a producer kernel's `absmax` output (only allocated in f16x3 mode)."""
+    return torch.zeros(1, dtype=_F32, device=device) if _GEMM_MODE["mode"] == "f16x3" else None
+
+
+def _register_absmax(t, slot):
+    """Remember that `slot` holds max |t| (the producing kernel reduced it while writing t)."""
+    if slot is None:
+        return
+    import weakref
+    key = t.untyped_storage().data_ptr()
+    _ABSMAX[key] = (weakref.ref(t, lambda _r, k=key: _ABSMAX.pop(k, None) if _ABSMAX.get(k, (None,))[0] is _r else None),
+                    slot, t._version)
+
+
+def _known_absmax(t):
+    """Slot with max |t| if t (or a same-size view of it) was written by an instrumented kernel and not modified since."""
+    hit = _ABSMAX.get(t.untyped_storage().data_ptr())
+    if hit is None:
+        return None
+    orig = hit[0]()
+    if orig is None or orig._version != hit[2] or t._version != hit[2] or t.numel() != orig.numel() or t.storage_offset() != 0:
+        return None
+    return hit[1]
+
+
 _SPLIT_SCOPES = []        # stack of {(id(tensor), slab_k): (tensor, SplitF16)}: splits valid while a backward pass runs
-_PARAM_SPLITS = {}        # (id(parameter), slab_k) -> (weakref, version, SplitF16): weights are split once per update
+# NOTE: there is deliberately no cross-call cache of parameter splits.  `Tensor._version` is not a safe validity tag
+# for parameters: the fused optimizers (torch.optim.AdamW(fused=True)) update them without bumping it.  A weight is
+# split in the forward pass (~1 GB of traffic per step for 82.5 M parameters) and that split is reused by its dgrad.
 
 
 class split_scope:
@@ -450,22 +582,24 @@ class split_scope:
         return False
 
 
+def reset_caches():
+    """Drop every identity-keyed host cache (edge plans, producer maxima).  Called around CUDA-graph
+    capture (graphs.py): work skipped because of a cache hit would be missing from the captured step."""
+    _plan_cache.clear()
+    _ABSMAX.clear()
+
+
 def _find_split(src):
     t = src.t
     for d in reversed(_SPLIT_SCOPES):
         hit = d.get(src.key)
         if hit is not None and hit[0] is t and hit[1].version == t._version:
             return hit[1]
-    if t.is_leaf and t.requires_grad:
-        hit = _PARAM_SPLITS.get(src.key)
-        if hit is not None and hit[0]() is t and hit[1] == t._version:
-            return hit[2]
     return None
 
 
 def _splits_for(srcs):
     """-> {src.key: SplitF16}; the missing splits are made by ONE eqv2_split_f16 call (two kernels)."""
-    import weakref
     out, missing = {}, []
     for src in srcs:
         if src.key in out:
@@ -473,23 +607,24 @@ def _splits_for(srcs):
         sp = _find_split(src)
         if sp is None:
             sp = SplitF16(src)
-            missing.append((src, sp))
+            known = _known_absmax(src.t)
+            if known is not None:
+                sp.absmax = known
+            missing.append((src, sp, known is not None))
         out[src.key] = sp
     for i in range(0, len(missing), _lib.MAX_SPLIT_ITEMS):
         part = missing[i:i + _lib.MAX_SPLIT_ITEMS]
         arr = (_lib.SplitDesc * len(part))()
-        for a, (src, sp) in zip(arr, part):
+        for a, (src, sp, given) in zip(arr, part):
             a.src, a.dst, a.absmax = src.t.data_ptr(), sp.buf.data_ptr(), sp.absmax.data_ptr()
             a.rows, a.cols, a.rows_pad, a.cols_pad, a.slab_k = sp.rows, sp.cols, sp.rows, sp.cols_pad, sp.slab_k
-        nb = sum(12.0 * sp.rows * sp.cols for _, sp in part)
-        _lib.call("eqv2_split_f16", ctypes.cast(arr, ctypes.c_void_p), len(part), _lib.stream_ptr(), n_kernels=2,
-                  work=(0.0, nb))
-    for src, sp in missing:
-        t = src.t
-        if t.is_leaf and t.requires_grad:
-            _PARAM_SPLITS[src.key] = (weakref.ref(t), t._version, sp)
-        elif _SPLIT_SCOPES:
-            _SPLIT_SCOPES[-1][src.key] = (t, sp)
+            a.absmax_given = int(given)
+        nb = sum((8.0 if given else 12.0) * sp.rows * sp.cols for _, sp, given in part)
+        _lib.call("eqv2_split_f16", ctypes.cast(arr, ctypes.c_void_p), len(part), _lib.stream_ptr(),
+                  n_kernels=1 if all(g for _, _, g in part) else 2, work=(0.0, nb))
+    if _SPLIT_SCOPES:
+        for src, sp, _ in missing:
+            _SPLIT_SCOPES[-1][src.key] = (src.t, sp)
     return out
 
 
@@ -605,7 +740,7 @@ class SliceMm(torch.autograd.Function):
                 gWs = list(outs) if isinstance(outs, tuple) else [outs]
         if has_bias and ctx.needs_input_grad[1]:
             yo, n = ys[0]
-            gb = gY[:, yo:yo + n].sum(0)
+            gb = colsum(gY, yo, n)
         return (gX, gb, None, None, None, None, *gWs)
 
 
@@ -793,9 +928,11 @@ def _gr_fwd(x, rad, plan, wig, lmax, mmax):
     if rad is not None:
         assert rad.shape == (plan.E, nrad), (rad.shape, plan.E, nrad)
     out = torch.empty(plan.E, lay.Kr * 2 * C, dtype=_F32, device=x.device)
+    slot = _absmax_slot(x.device)
     _lib.call("eqv2_gather_rotate_fwd", x.data_ptr(), plan.src.data_ptr(), plan.dst.data_ptr(), wig.data_ptr(),
               _lib.ptr(rad), out.data_ptr(), tabs["pos_of_full"].data_ptr(), tabs["rad_slot"].data_ptr(),
-              plan.E, C, lmax, mmax, lay.Kr, nrad, _lib.stream_ptr())
+              plan.E, C, lmax, mmax, lay.Kr, nrad, _lib.ptr(slot), _lib.stream_ptr())
+    _register_absmax(out, slot)
     return out
 
 
@@ -812,8 +949,10 @@ def _gr_bwd(x, rad, gA, plan, wig, lmax, mmax, want_dx=True, want_drad=True):
                   lmax, mmax, lay.Kr, nrad, _lib.stream_ptr())
     if want_drad:
         grad = torch.empty(plan.E, nrad, dtype=_F32, device=x.device)
+        slot = _absmax_slot(x.device)
         _lib.call("eqv2_gather_rotate_drad", x.data_ptr(), plan.src.data_ptr(), plan.dst.data_ptr(), wig.data_ptr(),
-                  gA.data_ptr(), grad.data_ptr(), plan.E, C, lmax, mmax, lay.Kr, nrad, _lib.stream_ptr())
+                  gA.data_ptr(), grad.data_ptr(), plan.E, C, lmax, mmax, lay.Kr, nrad, _lib.ptr(slot), _lib.stream_ptr())
+        _register_absmax(grad, slot)
     return gx, grad
 
 
@@ -887,9 +1026,11 @@ def _rir_bwd(gout, val, alpha, plan, wig, lmax, mmax, rows_used, heads, scale, C
     tabs = lay.dev(val.device)
     gval = torch.empty_like(val)
     galpha = torch.empty_like(alpha) if alpha is not None else None
+    slot = _absmax_slot(val.device)
     _lib.call("eqv2_rotinv_reduce_bwd", gout.data_ptr(), val.data_ptr(), _lib.ptr(alpha), wig.data_ptr(),
               plan.dst.data_ptr(), gval.data_ptr(), _lib.ptr(galpha), tabs["pos_of_full"].data_ptr(),
-              plan.E, Cv, rows_used, rows_used * Cv, heads, lmax, mmax, float(scale), _lib.stream_ptr())
+              plan.E, Cv, rows_used, rows_used * Cv, heads, lmax, mmax, float(scale), _lib.ptr(slot), _lib.stream_ptr())
+    _register_absmax(gval, slot)
     return gval, galpha
 
 

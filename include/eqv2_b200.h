@@ -63,6 +63,7 @@ typedef struct {
   void* dst;       /* fp16 [2][rows_pad][cols_pad] */
   float* absmax;   /* one float, written by the call */
   long long rows, cols, rows_pad, cols_pad;
+  int absmax_given; /* 1: *absmax already holds max |v| of src (written by the producing kernel): skip the reduction pass */
   int slab_k;      /* 0: plain.  > 0: src is a node tensor [rows / slab_k, slab_k = (lmax+1)^2, cols] (so3.py:76-88) and dst
                       receives its degree slabs one after the other -- slab l = rows [n l^2, n (l+1)^2), row (node, j) at
                       node (2l+1) + j -- so that every SO3_LinearV2 block (so3.py:722-727) is a plain matrix */
@@ -91,8 +92,11 @@ int eqv2_gather_rotate_fwd(const float* x /*[N,K,C]*/, const long long* src, con
                            const float* wig, const float* rad /*[E,nrad] or NULL*/,
                            float* out /*[E,Kr,2C] m-primary*/, const int* pos_of_full /*[K]*/,
                            const int* rad_slot /*[Kr]*/, long long E, int C, int lmax, int mmax, int Kr,
-                           int nrad, void* stream);
+                           int nrad, float* absmax /*or NULL*/, void* stream);
 
+/* `absmax` (gather_rotate_fwd / _drad, rotinv_reduce_bwd): optional device float, zero-initialised by the caller, that
+ * receives max |v| over everything the launch writes -- the operand scale the f16x3 GEMM engine needs for this tensor,
+ * produced for free instead of by a separate pass (eqv2_split_desc.absmax_given). */
 /* backward of the gather/rotate, split by its two outputs:
  *   dx   [N,K,C]   = sum over the node's outgoing (src half) and incoming (dst half) edges of W_e^T (dA * rad)
  *                    -- node-centric over the two CSR views, deterministic (no atomics);
@@ -102,7 +106,7 @@ int eqv2_gather_rotate_dx(const float* wig, const float* rad /*or NULL*/, const 
                           float* dx, long long N, int C, int lmax, int mmax, int Kr, int nrad, void* stream);
 int eqv2_gather_rotate_drad(const float* x, const long long* src, const long long* dst, const float* wig,
                             const float* dA, float* drad, long long E, int C, int lmax, int mmax, int Kr, int nrad,
-                            void* stream);
+                            float* absmax /*or NULL*/, void* stream);
 
 int eqv2_rotinv_reduce_fwd(const float* val /*[E,rows,Cv]*/, const float* alpha /*[E,heads] or NULL*/,
                            const float* wig, const int* rowptr_dst, const int* perm_dst,
@@ -112,7 +116,7 @@ int eqv2_rotinv_reduce_fwd(const float* val /*[E,rows,Cv]*/, const float* alpha 
 int eqv2_rotinv_reduce_bwd(const float* dout /*[N,K,Cv]*/, const float* val, const float* alpha,
                            const float* wig, const long long* dst, float* dval, float* dalpha /*or NULL*/,
                            const int* pos_of_full, long long E, int Cv, int rows_used, long long val_estride,
-                           int heads, int lmax, int mmax, float scale, void* stream);
+                           int heads, int lmax, int mmax, float scale, float* absmax /*or NULL*/, void* stream);
 
 /* ---- separable S2 activation (activation.py:153-192, so3.py:552-646) --------------------- */
 int eqv2_s2act_padded_rows(int Kr);
@@ -205,6 +209,16 @@ int eqv2_segment_sum_fwd(const float* v, long long v_stride, const long long* ba
                          float* out /*[B]*/, long long N, int B, void* stream);
 int eqv2_segment_sum_bwd(const float* gout /*[B]*/, const long long* batch, float* gv /*[N]*/, long long N,
                          void* stream);
+
+/* ---- row gathers and deterministic segmented column sums (csrc/rows.cu) --------------------------
+ * eqv2_embed_rows: out[e,:] = table[idx[e],:] -- nn.Embedding lookups source_embedding(Z[src]) / target_embedding(Z[dst])
+ *   of transformer_block.py:241-248 and input_block.py:93-100.
+ * eqv2_seg_colsum: out[v,c] = sum over rows i in [rowptr[v], rowptr[v+1]) of src[perm[i]*ld + c] (rowptr NULL: one
+ *   segment [0, rows); perm NULL: identity) in a fixed order; `partial` is a [V, S, C] workspace.  Embedding weight
+ *   gradients (segments = element types) and bias gradients of the dense layers. */
+int eqv2_embed_rows(const float* table, const long long* idx, float* out, long long E, int C, void* stream);
+int eqv2_seg_colsum(const float* src, long long ld, const int* rowptr, const int* perm, long long rows, int V, int C,
+                    int S, float* partial, float* out, void* stream);
 
 #ifdef __cplusplus
 }

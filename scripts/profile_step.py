@@ -1,0 +1,47 @@
+"""Diagnostic (GPU): per-kernel device time of ONE eager OC20 train step from torch.profiler (CUPTI), aggregated by kernel
+name -- the cheap companion of the ncu launch list (profiles/).   python scripts/profile_step.py [--layers N] [--top K]"""
+import argparse, collections, os, re, sys
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import torch
+from torch.profiler import profile, ProfilerActivity
+import bench
+from equivarianttransformermpnn4quantumcomputations_b200 import synthetic
+from equivarianttransformermpnn4quantumcomputations_b200.models import equiformerv2_oc20 as oc20
+
+ap = argparse.ArgumentParser()
+ap.add_argument("--layers", type=int, default=12)
+ap.add_argument("--top", type=int, default=45)
+ap.add_argument("--structures", type=int, default=8)
+a = ap.parse_args()
+kw = dict(bench.MODEL_KW, num_layers=a.layers)
+torch.manual_seed(0)
+dev = torch.device("cuda")
+model = oc20.EquiformerV2_OC20(**kw).to(dev)
+opt = torch.optim.AdamW(model.parameters(), lr=1e-4, fused=True)
+data = {k: (v.to(dev) if torch.is_tensor(v) else v) for k, v in synthetic.oc20_batch(a.structures, seed=1000).items()}
+
+
+def step():
+    e, f = model(data)
+    loss = bench.losses(e, f, data)
+    opt.zero_grad(set_to_none=True)
+    loss.backward()
+    opt.step()
+
+
+for _ in range(3):
+    step()
+torch.cuda.synchronize()
+with profile(activities=[ProfilerActivity.CUDA, ProfilerActivity.CPU]) as prof:
+    step()
+    torch.cuda.synchronize()
+agg = collections.defaultdict(lambda: [0, 0.0])
+for ev in prof.events():
+    if ev.device_type == torch.autograd.DeviceType.CUDA:
+        n = re.sub(r"\(.*", "", ev.name).replace("(anonymous namespace)::", "").replace("void ", "").replace("at::native::", "")
+        agg[n[:100]][0] += 1
+        agg[n[:100]][1] += ev.device_time
+tot = sum(v[1] for v in agg.values())
+print(f"total device time {tot / 1e3:.2f} ms in {sum(v[0] for v in agg.values())} kernels/memops")
+for k, (c, t) in sorted(agg.items(), key=lambda kv: -kv[1][1])[:a.top]:
+    print(f"{t / 1e3:8.3f} ms {100 * t / tot:5.1f}% {c:5d}  {k}")

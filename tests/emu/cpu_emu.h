@@ -130,6 +130,12 @@ static inline float atomicAdd(float* p, float v) {
     if (a->compare_exchange_weak(old, nb)) return f;
   }
 }
+static inline unsigned atomicMax(unsigned* p, unsigned v) {
+  std::atomic<unsigned>* a = reinterpret_cast<std::atomic<unsigned>*>(p);
+  unsigned old = a->load();
+  while (old < v && !a->compare_exchange_weak(old, v)) {}
+  return old;
+}
 static inline int atomicAdd(int* p, int v) { return reinterpret_cast<std::atomic<int>*>(p)->fetch_add(v); }
 static inline unsigned atomicAdd(unsigned* p, unsigned v) { return reinterpret_cast<std::atomic<unsigned>*>(p)->fetch_add(v); }
 

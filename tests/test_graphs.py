@@ -1,0 +1,59 @@
+"""GPU only: a train step replayed from a CUDA graph (graphs.GraphedTrainStep: forward + loss + backward captured,
+neighbour list / edge frames / optimizer eager) must follow the same trajectory as the eager step -- losses and
+parameters after several updates, including a change of batch signature (re-capture) and a return to the first one."""
+import pytest
+import torch
+
+from helpers import pkg
+
+
+def _loss(out, d):
+    return (out[0] - d["energy"]).abs().mean() + (out[1] - d["forces"]).abs().mean()
+
+
+def _run(graphed, batches, mode=None):
+    oc20, graphs, ops = pkg("models.equiformerv2_oc20"), pkg("graphs"), pkg("ops")
+    ops.set_gemm_mode(mode or ops.DEFAULT_GEMM_MODE)
+    torch.manual_seed(0)
+    model = oc20.EquiformerV2_OC20(num_layers=2, sphere_channels=32, attn_hidden_channels=16, num_heads=2,
+                                   attn_alpha_channels=16, attn_value_channels=8, ffn_hidden_channels=32, lmax_list=[3],
+                                   mmax_list=[2], edge_channels=32, alpha_drop=0.0, drop_path_rate=0.0, max_radius=8.0).cuda()
+    opt = torch.optim.AdamW(model.parameters(), lr=1e-3, fused=True)
+    stepper = graphs.GraphedTrainStep(model, _loss, opt) if graphed else None
+    torch.manual_seed(3)
+    out = []
+    for d in batches:
+        if graphed:
+            out.append(float(stepper(d)))
+        else:
+            loss = _loss(model(d), d)
+            opt.zero_grad(set_to_none=True)
+            loss.backward()
+            opt.step()
+            out.append(float(loss))
+    if graphed:
+        assert stepper.replays == len(batches) and len(stepper.graphs) == 2
+    return out, [p.detach().clone() for p in model.parameters()]
+
+
+@pytest.mark.gpu
+def test_graphed_step_follows_eager_trajectory():
+    if not torch.cuda.is_available():
+        pytest.skip("no CUDA device")
+    pkg("_lib")._state["lib"] = None
+    syn = pkg("synthetic")
+    a = {k: (v.cuda() if torch.is_tensor(v) else v) for k, v in syn.oc20_batch(2, seed=5).items()}
+    b = {k: (v.cuda() if torch.is_tensor(v) else v) for k, v in syn.oc20_batch(3, seed=6).items()}
+    batches = [a, a, b, a, b]
+    l0, p0 = _run(False, batches)
+    l1, p1 = _run(True, batches)
+    assert max(abs(x - y) / abs(x) for x, y in zip(l0, l1)) < 1e-5, (l0, l1)
+    worst = max(float((x - y).abs().max() / (x.abs().max() + 1e-12)) for x, y in zip(p0, p1))
+    assert worst < 1e-4, worst
+    # the same trajectory on the exact FFMA engine: catches host-side caches that go stale across optimizer updates
+    # (fused AdamW does not bump Tensor._version) -- several steps, not just one
+    try:
+        l2, _ = _run(False, batches, mode="fp32")
+    finally:
+        pkg("ops").set_gemm_mode(pkg("ops").DEFAULT_GEMM_MODE)
+    assert max(abs(x - y) / abs(x) for x, y in zip(l0, l2)) < 1e-4, (l0, l2)
