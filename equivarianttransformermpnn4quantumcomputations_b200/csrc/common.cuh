@@ -62,9 +62,12 @@ __device__ __forceinline__ float eqv2_warp_max(float v) {
 // offset of the (2l+1)x(2l+1) block of degree l inside a packed block-diagonal Wigner row
 __host__ __device__ __forceinline__ int eqv2_wig_off(int l) { return l * (4 * l * l - 1) / 3; }
 
-// Running max |v| of everything a launch writes (for the f16x3 GEMM engine's operand scale, csrc/gemm_f16.cu): block
-// reduction, then ONE conditional atomic per block -- same-address atomics serialise, so a block whose maximum does not
-// raise the running value only reads it.  Every thread of the block must call (contains __syncthreads).
+// Running max |v| of everything a launch writes (the f16x3 GEMM engine's operand scale, csrc/gemm_f16.cu).  The slot is
+// EQV2_ABSMAX_SLOTS floats (zero-initialised by the caller); the tensor's maximum is the maximum over the slots.
+// Block reduction, then ONE fire-and-forget atomic per block, spread over the slots by block index: same-address atomics
+// serialise in L2, and waiting for a read of the running value at the tail of every (short) CTA cost 20-28 % in the
+// edge-parallel rotate kernels.  Every thread of the block must call (contains __syncthreads).
+#define EQV2_ABSMAX_SLOTS 64
 __device__ __forceinline__ void eqv2_commit_absmax(float m, float* slot) {
   __shared__ float eqv2_absmax_red[32];
   m = eqv2_warp_max(m);
@@ -73,7 +76,15 @@ __device__ __forceinline__ void eqv2_commit_absmax(float m, float* slot) {
   if (threadIdx.x == 0) {
     const int nw = (blockDim.x + 31) >> 5;
     for (int i = 1; i < nw; ++i) m = fmaxf(m, eqv2_absmax_red[i]);
-    const unsigned bits = __float_as_uint(m);           // non-negative floats order like their bit patterns
-    if (bits > *reinterpret_cast<volatile unsigned*>(slot)) atomicMax(reinterpret_cast<unsigned*>(slot), bits);
+    // non-negative floats order like their bit patterns
+    if (m > 0.f) atomicMax(reinterpret_cast<unsigned*>(slot) + (blockIdx.x & (EQV2_ABSMAX_SLOTS - 1)), __float_as_uint(m));
   }
+}
+// max over the slots, computed by a full warp (every lane returns it)
+__device__ __forceinline__ float eqv2_read_absmax(const float* slot) {
+  const int lane = threadIdx.x & 31;
+  float m = 0.f;
+#pragma unroll
+  for (int i = 0; i < EQV2_ABSMAX_SLOTS / 32; ++i) m = fmaxf(m, slot[lane + 32 * i]);
+  return eqv2_warp_max(m);
 }

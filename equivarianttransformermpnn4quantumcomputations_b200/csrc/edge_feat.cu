@@ -122,13 +122,25 @@ __global__ void ln_silu_bwd_kernel(const float* __restrict__ x, const float* __r
       if (i < width) gx[r * width + i] = rstd * (dxh[k] - s1 - xh[k] * s2);
     }
   }
+  // block-level sum of the 8 warps' partial weight / bias gradients first: one atomic per (block, column) instead of
+  // one per (warp, column) -- same-address atomics serialise in L2
+  __shared__ float sred[2][8][32 * LN_PL];
+  const int wib = threadIdx.x >> 5;
 #pragma unroll
   for (int k = 0; k < LN_PL; ++k) {
-    const int i = lane + 32 * k;
-    if (i < width) {
-      atomicAdd(&gw[i], aw[k]);
-      atomicAdd(&gb[i], ab[k]);
+    sred[0][wib][lane + 32 * k] = aw[k];
+    sred[1][wib][lane + 32 * k] = ab[k];
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < width; i += blockDim.x) {
+    float sw_ = 0.f, sb_ = 0.f;
+#pragma unroll
+    for (int q = 0; q < 8; ++q) {
+      sw_ += sred[0][q][i];
+      sb_ += sred[1][q][i];
     }
+    atomicAdd(&gw[i], sw_);
+    atomicAdd(&gb[i], sb_);
   }
 }
 
@@ -286,7 +298,7 @@ extern "C" int eqv2_ln_silu_bwd(const float* x, const float* w, const float* b, 
   if (rows == 0) return 0;
   EQV2_REQUIRE(width > 0 && width <= 32 * LN_PL, "ln_silu_bwd: width %d > %d", width, 32 * LN_PL);
   long long blocks = (rows * 32 + 255) / 256;
-  if (blocks > 148 * 8) blocks = 148 * 8;
+  if (blocks > 148 * 4) blocks = 148 * 4;
   EQV2_LAUNCH(ln_silu_bwd_kernel, dim3((unsigned)blocks), dim3(256), 0, stream, x, w, b, gy, gx, gw, gb, rows, width, eps);
   EQV2_CHECK_LAUNCH("eqv2_ln_silu_bwd");
   return 0;

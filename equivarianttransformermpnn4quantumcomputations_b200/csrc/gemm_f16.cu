@@ -341,8 +341,8 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) gemm_f16_kernel(const __grid_c
       }
       // ---- epilogue (overlaps the next tile's main loop: TMEM is already released) ----
       float sa, ia, sb, ib;
-      scale_of(__ldg(G.a_absmax), sa, ia);
-      scale_of(__ldg(G.b_absmax), sb, ib);
+      scale_of(eqv2_read_absmax(G.a_absmax), sa, ia);
+      scale_of(eqv2_read_absmax(G.b_absmax), sb, ib);
       const int row = W.m0 + q * 32 + lane;
       const bool atomic = P.split_k > 1;
       if (row < G.M) {
@@ -443,7 +443,8 @@ __global__ void __launch_bounds__(256) absmax_kernel(const __grid_constant__ Spl
 #pragma unroll
     for (int o = 4; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffu, m, o));
     // non-negative floats order like their bit patterns; +inf is kept (the split then uses scale 1)
-    if (threadIdx.x == 0) atomicMax(reinterpret_cast<unsigned int*>(T.absmax), __float_as_uint(m));
+    if (threadIdx.x == 0 && m > 0.f)
+      atomicMax(reinterpret_cast<unsigned int*>(T.absmax) + (blockIdx.x & (EQV2_ABSMAX_SLOTS - 1)), __float_as_uint(m));
   }
 }
 
@@ -451,7 +452,7 @@ __global__ void __launch_bounds__(256) split_kernel(const __grid_constant__ Spli
   const SplitItem& T = find_item(P, blockIdx.x);
   const int lb = blockIdx.x - T.block_start;
   float s, inv;
-  scale_of(*T.absmax, s, inv);
+  scale_of(eqv2_read_absmax(T.absmax), s, inv);
   const unsigned gpr = (unsigned)(T.cols_pad >> 3);                      // 8-element groups per padded row
   const long long ngroups = T.rows_pad * (long long)gpr;
   const long long plane = T.rows_pad * T.cols_pad;
@@ -562,7 +563,7 @@ extern "C" int eqv2_split_f16(const eqv2_split_desc* descs, int n, void* stream)
     blocks += (int)nb;
     if (!d.absmax_given) {
       need_pass = true;
-      cudaError_t e = cudaMemsetAsync(d.absmax, 0, sizeof(float), (cudaStream_t)stream);
+      cudaError_t e = cudaMemsetAsync(d.absmax, 0, EQV2_ABSMAX_SLOTS * sizeof(float), (cudaStream_t)stream);
       EQV2_REQUIRE(e == cudaSuccess, "eqv2_split_f16: memset failed: %s", cudaGetErrorString(e));
     }
   }

@@ -54,6 +54,13 @@ __host__ __device__ constexpr int rslot(int l, int am) {
   for (int j = 1; j < am; ++j) base += (L - j + 1);
   return base + (l - am);
 }
+// number of radial-weight slots = number of (l, |m|) pairs with |m| <= min(l, M)
+template <int L, int M>
+__host__ __device__ constexpr int nslots() {
+  int n = L + 1;
+  for (int j = 1; j <= M; ++j) n += (L - j + 1);
+  return n;
+}
 __host__ __device__ constexpr float rescale_l(int l, int mmax) {
   // sqrt((2l+1)/(2 mmax+1)) for l > mmax, evaluated at run time where needed (sqrtf is not constexpr)
   return (l > mmax) ? (float)(2 * l + 1) / (float)(2 * mmax + 1) : 1.0f;
@@ -109,6 +116,22 @@ __device__ __forceinline__ void for_each_degree(F&& f) {
   if constexpr (LDEG < L) for_each_degree<LDEG + 1, L, M>(static_cast<F&&>(f));
 }
 
+// compile-time loop i = I .. N-1 (register arrays indexed by i stay in registers)
+template <int I, int N, typename F>
+__device__ __forceinline__ void static_for(F&& f) {
+  if constexpr (I < N) {
+    f(std::integral_constant<int, I>{});
+    static_for<I + 1, N>(static_cast<F&&>(f));
+  }
+}
+
+// column `n` values, `stride` apart, into a register array
+template <int N>
+__device__ __forceinline__ void load_column(float (&v)[N], const float* __restrict__ p, long long stride) {
+#pragma unroll
+  for (int i = 0; i < N; ++i) v[i] = __ldg(p + (long long)i * stride);
+}
+
 // ------------------------------------------------------------------------------------------
 template <int L, int M>
 __global__ void __launch_bounds__(256)
@@ -117,33 +140,39 @@ gather_rotate_fwd_kernel(const float* __restrict__ x, const long long* __restric
                          const float* __restrict__ rad, float* __restrict__ out, int C, int Kr, int nrad,
                          float* __restrict__ absmax) {
   constexpr int K = Dim<L>::K, WS = Dim<L>::WS;
+  constexpr int NS = nslots<L, M>();
   __shared__ __align__(16) float sw[wpad_off(L + 1)];
   const long long e = blockIdx.x;
-  stage_wigner<L>(sw, wig + e * WS, threadIdx.x, blockDim.x);
-  __syncthreads();
   const long long ns_ = src[e], nd_ = dst[e];
   const int C2 = 2 * C;
   float amax = 0.f;
-  for (int ch = threadIdx.x; ch < C2; ch += blockDim.x) {
-    const long long node = (ch < C) ? ns_ : nd_;
-    const int c = (ch < C) ? ch : ch - C;
-    const float* xp = x + node * (long long)K * C + c;
-    float xc[K];
+  // The x column and all radial weights of this (edge, channel) are requested BEFORE the Wigner blocks are staged:
+  // the barrier then waits on one memory latency, not on wigner-then-x-then-rad in sequence (ncu r01: long_scoreboard
+  // 12.5 and barrier 2.8 stall cycles per issue with one short-lived CTA per edge).
+  float xc[K], rv[NS];
+  const int ch = blockIdx.y * blockDim.x + threadIdx.x;       // channel chunks of blockDim.x are a grid dimension
+  if (ch < C2) {
+    load_column<K>(xc, x + ((ch < C) ? ns_ : nd_) * (long long)K * C + ((ch < C) ? ch : ch - C), C);
+    if (rad) load_column<NS>(rv, rad + e * (long long)nrad + ch, C2);
+  }
+  if (!rad) {
 #pragma unroll
-    for (int k = 0; k < K; ++k) xc[k] = __ldg(xp + (long long)k * C);
-    const float* rp = rad ? rad + e * (long long)nrad + ch : nullptr;
+    for (int i = 0; i < NS; ++i) rv[i] = 1.0f;
+  }
+  stage_wigner<L>(sw, wig + e * WS, threadIdx.x, blockDim.x);
+  __syncthreads();
+  if (ch < C2) {
     float* op = out + e * (long long)Kr * C2 + ch;
     for_each_degree<0, L, M>([&](auto ld) {
       constexpr int l = decltype(ld)::value;
       constexpr int mm = l < M ? l : M;
-#pragma unroll
-      for (int m = -mm; m <= mm; ++m) {
-        float acc = row_dot<l>(sw, l + m, xc + l * l);
-        const int p = mpos<L, M>(l, m);
-        if (rp) acc *= __ldg(rp + (long long)rslot<L, M>(l, m < 0 ? -m : m) * C2);
+      static_for<0, 2 * mm + 1>([&](auto mc) {
+        constexpr int m = decltype(mc)::value - mm;
+        constexpr int p = mpos<L, M>(l, m), sl = rslot<L, M>(l, m < 0 ? -m : m);
+        const float acc = row_dot<l>(sw, l + m, xc + l * l) * rv[sl];
         op[(long long)p * C2] = acc;
         amax = fmaxf(amax, fabsf(acc));
-      }
+      });
     });
   }
   if (absmax != nullptr) eqv2_commit_absmax(amax, absmax);
@@ -161,30 +190,32 @@ gather_rotate_drad_kernel(const float* __restrict__ x, const long long* __restri
   constexpr int K = Dim<L>::K, WS = Dim<L>::WS;
   __shared__ __align__(16) float sw[wpad_off(L + 1)];
   const long long e = blockIdx.x;
-  stage_wigner<L>(sw, wig + e * WS, threadIdx.x, blockDim.x);
-  __syncthreads();
   const long long ns_ = src[e], nd_ = dst[e];
   const int C2 = 2 * C;
   float amax = 0.f;
-  for (int ch = threadIdx.x; ch < C2; ch += blockDim.x) {
-    const long long node = (ch < C) ? ns_ : nd_;
-    const int c = (ch < C) ? ch : ch - C;
-    const float* xp = x + node * (long long)K * C + c;
-    float xc[K];
-#pragma unroll
-    for (int k = 0; k < K; ++k) xc[k] = __ldg(xp + (long long)k * C);
-    const float* gp = dA + e * (long long)Kr * C2 + ch;
+  // x and dA columns first, Wigner staging + barrier second (see gather_rotate_fwd_kernel)
+  constexpr int KR = mpos<L, M>(L, -M) + 1;      // Kr consecutive m-primary rows
+  float xc[K], gv[KR];
+  const int ch = blockIdx.y * blockDim.x + threadIdx.x;
+  if (ch < C2) {
+    load_column<K>(xc, x + ((ch < C) ? ns_ : nd_) * (long long)K * C + ((ch < C) ? ch : ch - C), C);
+    load_column<KR>(gv, dA + e * (long long)Kr * C2 + ch, C2);
+  }
+  stage_wigner<L>(sw, wig + e * WS, threadIdx.x, blockDim.x);
+  __syncthreads();
+  if (ch < C2) {
     float* drp = drad + e * (long long)nrad + ch;
     for_each_degree<0, L, M>([&](auto ld) {
       constexpr int l = decltype(ld)::value;
       constexpr int mm = l < M ? l : M;
-#pragma unroll
-      for (int m = 0; m <= mm; ++m) {
-        float d = __ldg(gp + (long long)mpos<L, M>(l, m) * C2) * row_dot<l>(sw, l + m, xc + l * l);
-        if (m > 0) d = fmaf(__ldg(gp + (long long)mpos<L, M>(l, -m) * C2), row_dot<l>(sw, l - m, xc + l * l), d);
-        drp[(long long)rslot<L, M>(l, m) * C2] = d;
+      static_for<0, mm + 1>([&](auto mc) {
+        constexpr int m = decltype(mc)::value;
+        constexpr int pp = mpos<L, M>(l, m), pm = mpos<L, M>(l, -m), sl = rslot<L, M>(l, m);
+        float d = gv[pp] * row_dot<l>(sw, l + m, xc + l * l);
+        if constexpr (m > 0) d = fmaf(gv[pm], row_dot<l>(sw, l - m, xc + l * l), d);
+        drp[(long long)sl * C2] = d;
         amax = fmaxf(amax, fabsf(d));
-      }
+      });
     });
   }
   if (absmax != nullptr) eqv2_commit_absmax(amax, absmax);
@@ -319,38 +350,48 @@ rotinv_reduce_bwd_kernel(const float* __restrict__ dout, const float* __restrict
   constexpr int K = Dim<L>::K, WS = Dim<L>::WS;
   __shared__ __align__(16) float sw[wpad_off(L + 1)];
   EQV2_DYN_SMEM(float, spart);   // [blockDim.x] partial d(alpha)
+  constexpr int KR = mpos<L, M>(L, -M) + 1;
   const long long e = blockIdx.x;
-  stage_wigner<L>(sw, wig + e * WS, threadIdx.x, blockDim.x);
-  __syncthreads();
   const int c = threadIdx.x;
   const bool live = c < Cv;
   const int vch = heads > 0 ? Cv / heads : Cv;
   const long long node = dst[e];
   float da = 0.f, amax = 0.f;
+  // inputs first (node gradient column, attention weight, value column), Wigner staging + barrier second: one exposed
+  // memory latency per CTA instead of three in sequence
+  float g[K], vv[KR];
+  float a = 1.0f;
   if (live) {
-    float g[K];
     for_each_degree<0, L, M>([&](auto ld) {
       constexpr int l = decltype(ld)::value;
       const float f = (l > M ? sqrtf(rescale_l(l, M)) : 1.0f) * scale;
 #pragma unroll
       for (int j = 0; j < 2 * l + 1; ++j) g[l * l + j] = __ldg(dout + (node * K + l * l + j) * (long long)Cv + c) * f;
     });
-    const float a = alpha ? __ldg(alpha + e * heads + c / vch) : 1.0f;
-    const float* vp = val + e * val_estride + c;
+    if (alpha) {
+      a = __ldg(alpha + e * heads + c / vch);
+      const float* vp = val + e * val_estride + c;
+#pragma unroll
+      for (int p = 0; p < KR; ++p) vv[p] = (p < rows_used) ? __ldg(vp + (long long)p * Cv) : 0.f;
+    }
+  }
+  stage_wigner<L>(sw, wig + e * WS, threadIdx.x, blockDim.x);
+  __syncthreads();
+  if (live) {
     float* dvp = dval + e * val_estride + c;
     for_each_degree<0, L, M>([&](auto ld) {
       constexpr int l = decltype(ld)::value;
       constexpr int mm = l < M ? l : M;
-#pragma unroll
-      for (int m = -mm; m <= mm; ++m) {
-        const int p = mpos<L, M>(l, m);
+      static_for<0, 2 * mm + 1>([&](auto mc) {
+        constexpr int m = decltype(mc)::value - mm;
+        constexpr int p = mpos<L, M>(l, m);
         if (p < rows_used) {
           const float t = row_dot<l>(sw, l + m, g + l * l);
-          if (alpha) da = fmaf(t, __ldg(vp + (long long)p * Cv), da);
+          if (alpha) da = fmaf(t, vv[p], da);
           dvp[(long long)p * Cv] = t * a;
           amax = fmaxf(amax, fabsf(t * a));
         }
-      }
+      });
     });
   }
   if (dalpha) {
@@ -388,7 +429,7 @@ extern "C" int eqv2_gather_rotate_fwd(const float* x, const long long* src, cons
 #define X(L_, M_)                                                                                              \
   if (lmax == L_ && mmax == M_) {                                                                              \
     auto kfn = gather_rotate_fwd_kernel<L_, M_>;                                                                                    \
-    EQV2_LAUNCH(kfn, dim3((unsigned)E), dim3(threads), 0, stream, x, src, dst, wig, rad, out, C, Kr, nrad, absmax); \
+    EQV2_LAUNCH(kfn, dim3((unsigned)E, (2 * C + threads - 1) / threads), dim3(threads), 0, stream, x, src, dst, wig, rad, out, C, Kr, nrad, absmax); \
     EQV2_CHECK_LAUNCH("eqv2_gather_rotate_fwd");                                                               \
     return 0;                                                                                                  \
   }
@@ -425,7 +466,7 @@ extern "C" int eqv2_gather_rotate_drad(const float* x, const long long* src, con
 #define X(L_, M_)                                                                                              \
   if (lmax == L_ && mmax == M_) {                                                                              \
     auto kfn = gather_rotate_drad_kernel<L_, M_>;                                                              \
-    EQV2_LAUNCH(kfn, dim3((unsigned)E), dim3(threads), 0, stream, x, src, dst, wig, dA, drad, C, Kr, nrad, absmax);     \
+    EQV2_LAUNCH(kfn, dim3((unsigned)E, (2 * C + threads - 1) / threads), dim3(threads), 0, stream, x, src, dst, wig, dA, drad, C, Kr, nrad, absmax);     \
     EQV2_CHECK_LAUNCH("eqv2_gather_rotate_drad");                                                              \
     return 0;                                                                                                  \
   }

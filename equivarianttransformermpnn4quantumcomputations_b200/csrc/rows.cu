@@ -26,27 +26,40 @@ __global__ void seg_colsum_partial_kernel(const float* __restrict__ src, long lo
   const int c = blockIdx.x * blockDim.x + threadIdx.x;
   if (c >= C) return;
   const long long beg = rowptr != nullptr ? rowptr[v] : 0, end = rowptr != nullptr ? rowptr[v + 1] : rows;
-  float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;          // 4 independent chains hide the load latency; fixed order
+  // 8 independent chains keep 8 loads in flight per thread (the kernel is latency-bound otherwise); fixed order
+  float a[8];
+#pragma unroll
+  for (int u = 0; u < 8; ++u) a[u] = 0.f;
   long long i = beg + s;
-  for (; i + 3ll * S < end; i += 4ll * S) {
-    const long long r0 = perm != nullptr ? perm[i] : i, r1 = perm != nullptr ? perm[i + S] : i + S;
-    const long long r2 = perm != nullptr ? perm[i + 2ll * S] : i + 2ll * S, r3 = perm != nullptr ? perm[i + 3ll * S] : i + 3ll * S;
-    a0 += __ldg(src + r0 * ld + c);
-    a1 += __ldg(src + r1 * ld + c);
-    a2 += __ldg(src + r2 * ld + c);
-    a3 += __ldg(src + r3 * ld + c);
+  for (; i + 7ll * S < end; i += 8ll * S) {
+    long long r[8];
+#pragma unroll
+    for (int u = 0; u < 8; ++u) r[u] = perm != nullptr ? (long long)perm[i + (long long)u * S] : i + (long long)u * S;
+#pragma unroll
+    for (int u = 0; u < 8; ++u) a[u] += __ldg(src + r[u] * ld + c);
   }
-  for (; i < end; i += S) a0 += __ldg(src + (perm != nullptr ? (long long)perm[i] : i) * ld + c);
+  for (; i < end; i += S) a[0] += __ldg(src + (perm != nullptr ? (long long)perm[i] : i) * ld + c);
+  const float a0 = a[0] + a[4], a1 = a[1] + a[5], a2 = a[2] + a[6], a3 = a[3] + a[7];
   partial[((long long)v * S + s) * C + c] = (a0 + a1) + (a2 + a3);
 }
 
+// blockDim = (32 columns, 8 split lanes): lane y adds splits y, y + 8, ... (fixed order), the 8 partial sums meet in
+// shared memory and are added in order
 __global__ void seg_colsum_final_kernel(const float* __restrict__ partial, int C, int S, float* __restrict__ out) {
+  __shared__ float red[8][33];
   const int v = blockIdx.y;
-  const int c = blockIdx.x * blockDim.x + threadIdx.x;
-  if (c >= C) return;
+  const int c = blockIdx.x * 32 + threadIdx.x;
   float a = 0.f;
-  for (int s = 0; s < S; ++s) a += partial[((long long)v * S + s) * C + c];
-  out[(long long)v * C + c] = a;
+  if (c < C)
+    for (int s = threadIdx.y; s < S; s += 8) a += partial[((long long)v * S + s) * C + c];
+  red[threadIdx.y][threadIdx.x] = a;
+  __syncthreads();
+  if (threadIdx.y == 0 && c < C) {
+    float t = 0.f;
+#pragma unroll
+    for (int q = 0; q < 8; ++q) t += red[q][threadIdx.x];
+    out[(long long)v * C + c] = t;
+  }
 }
 
 }  // namespace
@@ -67,7 +80,7 @@ extern "C" int eqv2_seg_colsum(const float* src, long long ld, const int* rowptr
   const int tx = 128, bx = (C + tx - 1) / tx;
   EQV2_LAUNCH(seg_colsum_partial_kernel, dim3(bx, S, V), dim3(tx), 0, stream, src, ld, rowptr, perm, rows, C, S, partial);
   EQV2_CHECK_LAUNCH("eqv2_seg_colsum (partial)");
-  EQV2_LAUNCH(seg_colsum_final_kernel, dim3(bx, V), dim3(tx), 0, stream, partial, C, S, out);
+  EQV2_LAUNCH(seg_colsum_final_kernel, dim3((C + 31) / 32, V), dim3(32, 8), 0, stream, partial, C, S, out);
   EQV2_CHECK_LAUNCH("eqv2_seg_colsum (final)");
   return 0;
 }

@@ -369,7 +369,7 @@ class EmbedRowsBwdFn(torch.autograd.Function):
         ctx.save_for_backward(idx)
         ctx.csr = csr
         # few element types occur in a batch -> few non-empty segments: split each into many row groups
-        S = max(1, min(128, int(g.shape[0]) // 32))
+        S = max(1, min(256, int(g.shape[0]) // 32))
         return _seg_colsum(g, g.shape[1], 0, g.shape[0], g.shape[1], V, rowptr, perm, S)
 
     @staticmethod
@@ -393,7 +393,7 @@ class ColsumFn(torch.autograd.Function):
         rows = int(X.shape[0])
         if rows == 0:
             return torch.zeros(n, dtype=_F32, device=X.device)
-        S = max(1, min(rows // 16, -(-592 // ((n + 127) // 128))))       # ~4 CTAs per SM
+        S = max(1, min(rows // 16, -(-2368 // ((n + 127) // 128))))      # ~16 CTAs of 128 threads per SM
         return _seg_colsum(X, X.shape[1], off, rows, n, 1, None, None, S).view(n)
 
     @staticmethod
@@ -515,6 +515,9 @@ def _tc_ok(d):
 
 
 # ---- f16x3 engine: operand splits --------------------------------------------------------------------------
+ABSMAX_SLOTS = 64        # EQV2_ABSMAX_SLOTS of csrc/common.cuh: a tensor's max |v| is the maximum over this many floats
+
+
 class SplitF16:
     """Scaled fp16 hi/lo planes [2, rows, cols_pad] of a contiguous fp32 matrix + its absolute maximum (device)."""
     __slots__ = ("buf", "absmax", "rows", "cols", "cols_pad", "slab_k", "version")
@@ -523,7 +526,7 @@ class SplitF16:
         self.rows, self.cols, self.slab_k = src.rows, src.cols, src.slab_k
         self.cols_pad = (self.cols + 63) // 64 * 64
         self.buf = torch.empty(2, self.rows, self.cols_pad, dtype=torch.float16, device=src.t.device)
-        self.absmax = torch.empty(1, dtype=_F32, device=src.t.device)
+        self.absmax = torch.empty(ABSMAX_SLOTS, dtype=_F32, device=src.t.device)
         self.version = src.t._version
 
     @property
@@ -536,7 +539,7 @@ _ABSMAX = {}             # storage pointer -> (weakref(tensor), slot, version): 
 
 def _absmax_slot(device):
     """Zero-initialised device float for a producer kernel's `absmax` output (only allocated in f16x3 mode)."""
-    return torch.zeros(1, dtype=_F32, device=device) if _GEMM_MODE["mode"] == "f16x3" else None
+    return torch.zeros(ABSMAX_SLOTS, dtype=_F32, device=device) if _GEMM_MODE["mode"] == "f16x3" else None
 
 
 def _register_absmax(t, slot):
@@ -634,8 +637,9 @@ def _split_of(splits, src):
 
 def _f16_ok(descs):
     """Should the f16x3 engine take this launch?  Measured (profiles/): the persistent TMA kernel beats the FFMA engine
-    and the in-kernel-split tf32 engine from ~16 M multiply-adds per launch, operand splits included."""
-    return all(_f16_addressable(d) for d in descs) and sum(d.M * d.N * d.K for d in descs) >= (1 << 24)
+    and the in-kernel-split tf32 engine from ~4 M multiply-adds per launch, operand splits included (a 640 x 128 x 128
+    node-level linear takes 69 us on the FFMA engine: 5 CTAs)."""
+    return all(_f16_addressable(d) for d in descs) and sum(d.M * d.N * d.K for d in descs) >= (1 << 22)
 
 
 def _f16_addressable(d):
@@ -666,6 +670,9 @@ def _run_gemm_f16(descs, split_k, flops, nbytes):
     return splits
 
 
+_GEMM_LOG = None          # diagnostics: set to a list to record the launches the f16x3 engine declines
+
+
 def run_gemm(descs, split_k=1):
     """-> {OperandSrc.key: SplitF16} of the operand splits the f16x3 engine used ({} on the other engines)."""
     n = len(descs)
@@ -676,6 +683,8 @@ def run_gemm(descs, split_k=1):
     if mode == "f16x3":
         if _f16_ok(descs):
             return _run_gemm_f16(descs, split_k, flops, nbytes)
+        if _GEMM_LOG is not None:
+            _GEMM_LOG.append([(d.M, d.N, d.K, d.transA, d.transB, _f16_addressable(d)) for d in descs])
         mode = "tf32x3"
     arr = (_lib.GemmDesc * n)(*descs)
     if mode != "fp32" and all(_tc_ok(d) for d in descs):

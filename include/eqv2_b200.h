@@ -52,7 +52,8 @@ int eqv2_gemm_tc(const eqv2_gemm_desc* descs, int ngroups, int split_k, int mode
  * fp16 passes over PRE-SPLIT operands.
  *   eqv2_split_f16: for each contiguous fp32 tensor [rows, cols] write the planes hi = fp16(s v), lo = fp16(s v - hi)
  *     into dst[2][rows_pad][cols_pad] (fp16, zero padding; cols_pad % 64 == 0) with s the power of two that puts
- *     max |s v| into [2^14, 2^15); *absmax receives max |v| (the GEMM derives 1/s from it on the device).
+ *     max |s v| into [2^14, 2^15); absmax[64] receives max |v| (spread over 64 slots; the GEMM derives 1/s from their
+ *     maximum on the device).
  *   eqv2_gemm_f16: A / B point at the hi plane of the operand's sub-block (lo plane `*_plane` elements further,
  *     leading dimension `*_ld`; both multiples of 8 elements, pointers 16-byte aligned).
  *     transA = 0: A(m,k) at A[m*a_ld + k]; 1: A[k*a_ld + m].  transB = 1: B(k,n) at B[n*b_ld + k]; 0: B[k*b_ld + n].
@@ -61,7 +62,7 @@ int eqv2_gemm_tc(const eqv2_gemm_desc* descs, int ngroups, int split_k, int mode
 typedef struct {
   const float* src;
   void* dst;       /* fp16 [2][rows_pad][cols_pad] */
-  float* absmax;   /* one float, written by the call */
+  float* absmax;   /* EQV2_ABSMAX_SLOTS (64) floats whose maximum is max |v| of src; written by the call */
   long long rows, cols, rows_pad, cols_pad;
   int absmax_given; /* 1: *absmax already holds max |v| of src (written by the producing kernel): skip the reduction pass */
   int slab_k;      /* 0: plain.  > 0: src is a node tensor [rows / slab_k, slab_k = (lmax+1)^2, cols] (so3.py:76-88) and dst
@@ -94,8 +95,8 @@ int eqv2_gather_rotate_fwd(const float* x /*[N,K,C]*/, const long long* src, con
                            const int* rad_slot /*[Kr]*/, long long E, int C, int lmax, int mmax, int Kr,
                            int nrad, float* absmax /*or NULL*/, void* stream);
 
-/* `absmax` (gather_rotate_fwd / _drad, rotinv_reduce_bwd): optional device float, zero-initialised by the caller, that
- * receives max |v| over everything the launch writes -- the operand scale the f16x3 GEMM engine needs for this tensor,
+/* `absmax` (gather_rotate_fwd / _drad, rotinv_reduce_bwd): optional device array of 64 floats, zero-initialised by the
+ * caller, whose maximum becomes max |v| over everything the launch writes -- the operand scale the f16x3 GEMM engine needs for this tensor,
  * produced for free instead of by a separate pass (eqv2_split_desc.absmax_given). */
 /* backward of the gather/rotate, split by its two outputs:
  *   dx   [N,K,C]   = sum over the node's outgoing (src half) and incoming (dst half) edges of W_e^T (dA * rad)

@@ -32,13 +32,22 @@ def step():
 for _ in range(3):
     step()
 torch.cuda.synchronize()
+from equivarianttransformermpnn4quantumcomputations_b200 import ops
+ops._GEMM_LOG = []
+step()
+torch.cuda.synchronize()
+seen = collections.Counter(str(x) for x in ops._GEMM_LOG)
+ops._GEMM_LOG = None
+print("GEMM launches declined by the f16x3 engine (M, N, K, tA, tB, addressable):")
+for k, c in seen.most_common(20):
+    print(f"  {c:4d} x {k}")
 with profile(activities=[ProfilerActivity.CUDA, ProfilerActivity.CPU]) as prof:
     step()
     torch.cuda.synchronize()
 agg = collections.defaultdict(lambda: [0, 0.0])
 for ev in prof.events():
     if ev.device_type == torch.autograd.DeviceType.CUDA:
-        n = re.sub(r"\(.*", "", ev.name).replace("(anonymous namespace)::", "").replace("void ", "").replace("at::native::", "")
+        n = re.sub(r"\(.*", "", ev.name.replace("(anonymous namespace)::", "")).replace("void ", "").replace("at::native::", "")
         agg[n[:100]][0] += 1
         agg[n[:100]][1] += ev.device_time
 tot = sum(v[1] for v in agg.values())
