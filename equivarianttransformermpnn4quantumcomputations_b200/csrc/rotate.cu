@@ -221,19 +221,32 @@ gather_rotate_drad_kernel(const float* __restrict__ x, const long long* __restri
   if (absmax != nullptr) eqv2_commit_absmax(amax, absmax);
 }
 
-// d(x): node-centric and deterministic.  CTA = one node; thread group h (0: edges where the node is the source,
-// 1: where it is the destination) walks its CSR segment; the two partial sums meet in shared memory.
+// Node-centric kernels (deterministic, no atomics).  CTA = (node, slice of CW channels), 256 threads = G groups of CW
+// threads; every group walks its share of the node's edges, one edge per iteration:
+//   * the edge's data columns (dA and radial weights, or values and attention weight) are requested first and the
+//     Wigner blocks staged second, so an iteration exposes one memory latency instead of one per degree
+//     (ncu r01: long_scoreboard 6.7 / 25 stall cycles per issue, 640 CTAs of serial edge walks at 12-32 % of HBM peak);
+//   * the G partial sums meet in shared memory in group order.
+constexpr int NODE_THREADS = 256;
+constexpr int NODE_MAX_GROUPS = 8;
+
+// d(x): groups with even index walk the edges where the node is the source (first C columns of dA), odd groups the
+// edges where it is the destination (last C columns); sub-group g >> 1 of G / 2 takes every (G/2)-th edge.
 template <int L, int M>
-__global__ void __launch_bounds__(256, 2)
+__global__ void __launch_bounds__(NODE_THREADS, 2)
 gather_rotate_dx_kernel(const float* __restrict__ wig, const float* __restrict__ rad, const float* __restrict__ dA,
                         const int* __restrict__ rowptr_src, const int* __restrict__ perm_src,
                         const int* __restrict__ rowptr_dst, const int* __restrict__ perm_dst, float* __restrict__ dx,
-                        int C, int CP /* C rounded to 32 */, int Kr, int nrad) {
+                        int C, int CW /* channels per CTA: 32 or 64 */, int Kr, int nrad) {
   constexpr int K = Dim<L>::K, WS = Dim<L>::WS, WP = wpad_off(L + 1);
-  __shared__ __align__(16) float sw[2][WP];
-  EQV2_DYN_SMEM(float, sred);     // [K][CP]: partial dx of group 1
+  constexpr int KR = mpos<L, M>(L, -M) + 1, NS = nslots<L, M>();
+  __shared__ __align__(16) float sw[NODE_MAX_GROUPS][WP];
+  EQV2_DYN_SMEM(float, sred);     // [K][CW]
   const long long node = blockIdx.x;
-  const int half = threadIdx.x / CP, c = threadIdx.x % CP;
+  const int G = NODE_THREADS / CW;
+  const int grp = threadIdx.x / CW, ct = threadIdx.x % CW;
+  const int half = grp & 1, sub = grp >> 1, nsub = G >> 1;
+  const int c = blockIdx.y * CW + ct;
   const bool live = c < C;
   const int C2 = 2 * C;
   const int* rowptr = half ? rowptr_dst : rowptr_src;
@@ -245,97 +258,121 @@ gather_rotate_dx_kernel(const float* __restrict__ wig, const float* __restrict__
   float acc[K];
 #pragma unroll
   for (int k = 0; k < K; ++k) acc[k] = 0.f;
-  for (int it = 0; it < maxlen; ++it) {
-    __syncthreads();
+  for (int it = sub; it < maxlen + sub; it += nsub) {      // same trip count in every group (barriers inside)
     const bool has = it < len;
     long long e = 0;
+    float gv[KR], rv[NS];
     if (has) {
       e = perm[beg + it];
-      stage_wigner<L>(sw[half], wig + e * WS, c, CP);
+      if (live) {
+        load_column<KR>(gv, dA + e * (long long)Kr * C2 + ch, C2);
+        if (rad) load_column<NS>(rv, rad + e * (long long)nrad + ch, C2);
+      }
     }
+    __syncthreads();                                       // the previous iteration has finished reading sw
+    if (has) stage_wigner<L>(sw[grp], wig + e * WS, ct, CW);
     __syncthreads();
     if (!has || !live) continue;
-    const float* gp = dA + e * (long long)Kr * C2 + ch;
-    const float* rp = rad ? rad + e * (long long)nrad + ch : nullptr;
-    const float* w = sw[half];
+    const float* w = sw[grp];
     for_each_degree<0, L, M>([&](auto ld) {
       constexpr int l = decltype(ld)::value;
       constexpr int mm = l < M ? l : M;
-#pragma unroll
-      for (int m = 0; m <= mm; ++m) {
-        const float r = rp ? __ldg(rp + (long long)rslot<L, M>(l, m) * C2) : 1.0f;
-        row_axpy<l>(w, l + m, __ldg(gp + (long long)mpos<L, M>(l, m) * C2) * r, acc + l * l);
-        if (m > 0) row_axpy<l>(w, l - m, __ldg(gp + (long long)mpos<L, M>(l, -m) * C2) * r, acc + l * l);
-      }
+      static_for<0, mm + 1>([&](auto mc) {
+        constexpr int m = decltype(mc)::value;
+        constexpr int pp = mpos<L, M>(l, m), pm = mpos<L, M>(l, -m), sl = rslot<L, M>(l, m);
+        const float r = rad ? rv[sl] : 1.0f;
+        row_axpy<l>(w, l + m, gv[pp] * r, acc + l * l);
+        if constexpr (m > 0) row_axpy<l>(w, l - m, gv[pm] * r, acc + l * l);
+      });
     });
   }
-  __syncthreads();
-  if (half == 1 && live) {
+  for (int g = 1; g < G; ++g) {                            // acc(group 0) += acc(group g), in group order
+    __syncthreads();
+    if (grp == g && live) {
 #pragma unroll
-    for (int k = 0; k < K; ++k) sred[k * CP + c] = acc[k];
+      for (int k = 0; k < K; ++k) sred[k * CW + ct] = acc[k];
+    }
+    __syncthreads();
+    if (grp == 0 && live) {
+#pragma unroll
+      for (int k = 0; k < K; ++k) acc[k] += sred[k * CW + ct];
+    }
   }
-  __syncthreads();
-  if (half == 0 && live) {
+  if (grp == 0 && live) {
 #pragma unroll
-    for (int k = 0; k < K; ++k) dx[(node * K + k) * (long long)C + c] = acc[k] + sred[k * CP + c];
+    for (int k = 0; k < K; ++k) dx[(node * K + k) * (long long)C + c] = acc[k];
   }
 }
 
 // ------------------------------------------------------------------------------------------
-// CTA = one destination node; two thread groups take alternate edges of its segment
+// CTA = (destination node, channel slice); group g takes every G-th edge of the node's segment
 template <int L, int M>
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(NODE_THREADS, 2)
 rotinv_reduce_fwd_kernel(const float* __restrict__ val, const float* __restrict__ alpha, const float* __restrict__ wig,
                          const int* __restrict__ rowptr_dst, const int* __restrict__ perm_dst, float* __restrict__ out,
-                         int Cv, int CP, int rows_used, long long val_estride, int heads, float scale) {
+                         int Cv, int CW, int rows_used, long long val_estride, int heads, float scale) {
   constexpr int K = Dim<L>::K, WS = Dim<L>::WS, WP = wpad_off(L + 1);
-  __shared__ __align__(16) float sw[2][WP];
-  EQV2_DYN_SMEM(float, sred);     // [K][CP]
+  constexpr int KR = mpos<L, M>(L, -M) + 1;
+  __shared__ __align__(16) float sw[NODE_MAX_GROUPS][WP];
+  EQV2_DYN_SMEM(float, sred);     // [K][CW]
   const long long node = blockIdx.x;
-  const int grp = threadIdx.x / CP, c = threadIdx.x % CP;
+  const int G = NODE_THREADS / CW;
+  const int grp = threadIdx.x / CW, ct = threadIdx.x % CW;
+  const int c = blockIdx.y * CW + ct;
   const bool live = c < Cv;
   const int vch = heads > 0 ? Cv / heads : Cv;
   float acc[K];
 #pragma unroll
   for (int k = 0; k < K; ++k) acc[k] = 0.f;
   const int beg = rowptr_dst[node], end = rowptr_dst[node + 1];
-  for (int idx0 = beg; idx0 < end; idx0 += 2) {
+  for (int idx0 = beg; idx0 < end; idx0 += G) {
     const int idx = idx0 + grp;
     const bool has = idx < end;
     long long e = 0;
-    __syncthreads();
+    float vv[KR];
+    float a = 1.0f;
     if (has) {
       e = perm_dst[idx];
-      stage_wigner<L>(sw[grp], wig + e * WS, c, CP);
+      if (live) {
+        if (alpha) a = __ldg(alpha + e * heads + c / vch);
+        const float* vp = val + e * val_estride + c;
+#pragma unroll
+        for (int p = 0; p < KR; ++p) vv[p] = (p < rows_used) ? __ldg(vp + (long long)p * Cv) : 0.f;
+      }
     }
     __syncthreads();
+    if (has) stage_wigner<L>(sw[grp], wig + e * WS, ct, CW);
+    __syncthreads();
     if (!has || !live) continue;
-    const float a = alpha ? __ldg(alpha + e * heads + c / vch) : 1.0f;
-    const float* vp = val + e * val_estride + c;
     const float* w = sw[grp];
     for_each_degree<0, L, M>([&](auto ld) {
       constexpr int l = decltype(ld)::value;
       constexpr int mm = l < M ? l : M;
-#pragma unroll
-      for (int m = -mm; m <= mm; ++m) {
-        const int p = mpos<L, M>(l, m);
-        if (p < rows_used) row_axpy<l>(w, l + m, __ldg(vp + (long long)p * Cv) * a, acc + l * l);
-      }
+      static_for<0, 2 * mm + 1>([&](auto mc) {
+        constexpr int m = decltype(mc)::value - mm;
+        constexpr int p = mpos<L, M>(l, m);
+        if (p < rows_used) row_axpy<l>(w, l + m, vv[p] * a, acc + l * l);
+      });
     });
   }
-  __syncthreads();
-  if (grp == 1 && live) {
+  for (int g = 1; g < G; ++g) {
+    __syncthreads();
+    if (grp == g && live) {
 #pragma unroll
-    for (int k = 0; k < K; ++k) sred[k * CP + c] = acc[k];
+      for (int k = 0; k < K; ++k) sred[k * CW + ct] = acc[k];
+    }
+    __syncthreads();
+    if (grp == 0 && live) {
+#pragma unroll
+      for (int k = 0; k < K; ++k) acc[k] += sred[k * CW + ct];
+    }
   }
-  __syncthreads();
   if (grp == 0 && live) {
     for_each_degree<0, L, M>([&](auto ld) {
       constexpr int l = decltype(ld)::value;
       const float f = (l > M ? sqrtf(rescale_l(l, M)) : 1.0f) * scale;
 #pragma unroll
-      for (int j = 0; j < 2 * l + 1; ++j)
-        out[(node * K + l * l + j) * (long long)Cv + c] = (acc[l * l + j] + sred[(l * l + j) * CP + c]) * f;
+      for (int j = 0; j < 2 * l + 1; ++j) out[(node * K + l * l + j) * (long long)Cv + c] = acc[l * l + j] * f;
     });
   }
 }
@@ -442,13 +479,13 @@ extern "C" int eqv2_gather_rotate_dx(const float* wig, const float* rad, const f
                                      const int* perm_src, const int* rowptr_dst, const int* perm_dst, float* dx,
                                      long long N, int C, int lmax, int mmax, int Kr, int nrad, void* stream) {
   if (N == 0) return 0;
-  EQV2_REQUIRE(C > 0 && C <= 128, "gather_rotate_dx: C=%d out of range (1..128)", C);
-  const int CP = round32(C);
-  const size_t smem = (size_t)(lmax + 1) * (lmax + 1) * CP * sizeof(float);
+  EQV2_REQUIRE(C > 0, "gather_rotate_dx: C=%d out of range", C);
+  const int CW = C > 32 ? 64 : 32;
+  const size_t smem = (size_t)(lmax + 1) * (lmax + 1) * CW * sizeof(float);
 #define X(L_, M_)                                                                                              \
   if (lmax == L_ && mmax == M_) {                                                                              \
     auto kfn = gather_rotate_dx_kernel<L_, M_>;                                                                \
-    EQV2_LAUNCH(kfn, dim3((unsigned)N), dim3(2 * CP), smem, stream, wig, rad, dA, rowptr_src, perm_src, rowptr_dst, perm_dst, dx, C, CP, Kr, nrad); \
+    EQV2_LAUNCH(kfn, dim3((unsigned)N, (C + CW - 1) / CW), dim3(NODE_THREADS), smem, stream, wig, rad, dA, rowptr_src, perm_src, rowptr_dst, perm_dst, dx, C, CW, Kr, nrad); \
     EQV2_CHECK_LAUNCH("eqv2_gather_rotate_dx");                                                                \
     return 0;                                                                                                  \
   }
@@ -480,14 +517,14 @@ extern "C" int eqv2_rotinv_reduce_fwd(const float* val, const float* alpha, cons
                                       void* stream) {
   (void)pos_of_full;
   if (N == 0) return 0;
-  EQV2_REQUIRE(Cv > 0 && Cv <= 128, "rotinv_reduce_fwd: Cv=%d out of range (1..128)", Cv);
+  EQV2_REQUIRE(Cv > 0, "rotinv_reduce_fwd: Cv=%d out of range", Cv);
   EQV2_REQUIRE(alpha == nullptr || (heads > 0 && Cv % heads == 0), "rotinv_reduce_fwd: heads must divide Cv");
-  const int CP = round32(Cv);
-  const size_t smem = (size_t)(lmax + 1) * (lmax + 1) * CP * sizeof(float);
+  const int CW = Cv > 32 ? 64 : 32;
+  const size_t smem = (size_t)(lmax + 1) * (lmax + 1) * CW * sizeof(float);
 #define X(L_, M_)                                                                                              \
   if (lmax == L_ && mmax == M_) {                                                                              \
     auto kfn = rotinv_reduce_fwd_kernel<L_, M_>;                                                                                    \
-    EQV2_LAUNCH(kfn, dim3((unsigned)N), dim3(2 * CP), smem, stream, val, alpha, wig, rowptr_dst, perm_dst, out, Cv, CP, rows_used, val_estride, heads, scale); \
+    EQV2_LAUNCH(kfn, dim3((unsigned)N, (Cv + CW - 1) / CW), dim3(NODE_THREADS), smem, stream, val, alpha, wig, rowptr_dst, perm_dst, out, Cv, CW, rows_used, val_estride, heads, scale); \
     EQV2_CHECK_LAUNCH("eqv2_rotinv_reduce_fwd");                                                               \
     return 0;                                                                                                  \
   }
