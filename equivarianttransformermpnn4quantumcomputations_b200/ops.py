@@ -478,14 +478,18 @@ def _plain(ld):
 
 def _pick_split(descs, reduce_dim_large):
     """Split-K factor for reduction-heavy problems (weight gradients: K = #edges): choose the factor that
-    fills whole waves of 148 CTAs best, keeping >= 32 k-blocks per split."""
+    fills whole waves of 148 CTAs best.  The in-kernel-split engines keep >= 32 k-blocks (of 32) per split and at most
+    8 splits; the persistent f16x3 engine (64-wide k-blocks, cheap per-tile prologue) goes down to 4 k-blocks per split
+    and up to 32 splits, so a single 128 x 128 weight-gradient tile over 13 120 edges still spreads over 32 SMs."""
     if not reduce_dim_large:
         return 1
     tiles = sum(((d.M + 127) // 128) * ((d.N + 127) // 128) for d in descs)
     kmax = max(d.K for d in descs)
+    f16 = _GEMM_MODE["mode"] == "f16x3" and _f16_ok(descs)
+    smax, kb, kmin = (32, 64, 4) if f16 else (8, 32, 32)
     best, best_eff = 1, 0.0
-    for s in range(1, 9):
-        if s > 1 and kmax // (32 * s) < 32:
+    for s in range(1, smax + 1):
+        if s > 1 and kmax // (kb * s) < kmin:
             break
         ctas = tiles * s
         eff = ctas / (148.0 * ((ctas + 147) // 148))
@@ -637,9 +641,9 @@ def _split_of(splits, src):
 
 def _f16_ok(descs):
     """Should the f16x3 engine take this launch?  Measured (profiles/): the persistent TMA kernel beats the FFMA engine
-    and the in-kernel-split tf32 engine from ~4 M multiply-adds per launch, operand splits included (a 640 x 128 x 128
+    and the in-kernel-split tf32 engine from ~2 M multiply-adds per launch, operand splits included (a 640 x 128 x 128
     node-level linear takes 69 us on the FFMA engine: 5 CTAs)."""
-    return all(_f16_addressable(d) for d in descs) and sum(d.M * d.N * d.K for d in descs) >= (1 << 22)
+    return all(_f16_addressable(d) for d in descs) and sum(d.M * d.N * d.K for d in descs) >= (1 << 21)
 
 
 def _f16_addressable(d):
@@ -652,7 +656,12 @@ def _f16_addressable(d):
     return min(d.M, d.N, d.K) > 0
 
 
+_GEMM16_LOG = None        # diagnostics: set to a list to record (shapes, split_k) of every f16x3 launch, in order
+
+
 def _run_gemm_f16(descs, split_k, flops, nbytes):
+    if _GEMM16_LOG is not None:
+        _GEMM16_LOG.append((tuple((d.M, d.N, d.K, d.transA, d.transB) for d in descs), split_k))
     splits = _splits_for([src for d in descs for src in d.src])
     n = len(descs)
     arr = (_lib.Gemm16Desc * n)()

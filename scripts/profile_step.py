@@ -41,9 +41,24 @@ ops._GEMM_LOG = None
 print("GEMM launches declined by the f16x3 engine (M, N, K, tA, tB, addressable):")
 for k, c in seen.most_common(20):
     print(f"  {c:4d} x {k}")
+ops._GEMM16_LOG = []
 with profile(activities=[ProfilerActivity.CUDA, ProfilerActivity.CPU]) as prof:
     step()
     torch.cuda.synchronize()
+glog, ops._GEMM16_LOG = ops._GEMM16_LOG, None
+gev = sorted([ev for ev in prof.events() if ev.device_type == torch.autograd.DeviceType.CUDA and "gemm_f16_kernel" in ev.name],
+             key=lambda ev: ev.time_range.start)
+if len(gev) == len(glog):
+    per = collections.defaultdict(lambda: [0, 0.0, 0.0])
+    for ev, (shapes, sk) in zip(gev, glog):
+        key = (shapes if len(shapes) <= 2 else (shapes[0], "... %d groups" % len(shapes)), sk)
+        r = per[key]
+        r[0] += 1; r[1] += ev.device_time; r[2] += sum(2.0 * m * n * k for m, n, k, _, _ in shapes)
+    print("f16x3 GEMM launches by shape (M, N, K, tA, tB) x split_k:")
+    for key, (c, t, fl) in sorted(per.items(), key=lambda kv: -kv[1][1])[:24]:
+        print(f"  {t / 1e3:7.3f} ms {c:4d} x {fl / t / 1e6:6.1f} TFLOP/s  {key}")
+else:
+    print("gemm events / log mismatch", len(gev), len(glog))
 agg = collections.defaultdict(lambda: [0, 0.0])
 for ev in prof.events():
     if ev.device_type == torch.autograd.DeviceType.CUDA:

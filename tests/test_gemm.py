@@ -84,7 +84,7 @@ def test_tensor_core_engine_1xtf32_and_options(tA, tB):
     assert _run(ops, _lib, be, 300, 200, 512, tA, tB, "tf32x3", accumulate=True, bias=True) < 3e-6
 
 
-F16_SHAPES = SHAPES + [(130, 260, 520), (64, 8, 8), (13120 // 8, 384, 1280)]
+F16_SHAPES = SHAPES + [(130, 260, 520), (64, 8, 8), (13120 // 8, 384, 1280), (640, 1, 128), (640, 128, 1), (1, 128, 640)]
 
 
 @pytest.mark.gpu
@@ -106,6 +106,7 @@ def test_f16x3_engine_options(tA, tB):
     assert _run(ops, _lib, be, 300, 200, 4096, tA, tB, "f16x3", split_k=4, groups=3) < 3e-6
     assert _run(ops, _lib, be, 300, 200, 1000, tA, tB, "f16x3", accumulate=True, groups=2) < 3e-6
     assert _run(ops, _lib, be, 2000, 1100, 9000, tA, tB, "f16x3", bias=True) < 3e-6      # 144 tiles < 148 CTAs, 141 k-blocks
+    assert _run(ops, _lib, be, 128, 128, 13120, tA, tB, "f16x3", split_k=32) < 3e-6
 
 
 @pytest.mark.gpu
