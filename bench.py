@@ -183,7 +183,7 @@ def run_b200(args):
     torch.manual_seed(0)
     model = oc20.EquiformerV2_OC20(**kw).to(dev)
     net = model
-    if world > 1:
+    if world > 1 and args.no_graph:
         net = torch.nn.parallel.DistributedDataParallel(model, device_ids=[local], gradient_as_bucket_view=True)
     opt = torch.optim.AdamW(model.parameters(), lr=1e-4, fused=True)
 
@@ -203,12 +203,17 @@ def run_b200(args):
         opt.step()
         return loss
 
-    # one rank: the step (forward + loss + backward) is replayed from a CUDA graph, neighbour list / edge frames / AdamW
-    # stay eager (graphs.py).  Data parallel: eager under DistributedDataParallel (bucketed all-reduce overlapped).
-    use_graph = world == 1 and not args.no_graph
+    # The step (forward + loss + backward) is replayed from a CUDA graph; neighbour list / edge frames / AdamW stay eager
+    # (graphs.py).  Data parallel: every rank replays its own graph on its own structures, then the gradients are
+    # all-reduced in flat NCCL buckets.  --no-graph: eager launches (DistributedDataParallel when N > 1).
+    use_graph = not args.no_graph
     if use_graph:
         graphs = importlib.import_module(PKG + ".graphs")
-        stepper = graphs.GraphedTrainStep(model, lambda out, d: losses(out[0], out[1], d), opt)
+        sync = None
+        if world > 1:       # bucketed NCCL all-reduce (mean) of the gradients the replay leaves in place, then AdamW
+            parallel = importlib.import_module(PKG + ".parallel")
+            sync = parallel.GradientAllReducer(model.parameters(), bucket_mb=64).reduce
+        stepper = graphs.GraphedTrainStep(model, lambda out, d: losses(out[0], out[1], d), opt, grad_sync=sync)
         step = stepper
     else:
         stepper = None
@@ -291,8 +296,9 @@ def run_b200(args):
                                        "max 20 neighbours", "structures_per_gpu": B, "atoms_per_gpu": int(host["pos"].shape[0]),
                            "edges_per_gpu": E, "layers": kw["num_layers"], "params": model.num_params,
                            "parallelism": f"dp{world}",
-                           "launch": ("CUDA graph replay of forward+loss+backward; neighbour list, edge frames and AdamW "
-                                      "eager" if use_graph else "eager (every kernel enqueued from Python)"),
+                           "launch": ("CUDA graph replay of forward+loss+backward; neighbour list, edge frames, gradient "
+                                      "all-reduce (NCCL, N > 1) and AdamW eager" if use_graph
+                                      else "eager (every kernel enqueued from Python; DDP when N > 1)"),
                            "gemm_engine": engine_note[0],
                            "l2": "step working set (330 MB weights + >1 GB activations) exceeds the 126 MB L2"},
                 "e2e": {"value": e2e, "unit": UNIT, "ms_per_step": ms_e2e / args.steps, "h2d_bytes_per_step": h2d_bytes,

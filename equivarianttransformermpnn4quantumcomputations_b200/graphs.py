@@ -12,10 +12,12 @@ from . import ops
 
 
 class GraphedTrainStep:
-    def __init__(self, model, loss_fn, optimizer, max_graphs=8, warmup=2):
+    def __init__(self, model, loss_fn, optimizer, max_graphs=8, warmup=2, grad_sync=None):
         """model(data) -> outputs; loss_fn(outputs, data) -> scalar; `model.prepare(data)` must exist (see
-        models/equiformerv2_oc20.py) and `model` accept its results under the keys below."""
+        models/equiformerv2_oc20.py) and `model` accept its results under the keys below.  `grad_sync()` (data
+        parallel: parallel.GradientAllReducer.reduce, NCCL) runs between the replay and the optimizer update."""
         self.model, self.loss_fn, self.optimizer = model, loss_fn, optimizer
+        self.grad_sync = grad_sync
         self.max_graphs, self.warmup = max_graphs, warmup
         self.graphs = {}            # signature -> (graph, static inputs, static loss, gradient tensors, launches)
         self.params = [p for g in optimizer.param_groups for p in g["params"]]
@@ -71,6 +73,8 @@ class GraphedTrainStep:
             if len(self.graphs) >= self.max_graphs:
                 loss = self._eager(full)
                 self.active = None
+                if self.grad_sync is not None:
+                    self.grad_sync()
                 self.optimizer.step()
                 return loss
             self._capture(full, sig)
@@ -85,6 +89,8 @@ class GraphedTrainStep:
             for p, g in zip(self.params, grads):
                 p.grad = g
             self.active = sig
+        if self.grad_sync is not None:
+            self.grad_sync()
         self.optimizer.step()
         return loss
 
