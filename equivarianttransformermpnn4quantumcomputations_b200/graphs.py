@@ -12,11 +12,14 @@ from . import ops
 
 
 class GraphedTrainStep:
-    def __init__(self, model, loss_fn, optimizer, max_graphs=8, warmup=2, grad_sync=None):
-        """model(data) -> outputs; loss_fn(outputs, data) -> scalar; `model.prepare(data)` must exist (see
-        models/equiformerv2_oc20.py) and `model` accept its results under the keys below.  `grad_sync()` (data
+    def __init__(self, model, loss_fn, optimizer, max_graphs=8, warmup=2, grad_sync=None, forward_loss=None):
+        """model(data) -> outputs; loss_fn(outputs, data) -> scalar -- or `forward_loss(data)` -> scalar for steps that
+        need more than that (MatPES: forces = -autograd.grad(E, pos, create_graph=True) inside the loss).
+        `model.prepare(data)` must return the dict of data-dependent inputs the model then takes from `data` (OC20:
+        edge_index / edge_distance / edge_distance_vec / edge_frames; MatPES v2: edge_index).  `grad_sync()` (data
         parallel: parallel.GradientAllReducer.reduce, NCCL) runs between the replay and the optimizer update."""
         self.model, self.loss_fn, self.optimizer = model, loss_fn, optimizer
+        self.forward_loss = forward_loss if forward_loss is not None else (lambda d: loss_fn(model(d), d))
         self.grad_sync = grad_sync
         self.max_graphs, self.warmup = max_graphs, warmup
         self.graphs = {}            # signature -> (graph, static inputs, static loss, gradient tensors, launches)
@@ -26,17 +29,15 @@ class GraphedTrainStep:
         self.active = None          # signature whose gradient tensors are currently bound to the parameters
         self.replays = 0
 
-    PREPARED_KEYS = ("edge_index", "edge_distance", "edge_distance_vec", "edge_frames")
-
     def _with_prepared(self, data):
         with torch.no_grad():
             prepared = self.model.prepare(data)
         out = dict(data)
-        out.update(zip(self.PREPARED_KEYS, prepared))
+        out.update(prepared)
         return out
 
     def _eager(self, full):
-        loss = self.loss_fn(self.model(full), full)
+        loss = self.forward_loss(full)
         self.optimizer.zero_grad(set_to_none=True)
         loss.backward()
         return loss
@@ -57,7 +58,7 @@ class GraphedTrainStep:
         n0 = _lib.launch_count()
         graph = torch.cuda.CUDAGraph()
         with torch.cuda.graph(graph, pool=self.pool, stream=side):
-            loss = self.loss_fn(self.model(static), static)
+            loss = self.forward_loss(static)
             loss.backward()
         ops.reset_caches()
         if self.pool is None:

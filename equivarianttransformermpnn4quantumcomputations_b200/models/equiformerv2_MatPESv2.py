@@ -102,6 +102,14 @@ class EquiformerV2_MatPES(nn.Module):
         dvec = pos[edge_index[1]] - pos[edge_index[0]]
         return edge_index, torch.norm(dvec, dim=1), dvec
 
+    def prepare(self, data):
+        """Data-dependent head of a forward pass (graphs.GraphedTrainStep): the periodic neighbour list (host read-back of
+        the edge count).  Edge vectors, distances and the deterministic edge frames are recomputed from `pos` inside
+        the replayed part -- they carry the position gradient."""
+        with torch.no_grad():
+            return {"edge_index": self.generate_graph(data["pos"].detach(), data["batch"], data["cell"],
+                                                      data["natoms"])[0]}
+
     def forward(self, data):
         self.batch_size = len(data["natoms"])
         self.dtype, self.device = data["pos"].dtype, data["pos"].device

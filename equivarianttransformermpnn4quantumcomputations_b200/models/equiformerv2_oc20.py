@@ -104,7 +104,8 @@ class EquiformerV2_OC20(nn.Module):
         count) and edge frames (the reference's host-side checks, edge_rot_mat.py:24,46).  Everything after it has
         shapes fixed by (atoms, edges) and can be replayed from a CUDA graph (graphs.GraphedTrainStep)."""
         edge_index, edge_distance, edge_vec = self.generate_graph(data)
-        return edge_index, edge_distance, edge_vec, init_edge_rot_mat(edge_vec)
+        return {"edge_index": edge_index, "edge_distance": edge_distance, "edge_distance_vec": edge_vec,
+                "edge_frames": init_edge_rot_mat(edge_vec)}
 
     def forward(self, data):
         atomic_numbers = data["atomic_numbers"].long()
@@ -114,7 +115,9 @@ class EquiformerV2_OC20(nn.Module):
             edge_index, edge_distance, edge_vec, frames = (data["edge_index"], data["edge_distance"],
                                                            data["edge_distance_vec"], data["edge_frames"])
         else:
-            edge_index, edge_distance, edge_vec, frames = self.prepare(data)
+            p = self.prepare(data)
+            edge_index, edge_distance, edge_vec, frames = (p["edge_index"], p["edge_distance"], p["edge_distance_vec"],
+                                                           p["edge_frames"])
         for rot in self.SO3_rotation:
             rot.set_wigner(frames)
 

@@ -1407,15 +1407,24 @@ def norm_groups(norm_type, lmax):
     raise ValueError(norm_type)
 
 
+_norm_tables = {}     # (norm_type, lmax, device, dtype) -> (lk, bwk, gk): built once (no host->device copies in a hot loop / CUDA graph)
+
+
+def _equiv_norm_tables(norm_type, lmax, dev, dtype):
+    key = (norm_type, lmax, str(dev), dtype)
+    if key not in _norm_tables:
+        ng, gol, bw = norm_groups(norm_type, lmax)
+        lk = torch.tensor([l for l in range(lmax + 1) for _ in range(2 * l + 1)], device=dev)
+        _norm_tables[key] = (lk, torch.tensor(bw, dtype=dtype, device=dev)[lk], torch.tensor(gol, device=dev)[lk])
+    return _norm_tables[key]
+
+
 def _equiv_norm_expr(norm_type, lmax, eps):
     ng, gol, bw = norm_groups(norm_type, lmax)
 
     def fn(x, w, b):
         N, K, C = x.shape
-        dev = x.device
-        lk = torch.tensor([l for l in range(lmax + 1) for _ in range(2 * l + 1)], device=dev)
-        bwk = torch.tensor(bw, dtype=x.dtype, device=dev)[lk]
-        gk = torch.tensor(gol, device=dev)[lk]
+        lk, bwk, gk = _equiv_norm_tables(norm_type, lmax, x.device, x.dtype)
         f = torch.cat([x[:, :1] - x[:, :1].mean(dim=2, keepdim=True), x[:, 1:]], dim=1)
         onehot = torch.nn.functional.one_hot(gk, ng).to(x.dtype)
         s = torch.einsum("nkc,k,kg->ng", f * f, bwk, onehot) / C

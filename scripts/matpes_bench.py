@@ -26,6 +26,13 @@ def train_step(model, opt, data, w_e=1.0, w_f=1.0):
     return loss
 
 
+def forward_loss(model, data, w_e=1.0, w_f=1.0):
+    pos = data["pos"].detach().requires_grad_(True)
+    out = model(dict(data, pos=pos))
+    forces = -torch.autograd.grad(out["energy_total"].sum(), pos, create_graph=True, retain_graph=True)[0]
+    return w_e * (out["energy"] - data["energy"]).abs().mean() + w_f * (forces - data["forces"]).abs().mean()
+
+
 def main(B=8, steps=5, warmup=3):
     dev = torch.device("cuda:0")
     torch.manual_seed(0)
@@ -33,16 +40,25 @@ def main(B=8, steps=5, warmup=3):
     opt = torch.optim.AdamW(model.parameters(), lr=1e-4, fused=True)
     host = syn.matpes_batch(B, seed=7)
     data = {k: v.to(dev) for k, v in host.items()}
+    graphed = "--no-graph" not in sys.argv
+    if graphed:     # forward + force gradient + loss + double backward replayed from a CUDA graph (graphs.py)
+        graphs = importlib.import_module(PKG + ".graphs")
+        stepper = graphs.GraphedTrainStep(model, None, opt, forward_loss=lambda d: forward_loss(model, d))
+        run = lambda: stepper(data)
+    else:
+        run = lambda: train_step(model, opt, data)
     for _ in range(warmup):
-        loss = train_step(model, opt, data)
+        loss = run()
     torch.cuda.synchronize()
     E = int(model.generate_graph(data["pos"], data["batch"], data["cell"], data["natoms"])[0].shape[1])
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
     for _ in range(steps):
-        loss = train_step(model, opt, data)
+        loss = run()
     e1.record(); torch.cuda.synchronize()
     ms = e0.elapsed_time(e1) / steps
+    if graphed:
+        opt.zero_grad(set_to_none=True)
     _lib.start_kernel_timing()
     train_step(model, opt, data)
     prof = _lib.stop_kernel_timing()
@@ -65,7 +81,7 @@ def main(B=8, steps=5, warmup=3):
     ((et / small["natoms"]).unsqueeze(1) - small["energy"]).abs().mean().add((f - small["forces"]).abs().mean()).backward()
     dt = time.perf_counter() - t0
     print(json.dumps({"workload": "MatPES EquiformerV2 (lmax 4, mmax 2, 6 blocks) train step with autograd forces (double backward)",
-                      "structures_per_s": B / (ms / 1e3), "ms_per_step": ms, "structures": B, "atoms": int(data["pos"].shape[0]),
+                      "structures_per_s": B / (ms / 1e3), "ms_per_step": ms, "launch": "CUDA graph replay" if graphed else "eager", "structures": B, "atoms": int(data["pos"].shape[0]),
                       "edges": E, "loss": float(loss), "params": model.num_params, "kernel_time_shares": shares,
                       "kernel_ms_total": tot,
                       "cpu_baseline": {"structures_per_s": 2 / dt, "cores": os.cpu_count(), "kind": "port",

@@ -57,3 +57,43 @@ def test_graphed_step_follows_eager_trajectory():
     finally:
         pkg("ops").set_gemm_mode(pkg("ops").DEFAULT_GEMM_MODE)
     assert max(abs(x - y) / abs(x) for x, y in zip(l0, l2)) < 1e-4, (l0, l2)
+
+
+def _matpes_forward_loss(model, d):
+    pos = d["pos"].detach().requires_grad_(True)
+    out = model(dict(d, pos=pos))
+    forces = -torch.autograd.grad(out["energy_total"].sum(), pos, create_graph=True, retain_graph=True)[0]
+    return (out["energy"] - d["energy"]).abs().mean() + (forces - d["forces"]).abs().mean()
+
+
+@pytest.mark.gpu
+def test_graphed_matpes_double_backward_step_follows_eager_trajectory():
+    """MatPES pattern (train_MatPES_GATAWandB.py:67-91): forces by autograd.grad(create_graph=True) inside the loss, then
+    loss.backward() -- captured as one graph (forward + force gradient + double backward) and replayed."""
+    if not torch.cuda.is_available():
+        pytest.skip("no CUDA device")
+    pkg("_lib")._state["lib"] = None
+    syn, mp, graphs = pkg("synthetic"), pkg("models.equiformerv2_MatPESv2"), pkg("graphs")
+    data = {k: (v.cuda() if torch.is_tensor(v) else v) for k, v in syn.matpes_batch(2, seed=3).items()}
+    res = []
+    for graphed in (False, True):
+        torch.manual_seed(0)
+        model = mp.EquiformerV2_MatPES(num_layers=2, sphere_channels=32, attn_hidden_channels=32, num_heads=2,
+                                       attn_alpha_channels=16, attn_value_channels=8, ffn_hidden_channels=64, lmax_list=[3],
+                                       mmax_list=[2], edge_channels=32, alpha_drop=0.0, drop_path_rate=0.0).cuda()
+        opt = torch.optim.AdamW(model.parameters(), lr=1e-3, fused=True)
+        stepper = graphs.GraphedTrainStep(model, None, opt, forward_loss=lambda d, m=model: _matpes_forward_loss(m, d))
+        losses = []
+        for _ in range(4):
+            if graphed:
+                losses.append(float(stepper(data).detach()))
+            else:
+                loss = _matpes_forward_loss(model, data)
+                opt.zero_grad(set_to_none=True)
+                loss.backward()
+                opt.step()
+                losses.append(float(loss.detach()))
+        res.append((losses, [p.detach().clone() for p in model.parameters()]))
+    (l0, p0), (l1, p1) = res
+    assert max(abs(x - y) / abs(x) for x, y in zip(l0, l1)) < 1e-5, (l0, l1)
+    assert max(float((x - y).abs().max() / (x.abs().max() + 1e-12)) for x, y in zip(p0, p1)) < 1e-4
