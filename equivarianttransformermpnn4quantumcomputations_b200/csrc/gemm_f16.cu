@@ -425,9 +425,14 @@ __global__ void __launch_bounds__(256) absmax_kernel(const __grid_constant__ Spl
   if ((reinterpret_cast<uintptr_t>(T.src) & 15) == 0) {
     const long long n4 = n >> 2;
     const float4* s4 = reinterpret_cast<const float4*>(T.src);
-    for (long long i = (long long)lb * 256 + threadIdx.x; i < n4; i += (long long)T.nblocks * 256) {
-      const float4 v = __ldg(s4 + i);
-      m = fmaxf(m, fmaxf(fmaxf(fabsf(v.x), fabsf(v.y)), fmaxf(fabsf(v.z), fabsf(v.w))));
+    const long long stride = (long long)T.nblocks * 256;
+    for (long long i0 = (long long)lb * 256 + threadIdx.x; i0 < n4; i0 += 4 * stride) {      // 4 loads in flight
+      float4 v[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) v[u] = (i0 + u * stride < n4) ? __ldg(s4 + i0 + u * stride) : make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+      for (int u = 0; u < 4; ++u)
+        m = fmaxf(m, fmaxf(fmaxf(fabsf(v[u].x), fabsf(v[u].y)), fmaxf(fabsf(v[u].z), fabsf(v[u].w))));
     }
     if (lb == 0 && threadIdx.x < (int)(n & 3)) m = fmaxf(m, fabsf(__ldg(T.src + (n4 << 2) + threadIdx.x)));
   } else {
@@ -457,6 +462,43 @@ __global__ void __launch_bounds__(256) split_kernel(const __grid_constant__ Spli
   const long long ngroups = T.rows_pad * (long long)gpr;
   const long long plane = T.rows_pad * T.cols_pad;
   const bool vec_ok = ((reinterpret_cast<uintptr_t>(T.src) & 15) == 0) && ((T.cols & 3) == 0);
+  if (vec_ok && T.cols == T.cols_pad && T.rows == T.rows_pad && T.slab_k == 0) {
+    // Fast path (every large activation / gradient tensor): source and planes are the same linear sequence of
+    // 8-element groups; four groups per thread and iteration (8 x 128-bit loads in flight per thread).
+    const long long stride = (long long)T.nblocks * 256;
+    const float4* s4 = reinterpret_cast<const float4*>(T.src);
+    uint4* dh = reinterpret_cast<uint4*>(T.dst);
+    uint4* dl = reinterpret_cast<uint4*>(T.dst + plane);
+    for (long long g0 = (long long)lb * 256 + threadIdx.x; g0 < ngroups; g0 += 4 * stride) {
+      float4 a[4], b[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const long long g = g0 + u * stride;
+        if (g < ngroups) {
+          a[u] = __ldg(s4 + 2 * g);
+          b[u] = __ldg(s4 + 2 * g + 1);
+        }
+      }
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const long long g = g0 + u * stride;
+        if (g < ngroups) {
+          const float v[8] = {a[u].x, a[u].y, a[u].z, a[u].w, b[u].x, b[u].y, b[u].z, b[u].w};
+          __align__(16) __half h[8];
+          __align__(16) __half l[8];
+#pragma unroll
+          for (int t = 0; t < 8; ++t) {
+            const float x = v[t] * s;
+            h[t] = __float2half_rn(x);
+            l[t] = __float2half_rn(x - __half2float(h[t]));
+          }
+          dh[g] = *reinterpret_cast<const uint4*>(h);
+          dl[g] = *reinterpret_cast<const uint4*>(l);
+        }
+      }
+    }
+    return;
+  }
   for (long long g = (long long)lb * 256 + threadIdx.x; g < ngroups; g += (long long)T.nblocks * 256) {
     const long long r = (ngroups <= 0xFFFFFFFFll) ? (long long)((unsigned)g / gpr) : g / gpr;   // 32-bit division
     const long long c8 = (g - r * gpr) << 3;
