@@ -303,10 +303,18 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) gemm_f16_kernel(const __grid_c
     const int half = (warp - 2) >> 2;                      // column half
     const uint32_t lane_col = ((uint32_t)(q * 32) << 16) + (uint32_t)(half * 64);
     uint32_t c = 0;
+    int scale_gi = -1;                                      // group whose 1/(s_A s_B) is cached in ia / ib
+    float ia = 1.f, ib = 1.f;
     for (int w = blockIdx.x; w < P.total_work; w += gridDim.x) {
       const Work W = decode_work(P, w);
       const HGroup& G = P.g[W.gi];
       if (W.nkb == 0) continue;
+      if (W.gi != scale_gi) {       // the operand maxima are read once per group, BEFORE the tile's promotions: four
+        float sa, sb;               // dependent global loads per tile on the workers' path delayed the next promotion
+        scale_of(eqv2_read_absmax(G.a_absmax), sa, ia);
+        scale_of(eqv2_read_absmax(G.b_absmax), sb, ib);
+        scale_gi = W.gi;
+      }
       const int nchunks = (W.nkb + CHUNK_KB - 1) / CHUNK_KB;
       float acc[64];
 #pragma unroll
@@ -340,9 +348,6 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) gemm_f16_kernel(const __grid_c
         if (lane == 0) mbar_arrive(smem_u32(&acc_empty[b]));
       }
       // ---- epilogue (overlaps the next tile's main loop: TMEM is already released) ----
-      float sa, ia, sb, ib;
-      scale_of(eqv2_read_absmax(G.a_absmax), sa, ia);
-      scale_of(eqv2_read_absmax(G.b_absmax), sb, ib);
       const int row = W.m0 + q * 32 + lane;
       const bool atomic = P.split_k > 1;
       if (row < G.M) {

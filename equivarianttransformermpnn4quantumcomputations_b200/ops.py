@@ -477,19 +477,28 @@ def _plain(ld):
 
 
 def _pick_split(descs, reduce_dim_large):
-    """Split-K factor for reduction-heavy problems (weight gradients: K = #edges): choose the factor that
-    fills whole waves of 148 CTAs best.  The in-kernel-split engines keep >= 32 k-blocks (of 32) per split and at most
-    8 splits; the persistent f16x3 engine (64-wide k-blocks, cheap per-tile prologue) goes down to 4 k-blocks per split
-    and up to 32 splits, so a single 128 x 128 weight-gradient tile over 13 120 edges still spreads over 32 SMs."""
+    """Split-K factor for reduction-heavy problems (weight gradients: K = #edges).
+    In-kernel-split engines: the factor that fills whole waves of 148 CTAs best, >= 32 k-blocks (of 32) per split, <= 8.
+    Persistent f16x3 engine: minimise  waves x (k-blocks per split + fixed per-tile cost)  with the measured per-tile cost
+    of ~4 k-block times (promotion hand-over + epilogue, scripts/profile_step.py) + 2 for the atomic epilogue; up to 32
+    splits, so a single 128 x 128 weight-gradient tile over 13 120 edges still spreads over 32 SMs."""
     if not reduce_dim_large:
         return 1
     tiles = sum(((d.M + 127) // 128) * ((d.N + 127) // 128) for d in descs)
     kmax = max(d.K for d in descs)
-    f16 = _GEMM_MODE["mode"] == "f16x3" and _f16_ok(descs)
-    smax, kb, kmin = (32, 64, 4) if f16 else (8, 32, 32)
+    if _GEMM_MODE["mode"] == "f16x3" and _f16_ok(descs):
+        nkb = (kmax + 63) // 64
+        best, best_cost = 1, None
+        for s in range(1, 33):
+            if s > 1 and nkb // s < 4:
+                break
+            cost = ((tiles * s + 147) // 148) * ((nkb + s - 1) // s + (6.0 if s > 1 else 4.0))
+            if best_cost is None or cost < best_cost * 0.97:
+                best, best_cost = s, cost
+        return best
     best, best_eff = 1, 0.0
-    for s in range(1, smax + 1):
-        if s > 1 and kmax // (kb * s) < kmin:
+    for s in range(1, 9):
+        if s > 1 and kmax // (32 * s) < 32:
             break
         ctas = tiles * s
         eff = ctas / (148.0 * ((ctas + 147) // 148))
