@@ -55,7 +55,11 @@ def split_batch(data, structures):
 
 
 class GradientAllReducer:
-    """Average gradients over the process group in flat buckets of ~`bucket_mb` MB."""
+    """Average gradients over the process group in persistent flat buckets of ~`bucket_mb` MB.
+
+    Per bucket: ONE multi-tensor copy of the gradients into the flat buffer, one all-reduce (AVG on NCCL; SUM + scale
+    on backends without AVG), one multi-tensor copy back -- a handful of launches per step instead of one per parameter
+    (82.5 M parameters live in ~800 tensors; per-tensor copies cost the host ~4 ms per step)."""
 
     def __init__(self, parameters, bucket_mb=25, group=None):
         self.params = [p for p in parameters if p.requires_grad]
@@ -70,21 +74,37 @@ class GradientAllReducer:
                 cur, size = [], 0
         if cur:
             self.buckets.append(cur)
+        self._flat = {}          # bucket index -> (flat buffer, per-parameter views)
+
+    def _buffers(self, i, bucket):
+        hit = self._flat.get(i)
+        if hit is None or hit[0].device != bucket[0].device:
+            flat = torch.empty(sum(p.numel() for p in bucket), dtype=bucket[0].dtype, device=bucket[0].device)
+            views, off = [], 0
+            for p in bucket:
+                views.append(flat[off:off + p.numel()].view_as(p))
+                off += p.numel()
+            hit = self._flat[i] = (flat, views)
+        return hit
 
     def reduce(self):
         if not dist.is_initialized() or dist.get_world_size(self.group) == 1:
             return
         world = dist.get_world_size(self.group)
+        avg = dist.get_backend(self.group) == "nccl"
         pending = []
-        for bucket in self.buckets:
-            flat = torch.cat([(p.grad if p.grad is not None else torch.zeros_like(p)).reshape(-1) for p in bucket])
-            pending.append((dist.all_reduce(flat, op=dist.ReduceOp.SUM, group=self.group, async_op=True), flat, bucket))
-        for work, flat, bucket in pending:
+        for i, bucket in enumerate(self.buckets):
+            flat, views = self._buffers(i, bucket)
+            have = [(v, p.grad) for v, p in zip(views, bucket) if p.grad is not None]
+            if len(have) < len(bucket):
+                flat.zero_()                                  # parameters without gradient are sent as zeros
+            if have:
+                torch._foreach_copy_([v for v, _ in have], [g for _, g in have])
+            op = dist.ReduceOp.AVG if avg else dist.ReduceOp.SUM
+            pending.append((dist.all_reduce(flat, op=op, group=self.group, async_op=True), flat, have))
+        for work, flat, have in pending:
             work.wait()
-            flat.div_(world)
-            off = 0
-            for p in bucket:
-                n = p.numel()
-                if p.grad is not None:
-                    p.grad.copy_(flat[off:off + n].view_as(p))
-                off += n
+            if not avg:
+                flat.div_(world)
+            if have:
+                torch._foreach_copy_([g for _, g in have], [v for v, _ in have])
