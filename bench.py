@@ -36,7 +36,7 @@ UNIT = "structures/s"
 MODEL_KW = dict(max_neighbors=20, max_radius=12.0, max_num_elements=90, num_layers=12, sphere_channels=128,
                 attn_hidden_channels=64, num_heads=8, attn_alpha_channels=64, attn_value_channels=16,
                 ffn_hidden_channels=128, norm_type="rms_norm_sh", lmax_list=[6], mmax_list=[2], grid_resolution=18,
-                edge_channels=128, alpha_drop=0.0, drop_path_rate=0.0, proj_drop=0.0)
+                edge_channels=128, alpha_drop=0.1, drop_path_rate=0.05, proj_drop=0.0)
 
 
 def parse():
@@ -49,6 +49,9 @@ def parse():
     ap.add_argument("--layers", type=int, default=None, help="(debug) override the number of blocks")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-graph", action="store_true", help="enqueue every step from Python instead of replaying a CUDA graph")
+    ap.add_argument("--no-dropout", action="store_true",
+                    help="alpha_drop = drop_path_rate = 0 (default: the reference's training values 0.1 / 0.05, "
+                         "configs/OC20/oc20_config_corrected.py:35-37 = equiformerv2_oc20.py ctor defaults)")
     ap.add_argument("--gemm-mode", default=None, choices=["f16x3", "tf32x3", "tf32", "fp32"],
                     help="GEMM engine (default: the package default, f16x3 = fp32-class accuracy)")
     return ap.parse_args()
@@ -181,6 +184,8 @@ def run_b200(args):
     kw = dict(MODEL_KW)
     if args.layers:
         kw["num_layers"] = args.layers
+    if args.no_dropout:
+        kw.update(alpha_drop=0.0, drop_path_rate=0.0)
     torch.manual_seed(0)
     model = oc20.EquiformerV2_OC20(**kw).to(dev)
     net = model
@@ -294,7 +299,7 @@ def run_b200(args):
                 "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
                 "config": {"workload": "OC20 S2EF EquiformerV2 (lmax 6, mmax 2, 12 blocks + force head) train step "
                                        "(graph build + fwd + L1 loss + bwd + AdamW), ~80-atom slabs, 12 A cutoff, "
-                                       "max 20 neighbours", "structures_per_gpu": B, "atoms_per_gpu": int(host["pos"].shape[0]),
+                                       "max 20 neighbours, attention dropout %.2f / stochastic depth %.2f" % (kw["alpha_drop"], kw["drop_path_rate"]), "structures_per_gpu": B, "atoms_per_gpu": int(host["pos"].shape[0]),
                            "edges_per_gpu": E, "layers": kw["num_layers"], "params": model.num_params,
                            "parallelism": f"dp{world}",
                            "launch": ("CUDA graph replay of forward+loss+backward; neighbour list, edge frames, gradient "

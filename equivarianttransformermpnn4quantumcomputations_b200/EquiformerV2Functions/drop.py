@@ -26,6 +26,15 @@ class DropPath(nn.Module):
         return "drop_prob={}".format(self.drop_prob)
 
 
+_NUM_GRAPHS = {"n": None}
+
+
+def set_num_graphs(n):
+    """Number of structures in the batch the next forward passes work on (None: derive it from `batch` as the
+    reference does)."""
+    _NUM_GRAPHS["n"] = None if n is None else int(n)
+
+
 class GraphDropPath(nn.Module):
     """Per-graph stochastic depth (reference drop.py:49-68)."""
 
@@ -34,7 +43,10 @@ class GraphDropPath(nn.Module):
         self.drop_prob = drop_prob
 
     def forward(self, x, batch):
-        num_graphs = batch.max() + 1
+        # reference: batch.max() + 1 (drop.py:60) -- a device read-back on every call.  The model wrappers announce the
+        # number of structures they were given (set_num_graphs), which is the same value without the synchronisation
+        # (and keeps the block capturable in a CUDA graph); without the announcement the reference expression is used.
+        num_graphs = _NUM_GRAPHS["n"] if _NUM_GRAPHS["n"] is not None else int(batch.max()) + 1
         ones = torch.ones((num_graphs,) + (1,) * (x.ndim - 1), dtype=x.dtype, device=x.device)
         return x * drop_path(ones, self.drop_prob, self.training)[batch]
 

@@ -11,6 +11,7 @@ import torch
 import torch.nn as nn
 
 from .. import ops
+from ..EquiformerV2Functions.drop import set_num_graphs
 from ..EquiformerV2Functions.input_block import EdgeDegreeEmbedding
 from ..EquiformerV2Functions.layer_norm import get_normalization_layer
 from ..EquiformerV2Functions.radial_function import RadialFunction
@@ -111,6 +112,13 @@ class EquiformerV2_MatPES(nn.Module):
                                                       data["natoms"])[0]}
 
     def forward(self, data):
+        set_num_graphs(len(data["natoms"]))          # GraphDropPath: no batch.max() read-back (drop.py)
+        try:
+            return self._forward(data)
+        finally:
+            set_num_graphs(None)
+
+    def _forward(self, data):
         self.batch_size = len(data["natoms"])
         self.dtype, self.device = data["pos"].dtype, data["pos"].device
         atomic_numbers = data["atomic_numbers"].long()

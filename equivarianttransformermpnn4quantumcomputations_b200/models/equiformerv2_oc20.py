@@ -10,6 +10,7 @@ import torch
 import torch.nn as nn
 
 from .. import ops
+from ..EquiformerV2Functions.drop import set_num_graphs
 from ..EquiformerV2Functions.edge_rot_mat import init_edge_rot_mat
 from ..EquiformerV2Functions.input_block import EdgeDegreeEmbedding
 from ..EquiformerV2Functions.layer_norm import get_normalization_layer
@@ -108,6 +109,13 @@ class EquiformerV2_OC20(nn.Module):
                 "edge_frames": init_edge_rot_mat(edge_vec)}
 
     def forward(self, data):
+        set_num_graphs(len(data["natoms"]))          # GraphDropPath: no batch.max() read-back (drop.py)
+        try:
+            return self._forward(data)
+        finally:
+            set_num_graphs(None)
+
+    def _forward(self, data):
         atomic_numbers = data["atomic_numbers"].long()
         num_atoms = atomic_numbers.shape[0]
         pos = data["pos"]

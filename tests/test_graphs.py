@@ -81,7 +81,9 @@ def test_graphed_matpes_double_backward_step_follows_eager_trajectory():
         model = mp.EquiformerV2_MatPES(num_layers=2, sphere_channels=32, attn_hidden_channels=32, num_heads=2,
                                        attn_alpha_channels=16, attn_value_channels=8, ffn_hidden_channels=64, lmax_list=[3],
                                        mmax_list=[2], edge_channels=32, alpha_drop=0.0, drop_path_rate=0.0).cuda()
-        opt = torch.optim.AdamW(model.parameters(), lr=1e-3, fused=True)
+        # plain SGD: Adam's g / sqrt(v) turns rounding-level differences of near-zero gradients (split-K atomics) into
+        # lr-sized parameter differences, which says nothing about the replay
+        opt = torch.optim.SGD(model.parameters(), lr=1e-2)
         stepper = graphs.GraphedTrainStep(model, None, opt, forward_loss=lambda d, m=model: _matpes_forward_loss(m, d))
         losses = []
         for _ in range(4):
