@@ -98,6 +98,12 @@ class EquiformerV2_MatPES(nn.Module):
         dvec = pos[edge_index[1]] - pos[edge_index[0]]
         return edge_index, torch.norm(dvec, dim=1), dvec
 
+    def prepare(self, data):
+        """Data-dependent head of a forward pass (graphs.GraphedTrainStep): the periodic neighbour list."""
+        with torch.no_grad():
+            return {"edge_index": self.generate_graph(data["pos"].detach(), data["batch"], data["cell"],
+                                                      data["natoms"])[0]}
+
     def _compute_rl_ij(self, edge_distance_vec):
         return ops.edge_sh(edge_distance_vec, max(self.lmax_list))
 

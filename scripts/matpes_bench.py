@@ -1,4 +1,4 @@
-"""BASELINE config 3 (MatPES EquiformerV2, base family): train step = forward energy -> forces by
+"""BASELINE configs 3-5 (MatPES family; `--model base | gatav2 | gatav2_phi | global`, default base): train step = forward energy -> forces by
 autograd.grad(create_graph=True) -> L1(E) + L1(F) -> loss.backward() (double backward) -> AdamW,
 on synthetic 30-atom bulk cells (6 A cutoff, max 20 neighbours), batch 8 per GPU (config_cosinelearning.py:76).
 Prints one JSON line: GPU structures/s, per-entry-point time shares, and the CPU oracle port on a bounded sample."""
@@ -8,11 +8,18 @@ import torch
 PKG = "equivarianttransformermpnn4quantumcomputations_b200"
 _lib = importlib.import_module(PKG + "._lib")
 syn = importlib.import_module(PKG + ".synthetic")
-mp = importlib.import_module(PKG + ".models.equiformerv2_MatPESv2")
+MODELS = {"base": "equiformerv2_MatPESv2", "gatav2": "equiformerv2_MatPES_GATAV2",
+          "gatav2_phi": "equiformerv2_MatPES_GATAV2_phi_at_every_iteration_like_gata",
+          "global": "equiformerv2_MatPES_GATAV2_GLOBALALLATTENTION_HTR_phi_at_every_iteration_like_gata_with_DISTANCE"}
+WHICH = next((a.split("=")[1] for a in sys.argv if a.startswith("--model=")), "base")
+mp = importlib.import_module(PKG + ".models." + MODELS[WHICH])
+ATOMS = int(next((a.split("=")[1] for a in sys.argv if a.startswith("--atoms=")), 200 if WHICH == "global" else 30))
 
 KW = dict(max_neighbors=20, max_radius=6.0, num_layers=6, sphere_channels=128, attn_hidden_channels=128, num_heads=8,
           attn_alpha_channels=32, attn_value_channels=16, ffn_hidden_channels=512, lmax_list=[4], mmax_list=[2],
           edge_channels=128, alpha_drop=0.0, drop_path_rate=0.0)
+if WHICH != "base":      # configs/MatPES/config_cosinelearningGATA.py / ...MoreGATA_all2all.py: mmax 4
+    KW["mmax_list"] = [4]
 
 
 def train_step(model, opt, data, w_e=1.0, w_f=1.0):
@@ -38,9 +45,10 @@ def main(B=8, steps=5, warmup=3):
     torch.manual_seed(0)
     model = mp.EquiformerV2_MatPES(**KW).to(dev)
     opt = torch.optim.AdamW(model.parameters(), lr=1e-4, fused=True)
-    host = syn.matpes_batch(B, seed=7)
+    host = syn.matpes_batch(B, seed=7, n_atoms=ATOMS)
     data = {k: v.to(dev) for k, v in host.items()}
-    graphed = "--no-graph" not in sys.argv
+    # the all-to-all attention of config 5 loops over structures with host-side sizes (bincount().tolist()): eager only
+    graphed = "--no-graph" not in sys.argv and WHICH != "global"
     if graphed:     # forward + force gradient + loss + double backward replayed from a CUDA graph (graphs.py)
         graphs = importlib.import_module(PKG + ".graphs")
         stepper = graphs.GraphedTrainStep(model, None, opt, forward_loss=lambda d: forward_loss(model, d))
@@ -64,6 +72,13 @@ def main(B=8, steps=5, warmup=3):
     prof = _lib.stop_kernel_timing()
     tot = sum(r["ms"] for r in prof.values())
     shares = {k: round(v["ms"] / tot, 4) for k, v in sorted(prof.items(), key=lambda kv: -kv[1]["ms"])[:8]}
+    if WHICH != "base":
+        print(json.dumps({"workload": f"MatPES {WHICH} ({MODELS[WHICH]}; lmax 4, mmax 4, 6 blocks) train step with autograd "
+                                      "forces (double backward)", "structures_per_s": B / (ms / 1e3), "ms_per_step": ms,
+                          "launch": "CUDA graph replay" if graphed else "eager", "structures": B,
+                          "atoms": int(data["pos"].shape[0]), "edges": E, "loss": float(loss), "params": model.num_params,
+                          "kernel_time_shares": shares, "kernel_ms_total": tot}))
+        return
     # CPU oracle port: 2 cells, same pattern
     from oracle import eqv2_oracle as O
     torch.set_num_threads(os.cpu_count())
