@@ -56,6 +56,14 @@ def real_sh_integral(lmax, xyz):
     return torch.stack(cols, dim=-1)
 
 
+_SIZES = {"counts": None}
+
+
+def set_structure_sizes(counts):
+    """Atoms per structure of the batch the next forward works on (host ints), or None."""
+    _SIZES["counts"] = None if counts is None else [int(c) for c in counts]
+
+
 class GlobalNodeAttentionHTR_with_ROPE(nn.Module):
     def __init__(self, sphere_channels, lmax, num_heads=8, dropout=0.0, num_rbf=16, rbf_cutoff=10.0, use_rope=True,
                  rope_dim=16):
@@ -87,9 +95,15 @@ class GlobalNodeAttentionHTR_with_ROPE(nn.Module):
         N, K, C = x_emb.shape
         H, D = self.num_heads, self.head_dim
         dev = x_emb.device
-        wl = torch.tensor([1.0 / (2 * l + 1) for l in range(self.lmax + 1) for _ in range(2 * l + 1)], dtype=x_emb.dtype,
-                          device=dev)
-        counts = torch.bincount(batch).tolist()
+        key = (str(dev), x_emb.dtype)
+        if getattr(self, "_wl_key", None) != key:          # built once per device: no host->device copy per call
+            self._wl = torch.tensor([1.0 / (2 * l + 1) for l in range(self.lmax + 1) for _ in range(2 * l + 1)],
+                                    dtype=x_emb.dtype, device=dev)
+            self._wl_key = key
+        wl = self._wl
+        # structure sizes: announced by the model wrapper when it already has them on the host (set_structure_sizes:
+        # keeps this module free of device read-backs, hence capturable in a CUDA graph), else as the reference (:1487)
+        counts = list(_SIZES["counts"]) if _SIZES["counts"] is not None else torch.bincount(batch).tolist()
         starts = [0]
         for c in counts:
             starts.append(starts[-1] + c)

@@ -68,7 +68,10 @@ class GraphedTrainStep:
 
     def __call__(self, data):
         full = self._with_prepared(data)
-        sig = (int(full["pos"].shape[0]), int(full["edge_index"].shape[1]), len(full["natoms"]))
+        # host-side entries of the prepared inputs (e.g. the structure sizes the all-to-all attention loops over) are
+        # baked into the capture: they are part of the signature
+        sig = (int(full["pos"].shape[0]), int(full["edge_index"].shape[1]), len(full["natoms"])) + \
+            tuple(v for k, v in sorted(full.items()) if isinstance(v, tuple))
         hit = self.graphs.get(sig)
         if hit is None:
             if len(self.graphs) >= self.max_graphs:
