@@ -222,7 +222,8 @@ gather_rotate_drad_kernel(const float* __restrict__ x, const long long* __restri
 }
 
 // Node-centric kernels (deterministic, no atomics).  CTA = (node, slice of CW channels), 256 threads = G groups of CW
-// threads; every group walks its share of the node's edges, one edge per iteration:
+// threads (measured: CW = 128 / G = 2 beats 64 / 4 beats 32 / 8 -- every extra group costs a Wigner staging and a
+// reduction round); every group walks its share of the node's edges, one edge per iteration:
 //   * the edge's data columns (dA and radial weights, or values and attention weight) are requested first and the
 //     Wigner blocks staged second, so an iteration exposes one memory latency instead of one per degree
 //     (ncu r01: long_scoreboard 6.7 / 25 stall cycles per issue, 640 CTAs of serial edge walks at 12-32 % of HBM peak);
@@ -480,7 +481,7 @@ extern "C" int eqv2_gather_rotate_dx(const float* wig, const float* rad, const f
                                      long long N, int C, int lmax, int mmax, int Kr, int nrad, void* stream) {
   if (N == 0) return 0;
   EQV2_REQUIRE(C > 0, "gather_rotate_dx: C=%d out of range", C);
-  const int CW = C > 32 ? 64 : 32;
+  const int CW = C > 64 ? 128 : (C > 32 ? 64 : 32);      // 2 edge groups (source / destination role) x 128 channels
   const size_t smem = (size_t)(lmax + 1) * (lmax + 1) * CW * sizeof(float);
 #define X(L_, M_)                                                                                              \
   if (lmax == L_ && mmax == M_) {                                                                              \
@@ -519,7 +520,7 @@ extern "C" int eqv2_rotinv_reduce_fwd(const float* val, const float* alpha, cons
   if (N == 0) return 0;
   EQV2_REQUIRE(Cv > 0, "rotinv_reduce_fwd: Cv=%d out of range", Cv);
   EQV2_REQUIRE(alpha == nullptr || (heads > 0 && Cv % heads == 0), "rotinv_reduce_fwd: heads must divide Cv");
-  const int CW = Cv > 32 ? 64 : 32;
+  const int CW = Cv > 64 ? 128 : (Cv > 32 ? 64 : 32);
   const size_t smem = (size_t)(lmax + 1) * (lmax + 1) * CW * sizeof(float);
 #define X(L_, M_)                                                                                              \
   if (lmax == L_ && mmax == M_) {                                                                              \
