@@ -43,7 +43,8 @@ constexpr int NUM_WORKER_WARPS = 8;                // warps 2-9 (TMEM lane quart
 constexpr int NUM_THREADS = (2 + NUM_WORKER_WARPS) * 32;
 constexpr int TMEM_COLS = 512;                     // buffer b: D_hh at b*256, D_lo at b*256 + 128
 constexpr int CHUNK_KB = 4;                        // k-blocks per promoted hi*hi chain (16 tcgen05.mma)
-constexpr size_t SMEM_BYTES = (size_t)STAGES * STAGE_BYTES + 1024 /*align*/ + 256 /*barriers*/;
+constexpr int EPI_PATCH_BYTES = NUM_WORKER_WARPS * 16 * 36 * 4;   // per worker warp: a padded 16 x 32 fp32 transposition patch
+constexpr size_t SMEM_BYTES = (size_t)STAGES * STAGE_BYTES + 1024 /*align*/ + 256 /*barriers*/ + EPI_PATCH_BYTES;
 
 struct alignas(64) HGroup {
   CUtensorMap mapA, mapB;
@@ -196,6 +197,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) gemm_f16_kernel(const __grid_c
   uint64_t* acc_full = bars + 2 * STAGES;     // [2]       chunk complete in TMEM buffer b
   uint64_t* acc_empty = bars + 2 * STAGES + 2;  // [2]     workers drained buffer b
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * STAGES + 4);
+  float* epi_patch = reinterpret_cast<float*>(tiles + (size_t)STAGES * STAGE_BYTES + 256);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
@@ -350,7 +352,57 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) gemm_f16_kernel(const __grid_c
       // ---- epilogue (overlaps the next tile's main loop: TMEM is already released) ----
       const int row = W.m0 + q * 32 + lane;
       const bool atomic = P.split_k > 1;
-      if (row < G.M) {
+      const float sc = ia * ib;
+      // Fast path (plain row-major C, 16-byte aligned rows, N % 4 == 0, no split-K): the accumulators are row-per-lane,
+      // so a direct float4 store touches 32 different 128-byte lines per warp instruction (512 LSU tag cycles per warp and
+      // tile, 4 096 per tile over the 8 worker warps: longer than the MMAs of a K = 128 tile).  Each warp instead passes
+      // 16 x 32 blocks through a padded shared-memory patch and stores 4 rows x 128 bytes per instruction: same number
+      // of store instructions, 8x fewer lines per instruction.
+      const bool fast = !atomic && (G.ldc & 3) == 0 && (G.c_bs & 3) == 0 && (G.N & 3) == 0 &&
+                        (reinterpret_cast<uintptr_t>(G.C) & 15) == 0 && ((W.n0 & 3) == 0);
+      if (fast) {
+        float* patch = epi_patch + (warp - 2) * (16 * 36);
+        const int r16 = lane & 15, c4 = (lane & 7) * 4, rsub = lane >> 3;
+#pragma unroll
+        for (int cc = 0; cc < 2; ++cc) {
+          const int col = W.n0 + half * 64 + cc * 32 + c4;
+          const bool col_ok = col < G.N;
+          float4 bv = make_float4(0.f, 0.f, 0.f, 0.f);
+          if (G.bias != nullptr && col_ok) bv = __ldg(reinterpret_cast<const float4*>(G.bias + col));
+#pragma unroll
+          for (int rh = 0; rh < 2; ++rh) {
+            if ((lane >> 4) == rh) {
+#pragma unroll
+              for (int j = 0; j < 8; ++j)
+                *reinterpret_cast<float4*>(patch + r16 * 36 + 4 * j) =
+                    make_float4(acc[cc * 32 + 4 * j] * sc, acc[cc * 32 + 4 * j + 1] * sc, acc[cc * 32 + 4 * j + 2] * sc,
+                                acc[cc * 32 + 4 * j + 3] * sc);
+            }
+            __syncwarp();
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+              const int rl = 4 * i + rsub;
+              const int grow = W.m0 + q * 32 + rh * 16 + rl;
+              float4 o = *reinterpret_cast<const float4*>(patch + rl * 36 + c4);
+              if (grow < G.M && col_ok) {
+                long long roff = (long long)grow * G.ldc;
+                if (G.c_rpb != 0) {                      // two-level row map (degree slabs of [N, K, C])
+                  const int qd = grow / G.c_rpb;
+                  roff = (long long)qd * G.c_bs + (long long)(grow - qd * G.c_rpb) * G.ldc;
+                }
+                float* cp = G.C + roff + col;
+                o.x += bv.x; o.y += bv.y; o.z += bv.z; o.w += bv.w;
+                if (G.accumulate) {
+                  const float4 p = *reinterpret_cast<const float4*>(cp);
+                  o.x += p.x; o.y += p.y; o.z += p.z; o.w += p.w;
+                }
+                *reinterpret_cast<float4*>(cp) = o;
+              }
+            }
+            __syncwarp();
+          }
+        }
+      } else if (row < G.M) {
         const int col0 = half * 64;
         long long roff = (long long)row * G.ldc;
         if (G.c_rpb != 0) {
@@ -359,31 +411,14 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) gemm_f16_kernel(const __grid_c
         }
         float* crow = G.C + roff + W.n0 + col0;
         const int ncol = min(64, G.N - W.n0 - col0);
-        const bool vec = (ncol == 64) && ((reinterpret_cast<uintptr_t>(crow) & 15) == 0) && !atomic;
-        if (vec) {
 #pragma unroll
-          for (int x = 0; x < 64; x += 4) {
-            float4 o = make_float4(acc[x] * ia * ib, acc[x + 1] * ia * ib, acc[x + 2] * ia * ib, acc[x + 3] * ia * ib);
-            if (G.bias != nullptr) {
-              const float4 bb = __ldg(reinterpret_cast<const float4*>(G.bias + W.n0 + col0 + x));
-              o.x += bb.x; o.y += bb.y; o.z += bb.z; o.w += bb.w;
-            }
-            if (G.accumulate) {
-              const float4 p = *reinterpret_cast<const float4*>(crow + x);
-              o.x += p.x; o.y += p.y; o.z += p.z; o.w += p.w;
-            }
-            *reinterpret_cast<float4*>(crow + x) = o;
-          }
-        } else {
-#pragma unroll
-          for (int x = 0; x < 64; ++x) {
-            if (x < ncol) {
-              float o = acc[x] * ia * ib;
-              if (G.bias != nullptr && W.ks == 0) o += __ldg(G.bias + W.n0 + col0 + x);
-              if (atomic) atomicAdd(crow + x, o);
-              else if (G.accumulate) crow[x] += o;
-              else crow[x] = o;
-            }
+        for (int x = 0; x < 64; ++x) {
+          if (x < ncol) {
+            float o = acc[x] * sc;
+            if (G.bias != nullptr && W.ks == 0) o += __ldg(G.bias + W.n0 + col0 + x);
+            if (atomic) atomicAdd(crow + x, o);
+            else if (G.accumulate) crow[x] += o;
+            else crow[x] = o;
           }
         }
       }
