@@ -28,7 +28,7 @@ PKG = "equivarianttransformermpnn4quantumcomputations_b200"
 # dram__bytes_read.sum + dram__bytes_write.sum of ONE launch of the dominant kernel from the committed `ncu --set full`
 # captures: eqv2_gemm_f16 = conv1 forward m=0 block (48.1 GFLOP, 155 MB of operands + output; profiles/
 # r01k_ncu_gemm_f16_summary.txt), eqv2_gemm_tc = whole conv1 forward (153 GFLOP; profiles/r01c_ncu_gemm_tc_summary.txt)
-TRAFFIC = {"eqv2_gemm_tc": 2.18e9, "eqv2_gemm_f16": 1.261e8}
+TRAFFIC = {"eqv2_gemm_tc": 2.18e9, "eqv2_gemm_f16": 1.289e8}
 
 METRIC = "oc20_s2ef_train_structures_per_s"
 UNIT = "structures/s"
