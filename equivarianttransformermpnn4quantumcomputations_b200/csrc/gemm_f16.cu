@@ -635,7 +635,7 @@ extern "C" int eqv2_split_f16(const eqv2_split_desc* descs, int n, void* stream)
     EQV2_REQUIRE(d.slab_k >= 0 && (d.slab_k == 0 || (d.rows % d.slab_k == 0 && d.rows < (1ll << 31))),
                  "eqv2_split_f16: item %d: rows must be a multiple of slab_k", i);
     t.slab_k = d.slab_k;
-    t.absmax_given = d.absmax_given ? 1 : 0;
+    t.absmax_given = (d.absmax_given == 1) ? 1 : 0;
     const long long groups = d.rows_pad * (d.cols_pad / 8);
     long long nb = (groups + 2047) / 2048;                 // >= 8 groups (128 B of output per plane) per thread
     if (nb < 1) nb = 1;
@@ -643,8 +643,8 @@ extern "C" int eqv2_split_f16(const eqv2_split_desc* descs, int n, void* stream)
     t.block_start = blocks;
     t.nblocks = (int)nb;
     blocks += (int)nb;
-    if (!d.absmax_given) {
-      need_pass = true;
+    if (d.absmax_given != 1) need_pass = true;
+    if (d.absmax_given == 0) {                      // 2: the caller hands in a slot that is already zero
       cudaError_t e = cudaMemsetAsync(d.absmax, 0, EQV2_ABSMAX_SLOTS * sizeof(float), (cudaStream_t)stream);
       EQV2_REQUIRE(e == cudaSuccess, "eqv2_split_f16: memset failed: %s", cudaGetErrorString(e));
     }

@@ -539,7 +539,7 @@ class SplitF16:
         self.rows, self.cols, self.slab_k = src.rows, src.cols, src.slab_k
         self.cols_pad = (self.cols + 63) // 64 * 64
         self.buf = torch.empty(2, self.rows, self.cols_pad, dtype=torch.float16, device=src.t.device)
-        self.absmax = torch.empty(ABSMAX_SLOTS, dtype=_F32, device=src.t.device)
+        self.absmax = _zeroed_slot(src.t.device)
         self.version = src.t._version
 
     @property
@@ -550,9 +550,25 @@ class SplitF16:
 _ABSMAX = {}             # storage pointer -> (weakref(tensor), slot, version): max |v| written by the producing kernel
 
 
+_SLOT_ARENA = {"buf": None, "next": 0}
+_SLOT_ARENA_SIZE = 512
+
+
+def _zeroed_slot(device):
+    """One zero-initialised absmax slot (ABSMAX_SLOTS floats) out of an arena that is zero-filled 512 slots at a time:
+    one fill launch per ~1.7 train steps instead of one fill / memset node per producer and per operand split."""
+    a = _SLOT_ARENA
+    if a["buf"] is None or a["next"] >= _SLOT_ARENA_SIZE or a["buf"].device != device:
+        a["buf"] = torch.zeros(_SLOT_ARENA_SIZE, ABSMAX_SLOTS, dtype=_F32, device=device)
+        a["next"] = 0
+    slot = a["buf"][a["next"]]
+    a["next"] += 1
+    return slot
+
+
 def _absmax_slot(device):
-    """Zero-initialised device float for a producer kernel's `absmax` output (only allocated in f16x3 mode)."""
-    return torch.zeros(ABSMAX_SLOTS, dtype=_F32, device=device) if _GEMM_MODE["mode"] == "f16x3" else None
+    """Zero-initialised slot for a producer kernel's `absmax` output (only allocated in f16x3 mode)."""
+    return _zeroed_slot(device) if _GEMM_MODE["mode"] == "f16x3" else None
 
 
 def _register_absmax(t, slot):
@@ -603,6 +619,7 @@ def reset_caches():
     capture (graphs.py): work skipped because of a cache hit would be missing from the captured step."""
     _plan_cache.clear()
     _ABSMAX.clear()
+    _SLOT_ARENA["buf"] = None          # slots handed out inside a capture must be zero-filled inside it
 
 
 def _find_split(src):
@@ -634,7 +651,7 @@ def _splits_for(srcs):
         for a, (src, sp, given) in zip(arr, part):
             a.src, a.dst, a.absmax = src.t.data_ptr(), sp.buf.data_ptr(), sp.absmax.data_ptr()
             a.rows, a.cols, a.rows_pad, a.cols_pad, a.slab_k = sp.rows, sp.cols, sp.rows, sp.cols_pad, sp.slab_k
-            a.absmax_given = int(given)
+            a.absmax_given = 1 if given else 2          # 2: to be computed, slot already zero (no memset node)
         nb = sum((8.0 if given else 12.0) * sp.rows * sp.cols for _, sp, given in part)
         _lib.call("eqv2_split_f16", ctypes.cast(arr, ctypes.c_void_p), len(part), _lib.stream_ptr(),
                   n_kernels=1 if all(g for _, _, g in part) else 2, work=(0.0, nb))

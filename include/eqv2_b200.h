@@ -64,7 +64,8 @@ typedef struct {
   void* dst;       /* fp16 [2][rows_pad][cols_pad] */
   float* absmax;   /* EQV2_ABSMAX_SLOTS (64) floats whose maximum is max |v| of src; written by the call */
   long long rows, cols, rows_pad, cols_pad;
-  int absmax_given; /* 1: *absmax already holds max |v| of src (written by the producing kernel): skip the reduction pass */
+  int absmax_given; /* 0: compute max |v| (the call zeroes the slot first); 1: absmax already holds it (written by the
+                       producing kernel): skip the reduction pass; 2: compute it, the slot is already zero */
   int slab_k;      /* 0: plain.  > 0: src is a node tensor [rows / slab_k, slab_k = (lmax+1)^2, cols] (so3.py:76-88) and dst
                       receives its degree slabs one after the other -- slab l = rows [n l^2, n (l+1)^2), row (node, j) at
                       node (2l+1) + j -- so that every SO3_LinearV2 block (so3.py:722-727) is a plain matrix */
