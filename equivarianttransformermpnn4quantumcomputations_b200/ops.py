@@ -799,9 +799,14 @@ class SliceOuter(torch.autograd.Function):
             descs.append(_desc(U, V, U, None, m, n, rows, 1, 0, _plain(U.shape[1]), _plain(V.shape[1]), _plain(n),
                                a_off=uo, b_off=vo))
         split = _pick_split(descs, True) if rows > 0 else 1
-        outs = []
-        for d, ((uo, m), (vo, n)) in zip(descs, zip(us, vs)):
-            W = (torch.zeros if (split > 1 or rows == 0) else torch.empty)(m, n, dtype=_F32, device=U.device)
+        # all groups' outputs come out of ONE allocation (one zero-fill launch when split-K atomics need it, not one per
+        # group); every block starts 16-byte aligned
+        sizes = [(m * n + 3) // 4 * 4 for (_, m), (_, n) in zip(us, vs)]
+        flat = (torch.zeros if (split > 1 or rows == 0) else torch.empty)(sum(sizes), dtype=_F32, device=U.device)
+        outs, off = [], 0
+        for d, sz, ((uo, m), (vo, n)) in zip(descs, sizes, zip(us, vs)):
+            W = flat[off:off + m * n].view(m, n)
+            off += sz
             d.C = W.data_ptr()
             outs.append(W)
         sp = run_gemm(descs, split) if rows > 0 else {}
