@@ -566,6 +566,29 @@ def _zeroed_slot(device):
     return slot
 
 
+_ZERO_ARENA = {"buf": None, "next": 0}
+_ZERO_ARENA_FLOATS = 1 << 16
+
+
+def _small_zeros(shape, device):
+    """Zero-initialised fp32 tensor for the small atomically-accumulated parameter gradients (LayerNorm / norm weights,
+    attention dot vectors): carved out of a 256 KB arena that is zero-filled once per refill instead of one fill launch
+    per tensor (tiny nodes are disproportionately expensive inside a replayed CUDA graph)."""
+    n = 1
+    for d in shape:
+        n *= int(d)
+    n4 = (n + 3) // 4 * 4
+    if n4 > _ZERO_ARENA_FLOATS // 8:
+        return torch.zeros(shape, dtype=_F32, device=device)
+    a = _ZERO_ARENA
+    if a["buf"] is None or a["next"] + n4 > _ZERO_ARENA_FLOATS or a["buf"].device != device:
+        a["buf"] = torch.zeros(_ZERO_ARENA_FLOATS, dtype=_F32, device=device)
+        a["next"] = 0
+    out = a["buf"][a["next"]:a["next"] + n].view(shape)
+    a["next"] += n4
+    return out
+
+
 def _absmax_slot(device):
     """Zero-initialised slot for a producer kernel's `absmax` output (only allocated in f16x3 mode)."""
     return _zeroed_slot(device) if _GEMM_MODE["mode"] == "f16x3" else None
@@ -620,6 +643,7 @@ def reset_caches():
     _plan_cache.clear()
     _ABSMAX.clear()
     _SLOT_ARENA["buf"] = None          # slots handed out inside a capture must be zero-filled inside it
+    _ZERO_ARENA["buf"] = None
 
 
 def _find_split(src):
@@ -1335,9 +1359,9 @@ class EdgeActAlphaFn(torch.autograd.Function):
         if galpha is None:
             galpha = torch.zeros_like(alpha)
         galpha = galpha.contiguous()
-        g_lnw = torch.zeros_like(ln_w) if ln_w is not None else None
-        g_lnb = torch.zeros_like(ln_b) if ln_b is not None else None
-        g_dot = torch.zeros_like(alpha_dot)
+        g_lnw = _small_zeros(ln_w.shape, dev) if ln_w is not None else None
+        g_lnb = _small_zeros(ln_b.shape, dev) if ln_b is not None else None
+        g_dot = _small_zeros(alpha_dot.shape, dev)
         dlogits = torch.empty_like(alpha)
         _lib.call("eqv2_attn_alpha_bwd", yp, W, _lib.ptr(ln_w), _lib.ptr(ln_b), alpha_dot.data_ptr(),
                   plan.rowptr_dst.data_ptr(), plan.perm_dst.data_ptr(), alpha.data_ptr(), galpha.data_ptr(),
@@ -1497,8 +1521,8 @@ class EquivNormFn(torch.autograd.Function):
         bw_c = (ctypes.c_float * len(bw))(*bw)
         go = go.contiguous()
         gx = torch.empty_like(x)
-        gw = torch.zeros_like(w)
-        gb = torch.zeros(C, dtype=_F32, device=x.device)
+        gw = _small_zeros(w.shape, w.device)
+        gb = _small_zeros((C,), x.device)
         _lib.call("eqv2_equiv_norm_bwd", x.data_ptr(), w.data_ptr(), go.data_ptr(), inv.data_ptr(), mean.data_ptr(),
                   gx.data_ptr(), gw.data_ptr(), gb.data_ptr(), N, C, lmax, ng, ctypes.cast(gol_c, ctypes.c_void_p),
                   ctypes.cast(bw_c, ctypes.c_void_p), _lib.stream_ptr())
@@ -1531,8 +1555,8 @@ class LnSiluFn(torch.autograd.Function):
         rows, width = x.shape
         gy = gy.contiguous()
         gx = torch.empty_like(x)
-        gw = torch.zeros_like(w)
-        gb = torch.zeros_like(b)
+        gw = _small_zeros(w.shape, w.device)
+        gb = _small_zeros(b.shape, b.device)
         _lib.call("eqv2_ln_silu_bwd", x.data_ptr(), w.data_ptr(), b.data_ptr(), gy.data_ptr(), gx.data_ptr(),
                   gw.data_ptr(), gb.data_ptr(), rows, width, eps, _lib.stream_ptr())
         return gx, gw, gb, None
