@@ -267,6 +267,9 @@ def run_b200(args):
         launches += stepper.captured_launches() * args.steps      # kernels inside the replayed graphs
         opt.zero_grad(set_to_none=True)
         stepper.active = None
+    if hasattr(torch.autograd.graph, "set_warn_on_accumulate_grad_stream_mismatch"):
+        # the parameters' AccumulateGrad nodes were created on the capture stream; this one eager pass runs on the default
+        torch.autograd.graph.set_warn_on_accumulate_grad_stream_mismatch(False)
     _lib.start_kernel_timing()
     eager_step(resident)
     prof = _lib.stop_kernel_timing()
