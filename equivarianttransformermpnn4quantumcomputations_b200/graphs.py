@@ -1,18 +1,20 @@
 """CUDA-graph replay of a training step.
 
-A train step of this path is ~3 900 kernel launches of 5-500 us: enqueueing them from Python costs the host about as long
+A train step of this path is ~2 900 kernel launches of 2-500 us: enqueueing them from Python costs the host about as long
 as the GPU needs to run them (bench.py reports both), so the step is captured once per problem signature
 (atoms, edges, structures) and replayed.  Only the data-dependent head stays eager -- the neighbour list (its edge count
 is read back to size the edge tensors) and the edge frames (`model.prepare`) -- and the optimizer update, which runs
 eagerly on the gradients the replay leaves in place (its state and step count behave exactly as without graphs).
-A batch with a new signature is captured again (or runs eagerly with `max_graphs=0`)."""
+A batch with a new signature is captured again, up to `max_graphs` signatures (each capture keeps its activations in the
+graphs' shared private memory pool: several GB for the OC20 step, ~100 GB for config 5 at 8 x 200 atoms); beyond that, or
+with `max_graphs=0`, the step runs eagerly."""
 import torch
 
 from . import ops
 
 
 class GraphedTrainStep:
-    def __init__(self, model, loss_fn, optimizer, max_graphs=8, warmup=2, grad_sync=None, forward_loss=None):
+    def __init__(self, model, loss_fn, optimizer, max_graphs=4, warmup=2, grad_sync=None, forward_loss=None):
         """model(data) -> outputs; loss_fn(outputs, data) -> scalar -- or `forward_loss(data)` -> scalar for steps that
         need more than that (MatPES: forces = -autograd.grad(E, pos, create_graph=True) inside the loss).
         `model.prepare(data)` must return the dict of data-dependent inputs the model then takes from `data` (OC20:
