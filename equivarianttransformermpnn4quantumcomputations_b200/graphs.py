@@ -55,6 +55,9 @@ class GraphedTrainStep:
                 self._eager(static)
         torch.cuda.current_stream().wait_stream(side)
         self.optimizer.zero_grad(set_to_none=True)  # the captured backward then ASSIGNS the .grad tensors it allocates
+        torch.cuda.synchronize()
+        torch.cuda.empty_cache()                    # the warm-up's activations sit in the caching allocator; the capture
+                                                    # allocates its own copy in the graph pool -- do not hold both
         ops.reset_caches()
         from . import _lib
         n0 = _lib.launch_count()
