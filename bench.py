@@ -265,8 +265,7 @@ def run_b200(args):
     barrier()
     if stepper is not None:
         launches += stepper.captured_launches() * args.steps      # kernels inside the replayed graphs
-        opt.zero_grad(set_to_none=True)
-        stepper.active = None
+        stepper.release()               # the eager profiling pass below needs the memory of the graph pool
     if hasattr(torch.autograd.graph, "set_warn_on_accumulate_grad_stream_mismatch"):
         # the parameters' AccumulateGrad nodes were created on the capture stream; this one eager pass runs on the default
         torch.autograd.graph.set_warn_on_accumulate_grad_stream_mismatch(False)

@@ -103,6 +103,18 @@ class GraphedTrainStep:
         self.optimizer.step()
         return loss
 
+    def release(self):
+        """Drop every captured graph and the private memory pool they share (their activations stay allocated for as
+        long as a graph exists); the gradients the last replay left in place go with them."""
+        import gc
+        self.optimizer.zero_grad(set_to_none=True)
+        self.graphs.clear()
+        self.pool = None
+        self.active = None
+        gc.collect()
+        torch.cuda.synchronize()
+        torch.cuda.empty_cache()
+
     def captured_launches(self, sig=None):
         """C-ABI kernel launches inside the captured step (the library's own count at capture time)."""
         hit = self.graphs.get(sig if sig is not None else self.active)
