@@ -39,10 +39,7 @@ class SO2_m_Convolution(nn.Module):
 
     def block_weight(self):
         """[[Wr, -Wi], [Wi, Wr]]  ([2o', 2k]) -- differentiable w.r.t. fc.weight."""
-        W = self.fc.weight
-        half = W.shape[0] // 2
-        Wr, Wi = W[:half], W[half:]
-        return torch.cat([torch.cat([Wr, -Wi], dim=1), torch.cat([Wi, Wr], dim=1)], dim=0)
+        return ops.so2_block_weight(self.fc.weight)
 
     def forward(self, x_m):
         """API parity with the reference: x_m [E, 2, k] -> [E, 2, o']."""

@@ -83,6 +83,8 @@ _PROTOS = {
     "eqv2_csr_from_index": [P, L, L, P, P, P, P, P],
     "eqv2_segment_sum_fwd": [P, L, P, P, L, I, P],
     "eqv2_segment_sum_bwd": [P, P, P, L, P],
+    "eqv2_so2_block_weight": [P, P, I, I, P],
+    "eqv2_so2_block_weight_adj": [P, P, I, I, P],
     "eqv2_embed_rows": [P, P, P, L, I, P],
     "eqv2_seg_colsum": [P, L, P, P, L, I, I, I, P, P, P],
 }

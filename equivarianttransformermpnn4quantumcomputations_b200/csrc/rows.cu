@@ -62,7 +62,50 @@ __global__ void seg_colsum_final_kernel(const float* __restrict__ partial, int C
   }
 }
 
+// SO(2) convolution weights of order m > 0 in real 2x2 block form (so2_ops.py:53-61: out+ = x_r W_r - x_i W_i,
+// out- = x_r W_i + x_i W_r):  B[2h, 2k] = [[Wr, -Wi], [Wi, Wr]] from fc.weight W[2h, k] = [Wr; Wi], and its adjoint
+// gW = [gB00 + gB11; gB10 - gB01].  One launch each instead of 2 slices + neg + 3 cats (and, in backward, 3 narrow
+// views + neg + 2 x (zero-fill + copy) + add): ~12 graph nodes per m-block and pass.
+__global__ void so2_block_weight_kernel(const float* __restrict__ W, float* __restrict__ B, int h, int k) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  const long long total = 4ll * h * k;
+  if (i >= total) return;
+  const int r = (int)(i / (2 * k)), c = (int)(i % (2 * k));
+  float v;
+  if (r < h) v = (c < k) ? W[(long long)r * k + c] : -W[(long long)(h + r) * k + (c - k)];
+  else v = (c < k) ? W[(long long)r * k + c] : W[(long long)(r - h) * k + (c - k)];
+  B[i] = v;
+}
+
+__global__ void so2_block_weight_adj_kernel(const float* __restrict__ gB, float* __restrict__ gW, int h, int k) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  const long long total = 2ll * h * k;
+  if (i >= total) return;
+  const int r = (int)(i / k), c = (int)(i % k);
+  const long long ld = 2ll * k;
+  float v;
+  if (r < h) v = gB[(long long)r * ld + c] + gB[(long long)(h + r) * ld + k + c];
+  else v = gB[(long long)r * ld + c] - gB[(long long)(r - h) * ld + k + c];
+  gW[i] = v;
+}
+
 }  // namespace
+
+extern "C" int eqv2_so2_block_weight(const float* W, float* B, int h, int k, void* stream) {
+  const long long total = 4ll * h * k;
+  if (total == 0) return 0;
+  EQV2_LAUNCH(so2_block_weight_kernel, dim3((unsigned)((total + 255) / 256)), dim3(256), 0, stream, W, B, h, k);
+  EQV2_CHECK_LAUNCH("eqv2_so2_block_weight");
+  return 0;
+}
+
+extern "C" int eqv2_so2_block_weight_adj(const float* gB, float* gW, int h, int k, void* stream) {
+  const long long total = 2ll * h * k;
+  if (total == 0) return 0;
+  EQV2_LAUNCH(so2_block_weight_adj_kernel, dim3((unsigned)((total + 255) / 256)), dim3(256), 0, stream, gB, gW, h, k);
+  EQV2_CHECK_LAUNCH("eqv2_so2_block_weight_adj");
+  return 0;
+}
 
 extern "C" int eqv2_embed_rows(const float* table, const long long* idx, float* out, long long E, int C, void* stream) {
   if (E == 0 || C == 0) return 0;

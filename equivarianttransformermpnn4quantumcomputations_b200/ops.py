@@ -382,6 +382,44 @@ def embed_rows(table, idx, csr):
     return EmbedRowsFn.apply(table.contiguous(), idx.contiguous(), csr)
 
 
+class BlockWeightFn(torch.autograd.Function):
+    """B[2h, 2k] = [[Wr, -Wi], [Wi, Wr]] from W[2h, k] = [Wr; Wi]  (so2_ops.py:53-61 folded into the GEMM operand)."""
+
+    @staticmethod
+    def forward(ctx, W):
+        _lib.check_device(W)
+        assert W.is_contiguous() and W.dim() == 2 and W.shape[0] % 2 == 0
+        h, k = int(W.shape[0]) // 2, int(W.shape[1])
+        B = torch.empty(2 * h, 2 * k, dtype=_F32, device=W.device)
+        _lib.call("eqv2_so2_block_weight", W.data_ptr(), B.data_ptr(), h, k, _lib.stream_ptr())
+        return B
+
+    @staticmethod
+    def backward(ctx, gB):
+        return BlockWeightAdjFn.apply(gB.contiguous())
+
+
+class BlockWeightAdjFn(torch.autograd.Function):
+    """gW[2h, k] = [gB00 + gB11; gB10 - gB01] -- the adjoint of BlockWeightFn (and vice versa: both maps are linear)."""
+
+    @staticmethod
+    def forward(ctx, gB):
+        _lib.check_device(gB)
+        assert gB.is_contiguous()
+        h, k = int(gB.shape[0]) // 2, int(gB.shape[1]) // 2
+        gW = torch.empty(2 * h, k, dtype=_F32, device=gB.device)
+        _lib.call("eqv2_so2_block_weight_adj", gB.data_ptr(), gW.data_ptr(), h, k, _lib.stream_ptr())
+        return gW
+
+    @staticmethod
+    def backward(ctx, ggW):
+        return BlockWeightFn.apply(ggW.contiguous())
+
+
+def so2_block_weight(W):
+    return BlockWeightFn.apply(W.contiguous())
+
+
 class ColsumFn(torch.autograd.Function):
     """X[:, off:off+n].sum(0) for a contiguous matrix, fixed summation order (bias gradients)."""
 

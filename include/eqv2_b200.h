@@ -218,6 +218,11 @@ int eqv2_segment_sum_bwd(const float* gout /*[B]*/, const long long* batch, floa
  * eqv2_seg_colsum: out[v,c] = sum over rows i in [rowptr[v], rowptr[v+1]) of src[perm[i]*ld + c] (rowptr NULL: one
  *   segment [0, rows); perm NULL: identity) in a fixed order; `partial` is a [V, S, C] workspace.  Embedding weight
  *   gradients (segments = element types) and bias gradients of the dense layers. */
+/* eqv2_so2_block_weight: B[2h,2k] = [[Wr,-Wi],[Wi,Wr]] from fc.weight W[2h,k] = [Wr;Wi] of an order-m > 0 SO(2)
+ *   convolution (so2_ops.py:53-61), so that the +- recombination is part of the GEMM; _adj: the adjoint map
+ *   gW = [gB00 + gB11; gB10 - gB01] (weight gradient). */
+int eqv2_so2_block_weight(const float* W, float* B, int h, int k, void* stream);
+int eqv2_so2_block_weight_adj(const float* gB, float* gW, int h, int k, void* stream);
 int eqv2_embed_rows(const float* table, const long long* idx, float* out, long long E, int C, void* stream);
 int eqv2_seg_colsum(const float* src, long long ld, const int* rowptr, const int* perm, long long rows, int V, int C,
                     int S, float* partial, float* out, void* stream);
