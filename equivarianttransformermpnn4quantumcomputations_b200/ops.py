@@ -727,11 +727,14 @@ def _split_of(splits, src):
     return splits.get(src.key) if src is not None else None
 
 
+F16_MIN_MACS = 1 << 21      # launches below this many multiply-adds stay on the FFMA engine (tests set it to 0)
+
+
 def _f16_ok(descs):
     """Should the f16x3 engine take this launch?  Measured (profiles/): the persistent TMA kernel beats the FFMA engine
     and the in-kernel-split tf32 engine from ~2 M multiply-adds per launch, operand splits included (a 640 x 128 x 128
     node-level linear takes 69 us on the FFMA engine: 5 CTAs)."""
-    return all(_f16_addressable(d) for d in descs) and sum(d.M * d.N * d.K for d in descs) >= (1 << 21)
+    return all(_f16_addressable(d) for d in descs) and sum(d.M * d.N * d.K for d in descs) >= F16_MIN_MACS
 
 
 def _f16_addressable(d):

@@ -93,6 +93,45 @@ def test_oc20_small_other_gemm_modes(mode, tol):
         ops.set_gemm_mode(ops.DEFAULT_GEMM_MODE)
 
 
+@pytest.mark.gpu
+@pytest.mark.parametrize("fixture", ["oc20_small_rms_norm_sh.pt", "qm9_small.pt"])
+def test_small_fixtures_with_every_contraction_on_the_f16x3_engine(fixture):
+    """The golden fixtures are small: by default their contractions fall below the tensor-core engine's size threshold
+    and run on the FFMA engine.  Here the threshold is 0, so every addressable GEMM (forward, dgrad, wgrad, degree slabs)
+    goes through operand split + tcgen05 kind::f16 and is compared with the unmodified reference directly."""
+    from conftest import Backend
+    from helpers import pkg
+    ops, _lib = pkg("ops"), pkg("_lib")
+    be = Backend("cuda")
+    fx = golden(fixture)
+    old = ops.F16_MIN_MACS
+    ops.F16_MIN_MACS = 0
+    ops.set_gemm_mode("f16x3")
+    try:
+        _lib.start_kernel_timing()
+        if fixture.startswith("oc20"):
+            model = build_oc20(fx["hyper"], be.device)
+            load_params(model, fx["params"])
+            with fixed_rand_like(fx["rand_vec"] + 0.5):
+                energy, forces = model(_graph_inputs(fx, be))
+            assert rel_err(energy, fx["energy"]) < OUT_TOL and rel_err(forces, fx["forces"]) < OUT_TOL
+            w = torch.linspace(-1, 1, forces.numel(), device=forces.device).view_as(forces)
+            (energy.sum() + (forces * w).sum()).backward()
+        else:
+            model = build_qm9(fx["hyper"], be.device)
+            load_params(model, fx["params"])
+            with fixed_rand_like(fx["rand_vec"] + 0.5):
+                pred = model(_graph_inputs(fx, be))
+            assert rel_err(pred, fx["pred"]) < OUT_TOL
+            (pred * torch.linspace(-1, 1, pred.numel(), device=pred.device).view_as(pred)).sum().backward()
+        prof = _lib.stop_kernel_timing()
+        assert prof.get("eqv2_gemm_f16", {}).get("calls", 0) >= 10, sorted(prof)
+        _check_grads(model, fx)
+    finally:
+        ops.F16_MIN_MACS = old
+        ops.set_gemm_mode(ops.DEFAULT_GEMM_MODE)
+
+
 def test_matpes_v2_train_step_matches_reference(backend):
     """MatPES pattern (train_MatPES_GATAWandB.py:67-91): energy, forces = -autograd.grad(E, pos, create_graph=True),
     then the gradient of a loss on energy AND forces w.r.t. every parameter (double backward), against the golden
