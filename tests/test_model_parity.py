@@ -132,6 +132,39 @@ def test_small_fixtures_with_every_contraction_on_the_f16x3_engine(fixture):
         ops.set_gemm_mode(ops.DEFAULT_GEMM_MODE)
 
 
+@pytest.mark.gpu
+def test_matpes_v2_double_backward_with_every_contraction_on_the_f16x3_engine():
+    """Same as above for the MatPES pattern: energy, autograd forces and the double-backward parameter gradients of the
+    unmodified reference, with every GEMM of all three passes on the f16x3 engine."""
+    from conftest import Backend
+    from helpers import build_matpes_v2, pkg
+    ops, _lib = pkg("ops"), pkg("_lib")
+    be = Backend("cuda")
+    fx = golden("matpes_v2_small.pt")
+    old = ops.F16_MIN_MACS
+    ops.F16_MIN_MACS = 0
+    ops.set_gemm_mode("f16x3")
+    try:
+        model = build_matpes_v2(fx["hyper"], be.device)
+        load_params(model, fx["params"])
+        data = be.to(dict(fx["inputs"]))
+        pos = data["pos"].clone().requires_grad_(True)
+        _lib.start_kernel_timing()
+        out = model(dict(data, pos=pos))
+        assert rel_err(out["energy"], fx["energy"]) < OUT_TOL
+        forces = -torch.autograd.grad(out["energy_total"].sum(), pos, create_graph=True, retain_graph=True)[0]
+        assert rel_err(forces, fx["forces"]) < 2e-5
+        wf = torch.linspace(-1, 1, forces.numel(), device=forces.device).view_as(forces)
+        we = torch.linspace(0.5, 1.5, out["energy"].numel(), device=forces.device).view_as(out["energy"])
+        ((out["energy"] * we).sum() + (forces * wf).sum()).backward()
+        prof = _lib.stop_kernel_timing()
+        assert prof.get("eqv2_gemm_f16", {}).get("calls", 0) >= 30, sorted(prof)
+        _check_grads(model, fx)
+    finally:
+        ops.F16_MIN_MACS = old
+        ops.set_gemm_mode(ops.DEFAULT_GEMM_MODE)
+
+
 def test_matpes_v2_train_step_matches_reference(backend):
     """MatPES pattern (train_MatPES_GATAWandB.py:67-91): energy, forces = -autograd.grad(E, pos, create_graph=True),
     then the gradient of a loss on energy AND forces w.r.t. every parameter (double backward), against the golden
