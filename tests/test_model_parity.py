@@ -133,19 +133,23 @@ def test_small_fixtures_with_every_contraction_on_the_f16x3_engine(fixture):
 
 
 @pytest.mark.gpu
-def test_matpes_v2_double_backward_with_every_contraction_on_the_f16x3_engine():
-    """Same as above for the MatPES pattern: energy, autograd forces and the double-backward parameter gradients of the
-    unmodified reference, with every GEMM of all three passes on the f16x3 engine."""
+@pytest.mark.parametrize("variant,fixture", [("matpes_v2", "matpes_v2_small.pt"), ("gatav2", "matpes_gatav2_small.pt"),
+                                             ("gatav2_phi", "matpes_gatav2_phi_small.pt"),
+                                             ("gatav2_global", "matpes_gatav2_global_small.pt")])
+def test_matpes_family_double_backward_with_every_contraction_on_the_f16x3_engine(variant, fixture):
+    """Same as above for the MatPES pattern (configs 3-5): energy, autograd forces and the double-backward parameter
+    gradients of the unmodified reference, with every GEMM of all three passes on the f16x3 engine."""
+    import helpers
     from conftest import Backend
-    from helpers import build_matpes_v2, pkg
+    from helpers import pkg
     ops, _lib = pkg("ops"), pkg("_lib")
     be = Backend("cuda")
-    fx = golden("matpes_v2_small.pt")
+    fx = golden(fixture)
     old = ops.F16_MIN_MACS
     ops.F16_MIN_MACS = 0
     ops.set_gemm_mode("f16x3")
     try:
-        model = build_matpes_v2(fx["hyper"], be.device)
+        model = getattr(helpers, "build_" + variant)(fx["hyper"], be.device)
         load_params(model, fx["params"])
         data = be.to(dict(fx["inputs"]))
         pos = data["pos"].clone().requires_grad_(True)
