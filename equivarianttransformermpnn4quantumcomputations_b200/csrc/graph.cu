@@ -166,8 +166,9 @@ radius_graph_pbc_kernel(const float* __restrict__ pos, const float* __restrict__
       const double oz = a * c[2] + b * c[5] + cc * c[8];
       const double vx = ((double)pos[3 * j] + ox) - xi, vy = ((double)pos[3 * j + 1] + oy) - yi,
                    vz = ((double)pos[3 * j + 2] + oz) - zi;
-      d = sqrt(vx * vx + vy * vy + vz * vz);
-      ok = (d < cutoff) && (d > 1e-4);
+      // fairchem radius_graph_pbc works on SQUARED distances: within = d^2 <= r_c^2, not-self = d^2 > 1e-4
+      d = vx * vx + vy * vy + vz * vz;
+      ok = (d <= cutoff * cutoff) && (d > 1e-4);
     }
     const unsigned bal = __ballot_sync(0xffffffffu, ok);
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -191,13 +192,14 @@ radius_graph_pbc_kernel(const float* __restrict__ pos, const float* __restrict__
   }
   const int cnt = min(scnt, PBC_CAP);
   const bool trunc = cnt > max_nb;
-  // threshold: the max_nb-th smallest distance (rank max_nb-1 under (d, index) order)
+  // fairchem get_max_neighbors_mask, enforce_max_strictly=False: effective cutoff = distance_sort[:, max_nb] + 0.01 on
+  // SQUARED distances, i.e. the (max_nb + 1)-th smallest (rank max_nb under (d^2, index) order) plus the tolerance
   if (trunc) {
     for (int cidx = threadIdx.x; cidx < cnt; cidx += NB_THREADS) {
       int rank = 0;
       const double dc = sd[cidx];
       for (int k = 0; k < cnt; ++k) rank += (sd[k] < dc) || (sd[k] == dc && k < cidx);
-      if (rank == max_nb - 1) sthr = dc;
+      if (rank == max_nb) sthr = dc;
     }
   }
   __syncthreads();
@@ -237,7 +239,7 @@ radius_graph_pbc_kernel(const float* __restrict__ pos, const float* __restrict__
       const double oz = a * c[2] + b * c[5] + cc * c[8];
       nbr_out[o] = j;
       ctr_out[o] = i;
-      dist_out[o] = (float)sd[cidx];
+      dist_out[o] = (float)sqrt(sd[cidx]);
       vec_out[3 * o] = (float)(((double)pos[3 * j] + ox) - xi);
       vec_out[3 * o + 1] = (float)(((double)pos[3 * j + 1] + oy) - yi);
       vec_out[3 * o + 2] = (float)(((double)pos[3 * j + 2] + oz) - zi);

@@ -446,9 +446,14 @@ def radius_graph_qm9(pos, batch, cutoff, max_neighbors):
 
 def radius_graph_pbc_fairchem(pos, cell, batch, natoms, cutoff, max_neighbors, strict=False):
     """Brute-force stand-in for fairchem radius_graph_pbc + get_pbc_distances as called at
-    equiformerv2_oc20.py:223-234 (un-vendored; PARITY UNPINNED).
-    edge_index[0] = neighbour j, edge_index[1] = centre i, vec = pos[j] + offset - pos[i];
-    per centre keep neighbours with d <= d_(max_neighbors) + 0.01 when not strict."""
+    equiformerv2_oc20.py:223-234 (fairchem-core is un-vendored and un-pinned by the reference; PARITY UNPINNED,
+    SURVEY §8f-1).  Semantics restated from fairchem-core's published `radius_graph_pbc` / `get_max_neighbors_mask`
+    (graph/compute.py, 1.x / 2.x series): candidates are all periodic images with SQUARED distance d2 <= r_c^2 and
+    d2 > 1e-4; a centre with more than `max_neighbors` candidates keeps, when not strict, those with
+    d2 <= d2_sorted[max_neighbors] + 0.01 (the (max_neighbors+1)-th smallest squared distance plus the degeneracy
+    tolerance -- so a truncated centre keeps AT LEAST max_neighbors + 1 edges, which is what makes the reference's
+    _AVG_DEGREE 23.4 at max_neighbors 20), and exactly the max_neighbors nearest when strict.
+    edge_index[0] = neighbour j, edge_index[1] = centre i, vec = pos[j] + offset - pos[i]."""
     ei, dd, vv = [], [], []
     start = 0
     for g, n in enumerate(natoms.tolist()):
@@ -466,16 +471,17 @@ def radius_graph_pbc_fairchem(pos, cell, batch, natoms, cutoff, max_neighbors, s
         offs = cells @ c                                                       # [S,3]
         # vec[i, j, s] = p[j] + off[s] - p[i]
         vec = p.unsqueeze(0).unsqueeze(2) + offs.view(1, 1, -1, 3) - p.view(n, 1, 1, 3)
-        d = vec.norm(dim=-1)
-        ok = (d < cutoff) & (d > 1e-4)
+        d2 = (vec * vec).sum(-1)
+        d = d2.sqrt()
+        ok = (d2 <= cutoff * cutoff) & (d2 > 1e-4)
         ci, cj, cs = torch.where(ok)
-        dsel = d[ci, cj, cs]
+        dsel = d2[ci, cj, cs]
         keep = torch.ones(len(ci), dtype=torch.bool)
         for i in range(n):
             ids = torch.where(ci == i)[0]
             if len(ids) > max_neighbors:
                 ds, order = torch.sort(dsel[ids])
-                thr = ds[max_neighbors - 1] + (0.0 if strict else 0.01)
+                thr = ds[max_neighbors] + 0.01       # non-strict: index max_neighbors of the sorted squared distances
                 drop = ids[dsel[ids] > thr] if not strict else ids[order[max_neighbors:]]
                 keep[drop] = False
         ci, cj, cs = ci[keep], cj[keep], cs[keep]

@@ -1,13 +1,16 @@
-"""ORACLE tooling: import the UNMODIFIED reference (/root/reference/models) in the build
-container.  /root/reference does not exist on the GPU box, so nothing that runs there may
-call this; it is used only by oracle/make_golden.py and the CPU-side pinning tests (which
-skip when the reference tree is absent)."""
+"""ORACLE tooling (TEST INFRASTRUCTURE): import the UNMODIFIED reference.
+
+In the build container that is `/root/reference/models`; on the GPU box (no /root/reference) it is the
+byte-identical copy `oracle/_ref/models` that `oracle/make_ref.py` made here and gpurun shipped
+(git-ignored, never part of the history).  Used by oracle/make_golden.py, the parity tests (checker) and
+bench.py's CPU legs (baseline) -- never by the product path."""
 import os
 import sys
 
 import torch
 
-REF_ROOT = "/root/reference/models"
+_HERE = os.path.dirname(os.path.abspath(__file__))
+REF_ROOT = "/root/reference/models" if os.path.isdir("/root/reference/models") else os.path.join(_HERE, "_ref", "models")
 _SHIM = os.path.join(os.path.dirname(os.path.abspath(__file__)), "refshim")
 _REPO = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 

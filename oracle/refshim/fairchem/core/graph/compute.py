@@ -2,8 +2,9 @@
 equiformerv2_oc20.py:223-234).  fairchem is un-vendored and un-pinned; this brute-force
 restatement follows its documented semantics: all periodic images within `cutoff`,
 edge_index[0] = neighbour j, edge_index[1] = centre i, vec = pos[j] - pos[i] + offset,
-per-centre truncation to `max_neighbors` with a 0.01 A degeneracy tolerance when
-enforce_max_neighbors_strictly=False.  PARITY UNPINNED."""
+per-centre truncation on SQUARED distances: keep d2 <= d2_sorted[max_neighbors] + 0.01 when
+enforce_max_neighbors_strictly=False (fairchem-core `get_max_neighbors_mask`), self images need d2 > 1e-4.
+PARITY UNPINNED: restated from the published fairchem-core source, not checked against a run of it."""
 import torch
 
 from oracle.eqv2_oracle import radius_graph_pbc_fairchem

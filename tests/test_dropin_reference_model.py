@@ -1,7 +1,7 @@
 """Drop-in proof: the UNMODIFIED reference model files (`/root/reference/models/equiformerv2_{qm9,oc20}.py`)
 run on top of this repo's `EquiformerV2Functions` (installed under the bare name) and
-reproduce the golden outputs of the all-reference run.  Needs the reference tree -> build container only
-(skipped on the GPU box, which has no /root/reference)."""
+reproduce the golden outputs of the all-reference run.  On the GPU box the reference tree is the byte-identical
+copy `oracle/_ref/models` made by oracle/make_ref.py (git-ignored, shipped by gpurun)."""
 import importlib
 import os
 import sys
@@ -12,8 +12,10 @@ import torch
 from conftest import REPO, golden
 from helpers import fixed_rand_like, pkg, rel_err
 
-REF = "/root/reference/models"
-pytestmark = pytest.mark.skipif(not os.path.isdir(REF), reason="reference tree not present")
+from oracle import ref_loader
+
+REF = ref_loader.REF_ROOT        # /root/reference/models here, the shipped copy oracle/_ref/models on the GPU box
+pytestmark = pytest.mark.skipif(not os.path.isdir(REF), reason="reference tree not present (run oracle/make_ref.py)")
 
 
 @pytest.fixture

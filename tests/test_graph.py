@@ -85,6 +85,32 @@ def test_radius_graph_pbc_matches_oracle_skewed_cells(backend, strict):
     assert torch.allclose(a[1], b[1], atol=2e-6) and torch.allclose(a[2], b[2], atol=2e-6)
 
 
+def test_radius_graph_pbc_nonstrict_truncation_semantics(backend):
+    """Independent numpy pin of the fairchem-core truncation rule the kernel follows: on SQUARED distances,
+    a centre with more than max_nb candidates keeps d2 <= d2_sorted[max_nb] + 0.01, i.e. at least max_nb + 1 edges;
+    self images need d2 > 1e-4; the cutoff is inclusive."""
+    import numpy as np
+    ops = pkg("ops")
+    rng = np.random.default_rng(3)
+    cell = np.diag([4.1, 4.3, 4.7]) + 0.1 * rng.normal(size=(3, 3))
+    n, cutoff, max_nb = 7, 6.0, 9
+    p = rng.uniform(0, 1, (n, 3)) @ cell
+    pos, cells = torch.tensor(p, dtype=torch.float32), torch.tensor(cell, dtype=torch.float32).unsqueeze(0)
+    natoms, batch = torch.tensor([n]), torch.zeros(n, dtype=torch.long)
+    ei, d, v = ops.radius_graph_pbc(backend.to(pos), backend.to(cells), backend.to(natoms), backend.to(batch), cutoff, max_nb)
+    ei, d = ei.cpu().numpy(), d.cpu().numpy()
+    p32, c32 = pos.double().numpy(), cells[0].double().numpy()
+    R = 4
+    offs = np.array([[a, b, c] for a in range(-R, R + 1) for b in range(-R, R + 1) for c in range(-R, R + 1)], float) @ c32
+    for i in range(n):
+        d2 = (((p32[None, :, None, :] + offs[None, None, :, :]) - p32[i]) ** 2).sum(-1)[0]        # [n, S]
+        cand = np.sort(d2[(d2 <= cutoff * cutoff) & (d2 > 1e-4)])
+        keep = cand[cand <= cand[max_nb] + 0.01] if len(cand) > max_nb else cand
+        mine = np.sort(d[ei[1] == i].astype(np.float64) ** 2)
+        assert len(mine) == len(keep) and len(mine) >= min(len(cand), max_nb + 1), (i, len(mine), len(keep))
+        assert np.allclose(mine, keep, rtol=1e-5)
+
+
 def test_segment_sum(backend):
     ops = pkg("ops")
     v = torch.randn(11, requires_grad=True)

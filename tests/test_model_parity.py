@@ -1,7 +1,7 @@
 """End-to-end parity of the CUDA path against golden vectors produced by the UNMODIFIED reference
 (oracle/make_golden.py): same parameters (by the reference's own state_dict keys), same graph, same
-edge-frame draw.  Tolerance: 1e-5 relative on outputs (north_star, fp32 mode), 2e-4 relative (to the
-largest entry of each tensor) on parameter gradients."""
+edge-frame draw.  Tolerance: 1e-5 relative on outputs (north_star, fp32 mode), 5e-5 relative (to the
+largest entry of each tensor) on parameter gradients (5e-5 since round 2; measured 9e-6)."""
 import pytest
 import torch
 
@@ -9,7 +9,7 @@ from conftest import golden
 from helpers import build_oc20, build_qm9, fixed_rand_like, load_params, rel_err
 
 OUT_TOL = 1e-5
-GRAD_TOL = 2e-4
+GRAD_TOL = 5e-5
 
 
 def _graph_inputs(fx, backend):
@@ -157,7 +157,7 @@ def test_matpes_family_double_backward_with_every_contraction_on_the_f16x3_engin
         out = model(dict(data, pos=pos))
         assert rel_err(out["energy"], fx["energy"]) < OUT_TOL
         forces = -torch.autograd.grad(out["energy_total"].sum(), pos, create_graph=True, retain_graph=True)[0]
-        assert rel_err(forces, fx["forces"]) < 2e-5
+        assert rel_err(forces, fx["forces"]) < OUT_TOL
         wf = torch.linspace(-1, 1, forces.numel(), device=forces.device).view_as(forces)
         we = torch.linspace(0.5, 1.5, out["energy"].numel(), device=forces.device).view_as(out["energy"])
         ((out["energy"] * we).sum() + (forces * wf).sum()).backward()
@@ -182,7 +182,7 @@ def test_matpes_v2_train_step_matches_reference(backend):
     out = model(dict(data, pos=pos))
     assert rel_err(out["energy"], fx["energy"]) < OUT_TOL
     forces = -torch.autograd.grad(out["energy_total"].sum(), pos, create_graph=True, retain_graph=True)[0]
-    assert rel_err(forces, fx["forces"]) < 2e-5
+    assert rel_err(forces, fx["forces"]) < OUT_TOL
     wf = torch.linspace(-1, 1, forces.numel(), device=forces.device).view_as(forces)
     we = torch.linspace(0.5, 1.5, out["energy"].numel(), device=forces.device).view_as(out["energy"])
     ((out["energy"] * we).sum() + (forces * wf).sum()).backward()
@@ -248,7 +248,7 @@ def test_matpes_gatav2_train_step_matches_reference(backend, variant):
     out = model(dict(data, pos=pos))
     assert rel_err(out["energy"], fx["energy"]) < OUT_TOL
     forces = -torch.autograd.grad(out["energy_total"].sum(), pos, create_graph=True, retain_graph=True)[0]
-    assert rel_err(forces, fx["forces"]) < 2e-5
+    assert rel_err(forces, fx["forces"]) < OUT_TOL
     wf = torch.linspace(-1, 1, forces.numel(), device=forces.device).view_as(forces)
     we = torch.linspace(0.5, 1.5, out["energy"].numel(), device=forces.device).view_as(out["energy"])
     ((out["energy"] * we).sum() + (forces * wf).sum()).backward()
