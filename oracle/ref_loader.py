@@ -43,5 +43,5 @@ def install(lmax_jd=8):
     for name in list(sys.modules):
         if name == "EquiformerV2Functions" or name.startswith("EquiformerV2Functions."):
             mod = sys.modules[name]
-            if not getattr(mod, "__file__", "").startswith(REF_ROOT):
+            if not (getattr(mod, "__file__", None) or "").startswith(REF_ROOT):
                 del sys.modules[name]

@@ -12,7 +12,8 @@ from oracle.eqv2_oracle import radius_graph_pbc_fairchem
 
 def generate_graph(data, cutoff, max_neighbors, enforce_max_neighbors_strictly=False,
                    radius_pbc_version=1, pbc=None):
+    dev = data.pos.device          # the brute-force restatement runs on the host whatever device the model lives on
     ei, dist, vec = radius_graph_pbc_fairchem(
-        data.pos, data.cell, data.batch, data.natoms, cutoff, max_neighbors,
+        data.pos.detach().cpu(), data.cell.detach().cpu(), data.batch.cpu(), data.natoms.cpu(), cutoff, max_neighbors,
         enforce_max_neighbors_strictly)
-    return {"edge_index": ei, "edge_distance": dist, "edge_distance_vec": vec}
+    return {"edge_index": ei.to(dev), "edge_distance": dist.to(dev), "edge_distance_vec": vec.to(dev)}

@@ -8,6 +8,12 @@ One block (+ the force head for OC20) at the full channel / degree dimensions on
 side at seconds; every kernel template instance and every GEMM shape class of the full model is exercised.
 Tolerances (north_star): energy / forces <= 1e-5 relative, parameter gradients <= 5e-5 of each tensor's largest entry,
 in the default f16x3 engine and in the exact fp32 (FFMA) engine.
+
+MatPES family (forces by autograd, double backward): the reference's OWN fp32 evaluation at these shapes is 1.8e-5
+(forces) / 3.2e-5 (gradients) away from the same unmodified reference evaluated in float64 -- its rounding noise
+exceeds north_star's 1e-5.  As in tests/test_model_parity.py::test_matpes_v1_*, the CUDA path is therefore compared
+with the reference's float64 evaluation, bound = max(north_star tolerance, 2 x the reference's own fp32 deviation),
+plus a sanity bound of 5e-5 / 2e-4 against the reference's fp32 numbers.
 """
 import importlib
 import os
@@ -135,14 +141,35 @@ def _reference(case):
             (pred * torch.linspace(-1, 1, pred.numel()).view_as(pred)).sum().backward()
             res.update(edge_index=ei, edge_distance=dist, edge_vec=vec, draw=rr.draws[0], pred=pred.detach())
         else:
-            pos = data["pos"].clone().requires_grad_(True)
-            out = model(dict(data, pos=pos))
-            forces = -torch.autograd.grad(out["energy_total"].sum(), pos, create_graph=True, retain_graph=True)[0]
-            wf = torch.linspace(-1, 1, forces.numel()).view_as(forces)
-            we = torch.linspace(0.5, 1.5, out["energy"].numel()).view_as(out["energy"])
-            ((out["energy"] * we).sum() + (forces * wf).sum()).backward()
-            res.update(energy=out["energy"].detach(), forces=forces.detach())
+            def train_pattern(m, d):
+                pos = d["pos"].clone().requires_grad_(True)
+                out = m(dict(d, pos=pos))
+                forces = -torch.autograd.grad(out["energy_total"].sum(), pos, create_graph=True, retain_graph=True)[0]
+                wf = torch.linspace(-1, 1, forces.numel(), dtype=forces.dtype).view_as(forces)
+                we = torch.linspace(0.5, 1.5, out["energy"].numel(), dtype=forces.dtype).view_as(out["energy"])
+                ((out["energy"] * we).sum() + (forces * wf).sum()).backward()
+                return out["energy"].detach(), forces.detach()
+
+            energy, forces = train_pattern(model, data)
+            res.update(energy=energy, forces=forces)
         res["grads"] = {k: p.grad.detach().clone() for k, p in model.named_parameters() if p.grad is not None}
+        if kind == "matpes":
+            # the same unmodified reference in float64 (it hard-codes dtype=torch.float32 in one torch.arange of the
+            # graph builder; that single dtype is redirected, as in oracle/make_golden.py::golden_matpes_v1)
+            real_arange = torch.arange
+            torch.arange = lambda *a, **k: real_arange(
+                *a, **{**k, "dtype": torch.float64 if k.get("dtype") == torch.float32 else k.get("dtype")})
+            torch.set_default_dtype(torch.float64)
+            try:
+                model.zero_grad(set_to_none=True)
+                m64 = model.double()
+                d64 = {k: (v.double() if v.is_floating_point() else v) for k, v in data.items()}
+                e64, f64 = train_pattern(m64, d64)
+            finally:
+                torch.arange = real_arange
+                torch.set_default_dtype(torch.float32)
+            res.update(energy_f64=e64, forces_f64=f64,
+                       grads_f64={k: p.grad.detach().clone() for k, p in m64.named_parameters() if p.grad is not None})
     finally:
         for k in list(sys.modules):
             if k.split(".")[0] in ("EquiformerV2Functions", "NewFunctions") or k == ref_mod:
@@ -154,7 +181,8 @@ def _reference(case):
 
 def _check_grads(model, ref):
     floor = 1e-7 * max(float(g.abs().max()) for g in ref["grads"].values())
-    bad = []
+    g64 = ref.get("grads_f64")
+    bad, worst = [], 0.0
     for k, p in model.named_parameters():
         g_ref = ref["grads"].get(k)
         if g_ref is None:
@@ -163,10 +191,21 @@ def _check_grads(model, ref):
         assert p.grad is not None, k
         if k.endswith("global_attn.k_proj.bias"):      # exactly zero mathematically (softmax shift invariance)
             continue
-        e = float((p.grad.detach().double().cpu() - g_ref.double()).abs().max() / max(float(g_ref.abs().max()), floor))
-        if e > GRAD_TOL:
-            bad.append((k, e))
+        mine = p.grad.detach().double().cpu()
+        scale = max(float(g_ref.abs().max()), floor)
+        e32 = float((mine - g_ref.double()).abs().max() / scale)
+        if g64 is None:
+            e, tol = e32, GRAD_TOL
+        else:       # against the float64 reference; the reference's own fp32 deviation sets the floor of the bound
+            own = float((g_ref.double() - g64[k]).abs().max() / scale)
+            e, tol = float((mine - g64[k]).abs().max() / scale), max(GRAD_TOL, 2 * own)
+            if e32 > 2e-4:
+                bad.append((k, "vs fp32 reference", e32))
+        worst = max(worst, e / tol)
+        if e > tol:
+            bad.append((k, e, tol))
     assert not bad, bad
+    return worst
 
 
 @pytest.mark.parametrize("mode", ["f16x3", "fp32"])
@@ -178,6 +217,7 @@ def test_cuda_path_matches_reference_at_baseline_shape(case, mode):
     dev = torch.device("cuda:0")
     ops.set_gemm_mode(mode)
     ops.reset_caches()
+    f_tol = OUT_TOL
     try:
         torch.manual_seed(0)
         model = getattr(pkg(prod_mod), cls)(**kw).to(dev)
@@ -203,17 +243,19 @@ def test_cuda_path_matches_reference_at_baseline_shape(case, mode):
             pos = data["pos"].clone().requires_grad_(True)
             out = model(dict(data, pos=pos))
             forces = -torch.autograd.grad(out["energy_total"].sum(), pos, create_graph=True, retain_graph=True)[0]
-            e_err, f_err = rel_err(out["energy"], ref["energy"]), rel_err(forces, ref["forces"])
+            e_err, f_err = rel_err(out["energy"], ref["energy_f64"]), rel_err(forces, ref["forces_f64"])
+            f_tol = max(OUT_TOL, 2 * rel_err(ref["forces"], ref["forces_f64"]))
+            assert rel_err(forces, ref["forces"]) < 5e-5
             wf = torch.linspace(-1, 1, forces.numel(), device=dev).view_as(forces)
             we = torch.linspace(0.5, 1.5, out["energy"].numel(), device=dev).view_as(out["energy"])
             ((out["energy"] * we).sum() + (forces * wf).sum()).backward()
         prof = _lib.stop_kernel_timing()
-        print(f"{case} [{mode}]: energy {e_err:.2e} forces {f_err:.2e}; "
-              f"gemm_f16 launches {prof.get('eqv2_gemm_f16', {}).get('calls', 0)}")
-        assert e_err < OUT_TOL and f_err < OUT_TOL, (e_err, f_err)
+        assert e_err < OUT_TOL and f_err < f_tol, (e_err, f_err, f_tol)
         if mode == "f16x3":      # the default engine must really have been the one running the contractions
             assert prof.get("eqv2_gemm_f16", {}).get("calls", 0) >= 6, sorted(prof)
-        _check_grads(model, ref)
+        worst = _check_grads(model, ref)
+        print(f"PARITY {case} [{mode}]: energy {e_err:.2e} forces {f_err:.2e} (bound {f_tol:.1e}); worst gradient at "
+              f"{worst:.2f} of its bound; gemm_f16 launches {prof.get('eqv2_gemm_f16', {}).get('calls', 0)}")
     finally:
         ops.set_gemm_mode(ops.DEFAULT_GEMM_MODE)
 
