@@ -89,12 +89,16 @@ class SO2_Convolution(nn.Module):
         """[E, n_rad] per-edge modulation (so2_ops.py:145-146) or None."""
         return self.rad_func(x_edge) if self.rad_func is not None else None
 
+    def groups_and_weights(self):
+        """(column groups, GEMM weights) of the m = 0..mmax blocks in m-primary order (ops.so2_conv)."""
+        groups = tuple(self.layout().conv_groups(self.sphere_channels, self.m_output_channels,
+                                                 self.extra_m0_output_channels or 0))
+        return groups, [self.fc_m0.weight] + [mc.block_weight() for mc in self.so2_m_conv]
+
     def conv_m_primary(self, A):
         """A: [E, Kr*c_in] m-primary rows with the radial modulation already applied (it is fused into
         the gather/rotate kernel).  Returns Y [E, extra + Kr*c_out] (m-primary)."""
-        groups = tuple(self.layout().conv_groups(self.sphere_channels, self.m_output_channels,
-                                                 self.extra_m0_output_channels or 0))
-        weights = [self.fc_m0.weight] + [mc.block_weight() for mc in self.so2_m_conv]
+        groups, weights = self.groups_and_weights()
         return ops.so2_conv(A, self.fc_m0.bias, groups, weights)
 
     # -- reference-shaped entry point -------------------------------------------------------

@@ -124,12 +124,18 @@ class SO2EquivariantGraphAttention(nn.Module):
 
         x_edge = edge_scalar_features(self, atomic_numbers, edge_distance, edge_index)
         rad = self.so2_conv_1.radial_weights(x_edge)                          # [E, n_rad]
-        A = ops.gather_rotate(emb, rad, plan, wig, lmax, mmax)         # [E, Kr*2C]  m-primary
-        Y = self.so2_conv_1.conv_m_primary(A)                                 # [E, h*a + H + Kr*H]
+        second_order = torch.is_grad_enabled() and edge_distance.requires_grad
+        if not second_order and ops.fused_planes_available(emb, rad, lay.Kr * 2 * self.sphere_channels):
+            # f16 engine, step differentiated once: the rotated / modulated rows exist only as the GEMM's operand planes
+            groups, weights = self.so2_conv_1.groups_and_weights()
+            Y = ops.gather_rotate_conv(emb, rad, self.so2_conv_1.fc_m0.bias, plan, wig, lmax, mmax, groups, weights)
+        else:
+            A = ops.gather_rotate(emb, rad, plan, wig, lmax, mmax)     # [E, Kr*2C]  m-primary
+            Y = self.so2_conv_1.conv_m_primary(A)                             # [E, h*a + H + Kr*H]
         mats = self.SO3_grid[lmax][mmax].kernel_mats("m")
         ln_w = self.alpha_norm.weight if self.use_attn_renorm else None
         ln_b = self.alpha_norm.bias if self.use_attn_renorm else None
-        if torch.is_grad_enabled() and edge_distance.requires_grad:
+        if second_order:
             # positions are being differentiated (forces by autograd, train_MatPES_GATAWandB.py:72-77): use the
             # operators whose backward passes are themselves differentiable
             ha = self.num_heads * self.attn_alpha_channels
@@ -141,10 +147,18 @@ class SO2EquivariantGraphAttention(nn.Module):
         else:
             Zm, alpha = ops.edge_act_alpha(Y, ln_w, ln_b, self.alpha_dot, plan, mats, self.num_heads,
                                                  self.attn_alpha_channels, self.hidden_channels)
+        alpha_bound = 1.0
         if self.alpha_dropout is not None:
             alpha = self.alpha_dropout(alpha)
-        V = self.so2_conv_2.conv_m_primary(Zm)                                # [E, Kr*h*v]
-        out = ops.rotinv_reduce(V, alpha, plan, wig, lmax, mmax, lay.Kr, self.num_heads, 1.0)
+            if self.training:
+                alpha_bound = 1.0 / (1.0 - self.alpha_dropout.p)              # nn.Dropout rescales the kept weights
+        if not second_order and ops.gemm_mode() in ("f16x3", "f16"):
+            groups, weights = self.so2_conv_2.groups_and_weights()
+            out = ops.conv_rotinv_reduce(Zm, alpha, self.so2_conv_2.fc_m0.bias, plan, wig, lmax, mmax, self.num_heads,
+                                         alpha_bound, groups, weights)
+        else:
+            V = self.so2_conv_2.conv_m_primary(Zm)                            # [E, Kr*h*v]
+            out = ops.rotinv_reduce(V, alpha, plan, wig, lmax, mmax, lay.Kr, self.num_heads, 1.0)
         msg = SO3_Embedding(0, x.lmax_list.copy(), self.num_heads * self.attn_value_channels,
                             device=x.device, dtype=x.dtype)
         msg.set_embedding(out)

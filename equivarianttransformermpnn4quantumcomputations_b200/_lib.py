@@ -38,7 +38,7 @@ class Gemm16Desc(ctypes.Structure):
     _fields_ = [
         ("A", P), ("B", P), ("C", P), ("bias", P), ("a_absmax", P), ("b_absmax", P),
         ("a_ld", L), ("a_plane", L), ("b_ld", L), ("b_plane", L), ("c_ld", L), ("c_rpb", L), ("c_bs", L),
-        ("M", I), ("N", I), ("K", I), ("transA", I), ("transB", I), ("accumulate", I),
+        ("M", I), ("N", I), ("K", I), ("transA", I), ("transB", I), ("accumulate", I), ("c_absmax", P),
     ]
 
 
@@ -51,12 +51,17 @@ _PROTOS = {
     "eqv2_gemm_tc": [P, I, I, I, P],
     "eqv2_split_f16": [P, I, P],
     "eqv2_gemm_f16": [P, I, I, P],
+    "eqv2_gemm_f16_ex": [P, I, I, I, P],
     "eqv2_wigner_from_rot": [P, P, P, L, I, P],
     "eqv2_gather_rotate_fwd": [P, P, P, P, P, P, P, P, L, I, I, I, I, I, P, P],
     "eqv2_gather_rotate_dx": [P, P, P, P, P, P, P, P, L, I, I, I, I, I, P],
     "eqv2_gather_rotate_drad": [P, P, P, P, P, P, L, I, I, I, I, I, P, P],
     "eqv2_rotinv_reduce_fwd": [P, P, P, P, P, P, P, L, I, I, L, I, I, I, F, P],
     "eqv2_rotinv_reduce_bwd": [P, P, P, P, P, P, P, P, L, I, I, L, I, I, I, F, P, P],
+    "eqv2_planes_colsum": [P, L, L, L, L, I, I, P, P, P, P],
+    "eqv2_gather_rotate_fwd_planes": [P, P, P, P, P, P, L, L, P, P, P, L, I, I, I, I, I, P],
+    "eqv2_gather_rotate_drad_planes": [P, P, P, P, P, P, L, L, P, P, P, L, I, I, I, I, I, P],
+    "eqv2_rotinv_reduce_bwd_planes": [P, P, P, P, P, P, L, L, P, F, P, P, L, I, I, L, I, I, I, F, P],
     "eqv2_s2act_padded_rows": [I],
     "eqv2_s2act_fwd": [P, L, P, L, P, L, P, P, L, I, I, I, I, I, P],
     "eqv2_s2act_bwd": [P, L, P, L, P, L, P, L, P, L, P, P, L, I, I, I, I, I, P],
@@ -67,7 +72,7 @@ _PROTOS = {
     "eqv2_s2sep_bwd2": [P, L, P, L, P, L, P, L, P, L, P, L, P, L, P, L, L, I, I, I, I, I, P],
     "eqv2_attn_alpha_fwd": [P, L, P, P, P, P, P, P, P, L, L, I, I, F, P],
     "eqv2_attn_alpha_bwd": [P, L, P, P, P, P, P, P, P, P, P, L, P, P, P, L, L, I, I, F, P],
-    "eqv2_equiv_norm_fwd": [P, P, P, P, P, P, L, I, I, I, P, P, F, P],
+    "eqv2_equiv_norm_fwd": [P, P, P, P, P, P, L, I, I, I, P, P, F, P, P],
     "eqv2_equiv_norm_bwd": [P, P, P, P, P, P, P, P, L, I, I, I, P, P, P],
     "eqv2_rbf_fwd": [P, P, L, I, P, F, P],
     "eqv2_rbf_bwd": [P, P, P, L, I, P, F, P],
@@ -89,7 +94,8 @@ _PROTOS = {
     "eqv2_seg_colsum": [P, L, P, P, L, I, I, I, P, P, P],
 }
 # entry points that only exist in the real (nvcc-built) library
-_OPTIONAL = {"eqv2_gemm_tc", "eqv2_split_f16", "eqv2_gemm_f16"}   # inline-PTX kernels: not part of the CPU emulator build
+_OPTIONAL = {"eqv2_gemm_tc", "eqv2_split_f16", "eqv2_gemm_f16", "eqv2_gemm_f16_ex", "eqv2_gather_rotate_fwd_planes",
+             "eqv2_gather_rotate_drad_planes", "eqv2_rotinv_reduce_bwd_planes", "eqv2_planes_colsum"}   # inline-PTX kernels: not part of the CPU emulator build
 
 _state = {"lib": None, "launches": 0}
 

@@ -7,6 +7,7 @@
 #ifdef EQV2_CPU_EMU
 #include "cpu_emu.h"
 #else
+#include <cuda_fp16.h>
 #include <cuda_runtime.h>
 #define EQV2_LAUNCH(kernel, grid, block, smem, stream, ...) \
   kernel<<<(grid), (block), (smem), (cudaStream_t)(stream)>>>(__VA_ARGS__)
@@ -88,3 +89,50 @@ __device__ __forceinline__ float eqv2_read_absmax(const float* slot) {
   for (int i = 0; i < EQV2_ABSMAX_SLOTS / 32; ++i) m = fmaxf(m, slot[lane + 32 * i]);
   return eqv2_warp_max(m);
 }
+
+// ---- producer-side operand planes (f16x3 GEMM engine, csrc/gemm_f16.cu) ----------------------------------------------
+// The engine multiplies fp32 matrices as scaled fp16 hi/lo planes: T ~ (hi + lo) / s_T with s_T a power of two derived
+// from a value B >= max |T| (scale_of: s_T B in [2^14, 2^15)).  B need not be the exact maximum: hi + lo keeps 22
+// significant bits for |v| >= 2^-18 B and an absolute error <= 2^-40 B below, so a bound that overshoots the true maximum
+// by up to ~2^8 still leaves every dot product fp32-class (error floor 2^-32 of the tensor maximum).  A kernel that
+// PRODUCES a GEMM operand therefore writes the planes itself -- the fp32 tensor and the separate split pass (one read +
+// one write of the tensor) disappear -- with B computed on the device from the maxima of its own inputs:
+//   B = max(bound_a) * max(bound_b) * bound_c     (bound_b may be null = 1)
+// and stores B where the GEMM reads "max |T|" (bound_out, a zero-initialised absmax slot).
+struct Eqv2PlaneArgs {
+  void* hi;               // __half [2][rows][ld]; plane 1 (lo) starts `plane` elements after plane 0
+  long long plane, ld;
+  const float* bound_a;
+  const float* bound_b;
+  float bound_c;
+  float* bound_out;
+};
+#ifndef EQV2_CPU_EMU
+__device__ __forceinline__ void eqv2_scale_of(float amax, float& s, float& inv) {
+  if (!(amax > 0.f) || !(amax < 3.0e38f)) { s = 1.f; inv = 1.f; return; }
+  int e;
+  frexpf(amax, &e);                       // amax = f * 2^e, f in [0.5, 1)
+  e = max(e, -100);
+  s = ldexpf(1.f, 15 - e);                // s * amax in [2^14, 2^15)
+  inv = ldexpf(1.f, e - 15);
+}
+// scale of this launch's plane output (full warps must call: warp-collective slot reads); one thread publishes B
+__device__ __forceinline__ float eqv2_plane_scale(const Eqv2PlaneArgs& P, bool publisher) {
+  float B = eqv2_read_absmax(P.bound_a) * P.bound_c;
+  if (P.bound_b != nullptr) B *= eqv2_read_absmax(P.bound_b);
+  if (publisher) P.bound_out[0] = B;
+  float s, inv;
+  eqv2_scale_of(B, s, inv);
+  return s;
+}
+__device__ __forceinline__ void eqv2_plane_store(const Eqv2PlaneArgs& P, long long idx, float v, float s) {
+  const float x = v * s;
+  const __half h = __float2half_rn(x);
+  __half* hp = reinterpret_cast<__half*>(P.hi);
+  hp[idx] = h;
+  hp[idx + P.plane] = __float2half_rn(x - __half2float(h));
+}
+#else   // the CPU emulator (tests/emu) builds the fp32 instances only
+inline float eqv2_plane_scale(const Eqv2PlaneArgs&, bool) { return 1.f; }
+inline void eqv2_plane_store(const Eqv2PlaneArgs&, long long, float, float) {}
+#endif

@@ -52,6 +52,7 @@ struct alignas(64) HGroup {
   const float* bias;
   const float* a_absmax;
   const float* b_absmax;
+  float* c_absmax;     // optional: receives max |C| of what this launch stores (64 slots, zero-initialised by the caller)
   long long ldc, c_bs;
   int c_rpb;           // C row r lives at (r / c_rpb) * c_bs + (r % c_rpb) * ldc (degree slabs of [N,K,C]); 0 = plain
   int M, N, K;
@@ -66,17 +67,11 @@ struct HParams {
   int ngroups;
   int split_k;
   int total_work;
+  int passes;          // 3: hi*hi + hi*lo + lo*hi (fp32-class); 1: hi*hi only (single fp16 pass, reduced precision)
 };
 
-// ---- scale shared by the split kernel and the GEMM epilogue ---------------------------------------------
-__device__ __forceinline__ void scale_of(float amax, float& s, float& inv) {
-  if (!(amax > 0.f) || !(amax < 3.0e38f)) { s = 1.f; inv = 1.f; return; }
-  int e;
-  frexpf(amax, &e);                       // amax = f * 2^e, f in [0.5, 1)
-  e = max(e, -100);
-  s = ldexpf(1.f, 15 - e);                // s * amax in [2^14, 2^15)
-  inv = ldexpf(1.f, e - 15);
-}
+// ---- scale shared by the split kernel, the producer kernels and the GEMM epilogue: eqv2_scale_of (common.cuh) ----
+__device__ __forceinline__ void scale_of(float amax, float& s, float& inv) { eqv2_scale_of(amax, s, inv); }
 
 // ---- PTX wrappers -----------------------------------------------------------------------------------------
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -229,11 +224,13 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) gemm_f16_kernel(const __grid_c
           const uint32_t s = it % STAGES, round = it / STAGES;
           mbar_wait(smem_u32(&empty[s]), (round & 1u) ^ 1u);
           const uint32_t bar = smem_u32(&full[s]);
-          mbar_expect_tx(bar, (uint32_t)STAGE_BYTES);
+          const int nplanes = P.passes == 1 ? 1 : 2;
+          mbar_expect_tx(bar, (uint32_t)(nplanes * 2 * TILE_BYTES));
           const uint32_t st = smem_u32(tiles + (size_t)s * STAGE_BYTES);
           const int k0 = (W.kb0 + i) * BK;
 #pragma unroll
           for (int plane = 0; plane < 2; ++plane) {
+            if (plane >= nplanes) break;
             const uint32_t da = st + plane * TILE_BYTES, db = st + (2 + plane) * TILE_BYTES;
             if (!G.a_mn) {
               tma_load_3d(da, &G.mapA, bar, k0, W.m0, plane);
@@ -282,6 +279,10 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) gemm_f16_kernel(const __grid_c
               const uint64_t dah = make_desc(a_hi + k * a_step, amn);
               const uint64_t dal = make_desc(a_lo + k * a_step, amn);
               const uint64_t dbh = make_desc(b_hi + k * b_step, bmn);     // as an N=256 operand: B_hi | B_lo
+              if (P.passes == 1) {                                         // single pass: D_hh (+)= A_hi B_hi
+                umma_f16(d_hh, dah, dbh, idesc128, (i == i0 && k == 0) ? 0u : 1u);
+                continue;
+              }
               if (i == i0 && k == 0) {
                 // first slice of a chunk: D_hh restarts; D_lo restarts only on the first chunk of each buffer
                 const uint64_t dbl = make_desc(b_lo + k * b_step, bmn);
@@ -335,7 +336,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) gemm_f16_kernel(const __grid_c
           acc[x] += __uint_as_float(r0[x]);
           acc[32 + x] += __uint_as_float(r1[x]);
         }
-        if (j >= nchunks - 2) {                              // last chunk on this buffer: its D_lo is final
+        if (j >= nchunks - 2 && P.passes != 1) {             // last chunk on this buffer: its D_lo is final
           tmem_ld32_nowait(d_hh + 128u, r0);
           tmem_ld32_nowait(d_hh + 160u, r1);
           tmem_ld_wait();
@@ -353,6 +354,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) gemm_f16_kernel(const __grid_c
       const int row = W.m0 + q * 32 + lane;
       const bool atomic = P.split_k > 1;
       const float sc = ia * ib;
+      float cmax = 0.f;                                     // max |C| of what this thread stores (c_absmax)
       // Fast path (plain row-major C, 16-byte aligned rows, N % 4 == 0, no split-K): the accumulators are row-per-lane,
       // so a direct float4 store touches 32 different 128-byte lines per warp instruction (512 LSU tag cycles per warp and
       // tile, 4 096 per tile over the 8 worker warps: longer than the MMAs of a K = 128 tile).  Each warp instead passes
@@ -397,6 +399,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) gemm_f16_kernel(const __grid_c
                   o.x += p.x; o.y += p.y; o.z += p.z; o.w += p.w;
                 }
                 *reinterpret_cast<float4*>(cp) = o;
+                cmax = fmaxf(cmax, fmaxf(fmaxf(fabsf(o.x), fabsf(o.y)), fmaxf(fabsf(o.z), fabsf(o.w))));
               }
             }
             __syncwarp();
@@ -417,10 +420,17 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) gemm_f16_kernel(const __grid_c
             float o = acc[x] * sc;
             if (G.bias != nullptr && W.ks == 0) o += __ldg(G.bias + W.n0 + col0 + x);
             if (atomic) atomicAdd(crow + x, o);
-            else if (G.accumulate) crow[x] += o;
+            else if (G.accumulate) { o += crow[x]; crow[x] = o; }
             else crow[x] = o;
+            cmax = fmaxf(cmax, fabsf(o));
           }
         }
+      }
+      if (G.c_absmax != nullptr && !atomic) {               // one fire-and-forget atomic per warp and tile
+        cmax = eqv2_warp_max(cmax);
+        if (lane == 0 && cmax > 0.f)
+          atomicMax(reinterpret_cast<unsigned*>(G.c_absmax) + ((blockIdx.x * NUM_WORKER_WARPS + warp) & (EQV2_ABSMAX_SLOTS - 1)),
+                    __float_as_uint(cmax));
       }
     }
   }
@@ -606,13 +616,16 @@ bool make_map(CUtensorMap* m, const void* base, long long inner, long long outer
 }
 
 int sm_count() {
-  static int n = 0;
-  if (n == 0) {
-    int dev = 0;
-    cudaGetDevice(&dev);
+  static int cache[64] = {};              // per device ordinal
+  int dev = 0;
+  cudaGetDevice(&dev);
+  if (dev < 0 || dev >= 64) return 148;
+  if (cache[dev] == 0) {
+    int n = 0;
     if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0) n = 148;
+    cache[dev] = n;
   }
-  return n;
+  return cache[dev];
 }
 
 }  // namespace
@@ -660,8 +673,13 @@ extern "C" int eqv2_split_f16(const eqv2_split_desc* descs, int n, void* stream)
 }
 
 extern "C" int eqv2_gemm_f16(const eqv2_gemm16_desc* descs, int ngroups, int split_k, void* stream) {
+  return eqv2_gemm_f16_ex(descs, ngroups, split_k, 3, stream);
+}
+
+extern "C" int eqv2_gemm_f16_ex(const eqv2_gemm16_desc* descs, int ngroups, int split_k, int passes, void* stream) {
   EQV2_REQUIRE(ngroups >= 1 && ngroups <= EQV2_GEMM_MAX_GROUPS, "eqv2_gemm_f16: ngroups=%d out of range", ngroups);
   EQV2_REQUIRE(split_k >= 1, "eqv2_gemm_f16: bad split_k");
+  EQV2_REQUIRE(passes == 1 || passes == 3, "eqv2_gemm_f16: passes must be 1 or 3");
   HParams P;
   memset(&P, 0, sizeof(P));
   int tiles = 0;
@@ -674,6 +692,7 @@ extern "C" int eqv2_gemm_f16(const eqv2_gemm16_desc* descs, int ngroups, int spl
                  "eqv2_gemm_f16: split operands must be 16-byte aligned with leading dimensions multiple of 8");
     HGroup& g = P.g[i];
     g.C = d.C; g.bias = d.bias; g.a_absmax = d.a_absmax; g.b_absmax = d.b_absmax;
+    g.c_absmax = d.c_absmax;
     g.ldc = d.c_ld;
     g.c_rpb = (d.c_rpb <= 0 || d.c_rpb >= (1ll << 31)) ? 0 : (int)d.c_rpb;
     g.c_bs = d.c_bs;
@@ -694,12 +713,15 @@ extern "C" int eqv2_gemm_f16(const eqv2_gemm16_desc* descs, int ngroups, int spl
   P.ngroups = ngroups;
   P.split_k = split_k;
   P.total_work = tiles * split_k;
-  static bool attr_set = false;
-  if (!attr_set) {
+  P.passes = passes;
+  static bool attr_set[64] = {};          // the attribute is per device: one flag per device ordinal
+  int dev = 0;
+  cudaGetDevice(&dev);
+  if (dev < 0 || dev >= 64 || !attr_set[dev]) {
     cudaError_t e = cudaFuncSetAttribute(gemm_f16_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_BYTES);
     EQV2_REQUIRE(e == cudaSuccess, "eqv2_gemm_f16: cannot reserve %zu B of shared memory: %s", SMEM_BYTES,
                  cudaGetErrorString(e));
-    attr_set = true;
+    if (dev >= 0 && dev < 64) attr_set[dev] = true;
   }
   const int grid = P.total_work < sm_count() ? P.total_work : sm_count();
   gemm_f16_kernel<<<dim3((unsigned)grid), dim3(NUM_THREADS), SMEM_BYTES, (cudaStream_t)stream>>>(P);

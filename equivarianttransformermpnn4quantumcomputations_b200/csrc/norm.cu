@@ -38,7 +38,8 @@ __device__ __forceinline__ void block_sum(float* vals, int nv, float* scratch, f
 
 __global__ void equiv_norm_fwd_kernel(const float* __restrict__ x, const float* __restrict__ w,
                                       const float* __restrict__ b, float* __restrict__ out, float* __restrict__ inv_out,
-                                      float* __restrict__ mean_out, const NormMeta M, int C, float eps) {
+                                      float* __restrict__ mean_out, const NormMeta M, int C, float eps,
+                                      float* __restrict__ absmax) {
   __shared__ float scratch[MAXG * 32];
   __shared__ float res[MAXG];
   const int K = (M.lmax + 1) * (M.lmax + 1);
@@ -72,6 +73,7 @@ __global__ void equiv_norm_fwd_kernel(const float* __restrict__ x, const float* 
   for (int g = 0; g < MAXG; ++g) inv[g] = (g < M.ngroups) ? rsqrtf(res[g] / C + eps) : 0.f;
   if (threadIdx.x < M.ngroups) inv_out[n * M.ngroups + threadIdx.x] = inv[threadIdx.x];
   if (threadIdx.x == 0) mean_out[n] = mean0;
+  float amax = 0.f;
   if (live) {
     float* op = out + n * (long long)K * C + c;
     for (int l = 0; l <= M.lmax; ++l) {
@@ -86,9 +88,12 @@ __global__ void equiv_norm_fwd_kernel(const float* __restrict__ x, const float* 
         float o = f * sc;
         if (k == 0) o += b[c];
         op[(long long)k * C] = o;
+        amax = fmaxf(amax, fabsf(o));
       }
     }
   }
+  // max |out|: the operand bound of the gather/rotate kernel that consumes the normed embedding (common.cuh)
+  if (absmax != nullptr) eqv2_commit_absmax(amax, absmax);
 }
 
 __global__ void equiv_norm_bwd_kernel(const float* __restrict__ x, const float* __restrict__ w,
@@ -184,13 +189,13 @@ static int fill_meta(NormMeta& M, int lmax, int ngroups, const int* group_of_l, 
 
 extern "C" int eqv2_equiv_norm_fwd(const float* x, const float* w, const float* b, float* out, float* inv_out,
                                    float* mean_out, long long N, int C, int lmax, int ngroups, const int* group_of_l,
-                                   const float* bw_l, float eps, void* stream) {
+                                   const float* bw_l, float eps, float* absmax, void* stream) {
   if (N == 0) return 0;
   EQV2_REQUIRE(C > 0 && C <= 1024, "equiv_norm_fwd: C=%d out of range", C);
   NormMeta M;
   EQV2_REQUIRE(fill_meta(M, lmax, ngroups, group_of_l, bw_l) == 0, "equiv_norm_fwd: bad group table");
   const int threads = (C + 31) / 32 * 32;
-  EQV2_LAUNCH(equiv_norm_fwd_kernel, dim3((unsigned)N), dim3(threads), 0, stream, x, w, b, out, inv_out, mean_out, M, C, eps);
+  EQV2_LAUNCH(equiv_norm_fwd_kernel, dim3((unsigned)N), dim3(threads), 0, stream, x, w, b, out, inv_out, mean_out, M, C, eps, absmax);
   EQV2_CHECK_LAUNCH("eqv2_equiv_norm_fwd");
   return 0;
 }

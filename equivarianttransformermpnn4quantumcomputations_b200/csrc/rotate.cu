@@ -133,16 +133,20 @@ __device__ __forceinline__ void load_column(float (&v)[N], const float* __restri
 }
 
 // ------------------------------------------------------------------------------------------
-template <int L, int M>
+// PL = true: the result goes out as scaled fp16 hi/lo planes (the A operand of the first SO(2) convolution's GEMM) instead
+// of fp32 (Eqv2PlaneArgs, common.cuh); bound = max |rad| * max |x| * sqrt(2 lmax + 1)  (|(W x)_row| <= ||x_l||_2).
+template <int L, int M, bool PL>
 __global__ void __launch_bounds__(256)
 gather_rotate_fwd_kernel(const float* __restrict__ x, const long long* __restrict__ src,
                          const long long* __restrict__ dst, const float* __restrict__ wig,
                          const float* __restrict__ rad, float* __restrict__ out, int C, int Kr, int nrad,
-                         float* __restrict__ absmax) {
+                         float* __restrict__ absmax, const Eqv2PlaneArgs PA) {
   constexpr int K = Dim<L>::K, WS = Dim<L>::WS;
   constexpr int NS = nslots<L, M>();
   __shared__ __align__(16) float sw[wpad_off(L + 1)];
   const long long e = blockIdx.x;
+  float pscale = 1.f;
+  if constexpr (PL) pscale = eqv2_plane_scale(PA, blockIdx.x == 0 && blockIdx.y == 0 && threadIdx.x == 0);
   const long long ns_ = src[e], nd_ = dst[e];
   const int C2 = 2 * C;
   float amax = 0.f;
@@ -170,7 +174,8 @@ gather_rotate_fwd_kernel(const float* __restrict__ x, const long long* __restric
         constexpr int m = decltype(mc)::value - mm;
         constexpr int p = mpos<L, M>(l, m), sl = rslot<L, M>(l, m < 0 ? -m : m);
         const float acc = row_dot<l>(sw, l + m, xc + l * l) * rv[sl];
-        op[(long long)p * C2] = acc;
+        if constexpr (PL) eqv2_plane_store(PA, e * PA.ld + (long long)p * C2 + ch, acc, pscale);
+        else op[(long long)p * C2] = acc;
         amax = fmaxf(amax, fabsf(acc));
       });
     });
@@ -181,15 +186,19 @@ gather_rotate_fwd_kernel(const float* __restrict__ x, const long long* __restric
 // ------------------------------------------------------------------------------------------
 // d(rad): edge-parallel (same shape as the forward).  drad[e, slot, ch] = sum over the rows (l, +-m) sharing the
 // slot of  dA[e, row, ch] * (W_e x)[row, ch]   (so2_ops.py:170-175: rows +m and -m share one radial weight).
-template <int L, int M>
+// PL = true: drad goes out as fp16 hi/lo planes (operand of the radial MLP's backward GEMMs);
+// bound = 2 * max |dA| * max |x| * sqrt(2 lmax + 1)  (two rows share a slot).
+template <int L, int M, bool PL>
 __global__ void __launch_bounds__(256)
 gather_rotate_drad_kernel(const float* __restrict__ x, const long long* __restrict__ src,
                           const long long* __restrict__ dst, const float* __restrict__ wig,
                           const float* __restrict__ dA, float* __restrict__ drad, int C, int Kr, int nrad,
-                          float* __restrict__ absmax) {
+                          float* __restrict__ absmax, const Eqv2PlaneArgs PA) {
   constexpr int K = Dim<L>::K, WS = Dim<L>::WS;
   __shared__ __align__(16) float sw[wpad_off(L + 1)];
   const long long e = blockIdx.x;
+  float pscale = 1.f;
+  if constexpr (PL) pscale = eqv2_plane_scale(PA, blockIdx.x == 0 && blockIdx.y == 0 && threadIdx.x == 0);
   const long long ns_ = src[e], nd_ = dst[e];
   const int C2 = 2 * C;
   float amax = 0.f;
@@ -213,7 +222,8 @@ gather_rotate_drad_kernel(const float* __restrict__ x, const long long* __restri
         constexpr int pp = mpos<L, M>(l, m), pm = mpos<L, M>(l, -m), sl = rslot<L, M>(l, m);
         float d = gv[pp] * row_dot<l>(sw, l + m, xc + l * l);
         if constexpr (m > 0) d = fmaf(gv[pm], row_dot<l>(sw, l - m, xc + l * l), d);
-        drp[(long long)sl * C2] = d;
+        if constexpr (PL) eqv2_plane_store(PA, e * PA.ld + (long long)sl * C2 + ch, d, pscale);
+        else drp[(long long)sl * C2] = d;
         amax = fmaxf(amax, fabsf(d));
       });
     });
@@ -379,14 +389,18 @@ rotinv_reduce_fwd_kernel(const float* __restrict__ val, const float* __restrict_
 }
 
 // ------------------------------------------------------------------------------------------
-template <int L, int M>
+// PL = true: d(value) goes out as fp16 hi/lo planes (operand of the second SO(2) convolution's backward GEMMs);
+// bound = max |dout| * alpha_bound * scale * sqrt((2 lmax + 1) * max(1, (2 lmax + 1) / (2 mmax + 1))).
+template <int L, int M, bool PL>
 __global__ void __launch_bounds__(256)
 rotinv_reduce_bwd_kernel(const float* __restrict__ dout, const float* __restrict__ val, const float* __restrict__ alpha,
                          const float* __restrict__ wig, const long long* __restrict__ dst, float* __restrict__ dval,
                          float* __restrict__ dalpha, int Cv, int rows_used, long long val_estride, int heads, float scale,
-                         float* __restrict__ absmax) {
+                         float* __restrict__ absmax, const Eqv2PlaneArgs PA) {
   constexpr int K = Dim<L>::K, WS = Dim<L>::WS;
   __shared__ __align__(16) float sw[wpad_off(L + 1)];
+  float pscale = 1.f;
+  if constexpr (PL) pscale = eqv2_plane_scale(PA, blockIdx.x == 0 && threadIdx.x == 0);
   EQV2_DYN_SMEM(float, spart);   // [blockDim.x] partial d(alpha)
   constexpr int KR = mpos<L, M>(L, -M) + 1;
   const long long e = blockIdx.x;
@@ -426,7 +440,8 @@ rotinv_reduce_bwd_kernel(const float* __restrict__ dout, const float* __restrict
         if (p < rows_used) {
           const float t = row_dot<l>(sw, l + m, g + l * l);
           if (alpha) da = fmaf(t, vv[p], da);
-          dvp[(long long)p * Cv] = t * a;
+          if constexpr (PL) eqv2_plane_store(PA, e * PA.ld + (long long)p * Cv + c, t * a, pscale);
+          else dvp[(long long)p * Cv] = t * a;
           amax = fmaxf(amax, fabsf(t * a));
         }
       });
@@ -466,8 +481,8 @@ extern "C" int eqv2_gather_rotate_fwd(const float* x, const long long* src, cons
   const int threads = min(256, round32(2 * C));
 #define X(L_, M_)                                                                                              \
   if (lmax == L_ && mmax == M_) {                                                                              \
-    auto kfn = gather_rotate_fwd_kernel<L_, M_>;                                                                                    \
-    EQV2_LAUNCH(kfn, dim3((unsigned)E, (2 * C + threads - 1) / threads), dim3(threads), 0, stream, x, src, dst, wig, rad, out, C, Kr, nrad, absmax); \
+    auto kfn = gather_rotate_fwd_kernel<L_, M_, false>;                                                                             \
+    EQV2_LAUNCH(kfn, dim3((unsigned)E, (2 * C + threads - 1) / threads), dim3(threads), 0, stream, x, src, dst, wig, rad, out, C, Kr, nrad, absmax, Eqv2PlaneArgs{}); \
     EQV2_CHECK_LAUNCH("eqv2_gather_rotate_fwd");                                                               \
     return 0;                                                                                                  \
   }
@@ -503,8 +518,8 @@ extern "C" int eqv2_gather_rotate_drad(const float* x, const long long* src, con
   const int threads = min(256, round32(2 * C));
 #define X(L_, M_)                                                                                              \
   if (lmax == L_ && mmax == M_) {                                                                              \
-    auto kfn = gather_rotate_drad_kernel<L_, M_>;                                                              \
-    EQV2_LAUNCH(kfn, dim3((unsigned)E, (2 * C + threads - 1) / threads), dim3(threads), 0, stream, x, src, dst, wig, dA, drad, C, Kr, nrad, absmax);     \
+    auto kfn = gather_rotate_drad_kernel<L_, M_, false>;                                                       \
+    EQV2_LAUNCH(kfn, dim3((unsigned)E, (2 * C + threads - 1) / threads), dim3(threads), 0, stream, x, src, dst, wig, dA, drad, C, Kr, nrad, absmax, Eqv2PlaneArgs{});     \
     EQV2_CHECK_LAUNCH("eqv2_gather_rotate_drad");                                                              \
     return 0;                                                                                                  \
   }
@@ -544,11 +559,87 @@ extern "C" int eqv2_rotinv_reduce_bwd(const float* dout, const float* val, const
   const int threads = round32(max(Cv, heads));
 #define X(L_, M_)                                                                                              \
   if (lmax == L_ && mmax == M_) {                                                                              \
-    auto kfn = rotinv_reduce_bwd_kernel<L_, M_>;                                                                                    \
-    EQV2_LAUNCH(kfn, dim3((unsigned)E), dim3(threads), threads * sizeof(float), stream, dout, val, alpha, wig, dst, dval, dalpha, Cv, rows_used, val_estride, heads, scale, absmax); \
+    auto kfn = rotinv_reduce_bwd_kernel<L_, M_, false>;                                                                             \
+    EQV2_LAUNCH(kfn, dim3((unsigned)E), dim3(threads), threads * sizeof(float), stream, dout, val, alpha, wig, dst, dval, dalpha, Cv, rows_used, val_estride, heads, scale, absmax, Eqv2PlaneArgs{}); \
     EQV2_CHECK_LAUNCH("eqv2_rotinv_reduce_bwd");                                                               \
     return 0;                                                                                                  \
   }
   EQV2_ROT_DISPATCH("rotinv_reduce_bwd", X)
 #undef X
 }
+
+#ifndef EQV2_CPU_EMU
+// ---- producer-side operand planes: the same three kernels writing scaled fp16 hi/lo planes instead of fp32 ----------
+static int check_planes(const char* who, const void* planes, long long plane, long long ld, long long cols,
+                        const float* bound_a, const float* bound_out) {
+  EQV2_REQUIRE(planes != nullptr && bound_a != nullptr && bound_out != nullptr, "%s: null plane / bound pointer", who);
+  EQV2_REQUIRE(ld >= cols && (ld % 8) == 0 && (plane % 8) == 0 && (((uintptr_t)planes) & 15) == 0,
+               "%s: planes must be 16-byte aligned, ld %% 8 == 0 and ld >= cols", who);
+  return 0;
+}
+
+extern "C" int eqv2_gather_rotate_fwd_planes(const float* x, const long long* src, const long long* dst,
+                                             const float* wig, const float* rad, void* planes, long long plane,
+                                             long long ld, const float* bound_x, const float* bound_rad, float* bound_out,
+                                             long long E, int C, int lmax, int mmax, int Kr, int nrad, void* stream) {
+  if (E == 0) return 0;
+  EQV2_REQUIRE(C > 0 && Kr > 0 && rad != nullptr && bound_rad != nullptr, "gather_rotate_fwd_planes: bad arguments");
+  if (check_planes("gather_rotate_fwd_planes", planes, plane, ld, (long long)Kr * 2 * C, bound_x, bound_out)) return 1;
+  const Eqv2PlaneArgs PA{planes, plane, ld, bound_x, bound_rad, 1.01f * sqrtf((float)(2 * lmax + 1)), bound_out};
+  const int threads = min(256, round32(2 * C));
+#define X(L_, M_)                                                                                              \
+  if (lmax == L_ && mmax == M_) {                                                                              \
+    auto kfn = gather_rotate_fwd_kernel<L_, M_, true>;                                                         \
+    EQV2_LAUNCH(kfn, dim3((unsigned)E, (2 * C + threads - 1) / threads), dim3(threads), 0, stream, x, src, dst, wig, rad, (float*)nullptr, C, Kr, nrad, (float*)nullptr, PA); \
+    EQV2_CHECK_LAUNCH("eqv2_gather_rotate_fwd_planes");                                                        \
+    return 0;                                                                                                  \
+  }
+  EQV2_ROT_DISPATCH("gather_rotate_fwd_planes", X)
+#undef X
+}
+
+extern "C" int eqv2_gather_rotate_drad_planes(const float* x, const long long* src, const long long* dst,
+                                              const float* wig, const float* dA, void* planes, long long plane,
+                                              long long ld, const float* bound_x, const float* bound_dA, float* bound_out,
+                                              long long E, int C, int lmax, int mmax, int Kr, int nrad, void* stream) {
+  if (E == 0) return 0;
+  EQV2_REQUIRE(C > 0 && Kr > 0 && bound_dA != nullptr, "gather_rotate_drad_planes: bad arguments");
+  if (check_planes("gather_rotate_drad_planes", planes, plane, ld, nrad, bound_x, bound_out)) return 1;
+  const Eqv2PlaneArgs PA{planes, plane, ld, bound_x, bound_dA, 2.02f * sqrtf((float)(2 * lmax + 1)), bound_out};
+  const int threads = min(256, round32(2 * C));
+#define X(L_, M_)                                                                                              \
+  if (lmax == L_ && mmax == M_) {                                                                              \
+    auto kfn = gather_rotate_drad_kernel<L_, M_, true>;                                                        \
+    EQV2_LAUNCH(kfn, dim3((unsigned)E, (2 * C + threads - 1) / threads), dim3(threads), 0, stream, x, src, dst, wig, dA, (float*)nullptr, C, Kr, nrad, (float*)nullptr, PA); \
+    EQV2_CHECK_LAUNCH("eqv2_gather_rotate_drad_planes");                                                       \
+    return 0;                                                                                                  \
+  }
+  EQV2_ROT_DISPATCH("gather_rotate_drad_planes", X)
+#undef X
+}
+
+extern "C" int eqv2_rotinv_reduce_bwd_planes(const float* dout, const float* val, const float* alpha, const float* wig,
+                                             const long long* dst, void* planes, long long plane, long long ld,
+                                             const float* bound_dout, float alpha_bound, float* bound_out, float* dalpha,
+                                             long long E, int Cv, int rows_used, long long val_estride, int heads,
+                                             int lmax, int mmax, float scale, void* stream) {
+  if (E == 0) return 0;
+  EQV2_REQUIRE(Cv > 0 && Cv <= 256, "rotinv_reduce_bwd_planes: Cv=%d out of range", Cv);
+  EQV2_REQUIRE(alpha == nullptr || (heads > 0 && Cv % heads == 0), "rotinv_reduce_bwd_planes: heads must divide Cv");
+  EQV2_REQUIRE(alpha_bound > 0.f, "rotinv_reduce_bwd_planes: alpha_bound must be positive");
+  if (check_planes("rotinv_reduce_bwd_planes", planes, plane, ld, (long long)rows_used * Cv, bound_dout, bound_out)) return 1;
+  const float resc = (lmax > mmax) ? (float)(2 * lmax + 1) / (float)(2 * mmax + 1) : 1.0f;
+  const Eqv2PlaneArgs PA{planes, plane, ld, bound_dout, nullptr,
+                         1.01f * alpha_bound * fabsf(scale) * sqrtf((float)(2 * lmax + 1) * resc), bound_out};
+  const int threads = round32(max(Cv, heads));
+#define X(L_, M_)                                                                                              \
+  if (lmax == L_ && mmax == M_) {                                                                              \
+    auto kfn = rotinv_reduce_bwd_kernel<L_, M_, true>;                                                         \
+    EQV2_LAUNCH(kfn, dim3((unsigned)E), dim3(threads), threads * sizeof(float), stream, dout, val, alpha, wig, dst, (float*)nullptr, dalpha, Cv, rows_used, val_estride, heads, scale, (float*)nullptr, PA); \
+    EQV2_CHECK_LAUNCH("eqv2_rotinv_reduce_bwd_planes");                                                        \
+    return 0;                                                                                                  \
+  }
+  EQV2_ROT_DISPATCH("rotinv_reduce_bwd_planes", X)
+#undef X
+}
+#endif  // EQV2_CPU_EMU

@@ -127,3 +127,58 @@ extern "C" int eqv2_seg_colsum(const float* src, long long ld, const int* rowptr
   EQV2_CHECK_LAUNCH("eqv2_seg_colsum (final)");
   return 0;
 }
+
+#ifndef EQV2_CPU_EMU
+// Column sums of a matrix that exists only as scaled fp16 hi/lo operand planes (bias gradient of a layer whose output
+// gradient was written as planes by its producer kernel): out[c] = (1/s) sum_r (hi + lo)[r, col_off + c], s from the
+// plane's bound slot.  Same two stages and fixed order as seg_colsum.
+namespace {
+__global__ void planes_colsum_partial_kernel(const __half* __restrict__ hi, long long plane, long long ld, long long rows,
+                                             int C, int S, float* __restrict__ partial) {
+  const int s = blockIdx.y;
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= C) return;
+  float a[4] = {0.f, 0.f, 0.f, 0.f};
+  long long i = s;
+  for (; i + 3ll * S < rows; i += 4ll * S) {
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const long long o = (i + (long long)u * S) * ld + c;
+      a[u] += __half2float(hi[o]) + __half2float(hi[o + plane]);
+    }
+  }
+  for (; i < rows; i += S) a[0] += __half2float(hi[i * ld + c]) + __half2float(hi[i * ld + c + plane]);
+  partial[(long long)s * C + c] = (a[0] + a[1]) + (a[2] + a[3]);
+}
+__global__ void planes_colsum_final_kernel(const float* __restrict__ partial, int C, int S, const float* __restrict__ bound,
+                                           float* __restrict__ out) {
+  __shared__ float red[8][33];
+  float sc, inv;
+  eqv2_scale_of(eqv2_read_absmax(bound), sc, inv);
+  const int c = blockIdx.x * 32 + threadIdx.x;
+  float a = 0.f;
+  if (c < C)
+    for (int s = threadIdx.y; s < S; s += 8) a += partial[(long long)s * C + c];
+  red[threadIdx.y][threadIdx.x] = a;
+  __syncthreads();
+  if (threadIdx.y == 0 && c < C) {
+    float t = 0.f;
+#pragma unroll
+    for (int q = 0; q < 8; ++q) t += red[q][threadIdx.x];
+    out[c] = t * inv;
+  }
+}
+}  // namespace
+
+extern "C" int eqv2_planes_colsum(const void* planes, long long plane, long long ld, long long col_off, long long rows,
+                                  int C, int S, const float* bound, float* partial, float* out, void* stream) {
+  EQV2_REQUIRE(S >= 1 && C >= 0 && planes && bound && partial && out, "eqv2_planes_colsum: bad arguments");
+  if (C == 0) return 0;
+  const __half* hi = reinterpret_cast<const __half*>(planes) + col_off;
+  EQV2_LAUNCH(planes_colsum_partial_kernel, dim3((C + 127) / 128, S), dim3(128), 0, stream, hi, plane, ld, rows, C, S, partial);
+  EQV2_CHECK_LAUNCH("eqv2_planes_colsum (partial)");
+  EQV2_LAUNCH(planes_colsum_final_kernel, dim3((C + 31) / 32), dim3(32, 8), 0, stream, partial, C, S, bound, out);
+  EQV2_CHECK_LAUNCH("eqv2_planes_colsum (final)");
+  return 0;
+}
+#endif

@@ -6,6 +6,7 @@ import torch
 import torch.nn as nn
 
 from .. import ops
+from ..EquiformerV2Functions.drop import set_num_graphs
 from ..EquiformerV2Functions.edge_rot_mat import init_edge_rot_mat
 from ..EquiformerV2Functions.input_block import EdgeDegreeEmbedding
 from ..EquiformerV2Functions.layer_norm import get_normalization_layer
@@ -100,13 +101,34 @@ class EquiformerV2_QM9(nn.Module):
     def _init_edge_rot_mat(self, data, edge_index, edge_distance_vec):
         return init_edge_rot_mat(edge_distance_vec)
 
+    def prepare(self, data):
+        """Data-dependent, host-synchronising head of a forward pass (graphs.GraphedTrainStep): radius graph (one
+        read-back of the edge count) and edge frames; everything after it has shapes fixed by (atoms, edges)."""
+        if "edge_index" in data:
+            ei, d, v = data["edge_index"], data["edge_distance"], data["edge_distance_vec"]
+        else:
+            ei, d, v = ops.radius_graph(data["pos"], data["natoms"], data["batch"], self.max_radius, self.max_neighbors)
+        return {"edge_index": ei, "edge_distance": d, "edge_distance_vec": v,
+                "edge_frames": self._init_edge_rot_mat(data, ei, v)}
+
     def forward(self, data):
+        set_num_graphs(len(data["natoms"]))          # GraphDropPath: no batch.max() read-back (drop.py)
+        try:
+            return self._forward(data)
+        finally:
+            set_num_graphs(None)
+
+    def _forward(self, data):
         self.batch_size = len(data["natoms"])
         self.dtype, self.device = data["pos"].dtype, data["pos"].device
         atomic_numbers = data["atomic_numbers"].long()
         num_atoms = atomic_numbers.shape[0]
-        edge_index, edge_distance, edge_vec, _, _, _ = self.generate_graph(data)
-        frames = self._init_edge_rot_mat(data, edge_index, edge_vec)
+        if "edge_frames" in data:
+            edge_index, edge_distance, edge_vec, frames = (data["edge_index"], data["edge_distance"],
+                                                           data["edge_distance_vec"], data["edge_frames"])
+        else:
+            edge_index, edge_distance, edge_vec, _, _, _ = self.generate_graph(data)
+            frames = self._init_edge_rot_mat(data, edge_index, edge_vec)
         for rot in self.SO3_rotation:
             rot.set_wigner(frames)
 

@@ -460,14 +460,38 @@ def set_gemm_mode(mode):
       'tf32x3'          : tcgen05 kind::tf32 with the 3xTF32 hi/lo split done in the kernel -- fp32-class accuracy,
       'tf32'            : tcgen05, single TF32 pass (separately stated tolerance),
       'fp32'            : exact FFMA engine for everything.
+      'f16'             : the f16x3 engine reading the hi planes only -- ONE fp16 tensor-core pass (reduced precision,
+                          separately stated tolerance; BASELINE configs[3] "bf16/TF32 GEMM mode").
     Problems a tensor-core engine cannot address (two-level strided degree slabs, unaligned operands) run on the
     next engine down the list."""
-    assert mode in ("fp32", "tf32x3", "tf32", "f16x3")
+    assert mode in ("fp32", "tf32x3", "tf32", "f16x3", "f16")
     _GEMM_MODE["mode"] = mode
 
 
 def gemm_mode():
     return _GEMM_MODE["mode"]
+
+
+class PlaneRef:
+    """Stand-in for an fp32 matrix [rows, cols] that exists ONLY as the scaled fp16 hi/lo planes a producer kernel wrote
+    (eqv2_*_planes entry points): it gives the GEMM descriptors an identity to find those planes by (split_scope) and the
+    few tensor attributes the descriptor code looks at.  A launch with such an operand always runs on the f16 engine."""
+    is_cuda = True
+    dtype = _F32
+    _version = 0
+
+    def __init__(self, rows, cols, device):
+        self.shape = (int(rows), int(cols))
+        self.device = device
+
+    def is_contiguous(self):
+        return True
+
+    def dim(self):
+        return 2
+
+    def data_ptr(self):
+        return 0
 
 
 class OperandSrc:
@@ -524,7 +548,7 @@ def _pick_split(descs, reduce_dim_large):
         return 1
     tiles = sum(((d.M + 127) // 128) * ((d.N + 127) // 128) for d in descs)
     kmax = max(d.K for d in descs)
-    if _GEMM_MODE["mode"] == "f16x3" and _f16_ok(descs):
+    if _GEMM_MODE["mode"] in ("f16x3", "f16") and _f16_ok(descs):
         nkb = (kmax + 63) // 64
         best, best_cost = 1, None
         for s in range(1, 33):
@@ -629,7 +653,7 @@ def _small_zeros(shape, device):
 
 def _absmax_slot(device):
     """Zero-initialised slot for a producer kernel's `absmax` output (only allocated in f16x3 mode)."""
-    return _zeroed_slot(device) if _GEMM_MODE["mode"] == "f16x3" else None
+    return _zeroed_slot(device) if _GEMM_MODE["mode"] in ("f16x3", "f16") else None
 
 
 def _register_absmax(t, slot):
@@ -730,11 +754,18 @@ def _split_of(splits, src):
 F16_MIN_MACS = 1 << 21      # launches below this many multiply-adds stay on the FFMA engine (tests set it to 0)
 
 
+def _f16_forced(descs):
+    return any(src is not None and isinstance(src.t, PlaneRef) for d in descs for src in d.src)
+
+
 def _f16_ok(descs):
     """Should the f16x3 engine take this launch?  Measured (profiles/): the persistent TMA kernel beats the FFMA engine
     and the in-kernel-split tf32 engine from ~2 M multiply-adds per launch, operand splits included (a 640 x 128 x 128
-    node-level linear takes 69 us on the FFMA engine: 5 CTAs)."""
-    return all(_f16_addressable(d) for d in descs) and sum(d.M * d.N * d.K for d in descs) >= F16_MIN_MACS
+    node-level linear takes 69 us on the FFMA engine: 5 CTAs).  Operands that exist only as planes force it."""
+    if not all(_f16_addressable(d) for d in descs):
+        assert not _f16_forced(descs), "an operand that exists only as fp16 planes is not addressable by the f16 engine"
+        return False
+    return _f16_forced(descs) or sum(d.M * d.N * d.K for d in descs) >= F16_MIN_MACS
 
 
 def _f16_addressable(d):
@@ -750,7 +781,7 @@ def _f16_addressable(d):
 _GEMM16_LOG = None        # diagnostics: set to a list to record (shapes, split_k) of every f16x3 launch, in order
 
 
-def _run_gemm_f16(descs, split_k, flops, nbytes):
+def _run_gemm_f16(descs, split_k, flops, nbytes, out=None):
     if _GEMM16_LOG is not None:
         _GEMM16_LOG.append((tuple((d.M, d.N, d.K, d.transA, d.transB) for d in descs), split_k))
     splits = _splits_for([src for d in descs for src in d.src])
@@ -765,24 +796,39 @@ def _run_gemm_f16(descs, split_k, flops, nbytes):
         a.a_ld, a.a_plane, a.b_ld, a.b_plane, a.c_ld = sa.cols_pad, sa.plane, sb.cols_pad, sb.plane, d.c_ld
         a.c_rpb, a.c_bs = d.c_rpb, d.c_bs
         a.M, a.N, a.K, a.transA, a.transB, a.accumulate = d.M, d.N, d.K, d.transA, d.transB, d.accumulate
-    _lib.call("eqv2_gemm_f16", ctypes.cast(arr, ctypes.c_void_p), n, int(split_k), _lib.stream_ptr(),
-              work=(flops, nbytes))
+    slot = None
+    if out is not None and split_k == 1:
+        # the epilogue reduces max |C| while storing: whichever kernel consumes `out` next (a producer that writes operand
+        # planes, or the operand split) finds it in the registry instead of re-reading the tensor
+        slot = _zeroed_slot(out.device)
+        for a in arr:
+            a.c_absmax = slot.data_ptr()
+    if _GEMM_MODE["mode"] == "f16":
+        _lib.call("eqv2_gemm_f16_ex", ctypes.cast(arr, ctypes.c_void_p), n, int(split_k), 1, _lib.stream_ptr(),
+                  work=(flops, nbytes))
+    else:
+        _lib.call("eqv2_gemm_f16", ctypes.cast(arr, ctypes.c_void_p), n, int(split_k), _lib.stream_ptr(),
+                  work=(flops, nbytes))
+    if slot is not None:
+        _register_absmax(out, slot)
     return splits
 
 
 _GEMM_LOG = None          # diagnostics: set to a list to record the launches the f16x3 engine declines
 
 
-def run_gemm(descs, split_k=1):
-    """-> {OperandSrc.key: SplitF16} of the operand splits the f16x3 engine used ({} on the other engines)."""
+def run_gemm(descs, split_k=1, out=None):
+    """-> {OperandSrc.key: SplitF16} of the operand splits the f16x3 engine used ({} on the other engines).
+    `out`: the tensor all groups write into (when every group's C lies in one tensor): its max |.| is then reduced by the
+    GEMM epilogue and registered (`_known_absmax`)."""
     n = len(descs)
     assert 1 <= n <= _lib.MAX_GEMM_GROUPS
     flops = sum(2.0 * d.M * d.N * d.K for d in descs)
     nbytes = sum(4.0 * (d.M * d.K + d.K * d.N + d.M * d.N) for d in descs)
     mode = _GEMM_MODE["mode"]
-    if mode == "f16x3":
+    if mode in ("f16x3", "f16"):
         if _f16_ok(descs):
-            return _run_gemm_f16(descs, split_k, flops, nbytes)
+            return _run_gemm_f16(descs, split_k, flops, nbytes, out)
         if _GEMM_LOG is not None:
             _GEMM_LOG.append([(d.M, d.N, d.K, d.transA, d.transB, _f16_addressable(d)) for d in descs])
         mode = "tf32x3"
@@ -813,22 +859,51 @@ def _covers(slices, width):
     return pos == width
 
 
+def _slice_mm(X, bias, xs, ys, y_width, transW, Ws):
+    """Y[:, ys_g] = X[:, xs_g] @ (W_g^T | W_g) as ONE grouped launch -> (Y, [split of X, splits of the W_g]).
+    X may be a PlaneRef (operand that exists only as fp16 planes, found through the active split_scope)."""
+    rows, xw = X.shape
+    Y = (torch.empty if _covers(ys, y_width) else torch.zeros)(rows, y_width, dtype=_F32, device=X.device)
+    descs = []
+    for g, ((xo, k), (yo, n)) in enumerate(zip(xs, ys)):
+        assert tuple(Ws[g].shape) == ((n, k) if transW else (k, n)), (Ws[g].shape, n, k, transW)
+        descs.append(_desc(X, Ws[g], Y, bias if g == 0 else None, rows, n, k, 0, 1 if transW else 0,
+                           _plain(xw), _plain(Ws[g].shape[1]), _plain(y_width), a_off=xo, c_off=yo))
+    sp = run_gemm(descs, out=Y) if rows > 0 else {}
+    return Y, [_split_of(sp, descs[0].src[0])] + [_split_of(sp, d.src[1]) for d in descs]
+
+
+def _slice_outer(U, V, us, vs):
+    """W_g = U[:, us_g]^T @ V[:, vs_g] (split-K over the rows) -> (list of W_g, [split of U, split of V]); U / V may be
+    PlaneRefs."""
+    rows = U.shape[0]
+    descs = []
+    for (uo, m), (vo, n) in zip(us, vs):
+        descs.append(_desc(U, V, U, None, m, n, rows, 1, 0, _plain(U.shape[1]), _plain(V.shape[1]), _plain(n),
+                           a_off=uo, b_off=vo))
+    split = _pick_split(descs, True) if rows > 0 else 1
+    # all groups' outputs come out of ONE allocation (one zero-fill launch when split-K atomics need it, not one per
+    # group); every block starts 16-byte aligned
+    sizes = [(m * n + 3) // 4 * 4 for (_, m), (_, n) in zip(us, vs)]
+    flat = (torch.zeros if (split > 1 or rows == 0) else torch.empty)(sum(sizes), dtype=_F32, device=U.device)
+    outs, off = [], 0
+    for d, sz, ((uo, m), (vo, n)) in zip(descs, sizes, zip(us, vs)):
+        W = flat[off:off + m * n].view(m, n)
+        off += sz
+        d.C = W.data_ptr()
+        outs.append(W)
+    sp = run_gemm(descs, split) if rows > 0 else {}
+    return outs, ([_split_of(sp, descs[0].src[0]), _split_of(sp, descs[0].src[1])] if descs else [None, None])
+
+
 class SliceMm(torch.autograd.Function):
     @staticmethod
     def forward(ctx, X, bias, xs, ys, y_width, transW, *Ws):
         _lib.check_device(X, bias, *Ws)
         assert X.is_contiguous() and all(w.is_contiguous() for w in Ws)
-        rows, xw = X.shape
-        Y = (torch.empty if _covers(ys, y_width) else torch.zeros)(rows, y_width, dtype=_F32, device=X.device)
-        descs = []
-        for g, ((xo, k), (yo, n)) in enumerate(zip(xs, ys)):
-            assert tuple(Ws[g].shape) == ((n, k) if transW else (k, n)), (Ws[g].shape, n, k, transW)
-            descs.append(_desc(X, Ws[g], Y, bias if g == 0 else None, rows, n, k, 0, 1 if transW else 0,
-                               _plain(xw), _plain(Ws[g].shape[1]), _plain(y_width), a_off=xo, c_off=yo))
-        sp = run_gemm(descs) if rows > 0 else {}
+        Y, ctx.splits = _slice_mm(X, bias, xs, ys, y_width, transW, Ws)
         ctx.save_for_backward(X, *Ws)
         ctx.spec = (xs, ys, y_width, transW, bias is not None)
-        ctx.splits = [_split_of(sp, descs[0].src[0])] + [_split_of(sp, d.src[1]) for d in descs]
         return Y
 
     @staticmethod
@@ -858,26 +933,9 @@ class SliceOuter(torch.autograd.Function):
     def forward(ctx, U, V, us, vs):
         _lib.check_device(U, V)
         assert U.is_contiguous() and V.is_contiguous()
-        rows = U.shape[0]
-        descs = []
-        for (uo, m), (vo, n) in zip(us, vs):
-            descs.append(_desc(U, V, U, None, m, n, rows, 1, 0, _plain(U.shape[1]), _plain(V.shape[1]), _plain(n),
-                               a_off=uo, b_off=vo))
-        split = _pick_split(descs, True) if rows > 0 else 1
-        # all groups' outputs come out of ONE allocation (one zero-fill launch when split-K atomics need it, not one per
-        # group); every block starts 16-byte aligned
-        sizes = [(m * n + 3) // 4 * 4 for (_, m), (_, n) in zip(us, vs)]
-        flat = (torch.zeros if (split > 1 or rows == 0) else torch.empty)(sum(sizes), dtype=_F32, device=U.device)
-        outs, off = [], 0
-        for d, sz, ((uo, m), (vo, n)) in zip(descs, sizes, zip(us, vs)):
-            W = flat[off:off + m * n].view(m, n)
-            off += sz
-            d.C = W.data_ptr()
-            outs.append(W)
-        sp = run_gemm(descs, split) if rows > 0 else {}
+        outs, ctx.splits = _slice_outer(U, V, us, vs)
         ctx.save_for_backward(U, V)
         ctx.spec = (us, vs)
-        ctx.splits = [_split_of(sp, descs[0].src[0]), _split_of(sp, descs[0].src[1])] if descs else [None, None]
         return tuple(outs)
 
     @staticmethod
@@ -913,7 +971,7 @@ class SlabMm(torch.autograd.Function):
                                a_off=l * l * Ci, b_off=l * Wo * Wi, c_off=l * l * Co,
                                a_src=OperandSrc(x, N * K, Ci, K, N * l * l, 0),
                                b_src=OperandSrc(W, L1 * Wo, Wi, 0, l * Wo, 0)))
-        sp = run_gemm(descs) if N > 0 else {}
+        sp = run_gemm(descs, out=y) if N > 0 else {}
         ctx.save_for_backward(x, W)
         ctx.spec = (transW, bias is not None)
         ctx.splits = [_split_of(sp, descs[0].src[0]), _split_of(sp, descs[0].src[1])]
@@ -1034,6 +1092,14 @@ def wigner_to_dense(wig, lmax):
     return out
 
 
+def _rot_work(lay, E, N, cols, node_cols, floats_per_edge):
+    """Algorithmic (FLOPs, bytes) of one Wigner rotate / inverse-rotate launch: per edge and feature column every kept
+    row of degree l costs 2l+1 multiply-adds (block-diagonal rotation) + 1 for the radial / attention weighting; traffic =
+    the per-edge operands read / written once (`floats_per_edge`) + one pass over the node tensor [N, K, node_cols]."""
+    macs = sum(2 * l + 2 for l in lay.row_l)
+    return (2.0 * E * cols * macs, 4.0 * (E * floats_per_edge + N * lay.K * node_cols))
+
+
 def _gr_fwd(x, rad, plan, wig, lmax, mmax):
     lay = CoeffLayout.get(lmax, mmax)
     tabs = lay.dev(x.device)
@@ -1045,7 +1111,8 @@ def _gr_fwd(x, rad, plan, wig, lmax, mmax):
     slot = _absmax_slot(x.device)
     _lib.call("eqv2_gather_rotate_fwd", x.data_ptr(), plan.src.data_ptr(), plan.dst.data_ptr(), wig.data_ptr(),
               _lib.ptr(rad), out.data_ptr(), tabs["pos_of_full"].data_ptr(), tabs["rad_slot"].data_ptr(),
-              plan.E, C, lmax, mmax, lay.Kr, nrad, _lib.ptr(slot), _lib.stream_ptr())
+              plan.E, C, lmax, mmax, lay.Kr, nrad, _lib.ptr(slot), _lib.stream_ptr(),
+              work=_rot_work(lay, plan.E, N, 2 * C, C, (nrad if rad is not None else 0) + wig.shape[1] + lay.Kr * 2 * C))
     _register_absmax(out, slot)
     return out
 
@@ -1060,12 +1127,14 @@ def _gr_bwd(x, rad, gA, plan, wig, lmax, mmax, want_dx=True, want_drad=True):
         gx = torch.empty_like(x)
         _lib.call("eqv2_gather_rotate_dx", wig.data_ptr(), _lib.ptr(rad), gA.data_ptr(), plan.rowptr_src.data_ptr(),
                   plan.perm_src.data_ptr(), plan.rowptr_dst.data_ptr(), plan.perm_dst.data_ptr(), gx.data_ptr(), N, C,
-                  lmax, mmax, lay.Kr, nrad, _lib.stream_ptr())
+                  lmax, mmax, lay.Kr, nrad, _lib.stream_ptr(),
+                  work=_rot_work(lay, plan.E, N, 2 * C, C, (nrad if rad is not None else 0) + wig.shape[1] + lay.Kr * 2 * C))
     if want_drad:
         grad = torch.empty(plan.E, nrad, dtype=_F32, device=x.device)
         slot = _absmax_slot(x.device)
         _lib.call("eqv2_gather_rotate_drad", x.data_ptr(), plan.src.data_ptr(), plan.dst.data_ptr(), wig.data_ptr(),
-                  gA.data_ptr(), grad.data_ptr(), plan.E, C, lmax, mmax, lay.Kr, nrad, _lib.ptr(slot), _lib.stream_ptr())
+                  gA.data_ptr(), grad.data_ptr(), plan.E, C, lmax, mmax, lay.Kr, nrad, _lib.ptr(slot), _lib.stream_ptr(),
+                  work=_rot_work(lay, plan.E, N, 2 * C, C, nrad + wig.shape[1] + lay.Kr * 2 * C))
         _register_absmax(grad, slot)
     return gx, grad
 
@@ -1130,7 +1199,8 @@ def _rir_fwd(val, alpha, plan, wig, lmax, mmax, rows_used, heads, scale, Cv):
     _lib.call("eqv2_rotinv_reduce_fwd", val.data_ptr(), _lib.ptr(alpha), wig.data_ptr(),
               plan.rowptr_dst.data_ptr(), plan.perm_dst.data_ptr(), out.data_ptr(),
               tabs["pos_of_full"].data_ptr(), plan.N, Cv, rows_used, rows_used * Cv, heads, lmax, mmax,
-              float(scale), _lib.stream_ptr())
+              float(scale), _lib.stream_ptr(),
+              work=_rot_work(lay, plan.E, plan.N, Cv, Cv, rows_used * Cv + heads + wig.shape[1]))
     return out
 
 
@@ -1143,7 +1213,8 @@ def _rir_bwd(gout, val, alpha, plan, wig, lmax, mmax, rows_used, heads, scale, C
     slot = _absmax_slot(val.device)
     _lib.call("eqv2_rotinv_reduce_bwd", gout.data_ptr(), val.data_ptr(), _lib.ptr(alpha), wig.data_ptr(),
               plan.dst.data_ptr(), gval.data_ptr(), _lib.ptr(galpha), tabs["pos_of_full"].data_ptr(),
-              plan.E, Cv, rows_used, rows_used * Cv, heads, lmax, mmax, float(scale), _lib.ptr(slot), _lib.stream_ptr())
+              plan.E, Cv, rows_used, rows_used * Cv, heads, lmax, mmax, float(scale), _lib.ptr(slot), _lib.stream_ptr(),
+              work=_rot_work(lay, plan.E, plan.N, Cv, Cv, 2 * rows_used * Cv + 2 * heads + wig.shape[1]))
     _register_absmax(gval, slot)
     return gval, galpha
 
@@ -1198,6 +1269,162 @@ class RotInvReduceBwdFn(torch.autograd.Function):
             d_g = t if d_g is None else d_g + t
             d_val, _ = _rir_bwd(gout, val, a, plan, wig, *meta)
         return d_g, d_val, d_alpha, None, None, None
+
+
+# ----------------------------------------------------------------------------------------------
+# First-order fused edge path of the f16 engine: producer kernels write the GEMM operand planes themselves
+# ----------------------------------------------------------------------------------------------
+# With the f16x3 engine every fp32 GEMM operand used to be re-read and re-written once by the operand split (r01:
+# 12.7 % + 2.3 % of the OC20 step, 24.5 GB of HBM traffic per step).  The three edge-parallel rotate kernels now write
+# scaled fp16 hi/lo planes directly, with the scale taken from a bound computed on the device from the registered
+# maxima of their inputs (csrc/common.cuh).  Only for steps that are differentiated once (configs 1-2): the operand
+# then never exists as an fp32 tensor autograd could differentiate again.
+def _planes_for(rows, cols, device):
+    """(PlaneRef, SplitF16) of a [rows, cols] operand a producer kernel is about to write (cols % 64 == 0: no padding)."""
+    ref = PlaneRef(rows, cols, device)
+    return ref, SplitF16(OperandSrc(ref, rows, cols))
+
+
+def fused_planes_available(x, rad, cols):
+    """Can gather_rotate write conv1's A operand as planes?  f16 engine, no padding columns, both input maxima known."""
+    return (_GEMM_MODE["mode"] in ("f16x3", "f16") and rad is not None and cols % 64 == 0 and x.is_cuda
+            and hasattr(_lib.lib(), "eqv2_gather_rotate_fwd_planes")
+            and _known_absmax(x) is not None and _known_absmax(rad) is not None)
+
+
+class GatherRotateConvFn(torch.autograd.Function):
+    """gather x[src]|x[dst] + Wigner rotate + radial modulation (transformer_block.py:250-275, so2_ops.py:142-175) ->
+    first SO(2) convolution (so2_ops.py:150-185) with the intermediate [E, Kr*2C] tensor living only as the GEMM's
+    fp16 operand planes: written once by `eqv2_gather_rotate_fwd_planes`, read by the forward GEMM and again by the
+    weight-gradient GEMM.  Backward: dgrad + wgrad GEMMs, then the dx / drad kernels on the fp32 dgrad output."""
+
+    @staticmethod
+    def forward(ctx, x, rad, bias0, plan, wig, lmax, mmax, groups, *Ws):
+        _lib.check_device(x, rad, wig, bias0, *Ws)
+        assert x.is_contiguous() and rad.is_contiguous() and all(w.is_contiguous() for w in Ws)
+        lay = CoeffLayout.get(lmax, mmax)
+        N, K, C = x.shape
+        E, cols, nrad = plan.E, lay.Kr * 2 * C, lay.nslot * 2 * C
+        assert rad.shape == (E, nrad), (rad.shape, E, nrad)
+        ref, spA = _planes_for(E, cols, x.device)
+        _lib.call("eqv2_gather_rotate_fwd_planes", x.data_ptr(), plan.src.data_ptr(), plan.dst.data_ptr(), wig.data_ptr(),
+                  rad.data_ptr(), spA.buf.data_ptr(), spA.plane, spA.cols_pad, _known_absmax(x).data_ptr(),
+                  _known_absmax(rad).data_ptr(), spA.absmax.data_ptr(), E, C, lmax, mmax, lay.Kr, nrad, _lib.stream_ptr(),
+                  work=_rot_work(lay, E, N, 2 * C, C, nrad + wig.shape[1] + lay.Kr * C))      # planes: 2 x 2 B per value
+        xs = tuple((a_off, k_g) for a_off, k_g, _, _ in groups)
+        ys = tuple((c_off, n_g) for _, _, c_off, n_g in groups)
+        width = sum(n for _, n in ys)
+        with split_scope([(ref, spA)]):
+            Y, splits = _slice_mm(ref, bias0, xs, ys, width, True, Ws)
+        ctx.save_for_backward(x, rad, wig, *Ws)
+        ctx.plan, ctx.lm, ctx.spec = plan, (lmax, mmax), (xs, ys, width, bias0 is not None)
+        ctx.ref, ctx.spA, ctx.wsplits = ref, spA, splits[1:]
+        return Y
+
+    @staticmethod
+    @torch.autograd.function.once_differentiable
+    def backward(ctx, gY):
+        x, rad, wig, *Ws = ctx.saved_tensors
+        xs, ys, width, has_bias = ctx.spec
+        plan, (lmax, mmax) = ctx.plan, ctx.lm
+        gY = gY.contiguous()
+        need_w = any(ctx.needs_input_grad[8:])
+        with split_scope([(ctx.ref, ctx.spA)] + list(zip(Ws, ctx.wsplits))):     # gY is split once for both products
+            gA, _ = _slice_mm(gY, None, ys, xs, ctx.ref.shape[1], False, Ws)
+            gWs = _slice_outer(gY, ctx.ref, ys, xs)[0] if need_w else [None] * len(Ws)
+        gx, grad = _gr_bwd(x, rad, gA, plan, wig, lmax, mmax, want_dx=ctx.needs_input_grad[0],
+                           want_drad=ctx.needs_input_grad[1])
+        gb = colsum(gY, ys[0][0], ys[0][1]) if (has_bias and ctx.needs_input_grad[2]) else None
+        return (gx, grad, gb, None, None, None, None, None, *gWs)
+
+
+class ConvRotInvReduceFn(torch.autograd.Function):
+    """second SO(2) convolution (transformer_block.py:305) -> alpha-weighting + inverse rotation + deterministic
+    dst-segmented sum (transformer_block.py:321-331, so3.py:367-387,304-318).  Backward: `eqv2_rotinv_reduce_bwd_planes`
+    writes d(value) directly as the operand planes of the dgrad / wgrad GEMMs (bound from the registered maximum of the
+    node gradient and `alpha_bound` >= max |alpha|); Z is kept only as the planes the forward GEMM read."""
+
+    @staticmethod
+    def forward(ctx, Zm, alpha, bias0, plan, wig, lmax, mmax, heads, alpha_bound, groups, *Ws):
+        _lib.check_device(Zm, alpha, wig, bias0, *Ws)
+        assert Zm.is_contiguous() and alpha.is_contiguous() and all(w.is_contiguous() for w in Ws)
+        lay = CoeffLayout.get(lmax, mmax)
+        xs = tuple((a_off, k_g) for a_off, k_g, _, _ in groups)
+        ys = tuple((c_off, n_g) for _, _, c_off, n_g in groups)
+        width = sum(n for _, n in ys)
+        V, splits = _slice_mm(Zm, bias0, xs, ys, width, True, Ws)
+        Cv = width // lay.Kr
+        meta = (lmax, mmax, lay.Kr, heads, 1.0, Cv)
+        out = _rir_fwd(V, alpha, plan, wig, *meta)
+        planes_ok = splits[0] is not None and width % 64 == 0 and hasattr(_lib.lib(), "eqv2_rotinv_reduce_bwd_planes")
+        if planes_ok:           # Z itself is not needed again: its planes serve the weight gradient
+            ctx.save_for_backward(V, alpha, wig, *Ws)
+            ctx.zref = PlaneRef(Zm.shape[0], Zm.shape[1], Zm.device)
+            ctx.spZ = splits[0]
+            ctx.spZ.version = 0
+        else:
+            ctx.save_for_backward(V, alpha, wig, *Ws, Zm)
+            ctx.zref, ctx.spZ = None, splits[0]
+        ctx.plan, ctx.meta, ctx.spec, ctx.wsplits = plan, meta, (xs, ys, width, float(alpha_bound)), splits[1:]
+        ctx.nw, ctx.has_bias = len(Ws), bias0 is not None
+        return out
+
+    @staticmethod
+    @torch.autograd.function.once_differentiable
+    def backward(ctx, gout):
+        saved = ctx.saved_tensors
+        V, alpha, wig = saved[:3]
+        Ws = saved[3:3 + ctx.nw]
+        xs, ys, width, alpha_bound = ctx.spec
+        plan, meta = ctx.plan, ctx.meta
+        lmax, mmax, rows_used, heads, scale, Cv = meta
+        lay = CoeffLayout.get(lmax, mmax)
+        gout = gout.contiguous()
+        bound = _known_absmax(gout)
+        E = plan.E
+        need_w = any(ctx.needs_input_grad[10:])
+        want_b = ctx.has_bias and ctx.needs_input_grad[2]
+        gb = None
+        if ctx.zref is not None and bound is not None:
+            gref, spG = _planes_for(E, width, gout.device)
+            galpha = torch.empty_like(alpha)
+            _lib.call("eqv2_rotinv_reduce_bwd_planes", gout.data_ptr(), V.data_ptr(), alpha.data_ptr(), wig.data_ptr(),
+                      plan.dst.data_ptr(), spG.buf.data_ptr(), spG.plane, spG.cols_pad, bound.data_ptr(),
+                      float(alpha_bound), spG.absmax.data_ptr(), galpha.data_ptr(), E, Cv, rows_used, rows_used * Cv,
+                      heads, lmax, mmax, float(scale), _lib.stream_ptr(),
+                      work=_rot_work(lay, E, plan.N, Cv, Cv, 2 * rows_used * Cv + 2 * heads + wig.shape[1]))
+            scope = [(gref, spG), (ctx.zref, ctx.spZ)] + list(zip(Ws, ctx.wsplits))
+            gv_op, z_op = gref, ctx.zref
+            if want_b:          # bias gradient = column sums of d(value) over the m = 0 block, read from the planes
+                yo, n = ys[0]
+                S = max(1, min(E // 16, -(-2368 // ((n + 127) // 128))))
+                partial = torch.empty(S * n, dtype=_F32, device=gout.device)
+                gb = torch.empty(n, dtype=_F32, device=gout.device)
+                _lib.call("eqv2_planes_colsum", spG.buf.data_ptr(), spG.plane, spG.cols_pad, yo, E, n, S,
+                          spG.absmax.data_ptr(), partial.data_ptr(), gb.data_ptr(), _lib.stream_ptr(), n_kernels=2,
+                          work=(0.0, 4.0 * E * n))
+        else:
+            # the node gradient's maximum is unknown (it did not come from an instrumented kernel) or Z was not split:
+            # d(value) as an fp32 tensor (its maximum is reduced while it is written); Z from its planes if it has them
+            gv_op, galpha = _rir_bwd(gout, V, alpha, plan, wig, *meta)
+            z_op = ctx.zref if ctx.zref is not None else saved[3 + ctx.nw]
+            scope = [(z_op, ctx.spZ)] + list(zip(Ws, ctx.wsplits))
+            if want_b:
+                gb = colsum(gv_op, ys[0][0], ys[0][1])
+        with split_scope(scope):
+            gZ, _ = _slice_mm(gv_op, None, ys, xs, z_op.shape[1], False, Ws)
+            gWs = _slice_outer(gv_op, z_op, ys, xs)[0] if need_w else [None] * len(Ws)
+        return (gZ, galpha, gb, None, None, None, None, None, None, None, *gWs)
+
+
+def gather_rotate_conv(x, rad, bias0, plan, wig, lmax, mmax, groups, weights):
+    return GatherRotateConvFn.apply(x.contiguous(), rad.contiguous(), bias0, plan, wig, lmax, mmax, groups,
+                                    *[w.contiguous() for w in weights])
+
+
+def conv_rotinv_reduce(Zm, alpha, bias0, plan, wig, lmax, mmax, heads, alpha_bound, groups, weights):
+    return ConvRotInvReduceFn.apply(Zm.contiguous(), alpha.contiguous(), bias0, plan, wig, lmax, mmax, heads, alpha_bound,
+                                    groups, *[w.contiguous() for w in weights])
 
 
 # ----------------------------------------------------------------------------------------------
@@ -1263,11 +1490,19 @@ def _s2_bind_tables(mats, device):
     return slot
 
 
+def _s2_work(mats, R, C, passes):
+    """Separable form (csrc/s2act_sep.cu): per (row, channel) and direction, the latitude transform costs 18 x Kr and the
+    longitude transform 18 x 18 x (2 mmax + 1) multiply-adds; forward = to-grid + from-grid (`passes` = 2), backward
+    recomputes the grid and applies both transposes (4), second order 6.  Bytes: the coefficient tensors in and out."""
+    macs = 18 * mats.Kr + 324 * (2 * mats.mmax + 1)
+    return (2.0 * R * C * macs * passes, 4.0 * R * C * (mats.Kr + 1) * (1 + passes // 2))
+
+
 def _s2_fwd(mats, xp, x_rs, gp, g_rs, op, o_rs, R, C, device):
     if mats.factors is not None:
         slot = _s2_bind_tables(mats, device)
         _lib.call("eqv2_s2sep_fwd", xp, x_rs, gp, g_rs, op, o_rs, R, C, mats.lmax, mats.mmax, int(mats.order == "m"), slot,
-                  _lib.stream_ptr())
+                  _lib.stream_ptr(), work=_s2_work(mats, R, C, 2))
     else:
         _lib.call("eqv2_s2act_fwd", xp, x_rs, gp, g_rs, op, o_rs, mats.T.data_ptr(), mats.F.data_ptr(), R, C, mats.Kr,
                   mats.KP, mats.G, _s2_blocks(R, C), _lib.stream_ptr())
@@ -1277,7 +1512,7 @@ def _s2_bwd(mats, xp, x_rs, gp, g_rs, dop, o_rs, dxp, dx_rs, dgp, dg_rs, R, C, d
     if mats.factors is not None:
         slot = _s2_bind_tables(mats, device)
         _lib.call("eqv2_s2sep_bwd", xp, x_rs, gp, g_rs, dop, o_rs, dxp, dx_rs, dgp, dg_rs, R, C, mats.lmax, mats.mmax,
-                  int(mats.order == "m"), slot, _lib.stream_ptr())
+                  int(mats.order == "m"), slot, _lib.stream_ptr(), work=_s2_work(mats, R, C, 4))
     else:
         _lib.call("eqv2_s2act_bwd", xp, x_rs, gp, g_rs, dop, o_rs, dxp, dx_rs, dgp, dg_rs, mats.T.data_ptr(),
                   mats.F.data_ptr(), R, C, mats.Kr, mats.KP, mats.G, _s2_blocks(R, C), _lib.stream_ptr())
@@ -1293,7 +1528,8 @@ def _s2_bwd2(mats, xp, x_rs, gp, g_rs, dop, o_rs, up, u_rs, wp, w_rs, d2xp, d2x_
         raise _lib.Eqv2Error("S2 activation: second-order terms need the resolution-18 factorised grid")
     slot = _s2_bind_tables(mats, device)
     _lib.call("eqv2_s2sep_bwd2", xp, x_rs, gp, g_rs, dop, o_rs, up, u_rs, wp, w_rs, d2xp, d2x_rs, d2gp, d2g_rs, d2op,
-              d2o_rs, R, C, mats.lmax, mats.mmax, int(mats.order == "m"), slot, _lib.stream_ptr())
+              d2o_rs, R, C, mats.lmax, mats.mmax, int(mats.order == "m"), slot, _lib.stream_ptr(),
+              work=_s2_work(mats, R, C, 6))
 
 
 class S2ActFn(torch.autograd.Function):
@@ -1542,9 +1778,12 @@ class EquivNormFn(torch.autograd.Function):
         out = torch.empty_like(x)
         inv = torch.empty(N, ng, dtype=_F32, device=x.device)
         mean = torch.empty(N, dtype=_F32, device=x.device)
+        slot = _absmax_slot(x.device)       # max |out|: operand bound of the gather/rotate kernel that consumes it
         _lib.call("eqv2_equiv_norm_fwd", x.data_ptr(), w.data_ptr(), b.data_ptr(), out.data_ptr(), inv.data_ptr(),
                   mean.data_ptr(), N, C, lmax, ng, ctypes.cast(gol_c, ctypes.c_void_p),
-                  ctypes.cast(bw_c, ctypes.c_void_p), float(eps), _lib.stream_ptr())
+                  ctypes.cast(bw_c, ctypes.c_void_p), float(eps), _lib.ptr(slot), _lib.stream_ptr(),
+                  work=(0.0, 8.0 * N * K * C))
+        _register_absmax(out, slot)
         ctx.save_for_backward(x, w, b, inv, mean)
         ctx.meta = (norm_type, lmax, float(eps))
         return out
@@ -1566,7 +1805,7 @@ class EquivNormFn(torch.autograd.Function):
         gb = _small_zeros((C,), x.device)
         _lib.call("eqv2_equiv_norm_bwd", x.data_ptr(), w.data_ptr(), go.data_ptr(), inv.data_ptr(), mean.data_ptr(),
                   gx.data_ptr(), gw.data_ptr(), gb.data_ptr(), N, C, lmax, ng, ctypes.cast(gol_c, ctypes.c_void_p),
-                  ctypes.cast(bw_c, ctypes.c_void_p), _lib.stream_ptr())
+                  ctypes.cast(bw_c, ctypes.c_void_p), _lib.stream_ptr(), work=(0.0, 12.0 * N * K * C))
         return gx, gw, gb, None, None, None
 
 
@@ -1580,7 +1819,7 @@ class LnSiluFn(torch.autograd.Function):
         rows, width = x.shape
         y = torch.empty_like(x)
         _lib.call("eqv2_ln_silu_fwd", x.data_ptr(), w.data_ptr(), b.data_ptr(), y.data_ptr(), rows, width, float(eps),
-                  _lib.stream_ptr())
+                  _lib.stream_ptr(), work=(0.0, 8.0 * rows * width))
         ctx.save_for_backward(x, w, b)
         ctx.eps = float(eps)
         return y
@@ -1599,7 +1838,7 @@ class LnSiluFn(torch.autograd.Function):
         gw = _small_zeros(w.shape, w.device)
         gb = _small_zeros(b.shape, b.device)
         _lib.call("eqv2_ln_silu_bwd", x.data_ptr(), w.data_ptr(), b.data_ptr(), gy.data_ptr(), gx.data_ptr(),
-                  gw.data_ptr(), gb.data_ptr(), rows, width, eps, _lib.stream_ptr())
+                  gw.data_ptr(), gb.data_ptr(), rows, width, eps, _lib.stream_ptr(), work=(0.0, 12.0 * rows * width))
         return gx, gw, gb, None
 
 
@@ -1613,7 +1852,7 @@ class RbfFn(torch.autograd.Function):
         R = offset.shape[0]
         out = torch.empty(d.shape[0], R, dtype=_F32, device=d.device)
         _lib.call("eqv2_rbf_fwd", d.data_ptr(), out.data_ptr(), d.shape[0], R, offset.data_ptr(), float(coeff),
-                  _lib.stream_ptr())
+                  _lib.stream_ptr(), work=(0.0, 4.0 * d.shape[0] * (R + 1)))
         ctx.save_for_backward(d, offset)
         ctx.coeff = float(coeff)
         return out

@@ -82,9 +82,15 @@ typedef struct {
   int M, N, K;
   int transA, transB;
   int accumulate;
+  float* c_absmax;   /* may be NULL.  Else (split_k == 1 only): 64 zero-initialised floats whose maximum becomes max |C| of
+                        everything the launch stores -- the operand bound of whichever kernel consumes C next */
 } eqv2_gemm16_desc;
 int eqv2_split_f16(const eqv2_split_desc* descs, int n, void* stream);
 int eqv2_gemm_f16(const eqv2_gemm16_desc* descs, int ngroups, int split_k, void* stream);
+/* passes = 3: the fp32-class product above; passes = 1: hi planes only -- ONE fp16 tensor-core pass, ~3x the rate,
+ * relative error ~5e-4 per product (the reduced-precision "bf16/TF32 GEMM mode" of BASELINE configs[3]; tolerance stated
+ * in tests/test_model_parity.py).  The lo planes are not read. */
+int eqv2_gemm_f16_ex(const eqv2_gemm16_desc* descs, int ngroups, int split_k, int passes, void* stream);
 
 /* ---- Wigner-D rotation (so3.py:343-387,499-545; transformer_block.py:250-275,321-331) ---- */
 int eqv2_wigner_from_rot(const float* rot /*[E,3,3]*/, const float* Jd /*packed blocks*/,
@@ -119,6 +125,35 @@ int eqv2_rotinv_reduce_bwd(const float* dout /*[N,K,Cv]*/, const float* val, con
                            const float* wig, const long long* dst, float* dval, float* dalpha /*or NULL*/,
                            const int* pos_of_full, long long E, int Cv, int rows_used, long long val_estride,
                            int heads, int lmax, int mmax, float scale, float* absmax /*or NULL*/, void* stream);
+
+/* Producer-side operand planes (f16x3 engine).  The three edge-parallel rotate kernels can write their result directly as
+ * the scaled fp16 hi/lo planes the GEMM consumes ([2][E][ld] fp16, plane 1 `plane` elements after plane 0) instead of an
+ * fp32 tensor that a separate eqv2_split_f16 pass would re-read: the scale comes from a BOUND on the result computed on
+ * the device from the maxima of the kernel's own inputs (64-float slots as written by the `absmax` outputs of the kernels
+ * above / `c_absmax` of eqv2_gemm_f16), and the bound is stored to bound_out[0] -- the slot the consuming GEMM is handed
+ * as a_absmax / b_absmax (the other 63 floats must be zero).  A bound that overshoots the true maximum by up to ~2^8 keeps
+ * the product fp32-class (csrc/common.cuh).  Same argument meaning as the fp32 entry points otherwise.
+ *   gather_rotate_fwd_planes : bound = max|x| max|rad| sqrt(2 lmax + 1)                (transformer_block.py:250-275)
+ *   gather_rotate_drad_planes: bound = 2 max|x| max|dA| sqrt(2 lmax + 1)
+ *   rotinv_reduce_bwd_planes : bound = max|dout| alpha_bound |scale| sqrt((2 lmax+1) max(1, (2 lmax+1)/(2 mmax+1)));
+ *                              alpha_bound >= max |alpha| is the caller's (softmax output: 1, with dropout p: 1/(1-p)) */
+/* out[c] = sum_r T[r, col_off + c] of a matrix T held only as operand planes (bias gradients); `bound` = the planes'
+ * bound slot; partial: S * C floats of workspace; deterministic (fixed summation order). */
+int eqv2_planes_colsum(const void* planes, long long plane, long long ld, long long col_off, long long rows, int C, int S,
+                       const float* bound, float* partial, float* out, void* stream);
+int eqv2_gather_rotate_fwd_planes(const float* x, const long long* src, const long long* dst, const float* wig,
+                                  const float* rad, void* planes, long long plane, long long ld, const float* bound_x,
+                                  const float* bound_rad, float* bound_out, long long E, int C, int lmax, int mmax,
+                                  int Kr, int nrad, void* stream);
+int eqv2_gather_rotate_drad_planes(const float* x, const long long* src, const long long* dst, const float* wig,
+                                   const float* dA, void* planes, long long plane, long long ld, const float* bound_x,
+                                   const float* bound_dA, float* bound_out, long long E, int C, int lmax, int mmax,
+                                   int Kr, int nrad, void* stream);
+int eqv2_rotinv_reduce_bwd_planes(const float* dout, const float* val, const float* alpha, const float* wig,
+                                  const long long* dst, void* planes, long long plane, long long ld,
+                                  const float* bound_dout, float alpha_bound, float* bound_out, float* dalpha,
+                                  long long E, int Cv, int rows_used, long long val_estride, int heads, int lmax,
+                                  int mmax, float scale, void* stream);
 
 /* ---- separable S2 activation (activation.py:153-192, so3.py:552-646) --------------------- */
 int eqv2_s2act_padded_rows(int Kr);
@@ -163,7 +198,7 @@ int eqv2_attn_alpha_bwd(const float* Y, long long y_rs, const float* ln_w, const
 int eqv2_equiv_norm_fwd(const float* x /*[N,K,C]*/, const float* w /*[lmax+1,C]*/, const float* b /*[C]*/,
                         float* out, float* inv_out /*[N,ngroups]*/, float* mean_out /*[N]*/, long long N, int C,
                         int lmax, int ngroups, const int* group_of_l /*host*/, const float* bw_l /*host*/,
-                        float eps, void* stream);
+                        float eps, float* absmax /*may be NULL; else 64 zeroed floats receiving max |out|*/, void* stream);
 int eqv2_equiv_norm_bwd(const float* x, const float* w, const float* go, const float* inv_in,
                         const float* mean_in, float* dx, float* dw /*zeroed*/, float* db /*zeroed*/,
                         long long N, int C, int lmax, int ngroups, const int* group_of_l /*host*/,

@@ -253,6 +253,9 @@ def test_cuda_path_matches_reference_at_baseline_shape(case, mode):
         assert e_err < OUT_TOL and f_err < f_tol, (e_err, f_err, f_tol)
         if mode == "f16x3":      # the default engine must really have been the one running the contractions
             assert prof.get("eqv2_gemm_f16", {}).get("calls", 0) >= 6, sorted(prof)
+            if kind in ("oc20", "qm9"):     # ... fed by the producer kernels that write operand planes (no split pass)
+                assert prof.get("eqv2_gather_rotate_fwd_planes", {}).get("calls", 0) >= 1, sorted(prof)
+                assert prof.get("eqv2_rotinv_reduce_bwd_planes", {}).get("calls", 0) >= 1, sorted(prof)
         worst = _check_grads(model, ref)
         print(f"PARITY {case} [{mode}]: energy {e_err:.2e} forces {f_err:.2e} (bound {f_tol:.1e}); worst gradient at "
               f"{worst:.2f} of its bound; gemm_f16 launches {prof.get('eqv2_gemm_f16', {}).get('calls', 0)}")
