@@ -149,9 +149,15 @@ class SO2EquivariantGraphAttention(nn.Module):
                                                  self.attn_alpha_channels, self.hidden_channels)
         alpha_bound = 1.0
         if self.alpha_dropout is not None:
-            alpha = self.alpha_dropout(alpha)
             if self.training:
+                # The reference draws this mask on the OUTPUT LAYOUT OF ITS einsum('bik, ik -> bi') (transformer_block.py:
+                # 314-318): [E, heads] with strides (1, E), i.e. head-major memory -- and torch's dropout assigns random
+                # numbers in memory order.  Same layout here => same mask for the same seed (tests/test_drop_semantics.py).
+                a = alpha.t().contiguous().t().reshape(alpha.shape[0], 1, self.num_heads, 1)
+                alpha = self.alpha_dropout(a).reshape(alpha.shape[0], self.num_heads)
                 alpha_bound = 1.0 / (1.0 - self.alpha_dropout.p)              # nn.Dropout rescales the kept weights
+            else:
+                alpha = self.alpha_dropout(alpha)
         if not second_order and ops.gemm_mode() in ("f16x3", "f16"):
             groups, weights = self.so2_conv_2.groups_and_weights()
             out = ops.conv_rotinv_reduce(Zm, alpha, self.so2_conv_2.fc_m0.bias, plan, wig, lmax, mmax, self.num_heads,

@@ -132,7 +132,21 @@ __device__ __forceinline__ void eqv2_plane_store(const Eqv2PlaneArgs& P, long lo
   hp[idx] = h;
   hp[idx + P.plane] = __float2half_rn(x - __half2float(h));
 }
+// Same, for a FULL warp whose lanes hold consecutive columns (idx = base + lane, base even): lane pairs exchange their
+// halves so that every lane issues ONE 32-bit store -- even lanes the hi pair, odd lanes the lo pair -- instead of two
+// 16-bit stores (the producer kernels issue one store per coefficient row and thread; 16-bit stores doubled that).
+__device__ __forceinline__ void eqv2_plane_store_warp(const Eqv2PlaneArgs& P, long long idx, float v, float s) {
+  const float x = v * s;
+  const __half h = __float2half_rn(x);
+  const __half l = __float2half_rn(x - __half2float(h));
+  const unsigned mine = (unsigned)__half_as_ushort(h) | ((unsigned)__half_as_ushort(l) << 16);
+  const unsigned other = __shfl_xor_sync(0xffffffffu, mine, 1);
+  __half* hp = reinterpret_cast<__half*>(P.hi);
+  if ((threadIdx.x & 1) == 0) *reinterpret_cast<unsigned*>(hp + idx) = (mine & 0xffffu) | (other << 16);
+  else *reinterpret_cast<unsigned*>(hp + idx - 1 + P.plane) = (other >> 16) | (mine & 0xffff0000u);
+}
 #else   // the CPU emulator (tests/emu) builds the fp32 instances only
+inline void eqv2_plane_store_warp(const Eqv2PlaneArgs&, long long, float, float) {}
 inline float eqv2_plane_scale(const Eqv2PlaneArgs&, bool) { return 1.f; }
 inline void eqv2_plane_store(const Eqv2PlaneArgs&, long long, float, float) {}
 #endif

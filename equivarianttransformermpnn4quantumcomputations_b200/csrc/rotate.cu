@@ -174,7 +174,7 @@ gather_rotate_fwd_kernel(const float* __restrict__ x, const long long* __restric
         constexpr int m = decltype(mc)::value - mm;
         constexpr int p = mpos<L, M>(l, m), sl = rslot<L, M>(l, m < 0 ? -m : m);
         const float acc = row_dot<l>(sw, l + m, xc + l * l) * rv[sl];
-        if constexpr (PL) eqv2_plane_store(PA, e * PA.ld + (long long)p * C2 + ch, acc, pscale);
+        if constexpr (PL) eqv2_plane_store_warp(PA, e * PA.ld + (long long)p * C2 + ch, acc, pscale);
         else op[(long long)p * C2] = acc;
         amax = fmaxf(amax, fabsf(acc));
       });
@@ -222,7 +222,7 @@ gather_rotate_drad_kernel(const float* __restrict__ x, const long long* __restri
         constexpr int pp = mpos<L, M>(l, m), pm = mpos<L, M>(l, -m), sl = rslot<L, M>(l, m);
         float d = gv[pp] * row_dot<l>(sw, l + m, xc + l * l);
         if constexpr (m > 0) d = fmaf(gv[pm], row_dot<l>(sw, l - m, xc + l * l), d);
-        if constexpr (PL) eqv2_plane_store(PA, e * PA.ld + (long long)sl * C2 + ch, d, pscale);
+        if constexpr (PL) eqv2_plane_store_warp(PA, e * PA.ld + (long long)sl * C2 + ch, d, pscale);
         else drp[(long long)sl * C2] = d;
         amax = fmaxf(amax, fabsf(d));
       });
@@ -440,7 +440,7 @@ rotinv_reduce_bwd_kernel(const float* __restrict__ dout, const float* __restrict
         if (p < rows_used) {
           const float t = row_dot<l>(sw, l + m, g + l * l);
           if (alpha) da = fmaf(t, vv[p], da);
-          if constexpr (PL) eqv2_plane_store(PA, e * PA.ld + (long long)p * Cv + c, t * a, pscale);
+          if constexpr (PL) eqv2_plane_store_warp(PA, e * PA.ld + (long long)p * Cv + c, t * a, pscale);
           else dvp[(long long)p * Cv] = t * a;
           amax = fmaxf(amax, fabsf(t * a));
         }
@@ -585,6 +585,7 @@ extern "C" int eqv2_gather_rotate_fwd_planes(const float* x, const long long* sr
   if (E == 0) return 0;
   EQV2_REQUIRE(C > 0 && Kr > 0 && rad != nullptr && bound_rad != nullptr, "gather_rotate_fwd_planes: bad arguments");
   if (check_planes("gather_rotate_fwd_planes", planes, plane, ld, (long long)Kr * 2 * C, bound_x, bound_out)) return 1;
+  EQV2_REQUIRE((2 * C) % 32 == 0, "gather_rotate_fwd_planes: 2 C must be a multiple of 32 (paired 32-bit plane stores)");
   const Eqv2PlaneArgs PA{planes, plane, ld, bound_x, bound_rad, 1.01f * sqrtf((float)(2 * lmax + 1)), bound_out};
   const int threads = min(256, round32(2 * C));
 #define X(L_, M_)                                                                                              \
@@ -605,6 +606,7 @@ extern "C" int eqv2_gather_rotate_drad_planes(const float* x, const long long* s
   if (E == 0) return 0;
   EQV2_REQUIRE(C > 0 && Kr > 0 && bound_dA != nullptr, "gather_rotate_drad_planes: bad arguments");
   if (check_planes("gather_rotate_drad_planes", planes, plane, ld, nrad, bound_x, bound_out)) return 1;
+  EQV2_REQUIRE((2 * C) % 32 == 0, "gather_rotate_drad_planes: 2 C must be a multiple of 32 (paired 32-bit plane stores)");
   const Eqv2PlaneArgs PA{planes, plane, ld, bound_x, bound_dA, 2.02f * sqrtf((float)(2 * lmax + 1)), bound_out};
   const int threads = min(256, round32(2 * C));
 #define X(L_, M_)                                                                                              \
@@ -628,6 +630,7 @@ extern "C" int eqv2_rotinv_reduce_bwd_planes(const float* dout, const float* val
   EQV2_REQUIRE(alpha == nullptr || (heads > 0 && Cv % heads == 0), "rotinv_reduce_bwd_planes: heads must divide Cv");
   EQV2_REQUIRE(alpha_bound > 0.f, "rotinv_reduce_bwd_planes: alpha_bound must be positive");
   if (check_planes("rotinv_reduce_bwd_planes", planes, plane, ld, (long long)rows_used * Cv, bound_dout, bound_out)) return 1;
+  EQV2_REQUIRE(Cv % 32 == 0 && heads <= Cv, "rotinv_reduce_bwd_planes: Cv must be a multiple of 32 (paired 32-bit plane stores)");
   const float resc = (lmax > mmax) ? (float)(2 * lmax + 1) / (float)(2 * mmax + 1) : 1.0f;
   const Eqv2PlaneArgs PA{planes, plane, ld, bound_dout, nullptr,
                          1.01f * alpha_bound * fabsf(scale) * sqrtf((float)(2 * lmax + 1) * resc), bound_out};

@@ -449,6 +449,12 @@ def colsum(X, off, n):
 # ----------------------------------------------------------------------------------------------
 # GEMM engine
 # ----------------------------------------------------------------------------------------------
+import os as _os
+
+# A/B switches for measurements (bench.py --disable ...): "planes" = producer kernels write operand planes,
+# "c_absmax" = the GEMM epilogue reduces max |C|.  Both on by default; EQV2_DISABLE=planes,c_absmax turns them off.
+_FEATURES = {k: k not in _os.environ.get("EQV2_DISABLE", "").split(",") for k in ("planes", "c_absmax")}
+
 DEFAULT_GEMM_MODE = "f16x3"
 _GEMM_MODE = {"mode": DEFAULT_GEMM_MODE}
 
@@ -797,7 +803,7 @@ def _run_gemm_f16(descs, split_k, flops, nbytes, out=None):
         a.c_rpb, a.c_bs = d.c_rpb, d.c_bs
         a.M, a.N, a.K, a.transA, a.transB, a.accumulate = d.M, d.N, d.K, d.transA, d.transB, d.accumulate
     slot = None
-    if out is not None and split_k == 1:
+    if out is not None and split_k == 1 and _FEATURES["c_absmax"]:
         # the epilogue reduces max |C| while storing: whichever kernel consumes `out` next (a producer that writes operand
         # planes, or the operand split) finds it in the registry instead of re-reading the tensor
         slot = _zeroed_slot(out.device)
@@ -1280,14 +1286,17 @@ class RotInvReduceBwdFn(torch.autograd.Function):
 # maxima of their inputs (csrc/common.cuh).  Only for steps that are differentiated once (configs 1-2): the operand
 # then never exists as an fp32 tensor autograd could differentiate again.
 def _planes_for(rows, cols, device):
-    """(PlaneRef, SplitF16) of a [rows, cols] operand a producer kernel is about to write (cols % 64 == 0: no padding)."""
+    """(PlaneRef, SplitF16) of a [rows, cols] operand a producer kernel is about to write.  cols % 8 == 0 (16-byte rows);
+    the padding columns up to the next multiple of 64 stay unwritten -- the GEMM's tensor maps are bounded by the true
+    extents, reads beyond them are zero-filled by the TMA unit."""
     ref = PlaneRef(rows, cols, device)
     return ref, SplitF16(OperandSrc(ref, rows, cols))
 
 
 def fused_planes_available(x, rad, cols):
-    """Can gather_rotate write conv1's A operand as planes?  f16 engine, no padding columns, both input maxima known."""
-    return (_GEMM_MODE["mode"] in ("f16x3", "f16") and rad is not None and cols % 64 == 0 and x.is_cuda
+    """Can gather_rotate write conv1's A operand as planes?  f16 engine, whole warps of channels, both input maxima known."""
+    return (_FEATURES["planes"] and _GEMM_MODE["mode"] in ("f16x3", "f16") and rad is not None and cols % 8 == 0
+            and (2 * x.shape[2]) % 32 == 0 and x.is_cuda
             and hasattr(_lib.lib(), "eqv2_gather_rotate_fwd_planes")
             and _known_absmax(x) is not None and _known_absmax(rad) is not None)
 
@@ -1356,7 +1365,8 @@ class ConvRotInvReduceFn(torch.autograd.Function):
         Cv = width // lay.Kr
         meta = (lmax, mmax, lay.Kr, heads, 1.0, Cv)
         out = _rir_fwd(V, alpha, plan, wig, *meta)
-        planes_ok = splits[0] is not None and width % 64 == 0 and hasattr(_lib.lib(), "eqv2_rotinv_reduce_bwd_planes")
+        planes_ok = (_FEATURES["planes"] and splits[0] is not None and width % 8 == 0 and Cv % 32 == 0 and heads <= Cv
+                     and hasattr(_lib.lib(), "eqv2_rotinv_reduce_bwd_planes"))
         if planes_ok:           # Z itself is not needed again: its planes serve the weight gradient
             ctx.save_for_backward(V, alpha, wig, *Ws)
             ctx.zref = PlaneRef(Zm.shape[0], Zm.shape[1], Zm.device)
