@@ -103,6 +103,8 @@ def parse():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-graph", action="store_true", help="enqueue every step from Python instead of replaying a CUDA graph")
     ap.add_argument("--no-dropout", action="store_true", help="alpha_drop = drop_path_rate = 0")
+    ap.add_argument("--disable", default="", help="(A/B measurements) comma list: planes (producer-written operand "
+                    "planes), c_absmax (max |C| in the GEMM epilogue)")
     ap.add_argument("--gemm-mode", default=None, choices=["f16x3", "f16", "tf32x3", "tf32", "fp32"],
                     help="GEMM engine (default: the package default, f16x3 = fp32-class accuracy)")
     return ap.parse_args()
@@ -340,6 +342,8 @@ def run_b200(args):
     ops = importlib.import_module(PKG + ".ops")
     if args.gemm_mode:
         ops.set_gemm_mode(args.gemm_mode)
+    for f in filter(None, args.disable.split(",")):
+        ops._FEATURES[f] = False
     engine_note = {
         "f16x3": ("tcgen05 kind::f16 on operands pre-split into scaled fp16 hi/lo planes (3 passes, TMA, persistent CTAs, "
                   "fp32 register promotion: fp32-class accuracy); short reductions and degree slabs on the FFMA engine",

@@ -172,4 +172,8 @@ def test_reference_matpes_v1_model_file_runs_on_dropin(reference_on_dropin):
         with fixed_rand_like(fx["rand_vec"] + 0.5):
             out = model(dict(data, pos=data["pos"].clone()))
         assert rel_err(out["energy"], fx[keys[0]]) < 1e-5
-        assert rel_err(out[keys[1]], fx[keys[1]]) < 2e-5
+        # autograd forces / stress: the reference's own fp32 numbers are ~1.2e-5 / 1.6e-5 away from its float64
+        # evaluation (fixture fields *_f64) -- compare with the float64 values, bound = max(1e-5, 2 x that deviation)
+        f64 = fx[keys[1] + "_f64"]
+        assert rel_err(out[keys[1]], f64) < max(1e-5, 2 * rel_err(fx[keys[1]], f64))
+        assert rel_err(out[keys[1]], fx[keys[1]]) < 5e-5
