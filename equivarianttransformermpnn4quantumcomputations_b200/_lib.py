@@ -53,6 +53,7 @@ _PROTOS = {
     "eqv2_gemm_f16": [P, I, I, P],
     "eqv2_gemm_f16_ex": [P, I, I, I, P],
     "eqv2_wigner_from_rot": [P, P, P, L, I, P],
+    "eqv2_edge_frames": [P, P, P, L, I, P, P],
     "eqv2_gather_rotate_fwd": [P, P, P, P, P, P, P, P, L, I, I, I, I, I, P, P],
     "eqv2_gather_rotate_dx": [P, P, P, P, P, P, P, P, L, I, I, I, I, I, P],
     "eqv2_gather_rotate_drad": [P, P, P, P, P, P, L, I, I, I, I, I, P, P],

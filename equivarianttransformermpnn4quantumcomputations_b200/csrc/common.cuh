@@ -132,21 +132,48 @@ __device__ __forceinline__ void eqv2_plane_store(const Eqv2PlaneArgs& P, long lo
   hp[idx] = h;
   hp[idx + P.plane] = __float2half_rn(x - __half2float(h));
 }
-// Same, for a FULL warp whose lanes hold consecutive columns (idx = base + lane, base even): lane pairs exchange their
-// halves so that every lane issues ONE 32-bit store -- even lanes the hi pair, odd lanes the lo pair -- instead of two
-// 16-bit stores (the producer kernels issue one store per coefficient row and thread; 16-bit stores doubled that).
-__device__ __forceinline__ void eqv2_plane_store_warp(const Eqv2PlaneArgs& P, long long idx, float v, float s) {
+// Staged variant used by the producer kernels (measured: per-thread 16-bit / paired 32-bit global stores, one per coefficient
+// row and thread, made the plane-writing kernels 40-75 % slower than their fp32 twins -- twice the store requests at half
+// the width).  Every thread instead deposits its values in a shared-memory image of the CTA's output tile,
+// hi[rows][T] | lo[rows][T] (T = threads = columns of the tile), and ONE thread hands the tile to the bulk-copy engine
+// (cp.async.bulk shared -> global, SASS UBLKCP): when the tile's rows are adjacent in the plane it is one contiguous chunk
+// per plane (two instructions per CTA), else one chunk per row.  Sizes / addresses are multiples of 16 bytes (T % 8 == 0,
+// ld % 8 == 0, plane % 8 == 0).
+__device__ __forceinline__ void eqv2_plane_stage(__half* st, int rows, int T, int row, int t, float v, float s) {
   const float x = v * s;
   const __half h = __float2half_rn(x);
-  const __half l = __float2half_rn(x - __half2float(h));
-  const unsigned mine = (unsigned)__half_as_ushort(h) | ((unsigned)__half_as_ushort(l) << 16);
-  const unsigned other = __shfl_xor_sync(0xffffffffu, mine, 1);
-  __half* hp = reinterpret_cast<__half*>(P.hi);
-  if ((threadIdx.x & 1) == 0) *reinterpret_cast<unsigned*>(hp + idx) = (mine & 0xffffu) | (other << 16);
-  else *reinterpret_cast<unsigned*>(hp + idx - 1 + P.plane) = (other >> 16) | (mine & 0xffff0000u);
+  st[row * T + t] = h;
+  st[(rows + row) * T + t] = __float2half_rn(x - __half2float(h));
+}
+__device__ __forceinline__ void eqv2_bulk_s2g(void* dst, const void* src_smem, unsigned bytes) {
+  asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(dst),
+               "r"((unsigned)__cvta_generic_to_shared(src_smem)), "r"(bytes)
+               : "memory");
+}
+// every thread of the CTA must call; idx0 = element offset of tile row 0, row_stride = elements between tile rows
+__device__ __forceinline__ void eqv2_plane_flush(const Eqv2PlaneArgs& P, const __half* st, int rows, int T, long long idx0,
+                                                 long long row_stride) {
+  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");     // generic-proxy writes -> visible to the copy engine
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    __half* hp = reinterpret_cast<__half*>(P.hi);
+    if (row_stride == (long long)T) {
+      eqv2_bulk_s2g(hp + idx0, st, (unsigned)(rows * T * 2));
+      eqv2_bulk_s2g(hp + idx0 + P.plane, st + rows * T, (unsigned)(rows * T * 2));
+    } else {
+      for (int r = 0; r < rows; ++r) {
+        eqv2_bulk_s2g(hp + idx0 + r * row_stride, st + r * T, (unsigned)(T * 2));
+        eqv2_bulk_s2g(hp + idx0 + r * row_stride + P.plane, st + (rows + r) * T, (unsigned)(T * 2));
+      }
+    }
+    asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+    asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");   // shared memory must outlive the reads
+  }
 }
 #else   // the CPU emulator (tests/emu) builds the fp32 instances only
-inline void eqv2_plane_store_warp(const Eqv2PlaneArgs&, long long, float, float) {}
+struct __half;
+inline void eqv2_plane_stage(__half*, int, int, int, int, float, float) {}
+inline void eqv2_plane_flush(const Eqv2PlaneArgs&, const __half*, int, int, long long, long long) {}
 inline float eqv2_plane_scale(const Eqv2PlaneArgs&, bool) { return 1.f; }
 inline void eqv2_plane_store(const Eqv2PlaneArgs&, long long, float, float) {}
 #endif

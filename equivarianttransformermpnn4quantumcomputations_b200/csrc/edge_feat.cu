@@ -322,3 +322,78 @@ extern "C" int eqv2_edge_sh(const float* vec, float* out, long long E, int lmax,
   EQV2_CHECK_LAUNCH("eqv2_edge_sh");
   return 0;
 }
+
+// ---------------------------------------------------------------------------------------------
+// Edge frames (edge_rot_mat.py:13-80 with a caller-supplied helper draw; equiformerv2_MatPESv2.py:41-66 deterministic).
+// One thread per edge; fp32 in the reference's operation order (no FMA contraction).  Rows of the result: z, x_edge, -y.
+//   mode 0: helper = draw[e] (already `rand - 0.5`), normalised; swapped for one of its two 90-degree alternates when
+//           (anti)parallel to the edge (edge_rot_mat.py:32-55).  stats[0] = ~bits(min |vec|), stats[1] = bits(max |<helper, x>|)
+//           (atomicMax on unsigned; the host checks the reference's two conditions from them in ONE read-back).
+//   mode 1: helper = cardinal axis of the smallest |component| of the direction; every norm clamped at 1e-8.
+namespace {
+__device__ __forceinline__ float ef_norm3(float a, float b, float c) {
+  return sqrtf(__fadd_rn(__fadd_rn(__fmul_rn(a, a), __fmul_rn(b, b)), __fmul_rn(c, c)));
+}
+__device__ __forceinline__ float ef_dot3(float a0, float a1, float a2, float b0, float b1, float b2) {
+  return __fadd_rn(__fadd_rn(__fmul_rn(a0, b0), __fmul_rn(a1, b1)), __fmul_rn(a2, b2));
+}
+__global__ void edge_frames_kernel(const float* __restrict__ vec, const float* __restrict__ draw, float* __restrict__ out,
+                                   long long E, int mode, unsigned* __restrict__ stats) {
+  const long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= E) return;
+  const float v0 = vec[3 * e], v1 = vec[3 * e + 1], v2 = vec[3 * e + 2];
+  float len = ef_norm3(v0, v1, v2);
+  float h0, h1, h2;
+  if (mode == 0) {
+    atomicMax(stats, ~__float_as_uint(len));
+  } else {
+    len = fmaxf(len, 1e-8f);
+  }
+  const float x0 = v0 / len, x1 = v1 / len, x2 = v2 / len;
+  if (mode == 0) {
+    const float d0 = draw[3 * e], d1 = draw[3 * e + 1], d2 = draw[3 * e + 2];
+    const float dn = ef_norm3(d0, d1, d2);
+    h0 = d0 / dn; h1 = d1 / dn; h2 = d2 / dn;
+    const float b0 = -h1, b1 = h0, b2 = h2;            // alternates (edge_rot_mat.py:36-41)
+    const float c0 = h0, c1 = -h2, c2 = h1;
+    const float dot_b = fabsf(ef_dot3(b0, b1, b2, x0, x1, x2)), dot_c = fabsf(ef_dot3(c0, c1, c2, x0, x1, x2));
+    if (fabsf(ef_dot3(h0, h1, h2, x0, x1, x2)) > dot_b) { h0 = b0; h1 = b1; h2 = b2; }
+    if (fabsf(ef_dot3(h0, h1, h2, x0, x1, x2)) > dot_c) { h0 = c0; h1 = c1; h2 = c2; }
+    atomicMax(stats + 1, __float_as_uint(fabsf(ef_dot3(h0, h1, h2, x0, x1, x2))));
+  } else {
+    const float a0 = fabsf(x0), a1 = fabsf(x1), a2 = fabsf(x2);
+    const int best = (a0 <= a1 && a0 <= a2) ? 0 : ((a1 <= a2) ? 1 : 2);      // torch.argmin: first minimum
+    h0 = best == 0 ? 1.f : 0.f; h1 = best == 1 ? 1.f : 0.f; h2 = best == 2 ? 1.f : 0.f;
+  }
+  // z = x cross helper
+  float z0 = __fadd_rn(__fmul_rn(x1, h2), -__fmul_rn(x2, h1));
+  float z1 = __fadd_rn(__fmul_rn(x2, h0), -__fmul_rn(x0, h2));
+  float z2 = __fadd_rn(__fmul_rn(x0, h1), -__fmul_rn(x1, h0));
+  float zn = ef_norm3(z0, z1, z2);
+  if (mode == 1) zn = fmaxf(zn, 1e-8f);
+  z0 /= zn; z1 /= zn; z2 /= zn;
+  if (mode == 0) {                                     // the reference normalises twice (edge_rot_mat.py:60-63)
+    zn = ef_norm3(z0, z1, z2);
+    z0 /= zn; z1 /= zn; z2 /= zn;
+  }
+  float y0 = __fadd_rn(__fmul_rn(x1, z2), -__fmul_rn(x2, z1));
+  float y1 = __fadd_rn(__fmul_rn(x2, z0), -__fmul_rn(x0, z2));
+  float y2 = __fadd_rn(__fmul_rn(x0, z1), -__fmul_rn(x1, z0));
+  float yn = ef_norm3(y0, y1, y2);
+  if (mode == 1) yn = fmaxf(yn, 1e-8f);
+  y0 /= yn; y1 /= yn; y2 /= yn;
+  float* o = out + 9 * e;
+  o[0] = z0; o[1] = z1; o[2] = z2;
+  o[3] = x0; o[4] = x1; o[5] = x2;
+  o[6] = -y0; o[7] = -y1; o[8] = -y2;
+}
+}  // namespace
+
+extern "C" int eqv2_edge_frames(const float* vec, const float* draw, float* out, long long E, int mode, unsigned* stats,
+                                void* stream) {
+  if (E == 0) return 0;
+  EQV2_REQUIRE(mode == 1 || (draw != nullptr && stats != nullptr), "edge_frames: mode 0 needs the helper draw and stats");
+  EQV2_LAUNCH(edge_frames_kernel, dim3((unsigned)((E + 127) / 128)), dim3(128), 0, stream, vec, draw, out, E, mode, stats);
+  EQV2_CHECK_LAUNCH("eqv2_edge_frames");
+  return 0;
+}

@@ -147,6 +147,7 @@ gather_rotate_fwd_kernel(const float* __restrict__ x, const long long* __restric
   const long long e = blockIdx.x;
   float pscale = 1.f;
   if constexpr (PL) pscale = eqv2_plane_scale(PA, blockIdx.x == 0 && blockIdx.y == 0 && threadIdx.x == 0);
+  EQV2_DYN_SMEM(__half, stage);          // PL: hi[Kr][T] | lo[Kr][T] image of this CTA's output tile
   const long long ns_ = src[e], nd_ = dst[e];
   const int C2 = 2 * C;
   float amax = 0.f;
@@ -174,12 +175,13 @@ gather_rotate_fwd_kernel(const float* __restrict__ x, const long long* __restric
         constexpr int m = decltype(mc)::value - mm;
         constexpr int p = mpos<L, M>(l, m), sl = rslot<L, M>(l, m < 0 ? -m : m);
         const float acc = row_dot<l>(sw, l + m, xc + l * l) * rv[sl];
-        if constexpr (PL) eqv2_plane_store_warp(PA, e * PA.ld + (long long)p * C2 + ch, acc, pscale);
+        if constexpr (PL) eqv2_plane_stage(stage, Kr, blockDim.x, p, threadIdx.x, acc, pscale);
         else op[(long long)p * C2] = acc;
         amax = fmaxf(amax, fabsf(acc));
       });
     });
   }
+  if constexpr (PL) eqv2_plane_flush(PA, stage, Kr, blockDim.x, e * PA.ld + (long long)blockIdx.y * blockDim.x, C2);
   if (absmax != nullptr) eqv2_commit_absmax(amax, absmax);
 }
 
@@ -199,6 +201,8 @@ gather_rotate_drad_kernel(const float* __restrict__ x, const long long* __restri
   const long long e = blockIdx.x;
   float pscale = 1.f;
   if constexpr (PL) pscale = eqv2_plane_scale(PA, blockIdx.x == 0 && blockIdx.y == 0 && threadIdx.x == 0);
+  EQV2_DYN_SMEM(__half, stage);          // PL: hi[NS][T] | lo[NS][T]
+  constexpr int NSL = nslots<L, M>();
   const long long ns_ = src[e], nd_ = dst[e];
   const int C2 = 2 * C;
   float amax = 0.f;
@@ -222,12 +226,13 @@ gather_rotate_drad_kernel(const float* __restrict__ x, const long long* __restri
         constexpr int pp = mpos<L, M>(l, m), pm = mpos<L, M>(l, -m), sl = rslot<L, M>(l, m);
         float d = gv[pp] * row_dot<l>(sw, l + m, xc + l * l);
         if constexpr (m > 0) d = fmaf(gv[pm], row_dot<l>(sw, l - m, xc + l * l), d);
-        if constexpr (PL) eqv2_plane_store_warp(PA, e * PA.ld + (long long)sl * C2 + ch, d, pscale);
+        if constexpr (PL) eqv2_plane_stage(stage, NSL, blockDim.x, sl, threadIdx.x, d, pscale);
         else drp[(long long)sl * C2] = d;
         amax = fmaxf(amax, fabsf(d));
       });
     });
   }
+  if constexpr (PL) eqv2_plane_flush(PA, stage, NSL, blockDim.x, e * PA.ld + (long long)blockIdx.y * blockDim.x, C2);
   if (absmax != nullptr) eqv2_commit_absmax(amax, absmax);
 }
 
@@ -401,7 +406,8 @@ rotinv_reduce_bwd_kernel(const float* __restrict__ dout, const float* __restrict
   __shared__ __align__(16) float sw[wpad_off(L + 1)];
   float pscale = 1.f;
   if constexpr (PL) pscale = eqv2_plane_scale(PA, blockIdx.x == 0 && threadIdx.x == 0);
-  EQV2_DYN_SMEM(float, spart);   // [blockDim.x] partial d(alpha)
+  EQV2_DYN_SMEM(float, spart);   // [blockDim.x] partial d(alpha); PL: then hi[rows_used][T] | lo[rows_used][T]
+  __half* stage = reinterpret_cast<__half*>(spart + blockDim.x);
   constexpr int KR = mpos<L, M>(L, -M) + 1;
   const long long e = blockIdx.x;
   const int c = threadIdx.x;
@@ -440,7 +446,7 @@ rotinv_reduce_bwd_kernel(const float* __restrict__ dout, const float* __restrict
         if (p < rows_used) {
           const float t = row_dot<l>(sw, l + m, g + l * l);
           if (alpha) da = fmaf(t, vv[p], da);
-          if constexpr (PL) eqv2_plane_store_warp(PA, e * PA.ld + (long long)p * Cv + c, t * a, pscale);
+          if constexpr (PL) eqv2_plane_stage(stage, rows_used, blockDim.x, p, c, t * a, pscale);
           else dvp[(long long)p * Cv] = t * a;
           amax = fmaxf(amax, fabsf(t * a));
         }
@@ -456,6 +462,7 @@ rotinv_reduce_bwd_kernel(const float* __restrict__ dout, const float* __restrict
       dalpha[e * heads + threadIdx.x] = s;
     }
   }
+  if constexpr (PL) eqv2_plane_flush(PA, stage, rows_used, blockDim.x, e * PA.ld, Cv);
   if (absmax != nullptr) eqv2_commit_absmax(amax, absmax);
 }
 
@@ -570,6 +577,14 @@ extern "C" int eqv2_rotinv_reduce_bwd(const float* dout, const float* val, const
 
 #ifndef EQV2_CPU_EMU
 // ---- producer-side operand planes: the same three kernels writing scaled fp16 hi/lo planes instead of fp32 ----------
+// the staged tile can exceed the 48 KB default of dynamic shared memory (lmax 6 / mmax 6: 49 rows x 256 columns x 4 B)
+static int plane_smem_attr(const void* kfn, size_t smem) {
+  if (smem <= 48 * 1024) return 0;
+  cudaError_t e = cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  EQV2_REQUIRE(e == cudaSuccess, "plane kernels: cannot reserve %zu B of shared memory: %s", smem, cudaGetErrorString(e));
+  return 0;
+}
+
 static int check_planes(const char* who, const void* planes, long long plane, long long ld, long long cols,
                         const float* bound_a, const float* bound_out) {
   EQV2_REQUIRE(planes != nullptr && bound_a != nullptr && bound_out != nullptr, "%s: null plane / bound pointer", who);
@@ -585,13 +600,16 @@ extern "C" int eqv2_gather_rotate_fwd_planes(const float* x, const long long* sr
   if (E == 0) return 0;
   EQV2_REQUIRE(C > 0 && Kr > 0 && rad != nullptr && bound_rad != nullptr, "gather_rotate_fwd_planes: bad arguments");
   if (check_planes("gather_rotate_fwd_planes", planes, plane, ld, (long long)Kr * 2 * C, bound_x, bound_out)) return 1;
-  EQV2_REQUIRE((2 * C) % 32 == 0, "gather_rotate_fwd_planes: 2 C must be a multiple of 32 (paired 32-bit plane stores)");
+  EQV2_REQUIRE((2 * C) % 32 == 0 && (2 * C) % min(256, 2 * C) == 0,
+               "gather_rotate_fwd_planes: 2 C must be a multiple of 32 and of the CTA width (whole staged tiles)");
   const Eqv2PlaneArgs PA{planes, plane, ld, bound_x, bound_rad, 1.01f * sqrtf((float)(2 * lmax + 1)), bound_out};
   const int threads = min(256, round32(2 * C));
 #define X(L_, M_)                                                                                              \
   if (lmax == L_ && mmax == M_) {                                                                              \
     auto kfn = gather_rotate_fwd_kernel<L_, M_, true>;                                                         \
-    EQV2_LAUNCH(kfn, dim3((unsigned)E, (2 * C + threads - 1) / threads), dim3(threads), 0, stream, x, src, dst, wig, rad, (float*)nullptr, C, Kr, nrad, (float*)nullptr, PA); \
+    const size_t smem = (size_t)Kr * threads * 4;                                                              \
+    if (plane_smem_attr((const void*)kfn, smem)) return 1;                                                     \
+    EQV2_LAUNCH(kfn, dim3((unsigned)E, (2 * C + threads - 1) / threads), dim3(threads), smem, stream, x, src, dst, wig, rad, (float*)nullptr, C, Kr, nrad, (float*)nullptr, PA); \
     EQV2_CHECK_LAUNCH("eqv2_gather_rotate_fwd_planes");                                                        \
     return 0;                                                                                                  \
   }
@@ -606,13 +624,16 @@ extern "C" int eqv2_gather_rotate_drad_planes(const float* x, const long long* s
   if (E == 0) return 0;
   EQV2_REQUIRE(C > 0 && Kr > 0 && bound_dA != nullptr, "gather_rotate_drad_planes: bad arguments");
   if (check_planes("gather_rotate_drad_planes", planes, plane, ld, nrad, bound_x, bound_out)) return 1;
-  EQV2_REQUIRE((2 * C) % 32 == 0, "gather_rotate_drad_planes: 2 C must be a multiple of 32 (paired 32-bit plane stores)");
+  EQV2_REQUIRE((2 * C) % 32 == 0 && (2 * C) % min(256, 2 * C) == 0,
+               "gather_rotate_drad_planes: 2 C must be a multiple of 32 and of the CTA width (whole staged tiles)");
   const Eqv2PlaneArgs PA{planes, plane, ld, bound_x, bound_dA, 2.02f * sqrtf((float)(2 * lmax + 1)), bound_out};
   const int threads = min(256, round32(2 * C));
 #define X(L_, M_)                                                                                              \
   if (lmax == L_ && mmax == M_) {                                                                              \
     auto kfn = gather_rotate_drad_kernel<L_, M_, true>;                                                        \
-    EQV2_LAUNCH(kfn, dim3((unsigned)E, (2 * C + threads - 1) / threads), dim3(threads), 0, stream, x, src, dst, wig, dA, (float*)nullptr, C, Kr, nrad, (float*)nullptr, PA); \
+    const size_t smem = (size_t)(nrad / (2 * C)) * threads * 4;                                                \
+    if (plane_smem_attr((const void*)kfn, smem)) return 1;                                                     \
+    EQV2_LAUNCH(kfn, dim3((unsigned)E, (2 * C + threads - 1) / threads), dim3(threads), smem, stream, x, src, dst, wig, dA, (float*)nullptr, C, Kr, nrad, (float*)nullptr, PA); \
     EQV2_CHECK_LAUNCH("eqv2_gather_rotate_drad_planes");                                                       \
     return 0;                                                                                                  \
   }
@@ -630,7 +651,7 @@ extern "C" int eqv2_rotinv_reduce_bwd_planes(const float* dout, const float* val
   EQV2_REQUIRE(alpha == nullptr || (heads > 0 && Cv % heads == 0), "rotinv_reduce_bwd_planes: heads must divide Cv");
   EQV2_REQUIRE(alpha_bound > 0.f, "rotinv_reduce_bwd_planes: alpha_bound must be positive");
   if (check_planes("rotinv_reduce_bwd_planes", planes, plane, ld, (long long)rows_used * Cv, bound_dout, bound_out)) return 1;
-  EQV2_REQUIRE(Cv % 32 == 0 && heads <= Cv, "rotinv_reduce_bwd_planes: Cv must be a multiple of 32 (paired 32-bit plane stores)");
+  EQV2_REQUIRE(Cv % 32 == 0 && heads <= Cv, "rotinv_reduce_bwd_planes: Cv must be a multiple of 32 (whole staged tiles)");
   const float resc = (lmax > mmax) ? (float)(2 * lmax + 1) / (float)(2 * mmax + 1) : 1.0f;
   const Eqv2PlaneArgs PA{planes, plane, ld, bound_dout, nullptr,
                          1.01f * alpha_bound * fabsf(scale) * sqrtf((float)(2 * lmax + 1) * resc), bound_out};
@@ -638,7 +659,9 @@ extern "C" int eqv2_rotinv_reduce_bwd_planes(const float* dout, const float* val
 #define X(L_, M_)                                                                                              \
   if (lmax == L_ && mmax == M_) {                                                                              \
     auto kfn = rotinv_reduce_bwd_kernel<L_, M_, true>;                                                         \
-    EQV2_LAUNCH(kfn, dim3((unsigned)E), dim3(threads), threads * sizeof(float), stream, dout, val, alpha, wig, dst, (float*)nullptr, dalpha, Cv, rows_used, val_estride, heads, scale, (float*)nullptr, PA); \
+    const size_t smem = threads * sizeof(float) + (size_t)rows_used * threads * 4;                             \
+    if (plane_smem_attr((const void*)kfn, smem)) return 1;                                                     \
+    EQV2_LAUNCH(kfn, dim3((unsigned)E), dim3(threads), smem, stream, dout, val, alpha, wig, dst, (float*)nullptr, dalpha, Cv, rows_used, val_estride, heads, scale, (float*)nullptr, PA); \
     EQV2_CHECK_LAUNCH("eqv2_rotinv_reduce_bwd_planes");                                                        \
     return 0;                                                                                                  \
   }

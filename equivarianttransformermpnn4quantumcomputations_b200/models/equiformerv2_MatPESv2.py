@@ -24,16 +24,9 @@ _AVG_DEGREE_MATPES = 12.0
 
 def init_edge_rot_mat(edge_distance_vec):
     """Deterministic edge frames (reference equiformerv2_MatPESv2.py:41-66): the helper vector is the cardinal
-    axis of the smallest |component| of the edge direction.  Detached, like the reference."""
-    ev = edge_distance_vec.detach()
-    dist = torch.sqrt(torch.sum(ev ** 2, dim=1, keepdim=True)).clamp(min=1e-8)
-    nx = ev / dist
-    ref = torch.eye(3, device=ev.device, dtype=ev.dtype)[torch.argmin(torch.abs(nx), dim=1)]
-    nz = torch.cross(nx, ref, dim=1)
-    nz = nz / torch.sqrt(torch.sum(nz ** 2, dim=1, keepdim=True)).clamp(min=1e-8)
-    ny = torch.cross(nx, nz, dim=1)
-    ny = ny / torch.sqrt(torch.sum(ny ** 2, dim=1, keepdim=True)).clamp(min=1e-8)
-    return torch.stack([nz, nx, -ny], dim=2).transpose(1, 2)
+    axis of the smallest |component| of the edge direction.  Detached, like the reference; one kernel
+    (`eqv2_edge_frames` mode 1), no host read-back -- it sits inside the replayed CUDA graph."""
+    return ops.edge_frames(edge_distance_vec, None)
 
 
 class EquiformerV2_MatPES(nn.Module):

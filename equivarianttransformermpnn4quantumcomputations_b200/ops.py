@@ -1075,6 +1075,31 @@ def wigner_from_rot(rot, lmax):
     return wig
 
 
+def edge_frames(edge_vec, draw=None):
+    """Per-edge frames [E,3,3] (rows z, x_edge, -y), detached.  `draw` = the reference's helper draw
+    (`torch.rand_like(vec) - 0.5`, edge_rot_mat.py:28) -> edge_rot_mat.py:13-80, with its two host-side conditions
+    (lines 19-24: short-edge warning, line 58: assert) checked from one read-back; `draw=None` -> the deterministic frames
+    of equiformerv2_MatPESv2.py:41-66 (no read-back: capturable in a CUDA graph)."""
+    _lib.check_device(edge_vec, draw)
+    vec = edge_vec.detach().to(_F32).contiguous()
+    E = vec.shape[0]
+    out = torch.empty(E, 3, 3, dtype=_F32, device=vec.device)
+    if draw is None:
+        _lib.call("eqv2_edge_frames", vec.data_ptr(), None, out.data_ptr(), E, 1, None, _lib.stream_ptr())
+        return out
+    draw = draw.detach().to(_F32).contiguous()
+    stats = torch.zeros(2, dtype=torch.int32, device=vec.device)
+    _lib.call("eqv2_edge_frames", vec.data_ptr(), draw.data_ptr(), out.data_ptr(), E, 0, stats.data_ptr(), _lib.stream_ptr())
+    if E > 0:
+        s0, s1 = stats.tolist()
+        min_len = np.array([~s0 & 0xFFFFFFFF], dtype=np.uint32).view(np.float32)[0]
+        max_dot = np.array([s1 & 0xFFFFFFFF], dtype=np.uint32).view(np.float32)[0]
+        if min_len < 0.0001:
+            print("Error edge_vec_0_distance: {}".format(min_len))
+        assert max_dot < 0.99
+    return out
+
+
 def edge_sh(edge_vec, lmax):
     """Edge spherical harmonics l = 1..lmax in the original frame, detached (equiformerv2_MatPES_GATAV2.py:232-241)."""
     _lib.check_device(edge_vec)
@@ -1296,7 +1321,7 @@ def _planes_for(rows, cols, device):
 def fused_planes_available(x, rad, cols):
     """Can gather_rotate write conv1's A operand as planes?  f16 engine, whole warps of channels, both input maxima known."""
     return (_FEATURES["planes"] and _GEMM_MODE["mode"] in ("f16x3", "f16") and rad is not None and cols % 8 == 0
-            and (2 * x.shape[2]) % 32 == 0 and x.is_cuda
+            and (2 * x.shape[2]) % 32 == 0 and (2 * x.shape[2]) % min(256, 2 * x.shape[2]) == 0 and x.is_cuda
             and hasattr(_lib.lib(), "eqv2_gather_rotate_fwd_planes")
             and _known_absmax(x) is not None and _known_absmax(rad) is not None)
 

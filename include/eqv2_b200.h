@@ -93,6 +93,12 @@ int eqv2_gemm_f16(const eqv2_gemm16_desc* descs, int ngroups, int split_k, void*
 int eqv2_gemm_f16_ex(const eqv2_gemm16_desc* descs, int ngroups, int split_k, int passes, void* stream);
 
 /* ---- Wigner-D rotation (so3.py:343-387,499-545; transformer_block.py:250-275,321-331) ---- */
+/* Edge frames [E,3,3] (rows z, x_edge, -y) from edge vectors.  mode 0: edge_rot_mat.py:13-80 with the helper draw
+ * (`torch.rand_like(vec) - 0.5`, line 28) supplied by the caller so that the RNG stays the reference's; stats[2] (zeroed
+ * unsigned) receive ~bits(min |vec|) and bits(max |<helper, x>|) -- the two conditions the reference checks on the host
+ * (lines 19-24, 58).  mode 1: the deterministic variant of equiformerv2_MatPESv2.py:41-66 (draw / stats may be NULL). */
+int eqv2_edge_frames(const float* vec /*[E,3]*/, const float* draw /*[E,3]*/, float* out /*[E,3,3]*/, long long E, int mode,
+                     unsigned* stats, void* stream);
 int eqv2_wigner_from_rot(const float* rot /*[E,3,3]*/, const float* Jd /*packed blocks*/,
                          float* wig /*[E, sum (2l+1)^2]*/, long long E, int lmax, void* stream);
 
