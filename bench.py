@@ -103,6 +103,9 @@ def parse():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-graph", action="store_true", help="enqueue every step from Python instead of replaying a CUDA graph")
     ap.add_argument("--no-dropout", action="store_true", help="alpha_drop = drop_path_rate = 0")
+    ap.add_argument("--optimizer", default="fused", choices=["fused", "torch"],
+                    help="fused: clip_grad_norm_ + AdamW + EMA as one multi-tensor pass (optim.FusedAdamW, the reference's "
+                         "optimizer-side step); torch: torch.optim.AdamW(fused=True) alone (the round-1 step)")
     ap.add_argument("--disable", default="", help="(A/B measurements) comma list: planes (producer-written operand "
                     "planes), c_absmax (max |C| in the GEMM epilogue)")
     ap.add_argument("--gemm-mode", default=None, choices=["f16x3", "f16", "tf32x3", "tf32", "fp32"],
@@ -201,13 +204,18 @@ def reference_stepper(cfg, kw):
         torch.manual_seed(0)
         model = getattr(mod, cfg["cls"])(**kw)
         model.train()
-        opt = torch.optim.AdamW(model.parameters(), lr=1e-4)
+        opt = torch.optim.AdamW(model.parameters(), lr=1e-4, weight_decay=1e-3)
+        shadow = {n: p.data.clone() for n, p in model.named_parameters() if p.requires_grad}
 
-        def step(data):
+        def step(data):     # the reference's optimizer-side step (train_oc20v2_parallel.py:171-186): clip, AdamW, EMA
             loss = forward_loss(cfg, model, data)
             opt.zero_grad(set_to_none=True)
             loss.backward()
+            torch.nn.utils.clip_grad_norm_(model.parameters(), 100.0)
             opt.step()
+            for n, p in model.named_parameters():
+                if p.requires_grad:
+                    shadow[n] = ((1.0 - 0.999) * p.data + 0.999 * shadow[n]).clone()
             return float(loss)
         return step, "reference", "unmodified reference model files (oracle/_ref copy) + third-party shims, torch CPU"
     if cfg["kind"] != "direct":
@@ -364,7 +372,11 @@ def run_b200(args):
     net = model
     if world > 1 and args.no_graph:
         net = torch.nn.parallel.DistributedDataParallel(model, device_ids=[local], gradient_as_bucket_view=True)
-    opt = torch.optim.AdamW(model.parameters(), lr=1e-4, fused=True)
+    if args.optimizer == "fused":       # reference: clip_grad_norm_ -> AdamW -> EMA.update (train_oc20v2_parallel.py:177-186)
+        optim = importlib.import_module(PKG + ".optim")
+        opt = optim.FusedAdamW(model.parameters(), lr=1e-4, weight_decay=1e-3, max_grad_norm=100.0, ema_decay=0.999)
+    else:
+        opt = torch.optim.AdamW(model.parameters(), lr=1e-4, fused=True)
 
     B = args.structures or cfg["structures"]
     host = make_batch(cfg, B, seed=1000 + rank)
@@ -468,7 +480,10 @@ def run_b200(args):
                                     "launch": ("CUDA graph replay of forward+loss+backward; neighbour list, edge frames, "
                                                "gradient all-reduce (NCCL, N > 1) and AdamW eager" if use_graph
                                                else "eager (every kernel enqueued from Python; DDP when N > 1)"),
-                                    "gemm_engine": engine_note[0]},
+                                    "gemm_engine": engine_note[0],
+                                    "optimizer": ("FusedAdamW: gradient-norm clip (100) + AdamW (wd 1e-3) + EMA (0.999) in one "
+                                                  "multi-tensor pass" if args.optimizer == "fused"
+                                                  else "torch.optim.AdamW(fused=True), no clip, no EMA")},
                 "e2e": {"value": e2e, "unit": UNIT, "ms_per_step": ms_e2e / args.steps, "h2d_bytes_per_step": h2d_bytes,
                         "d2h_bytes_per_step": 4},
                 "gpu_launches": launches, "host_enqueue_ms_per_step": host_ms,

@@ -93,6 +93,9 @@ _PROTOS = {
     "eqv2_so2_block_weight_adj": [P, P, I, I, P],
     "eqv2_embed_rows": [P, P, P, L, I, P],
     "eqv2_seg_colsum": [P, L, P, P, L, I, I, I, P, P, P],
+    "eqv2_opt_chunk_elems": [],
+    "eqv2_grad_sqnorm": [P, P, P, I, F, P, P, P],
+    "eqv2_adamw_ema_step": [P, P, P, I, P, F, F, F, I, F, P],
 }
 # entry points that only exist in the real (nvcc-built) library
 _OPTIONAL = {"eqv2_gemm_tc", "eqv2_split_f16", "eqv2_gemm_f16", "eqv2_gemm_f16_ex", "eqv2_gather_rotate_fwd_planes",

@@ -268,6 +268,35 @@ int eqv2_embed_rows(const float* table, const long long* idx, float* out, long l
 int eqv2_seg_colsum(const float* src, long long ld, const int* rowptr, const int* perm, long long rows, int V, int C,
                     int S, float* partial, float* out, void* stream);
 
+/* ---- optimizer-side step (train_oc20v2_parallel.py:95-126,177-186) -----------------------------------
+ * Multi-tensor kernels over ONE device table of the model's parameter tensors, processed in chunks of
+ * eqv2_opt_chunk_elems() elements: chunk c covers elements [chunk_index[c] * chunk, ...) of tensors[chunk_tensor[c]].
+ *   eqv2_grad_sqnorm   : out[0] = global L2 norm of all gradients (deterministic summation order), out[1] = the
+ *                        clip coefficient min(1, max_norm / (norm + 1e-6)) of torch.nn.utils.clip_grad_norm_
+ *                        (1 when max_norm <= 0); partial: nchunks floats of workspace.
+ *   eqv2_adamw_ema_step: torch.optim.AdamW update (decoupled weight decay, bias corrections 1 - beta^t with the
+ *                        tensor's own t = step - lag, evaluated in double) on the clipped gradient
+ *                        (clip = out of eqv2_grad_sqnorm, or NULL), followed by the reference's
+ *                        ExponentialMovingAverage.update on `ema` (NULL: none).  Tensors with g == NULL are skipped. */
+typedef struct {
+  float* p;        /* parameter */
+  const float* g;  /* gradient, may be NULL */
+  float* m;        /* exp_avg */
+  float* v;        /* exp_avg_sq */
+  float* ema;      /* EMA shadow, may be NULL */
+  long long n;
+  float lr, wd;
+  int lag;         /* optimizer steps this tensor has NOT taken (no gradient): its own step count = step - lag, as torch */
+  int pad_;
+} eqv2_opt_tensor;
+int eqv2_opt_chunk_elems(void);
+int eqv2_grad_sqnorm(const eqv2_opt_tensor* tensors /*device*/, const int* chunk_tensor /*device*/,
+                     const int* chunk_index /*device*/, int nchunks, float max_norm, float* partial, float* out /*[2]*/,
+                     void* stream);
+int eqv2_adamw_ema_step(const eqv2_opt_tensor* tensors, const int* chunk_tensor, const int* chunk_index, int nchunks,
+                        const float* clip /*[2] or NULL*/, float beta1, float beta2, float eps, int step /*>= 1*/,
+                        float ema_decay, void* stream);
+
 #ifdef __cplusplus
 }
 #endif
