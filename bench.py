@@ -103,6 +103,8 @@ def parse():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-graph", action="store_true", help="enqueue every step from Python instead of replaying a CUDA graph")
     ap.add_argument("--no-dropout", action="store_true", help="alpha_drop = drop_path_rate = 0")
+    ap.add_argument("--bucket", default=None, help="pad every batch to multiples ATOMS,EDGES (e.g. 64,512) with a masked "
+                    "ghost structure so that one captured graph serves a whole bucket of batch sizes")
     ap.add_argument("--optimizer", default="fused", choices=["fused", "torch"],
                     help="fused: clip_grad_norm_ + AdamW + EMA as one multi-tensor pass (optim.FusedAdamW, the reference's "
                          "optimizer-side step); torch: torch.optim.AdamW(fused=True) alone (the round-1 step)")
@@ -174,15 +176,22 @@ def make_batch(cfg, n, seed):
 def forward_loss(cfg, model, data):
     """The scalar a train step back-propagates (reference train scripts: L1 on energy and forces,
     train_oc20v2_parallel.py:150-176, train_MatPES_GATAWandB.py:67-91; L1 on the property vector for QM9)."""
+    if "atom_mask" in data:          # batch padded to an (atoms, edges) bucket: the ghost structure is masked out
+        import importlib
+        mm = importlib.import_module(PKG + ".batching").masked_mean
+        mean_s = lambda x: mm(x, data["structure_mask"])
+        mean_a = lambda x: mm(x, data["atom_mask"])
+    else:
+        mean_s = mean_a = lambda x: x.mean()
     if cfg["kind"] == "direct":
         energy, forces = model(data)
-        return (energy - data["energy"]).abs().mean() + (forces - data["forces"]).abs().mean()
+        return mean_s((energy - data["energy"]).abs()) + mean_a((forces - data["forces"]).abs())
     if cfg["kind"] == "qm9":
-        return (model(data) - data["targets"]).abs().mean()
+        return mean_s((model(data) - data["targets"]).abs())
     pos = data["pos"].detach().requires_grad_(True)
     out = model(dict(data, pos=pos))
     forces = -torch.autograd.grad(out["energy_total"].sum(), pos, create_graph=True, retain_graph=True)[0]
-    return (out["energy"] - data["energy"]).abs().mean() + (forces - data["forces"]).abs().mean()
+    return mean_s((out["energy"] - data["energy"]).abs()) + mean_a((forces - data["forces"]).abs())
 
 
 def config_dict(cfg, kw, structures, world):
@@ -403,7 +412,8 @@ def run_b200(args):
         if world > 1:
             parallel = importlib.import_module(PKG + ".parallel")
             sync = parallel.GradientAllReducer(model.parameters(), bucket_mb=64).reduce
-        stepper = graphs.GraphedTrainStep(model, None, opt, grad_sync=sync,
+        bucket = tuple(int(v) for v in args.bucket.split(",")) if args.bucket else None
+        stepper = graphs.GraphedTrainStep(model, None, opt, grad_sync=sync, bucket=bucket,
                                           forward_loss=lambda d: forward_loss(cfg, model, d))
         step = stepper
     else:

@@ -7,14 +7,19 @@ is read back to size the edge tensors) and the edge frames (`model.prepare`) -- 
 eagerly on the gradients the replay leaves in place (its state and step count behave exactly as without graphs).
 A batch with a new signature is captured again, up to `max_graphs` signatures (each capture keeps its activations in the
 graphs' shared private memory pool: several GB for the OC20 step, ~100 GB for config 5 at 8 x 200 atoms); beyond that, or
-with `max_graphs=0`, the step runs eagerly."""
+with `max_graphs=0`, the step runs eagerly.
+
+Real data has a new (atoms, edges) pair almost every step.  With `bucket=(n_mult, e_mult)` the prepared batch is padded
+with one ghost structure to the next multiples (batching.pad_to_bucket: exact -- the ghost exchanges no messages with
+real atoms and is masked out of the loss), so one capture serves every batch of its bucket; the loss must then weight
+by `data["atom_mask"]` / `data["structure_mask"]` (batching.masked_mean)."""
 import torch
 
 from . import ops
 
 
 class GraphedTrainStep:
-    def __init__(self, model, loss_fn, optimizer, max_graphs=4, warmup=2, grad_sync=None, forward_loss=None):
+    def __init__(self, model, loss_fn, optimizer, max_graphs=4, warmup=2, grad_sync=None, forward_loss=None, bucket=None):
         """model(data) -> outputs; loss_fn(outputs, data) -> scalar -- or `forward_loss(data)` -> scalar for steps that
         need more than that (MatPES: forces = -autograd.grad(E, pos, create_graph=True) inside the loss).
         `model.prepare(data)` must return the dict of data-dependent inputs the model then takes from `data` (OC20:
@@ -24,6 +29,8 @@ class GraphedTrainStep:
         self.forward_loss = forward_loss if forward_loss is not None else (lambda d: loss_fn(model(d), d))
         self.grad_sync = grad_sync
         self.max_graphs, self.warmup = max_graphs, warmup
+        self.bucket = bucket        # (atoms multiple, edges multiple) or None: exact signatures
+        self.eager_steps = 0
         self.graphs = {}            # signature -> (graph, static inputs, static loss, gradient tensors, launches)
         self.params = [p for g in optimizer.param_groups for p in g["params"]]
         self.pool = None
@@ -36,6 +43,9 @@ class GraphedTrainStep:
             prepared = self.model.prepare(data)
         out = dict(data)
         out.update(prepared)
+        if self.bucket is not None:
+            from . import batching
+            out = batching.pad_to_bucket(out, *self.bucket)
         return out
 
     def _eager(self, full):
@@ -80,6 +90,7 @@ class GraphedTrainStep:
         hit = self.graphs.get(sig)
         if hit is None:
             if len(self.graphs) >= self.max_graphs:
+                self.eager_steps += 1
                 loss = self._eager(full)
                 self.active = None
                 if self.grad_sync is not None:
