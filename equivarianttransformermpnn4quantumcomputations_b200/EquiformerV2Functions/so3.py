@@ -286,11 +286,12 @@ class SO3_Grid(nn.Module):
     def kernel_mats(self, order):
         """Padded [G, KP] copies of the buffers for the fused kernel, columns in l-primary ('l')
         or m-primary ('m') reduced order.  Rebuilt if the buffers were reloaded / moved."""
-        key = (order, self.to_grid_mat.device, self.to_grid_mat._version, self.to_grid_mat.data_ptr())
-        if self._padded.get("key") != key:
-            self._padded = {"key": key, "mats": ops.GridMats.from_buffers(
-                self.to_grid_mat, self.from_grid_mat, self.lmax, self.mmax, order)}
-        return self._padded["mats"]
+        key = (self.to_grid_mat.device, self.to_grid_mat._version, self.to_grid_mat.data_ptr())
+        hit = self._padded.get(order)       # one entry PER ORDER: a grid with lmax == mmax serves both the attention
+        if hit is None or hit[0] != key:    # ('m') and the FFN ('l') -- a single entry would be rebuilt on every call
+            hit = self._padded[order] = (key, ops.GridMats.from_buffers(
+                self.to_grid_mat, self.from_grid_mat, self.lmax, self.mmax, order))
+        return hit[1]
 
 
 class SO3_LinearV2(nn.Module):

@@ -26,10 +26,11 @@ struct S2Tables {
   float st[S2_RES][S2_MAXL + 1];                // sqrt2 sin(m alpha_a)  (m = 0: unused)
 };
 
+constexpr int S2_SLOTS = 6;       // one slot per (lmax, mmax, order) in use: bound once, never overwritten
 #ifdef EQV2_CPU_EMU
-static S2Tables g_tab[2];
+static S2Tables g_tab[S2_SLOTS];
 #else
-__constant__ S2Tables g_tab[2];
+__constant__ S2Tables g_tab[S2_SLOTS];
 #endif
 
 // position of coefficient (l, +-mi) in the reduced tensor
@@ -282,7 +283,7 @@ extern "C" int eqv2_s2sep_supported(int lmax, int mmax) {
 
 // tables: host pointer to an S2Tables-shaped float block (see ops.py::S2Factors), copied into constant slot 0/1
 extern "C" int eqv2_s2sep_set_tables(const float* host_tables, int nfloats, int slot, void* stream) {
-  EQV2_REQUIRE(slot == 0 || slot == 1, "s2sep_set_tables: slot must be 0 or 1");
+  EQV2_REQUIRE(slot >= 0 && slot < S2_SLOTS, "s2sep_set_tables: slot must be in [0, %d)", S2_SLOTS);
   EQV2_REQUIRE(nfloats == (int)(sizeof(S2Tables) / sizeof(float)), "s2sep_set_tables: expected %d floats, got %d",
                (int)(sizeof(S2Tables) / sizeof(float)), nfloats);
 #ifdef EQV2_CPU_EMU

@@ -27,17 +27,33 @@ class EquiformerV2_MatPES(_V2):
     def __init__(self, use_pbc=True, regress_forces=True, regress_stress=True, **kwargs):
         super().__init__(use_pbc=use_pbc, regress_forces=regress_forces, regress_stress=regress_stress, **kwargs)
 
+    def prepare(self, data):
+        """Data-dependent head of a forward pass (graphs.GraphedTrainStep): the 27-image neighbour list -- topology and
+        image indices only (one read-back of the edge count).  The differentiable edge vectors are rebuilt from pos / cell
+        inside the replayable part (`generate_graph` with the topology supplied)."""
+        pos, cell, batch = data["pos"].detach(), data["cell"].detach(), data["batch"]
+        natoms = data["natoms"] if "natoms" in data else torch.bincount(batch, minlength=cell.shape[0])
+        with torch.no_grad():
+            edge_index, _, _, img = ops.radius_graph_matpes(pos, cell, natoms, batch, self.max_radius,
+                                                            self.max_neighbors, 1)
+        return {"edge_index": edge_index, "edge_image": img}
+
     def generate_graph(self, data):
         """-> (edge_index, edge_distance, edge_distance_vec, None, None, neighbors); vectors differentiable w.r.t.
-        data['pos'] and data['cell']."""
+        data['pos'] and data['cell'].  A topology supplied as data['edge_index'] / data['edge_image'] (from `prepare`) is
+        reused instead of running the host-synchronising builder."""
         pos, cell, batch = data["pos"], data["cell"], data["batch"]
-        natoms = data["natoms"] if "natoms" in data else torch.bincount(batch, minlength=cell.shape[0])
-        edge_index, _, _, img = ops.radius_graph_matpes(pos, cell, natoms, batch, self.max_radius, self.max_neighbors, 1)
+        if "edge_index" in data and "edge_image" in data:
+            edge_index, img = data["edge_index"], data["edge_image"]
+        else:
+            natoms = data["natoms"] if "natoms" in data else torch.bincount(batch, minlength=cell.shape[0])
+            edge_index, _, _, img = ops.radius_graph_matpes(pos, cell, natoms, batch, self.max_radius,
+                                                            self.max_neighbors, 1)
         img = img.long()
         frac = torch.stack([img // 9 - 1, (img // 3) % 3 - 1, img % 3 - 1], dim=1).to(pos.dtype)
         offset = torch.einsum("ek,ekj->ej", frac, cell[batch[edge_index[1]]])
         vec = pos[edge_index[1]] + offset - pos[edge_index[0]]
-        neighbors = torch.bincount(edge_index[1], minlength=pos.shape[0])
+        neighbors = None if "edge_image" in data else torch.bincount(edge_index[1], minlength=pos.shape[0])
         return edge_index, torch.norm(vec, dim=1), vec, None, None, neighbors
 
     def _init_edge_rot_mat(self, data, edge_index, edge_distance_vec):

@@ -1511,18 +1511,24 @@ class GridMats:
         return np.ascontiguousarray(np.concatenate([a.reshape(-1) for a in (Pt, Pf, ct, st)]).astype(np.float32))
 
 
-_s2_slots = {}
+_s2_slots = {}            # (device, lmax, mmax, order) -> constant-memory slot; a slot is bound ONCE and never overwritten
+S2_SLOTS = 6
 
 
 def _s2_bind_tables(mats, device):
-    """Make sure the constant-memory slot of this coefficient order holds `mats`' factor tables."""
-    slot = 0 if mats.order == "m" else 1
-    key = (str(device), slot)
-    if _s2_slots.get(key, (None,))[0] != (mats.lmax, mats.mmax):
+    """Constant-memory slot holding `mats`' factor tables.  Every (device, lmax, mmax, coefficient order) gets its own
+    slot for the life of the process, so a captured CUDA graph can never see its tables replaced by another model's
+    (ADVICE r1); the ninth distinct combination raises instead of evicting."""
+    key = (str(device), mats.lmax, mats.mmax, mats.order)
+    hit = _s2_slots.get(key)
+    if hit is None:
+        slot = sum(1 for k in _s2_slots if k[0] == key[0])
+        if slot >= S2_SLOTS:
+            raise _lib.Eqv2Error("S2 activation: more than %d (lmax, mmax, order) table sets in one process" % S2_SLOTS)
         _lib.call("eqv2_s2sep_set_tables", mats.factors.ctypes.data, int(mats.factors.size), slot, _lib.stream_ptr(),
                   n_kernels=0)
-        _s2_slots[key] = ((mats.lmax, mats.mmax), mats.factors)     # keep the host block alive
-    return slot
+        hit = _s2_slots[key] = (slot, mats.factors)     # keep the host block alive
+    return hit[0]
 
 
 def _s2_work(mats, R, C, passes):

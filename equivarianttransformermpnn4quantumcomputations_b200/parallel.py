@@ -61,9 +61,15 @@ class GradientAllReducer:
     on backends without AVG), one multi-tensor copy back -- a handful of launches per step instead of one per parameter
     (82.5 M parameters live in ~800 tensors; per-tensor copies cost the host ~4 ms per step)."""
 
-    def __init__(self, parameters, bucket_mb=25, group=None):
+    def __init__(self, parameters, bucket_mb=25, group=None, sync_presence=False):
+        """sync_presence: also exchange which parameters have a gradient on ANY rank and give the ranks that lack one
+        the averaged gradient, so that every replica applies the same update when gradients are present on some ranks
+        only (empty sub-batch, a branch not exercised on a rank).  Costs one small all-reduce and one host read-back
+        per step, so it is off by default: the reference models either give every parameter a gradient on every rank
+        or leave the same parameters without one everywhere (GATA family)."""
         self.params = [p for p in parameters if p.requires_grad]
         self.group = group
+        self.sync_presence = sync_presence
         self.buckets, cur, size = [], [], 0
         limit = bucket_mb * (1 << 20)
         for p in self.params:
@@ -101,10 +107,24 @@ class GradientAllReducer:
             if have:
                 torch._foreach_copy_([v for v, _ in have], [g for _, g in have])
             op = dist.ReduceOp.AVG if avg else dist.ReduceOp.SUM
-            pending.append((dist.all_reduce(flat, op=op, group=self.group, async_op=True), flat, have))
-        for work, flat, have in pending:
+            pending.append((dist.all_reduce(flat, op=op, group=self.group, async_op=True), flat, have, i))
+        # A parameter may have a gradient on some ranks only (empty sub-batch, a branch not exercised on a rank): every
+        # rank must then apply the same averaged update or the replicas drift apart.  One small all-reduce of
+        # the per-parameter presence flags tells each rank which gradients exist anywhere.
+        anywhere = None
+        if self.sync_presence:
+            present = torch.tensor([0.0 if p.grad is None else 1.0 for p in self.params], device=self.params[0].device)
+            dist.all_reduce(present, op=dist.ReduceOp.MAX, group=self.group)
+            anywhere = present.bool().tolist()
+            index = {id(p): k for k, p in enumerate(self.params)}
+        for work, flat, have, i in pending:
             work.wait()
             if not avg:
                 flat.div_(world)
             if have:
                 torch._foreach_copy_([g for _, g in have], [v for v, _ in have])
+            if anywhere is not None:
+                _, views = self._flat[i]
+                for v, p in zip(views, self.buckets[i]):
+                    if p.grad is None and anywhere[index[id(p)]]:
+                        p.grad = v.clone()

@@ -173,7 +173,7 @@ int eqv2_s2act_bwd(const float* X, long long x_rs, const float* gate, long long 
 
 /* latitude/longitude-factorised version of the same operator (csrc/s2act_sep.cu): resolution-18 grids,
  * factor tables (float block laid out as [7][18][7] Pt | [7][18][7] Pf | [18][7] cos | [18][7] sin) in one
- * of two __constant__ slots; m_primary selects the coefficient order of X / O. */
+ * of six __constant__ slots (one per (lmax, mmax, order) in use, bound once); m_primary selects the coefficient order of X / O. */
 int eqv2_s2sep_supported(int lmax, int mmax);
 int eqv2_s2sep_set_tables(const float* host_tables, int nfloats, int slot, void* stream);
 int eqv2_s2sep_fwd(const float* X, long long x_rs, const float* gate, long long g_rs, float* O, long long o_rs,

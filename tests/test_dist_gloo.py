@@ -87,3 +87,33 @@ def test_two_rank_gradients_match_single_process(tmp_path, use_ddp):
     assert set(g0) == set(fx["params"])
     assert all(torch.isfinite(v).all() for v in g0.values())
     assert max(float(v.abs().max()) for v in g0.values()) > 0
+
+
+def _presence_worker(rank, world, port, out_dir):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+    sys.path.insert(0, REPO)
+    import importlib
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    par = importlib.import_module(PKG + ".parallel")
+    torch.manual_seed(0)
+    params = [torch.nn.Parameter(torch.randn(5)), torch.nn.Parameter(torch.randn(3, 2)), torch.nn.Parameter(torch.randn(4))]
+    params[0].grad = torch.full((5,), float(rank + 1))
+    params[1].grad = torch.full((3, 2), 2.0) if rank == 0 else None       # gradient on rank 0 only
+    params[2].grad = None                                                  # nowhere: must stay None
+    par.GradientAllReducer(params, bucket_mb=1, sync_presence=True).reduce()
+    torch.save([None if p.grad is None else p.grad.clone() for p in params], os.path.join(out_dir, f"p_{rank}.pt"))
+    dist.destroy_process_group()
+
+
+def test_gradient_present_on_one_rank_only_is_shared(tmp_path):
+    """a parameter with a gradient on some ranks only must get the same averaged gradient everywhere (zeros
+    counted for the ranks without), and a parameter without gradient on every rank keeps `grad is None`."""
+    import socket
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        port = s.getsockname()[1]
+    mp.spawn(_presence_worker, args=(2, port, str(tmp_path)), nprocs=2, join=True)
+    g0, g1 = torch.load(tmp_path / "p_0.pt"), torch.load(tmp_path / "p_1.pt")
+    assert torch.equal(g0[0], torch.full((5,), 1.5)) and torch.equal(g1[0], g0[0])
+    assert g1[1] is not None and torch.equal(g0[1], torch.full((3, 2), 1.0)) and torch.equal(g1[1], g0[1])
+    assert g0[2] is None and g1[2] is None
