@@ -23,7 +23,10 @@ class RadialFunction(nn.Module):
         i = 0
         while i < len(mods):
             lin = mods[i]
-            x = ops.linear(x, lin.weight, lin.bias)
+            if isinstance(x, ops.FusedEdgeFeatures):        # x_edge as a description: fused GaussianSmearing + layer 1
+                x = ops.rbf_linear(x, lin.weight, lin.bias)
+            else:
+                x = ops.linear(x, lin.weight, lin.bias)
             i += 1
             if i < len(mods):
                 ln = mods[i]

@@ -53,6 +53,11 @@ def edge_scalar_features(module, atomic_numbers, edge_distance, edge_index):
     # the element types that is built once per graph (F.embedding's backward sorts the indices on every call)
     plan = ops.edge_plan(edge_index, atomic_numbers.shape[0])
     zs, csr_s, zd, csr_d = plan.element_types(atomic_numbers, src_w.shape[0])
+    src = ops.rbf_source_of(edge_distance)
+    if src is not None:
+        # first-order step and the rbf tensor came from this package's GaussianSmearing: hand the radial MLP a DESCRIPTION
+        # of x_edge -- its first layer is evaluated from the raw distances (banded) and two table lookups (ops.rbf_linear)
+        return ops.FusedEdgeFeatures(src, src_w, dst_w, zs, csr_s, zd, csr_d)
     return torch.cat((edge_distance, ops.embed_rows(src_w, zs, csr_s), ops.embed_rows(dst_w, zd, csr_d)), dim=1)
 
 

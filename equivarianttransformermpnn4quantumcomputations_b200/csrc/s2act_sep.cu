@@ -26,7 +26,7 @@ struct S2Tables {
   float st[S2_RES][S2_MAXL + 1];                // sqrt2 sin(m alpha_a)  (m = 0: unused)
 };
 
-constexpr int S2_SLOTS = 6;       // one slot per (lmax, mmax, order) in use: bound once, never overwritten
+constexpr int S2_SLOTS = 6;       // table sets resident at once; ops.py owns the slot map (LRU, slots used by a captured graph are pinned)
 #ifdef EQV2_CPU_EMU
 static S2Tables g_tab[S2_SLOTS];
 #else

@@ -26,7 +26,8 @@ class GaussianSmearing(nn.Module):
         return self.num_gaussians
 
     def forward(self, dist):
-        return ops.rbf(dist.reshape(-1), self.offset, self.coeff)
+        delta = (self.stop - self.start) / (self.num_gaussians - 1) if self.num_gaussians > 1 else None
+        return ops.rbf(dist.reshape(-1), self.offset, self.coeff, start=self.start, delta=delta)
 
 
 def build_so3_grid(lmax_list, grid_resolution):

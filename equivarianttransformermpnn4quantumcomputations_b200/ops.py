@@ -1511,24 +1511,39 @@ class GridMats:
         return np.ascontiguousarray(np.concatenate([a.reshape(-1) for a in (Pt, Pf, ct, st)]).astype(np.float32))
 
 
-_s2_slots = {}            # (device, lmax, mmax, order) -> constant-memory slot; a slot is bound ONCE and never overwritten
+_s2_slots = {}            # (device, lmax, mmax, order) -> [slot, host tables, last use, pinned]
+_s2_clock = [0]
 S2_SLOTS = 6
 
 
 def _s2_bind_tables(mats, device):
-    """Constant-memory slot holding `mats`' factor tables.  Every (device, lmax, mmax, coefficient order) gets its own
-    slot for the life of the process, so a captured CUDA graph can never see its tables replaced by another model's
-    (ADVICE r1); the ninth distinct combination raises instead of evicting."""
+    """Constant-memory slot holding `mats`' factor tables.  Each (device, lmax, mmax, coefficient order) in use owns one
+    of S2_SLOTS slots; when they run out the least recently used one is rebound -- except slots that a CUDA-graph
+    capture has used: those are PINNED for the life of the process, so a replayed graph can never see its tables
+    replaced by another model's.  A miss during capture raises (the warm-up step binds everything)."""
     key = (str(device), mats.lmax, mats.mmax, mats.order)
+    capturing = torch.cuda.is_available() and torch.cuda.is_current_stream_capturing()
+    _s2_clock[0] += 1
     hit = _s2_slots.get(key)
-    if hit is None:
-        slot = sum(1 for k in _s2_slots if k[0] == key[0])
-        if slot >= S2_SLOTS:
-            raise _lib.Eqv2Error("S2 activation: more than %d (lmax, mmax, order) table sets in one process" % S2_SLOTS)
-        _lib.call("eqv2_s2sep_set_tables", mats.factors.ctypes.data, int(mats.factors.size), slot, _lib.stream_ptr(),
-                  n_kernels=0)
-        hit = _s2_slots[key] = (slot, mats.factors)     # keep the host block alive
-    return hit[0]
+    if hit is not None:
+        hit[2] = _s2_clock[0]
+        hit[3] = hit[3] or capturing
+        return hit[0]
+    if capturing:
+        raise _lib.Eqv2Error("S2 activation tables must be bound before a CUDA-graph capture (run one eager step first)")
+    mine = {k: v for k, v in _s2_slots.items() if k[0] == key[0]}
+    free = sorted(set(range(S2_SLOTS)) - {v[0] for v in mine.values()})
+    if free:
+        slot = free[0]
+    else:
+        victims = sorted((v[2], k) for k, v in mine.items() if not v[3])
+        if not victims:
+            raise _lib.Eqv2Error("S2 activation: all %d table slots are pinned by captured CUDA graphs" % S2_SLOTS)
+        slot = _s2_slots.pop(victims[0][1])[0]
+    _lib.call("eqv2_s2sep_set_tables", mats.factors.ctypes.data, int(mats.factors.size), slot, _lib.stream_ptr(),
+              n_kernels=0)
+    _s2_slots[key] = [slot, mats.factors, _s2_clock[0], False]       # the host block is kept alive
+    return slot
 
 
 def _s2_work(mats, R, C, passes):
@@ -1912,6 +1927,116 @@ class RbfFn(torch.autograd.Function):
         return gd, None, None
 
 
+# ----------------------------------------------------------------------------------------------
+# GaussianSmearing + first radial-MLP layer, fused (north_star piece 2)
+# ----------------------------------------------------------------------------------------------
+RBF_BAND_TOL = 1e-12          # neglected basis functions are below this (relative to the largest one, which is ~1)
+_FEATURES["rbf_linear"] = "rbf_linear" not in _os.environ.get("EQV2_DISABLE", "").split(",")
+
+
+class RbfSource:
+    """What GaussianSmearing attaches to the [E, R] tensor it returns (`tensor._eqv2_rbf`): the raw distances and the
+    basis description, so that a consumer that only needs W . rbf(d) can evaluate it from d without reading the tensor."""
+    __slots__ = ("dist", "offset", "coeff", "start", "delta", "band", "_bins")
+
+    def __init__(self, dist, offset, coeff, start, delta):
+        self.dist, self.offset, self.coeff, self.start, self.delta = dist, offset, float(coeff), float(start), float(delta)
+        # exp(coeff (j delta)^2) < tol  <=>  j > sqrt(ln(tol) / (coeff delta^2))
+        self.band = int(math.ceil(math.sqrt(math.log(RBF_BAND_TOL) / (self.coeff * self.delta ** 2))))
+        self._bins = None
+
+    def bins(self):
+        """(perm int32 [E], rowptr int32 [R+1]): edges grouped by nearest basis index -- once per graph, shared by
+        every block's weight gradient."""
+        if self._bins is None:
+            R = int(self.offset.shape[0])
+            k0 = torch.round((self.dist - self.start) / self.delta).clamp_(0, R - 1).long()
+            self._bins = _csr_few_buckets(k0, R)
+        return self._bins
+
+
+class FusedEdgeFeatures:
+    """x_edge = [rbf(d) | E_src[Z_src] | E_dst[Z_dst]] (transformer_block.py:241-248) as a DESCRIPTION: the radial MLP's
+    first layer evaluates W1 x_edge + b1 from it directly (`rbf_linear`), the [E, R + 2 Ce] matrix is never formed."""
+
+    def __init__(self, src, src_w, dst_w, zs, csr_s, zd, csr_d):
+        self.src, self.src_w, self.dst_w = src, src_w, dst_w
+        self.zs, self.csr_s, self.zd, self.csr_d = zs, csr_s, zd, csr_d
+
+    @property
+    def width(self):
+        return int(self.src.offset.shape[0]) + (2 * int(self.src_w.shape[1]) if self.src_w is not None else 0)
+
+
+def rbf_source_of(t):
+    """The RbfSource behind an rbf tensor if the fused first layer may use it: feature on, CUDA library has the kernels,
+    distances carry no gradient (first-order step)."""
+    src = getattr(t, "_eqv2_rbf", None)
+    if src is None or not _FEATURES["rbf_linear"] or not hasattr(_lib.lib(), "eqv2_rbf_linear_fwd"):
+        return None
+    if torch.is_grad_enabled() and src.dist.requires_grad:
+        return None
+    return src
+
+
+class RbfLinearFn(torch.autograd.Function):
+    """h = Wt^T rbf(d) + Ts[zs] + Td[zd] + b over the (2 band + 1) nearest basis functions.  Backward: banded weight
+    gradient in bin order, table gradients as deterministic segmented column sums, bias gradient as a column sum."""
+
+    @staticmethod
+    def forward(ctx, Wt, Ts, Td, bias, feat):
+        src = feat.src
+        _lib.check_device(Wt, Ts, Td, bias, src.dist)
+        assert Wt.is_contiguous() and (Ts is None or (Ts.is_contiguous() and Td.is_contiguous()))
+        E, (R, H) = int(src.dist.shape[0]), Wt.shape
+        out = torch.empty(E, H, dtype=_F32, device=Wt.device)
+        _lib.call("eqv2_rbf_linear_fwd", src.dist.data_ptr(), src.offset.data_ptr(), Wt.data_ptr(), _lib.ptr(Ts),
+                  _lib.ptr(Td), _lib.ptr(feat.zs) if Ts is not None else None, _lib.ptr(feat.zd) if Ts is not None else None,
+                  _lib.ptr(bias), out.data_ptr(), E, int(R), int(H), src.start, src.delta, src.coeff, src.band,
+                  _lib.stream_ptr(), work=(2.0 * E * H * (2 * src.band + 1), 4.0 * E * (H + 1)))
+        ctx.feat, ctx.shape = feat, (int(R), int(H))
+        ctx.has = (Ts is not None, bias is not None)
+        return out
+
+    @staticmethod
+    @torch.autograd.function.once_differentiable
+    def backward(ctx, gh):
+        feat, (R, H) = ctx.feat, ctx.shape
+        src = feat.src
+        gh = gh.contiguous()
+        gWt = gTs = gTd = gb = None
+        if ctx.needs_input_grad[0]:
+            perm, rowptr = src.bins()
+            gWt = torch.empty(R, H, dtype=_F32, device=gh.device)
+            _lib.call("eqv2_rbf_linear_wgrad", src.dist.data_ptr(), src.offset.data_ptr(), perm.data_ptr(),
+                      rowptr.data_ptr(), gh.data_ptr(), gWt.data_ptr(), R, H, src.coeff, src.band, _lib.stream_ptr(),
+                      work=(2.0 * gh.shape[0] * H * (2 * src.band + 1), 4.0 * gh.shape[0] * H))
+        if ctx.has[0]:
+            V = int(feat.src_w.shape[0])
+            S = max(1, min(256, int(gh.shape[0]) // 32))
+            if ctx.needs_input_grad[1]:
+                gTs = _seg_colsum(gh, H, 0, gh.shape[0], H, V, feat.csr_s[1], feat.csr_s[0], S)
+            if ctx.needs_input_grad[2]:
+                gTd = _seg_colsum(gh, H, 0, gh.shape[0], H, V, feat.csr_d[1], feat.csr_d[0], S)
+        if ctx.has[1] and ctx.needs_input_grad[3]:
+            gb = colsum(gh, 0, H)
+        return gWt, gTs, gTd, gb, None
+
+
+def rbf_linear(feat, W1, b1):
+    """First layer of the radial MLP on a FusedEdgeFeatures description: the weight slices are taken apart with ordinary
+    (differentiable) torch ops -- [H, R] -> transposed [R, H] for coalesced row reads; the embedding tables are multiplied
+    by their slices once per element type ([V, Ce] x [Ce, H], V ~ 90) instead of once per edge."""
+    R = int(feat.src.offset.shape[0])
+    Wt = W1[:, :R].t().contiguous()
+    Ts = Td = None
+    if feat.src_w is not None:
+        Ce = int(feat.src_w.shape[1])
+        Ts = torch.mm(feat.src_w, W1[:, R:R + Ce].t())
+        Td = torch.mm(feat.dst_w, W1[:, R + Ce:R + 2 * Ce].t())
+    return RbfLinearFn.apply(Wt, Ts, Td, b1, feat)
+
+
 def gather_rotate(x, rad, plan, wig, lmax, mmax):
     return GatherRotateFn.apply(x.contiguous(), rad.contiguous() if rad is not None else None, plan, wig, lmax, mmax)
 
@@ -1941,5 +2066,11 @@ def ln_silu(x, w, b, eps):
     return LnSiluFn.apply(x.contiguous(), w.contiguous(), b.contiguous(), eps)
 
 
-def rbf(d, offset, coeff):
-    return RbfFn.apply(d.reshape(-1).contiguous(), offset.contiguous(), coeff)
+def rbf(d, offset, coeff, start=None, delta=None):
+    """GaussianSmearing.  With `start` / `delta` (uniformly spaced offsets) the result also carries an RbfSource, which
+    lets the radial MLP's first layer skip the [E, R] tensor (rbf_linear)."""
+    d = d.reshape(-1).contiguous()
+    out = RbfFn.apply(d, offset.contiguous(), coeff)
+    if start is not None and delta is not None and delta > 0:
+        out._eqv2_rbf = RbfSource(d.detach() if not d.requires_grad else d, offset, coeff, start, delta)
+    return out

@@ -173,7 +173,7 @@ int eqv2_s2act_bwd(const float* X, long long x_rs, const float* gate, long long 
 
 /* latitude/longitude-factorised version of the same operator (csrc/s2act_sep.cu): resolution-18 grids,
  * factor tables (float block laid out as [7][18][7] Pt | [7][18][7] Pf | [18][7] cos | [18][7] sin) in one
- * of six __constant__ slots (one per (lmax, mmax, order) in use, bound once); m_primary selects the coefficient order of X / O. */
+ * of six __constant__ slots (the host side owns the slot -> table-set map; slots used inside a captured CUDA graph are never rebound); m_primary selects the coefficient order of X / O. */
 int eqv2_s2sep_supported(int lmax, int mmax);
 int eqv2_s2sep_set_tables(const float* host_tables, int nfloats, int slot, void* stream);
 int eqv2_s2sep_fwd(const float* X, long long x_rs, const float* gate, long long g_rs, float* O, long long o_rs,
@@ -267,6 +267,20 @@ int eqv2_so2_block_weight_adj(const float* gB, float* gW, int h, int k, void* st
 int eqv2_embed_rows(const float* table, const long long* idx, float* out, long long E, int C, void* stream);
 int eqv2_seg_colsum(const float* src, long long ld, const int* rowptr, const int* perm, long long rows, int V, int C,
                     int S, float* partial, float* out, void* stream);
+
+/* ---- GaussianSmearing + first radial-MLP layer, fused (equiformerv2_oc20.py:43-60, radial_function.py:5-30,
+ * transformer_block.py:241-248; north_star piece 2) -------------------------------------------------
+ *   out[e, :] = Wt^T rbf(d_e) + Ts[zs[e]] + Td[zd[e]] + bias,   rbf_k(d) = exp(coeff (d - offset[k])^2),
+ * evaluated over the 2 band + 1 basis functions nearest to d_e (offset = linspace(start, start + (R-1) delta, R); the
+ * neglected terms are < exp(-band^2 / (2 w^2))).  Wt = W1[:, :R]^T [R, H]; Ts / Td [V, H] = embedding tables already
+ * multiplied by their weight slices (NULL: no embedding terms).  First order: no gradient w.r.t. d.
+ *   eqv2_rbf_linear_wgrad: gWt[k, :] = sum_e rbf_k(d_e) gh[e, :] over the edges whose nearest basis index lies within
+ *   `band` of k; perm / rowptr = edges grouped by nearest basis index (R bins), summed in that order (deterministic). */
+int eqv2_rbf_linear_fwd(const float* d, const float* offset, const float* Wt, const float* Ts, const float* Td,
+                        const long long* zs, const long long* zd, const float* bias, float* out, long long E, int R, int H,
+                        float start, float delta, float coeff, int band, void* stream);
+int eqv2_rbf_linear_wgrad(const float* d, const float* offset, const int* perm, const int* rowptr, const float* gh,
+                          float* gWt, int R, int H, float coeff, int band, void* stream);
 
 /* ---- optimizer-side step (train_oc20v2_parallel.py:95-126,177-186) -----------------------------------
  * Multi-tensor kernels over ONE device table of the model's parameter tensors, processed in chunks of

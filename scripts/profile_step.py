@@ -13,7 +13,8 @@ ap.add_argument("--layers", type=int, default=12)
 ap.add_argument("--top", type=int, default=45)
 ap.add_argument("--structures", type=int, default=8)
 a = ap.parse_args()
-kw = dict(bench.MODEL_KW, num_layers=a.layers)
+CFG = bench.CONFIGS["oc20"]
+kw = dict(CFG["kw"], num_layers=a.layers)
 torch.manual_seed(0)
 dev = torch.device("cuda")
 model = oc20.EquiformerV2_OC20(**kw).to(dev)
@@ -22,8 +23,7 @@ data = {k: (v.to(dev) if torch.is_tensor(v) else v) for k, v in synthetic.oc20_b
 
 
 def step():
-    e, f = model(data)
-    loss = bench.losses(e, f, data)
+    loss = bench.forward_loss(CFG, model, data)
     opt.zero_grad(set_to_none=True)
     loss.backward()
     opt.step()
