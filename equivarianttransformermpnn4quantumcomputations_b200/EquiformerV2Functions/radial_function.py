@@ -24,7 +24,8 @@ class RadialFunction(nn.Module):
         while i < len(mods):
             lin = mods[i]
             if isinstance(x, ops.FusedEdgeFeatures):        # x_edge as a description: fused GaussianSmearing + layer 1
-                x = ops.rbf_linear(x, lin.weight, lin.bias)
+                x = ops.rbf_linear(x, lin.weight, lin.bias) if lin.out_features % 4 == 0 else \
+                    ops.linear(x.dense(), lin.weight, lin.bias)
             else:
                 x = ops.linear(x, lin.weight, lin.bias)
             i += 1

@@ -181,6 +181,10 @@ __device__ __forceinline__ Work decode_work(const HParams& P, int w) {
   return W;
 }
 
+// PASSES (3: fp32-class, 1: hi planes only) and CMAX (reduce max |C| in the epilogue) are compile-time: the single-thread
+// TMA-issue and MMA-issue loops are latency-critical, and a run-time `passes` test inside them cost the three-pass kernel
+// ~10 % (measured r02: conv1 forward 439 -> 383 TFLOP/s).
+template <int PASSES, bool CMAX>
 __global__ void __launch_bounds__(NUM_THREADS, 1) gemm_f16_kernel(const __grid_constant__ HParams P) {
   extern __shared__ unsigned char smem_raw[];
   const uint32_t raw_addr = smem_u32(smem_raw);
@@ -224,13 +228,12 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) gemm_f16_kernel(const __grid_c
           const uint32_t s = it % STAGES, round = it / STAGES;
           mbar_wait(smem_u32(&empty[s]), (round & 1u) ^ 1u);
           const uint32_t bar = smem_u32(&full[s]);
-          const int nplanes = P.passes == 1 ? 1 : 2;
+          constexpr int nplanes = PASSES == 1 ? 1 : 2;
           mbar_expect_tx(bar, (uint32_t)(nplanes * 2 * TILE_BYTES));
           const uint32_t st = smem_u32(tiles + (size_t)s * STAGE_BYTES);
           const int k0 = (W.kb0 + i) * BK;
 #pragma unroll
-          for (int plane = 0; plane < 2; ++plane) {
-            if (plane >= nplanes) break;
+          for (int plane = 0; plane < nplanes; ++plane) {
             const uint32_t da = st + plane * TILE_BYTES, db = st + (2 + plane) * TILE_BYTES;
             if (!G.a_mn) {
               tma_load_3d(da, &G.mapA, bar, k0, W.m0, plane);
@@ -279,7 +282,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) gemm_f16_kernel(const __grid_c
               const uint64_t dah = make_desc(a_hi + k * a_step, amn);
               const uint64_t dal = make_desc(a_lo + k * a_step, amn);
               const uint64_t dbh = make_desc(b_hi + k * b_step, bmn);     // as an N=256 operand: B_hi | B_lo
-              if (P.passes == 1) {                                         // single pass: D_hh (+)= A_hi B_hi
+              if constexpr (PASSES == 1) {                                 // single pass: D_hh (+)= A_hi B_hi
                 umma_f16(d_hh, dah, dbh, idesc128, (i == i0 && k == 0) ? 0u : 1u);
                 continue;
               }
@@ -336,7 +339,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) gemm_f16_kernel(const __grid_c
           acc[x] += __uint_as_float(r0[x]);
           acc[32 + x] += __uint_as_float(r1[x]);
         }
-        if (j >= nchunks - 2 && P.passes != 1) {             // last chunk on this buffer: its D_lo is final
+        if (PASSES != 1 && j >= nchunks - 2) {               // last chunk on this buffer: its D_lo is final
           tmem_ld32_nowait(d_hh + 128u, r0);
           tmem_ld32_nowait(d_hh + 160u, r1);
           tmem_ld_wait();
@@ -399,7 +402,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) gemm_f16_kernel(const __grid_c
                   o.x += p.x; o.y += p.y; o.z += p.z; o.w += p.w;
                 }
                 *reinterpret_cast<float4*>(cp) = o;
-                cmax = fmaxf(cmax, fmaxf(fmaxf(fabsf(o.x), fabsf(o.y)), fmaxf(fabsf(o.z), fabsf(o.w))));
+                if constexpr (CMAX) cmax = fmaxf(cmax, fmaxf(fmaxf(fabsf(o.x), fabsf(o.y)), fmaxf(fabsf(o.z), fabsf(o.w))));
               }
             }
             __syncwarp();
@@ -422,11 +425,11 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) gemm_f16_kernel(const __grid_c
             if (atomic) atomicAdd(crow + x, o);
             else if (G.accumulate) { o += crow[x]; crow[x] = o; }
             else crow[x] = o;
-            cmax = fmaxf(cmax, fabsf(o));
+            if constexpr (CMAX) cmax = fmaxf(cmax, fabsf(o));
           }
         }
       }
-      if (G.c_absmax != nullptr && !atomic) {               // one fire-and-forget atomic per warp and tile
+      if (CMAX && G.c_absmax != nullptr && !atomic) {       // one fire-and-forget atomic per warp and tile
         cmax = eqv2_warp_max(cmax);
         if (lane == 0 && cmax > 0.f)
           atomicMax(reinterpret_cast<unsigned*>(G.c_absmax) + ((blockIdx.x * NUM_WORKER_WARPS + warp) & (EQV2_ABSMAX_SLOTS - 1)),
@@ -714,17 +717,23 @@ extern "C" int eqv2_gemm_f16_ex(const eqv2_gemm16_desc* descs, int ngroups, int 
   P.split_k = split_k;
   P.total_work = tiles * split_k;
   P.passes = passes;
-  static bool attr_set[64] = {};          // the attribute is per device: one flag per device ordinal
+  bool want_cmax = false;
+  for (int i = 0; i < ngroups; ++i) want_cmax = want_cmax || (descs[i].c_absmax != nullptr && split_k == 1);
+  typedef void (*KernelFn)(const HParams);
+  const KernelFn variants[4] = {gemm_f16_kernel<3, false>, gemm_f16_kernel<3, true>, gemm_f16_kernel<1, false>,
+                                gemm_f16_kernel<1, true>};
+  const int vi = (passes == 1 ? 2 : 0) + (want_cmax ? 1 : 0);
+  static bool attr_set[64][4] = {};       // the attribute is per device and per kernel instance
   int dev = 0;
   cudaGetDevice(&dev);
-  if (dev < 0 || dev >= 64 || !attr_set[dev]) {
-    cudaError_t e = cudaFuncSetAttribute(gemm_f16_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_BYTES);
+  if (dev < 0 || dev >= 64 || !attr_set[dev][vi]) {
+    cudaError_t e = cudaFuncSetAttribute(variants[vi], cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_BYTES);
     EQV2_REQUIRE(e == cudaSuccess, "eqv2_gemm_f16: cannot reserve %zu B of shared memory: %s", SMEM_BYTES,
                  cudaGetErrorString(e));
-    if (dev >= 0 && dev < 64) attr_set[dev] = true;
+    if (dev >= 0 && dev < 64) attr_set[dev][vi] = true;
   }
   const int grid = P.total_work < sm_count() ? P.total_work : sm_count();
-  gemm_f16_kernel<<<dim3((unsigned)grid), dim3(NUM_THREADS), SMEM_BYTES, (cudaStream_t)stream>>>(P);
+  variants[vi]<<<dim3((unsigned)grid), dim3(NUM_THREADS), SMEM_BYTES, (cudaStream_t)stream>>>(P);
   EQV2_CHECK_LAUNCH("eqv2_gemm_f16");
   return 0;
 }

@@ -1967,6 +1967,14 @@ class FusedEdgeFeatures:
     def width(self):
         return int(self.src.offset.shape[0]) + (2 * int(self.src_w.shape[1]) if self.src_w is not None else 0)
 
+    def dense(self):
+        """The [E, R + 2 Ce] matrix after all (consumers the fused kernel does not cover)."""
+        rbf_t = RbfFn.apply(self.src.dist, self.src.offset.contiguous(), self.src.coeff)
+        if self.src_w is None:
+            return rbf_t
+        return torch.cat((rbf_t, embed_rows(self.src_w, self.zs, self.csr_s), embed_rows(self.dst_w, self.zd, self.csr_d)),
+                         dim=1)
+
 
 def rbf_source_of(t):
     """The RbfSource behind an rbf tensor if the fused first layer may use it: feature on, CUDA library has the kernels,
