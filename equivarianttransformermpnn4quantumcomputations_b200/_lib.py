@@ -79,7 +79,8 @@ _PROTOS = {
     "eqv2_rbf_bwd": [P, P, P, L, I, P, F, P],
     "eqv2_edge_sh": [P, P, L, I, P],
     "eqv2_rbf_linear_fwd": [P, P, P, P, P, P, P, P, P, L, I, I, F, F, F, I, P],
-    "eqv2_rbf_linear_wgrad": [P, P, P, P, P, P, I, I, F, I, P],
+    "eqv2_rbf_linear_chunk": [],
+    "eqv2_rbf_linear_wgrad": [P, P, P, P, P, P, P, P, P, L, I, I, F, P],
     "eqv2_ln_silu_fwd": [P, P, P, P, L, I, F, P],
     "eqv2_ln_silu_bwd": [P, P, P, P, P, P, P, L, I, F, P],
     "eqv2_graph_ptr": [P, P, I, P],

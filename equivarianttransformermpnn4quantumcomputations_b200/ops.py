@@ -1946,12 +1946,33 @@ class RbfSource:
         self._bins = None
 
     def bins(self):
-        """(perm int32 [E], rowptr int32 [R+1]): edges grouped by nearest basis index -- once per graph, shared by
-        every block's weight gradient."""
+        """Plan of the banded weight gradient (eqv2_rbf_linear_wgrad), built once per graph with device-side torch ops (no
+        read-back) and shared by every block: edges sorted by nearest basis index; per chunk of sorted edges the range of
+        basis functions it can touch and the first row of its partial sums; per basis function the chunks that touch it.
+        -> (perm, chunk_k [nchunks, 2], chunk_base [nchunks], k_chunks [R, 2], partial_rows)"""
         if self._bins is None:
-            R = int(self.offset.shape[0])
+            R, E = int(self.offset.shape[0]), int(self.dist.shape[0])
+            CH = int(_lib.lib().eqv2_rbf_linear_chunk())
+            dev = self.dist.device
             k0 = torch.round((self.dist - self.start) / self.delta).clamp_(0, R - 1).long()
-            self._bins = _csr_few_buckets(k0, R)
+            k0s, perm = torch.sort(k0, stable=True)
+            nchunks = max(1, -(-E // CH))
+            first_i = torch.arange(nchunks, device=dev) * CH
+            last_i = torch.clamp(first_i + CH - 1, max=max(E - 1, 0))
+            if E > 0:
+                kmin = (k0s[first_i] - self.band).clamp_(min=0)
+                kmax = (k0s[last_i] + self.band).clamp_(max=R - 1)
+            else:
+                kmin = torch.zeros(1, dtype=torch.long, device=dev)
+                kmax = torch.full((1,), -1, dtype=torch.long, device=dev)
+            nk = kmax - kmin + 1
+            base = torch.cumsum(nk, 0) - nk
+            ks = torch.arange(R, device=dev)
+            clo = torch.searchsorted(kmax, ks, right=False)
+            chi = torch.searchsorted(kmin, ks, right=True) - 1
+            self._bins = (perm.to(torch.int32), torch.stack([kmin, kmax], 1).to(torch.int32).contiguous(),
+                          base.to(torch.int32), torch.stack([clo, chi], 1).to(torch.int32).contiguous(),
+                          R + nchunks * (2 * self.band + 1))           # upper bound of sum(nk): no device read-back
         return self._bins
 
 
@@ -2014,10 +2035,12 @@ class RbfLinearFn(torch.autograd.Function):
         gh = gh.contiguous()
         gWt = gTs = gTd = gb = None
         if ctx.needs_input_grad[0]:
-            perm, rowptr = src.bins()
+            perm, chunk_k, chunk_base, k_chunks, rows = src.bins()
             gWt = torch.empty(R, H, dtype=_F32, device=gh.device)
+            partial = torch.empty(rows, H, dtype=_F32, device=gh.device)
             _lib.call("eqv2_rbf_linear_wgrad", src.dist.data_ptr(), src.offset.data_ptr(), perm.data_ptr(),
-                      rowptr.data_ptr(), gh.data_ptr(), gWt.data_ptr(), R, H, src.coeff, src.band, _lib.stream_ptr(),
+                      chunk_k.data_ptr(), chunk_base.data_ptr(), k_chunks.data_ptr(), gh.data_ptr(), partial.data_ptr(),
+                      gWt.data_ptr(), int(gh.shape[0]), R, H, src.coeff, _lib.stream_ptr(), n_kernels=2,
                       work=(2.0 * gh.shape[0] * H * (2 * src.band + 1), 4.0 * gh.shape[0] * H))
         if ctx.has[0]:
             V = int(feat.src_w.shape[0])

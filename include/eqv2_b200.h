@@ -274,13 +274,18 @@ int eqv2_seg_colsum(const float* src, long long ld, const int* rowptr, const int
  * evaluated over the 2 band + 1 basis functions nearest to d_e (offset = linspace(start, start + (R-1) delta, R); the
  * neglected terms are < exp(-band^2 / (2 w^2))).  Wt = W1[:, :R]^T [R, H]; Ts / Td [V, H] = embedding tables already
  * multiplied by their weight slices (NULL: no embedding terms).  First order: no gradient w.r.t. d.
- *   eqv2_rbf_linear_wgrad: gWt[k, :] = sum_e rbf_k(d_e) gh[e, :] over the edges whose nearest basis index lies within
- *   `band` of k; perm / rowptr = edges grouped by nearest basis index (R bins), summed in that order (deterministic). */
+ *   eqv2_rbf_linear_wgrad: gWt[k, :] = sum_e rbf_k(d_e) gh[e, :], deterministic, two stages over the edges sorted by nearest
+ *   basis index (perm): chunks of eqv2_rbf_linear_chunk() sorted edges write one partial row per basis function they can
+ *   touch -- chunk_k[2c], chunk_k[2c+1] = that contiguous range, chunk_base[c] = its first row in `partial`
+ *   (sum of the range lengths rows x H floats) -- and every basis function k adds the rows of the chunks
+ *   k_chunks[2k] .. k_chunks[2k+1] that touch it, in chunk order (an empty range: first > last). */
 int eqv2_rbf_linear_fwd(const float* d, const float* offset, const float* Wt, const float* Ts, const float* Td,
                         const long long* zs, const long long* zd, const float* bias, float* out, long long E, int R, int H,
                         float start, float delta, float coeff, int band, void* stream);
-int eqv2_rbf_linear_wgrad(const float* d, const float* offset, const int* perm, const int* rowptr, const float* gh,
-                          float* gWt, int R, int H, float coeff, int band, void* stream);
+int eqv2_rbf_linear_chunk(void);
+int eqv2_rbf_linear_wgrad(const float* d, const float* offset, const int* perm, const int* chunk_k, const int* chunk_base,
+                          const int* k_chunks, const float* gh, float* partial, float* gWt, long long E, int R, int H,
+                          float coeff, void* stream);
 
 /* ---- optimizer-side step (train_oc20v2_parallel.py:95-126,177-186) -----------------------------------
  * Multi-tensor kernels over ONE device table of the model's parameter tensors, processed in chunks of
