@@ -2,9 +2,11 @@
 (reference NewFunctions/Gotennet_morethaninspired/activation.py:166-264, :270-414); the base activations are
 re-exported as the reference fork does.
 
-All Linear layers run on the grouped-GEMM kernels (`ops.linear`, differentiable to any order); the per-degree
-rejections / inner products / gate products are thin torch element-wise expressions between them (they carry
-position gradients through `t_ij`, so they must stay differentiable twice)."""
+All Linear layers run on the grouped-GEMM kernels (`ops.linear`, differentiable to any order); the per-degree vector
+rejections + inner products of HTR and the output assembly of GATAValueActivation are kernels of their own
+(`ops.htr_inner`, `ops.gata_value`, csrc/gata.cu) whose backward passes are kernels again, so the double backward of the
+force loss (they carry position gradients through `t_ij`) never leaves the library.  What stays in torch are the three
+gate products (`gamma_w * gamma_t`, `W_rs(t) * SiLU(gamma_s(h))`, `* phi_proj`)."""
 import torch
 import torch.nn as nn
 import torch.nn.functional as F
@@ -49,15 +51,13 @@ class HTR(nn.Module):
 
     def forward(self, t_ij, X_i, X_j, rl_ij):
         q_all = _lin(self.W_vq, X_i)                                  # one GEMM for all degrees
-        w_ij = None
-        off = 0
+        k_parts, off = [], 0
         for l_idx, n in enumerate(self.degree_sizes):
-            rl_l = rl_ij[:, off:off + n]
-            qi = self.vector_rejection(q_all[:, off:off + n], rl_l)
-            kj = self.vector_rejection(_lin(self.W_vk[l_idx], X_j[:, off:off + n]), -rl_l)
-            term = (qi * kj).sum(dim=1) / n
-            w_ij = term if w_ij is None else w_ij + term
+            k_parts.append(_lin(self.W_vk[l_idx], X_j[:, off:off + n]))
             off += n
+        # sum_l <reject(q^l, r^l), reject(k^l, -r^l)> / (2l+1) in ONE kernel, differentiable to any order through its
+        # gradient-map kernel (ops.HtrInnerFn / HtrGradFn) -- formerly ~10 element-wise / reduction launches per degree
+        w_ij = ops.htr_inner(q_all, torch.cat(k_parts, dim=1), rl_ij.detach(), self.lmax)
         gw = F.silu(_lin(self.gamma_w[0], w_ij))
         gt = F.silu(_lin(self.gamma_t[2], F.silu(_lin(self.gamma_t[0], t_ij))))
         return t_ij + gw * gt
@@ -89,14 +89,7 @@ class GATAValueActivation(nn.Module):
         if phi_r is not None:
             bias = bias * _lin(self.phi_proj, phi_r)
         combined = attn_output + bias
-        chunks = combined.split(C, dim=-1)
-        out = [F.silu(chunks[0]).unsqueeze(1)]
         Xp = _lin(self.xj_proj, X_j)
-        off = 0
-        for l_idx, n in enumerate(self.full_degree_sizes):
-            w = self.reduced_degree_sizes[l_idx]
-            od = chunks[1 + l_idx].unsqueeze(1)
-            ot = chunks[1 + self.lmax + l_idx].unsqueeze(1)
-            out.append(od * rl_ij[:, off:off + w].unsqueeze(-1) + ot * Xp[:, off:off + w])
-            off += n
-        return torch.cat(out, dim=1)
+        # SiLU(o_s) | o_d^l r^l + o_t^l Xp^l on the first min(2l+1, 2 mmax+1) rows of each degree: one kernel per derivative
+        # order (ops.GataValueFn) instead of split / broadcast-multiply / add / cat per degree
+        return ops.gata_value(combined, Xp, rl_ij.detach(), self.lmax, self.mmax)

@@ -96,6 +96,11 @@ _PROTOS = {
     "eqv2_so2_block_weight_adj": [P, P, I, I, P],
     "eqv2_embed_rows": [P, P, P, L, I, P],
     "eqv2_seg_colsum": [P, L, P, P, L, I, I, I, P, P, P],
+    "eqv2_htr_inner": [P, P, P, P, L, I, I, P],
+    "eqv2_htr_grad": [P, P, P, P, L, I, I, P],
+    "eqv2_gata_value_fwd": [P, P, P, P, L, I, I, I, I, P],
+    "eqv2_gata_value_bwd": [P, P, P, P, P, P, L, I, I, I, I, P],
+    "eqv2_gata_value_bwd2": [P, P, P, P, P, P, P, P, P, L, I, I, I, I, P],
     "eqv2_opt_chunk_elems": [],
     "eqv2_grad_sqnorm": [P, P, P, I, F, P, P, P],
     "eqv2_adamw_ema_step": [P, P, P, I, P, F, F, F, I, F, P],

@@ -2068,6 +2068,125 @@ def rbf_linear(feat, W1, b1):
     return RbfLinearFn.apply(Wt, Ts, Td, b1, feat)
 
 
+# ----------------------------------------------------------------------------------------------
+# GATA / HTR per-edge operators (configs 4-5), differentiable twice through kernels only (csrc/gata.cu)
+# ----------------------------------------------------------------------------------------------
+class HtrInnerFn(torch.autograd.Function):
+    """T(q, k; r) [E, H]: the sum over degrees of <reject(q^l, r^l), reject(k^l, -r^l)> / (2l+1)  (HTR, activation.py:
+    166-264).  Bilinear; its gradient map is HtrGradFn, and the pair is closed under differentiation."""
+
+    @staticmethod
+    def forward(ctx, q, k, rl, lmax):
+        _lib.check_device(q, k, rl)
+        assert q.is_contiguous() and k.is_contiguous() and rl.is_contiguous() and q.shape == k.shape
+        E, M, H = q.shape
+        assert M == (lmax + 1) ** 2 - 1 and rl.shape == (E, M)
+        out = torch.empty(E, H, dtype=_F32, device=q.device)
+        _lib.call("eqv2_htr_inner", q.data_ptr(), k.data_ptr(), rl.data_ptr(), out.data_ptr(), E, H, lmax, _lib.stream_ptr(),
+                  work=(8.0 * E * M * H, 4.0 * E * (2 * M * H + H)))
+        ctx.save_for_backward(q, k, rl)
+        ctx.lmax = lmax
+        return out
+
+    @staticmethod
+    def backward(ctx, g):
+        q, k, rl = ctx.saved_tensors
+        g = g.contiguous()
+        dq = HtrGradFn.apply(g, k, rl, ctx.lmax) if ctx.needs_input_grad[0] else None
+        dk = HtrGradFn.apply(g, q, rl, ctx.lmax) if ctx.needs_input_grad[1] else None
+        return dq, dk, None, None
+
+
+class HtrGradFn(torch.autograd.Function):
+    """G(g, b; r) [E, M, H] = g / (2l+1) * (b - (2 - |r^l|^2)(b^l.r^l) r): <u, G(g, b)> = g . T(u, b)."""
+
+    @staticmethod
+    def forward(ctx, g, b, rl, lmax):
+        assert g.is_contiguous() and b.is_contiguous()
+        E, M, H = b.shape
+        out = torch.empty_like(b)
+        _lib.call("eqv2_htr_grad", g.data_ptr(), b.data_ptr(), rl.data_ptr(), out.data_ptr(), E, H, lmax, _lib.stream_ptr(),
+                  work=(6.0 * E * M * H, 4.0 * E * (2 * M * H + H)))
+        ctx.save_for_backward(g, b, rl)
+        ctx.lmax = lmax
+        return out
+
+    @staticmethod
+    def backward(ctx, u):
+        g, b, rl = ctx.saved_tensors
+        u = u.contiguous()
+        dg = HtrInnerFn.apply(u, b, rl, ctx.lmax) if ctx.needs_input_grad[0] else None
+        db = HtrGradFn.apply(g, u, rl, ctx.lmax) if ctx.needs_input_grad[1] else None
+        return dg, db, None, None
+
+
+def htr_inner(q, k, rl, lmax):
+    return HtrInnerFn.apply(q.contiguous(), k.contiguous(), rl.contiguous(), lmax)
+
+
+def gata_rows(lmax, mmax):
+    return 1 + sum(min(2 * l + 1, 2 * mmax + 1) for l in range(1, lmax + 1))
+
+
+class GataValueFn(torch.autograd.Function):
+    """GATAValueActivation's output assembly (activation.py:370-414): SiLU on the scalar row, o_d^l r^l + o_t^l Xp^l on the
+    first min(2l+1, 2 mmax+1) rows of every degree.  One kernel per derivative order (fwd / bwd / bwd-of-bwd)."""
+
+    @staticmethod
+    def forward(ctx, comb, Xp, rl, lmax, mmax):
+        _lib.check_device(comb, Xp, rl)
+        assert comb.is_contiguous() and Xp.is_contiguous() and rl.is_contiguous()
+        E, M, H = Xp.shape
+        assert comb.shape == (E, (1 + 2 * lmax) * H) and rl.shape == (E, M) and M == (lmax + 1) ** 2 - 1
+        Kr = gata_rows(lmax, mmax)
+        out = torch.empty(E, Kr, H, dtype=_F32, device=comb.device)
+        _lib.call("eqv2_gata_value_fwd", comb.data_ptr(), Xp.data_ptr(), rl.data_ptr(), out.data_ptr(), E, H, lmax, mmax, Kr,
+                  _lib.stream_ptr(), work=(4.0 * E * Kr * H, 4.0 * E * H * (1 + 2 * lmax + M + Kr)))
+        ctx.save_for_backward(comb, Xp, rl)
+        ctx.lm = (lmax, mmax)
+        return out
+
+    @staticmethod
+    def backward(ctx, g):
+        comb, Xp, rl = ctx.saved_tensors
+        dcomb, dXp = GataValueBwdFn.apply(comb, Xp, rl, g.contiguous(), *ctx.lm)
+        return dcomb, dXp, None, None, None
+
+
+class GataValueBwdFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, comb, Xp, rl, g, lmax, mmax):
+        assert g.is_contiguous()
+        E, M, H = Xp.shape
+        Kr = gata_rows(lmax, mmax)
+        dcomb, dXp = torch.empty_like(comb), torch.empty_like(Xp)
+        _lib.call("eqv2_gata_value_bwd", comb.data_ptr(), Xp.data_ptr(), rl.data_ptr(), g.data_ptr(), dcomb.data_ptr(),
+                  dXp.data_ptr(), E, H, lmax, mmax, Kr, _lib.stream_ptr(),
+                  work=(4.0 * E * Kr * H, 4.0 * E * H * (2 * (1 + 2 * lmax) + 2 * M + Kr)))
+        ctx.save_for_backward(comb, Xp, rl, g)
+        ctx.lm = (lmax, mmax)
+        return dcomb, dXp
+
+    @staticmethod
+    @torch.autograd.function.once_differentiable
+    def backward(ctx, u, v):
+        comb, Xp, rl, g = ctx.saved_tensors
+        lmax, mmax = ctx.lm
+        E, M, H = Xp.shape
+        Kr = gata_rows(lmax, mmax)
+        u = u.contiguous() if u is not None else None
+        v = v.contiguous() if v is not None else None
+        dg, d2comb, d2Xp = torch.empty_like(g), torch.empty_like(comb), torch.empty_like(Xp)
+        _lib.call("eqv2_gata_value_bwd2", comb.data_ptr(), Xp.data_ptr(), rl.data_ptr(), g.data_ptr(), _lib.ptr(u),
+                  _lib.ptr(v), dg.data_ptr(), d2comb.data_ptr(), d2Xp.data_ptr(), E, H, lmax, mmax, Kr, _lib.stream_ptr(),
+                  work=(8.0 * E * Kr * H, 4.0 * E * H * (3 * (1 + 2 * lmax) + 3 * M + 2 * Kr)))
+        return d2comb, d2Xp, None, dg, None, None
+
+
+def gata_value(comb, Xp, rl, lmax, mmax):
+    return GataValueFn.apply(comb.contiguous(), Xp.contiguous(), rl.contiguous(), lmax, mmax)
+
+
 def gather_rotate(x, rad, plan, wig, lmax, mmax):
     return GatherRotateFn.apply(x.contiguous(), rad.contiguous() if rad is not None else None, plan, wig, lmax, mmax)
 

@@ -287,6 +287,25 @@ int eqv2_rbf_linear_wgrad(const float* d, const float* offset, const int* perm, 
                           const int* k_chunks, const float* gh, float* partial, float* gWt, long long E, int R, int H,
                           float coeff, void* stream);
 
+/* ---- GATA / HTR per-edge operators (BASELINE configs 4-5; NewFunctions/Gotennet_morethaninspired/activation.py) ----
+ * HTR (:166-264): T(q, k; r)[e,c] = sum_{l>=1} [ q^l.k^l - (2 - |r^l|^2)(q^l.r^l)(k^l.r^l) ] / (2l+1)  -- the inner product of the
+ *   two vector rejections -- and its gradient map G(g, b; r)[e,m,c] = g[e,c]/(2l+1) (b - (2 - |r^l|^2)(b^l.r^l) r)[e,m,c];
+ *   q, k, b, G: [E, M, H] with M = (lmax+1)^2 - 1 rows (l = 1..lmax), r: [E, M] (detached), T, g: [E, H].
+ *   {T, G} is closed under differentiation (dT/dq = G(g,k), dT/dk = G(g,q), dG/dg = T(u,b), dG/db = G(g,u)).
+ * GATAValueActivation (:270-414): comb [E, (1 + 2 lmax) H] = (o_s | o_d^l | o_t^l), Xp [E, M, H] ->
+ *   out [E, Kr, H]: row 0 = SiLU(o_s); degree l rows m < min(2l+1, 2 mmax+1): o_d^l r[off_l+m] + o_t^l Xp[off_l+m]
+ *   (Kr = 1 + sum_l min(2l+1, 2 mmax+1), l-primary).  bwd: g -> (d_comb, d_Xp); bwd2: cotangents u (of d_comb, may be
+ *   NULL), v (of d_Xp, may be NULL) -> (d_g, d2_comb, d2_Xp). */
+int eqv2_htr_inner(const float* q, const float* k, const float* rl, float* out, long long E, int H, int lmax, void* stream);
+int eqv2_htr_grad(const float* g, const float* b, const float* rl, float* out, long long E, int H, int lmax, void* stream);
+int eqv2_gata_value_fwd(const float* comb, const float* Xp, const float* rl, float* out, long long E, int H, int lmax,
+                        int mmax, int Kr, void* stream);
+int eqv2_gata_value_bwd(const float* comb, const float* Xp, const float* rl, const float* g, float* dcomb, float* dXp,
+                        long long E, int H, int lmax, int mmax, int Kr, void* stream);
+int eqv2_gata_value_bwd2(const float* comb, const float* Xp, const float* rl, const float* g, const float* u,
+                         const float* v, float* dg, float* d2comb, float* d2Xp, long long E, int H, int lmax, int mmax,
+                         int Kr, void* stream);
+
 /* ---- optimizer-side step (train_oc20v2_parallel.py:95-126,177-186) -----------------------------------
  * Multi-tensor kernels over ONE device table of the model's parameter tensors, processed in chunks of
  * eqv2_opt_chunk_elems() elements: chunk c covers elements [chunk_index[c] * chunk, ...) of tensors[chunk_tensor[c]].
