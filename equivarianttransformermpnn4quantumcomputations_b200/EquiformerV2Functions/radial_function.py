@@ -17,9 +17,17 @@ class RadialFunction(nn.Module):
                 mods.append(nn.SiLU())
         self.net = nn.Sequential(*mods)
 
-    def forward(self, inputs):
-        x = inputs
+    def hidden_and_last(self, inputs):
+        """(activations entering the last Linear, that Linear): lets the graph-attention block fuse the output layer with
+        the kernels that consume the radial weights (ops.GatherRotateConvFn)."""
         mods = list(self.net)
+        return self._run(inputs, mods[:-1]), mods[-1]
+
+    def forward(self, inputs):
+        return self._run(inputs, list(self.net))
+
+    def _run(self, inputs, mods):
+        x = inputs
         i = 0
         while i < len(mods):
             lin = mods[i]

@@ -128,13 +128,23 @@ class SO2EquivariantGraphAttention(nn.Module):
             raise RuntimeError("SO3_Rotation.set_wigner must be called with this graph's edge frames first")
 
         x_edge = edge_scalar_features(self, atomic_numbers, edge_distance, edge_index)
-        rad = self.so2_conv_1.radial_weights(x_edge)                          # [E, n_rad]
         second_order = torch.is_grad_enabled() and edge_distance.requires_grad
-        if not second_order and ops.fused_planes_available(emb, rad, lay.Kr * 2 * self.sphere_channels):
-            # f16 engine, step differentiated once: the rotated / modulated rows exist only as the GEMM's operand planes
-            groups, weights = self.so2_conv_1.groups_and_weights()
-            Y = ops.gather_rotate_conv(emb, rad, self.so2_conv_1.fc_m0.bias, plan, wig, lmax, mmax, groups, weights)
+        Y = None
+        rad_func = self.so2_conv_1.rad_func
+        if not second_order and rad_func is not None:
+            h, last = rad_func.hidden_and_last(x_edge)                        # radial MLP up to its output layer
+            if torch.is_tensor(h) and ops.fused_planes_available(emb, h, last.weight, lay.Kr * 2 * self.sphere_channels):
+                # f16 engine, step differentiated once: the radial output layer, the gather / rotate / modulation and the
+                # convolution run as one Function -- the rotated rows and the gradient of the radial weights exist only
+                # as GEMM operand planes (ops.GatherRotateConvFn)
+                groups, weights = self.so2_conv_1.groups_and_weights()
+                Y = ops.gather_rotate_conv(emb, h, last.weight, last.bias, self.so2_conv_1.fc_m0.bias, plan, wig, lmax,
+                                           mmax, groups, weights)
+            else:
+                rad = ops.linear(h, last.weight, last.bias) if torch.is_tensor(h) else rad_func(x_edge)
         else:
+            rad = self.so2_conv_1.radial_weights(x_edge)                      # [E, n_rad]
+        if Y is None:
             A = ops.gather_rotate(emb, rad, plan, wig, lmax, mmax)     # [E, Kr*2C]  m-primary
             Y = self.so2_conv_1.conv_m_primary(A)                             # [E, h*a + H + Kr*H]
         mats = self.SO3_grid[lmax][mmax].kernel_mats("m")

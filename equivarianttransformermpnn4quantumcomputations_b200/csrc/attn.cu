@@ -108,12 +108,13 @@ __global__ void attn_logits_bwd_kernel(const float* __restrict__ Y, long long y_
                                        const float* __restrict__ ln_b, const float* __restrict__ alpha_dot,
                                        const float* __restrict__ dlogits, float* __restrict__ dY, long long dy_rs,
                                        float* __restrict__ d_ln_w, float* __restrict__ d_ln_b,
-                                       float* __restrict__ d_alpha_dot, long long E, int heads, int ach, float eps) {
+                                       float* __restrict__ d_alpha_dot, long long E, int heads, int ach, float eps, float* __restrict__ absmax) {
   const int lane = threadIdx.x & 31;
   const long long warp = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const long long nwarps = ((long long)gridDim.x * blockDim.x) >> 5;   // multiple of heads (host guarantees)
   const int h = (int)(warp % heads);
   float gw[MAXPL], gb[MAXPL], gd[MAXPL];
+  float amax = 0.f;
 #pragma unroll
   for (int k = 0; k < MAXPL; ++k) gw[k] = gb[k] = gd[k] = 0.f;
   for (long long e = warp / heads; e < E; e += nwarps / heads) {
@@ -173,9 +174,14 @@ __global__ void attn_logits_bwd_kernel(const float* __restrict__ Y, long long y_
 #pragma unroll
     for (int k = 0; k < MAXPL; ++k) {
       const int i = lane + 32 * k;
-      if (i < ach) dp[i] = ln_w ? rstd * (dxh[k] - s1 - xh[k] * s2) : dxh[k];
+      if (i < ach) {
+        const float o = ln_w ? rstd * (dxh[k] - s1 - xh[k] * s2) : dxh[k];
+        dp[i] = o;
+        amax = fmaxf(amax, fabsf(o));
+      }
     }
   }
+  if (absmax != nullptr) eqv2_commit_absmax(amax, absmax);    // max |dY| (operand scale of the consuming GEMM)
 #pragma unroll
   for (int k = 0; k < MAXPL; ++k) {
     const int i = lane + 32 * k;
@@ -213,7 +219,7 @@ extern "C" int eqv2_attn_alpha_bwd(const float* Y, long long y_rs, const float* 
                                    const float* alpha_dot, const int* rowptr_dst, const int* perm_dst,
                                    const float* alpha, const float* dalpha, float* dlogits, float* dY, long long dy_rs,
                                    float* d_ln_w, float* d_ln_b, float* d_alpha_dot, long long E, long long N,
-                                   int heads, int ach, float eps, void* stream) {
+                                   int heads, int ach, float eps, float* absmax, void* stream) {
   if (E == 0 || N == 0) return 0;
   EQV2_REQUIRE(ach > 0 && ach <= 32 * MAXPL, "attn_alpha_bwd: alpha channels %d > %d", ach, 32 * MAXPL);
   const long long t = N * heads;
@@ -225,7 +231,7 @@ extern "C" int eqv2_attn_alpha_bwd(const float* Y, long long y_rs, const float* 
   if (want > 148 * 8) want = 148 * 8;
   long long blocks = ((want * wpb + heads - 1) / heads * heads + wpb - 1) / wpb;
   while ((blocks * wpb) % heads != 0) ++blocks;
-  EQV2_LAUNCH(attn_logits_bwd_kernel, dim3((unsigned)blocks), dim3(wpb * 32), 0, stream, Y, y_rs, ln_w, ln_b, alpha_dot, dlogits, dY, dy_rs, d_ln_w, d_ln_b, d_alpha_dot, E, heads, ach, eps);
+  EQV2_LAUNCH(attn_logits_bwd_kernel, dim3((unsigned)blocks), dim3(wpb * 32), 0, stream, Y, y_rs, ln_w, ln_b, alpha_dot, dlogits, dY, dy_rs, d_ln_w, d_ln_b, d_alpha_dot, E, heads, ach, eps, absmax);
   EQV2_CHECK_LAUNCH("eqv2_attn_alpha_bwd/logits");
   return 0;
 }

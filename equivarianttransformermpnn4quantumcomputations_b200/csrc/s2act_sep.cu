@@ -91,10 +91,11 @@ __device__ __forceinline__ void lat_bwd(float (&o)[KrOf<L, M>::value()], const f
 template <int L, int M, bool MP>
 __global__ void __launch_bounds__(S2_THREADS)
 s2sep_fwd_kernel(const float* __restrict__ X, long long x_rs, const float* __restrict__ gate, long long g_rs,
-                 float* __restrict__ O, long long o_rs, long long R, int C, int slot) {
+                 float* __restrict__ O, long long o_rs, long long R, int C, int slot, float* __restrict__ absmax) {
   constexpr int Kr = KrOf<L, M>::value();
   const S2Tables& T = g_tab[slot];
   const long long total = R * C;
+  float amax = 0.f;          // max |O| of what this thread writes (operand scale of the GEMM that consumes O)
   for (long long w = (long long)blockIdx.x * blockDim.x + threadIdx.x; w < total; w += (long long)gridDim.x * blockDim.x) {
     const long long r = w / C;
     const int c = (int)(w % C);
@@ -127,18 +128,23 @@ s2sep_fwd_kernel(const float* __restrict__ X, long long x_rs, const float* __res
     }
     if (gate != nullptr) o[0] = eqv2_silu(__ldg(gate + r * g_rs + c));
 #pragma unroll
-    for (int p = 0; p < Kr; ++p) O[r * o_rs + (long long)p * C + c] = o[p];
+    for (int p = 0; p < Kr; ++p) {
+      O[r * o_rs + (long long)p * C + c] = o[p];
+      amax = fmaxf(amax, fabsf(o[p]));
+    }
   }
+  if (absmax != nullptr) eqv2_commit_absmax(amax, absmax);
 }
 
 template <int L, int M, bool MP>
 __global__ void __launch_bounds__(S2_THREADS)
 s2sep_bwd_kernel(const float* __restrict__ X, long long x_rs, const float* __restrict__ gate, long long g_rs,
                  const float* __restrict__ dO, long long o_rs, float* __restrict__ dX, long long dx_rs,
-                 float* __restrict__ dgate, long long dg_rs, long long R, int C, int slot) {
+                 float* __restrict__ dgate, long long dg_rs, long long R, int C, int slot, float* __restrict__ absmax) {
   constexpr int Kr = KrOf<L, M>::value();
   const S2Tables& T = g_tab[slot];
   const long long total = R * C;
+  float amax = 0.f;          // max |dX|, |dgate| of what this thread writes
   for (long long w = (long long)blockIdx.x * blockDim.x + threadIdx.x; w < total; w += (long long)gridDim.x * blockDim.x) {
     const long long r = w / C;
     const int c = (int)(w % C);
@@ -176,12 +182,18 @@ s2sep_bwd_kernel(const float* __restrict__ X, long long x_rs, const float* __res
       lat_bwd<L, M, MP>(dx, T.Pt, b, wp, wn);
     }
 #pragma unroll
-    for (int p = 0; p < Kr; ++p) dX[r * dx_rs + (long long)p * C + c] = dx[p];
+    for (int p = 0; p < Kr; ++p) {
+      dX[r * dx_rs + (long long)p * C + c] = dx[p];
+      amax = fmaxf(amax, fabsf(dx[p]));
+    }
     if (gate != nullptr) {
       const float gv = __ldg(gate + r * g_rs + c);
-      dgate[r * dg_rs + c] = __ldg(dO + r * o_rs + c) * eqv2_dsilu(gv);
+      const float dg = __ldg(dO + r * o_rs + c) * eqv2_dsilu(gv);
+      dgate[r * dg_rs + c] = dg;
+      amax = fmaxf(amax, fabsf(dg));
     }
   }
+  if (absmax != nullptr) eqv2_commit_absmax(amax, absmax);
 }
 
 // d/dz of SiLU'(z):  s (1 - s) (2 + z (1 - 2 s))
@@ -297,13 +309,14 @@ extern "C" int eqv2_s2sep_set_tables(const float* host_tables, int nfloats, int 
 }
 
 extern "C" int eqv2_s2sep_fwd(const float* Xp, long long x_rs, const float* gate, long long g_rs, float* O, long long o_rs,
-                              long long R, int C, int lmax, int mmax, int m_primary, int slot, void* stream) {
+                              long long R, int C, int lmax, int mmax, int m_primary, int slot, float* absmax,
+                              void* stream) {
   if (R == 0) return 0;
   const unsigned blocks = s2_grid_blocks(R * C);
 #define X(L_, M_)                                                                                                        \
   if (lmax == L_ && mmax == M_) {                                                                                        \
     auto kfn = m_primary ? s2sep_fwd_kernel<L_, M_, true> : s2sep_fwd_kernel<L_, M_, false>;                             \
-    EQV2_LAUNCH(kfn, dim3(blocks), dim3(S2_THREADS), 0, stream, Xp, x_rs, gate, g_rs, O, o_rs, R, C, slot);               \
+    EQV2_LAUNCH(kfn, dim3(blocks), dim3(S2_THREADS), 0, stream, Xp, x_rs, gate, g_rs, O, o_rs, R, C, slot, absmax);       \
     EQV2_CHECK_LAUNCH("eqv2_s2sep_fwd");                                                                                 \
     return 0;                                                                                                            \
   }
@@ -315,13 +328,13 @@ extern "C" int eqv2_s2sep_fwd(const float* Xp, long long x_rs, const float* gate
 
 extern "C" int eqv2_s2sep_bwd(const float* Xp, long long x_rs, const float* gate, long long g_rs, const float* dO,
                               long long o_rs, float* dX, long long dx_rs, float* dgate, long long dg_rs, long long R, int C,
-                              int lmax, int mmax, int m_primary, int slot, void* stream) {
+                              int lmax, int mmax, int m_primary, int slot, float* absmax, void* stream) {
   if (R == 0) return 0;
   const unsigned blocks = s2_grid_blocks(R * C);
 #define X(L_, M_)                                                                                                        \
   if (lmax == L_ && mmax == M_) {                                                                                        \
     auto kfn = m_primary ? s2sep_bwd_kernel<L_, M_, true> : s2sep_bwd_kernel<L_, M_, false>;                             \
-    EQV2_LAUNCH(kfn, dim3(blocks), dim3(S2_THREADS), 0, stream, Xp, x_rs, gate, g_rs, dO, o_rs, dX, dx_rs, dgate, dg_rs, R, C, slot); \
+    EQV2_LAUNCH(kfn, dim3(blocks), dim3(S2_THREADS), 0, stream, Xp, x_rs, gate, g_rs, dO, o_rs, dX, dx_rs, dgate, dg_rs, R, C, slot, absmax); \
     EQV2_CHECK_LAUNCH("eqv2_s2sep_bwd");                                                                                 \
     return 0;                                                                                                            \
   }

@@ -1318,58 +1318,105 @@ def _planes_for(rows, cols, device):
     return ref, SplitF16(OperandSrc(ref, rows, cols))
 
 
-def fused_planes_available(x, rad, cols):
-    """Can gather_rotate write conv1's A operand as planes?  f16 engine, whole warps of channels, both input maxima known."""
-    return (_FEATURES["planes"] and _GEMM_MODE["mode"] in ("f16x3", "f16") and rad is not None and cols % 8 == 0
-            and (2 * x.shape[2]) % 32 == 0 and (2 * x.shape[2]) % min(256, 2 * x.shape[2]) == 0 and x.is_cuda
-            and hasattr(_lib.lib(), "eqv2_gather_rotate_fwd_planes")
-            and _known_absmax(x) is not None and _known_absmax(rad) is not None)
+def fused_planes_available(x, h, W3, cols):
+    """Can gather_rotate write conv1's A operand as planes?  f16 engine, whole warps of channels, the maximum of x known,
+    and the radial output layer large enough to run on the f16 engine (its epilogue then supplies the maximum of rad)."""
+    if not (_FEATURES["planes"] and _GEMM_MODE["mode"] in ("f16x3", "f16") and cols % 8 == 0 and x.is_cuda
+            and (2 * x.shape[2]) % 32 == 0 and (2 * x.shape[2]) % min(256, 2 * x.shape[2]) == 0
+            and hasattr(_lib.lib(), "eqv2_gather_rotate_fwd_planes") and _known_absmax(x) is not None):
+        return False
+    E, k3 = h.shape
+    nrad = W3.shape[0]
+    return (h.dtype == _F32 and W3.dtype == _F32 and k3 % 8 == 0 and nrad % 8 == 0 and _FEATURES["c_absmax"]
+            and E * nrad * k3 >= F16_MIN_MACS and E > 0)
 
 
 class GatherRotateConvFn(torch.autograd.Function):
-    """gather x[src]|x[dst] + Wigner rotate + radial modulation (transformer_block.py:250-275, so2_ops.py:142-175) ->
-    first SO(2) convolution (so2_ops.py:150-185) with the intermediate [E, Kr*2C] tensor living only as the GEMM's
-    fp16 operand planes: written once by `eqv2_gather_rotate_fwd_planes`, read by the forward GEMM and again by the
-    weight-gradient GEMM.  Backward: dgrad + wgrad GEMMs, then the dx / drad kernels on the fp32 dgrad output."""
+    """last radial-MLP layer (radial_function.py:29) -> gather x[src]|x[dst] + Wigner rotate + radial modulation
+    (transformer_block.py:250-275, so2_ops.py:142-175) -> first SO(2) convolution (so2_ops.py:150-185), with the two big
+    per-edge intermediates living only as GEMM operand planes:
+      * the rotated / modulated rows [E, Kr*2C]: written once by `eqv2_gather_rotate_fwd_planes`, read by the forward GEMM
+        and again by the weight-gradient GEMM;
+      * the gradient of the radial weights [E, n_rad]: written by `eqv2_gather_rotate_drad_planes`, read by the radial
+        layer's dgrad / wgrad GEMMs and (for its bias gradient) by `eqv2_planes_colsum`.
+    Backward: dgrad + wgrad GEMMs of the convolution, the dx kernel on the fp32 dgrad output, then the radial layer's two
+    GEMMs.  Bounds come from the registered maxima of x (norm kernel), rad and dA (GEMM epilogues)."""
 
     @staticmethod
-    def forward(ctx, x, rad, bias0, plan, wig, lmax, mmax, groups, *Ws):
-        _lib.check_device(x, rad, wig, bias0, *Ws)
-        assert x.is_contiguous() and rad.is_contiguous() and all(w.is_contiguous() for w in Ws)
+    def forward(ctx, x, h, W3, b3, bias0, plan, wig, lmax, mmax, groups, *Ws):
+        _lib.check_device(x, h, W3, b3, wig, bias0, *Ws)
+        assert x.is_contiguous() and h.is_contiguous() and W3.is_contiguous() and all(w.is_contiguous() for w in Ws)
         lay = CoeffLayout.get(lmax, mmax)
         N, K, C = x.shape
         E, cols, nrad = plan.E, lay.Kr * 2 * C, lay.nslot * 2 * C
-        assert rad.shape == (E, nrad), (rad.shape, E, nrad)
+        assert W3.shape == (nrad, h.shape[1]) and h.shape[0] == E, (W3.shape, h.shape, E, nrad)
+        rad, rsplits = _slice_mm(h, b3, ((0, h.shape[1]),), ((0, nrad),), nrad, True, [W3])
+        bx, brad = _known_absmax(x), _known_absmax(rad)
+        assert bx is not None and brad is not None, "GatherRotateConvFn needs the registered maxima of x and rad"
         ref, spA = _planes_for(E, cols, x.device)
         _lib.call("eqv2_gather_rotate_fwd_planes", x.data_ptr(), plan.src.data_ptr(), plan.dst.data_ptr(), wig.data_ptr(),
-                  rad.data_ptr(), spA.buf.data_ptr(), spA.plane, spA.cols_pad, _known_absmax(x).data_ptr(),
-                  _known_absmax(rad).data_ptr(), spA.absmax.data_ptr(), E, C, lmax, mmax, lay.Kr, nrad, _lib.stream_ptr(),
+                  rad.data_ptr(), spA.buf.data_ptr(), spA.plane, spA.cols_pad, bx.data_ptr(), brad.data_ptr(),
+                  spA.absmax.data_ptr(), E, C, lmax, mmax, lay.Kr, nrad, _lib.stream_ptr(),
                   work=_rot_work(lay, E, N, 2 * C, C, nrad + wig.shape[1] + lay.Kr * C))      # planes: 2 x 2 B per value
         xs = tuple((a_off, k_g) for a_off, k_g, _, _ in groups)
         ys = tuple((c_off, n_g) for _, _, c_off, n_g in groups)
         width = sum(n for _, n in ys)
         with split_scope([(ref, spA)]):
             Y, splits = _slice_mm(ref, bias0, xs, ys, width, True, Ws)
-        ctx.save_for_backward(x, rad, wig, *Ws)
-        ctx.plan, ctx.lm, ctx.spec = plan, (lmax, mmax), (xs, ys, width, bias0 is not None)
-        ctx.ref, ctx.spA, ctx.wsplits = ref, spA, splits[1:]
+        ctx.save_for_backward(x, h, W3, rad, wig, *Ws)
+        ctx.plan, ctx.lm, ctx.spec = plan, (lmax, mmax), (xs, ys, width, bias0 is not None, b3 is not None)
+        ctx.ref, ctx.spA, ctx.wsplits, ctx.rsplits = ref, spA, splits[1:], rsplits
         return Y
 
     @staticmethod
     @torch.autograd.function.once_differentiable
     def backward(ctx, gY):
-        x, rad, wig, *Ws = ctx.saved_tensors
-        xs, ys, width, has_bias = ctx.spec
+        x, h, W3, rad, wig, *Ws = ctx.saved_tensors
+        xs, ys, width, has_bias, has_b3 = ctx.spec
         plan, (lmax, mmax) = ctx.plan, ctx.lm
+        lay = CoeffLayout.get(lmax, mmax)
+        N, K, C = x.shape
+        E, nrad = plan.E, rad.shape[1]
         gY = gY.contiguous()
-        need_w = any(ctx.needs_input_grad[8:])
+        need_w = any(ctx.needs_input_grad[11:])
         with split_scope([(ctx.ref, ctx.spA)] + list(zip(Ws, ctx.wsplits))):     # gY is split once for both products
             gA, _ = _slice_mm(gY, None, ys, xs, ctx.ref.shape[1], False, Ws)
             gWs = _slice_outer(gY, ctx.ref, ys, xs)[0] if need_w else [None] * len(Ws)
-        gx, grad = _gr_bwd(x, rad, gA, plan, wig, lmax, mmax, want_dx=ctx.needs_input_grad[0],
-                           want_drad=ctx.needs_input_grad[1])
-        gb = colsum(gY, ys[0][0], ys[0][1]) if (has_bias and ctx.needs_input_grad[2]) else None
-        return (gx, grad, gb, None, None, None, None, None, *gWs)
+        gb = colsum(gY, ys[0][0], ys[0][1]) if (has_bias and ctx.needs_input_grad[4]) else None
+        gx = None
+        if ctx.needs_input_grad[0]:
+            gx, _ = _gr_bwd(x, rad, gA, plan, wig, lmax, mmax, want_dx=True, want_drad=False)
+        gh = gW3 = gb3 = None
+        if any(ctx.needs_input_grad[1:4]):
+            bx, bg = _known_absmax(x), _known_absmax(gA)
+            k3 = h.shape[1]
+            scope = list(zip([h, W3], ctx.rsplits))
+            if (bx is not None and bg is not None and _FEATURES["planes"] and nrad % 8 == 0 and
+                    hasattr(_lib.lib(), "eqv2_gather_rotate_drad_planes")):
+                dref, spD = _planes_for(E, nrad, x.device)
+                _lib.call("eqv2_gather_rotate_drad_planes", x.data_ptr(), plan.src.data_ptr(), plan.dst.data_ptr(),
+                          wig.data_ptr(), gA.data_ptr(), spD.buf.data_ptr(), spD.plane, spD.cols_pad, bx.data_ptr(),
+                          bg.data_ptr(), spD.absmax.data_ptr(), E, C, lmax, mmax, lay.Kr, nrad, _lib.stream_ptr(),
+                          work=_rot_work(lay, E, N, 2 * C, C, nrad // 2 + wig.shape[1] + lay.Kr * 2 * C))
+                d_op = dref
+                scope.append((dref, spD))
+                if has_b3 and ctx.needs_input_grad[3]:
+                    S = max(1, min(E // 16, -(-2368 // ((nrad + 127) // 128))))
+                    partial = torch.empty(S * nrad, dtype=_F32, device=x.device)
+                    gb3 = torch.empty(nrad, dtype=_F32, device=x.device)
+                    _lib.call("eqv2_planes_colsum", spD.buf.data_ptr(), spD.plane, spD.cols_pad, 0, E, nrad, S,
+                              spD.absmax.data_ptr(), partial.data_ptr(), gb3.data_ptr(), _lib.stream_ptr(), n_kernels=2,
+                              work=(0.0, 4.0 * E * nrad))
+            else:
+                _, d_op = _gr_bwd(x, rad, gA, plan, wig, lmax, mmax, want_dx=False, want_drad=True)
+                if has_b3 and ctx.needs_input_grad[3]:
+                    gb3 = colsum(d_op, 0, nrad)
+            with split_scope(scope):
+                if ctx.needs_input_grad[1]:
+                    gh, _ = _slice_mm(d_op, None, ((0, nrad),), ((0, k3),), k3, False, [W3])
+                if ctx.needs_input_grad[2]:
+                    gW3 = _slice_outer(d_op, h, ((0, nrad),), ((0, k3),))[0][0]
+        return (gx, gh, gW3, gb3, gb, None, None, None, None, None, *gWs)
 
 
 class ConvRotInvReduceFn(torch.autograd.Function):
@@ -1452,9 +1499,9 @@ class ConvRotInvReduceFn(torch.autograd.Function):
         return (gZ, galpha, gb, None, None, None, None, None, None, None, *gWs)
 
 
-def gather_rotate_conv(x, rad, bias0, plan, wig, lmax, mmax, groups, weights):
-    return GatherRotateConvFn.apply(x.contiguous(), rad.contiguous(), bias0, plan, wig, lmax, mmax, groups,
-                                    *[w.contiguous() for w in weights])
+def gather_rotate_conv(x, h, W3, b3, bias0, plan, wig, lmax, mmax, groups, weights):
+    return GatherRotateConvFn.apply(x.contiguous(), h.contiguous(), W3.contiguous(), b3, bias0, plan, wig, lmax, mmax,
+                                    groups, *[w.contiguous() for w in weights])
 
 
 def conv_rotinv_reduce(Zm, alpha, bias0, plan, wig, lmax, mmax, heads, alpha_bound, groups, weights):
@@ -1554,21 +1601,23 @@ def _s2_work(mats, R, C, passes):
     return (2.0 * R * C * macs * passes, 4.0 * R * C * (mats.Kr + 1) * (1 + passes // 2))
 
 
-def _s2_fwd(mats, xp, x_rs, gp, g_rs, op, o_rs, R, C, device):
+def _s2_fwd(mats, xp, x_rs, gp, g_rs, op, o_rs, R, C, device, absmax=None):
     if mats.factors is not None:
         slot = _s2_bind_tables(mats, device)
         _lib.call("eqv2_s2sep_fwd", xp, x_rs, gp, g_rs, op, o_rs, R, C, mats.lmax, mats.mmax, int(mats.order == "m"), slot,
-                  _lib.stream_ptr(), work=_s2_work(mats, R, C, 2))
+                  _lib.ptr(absmax), _lib.stream_ptr(), work=_s2_work(mats, R, C, 2))
+        return absmax
     else:
         _lib.call("eqv2_s2act_fwd", xp, x_rs, gp, g_rs, op, o_rs, mats.T.data_ptr(), mats.F.data_ptr(), R, C, mats.Kr,
                   mats.KP, mats.G, _s2_blocks(R, C), _lib.stream_ptr())
 
 
-def _s2_bwd(mats, xp, x_rs, gp, g_rs, dop, o_rs, dxp, dx_rs, dgp, dg_rs, R, C, device):
+def _s2_bwd(mats, xp, x_rs, gp, g_rs, dop, o_rs, dxp, dx_rs, dgp, dg_rs, R, C, device, absmax=None):
     if mats.factors is not None:
         slot = _s2_bind_tables(mats, device)
         _lib.call("eqv2_s2sep_bwd", xp, x_rs, gp, g_rs, dop, o_rs, dxp, dx_rs, dgp, dg_rs, R, C, mats.lmax, mats.mmax,
-                  int(mats.order == "m"), slot, _lib.stream_ptr(), work=_s2_work(mats, R, C, 4))
+                  int(mats.order == "m"), slot, _lib.ptr(absmax), _lib.stream_ptr(), work=_s2_work(mats, R, C, 4))
+        return absmax
     else:
         _lib.call("eqv2_s2act_bwd", xp, x_rs, gp, g_rs, dop, o_rs, dxp, dx_rs, dgp, dg_rs, mats.T.data_ptr(),
                   mats.F.data_ptr(), R, C, mats.Kr, mats.KP, mats.G, _s2_blocks(R, C), _lib.stream_ptr())
@@ -1659,7 +1708,10 @@ class EdgeActAlphaFn(torch.autograd.Function):
         assert W == extra + Kr * H
         Z = torch.empty(E, Kr * H, dtype=_F32, device=Y.device)
         yp = Y.data_ptr()
-        _s2_fwd(mats, yp + 4 * extra, W, yp + 4 * heads * ach, W, Z.data_ptr(), Kr * H, E, H, Y.device)
+        # max |Z| is reduced while Z is written: the operand split of the second convolution skips its absmax pass
+        zslot = _s2_fwd(mats, yp + 4 * extra, W, yp + 4 * heads * ach, W, Z.data_ptr(), Kr * H, E, H, Y.device,
+                        absmax=_absmax_slot(Y.device))
+        _register_absmax(Z, zslot)
         logits = torch.empty(E, heads, dtype=_F32, device=Y.device)
         alpha = torch.empty(E, heads, dtype=_F32, device=Y.device)
         ln_w_c = ln_w.contiguous() if ln_w is not None else None
@@ -1687,8 +1739,9 @@ class EdgeActAlphaFn(torch.autograd.Function):
         if gZ is None:
             gZ = torch.zeros(E, Kr * H, dtype=_F32, device=dev)
         gZ = gZ.contiguous()
-        _s2_bwd(mats, yp + 4 * extra, W, yp + 4 * heads * ach, W, gZ.data_ptr(), Kr * H, gp + 4 * extra, W,
-                gp + 4 * heads * ach, W, E, H, dev)
+        # the S2 backward and the attention backward fill disjoint column ranges of gY and reduce max |gY| into ONE slot
+        gslot = _s2_bwd(mats, yp + 4 * extra, W, yp + 4 * heads * ach, W, gZ.data_ptr(), Kr * H, gp + 4 * extra, W,
+                        gp + 4 * heads * ach, W, E, H, dev, absmax=_absmax_slot(dev))
         if galpha is None:
             galpha = torch.zeros_like(alpha)
         galpha = galpha.contiguous()
@@ -1699,7 +1752,8 @@ class EdgeActAlphaFn(torch.autograd.Function):
         _lib.call("eqv2_attn_alpha_bwd", yp, W, _lib.ptr(ln_w), _lib.ptr(ln_b), alpha_dot.data_ptr(),
                   plan.rowptr_dst.data_ptr(), plan.perm_dst.data_ptr(), alpha.data_ptr(), galpha.data_ptr(),
                   dlogits.data_ptr(), gp, W, _lib.ptr(g_lnw), _lib.ptr(g_lnb), g_dot.data_ptr(), E, plan.N, heads,
-                  ach, 1e-5, _lib.stream_ptr(), n_kernels=2)
+                  ach, 1e-5, _lib.ptr(gslot), _lib.stream_ptr(), n_kernels=2)
+        _register_absmax(gY, gslot)
         return gY, g_lnw, g_lnb, g_dot, None, None, None, None, None
 
 
@@ -1780,7 +1834,7 @@ class AttnAlphaFn(torch.autograd.Function):
         _lib.call("eqv2_attn_alpha_bwd", Ya.data_ptr(), heads * ach, _lib.ptr(ln_w), _lib.ptr(ln_b), alpha_dot.data_ptr(),
                   plan.rowptr_dst.data_ptr(), plan.perm_dst.data_ptr(), alpha.data_ptr(), galpha.data_ptr(),
                   dlogits.data_ptr(), gY.data_ptr(), heads * ach, _lib.ptr(g_lnw), _lib.ptr(g_lnb), g_dot.data_ptr(),
-                  E, plan.N, heads, ach, 1e-5, _lib.stream_ptr(), n_kernels=2)
+                  E, plan.N, heads, ach, 1e-5, None, _lib.stream_ptr(), n_kernels=2)
         return gY, g_lnw, g_lnb, g_dot, None, None, None
 
 

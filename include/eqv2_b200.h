@@ -177,10 +177,11 @@ int eqv2_s2act_bwd(const float* X, long long x_rs, const float* gate, long long 
 int eqv2_s2sep_supported(int lmax, int mmax);
 int eqv2_s2sep_set_tables(const float* host_tables, int nfloats, int slot, void* stream);
 int eqv2_s2sep_fwd(const float* X, long long x_rs, const float* gate, long long g_rs, float* O, long long o_rs,
-                   long long R, int C, int lmax, int mmax, int m_primary, int slot, void* stream);
+                   long long R, int C, int lmax, int mmax, int m_primary, int slot,
+                   float* absmax /*may be NULL; else 64 zeroed floats receiving max |O|*/, void* stream);
 int eqv2_s2sep_bwd(const float* X, long long x_rs, const float* gate, long long g_rs, const float* dO, long long o_rs,
                    float* dX, long long dx_rs, float* dgate, long long dg_rs, long long R, int C, int lmax, int mmax,
-                   int m_primary, int slot, void* stream);
+                   int m_primary, int slot, float* absmax /*may be NULL; max |dX|, |dgate|*/, void* stream);
 
 /* derivative of eqv2_s2sep_bwd w.r.t. (X, gate, dO) for cotangents U (of dX) and Wg (of dgate): the second-order
  * term needed when forces = -dE/dpos are trained on (train_MatPES_GATAWandB.py:72-91). */
@@ -198,7 +199,8 @@ int eqv2_attn_alpha_bwd(const float* Y, long long y_rs, const float* ln_w, const
                         const float* alpha_dot, const int* rowptr_dst, const int* perm_dst, const float* alpha,
                         const float* dalpha, float* dlogits, float* dY, long long dy_rs,
                         float* d_ln_w /*zeroed*/, float* d_ln_b /*zeroed*/, float* d_alpha_dot /*zeroed*/,
-                        long long E, long long N, int heads, int ach, float eps, void* stream);
+                        long long E, long long N, int heads, int ach, float eps,
+                        float* absmax /*may be NULL; max |dY| into the same kind of slot*/, void* stream);
 
 /* ---- equivariant norms (layer_norm.py:38-108,112-201,265-351) ---------------------------- */
 int eqv2_equiv_norm_fwd(const float* x /*[N,K,C]*/, const float* w /*[lmax+1,C]*/, const float* b /*[C]*/,
