@@ -32,9 +32,10 @@ if REPO not in sys.path:
 PKG = "equivarianttransformermpnn4quantumcomputations_b200"
 
 # dram__bytes_read.sum + dram__bytes_write.sum of ONE launch of the dominant kernel from the committed `ncu --set full`
-# capture (profiles/r01k_ncu_gemm_f16_summary.txt: conv1 forward m=0 block, 48.1 GFLOP, 155 MB of operands + output).
-# A constant of that capture, not of this run (ncu cannot run inside the timed bench): reported with its source.
-TRAFFIC = {"eqv2_gemm_f16": (1.289e8, "profiles/r01k_ncu_gemm_f16_summary.txt (conv1 fwd m=0 block; algorithmic 155 MB)")}
+# capture of the round-2 build (profiles/r02_ncu_kernel_summary.txt: conv1 forward, all five m-groups in one launch,
+# 157 GFLOP; 425 MB read + 115 MB written against 554 MB algorithmic).  A constant of that capture, not of this run (ncu
+# cannot run inside the timed bench): reported with its source.
+TRAFFIC = {"eqv2_gemm_f16": (5.397e8, "profiles/r02_ncu_kernel_summary.txt (conv1 forward launch, E = 13 489; algorithmic 554 MB)")}
 FFMA_PEAK_TFLOPS = 73.0      # measured FFMA / FFMA2 peak of this pool's B200 (scripts/microbench/ffma2.cu)
 UNIT = "structures/s"
 
