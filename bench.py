@@ -488,6 +488,7 @@ def run_b200(args):
                 "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": conf,
                 "workload_detail": {"atoms_per_gpu": int(host["pos"].shape[0]), "edges_per_gpu": E,
                                     "params": model.num_params,
+                                    "peak_mem_gb": round(torch.cuda.max_memory_allocated() / 1e9, 2),
                                     "launch": ("CUDA graph replay of forward+loss+backward; neighbour list, edge frames, "
                                                "gradient all-reduce (NCCL, N > 1) and AdamW eager" if use_graph
                                                else "eager (every kernel enqueued from Python; DDP when N > 1)"),
