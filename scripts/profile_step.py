@@ -11,15 +11,20 @@ from equivarianttransformermpnn4quantumcomputations_b200.models import equiforme
 ap = argparse.ArgumentParser()
 ap.add_argument("--layers", type=int, default=12)
 ap.add_argument("--top", type=int, default=45)
-ap.add_argument("--structures", type=int, default=8)
+ap.add_argument("--structures", type=int, default=None)
+ap.add_argument("--config", default="oc20", choices=sorted(bench.CONFIGS))
 a = ap.parse_args()
-CFG = bench.CONFIGS["oc20"]
-kw = dict(CFG["kw"], num_layers=a.layers)
+CFG = bench.CONFIGS[a.config]
+kw = dict(CFG["kw"])
+if a.config == "oc20":
+    kw["num_layers"] = a.layers
 torch.manual_seed(0)
 dev = torch.device("cuda")
-model = oc20.EquiformerV2_OC20(**kw).to(dev)
+import importlib
+model = getattr(importlib.import_module(bench.PKG + ".models." + CFG["module"]), CFG["cls"])(**kw).to(dev)
 opt = torch.optim.AdamW(model.parameters(), lr=1e-4, fused=True)
-data = {k: (v.to(dev) if torch.is_tensor(v) else v) for k, v in synthetic.oc20_batch(a.structures, seed=1000).items()}
+data = {k: (v.to(dev) if torch.is_tensor(v) else v)
+        for k, v in bench.make_batch(CFG, a.structures or CFG["structures"], seed=1000).items()}
 
 
 def step():
