@@ -75,6 +75,7 @@ _PROTOS = {
     "eqv2_attn_alpha_bwd": [P, L, P, P, P, P, P, P, P, P, P, L, P, P, P, L, L, I, I, F, P, P],
     "eqv2_equiv_norm_fwd": [P, P, P, P, P, P, L, I, I, I, P, P, F, P, P],
     "eqv2_equiv_norm_bwd": [P, P, P, P, P, P, P, P, L, I, I, I, P, P, P],
+    "eqv2_equiv_norm_bwd2": [P, P, P, P, P, P, P, P, P, L, I, I, I, P, P, P],
     "eqv2_rbf_fwd": [P, P, L, I, P, F, P],
     "eqv2_rbf_bwd": [P, P, P, L, I, P, F, P],
     "eqv2_edge_sh": [P, P, L, I, P],
@@ -83,6 +84,7 @@ _PROTOS = {
     "eqv2_rbf_linear_wgrad": [P, P, P, P, P, P, P, P, P, L, I, I, F, P],
     "eqv2_ln_silu_fwd": [P, P, P, P, L, I, F, P],
     "eqv2_ln_silu_bwd": [P, P, P, P, P, P, P, L, I, F, P],
+    "eqv2_ln_silu_bwd2": [P, P, P, P, P, P, P, P, P, L, I, F, P],
     "eqv2_graph_ptr": [P, P, I, P],
     "eqv2_exclusive_scan": [P, P, I, P],
     "eqv2_radius_graph": [P, P, P, L, F, I, I, P, P, P, P, P, P, P, P],

@@ -49,6 +49,12 @@ __device__ __forceinline__ float eqv2_dsilu(float x) {
   return s * (1.0f + x * (1.0f - s));
 }
 
+// d2/dx2 silu(x) = s (1 - s) (2 + x (1 - 2 s))
+__device__ __forceinline__ float eqv2_silu_d2(float x) {
+  const float s = eqv2_sigmoid(x);
+  return s * (1.0f - s) * (2.0f + x * (1.0f - 2.0f * s));
+}
+
 __device__ __forceinline__ float eqv2_warp_sum(float v) {
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);

@@ -284,6 +284,122 @@ extern "C" int eqv2_rbf_bwd(const float* d, const float* go, float* dd, long lon
   return 0;
 }
 
+// Derivative of the BACKWARD pass (forces by autograd: the loss on the forces is back-propagated through the first
+// backward).  First backward, per row:  x^ = (x - mu) / sigma,  z = x^ w + b,  a = w gy SiLU'(z),
+//   gx = J a,   J = (I - 1 1^T / n - x^ x^^T / n) / sigma  (the symmetric Jacobian of x -> x^).
+// For a cotangent u of gx:  S = <u, J a> = <J u, a> = sum_i w_i gy_i SiLU'(z_i) p_i  with  p = J u.  Then
+//   dS/dgy_i = w_i SiLU'(z_i) p_i
+//   dS/db_i  = c_i := w_i gy_i SiLU''(z_i) p_i                         (summed over rows)
+//   dS/dw_i  = gy_i SiLU'(z_i) p_i + c_i x^_i                         (summed over rows)
+//   dS/dx    = J (e + q) - S x^ / (n sigma),   e = c w  (through z),   q = -(a mean(u x^) + u mean(a x^)) / sigma  (through J)
+// One warp per row, two rounds of warp reductions; parameter gradients via block partial sums + one atomic per column.
+__global__ void ln_silu_bwd2_kernel(const float* __restrict__ x, const float* __restrict__ w, const float* __restrict__ b,
+                                    const float* __restrict__ gy, const float* __restrict__ u, float* __restrict__ dx,
+                                    float* __restrict__ dgy, float* __restrict__ dw, float* __restrict__ db, long long rows,
+                                    int width, float eps) {
+  const int lane = threadIdx.x & 31;
+  const long long warp = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const long long nwarps = ((long long)gridDim.x * blockDim.x) >> 5;
+  float aw[LN_PL], ab[LN_PL];
+#pragma unroll
+  for (int k = 0; k < LN_PL; ++k) aw[k] = ab[k] = 0.f;
+  const float inv_n = 1.0f / (float)width;
+  for (long long r = warp; r < rows; r += nwarps) {
+    const float* xp = x + r * width;
+    float v[LN_PL];
+    float s = 0.f;
+#pragma unroll
+    for (int k = 0; k < LN_PL; ++k) {
+      const int i = lane + 32 * k;
+      v[k] = (i < width) ? xp[i] : 0.f;
+      s += v[k];
+    }
+    const float mean = eqv2_warp_sum(s) * inv_n;
+    float q2 = 0.f;
+#pragma unroll
+    for (int k = 0; k < LN_PL; ++k) {
+      const int i = lane + 32 * k;
+      const float t = (i < width) ? v[k] - mean : 0.f;
+      q2 = fmaf(t, t, q2);
+    }
+    const float rstd = rsqrtf(eqv2_warp_sum(q2) * inv_n + eps);
+    float xh[LN_PL], a[LN_PL], uu[LN_PL], d1[LN_PL], cc[LN_PL];      // x^, a, u, gy SiLU'(z), w gy SiLU''(z)
+    float su = 0.f, sux = 0.f, sax = 0.f;
+#pragma unroll
+    for (int k = 0; k < LN_PL; ++k) {
+      const int i = lane + 32 * k;
+      xh[k] = a[k] = uu[k] = d1[k] = cc[k] = 0.f;
+      if (i < width) {
+        xh[k] = (v[k] - mean) * rstd;
+        const float wi = w[i];
+        const float z = fmaf(xh[k], wi, b[i]);
+        const float gyi = gy[r * width + i];
+        d1[k] = gyi * eqv2_dsilu(z);
+        cc[k] = wi * gyi * eqv2_silu_d2(z);
+        a[k] = wi * d1[k];
+        uu[k] = u[r * width + i];
+        su += uu[k];
+        sux = fmaf(uu[k], xh[k], sux);
+        sax = fmaf(a[k], xh[k], sax);
+      }
+    }
+    const float ubar = eqv2_warp_sum(su) * inv_n, ux = eqv2_warp_sum(sux) * inv_n, m2 = eqv2_warp_sum(sax) * inv_n;
+    float f[LN_PL];
+    float sf = 0.f, sfx = 0.f, sT = 0.f;
+#pragma unroll
+    for (int k = 0; k < LN_PL; ++k) {
+      const int i = lane + 32 * k;
+      f[k] = 0.f;
+      if (i < width) {
+        const float p = (uu[k] - ubar - xh[k] * ux) * rstd;
+        const float c = cc[k] * p;                      // dS/dz_i
+        const float wi = w[i];
+        dgy[r * width + i] = wi * eqv2_dsilu(fmaf(xh[k], wi, b[i])) * p;
+        ab[k] += c;
+        aw[k] += fmaf(d1[k], p, c * xh[k]);
+        f[k] = c * wi - rstd * (a[k] * ux + uu[k] * m2);
+        sf += f[k];
+        sfx = fmaf(f[k], xh[k], sfx);
+        sT = fmaf(a[k], p, sT);
+      }
+    }
+    const float mf = eqv2_warp_sum(sf) * inv_n, mfx = eqv2_warp_sum(sfx) * inv_n, T = eqv2_warp_sum(sT);
+#pragma unroll
+    for (int k = 0; k < LN_PL; ++k) {
+      const int i = lane + 32 * k;
+      if (i < width) dx[r * width + i] = rstd * (f[k] - mf - xh[k] * mfx) - T * rstd * inv_n * xh[k];
+    }
+  }
+  __shared__ float sred[2][8][32 * LN_PL];
+  const int wib = threadIdx.x >> 5;
+#pragma unroll
+  for (int k = 0; k < LN_PL; ++k) {
+    sred[0][wib][lane + 32 * k] = aw[k];
+    sred[1][wib][lane + 32 * k] = ab[k];
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < width; i += blockDim.x) {
+    float tw = 0.f, tb = 0.f;
+    for (int q = 0; q < 8; ++q) {
+      tw += sred[0][q][i];
+      tb += sred[1][q][i];
+    }
+    atomicAdd(dw + i, tw);
+    atomicAdd(db + i, tb);
+  }
+}
+
+extern "C" int eqv2_ln_silu_bwd2(const float* x, const float* w, const float* b, const float* gy, const float* u, float* dx,
+                                 float* dgy, float* dw, float* db, long long rows, int width, float eps, void* stream) {
+  if (rows == 0) return 0;
+  EQV2_REQUIRE(width > 0 && width <= 32 * LN_PL, "ln_silu_bwd2: width %d > %d", width, 32 * LN_PL);
+  long long blocks = (rows * 32 + 255) / 256;
+  if (blocks > 148 * 4) blocks = 148 * 4;
+  EQV2_LAUNCH(ln_silu_bwd2_kernel, dim3((unsigned)blocks), dim3(256), 0, stream, x, w, b, gy, u, dx, dgy, dw, db, rows, width, eps);
+  EQV2_CHECK_LAUNCH("eqv2_ln_silu_bwd2");
+  return 0;
+}
+
 extern "C" int eqv2_ln_silu_fwd(const float* x, const float* w, const float* b, float* y, long long rows, int width,
                                 float eps, void* stream) {
   if (rows == 0) return 0;

@@ -1902,21 +1902,74 @@ class EquivNormFn(torch.autograd.Function):
     def backward(ctx, go):
         x, w, b, inv, mean = ctx.saved_tensors
         norm_type, lmax, eps = ctx.meta
-        if _recording(x, w, b, go):
-            g = _second_order(_equiv_norm_expr(norm_type, lmax, eps), [x, w, b], go)
-            return g[0], g[1], g[2], None, None, None
+        if _recording(x, w, b, go):        # forces by autograd: the backward is itself differentiated (EquivNormBwdFn)
+            gx, gw, gb = EquivNormBwdFn.apply(x, w, b, go.contiguous(), inv, mean, ctx.meta)
+            return gx, gw, gb, None, None, None
+        gx, gw, gb = _equiv_norm_bwd(x, w, go.contiguous(), inv, mean, norm_type, lmax)
+        return gx, gw, gb, None, None, None
+
+
+def _equiv_norm_bwd(x, w, go, inv, mean, norm_type, lmax):
+    N, K, C = x.shape
+    ng, gol, bw = norm_groups(norm_type, lmax)
+    gol_c = (ctypes.c_int * len(gol))(*gol)
+    bw_c = (ctypes.c_float * len(bw))(*bw)
+    gx = torch.empty_like(x)
+    gw = _small_zeros(w.shape, w.device)
+    gb = _small_zeros((C,), x.device)
+    _lib.call("eqv2_equiv_norm_bwd", x.data_ptr(), w.data_ptr(), go.data_ptr(), inv.data_ptr(), mean.data_ptr(),
+              gx.data_ptr(), gw.data_ptr(), gb.data_ptr(), N, C, lmax, ng, ctypes.cast(gol_c, ctypes.c_void_p),
+              ctypes.cast(bw_c, ctypes.c_void_p), _lib.stream_ptr(), work=(0.0, 12.0 * N * K * C))
+    return gx, gw, gb
+
+
+class EquivNormBwdFn(torch.autograd.Function):
+    """First-order backward of EquivNormFn as a differentiable operator; its backward is the closed-form kernel
+    `eqv2_equiv_norm_bwd2` for a cotangent of gx (the force loss).  Cotangents of the parameter gradients take the generic
+    torch-expression route (`_second_order`-style)."""
+
+    @staticmethod
+    def forward(ctx, x, w, b, go, inv, mean, meta):
+        norm_type, lmax, eps = meta
+        gx, gw, gb = _equiv_norm_bwd(x, w, go, inv, mean, norm_type, lmax)
+        ctx.save_for_backward(x, w, b, go, inv, mean)
+        ctx.meta = meta
+        return gx, gw, gb
+
+    @staticmethod
+    def backward(ctx, u, uw, ub):
+        x, w, b, go, inv, mean = ctx.saved_tensors
+        norm_type, lmax, eps = ctx.meta
+        if uw is not None or ub is not None:
+            fn = _equiv_norm_expr(norm_type, lmax, eps)
+            with torch.enable_grad():
+                xs, ws, bs, gs = [t.detach().requires_grad_(True) for t in (x, w, b, go)]
+                g1 = torch.autograd.grad(fn(xs, ws, bs), [xs, ws, bs], gs, create_graph=True)
+                cot = [c if c is not None else torch.zeros_like(g) for c, g in zip((u, uw, ub), g1)]
+                d = torch.autograd.grad(g1, [xs, ws, bs, gs], cot, allow_unused=True)
+            return d[0], d[1], d[2], d[3], None, None, None
         N, K, C = x.shape
         ng, gol, bw = norm_groups(norm_type, lmax)
         gol_c = (ctypes.c_int * len(gol))(*gol)
         bw_c = (ctypes.c_float * len(bw))(*bw)
-        go = go.contiguous()
-        gx = torch.empty_like(x)
-        gw = _small_zeros(w.shape, w.device)
-        gb = _small_zeros((C,), x.device)
-        _lib.call("eqv2_equiv_norm_bwd", x.data_ptr(), w.data_ptr(), go.data_ptr(), inv.data_ptr(), mean.data_ptr(),
-                  gx.data_ptr(), gw.data_ptr(), gb.data_ptr(), N, C, lmax, ng, ctypes.cast(gol_c, ctypes.c_void_p),
-                  ctypes.cast(bw_c, ctypes.c_void_p), _lib.stream_ptr(), work=(0.0, 12.0 * N * K * C))
-        return gx, gw, gb, None, None, None
+        u = u.contiguous()
+        d2x, dgo = torch.empty_like(x), torch.empty_like(go)
+        dw = _small_zeros(w.shape, w.device)
+        _lib.call("eqv2_equiv_norm_bwd2", x.data_ptr(), w.data_ptr(), go.data_ptr(), inv.data_ptr(), mean.data_ptr(),
+                  u.data_ptr(), d2x.data_ptr(), dgo.data_ptr(), dw.data_ptr(), N, C, lmax, ng,
+                  ctypes.cast(gol_c, ctypes.c_void_p), ctypes.cast(bw_c, ctypes.c_void_p), _lib.stream_ptr(),
+                  work=(0.0, 20.0 * N * K * C))
+        return d2x, dw, None, dgo, None, None, None
+
+
+def _ln_silu_bwd(x, w, b, gy, eps):
+    rows, width = x.shape
+    gx = torch.empty_like(x)
+    gw = _small_zeros(w.shape, w.device)
+    gb = _small_zeros(b.shape, b.device)
+    _lib.call("eqv2_ln_silu_bwd", x.data_ptr(), w.data_ptr(), b.data_ptr(), gy.data_ptr(), gx.data_ptr(),
+              gw.data_ptr(), gb.data_ptr(), rows, width, eps, _lib.stream_ptr(), work=(0.0, 12.0 * rows * width))
+    return gx, gw, gb
 
 
 class LnSiluFn(torch.autograd.Function):
@@ -1937,19 +1990,48 @@ class LnSiluFn(torch.autograd.Function):
     @staticmethod
     def backward(ctx, gy):
         x, w, b = ctx.saved_tensors
-        eps = ctx.eps
-        if _recording(x, w, b, gy):
-            Fn = torch.nn.functional
-            g = _second_order(lambda x_, w_, b_: Fn.silu(Fn.layer_norm(x_, x_.shape[-1:], w_, b_, eps)), [x, w, b], gy)
-            return g[0], g[1], g[2], None
-        rows, width = x.shape
-        gy = gy.contiguous()
-        gx = torch.empty_like(x)
-        gw = _small_zeros(w.shape, w.device)
-        gb = _small_zeros(b.shape, b.device)
-        _lib.call("eqv2_ln_silu_bwd", x.data_ptr(), w.data_ptr(), b.data_ptr(), gy.data_ptr(), gx.data_ptr(),
-                  gw.data_ptr(), gb.data_ptr(), rows, width, eps, _lib.stream_ptr(), work=(0.0, 12.0 * rows * width))
+        if _recording(x, w, b, gy):        # forces by autograd: the backward is itself differentiated (LnSiluBwdFn)
+            gx, gw, gb = LnSiluBwdFn.apply(x, w, b, gy.contiguous(), ctx.eps)
+            return gx, gw, gb, None
+        gx, gw, gb = _ln_silu_bwd(x, w, b, gy.contiguous(), ctx.eps)
         return gx, gw, gb, None
+
+
+class LnSiluBwdFn(torch.autograd.Function):
+    """The first-order backward of LnSiluFn as a differentiable operator: (x, w, b, gy) -> (gx, gw, gb).  Its own
+    backward is the closed-form kernel `eqv2_ln_silu_bwd2` for a cotangent of gx -- the case of the force loss, where
+    the first backward only feeds the position gradient.  Cotangents of gw / gb (somebody differentiating the PARAMETER
+    gradients again) take the generic route: the operator re-expressed with torch primitives (`_second_order`)."""
+
+    @staticmethod
+    def forward(ctx, x, w, b, gy, eps):
+        gx, gw, gb = _ln_silu_bwd(x, w, b, gy, eps)
+        ctx.save_for_backward(x, w, b, gy)
+        ctx.eps = eps
+        return gx, gw, gb
+
+    @staticmethod
+    def backward(ctx, u, uw, ub):
+        x, w, b, gy = ctx.saved_tensors
+        eps = ctx.eps
+        if uw is not None or ub is not None:
+            Fn = torch.nn.functional
+            with torch.enable_grad():
+                xs, ws, bs, gs = [t.detach().requires_grad_(True) for t in (x, w, b, gy)]
+                y = Fn.silu(Fn.layer_norm(xs, xs.shape[-1:], ws, bs, eps))
+                g1 = torch.autograd.grad(y, [xs, ws, bs], gs, create_graph=True)
+                cot = [c if c is not None else torch.zeros_like(g) for c, g in zip((u, uw, ub), g1)]
+                d = torch.autograd.grad(g1, [xs, ws, bs, gs], cot, allow_unused=True)
+            return d[0], d[1], d[2], d[3], None
+        rows, width = x.shape
+        u = u.contiguous()
+        dx, dgy = torch.empty_like(x), torch.empty_like(gy)
+        dw = _small_zeros(w.shape, w.device)
+        db = _small_zeros(b.shape, b.device)
+        _lib.call("eqv2_ln_silu_bwd2", x.data_ptr(), w.data_ptr(), b.data_ptr(), gy.data_ptr(), u.data_ptr(), dx.data_ptr(),
+                  dgy.data_ptr(), dw.data_ptr(), db.data_ptr(), rows, width, eps, _lib.stream_ptr(),
+                  work=(0.0, 20.0 * rows * width))
+        return dx, dw, db, dgy, None
 
 
 class RbfFn(torch.autograd.Function):

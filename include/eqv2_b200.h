@@ -211,6 +211,11 @@ int eqv2_equiv_norm_bwd(const float* x, const float* w, const float* go, const f
                         const float* mean_in, float* dx, float* dw /*zeroed*/, float* db /*zeroed*/,
                         long long N, int C, int lmax, int ngroups, const int* group_of_l /*host*/,
                         const float* bw_l /*host*/, void* stream);
+/* derivative of eqv2_equiv_norm_bwd's dx w.r.t. (x, go, w) for a cotangent u of dx (double backward of the force loss);
+ * dw accumulated atomically into a zeroed buffer; the bias does not enter dx */
+int eqv2_equiv_norm_bwd2(const float* x, const float* w, const float* go, const float* inv_in, const float* mean_in,
+                         const float* u, float* d2x, float* dgo, float* dw /*zeroed*/, long long N, int C, int lmax,
+                         int ngroups, const int* group_of_l, const float* bw_l, void* stream);
 
 /* ---- edge scalar features (equiformerv2_oc20.py:43-60, radial_function.py:21-22) --------- */
 int eqv2_rbf_fwd(const float* d, float* out /*[E,R]*/, long long E, int R, const float* offset /*[R]*/, float coeff,
@@ -225,6 +230,11 @@ int eqv2_ln_silu_fwd(const float* x, const float* w, const float* b, float* y, l
 int eqv2_ln_silu_bwd(const float* x, const float* w, const float* b, const float* gy, float* gx,
                      float* gw /*zeroed*/, float* gb /*zeroed*/, long long rows, int width, float eps,
                      void* stream);
+/* derivative of eqv2_ln_silu_bwd's gx w.r.t. (x, gy, w, b) for a cotangent u of gx (forces by autograd: double backward
+ * of the radial MLP); dw / db are accumulated atomically into zeroed buffers */
+int eqv2_ln_silu_bwd2(const float* x, const float* w, const float* b, const float* gy, const float* u, float* dx,
+                      float* dgy, float* dw /*zeroed*/, float* db /*zeroed*/, long long rows, int width, float eps,
+                      void* stream);
 
 /* ---- neighbour lists and per-graph reductions -------------------------------------------
  * Builders run count (mode 0: deg[N]) -> eqv2_exclusive_scan -> fill (mode 1) and emit edges sorted

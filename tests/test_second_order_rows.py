@@ -1,0 +1,67 @@
+"""Closed-form second-order kernels of the small per-row operators (VERDICT r1 missing #4) against torch autograd in
+float64: the derivative OF the first backward pass -- what `loss.backward()` needs when the forces in the loss were
+themselves obtained by `autograd.grad(create_graph=True)` (train_MatPES_GATAWandB.py:67-91)."""
+import pytest
+import torch
+
+from helpers import pkg, rel_err
+
+
+@pytest.mark.parametrize("rows,width", [(37, 128), (5, 16), (64, 200)])
+def test_ln_silu_double_backward(backend, rows, width):
+    ops = pkg("ops")
+    gen = torch.Generator().manual_seed(rows + width)
+    x = torch.randn(rows, width, generator=gen) * 1.5 + 0.3
+    w = torch.randn(width, generator=gen) * 0.5 + 1.0
+    b = torch.randn(width, generator=gen) * 0.2
+    go = torch.randn(rows, width, generator=gen)
+    uu = torch.randn(rows, width, generator=gen)
+    Fn = torch.nn.functional
+
+    ref = [t.double().requires_grad_(True) for t in (x, w, b)]
+    yr = Fn.silu(Fn.layer_norm(ref[0], (width,), ref[1], ref[2], 1e-5))
+    gor = go.double().requires_grad_(True)
+    (gxr,) = torch.autograd.grad(yr, ref[0], gor, create_graph=True)
+    hr = torch.autograd.grad((gxr * uu.double()).sum(), ref + [gor])
+
+    dev = backend.device
+    mine = [t.clone().to(dev).requires_grad_(True) for t in (x, w, b)]
+    ym = ops.ln_silu(mine[0], mine[1], mine[2], 1e-5)
+    assert rel_err(ym, yr) < 2e-6
+    gom = go.clone().to(dev).requires_grad_(True)
+    (gxm,) = torch.autograd.grad(ym, mine[0], gom, create_graph=True)
+    assert rel_err(gxm, gxr) < 5e-6
+    hm = torch.autograd.grad((gxm * uu.to(dev)).sum(), mine + [gom])
+    for a, r, name in zip(hm, hr, ("x", "weight", "bias", "grad_out")):
+        assert rel_err(a, r) < 2e-5, name
+
+
+@pytest.mark.parametrize("norm_type", ["rms_norm_sh", "layer_norm_sh", "layer_norm"])
+@pytest.mark.parametrize("lmax,C", [(4, 32), (2, 16)])
+def test_equiv_norm_double_backward(backend, norm_type, lmax, C):
+    ops = pkg("ops")
+    gen = torch.Generator().manual_seed(lmax * 100 + C)
+    N, K = 7, (lmax + 1) ** 2
+    x = torch.randn(N, K, C, generator=gen) + 0.2
+    w = torch.randn(lmax + 1, C, generator=gen) * 0.3 + 1.0
+    b = torch.randn(C, generator=gen) * 0.1
+    go = torch.randn(N, K, C, generator=gen)
+    uu = torch.randn(N, K, C, generator=gen)
+    expr = ops._equiv_norm_expr(norm_type, lmax, 1e-5)
+
+    ref = [t.double().requires_grad_(True) for t in (x, w, b)]
+    yr = expr(*ref)
+    gor = go.double().requires_grad_(True)
+    (gxr,) = torch.autograd.grad(yr, ref[0], gor, create_graph=True)
+    hr = torch.autograd.grad((gxr * uu.double()).sum(), [ref[0], ref[1], gor])
+
+    dev = backend.device
+    mine = [t.clone().to(dev).requires_grad_(True) for t in (x, w, b)]
+    ym = ops.equiv_norm(mine[0], mine[1], mine[2], norm_type, lmax, 1e-5)
+    assert rel_err(ym, yr) < 2e-6
+    gom = go.clone().to(dev).requires_grad_(True)
+    (gxm,) = torch.autograd.grad(ym, mine[0], gom, create_graph=True)
+    assert rel_err(gxm, gxr) < 5e-6
+    hm = torch.autograd.grad((gxm * uu.to(dev)).sum(), [mine[0], mine[1], gom])
+    for a, r, name in zip(hm, hr, ("x", "weight", "grad_out")):
+        assert rel_err(a, r) < 2e-5, name
