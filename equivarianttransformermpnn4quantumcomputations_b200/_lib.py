@@ -73,6 +73,7 @@ _PROTOS = {
     "eqv2_s2sep_bwd2": [P, L, P, L, P, L, P, L, P, L, P, L, P, L, P, L, L, I, I, I, I, I, P],
     "eqv2_attn_alpha_fwd": [P, L, P, P, P, P, P, P, P, L, L, I, I, F, P],
     "eqv2_attn_alpha_bwd": [P, L, P, P, P, P, P, P, P, P, P, L, P, P, P, L, L, I, I, F, P, P],
+    "eqv2_attn_alpha_bwd2": [P, L, P, P, P, P, P, P, P, P, P, L, P, P, L, P, P, P, P, P, L, L, I, I, F, P],
     "eqv2_equiv_norm_fwd": [P, P, P, P, P, P, L, I, I, I, P, P, F, P, P],
     "eqv2_equiv_norm_bwd": [P, P, P, P, P, P, P, P, L, I, I, I, P, P, P],
     "eqv2_equiv_norm_bwd2": [P, P, P, P, P, P, P, P, P, L, I, I, I, P, P, P],

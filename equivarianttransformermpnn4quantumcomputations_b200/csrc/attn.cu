@@ -195,7 +195,180 @@ __global__ void attn_logits_bwd_kernel(const float* __restrict__ Y, long long y_
   }
 }
 
+// ---- derivative of the BACKWARD pass (forces by autograd) ---------------------------------------------------------------
+// First backward (attn_alpha_bwd): dl = alpha (ga - sum_seg alpha ga);  per (edge, head): gy_i = dl ad_i,
+//   a_i = w_i gy_i slr'(y_i),  dY = J a  (J = Jacobian of the LayerNorm over the alpha channels; identity without it).
+// For a cotangent u of dY:  S = sum_{e,h} dl_{eh} R_{eh},   R = sum_i p_i w_i ad_i slr'(y_i),   p = J u.
+//   * with dl fixed the (e, h) terms have exactly the LayerNorm + activation structure of ln_silu_bwd2 (edge_feat.cu) with
+//     gy_i = dl ad_i and slr in place of SiLU: d(Y), d(ln_w), d(ln_b), and d(alpha_dot)_i = dl w_i slr'(y_i) p_i;
+//   * through dl:  dS/d(ga)_e = alpha_e (R_e - sum_seg alpha R),   dS/d(alpha)_e = (ga_e - G) R_e - ga_e sum_seg alpha R
+//     (G = sum_seg alpha ga); alpha is an INPUT of the differentiated backward, autograd carries dS/d(alpha) on through the
+//     forward operator's ordinary backward.
+// attn_logits_bwd2: one warp per head striding over edges (parameter gradients in registers), writes R and d(Y).
+__global__ void attn_logits_bwd2_kernel(const float* __restrict__ Y, long long y_rs, const float* __restrict__ ln_w,
+                                        const float* __restrict__ ln_b, const float* __restrict__ alpha_dot,
+                                        const float* __restrict__ dlogits, const float* __restrict__ U, long long u_rs,
+                                        float* __restrict__ R, float* __restrict__ d2Y, long long d_rs,
+                                        float* __restrict__ d_ln_w, float* __restrict__ d_ln_b,
+                                        float* __restrict__ d_alpha_dot, long long E, int heads, int ach, float eps) {
+  const int lane = threadIdx.x & 31;
+  const long long warp = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const long long nwarps = ((long long)gridDim.x * blockDim.x) >> 5;   // multiple of heads (host guarantees)
+  const int h = (int)(warp % heads);
+  const float inv_n = 1.0f / (float)ach;
+  float gw[MAXPL], gb[MAXPL], gd[MAXPL];
+#pragma unroll
+  for (int k = 0; k < MAXPL; ++k) gw[k] = gb[k] = gd[k] = 0.f;
+  for (long long e = warp / heads; e < E; e += nwarps / heads) {
+    const float* xp = Y + e * y_rs + (long long)h * ach;
+    const float* up = U + e * u_rs + (long long)h * ach;
+    const float dl = dlogits[e * heads + h];
+    float x[MAXPL], uu[MAXPL];
+    float s = 0.f;
+#pragma unroll
+    for (int k = 0; k < MAXPL; ++k) {
+      const int i = lane + 32 * k;
+      x[k] = (i < ach) ? xp[i] : 0.f;
+      uu[k] = (i < ach) ? up[i] : 0.f;
+      s += x[k];
+    }
+    float mean = 0.f, rstd = 1.f;
+    if (ln_w) {
+      mean = eqv2_warp_sum(s) * inv_n;
+      float v = 0.f;
+#pragma unroll
+      for (int k = 0; k < MAXPL; ++k) {
+        const int i = lane + 32 * k;
+        const float d = (i < ach) ? x[k] - mean : 0.f;
+        v += d * d;
+      }
+      rstd = rsqrtf(eqv2_warp_sum(v) * inv_n + eps);
+    }
+    float xh[MAXPL], g1[MAXPL], cc[MAXPL], a[MAXPL];     // x^, w ad slr'(y), w ad slr''(y) dl, w gy slr'(y)
+    float su = 0.f, sux = 0.f, sax = 0.f;
+#pragma unroll
+    for (int k = 0; k < MAXPL; ++k) {
+      const int i = lane + 32 * k;
+      xh[k] = g1[k] = cc[k] = a[k] = 0.f;
+      if (i < ach) {
+        const float wi = ln_w ? ln_w[i] : 1.0f;
+        float y = x[k];
+        if (ln_w) {
+          xh[k] = (x[k] - mean) * rstd;
+          y = fmaf(xh[k], wi, ln_b[i]);
+        }
+        const float ad = alpha_dot[h * ach + i];
+        g1[k] = wi * ad * dslr(y);
+        cc[k] = wi * ad * dl * (2.f * SLR_C2) * eqv2_silu_d2(y);
+        a[k] = g1[k] * dl;
+        su += uu[k];
+        sux = fmaf(uu[k], xh[k], sux);
+        sax = fmaf(a[k], xh[k], sax);
+      }
+    }
+    float ubar = 0.f, ux = 0.f, m2 = 0.f;
+    if (ln_w) {
+      ubar = eqv2_warp_sum(su) * inv_n;
+      ux = eqv2_warp_sum(sux) * inv_n;
+      m2 = eqv2_warp_sum(sax) * inv_n;
+    }
+    float f[MAXPL];
+    float sf = 0.f, sfx = 0.f, sR = 0.f;
+#pragma unroll
+    for (int k = 0; k < MAXPL; ++k) {
+      const int i = lane + 32 * k;
+      f[k] = 0.f;
+      if (i < ach) {
+        const float p = ln_w ? (uu[k] - ubar - xh[k] * ux) * rstd : uu[k];
+        const float c = cc[k] * p;                       // dS/dy_i
+        sR = fmaf(g1[k], p, sR);
+        gd[k] = fmaf(dl * (ln_w ? ln_w[i] : 1.0f) * dslr(ln_w ? fmaf(xh[k], ln_w[i], ln_b[i]) : x[k]), p, gd[k]);
+        if (ln_w) {
+          gb[k] += c;
+          gw[k] += fmaf(dl * alpha_dot[h * ach + i] * dslr(fmaf(xh[k], ln_w[i], ln_b[i])), p, c * xh[k]);
+          f[k] = c * ln_w[i] - rstd * (a[k] * ux + uu[k] * m2);
+          sf += f[k];
+          sfx = fmaf(f[k], xh[k], sfx);
+        } else {
+          f[k] = c;
+        }
+      }
+    }
+    const float Rv = eqv2_warp_sum(sR);
+    if (lane == 0) R[e * heads + h] = Rv;
+    float mf = 0.f, mfx = 0.f;
+    const float T = Rv * dl;                             // sum_i a_i p_i
+    if (ln_w) {
+      mf = eqv2_warp_sum(sf) * inv_n;
+      mfx = eqv2_warp_sum(sfx) * inv_n;
+    }
+    float* dp = d2Y + e * d_rs + (long long)h * ach;
+#pragma unroll
+    for (int k = 0; k < MAXPL; ++k) {
+      const int i = lane + 32 * k;
+      if (i < ach) dp[i] = ln_w ? rstd * (f[k] - mf - xh[k] * mfx) - T * rstd * inv_n * xh[k] : f[k];
+    }
+  }
+#pragma unroll
+  for (int k = 0; k < MAXPL; ++k) {
+    const int i = lane + 32 * k;
+    if (i < ach) {
+      atomicAdd(&d_alpha_dot[h * ach + i], gd[k]);
+      if (ln_w) {
+        atomicAdd(&d_ln_w[i], gw[k]);
+        atomicAdd(&d_ln_b[i], gb[k]);
+      }
+    }
+  }
+}
+
+// per (node, head): d(ga)_e = alpha_e (R_e - Rbar),  d(alpha)_e = (ga_e - G) R_e - ga_e Rbar
+__global__ void segment_softmax_bwd2_kernel(const float* __restrict__ alpha, const float* __restrict__ dalpha,
+                                            const float* __restrict__ R, const int* __restrict__ rowptr,
+                                            const int* __restrict__ perm, float* __restrict__ d_dalpha,
+                                            float* __restrict__ d_alpha, long long N, int heads) {
+  const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= N * heads) return;
+  const long long n = t / heads;
+  const int h = (int)(t % heads);
+  const int beg = rowptr[n], end = rowptr[n + 1];
+  float G = 0.f, Rbar = 0.f;
+  for (int i = beg; i < end; ++i) {
+    const long long e = perm[i];
+    const float al = alpha[e * heads + h];
+    G = fmaf(al, dalpha[e * heads + h], G);
+    Rbar = fmaf(al, R[e * heads + h], Rbar);
+  }
+  for (int i = beg; i < end; ++i) {
+    const long long e = perm[i];
+    const float al = alpha[e * heads + h], ga = dalpha[e * heads + h], r = R[e * heads + h];
+    d_dalpha[e * heads + h] = al * (r - Rbar);
+    d_alpha[e * heads + h] = (ga - G) * r - ga * Rbar;
+  }
+}
+
 }  // namespace
+
+extern "C" int eqv2_attn_alpha_bwd2(const float* Y, long long y_rs, const float* ln_w, const float* ln_b,
+                                    const float* alpha_dot, const int* rowptr_dst, const int* perm_dst,
+                                    const float* alpha, const float* dalpha, const float* dlogits, const float* U,
+                                    long long u_rs, float* R, float* d2Y, long long d_rs, float* d_ln_w, float* d_ln_b,
+                                    float* d_alpha_dot, float* d_dalpha, float* d_alpha, long long E, long long N,
+                                    int heads, int ach, float eps, void* stream) {
+  if (E == 0 || N == 0) return 0;
+  EQV2_REQUIRE(ach > 0 && ach <= 32 * MAXPL, "attn_alpha_bwd2: alpha channels %d > %d", ach, 32 * MAXPL);
+  const int wpb = 8;
+  long long want = (E * heads + wpb - 1) / wpb;
+  if (want > 148 * 8) want = 148 * 8;
+  long long blocks = ((want * wpb + heads - 1) / heads * heads + wpb - 1) / wpb;
+  while ((blocks * wpb) % heads != 0) ++blocks;
+  EQV2_LAUNCH(attn_logits_bwd2_kernel, dim3((unsigned)blocks), dim3(wpb * 32), 0, stream, Y, y_rs, ln_w, ln_b, alpha_dot, dlogits, U, u_rs, R, d2Y, d_rs, d_ln_w, d_ln_b, d_alpha_dot, E, heads, ach, eps);
+  EQV2_CHECK_LAUNCH("eqv2_attn_alpha_bwd2/logits");
+  const long long t = N * heads;
+  EQV2_LAUNCH(segment_softmax_bwd2_kernel, dim3((unsigned)((t + 127) / 128)), dim3(128), 0, stream, alpha, dalpha, R, rowptr_dst, perm_dst, d_dalpha, d_alpha, N, heads);
+  EQV2_CHECK_LAUNCH("eqv2_attn_alpha_bwd2/softmax");
+  return 0;
+}
 
 extern "C" int eqv2_attn_alpha_fwd(const float* Y, long long y_rs, const float* ln_w, const float* ln_b,
                                    const float* alpha_dot, const int* rowptr_dst, const int* perm_dst, float* logits,

@@ -1821,21 +1821,77 @@ class AttnAlphaFn(torch.autograd.Function):
     def backward(ctx, galpha):
         Ya, ln_w, ln_b, alpha_dot, alpha = ctx.saved_tensors
         plan, (heads, ach) = ctx.plan, ctx.meta
-        if _recording(Ya, ln_w, ln_b, alpha_dot, galpha):
-            g = _second_order(_alpha_expr(heads, ach, 1e-5, plan.dst, plan.N), [Ya, ln_w, ln_b, alpha_dot], galpha)
+        if _recording(Ya, ln_w, ln_b, alpha_dot, galpha):      # forces by autograd: differentiable backward
+            g = AttnAlphaBwdFn.apply(Ya, ln_w, ln_b, alpha_dot, alpha, galpha.contiguous(), plan, heads, ach)
+            if ln_w is None:
+                return g[0], None, None, g[1], None, None, None
             return g[0], g[1], g[2], g[3], None, None, None
-        E = Ya.shape[0]
-        galpha = galpha.contiguous()
-        gY = torch.empty_like(Ya)
-        g_lnw = torch.zeros_like(ln_w) if ln_w is not None else None
-        g_lnb = torch.zeros_like(ln_b) if ln_b is not None else None
-        g_dot = torch.zeros_like(alpha_dot)
-        dlogits = torch.empty_like(alpha)
-        _lib.call("eqv2_attn_alpha_bwd", Ya.data_ptr(), heads * ach, _lib.ptr(ln_w), _lib.ptr(ln_b), alpha_dot.data_ptr(),
-                  plan.rowptr_dst.data_ptr(), plan.perm_dst.data_ptr(), alpha.data_ptr(), galpha.data_ptr(),
-                  dlogits.data_ptr(), gY.data_ptr(), heads * ach, _lib.ptr(g_lnw), _lib.ptr(g_lnb), g_dot.data_ptr(),
-                  E, plan.N, heads, ach, 1e-5, None, _lib.stream_ptr(), n_kernels=2)
+        gY, g_lnw, g_lnb, g_dot, _ = _attn_alpha_bwd(Ya, ln_w, ln_b, alpha_dot, alpha, galpha.contiguous(), plan, heads, ach)
         return gY, g_lnw, g_lnb, g_dot, None, None, None
+
+
+def _attn_alpha_bwd(Ya, ln_w, ln_b, alpha_dot, alpha, galpha, plan, heads, ach):
+    E = Ya.shape[0]
+    gY = torch.empty_like(Ya)
+    g_lnw = torch.zeros_like(ln_w) if ln_w is not None else None
+    g_lnb = torch.zeros_like(ln_b) if ln_b is not None else None
+    g_dot = torch.zeros_like(alpha_dot)
+    dlogits = torch.empty_like(alpha)
+    _lib.call("eqv2_attn_alpha_bwd", Ya.data_ptr(), heads * ach, _lib.ptr(ln_w), _lib.ptr(ln_b), alpha_dot.data_ptr(),
+              plan.rowptr_dst.data_ptr(), plan.perm_dst.data_ptr(), alpha.data_ptr(), galpha.data_ptr(),
+              dlogits.data_ptr(), gY.data_ptr(), heads * ach, _lib.ptr(g_lnw), _lib.ptr(g_lnb), g_dot.data_ptr(),
+              E, plan.N, heads, ach, 1e-5, None, _lib.stream_ptr(), n_kernels=2)
+    return gY, g_lnw, g_lnb, g_dot, dlogits
+
+
+class AttnAlphaBwdFn(torch.autograd.Function):
+    """First-order backward of AttnAlphaFn as a differentiable operator of (Ya, ln_w, ln_b, alpha_dot, alpha, galpha).
+    Its backward for a cotangent of gY is the closed-form kernel pair `eqv2_attn_alpha_bwd2`; `alpha` is an input here, so
+    its cotangent flows on through AttnAlphaFn's ordinary backward.  Cotangents of the parameter gradients take the generic
+    torch-expression route."""
+
+    @staticmethod
+    def forward(ctx, Ya, ln_w, ln_b, alpha_dot, alpha, galpha, plan, heads, ach):
+        gY, g_lnw, g_lnb, g_dot, dlogits = _attn_alpha_bwd(Ya, ln_w, ln_b, alpha_dot, alpha, galpha, plan, heads, ach)
+        ctx.save_for_backward(Ya, ln_w, ln_b, alpha_dot, alpha, galpha, dlogits)
+        ctx.plan, ctx.meta = plan, (heads, ach)
+        ctx.has_ln = ln_w is not None
+        if not ctx.has_ln:
+            return gY, g_dot
+        return gY, g_lnw, g_lnb, g_dot
+
+    @staticmethod
+    def backward(ctx, u, *rest):
+        Ya, ln_w, ln_b, alpha_dot, alpha, galpha, dlogits = ctx.saved_tensors
+        plan, (heads, ach) = ctx.plan, ctx.meta
+        if any(r is not None for r in rest):
+            fn = _alpha_expr(heads, ach, 1e-5, plan.dst, plan.N)
+            with torch.enable_grad():
+                leaves = [t.detach().requires_grad_(True) if t is not None else None for t in (Ya, ln_w, ln_b, alpha_dot)]
+                gs = galpha.detach().requires_grad_(True)
+                live = [t for t in leaves if t is not None]
+                g1 = torch.autograd.grad(fn(*leaves), live, gs, create_graph=True)
+                cots = (u,) + tuple(rest)
+                cot = [c if c is not None else torch.zeros_like(g) for c, g in zip(cots, g1)]
+                d = list(torch.autograd.grad(g1, live + [gs], cot, allow_unused=True))
+            d_gs = d.pop()
+            full = [d.pop(0) if t is not None else None for t in leaves]
+            return full[0], full[1], full[2], full[3], None, d_gs, None, None, None
+        E = Ya.shape[0]
+        dev = Ya.device
+        u = u.contiguous()
+        R = torch.empty_like(alpha)
+        d2Y = torch.empty_like(Ya)
+        d_lnw = _small_zeros(ln_w.shape, dev) if ln_w is not None else None
+        d_lnb = _small_zeros(ln_b.shape, dev) if ln_b is not None else None
+        d_dot = _small_zeros(alpha_dot.shape, dev)
+        d_galpha, d_alpha = torch.empty_like(alpha), torch.empty_like(alpha)
+        _lib.call("eqv2_attn_alpha_bwd2", Ya.data_ptr(), heads * ach, _lib.ptr(ln_w), _lib.ptr(ln_b), alpha_dot.data_ptr(),
+                  plan.rowptr_dst.data_ptr(), plan.perm_dst.data_ptr(), alpha.data_ptr(), galpha.data_ptr(),
+                  dlogits.data_ptr(), u.data_ptr(), heads * ach, R.data_ptr(), d2Y.data_ptr(), heads * ach,
+                  _lib.ptr(d_lnw), _lib.ptr(d_lnb), d_dot.data_ptr(), d_galpha.data_ptr(), d_alpha.data_ptr(), E, plan.N,
+                  heads, ach, 1e-5, _lib.stream_ptr(), n_kernels=2)
+        return d2Y, d_lnw, d_lnb, d_dot, d_alpha, d_galpha, None, None, None
 
 
 def norm_groups(norm_type, lmax):

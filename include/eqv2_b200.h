@@ -200,7 +200,17 @@ int eqv2_attn_alpha_bwd(const float* Y, long long y_rs, const float* ln_w, const
                         const float* dalpha, float* dlogits, float* dY, long long dy_rs,
                         float* d_ln_w /*zeroed*/, float* d_ln_b /*zeroed*/, float* d_alpha_dot /*zeroed*/,
                         long long E, long long N, int heads, int ach, float eps,
-                        float* absmax /*may be NULL; max |dY| into the same kind of slot*/, void* stream);
+                        float* absmax /*may be NULL: max |dY| into the same kind of slot*/, void* stream);
+/* derivative of eqv2_attn_alpha_bwd's dY w.r.t. (Y, ln_w, ln_b, alpha_dot, alpha, dalpha) for a cotangent U of dY (double
+ * backward of the force loss).  dlogits = the first backward's softmax gradient; R [E, heads] workspace; parameter
+ * gradients accumulate atomically into zeroed buffers; d_alpha is the cotangent of `alpha` AS AN INPUT of the backward
+ * (the caller's autograd carries it on through the forward operator's backward). */
+int eqv2_attn_alpha_bwd2(const float* Y, long long y_rs, const float* ln_w, const float* ln_b, const float* alpha_dot,
+                         const int* rowptr_dst, const int* perm_dst, const float* alpha, const float* dalpha,
+                         const float* dlogits, const float* U, long long u_rs, float* R, float* d2Y, long long d_rs,
+                         float* d_ln_w /*zeroed*/, float* d_ln_b /*zeroed*/, float* d_alpha_dot /*zeroed*/,
+                         float* d_dalpha, float* d_alpha, long long E, long long N, int heads, int ach, float eps,
+                         void* stream);
 
 /* ---- equivariant norms (layer_norm.py:38-108,112-201,265-351) ---------------------------- */
 int eqv2_equiv_norm_fwd(const float* x /*[N,K,C]*/, const float* w /*[lmax+1,C]*/, const float* b /*[C]*/,

@@ -65,3 +65,43 @@ def test_equiv_norm_double_backward(backend, norm_type, lmax, C):
     hm = torch.autograd.grad((gxm * uu.to(dev)).sum(), [mine[0], mine[1], gom])
     for a, r, name in zip(hm, hr, ("x", "weight", "grad_out")):
         assert rel_err(a, r) < 2e-5, name
+
+
+@pytest.mark.parametrize("use_ln", [True, False])
+@pytest.mark.parametrize("heads,ach", [(8, 64), (2, 8), (4, 32)])
+def test_attn_alpha_double_backward(backend, use_ln, heads, ach):
+    """alpha = segment_softmax_dst(alpha_dot . SmoothLeakyReLU(LayerNorm(Ya)))  (transformer_block.py:311-315): the
+    derivative of dL/dYa w.r.t. (Ya, LN weight, LN bias, alpha_dot, grad_out), kernels vs torch autograd in float64."""
+    ops = pkg("ops")
+    gen = torch.Generator().manual_seed(heads * 100 + ach + int(use_ln))
+    N, E = 9, 61
+    ei = torch.randint(0, N, (2, E), generator=gen)
+    Ya = torch.randn(E, heads * ach, generator=gen)
+    ln_w = (torch.randn(ach, generator=gen) * 0.3 + 1.0) if use_ln else None
+    ln_b = (torch.randn(ach, generator=gen) * 0.2) if use_ln else None
+    ad = torch.randn(heads, ach, generator=gen) * 0.3
+    go = torch.randn(E, heads, generator=gen)
+    uu = torch.randn(E, heads * ach, generator=gen)
+
+    expr = ops._alpha_expr(heads, ach, 1e-5, ei[1], N)
+    leaves = [Ya, ln_w, ln_b, ad]
+    ref = [t.double().requires_grad_(True) if t is not None else None for t in leaves]
+    yr = expr(*ref)
+    gor = go.double().requires_grad_(True)
+    (gxr,) = torch.autograd.grad(yr, ref[0], gor, create_graph=True)
+    live_r = [t for t in ref if t is not None] + [gor]
+    hr = torch.autograd.grad((gxr * uu.double()).sum(), live_r)
+
+    dev = backend.device
+    plan = ops.edge_plan(ei.to(dev), N)
+    mine = [t.clone().to(dev).requires_grad_(True) if t is not None else None for t in leaves]
+    ym = ops.attn_alpha(mine[0], mine[1], mine[2], mine[3], plan, heads, ach)
+    assert rel_err(ym, yr) < 5e-6
+    gom = go.clone().to(dev).requires_grad_(True)
+    (gxm,) = torch.autograd.grad(ym, mine[0], gom, create_graph=True)
+    assert rel_err(gxm, gxr) < 1e-5
+    live_m = [t for t in mine if t is not None] + [gom]
+    hm = torch.autograd.grad((gxm * uu.to(dev)).sum(), live_m)
+    names = (["Ya", "ln_w", "ln_b", "alpha_dot"] if use_ln else ["Ya", "alpha_dot"]) + ["grad_out"]
+    for a, r, name in zip(hm, hr, names):
+        assert rel_err(a, r) < 5e-5, name
