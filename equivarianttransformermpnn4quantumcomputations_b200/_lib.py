@@ -79,6 +79,7 @@ _PROTOS = {
     "eqv2_equiv_norm_bwd2": [P, P, P, P, P, P, P, P, P, L, I, I, I, P, P, P],
     "eqv2_rbf_fwd": [P, P, L, I, P, F, P],
     "eqv2_rbf_bwd": [P, P, P, L, I, P, F, P],
+    "eqv2_rbf_bwd2": [P, P, P, P, P, L, I, P, F, P],
     "eqv2_edge_sh": [P, P, L, I, P],
     "eqv2_rbf_linear_fwd": [P, P, P, P, P, P, P, P, P, L, I, I, F, F, F, I, P],
     "eqv2_rbf_linear_chunk": [],

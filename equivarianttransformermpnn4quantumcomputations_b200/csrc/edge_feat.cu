@@ -276,6 +276,35 @@ extern "C" int eqv2_rbf_fwd(const float* d, float* out, long long E, int R, cons
   return 0;
 }
 
+// derivative of rbf_bwd for a cotangent u [E] of dd:  dd[e] = sum_k go[e,k] g_k(d),  g_k = 2 c (d - mu_k) rbf_k(d)
+//   d(go)[e,k] = u[e] g_k(d[e]);   d(d)[e] = u[e] sum_k go[e,k] (2 c + (2 c (d - mu_k))^2) rbf_k(d[e])
+__global__ void rbf_bwd2_kernel(const float* __restrict__ d, const float* __restrict__ go, const float* __restrict__ u,
+                                float* __restrict__ dgo, float* __restrict__ d2d, long long E, int R,
+                                const float* __restrict__ offset, float coeff) {
+  const int lane = threadIdx.x & 31;
+  const long long e = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  if (e >= E) return;   // whole warp exits together
+  const float de = d[e], ue = u[e];
+  float acc = 0.f;
+  for (int k = lane; k < R; k += 32) {
+    const float t = de - offset[k];
+    const float r = expf(coeff * t * t);
+    const float g1 = 2.f * coeff * t;
+    dgo[e * R + k] = ue * g1 * r;
+    acc = fmaf(go[e * R + k], (2.f * coeff + g1 * g1) * r, acc);
+  }
+  acc = eqv2_warp_sum(acc);
+  if (lane == 0) d2d[e] = ue * acc;
+}
+
+extern "C" int eqv2_rbf_bwd2(const float* d, const float* go, const float* u, float* dgo, float* d2d, long long E, int R,
+                             const float* offset, float coeff, void* stream) {
+  if (E == 0) return 0;
+  EQV2_LAUNCH(rbf_bwd2_kernel, dim3((unsigned)((E * 32 + 255) / 256)), dim3(256), 0, stream, d, go, u, dgo, d2d, E, R, offset, coeff);
+  EQV2_CHECK_LAUNCH("eqv2_rbf_bwd2");
+  return 0;
+}
+
 extern "C" int eqv2_rbf_bwd(const float* d, const float* go, float* dd, long long E, int R, const float* offset,
                             float coeff, void* stream) {
   if (E == 0) return 0;

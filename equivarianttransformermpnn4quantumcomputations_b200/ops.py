@@ -1758,25 +1758,14 @@ class EdgeActAlphaFn(torch.autograd.Function):
 
 
 # ----------------------------------------------------------------------------------------------
-# small per-row operators.  Forward and first-order backward are kernels.  When the backward pass itself is
-# being recorded (create_graph=True: forces by autograd), its derivative is obtained by re-expressing the
-# operator with torch primitives on the saved inputs and differentiating that expression -- these
-# operators are a negligible share of the step and their second derivatives are lengthy (LayerNorm of
-# LayerNorm-gradient terms); the heavy operators (GEMMs, rotations, S2 grids) differentiate through kernels.
+# small per-row operators (LayerNorm+SiLU of the radial MLP, attention logits + segment softmax, equivariant norms, RBF).
+# Forward and first-order backward are kernels.  When the backward pass itself is being recorded (create_graph=True:
+# forces by autograd), the backward runs as a differentiable operator of its own (`*BwdFn`) whose backward is a
+# CLOSED-FORM second-order kernel (`eqv2_ln_silu_bwd2`, `eqv2_attn_alpha_bwd2`, `eqv2_equiv_norm_bwd2`, `eqv2_rbf_bwd2`;
+# r02 -- round 1 re-expressed the operator with torch primitives here) for a cotangent of the INPUT gradient -- the case of
+# the force loss, where the first backward only feeds the position gradient.  Only a cotangent of a PARAMETER gradient
+# (differentiating weight gradients again: no reference script does) still takes the generic torch-expression route.
 # ----------------------------------------------------------------------------------------------
-def _second_order(fn, inputs, gout):
-    """Gradients of fn(*inputs) w.r.t. the inputs that require grad, as differentiable functions of
-    (inputs, gout).  Called from a backward running under create_graph=True."""
-    with torch.enable_grad():
-        out = fn(*inputs)
-        idx = [i for i, t in enumerate(inputs) if t is not None and t.requires_grad]
-        grads = torch.autograd.grad(out, [inputs[i] for i in idx], gout, create_graph=True, allow_unused=True)
-    res = [None] * len(inputs)
-    for i, g in zip(idx, grads):
-        res[i] = g
-    return res
-
-
 def _recording(*tensors):
     return torch.is_grad_enabled() and any(t is not None and t.requires_grad for t in tensors)
 
@@ -2108,15 +2097,36 @@ class RbfFn(torch.autograd.Function):
     @staticmethod
     def backward(ctx, go):
         d, offset = ctx.saved_tensors
-        coeff = ctx.coeff
-        if _recording(d, go):
-            g = _second_order(lambda d_: torch.exp(coeff * (d_.view(-1, 1) - offset.view(1, -1)) ** 2), [d], go)
-            return g[0], None, None
-        go = go.contiguous()
-        gd = torch.empty_like(d)
-        _lib.call("eqv2_rbf_bwd", d.data_ptr(), go.data_ptr(), gd.data_ptr(), d.shape[0], offset.shape[0],
-                  offset.data_ptr(), coeff, _lib.stream_ptr())
-        return gd, None, None
+        if _recording(d, go):              # forces by autograd: differentiable backward (RbfBwdFn)
+            return RbfBwdFn.apply(d, go.contiguous(), offset, ctx.coeff), None, None
+        return _rbf_bwd(d, go.contiguous(), offset, ctx.coeff), None, None
+
+
+def _rbf_bwd(d, go, offset, coeff):
+    gd = torch.empty_like(d)
+    _lib.call("eqv2_rbf_bwd", d.data_ptr(), go.data_ptr(), gd.data_ptr(), d.shape[0], offset.shape[0],
+              offset.data_ptr(), coeff, _lib.stream_ptr())
+    return gd
+
+
+class RbfBwdFn(torch.autograd.Function):
+    """dd = sum_k go_k d/dd rbf_k(d) as a differentiable operator of (d, go); its backward is `eqv2_rbf_bwd2`."""
+
+    @staticmethod
+    def forward(ctx, d, go, offset, coeff):
+        ctx.save_for_backward(d, go, offset)
+        ctx.coeff = coeff
+        return _rbf_bwd(d, go, offset, coeff)
+
+    @staticmethod
+    @torch.autograd.function.once_differentiable
+    def backward(ctx, u):
+        d, go, offset = ctx.saved_tensors
+        u = u.contiguous()
+        dgo, d2d = torch.empty_like(go), torch.empty_like(d)
+        _lib.call("eqv2_rbf_bwd2", d.data_ptr(), go.data_ptr(), u.data_ptr(), dgo.data_ptr(), d2d.data_ptr(), d.shape[0],
+                  offset.shape[0], offset.data_ptr(), ctx.coeff, _lib.stream_ptr())
+        return d2d, dgo, None, None
 
 
 # ----------------------------------------------------------------------------------------------

@@ -232,6 +232,9 @@ int eqv2_rbf_fwd(const float* d, float* out /*[E,R]*/, long long E, int R, const
                  void* stream);
 int eqv2_rbf_bwd(const float* d, const float* go, float* dd, long long E, int R, const float* offset, float coeff,
                  void* stream);
+/* derivative of eqv2_rbf_bwd's dd w.r.t. (go, d) for a cotangent u [E] of dd (double backward of the force loss) */
+int eqv2_rbf_bwd2(const float* d, const float* go, const float* u, float* dgo /*[E,R]*/, float* d2d /*[E]*/, long long E,
+                  int R, const float* offset, float coeff, void* stream);
 /* real SH of the edge direction, l = 1..lmax, |Y_l| = 1 (e3nn SphericalHarmonics(normalize=False,
  * normalization='norm') at equiformerv2_MatPES_GATAV2.py:137-140,232-241); out [E, (lmax+1)^2 - 1] */
 int eqv2_edge_sh(const float* vec /*[E,3]*/, float* out, long long E, int lmax, void* stream);

@@ -105,3 +105,30 @@ def test_attn_alpha_double_backward(backend, use_ln, heads, ach):
     names = (["Ya", "ln_w", "ln_b", "alpha_dot"] if use_ln else ["Ya", "alpha_dot"]) + ["grad_out"]
     for a, r, name in zip(hm, hr, names):
         assert rel_err(a, r) < 5e-5, name
+
+
+def test_rbf_double_backward(backend):
+    ops = pkg("ops")
+    gen = torch.Generator().manual_seed(5)
+    E, R, cutoff = 83, 600, 6.0
+    d = torch.rand(E, generator=gen) * cutoff
+    offset = torch.linspace(0.0, cutoff, R)
+    coeff = -0.5 / (2.0 * float(offset[1] - offset[0])) ** 2
+    go = torch.randn(E, R, generator=gen)
+    uu = torch.randn(E, generator=gen)
+
+    dr = d.double().requires_grad_(True)
+    yr = torch.exp(coeff * (dr.view(-1, 1) - offset.double().view(1, -1)) ** 2)
+    gor = go.double().requires_grad_(True)
+    (gdr,) = torch.autograd.grad(yr, dr, gor, create_graph=True)
+    hr = torch.autograd.grad((gdr * uu.double()).sum(), [dr, gor])
+
+    dev = backend.device
+    dm = d.clone().to(dev).requires_grad_(True)
+    ym = ops.rbf(dm, offset.to(dev), coeff)
+    assert rel_err(ym, yr) < 2e-6
+    gom = go.clone().to(dev).requires_grad_(True)
+    (gdm,) = torch.autograd.grad(ym, dm, gom, create_graph=True)
+    assert rel_err(gdm, gdr) < 1e-5
+    hm = torch.autograd.grad((gdm * uu.to(dev)).sum(), [dm, gom])
+    assert rel_err(hm[0], hr[0]) < 2e-5 and rel_err(hm[1], hr[1]) < 2e-5
