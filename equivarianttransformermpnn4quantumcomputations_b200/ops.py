@@ -1845,6 +1845,7 @@ class AttnAlphaBwdFn(torch.autograd.Function):
         ctx.save_for_backward(Ya, ln_w, ln_b, alpha_dot, alpha, galpha, dlogits)
         ctx.plan, ctx.meta = plan, (heads, ach)
         ctx.has_ln = ln_w is not None
+        ctx.set_materialize_grads(False)
         if not ctx.has_ln:
             return gY, g_dot
         return gY, g_lnw, g_lnb, g_dot
@@ -1853,6 +1854,8 @@ class AttnAlphaBwdFn(torch.autograd.Function):
     def backward(ctx, u, *rest):
         Ya, ln_w, ln_b, alpha_dot, alpha, galpha, dlogits = ctx.saved_tensors
         plan, (heads, ach) = ctx.plan, ctx.meta
+        if u is None and all(r is None for r in rest):
+            return (None,) * 9
         if any(r is not None for r in rest):
             fn = _alpha_expr(heads, ach, 1e-5, plan.dst, plan.N)
             with torch.enable_grad():
@@ -1979,12 +1982,15 @@ class EquivNormBwdFn(torch.autograd.Function):
         gx, gw, gb = _equiv_norm_bwd(x, w, go, inv, mean, norm_type, lmax)
         ctx.save_for_backward(x, w, b, go, inv, mean)
         ctx.meta = meta
+        ctx.set_materialize_grads(False)
         return gx, gw, gb
 
     @staticmethod
     def backward(ctx, u, uw, ub):
         x, w, b, go, inv, mean = ctx.saved_tensors
         norm_type, lmax, eps = ctx.meta
+        if u is None and uw is None and ub is None:
+            return None, None, None, None, None, None, None
         if uw is not None or ub is not None:
             fn = _equiv_norm_expr(norm_type, lmax, eps)
             with torch.enable_grad():
@@ -2053,12 +2059,15 @@ class LnSiluBwdFn(torch.autograd.Function):
         gx, gw, gb = _ln_silu_bwd(x, w, b, gy, eps)
         ctx.save_for_backward(x, w, b, gy)
         ctx.eps = eps
+        ctx.set_materialize_grads(False)      # cotangents of unused outputs (gw, gb in the force pass) arrive as None
         return gx, gw, gb
 
     @staticmethod
     def backward(ctx, u, uw, ub):
         x, w, b, gy = ctx.saved_tensors
         eps = ctx.eps
+        if u is None and uw is None and ub is None:
+            return None, None, None, None, None
         if uw is not None or ub is not None:
             Fn = torch.nn.functional
             with torch.enable_grad():

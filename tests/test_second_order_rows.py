@@ -7,6 +7,23 @@ import torch
 from helpers import pkg, rel_err
 
 
+@pytest.fixture(autouse=True)
+def _kernel_path_is_taken(monkeypatch):
+    """Every test here must reach the closed-form kernel, not the generic torch route kept for cotangents of parameter
+    gradients: record the C-ABI entry points that were called."""
+    _lib = pkg("_lib")
+    calls = []
+    orig = _lib.call
+
+    def spy(name, *a, **k):
+        calls.append(name)
+        return orig(name, *a, **k)
+
+    monkeypatch.setattr(_lib, "call", spy)
+    yield calls
+    assert any(n.endswith("_bwd2") for n in calls), sorted(set(calls))
+
+
 @pytest.mark.parametrize("rows,width", [(37, 128), (5, 16), (64, 200)])
 def test_ln_silu_double_backward(backend, rows, width):
     ops = pkg("ops")
