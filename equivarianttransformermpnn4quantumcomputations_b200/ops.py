@@ -902,6 +902,20 @@ def _slice_outer(U, V, us, vs):
     return outs, ([_split_of(sp, descs[0].src[0]), _split_of(sp, descs[0].src[1])] if descs else [None, None])
 
 
+def _grad_wanted(t):
+    """Will the autograd engine consume a gradient for `t` in the backward pass that is running NOW?  `ctx.needs_input_grad`
+    only says that `t` requires grad at all; in the force pass of the MatPES family (`autograd.grad(E, pos,
+    create_graph=True)`, train_MatPES_GATAWandB.py:72-77) no parameter gradient is wanted, and computing the weight-gradient
+    GEMMs there anyway (a third of that pass) would be thrown away -- the reference's pure-autograd path prunes them too.
+    The engine knows: it executes a node only if some requested input lies behind it.  Conservative on any doubt."""
+    if t is None or not t.requires_grad:
+        return False
+    try:
+        return bool(torch._C._will_engine_execute_node(torch.autograd.graph.get_gradient_edge(t).node))
+    except Exception:       # leaf passed as an explicit autograd.grad input, API missing, not inside a backward pass, ...
+        return True
+
+
 class SliceMm(torch.autograd.Function):
     @staticmethod
     def forward(ctx, X, bias, xs, ys, y_width, transW, *Ws):
@@ -910,6 +924,7 @@ class SliceMm(torch.autograd.Function):
         Y, ctx.splits = _slice_mm(X, bias, xs, ys, y_width, transW, Ws)
         ctx.save_for_backward(X, *Ws)
         ctx.spec = (xs, ys, y_width, transW, bias is not None)
+        ctx.bias_wanted = (lambda b=bias: _grad_wanted(b))       # the bias is only needed for this query
         return Y
 
     @staticmethod
@@ -920,15 +935,15 @@ class SliceMm(torch.autograd.Function):
         gWs = [None] * len(Ws)
         gY = gY.contiguous()
         with split_scope(zip([X, *Ws], ctx.splits)):      # forward splits of X / W; gY's is made once and shared
-            if ctx.needs_input_grad[0]:
+            if ctx.needs_input_grad[0] and _grad_wanted(X):
                 gX = SliceMm.apply(gY, None, ys, xs, X.shape[1], not transW, *Ws)
-            if any(ctx.needs_input_grad[6:]):
+            if any(ctx.needs_input_grad[6:]) and any(_grad_wanted(W) for W in Ws):
                 if transW:      # W_g [n,k]: gW = gY_g^T X_g
                     outs = SliceOuter.apply(gY, X, ys, xs)
                 else:           # W_g [k,n]: gW = X_g^T gY_g
                     outs = SliceOuter.apply(X, gY, xs, ys)
                 gWs = list(outs) if isinstance(outs, tuple) else [outs]
-        if has_bias and ctx.needs_input_grad[1]:
+        if has_bias and ctx.needs_input_grad[1] and ctx.bias_wanted():
             yo, n = ys[0]
             gb = colsum(gY, yo, n)
         return (gX, gb, None, None, None, None, *gWs)
@@ -952,9 +967,9 @@ class SliceOuter(torch.autograd.Function):
                for g, ((_, m), (_, n)) in zip(gWs, zip(us, vs))]
         gU = gV = None
         with split_scope(zip([U, V], ctx.splits)):
-            if ctx.needs_input_grad[0]:     # gU_g = V_g @ gW_g^T
+            if ctx.needs_input_grad[0] and _grad_wanted(U):     # gU_g = V_g @ gW_g^T
                 gU = SliceMm.apply(V, None, vs, us, U.shape[1], True, *gWs)
-            if ctx.needs_input_grad[1]:     # gV_g = U_g @ gW_g
+            if ctx.needs_input_grad[1] and _grad_wanted(V):     # gV_g = U_g @ gW_g
                 gV = SliceMm.apply(U, None, us, vs, V.shape[1], False, *gWs)
         return gU, gV, None, None
 
@@ -980,6 +995,7 @@ class SlabMm(torch.autograd.Function):
         sp = run_gemm(descs, out=y) if N > 0 else {}
         ctx.save_for_backward(x, W)
         ctx.spec = (transW, bias is not None)
+        ctx.bias_wanted = (lambda b=bias: _grad_wanted(b))
         ctx.splits = [_split_of(sp, descs[0].src[0]), _split_of(sp, descs[0].src[1])]
         return y
 
@@ -990,11 +1006,11 @@ class SlabMm(torch.autograd.Function):
         gx = gW = gb = None
         gy = gy.contiguous()
         with split_scope(zip([x, W], ctx.splits)):
-            if ctx.needs_input_grad[0]:
+            if ctx.needs_input_grad[0] and _grad_wanted(x):
                 gx = SlabMm.apply(gy, W, None, not transW)
-            if ctx.needs_input_grad[1]:
+            if ctx.needs_input_grad[1] and _grad_wanted(W):
                 gW = SlabOuter.apply(gy, x) if transW else SlabOuter.apply(x, gy)
-        if has_bias and ctx.needs_input_grad[2]:
+        if has_bias and ctx.needs_input_grad[2] and ctx.bias_wanted():
             gb = gy[:, 0, :].sum(0)
         return gx, gW, gb, None
 
@@ -1029,9 +1045,9 @@ class SlabOuter(torch.autograd.Function):
         gU = gV = None
         gW = gW.contiguous()
         with split_scope(zip([U, V], ctx.splits)):
-            if ctx.needs_input_grad[0]:     # gU_l = V_l @ gW_l^T
+            if ctx.needs_input_grad[0] and _grad_wanted(U):     # gU_l = V_l @ gW_l^T
                 gU = SlabMm.apply(V, gW, None, True)
-            if ctx.needs_input_grad[1]:     # gV_l = U_l @ gW_l
+            if ctx.needs_input_grad[1] and _grad_wanted(V):     # gV_l = U_l @ gW_l
                 gV = SlabMm.apply(U, gW, None, False)
         return gU, gV
 
