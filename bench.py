@@ -106,6 +106,9 @@ def parse():
     ap.add_argument("--no-dropout", action="store_true", help="alpha_drop = drop_path_rate = 0")
     ap.add_argument("--bucket", default=None, help="pad every batch to multiples ATOMS,EDGES (e.g. 64,512) with a masked "
                     "ghost structure so that one captured graph serves a whole bucket of batch sizes")
+    ap.add_argument("--grad-sync", default="overlap", choices=["overlap", "flat"],
+                    help="N > 1: 'overlap' = bucket all-reduces issued from inside the (captured) backward pass on a side "
+                         "stream, gradients live in the flat buckets; 'flat' = copy / all-reduce / copy back after it")
     ap.add_argument("--optimizer", default="fused", choices=["fused", "torch"],
                     help="fused: clip_grad_norm_ + AdamW + EMA as one multi-tensor pass (optim.FusedAdamW, the reference's "
                          "optimizer-side step); torch: torch.optim.AdamW(fused=True) alone (the round-1 step)")
@@ -412,7 +415,10 @@ def run_b200(args):
         sync = None
         if world > 1:
             parallel = importlib.import_module(PKG + ".parallel")
-            sync = parallel.GradientAllReducer(model.parameters(), bucket_mb=64).reduce
+            if args.grad_sync == "overlap":
+                sync = parallel.OverlappedGradientAllReducer(model.parameters(), bucket_mb=32)
+            else:
+                sync = parallel.GradientAllReducer(model.parameters(), bucket_mb=64).reduce
         bucket = tuple(int(v) for v in args.bucket.split(",")) if args.bucket else None
         stepper = graphs.GraphedTrainStep(model, None, opt, grad_sync=sync, bucket=bucket,
                                           forward_loss=lambda d: forward_loss(cfg, model, d))
@@ -489,8 +495,12 @@ def run_b200(args):
                 "workload_detail": {"atoms_per_gpu": int(host["pos"].shape[0]), "edges_per_gpu": E,
                                     "params": model.num_params,
                                     "peak_mem_gb": round(torch.cuda.max_memory_allocated() / 1e9, 2),
-                                    "launch": ("CUDA graph replay of forward+loss+backward; neighbour list, edge frames, "
-                                               "gradient all-reduce (NCCL, N > 1) and AdamW eager" if use_graph
+                                    "launch": (("CUDA graph replay of forward+loss+backward" +
+                                                (" with the bucketed NCCL gradient all-reduce captured inside the backward "
+                                                 "pass on a side stream" if world > 1 and args.grad_sync == "overlap" else "") +
+                                                "; neighbour list, edge frames" +
+                                                (", gradient all-reduce (NCCL, flat buckets)" if world > 1 and
+                                                 args.grad_sync != "overlap" else "") + " and AdamW eager") if use_graph
                                                else "eager (every kernel enqueued from Python; DDP when N > 1)"),
                                     "gemm_engine": engine_note[0],
                                     "optimizer": ("FusedAdamW: gradient-norm clip (100) + AdamW (wd 1e-3) + EMA (0.999) in one "

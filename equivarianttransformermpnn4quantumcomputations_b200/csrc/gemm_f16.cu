@@ -358,12 +358,13 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) gemm_f16_kernel(const __grid_c
       const bool atomic = P.split_k > 1;
       const float sc = ia * ib;
       float cmax = 0.f;                                     // max |C| of what this thread stores (c_absmax)
-      // Fast path (plain row-major C, 16-byte aligned rows, N % 4 == 0, no split-K): the accumulators are row-per-lane,
+      // Fast path (plain row-major C, 16-byte aligned rows, N % 4 == 0): the accumulators are row-per-lane,
       // so a direct float4 store touches 32 different 128-byte lines per warp instruction (512 LSU tag cycles per warp and
       // tile, 4 096 per tile over the 8 worker warps: longer than the MMAs of a K = 128 tile).  Each warp instead passes
       // 16 x 32 blocks through a padded shared-memory patch and stores 4 rows x 128 bytes per instruction: same number
-      // of store instructions, 8x fewer lines per instruction.
-      const bool fast = !atomic && (G.ldc & 3) == 0 && (G.c_bs & 3) == 0 && (G.N & 3) == 0 &&
+      // of store instructions, 8x fewer lines per instruction.  Split-K partial tiles take the same route with one
+      // 16-byte vector reduction (red.global.add.v4.f32) per float4 instead of four scalar atomics on 32 lines each.
+      const bool fast = (G.ldc & 3) == 0 && (G.c_bs & 3) == 0 && (G.N & 3) == 0 &&
                         (reinterpret_cast<uintptr_t>(G.C) & 15) == 0 && ((W.n0 & 3) == 0);
       if (fast) {
         float* patch = epi_patch + (warp - 2) * (16 * 36);
@@ -373,7 +374,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) gemm_f16_kernel(const __grid_c
           const int col = W.n0 + half * 64 + cc * 32 + c4;
           const bool col_ok = col < G.N;
           float4 bv = make_float4(0.f, 0.f, 0.f, 0.f);
-          if (G.bias != nullptr && col_ok) bv = __ldg(reinterpret_cast<const float4*>(G.bias + col));
+          if (G.bias != nullptr && col_ok && W.ks == 0) bv = __ldg(reinterpret_cast<const float4*>(G.bias + col));
 #pragma unroll
           for (int rh = 0; rh < 2; ++rh) {
             if ((lane >> 4) == rh) {
@@ -397,6 +398,11 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) gemm_f16_kernel(const __grid_c
                 }
                 float* cp = G.C + roff + col;
                 o.x += bv.x; o.y += bv.y; o.z += bv.z; o.w += bv.w;
+                if (atomic) {
+                  asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(cp), "f"(o.x), "f"(o.y), "f"(o.z), "f"(o.w)
+                               : "memory");
+                  continue;
+                }
                 if (G.accumulate) {
                   const float4 p = *reinterpret_cast<const float4*>(cp);
                   o.x += p.x; o.y += p.y; o.z += p.z; o.w += p.w;

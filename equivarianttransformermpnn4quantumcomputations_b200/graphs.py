@@ -23,11 +23,15 @@ class GraphedTrainStep:
         """model(data) -> outputs; loss_fn(outputs, data) -> scalar -- or `forward_loss(data)` -> scalar for steps that
         need more than that (MatPES: forces = -autograd.grad(E, pos, create_graph=True) inside the loss).
         `model.prepare(data)` must return the dict of data-dependent inputs the model then takes from `data` (OC20:
-        edge_index / edge_distance / edge_distance_vec / edge_frames; MatPES v2: edge_index).  `grad_sync()` (data
-        parallel: parallel.GradientAllReducer.reduce, NCCL) runs between the replay and the optimizer update."""
+        edge_index / edge_distance / edge_distance_vec / edge_frames; MatPES v2: edge_index).  `grad_sync`: a callable
+        (data parallel: parallel.GradientAllReducer.reduce, NCCL) that runs between the replay and the optimizer update,
+        or an object with begin() / finish() (parallel.OverlappedGradientAllReducer) whose bucket all-reduces are issued
+        from inside the backward pass and CAPTURED with it: the replayed graph then contains the exchange, overlapped
+        with the rest of the backward pass."""
         self.model, self.loss_fn, self.optimizer = model, loss_fn, optimizer
         self.forward_loss = forward_loss if forward_loss is not None else (lambda d: loss_fn(model(d), d))
-        self.grad_sync = grad_sync
+        self.overlapped = grad_sync if hasattr(grad_sync, "begin") else None
+        self.grad_sync = None if self.overlapped is not None else grad_sync
         self.max_graphs, self.warmup = max_graphs, warmup
         self.bucket = bucket        # (atoms multiple, edges multiple) or None: exact signatures
         self.eager_steps = 0
@@ -48,11 +52,19 @@ class GraphedTrainStep:
             out = batching.pad_to_bucket(out, *self.bucket)
         return out
 
-    def _eager(self, full):
+    def _eager(self, full, sync=True):
         loss = self.forward_loss(full)
         self.optimizer.zero_grad(set_to_none=True)
-        loss.backward()
+        self._backward(loss, sync)
         return loss
+
+    def _backward(self, loss, sync=True):
+        if self.overlapped is not None and sync:
+            self.overlapped.begin()
+            loss.backward()
+            self.overlapped.finish()
+        else:
+            loss.backward()
 
     def _capture(self, full, sig):
         static = {k: (v.clone() if torch.is_tensor(v) else v) for k, v in full.items()}
@@ -62,7 +74,7 @@ class GraphedTrainStep:
         side.wait_stream(torch.cuda.current_stream())
         with torch.cuda.stream(side):               # warm-up off the capture: lazy tables, kernel attributes, allocator
             for _ in range(self.warmup):
-                self._eager(static)
+                self._eager(static, sync=False)     # no exchange: ranks may capture at different steps
         torch.cuda.current_stream().wait_stream(side)
         self.optimizer.zero_grad(set_to_none=True)  # the captured backward then ASSIGNS the .grad tensors it allocates
         torch.cuda.synchronize()
@@ -74,7 +86,7 @@ class GraphedTrainStep:
         graph = torch.cuda.CUDAGraph()
         with torch.cuda.graph(graph, pool=self.pool, stream=side):
             loss = self.forward_loss(static)
-            loss.backward()
+            self._backward(loss)
         ops.reset_caches()
         if self.pool is None:
             self.pool = graph.pool()

@@ -723,6 +723,9 @@ def _find_split(src):
     return None
 
 
+_SPLIT_LOG = None         # diagnostics: set to a list to record (rows, cols, maximum known) of every operand split
+
+
 def _splits_for(srcs):
     """-> {src.key: SplitF16}; the missing splits are made by ONE eqv2_split_f16 call (two kernels)."""
     out, missing = {}, []
@@ -745,6 +748,8 @@ def _splits_for(srcs):
             a.rows, a.cols, a.rows_pad, a.cols_pad, a.slab_k = sp.rows, sp.cols, sp.rows, sp.cols_pad, sp.slab_k
             a.absmax_given = 1 if given else 2          # 2: to be computed, slot already zero (no memset node)
         nb = sum((8.0 if given else 12.0) * sp.rows * sp.cols for _, sp, given in part)
+        if _SPLIT_LOG is not None:
+            _SPLIT_LOG.extend((sp.rows, sp.cols, given) for _, sp, given in part)
         _lib.call("eqv2_split_f16", ctypes.cast(arr, ctypes.c_void_p), len(part), _lib.stream_ptr(),
                   n_kernels=1 if all(g for _, _, g in part) else 2, work=(0.0, nb))
     if _SPLIT_SCOPES:

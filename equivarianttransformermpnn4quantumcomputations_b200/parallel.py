@@ -8,6 +8,9 @@ train_oc20v2_parallel.py:335-346,431-436).
   GradientAllReducer : bucketed flat all-reduce of `.grad` after backward for models DDP cannot wrap
                      (the GATA family leaves some parameters without gradient); grads that
                      are None are sent as zeros so every rank issues the same collectives.
+  OverlappedGradientAllReducer : the same exchange issued bucket by bucket FROM INSIDE the backward pass on a side
+                     stream (what DDP's reducer does, train_oc20v2_parallel.py:431-436), capturable into the CUDA graph
+                     of the step; the gradients then LIVE in the flat buckets (no copy back).
 """
 import torch
 import torch.distributed as dist
@@ -128,3 +131,130 @@ class GradientAllReducer:
                 for v, p in zip(views, self.buckets[i]):
                     if p.grad is None and anywhere[index[id(p)]]:
                         p.grad = v.clone()
+
+
+class OverlappedGradientAllReducer:
+    """Gradient averaging that overlaps the backward pass, and that a CUDA-graph capture of the step can contain.
+
+    Buckets are filled in the order gradients become ready (reverse registration order ~ backward order).  A
+    post-accumulate-grad hook on every parameter counts its bucket down; when a bucket is complete the hook forks a side
+    stream off the stream the backward pass runs on, copies the bucket's gradients into its persistent flat buffer (one
+    multi-tensor copy) and all-reduces the buffer there, while the backward pass carries on.  `finish()` flushes the
+    buckets that never completed (parameters without gradient are sent as zeros, so every rank issues the same
+    collectives in the same order), joins the side stream and re-points `.grad` at the flat views: the optimizer reads
+    the averaged gradients where NCCL left them -- no copy back, and the FusedAdamW pointer table stays valid for ever.
+
+        sync = OverlappedGradientAllReducer(model.parameters())
+        sync.begin(); loss.backward(); sync.finish(); opt.step()
+
+    Inside `torch.cuda.graph` capture the fork / copy / all-reduce / join are captured with the step (NCCL collectives are
+    capturable); nothing is exchanged at capture time, every replay exchanges once.  Hooks are inert outside
+    begin()/finish(), so warm-up passes do not communicate (ranks may capture at different steps).
+    Parameters that did not get a gradient in the previous pass (the GATA family leaves some without) are
+    not waited for in the next one, so their bucket still goes out from inside the backward pass.
+    Requirement (as for DDP): every rank runs the same model, so buckets complete in the same order everywhere."""
+
+    def __init__(self, parameters, bucket_mb=32, group=None):
+        self.params = [p for p in parameters if p.requires_grad]
+        self.group = group
+        limit = bucket_mb * (1 << 20)
+        self.buckets, cur, size = [], [], 0
+        for p in reversed(self.params):
+            cur.append(p)
+            size += p.numel() * p.element_size()
+            if size >= limit:
+                self.buckets.append(cur)
+                cur, size = [], 0
+        if cur:
+            self.buckets.append(cur)
+        self.flat, self.view, self.bucket_of = [], {}, {}
+        for b, bucket in enumerate(self.buckets):
+            flat = torch.zeros(sum(p.numel() for p in bucket), dtype=bucket[0].dtype, device=bucket[0].device)
+            off = 0
+            for p in bucket:
+                self.view[id(p)] = flat[off:off + p.numel()].view_as(p)
+                self.bucket_of[id(p)] = b
+                off += p.numel()
+            self.flat.append(flat)
+        self.cuda = self.params[0].is_cuda
+        self.side = torch.cuda.Stream(device=self.params[0].device) if self.cuda else None
+        self.active = dist.is_initialized() and dist.get_world_size(group) > 1
+        self.avg = self.active and dist.get_backend(group) == "nccl"
+        self.world = dist.get_world_size(group) if self.active else 1
+        self.armed = False
+        self.silent = set()          # id(p) of the parameters that got no gradient in the previous pass
+        self.launched = 0            # buckets sent since begin() (diagnostics / tests)
+        self.handles = [p.register_post_accumulate_grad_hook(self._on_grad) for p in self.params]
+        if self.active and self.cuda:      # create the communicator now: it cannot be created inside a graph capture
+            dist.all_reduce(torch.zeros(1, device=self.params[0].device), group=group)
+            torch.cuda.synchronize()
+
+    def begin(self):
+        """Arm the hooks: call right before the backward pass (inside the capture when the step is captured)."""
+        self.left = [sum(id(p) not in self.silent for p in b) for b in self.buckets]
+        self.fired = set()
+        self.sent = [False] * len(self.buckets)
+        self.launched = 0
+        self.armed = True
+
+    def _on_grad(self, p):
+        if not self.armed:
+            return
+        b = self.bucket_of[id(p)]
+        self.fired.add(id(p))
+        if id(p) in self.silent:         # a gradient that was not there last time: its bucket goes (again) at finish()
+            self.sent[b] = False
+            self.left[b] = -1
+            return
+        self.left[b] -= 1
+        if self.left[b] == 0:
+            self._send(b)
+
+    def _send(self, b):
+        bucket, flat = self.buckets[b], self.flat[b]
+        have = [p for p in bucket if id(p) in self.fired and p.grad is not None]
+        if self.cuda:
+            main = torch.cuda.current_stream()
+            self.side.wait_stream(main)              # fork: everything the backward pass enqueued so far
+            ctx = torch.cuda.stream(self.side)
+        else:
+            import contextlib
+            ctx = contextlib.nullcontext()
+        with ctx:
+            if len(have) < len(bucket):
+                flat.zero_()
+            if have:
+                torch._foreach_copy_([self.view[id(p)] for p in have], [p.grad for p in have])
+            if self.active:
+                dist.all_reduce(flat, op=dist.ReduceOp.AVG if self.avg else dist.ReduceOp.SUM, group=self.group)
+                if not self.avg:
+                    flat.div_(self.world)
+        self.sent[b] = True
+        self.launched += 1
+
+    def finish(self):
+        """After the backward pass: send what is left, join, and let `.grad` be the averaged flat views."""
+        assert self.armed, "finish() without begin()"
+        self.armed = False
+        for b in range(len(self.buckets)):
+            if not self.sent[b]:
+                self._send(b)
+        if self.cuda:
+            torch.cuda.current_stream().wait_stream(self.side)
+        for p in self.params:
+            if id(p) in self.fired and p.grad is not None:
+                p.grad = self.view[id(p)]
+        self.silent = {id(p) for p in self.params if id(p) not in self.fired}
+
+    def reduce(self):
+        """Drop-in for GradientAllReducer.reduce (no overlap): exchange the gradients that exist now."""
+        self.begin()
+        for p in self.params:
+            if p.grad is not None:
+                self._on_grad(p)
+        self.finish()
+
+    def detach(self):
+        for h in self.handles:
+            h.remove()
+        self.handles = []

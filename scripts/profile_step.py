@@ -47,10 +47,18 @@ print("GEMM launches declined by the f16x3 engine (M, N, K, tA, tB, addressable)
 for k, c in seen.most_common(20):
     print(f"  {c:4d} x {k}")
 ops._GEMM16_LOG = []
+ops._SPLIT_LOG = []
 with profile(activities=[ProfilerActivity.CUDA, ProfilerActivity.CPU]) as prof:
     step()
     torch.cuda.synchronize()
 glog, ops._GEMM16_LOG = ops._GEMM16_LOG, None
+slog, ops._SPLIT_LOG = ops._SPLIT_LOG, None
+sagg = collections.Counter()
+for r, c, given in slog:
+    sagg[(r, c, given)] += 1
+print("operand splits (rows, cols, maximum known) x count, MB read+written per step:")
+for (r, c, given), n in sorted(sagg.items(), key=lambda kv: -kv[0][0] * kv[0][1] * kv[1])[:16]:
+    print(f"  {n:4d} x ({r}, {c}, {given})  {n * r * c * (8 if given else 12) / 1e6:8.1f} MB")
 gev = sorted([ev for ev in prof.events() if ev.device_type == torch.autograd.DeviceType.CUDA and "gemm_f16_kernel" in ev.name],
              key=lambda ev: ev.time_range.start)
 if len(gev) == len(glog):
