@@ -113,6 +113,28 @@ struct Eqv2PlaneArgs {
   float bound_c;
   float* bound_out;
 };
+// Asynchronous global -> shared copies (cp.async, SASS LDGSTS) for the software-pipelined node-centric kernels: the data of
+// the NEXT edge of a node's serial edge walk is in flight while the current edge is rotated.  (The emulator copies at once.)
+#ifndef EQV2_CPU_EMU
+__device__ __forceinline__ void eqv2_async_copy4(float* dst_smem, const float* src) {
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"((unsigned)__cvta_generic_to_shared(dst_smem)), "l"(src)
+               : "memory");
+}
+__device__ __forceinline__ void eqv2_async_copy16(float* dst_smem, const float* src) {     // both 16-byte aligned
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"((unsigned)__cvta_generic_to_shared(dst_smem)), "l"(src)
+               : "memory");
+}
+__device__ __forceinline__ void eqv2_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int PENDING>
+__device__ __forceinline__ void eqv2_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(PENDING) : "memory"); }
+#else
+inline void eqv2_async_copy4(float* d, const float* s) { *d = *s; }
+inline void eqv2_async_copy16(float* d, const float* s) { memcpy(d, s, 16); }
+inline void eqv2_async_commit() {}
+template <int PENDING>
+inline void eqv2_async_wait() {}
+#endif
+
 #ifndef EQV2_CPU_EMU
 __device__ __forceinline__ void eqv2_scale_of(float amax, float& s, float& inv) {
   if (!(amax > 0.f) || !(amax < 3.0e38f)) { s = 1.f; inv = 1.f; return; }

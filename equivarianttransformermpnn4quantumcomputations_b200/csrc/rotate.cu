@@ -19,6 +19,7 @@
 // radial slot) is a compile-time constant, the per-thread coefficient column lives in registers, and the
 // edge's Wigner blocks sit in shared memory with rows padded to a multiple of 4 floats so that a row is
 // read with broadcast 128-bit loads (one LDS.128 per 4 FMAs instead of one LDS.32 per FMA).
+#include <stdlib.h>
 #include <type_traits>
 
 #include "common.cuh"
@@ -320,6 +321,187 @@ gather_rotate_dx_kernel(const float* __restrict__ wig, const float* __restrict__
   }
 }
 
+// ---- software-pipelined versions of the two node-centric kernels -------------------------------------------------
+// ncu (profiles/r02_ncu_kernel_summary.txt): the serial edge walk exposes one full memory latency per edge (4.4
+// long-scoreboard stall cycles per issue, 36 % of HBM peak at 16 resident warps per SM).  Here every group keeps S stages
+// in shared memory -- stage = the edge's data columns [ROWS][256] (16-byte cp.async, coalesced 512-byte rows) and its padded
+// Wigner blocks -- and requests edge i + S - 1 before it rotates edge i: one barrier per edge, no exposed load latency.
+// Same arithmetic and summation order as the kernels above (bit-identical results).
+template <int L>
+__device__ __forceinline__ void stage_wigner_async(float* __restrict__ sw, const float* __restrict__ wig_e, int tid, int nthreads) {
+#pragma unroll
+  for (int l = 0; l <= L; ++l) {
+    const int n = 2 * l + 1, ns = pad4(n);
+    const float* src = wig_e + eqv2_wig_off(l);
+    float* dst = sw + wpad_off(l);
+    for (int i = tid; i < n * n; i += nthreads) eqv2_async_copy4(dst + (i / n) * ns + (i % n), src + i);
+  }
+}
+// rows x CW floats of one group: global row stride `gstride`, shared row stride NODE_THREADS; c_lim = valid channels
+__device__ __forceinline__ void stage_rows_async(float* __restrict__ sdst, const float* __restrict__ gsrc, int rows,
+                                                 long long gstride, int CW, int ct, int c_lim) {
+  const int mask = (CW >> 2) - 1;                                  // CW / 4 is a power of two (8, 16 or 32)
+  const int sh = CW >= 128 ? 5 : (CW >= 64 ? 4 : 3);
+  for (int q = ct; q < (rows << sh); q += CW) {
+    const int row = q >> sh, c4 = (q & mask) << 2;
+    if (c4 < c_lim) eqv2_async_copy16(sdst + row * NODE_THREADS + c4, gsrc + (long long)row * gstride + c4);
+  }
+}
+
+template <int L, int M, int S>
+__global__ void __launch_bounds__(NODE_THREADS, 2)
+gather_rotate_dx_pipe_kernel(const float* __restrict__ wig, const float* __restrict__ rad, const float* __restrict__ dA,
+                             const int* __restrict__ rowptr_src, const int* __restrict__ perm_src,
+                             const int* __restrict__ rowptr_dst, const int* __restrict__ perm_dst, float* __restrict__ dx,
+                             int C, int CW, int Kr, int nrad) {
+  constexpr int K = Dim<L>::K, WS = Dim<L>::WS, WP = wpad_off(L + 1);
+  constexpr int KR = mpos<L, M>(L, -M) + 1, NS = nslots<L, M>(), ROWS = KR + NS;
+  EQV2_DYN_SMEM(float, smem);     // S stages of { columns [ROWS][NODE_THREADS] | Wigner [G][WP] }; reused as sred [K][CW]
+  const long long node = blockIdx.x;
+  const int G = NODE_THREADS / CW;
+  const int stage_floats = ROWS * NODE_THREADS + G * WP;
+  const int grp = threadIdx.x / CW, ct = threadIdx.x % CW;
+  const int half = grp & 1, sub = grp >> 1, nsub = G >> 1;
+  const int c0 = blockIdx.y * CW, c = c0 + ct;
+  const bool live = c < C;
+  const int C2 = 2 * C;
+  const int* rowptr = half ? rowptr_dst : rowptr_src;
+  const int* perm = half ? perm_dst : perm_src;
+  const int beg = rowptr[node], len = rowptr[node + 1] - beg;
+  const int len_other = (half ? rowptr_src : rowptr_dst)[node + 1] - (half ? rowptr_src : rowptr_dst)[node];
+  const int maxlen = len > len_other ? len : len_other;
+  const int n_iter = (maxlen + nsub - 1) / nsub;            // same trip count in every group (barriers inside)
+  float acc[K];
+#pragma unroll
+  for (int k = 0; k < K; ++k) acc[k] = 0.f;
+  auto issue = [&](int i) {
+    const int it = sub + i * nsub;
+    if (i < n_iter && it < len) {
+      float* st = smem + (i % S) * stage_floats;
+      const long long e = perm[beg + it];
+      stage_rows_async(st + grp * CW, dA + e * (long long)Kr * C2 + half * C + c0, KR, C2, CW, ct, C - c0);
+      if (rad) stage_rows_async(st + KR * NODE_THREADS + grp * CW, rad + e * (long long)nrad + half * C + c0, NS, C2, CW, ct, C - c0);
+      stage_wigner_async<L>(st + ROWS * NODE_THREADS + grp * WP, wig + e * WS, ct, CW);
+    }
+    eqv2_async_commit();
+  };
+#pragma unroll
+  for (int i = 0; i < S - 1; ++i) issue(i);
+  for (int i = 0; i < n_iter; ++i) {
+    eqv2_async_wait<S - 2>();                               // this thread's copies of stage i have landed ...
+    __syncthreads();                                        // ... and everybody's; stage i - 1 is free again
+    issue(i + S - 1);
+    if (sub + i * nsub >= len || !live) continue;
+    const float* st = smem + (i % S) * stage_floats;
+    const float* gv = st + threadIdx.x;
+    const float* rv = st + KR * NODE_THREADS + threadIdx.x;
+    const float* w = st + ROWS * NODE_THREADS + grp * WP;
+    for_each_degree<0, L, M>([&](auto ld) {
+      constexpr int l = decltype(ld)::value;
+      constexpr int mm = l < M ? l : M;
+      static_for<0, mm + 1>([&](auto mc) {
+        constexpr int m = decltype(mc)::value;
+        constexpr int pp = mpos<L, M>(l, m), pm = mpos<L, M>(l, -m), sl = rslot<L, M>(l, m);
+        const float r = rad ? rv[sl * NODE_THREADS] : 1.0f;
+        row_axpy<l>(w, l + m, gv[pp * NODE_THREADS] * r, acc + l * l);
+        if constexpr (m > 0) row_axpy<l>(w, l - m, gv[pm * NODE_THREADS] * r, acc + l * l);
+      });
+    });
+  }
+  float* sred = smem;
+  for (int g = 1; g < G; ++g) {                            // acc(group 0) += acc(group g), in group order
+    __syncthreads();
+    if (grp == g && live) {
+#pragma unroll
+      for (int k = 0; k < K; ++k) sred[k * CW + ct] = acc[k];
+    }
+    __syncthreads();
+    if (grp == 0 && live) {
+#pragma unroll
+      for (int k = 0; k < K; ++k) acc[k] += sred[k * CW + ct];
+    }
+  }
+  if (grp == 0 && live) {
+#pragma unroll
+    for (int k = 0; k < K; ++k) dx[(node * K + k) * (long long)C + c] = acc[k];
+  }
+}
+
+template <int L, int M, int S>
+__global__ void __launch_bounds__(NODE_THREADS, 2)
+rotinv_reduce_fwd_pipe_kernel(const float* __restrict__ val, const float* __restrict__ alpha, const float* __restrict__ wig,
+                              const int* __restrict__ rowptr_dst, const int* __restrict__ perm_dst, float* __restrict__ out,
+                              int Cv, int CW, int rows_used, long long val_estride, int heads, float scale) {
+  constexpr int K = Dim<L>::K, WS = Dim<L>::WS, WP = wpad_off(L + 1);
+  constexpr int KR = mpos<L, M>(L, -M) + 1, ROWS = KR + 1;         // value rows + the attention weight
+  EQV2_DYN_SMEM(float, smem);
+  const long long node = blockIdx.x;
+  const int G = NODE_THREADS / CW;
+  const int stage_floats = ROWS * NODE_THREADS + G * WP;
+  const int grp = threadIdx.x / CW, ct = threadIdx.x % CW;
+  const int c0 = blockIdx.y * CW, c = c0 + ct;
+  const bool live = c < Cv;
+  const int vch = heads > 0 ? Cv / heads : Cv;
+  float acc[K];
+#pragma unroll
+  for (int k = 0; k < K; ++k) acc[k] = 0.f;
+  const int beg = rowptr_dst[node], end = rowptr_dst[node + 1];
+  const int n_iter = (end - beg + G - 1) / G;
+  auto issue = [&](int i) {
+    const int idx = beg + i * G + grp;
+    if (i < n_iter && idx < end) {
+      float* st = smem + (i % S) * stage_floats;
+      const long long e = perm_dst[idx];
+      stage_rows_async(st + grp * CW, val + e * val_estride + c0, rows_used, Cv, CW, ct, Cv - c0);
+      if (alpha && live) eqv2_async_copy4(st + KR * NODE_THREADS + threadIdx.x, alpha + e * heads + c / vch);
+      stage_wigner_async<L>(st + ROWS * NODE_THREADS + grp * WP, wig + e * WS, ct, CW);
+    }
+    eqv2_async_commit();
+  };
+#pragma unroll
+  for (int i = 0; i < S - 1; ++i) issue(i);
+  for (int i = 0; i < n_iter; ++i) {
+    eqv2_async_wait<S - 2>();
+    __syncthreads();
+    issue(i + S - 1);
+    if (beg + i * G + grp >= end || !live) continue;
+    const float* st = smem + (i % S) * stage_floats;
+    const float* vv = st + threadIdx.x;
+    const float a = alpha ? st[KR * NODE_THREADS + threadIdx.x] : 1.0f;
+    const float* w = st + ROWS * NODE_THREADS + grp * WP;
+    for_each_degree<0, L, M>([&](auto ld) {
+      constexpr int l = decltype(ld)::value;
+      constexpr int mm = l < M ? l : M;
+      static_for<0, 2 * mm + 1>([&](auto mc) {
+        constexpr int m = decltype(mc)::value - mm;
+        constexpr int p = mpos<L, M>(l, m);
+        if (p < rows_used) row_axpy<l>(w, l + m, vv[p * NODE_THREADS] * a, acc + l * l);
+      });
+    });
+  }
+  float* sred = smem;
+  for (int g = 1; g < G; ++g) {
+    __syncthreads();
+    if (grp == g && live) {
+#pragma unroll
+      for (int k = 0; k < K; ++k) sred[k * CW + ct] = acc[k];
+    }
+    __syncthreads();
+    if (grp == 0 && live) {
+#pragma unroll
+      for (int k = 0; k < K; ++k) acc[k] += sred[k * CW + ct];
+    }
+  }
+  if (grp == 0 && live) {
+    for_each_degree<0, L, M>([&](auto ld) {
+      constexpr int l = decltype(ld)::value;
+      const float f = (l > M ? sqrtf(rescale_l(l, M)) : 1.0f) * scale;
+#pragma unroll
+      for (int j = 0; j < 2 * l + 1; ++j) out[(node * K + l * l + j) * (long long)Cv + c] = acc[l * l + j] * f;
+    });
+  }
+}
+
 // ------------------------------------------------------------------------------------------
 // CTA = (destination node, channel slice); group g takes every G-th edge of the node's segment
 template <int L, int M>
@@ -471,6 +653,24 @@ inline int round32(int v) { return (v + 31) / 32 * 32; }
 }  // namespace
 
 // (lmax, mmax) pairs with kernels: every reference config and the test fixtures
+// kernels whose dynamic shared memory can exceed the 48 KB default (staged plane tiles, pipelined node kernels)
+static int plane_smem_attr(const void* kfn, size_t smem) {
+  if (smem <= 48 * 1024) return 0;
+  cudaError_t e = cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  EQV2_REQUIRE(e == cudaSuccess, "rotate kernels: cannot reserve %zu B of shared memory: %s", smem, cudaGetErrorString(e));
+  return 0;
+}
+constexpr size_t NODE_PIPE_SMEM_MAX = 112 * 1024;        // two CTAs per SM
+// EQV2_NODE_PIPE=0 selects the unpipelined node-centric kernels (A/B measurements)
+static int node_env_int(const char* name, int dflt) {
+  const char* v = getenv(name);
+  return (v != nullptr && v[0] != 0) ? atoi(v) : dflt;
+}
+static bool node_pipe_enabled() {
+  const char* v = getenv("EQV2_NODE_PIPE");      // read per call: tests toggle it
+  return v == nullptr || v[0] != '0';
+}
+
 #define EQV2_ROT_CONFIGS(X) X(1, 1) X(2, 1) X(2, 2) X(3, 2) X(3, 3) X(4, 2) X(4, 4) X(5, 2) X(6, 2) X(6, 4) X(6, 6)
 
 #define EQV2_ROT_DISPATCH(NAME, BODY)                                                    \
@@ -505,8 +705,20 @@ extern "C" int eqv2_gather_rotate_dx(const float* wig, const float* rad, const f
   EQV2_REQUIRE(C > 0, "gather_rotate_dx: C=%d out of range", C);
   const int CW = C > 64 ? 128 : (C > 32 ? 64 : 32);      // 2 edge groups (source / destination role) x 128 channels
   const size_t smem = (size_t)(lmax + 1) * (lmax + 1) * CW * sizeof(float);
+  // pipelined version: 16-byte aligned rows, two stages within half an SM's shared memory (2 CTAs per SM)
+  const bool aligned = (C % 4 == 0) && (nrad % 4 == 0) && ((reinterpret_cast<uintptr_t>(dA) | reinterpret_cast<uintptr_t>(rad)) & 15) == 0;
 #define X(L_, M_)                                                                                              \
   if (lmax == L_ && mmax == M_) {                                                                              \
+    constexpr int ROWS_ = (mpos<L_, M_>(L_, -M_) + 1) + nslots<L_, M_>();                                      \
+    const int PCW = node_env_int("EQV2_NODE_CW", CW), PS = node_env_int("EQV2_NODE_STAGES", 2);                 \
+    const size_t psmem = PS * ((size_t)ROWS_ * NODE_THREADS + (NODE_THREADS / PCW) * wpad_off(L_ + 1)) * sizeof(float); \
+    if (aligned && node_pipe_enabled() && psmem <= (PS == 2 ? NODE_PIPE_SMEM_MAX : 224 * 1024)) {               \
+      auto pfn = PS == 3 ? gather_rotate_dx_pipe_kernel<L_, M_, 3> : gather_rotate_dx_pipe_kernel<L_, M_, 2>;  \
+      if (plane_smem_attr((const void*)pfn, psmem)) return 1;                                                  \
+      EQV2_LAUNCH(pfn, dim3((unsigned)N, (C + PCW - 1) / PCW), dim3(NODE_THREADS), psmem, stream, wig, rad, dA, rowptr_src, perm_src, rowptr_dst, perm_dst, dx, C, PCW, Kr, nrad); \
+      EQV2_CHECK_LAUNCH("eqv2_gather_rotate_dx");                                                              \
+      return 0;                                                                                                \
+    }                                                                                                          \
     auto kfn = gather_rotate_dx_kernel<L_, M_>;                                                                \
     EQV2_LAUNCH(kfn, dim3((unsigned)N, (C + CW - 1) / CW), dim3(NODE_THREADS), smem, stream, wig, rad, dA, rowptr_src, perm_src, rowptr_dst, perm_dst, dx, C, CW, Kr, nrad); \
     EQV2_CHECK_LAUNCH("eqv2_gather_rotate_dx");                                                                \
@@ -544,8 +756,19 @@ extern "C" int eqv2_rotinv_reduce_fwd(const float* val, const float* alpha, cons
   EQV2_REQUIRE(alpha == nullptr || (heads > 0 && Cv % heads == 0), "rotinv_reduce_fwd: heads must divide Cv");
   const int CW = Cv > 64 ? 128 : (Cv > 32 ? 64 : 32);
   const size_t smem = (size_t)(lmax + 1) * (lmax + 1) * CW * sizeof(float);
+  const bool aligned = (Cv % 4 == 0) && (val_estride % 4 == 0) && (reinterpret_cast<uintptr_t>(val) & 15) == 0;
 #define X(L_, M_)                                                                                              \
   if (lmax == L_ && mmax == M_) {                                                                              \
+    constexpr int ROWS_ = (mpos<L_, M_>(L_, -M_) + 1) + 1;                                                     \
+    const int PCW = node_env_int("EQV2_NODE_CW", CW), PS = node_env_int("EQV2_NODE_STAGES", 2);                 \
+    const size_t psmem = PS * ((size_t)ROWS_ * NODE_THREADS + (NODE_THREADS / PCW) * wpad_off(L_ + 1)) * sizeof(float); \
+    if (aligned && node_pipe_enabled() && psmem <= (PS == 2 ? NODE_PIPE_SMEM_MAX : 224 * 1024) && rows_used <= ROWS_ - 1) { \
+      auto pfn = PS == 3 ? rotinv_reduce_fwd_pipe_kernel<L_, M_, 3> : rotinv_reduce_fwd_pipe_kernel<L_, M_, 2>; \
+      if (plane_smem_attr((const void*)pfn, psmem)) return 1;                                                  \
+      EQV2_LAUNCH(pfn, dim3((unsigned)N, (Cv + PCW - 1) / PCW), dim3(NODE_THREADS), psmem, stream, val, alpha, wig, rowptr_dst, perm_dst, out, Cv, PCW, rows_used, val_estride, heads, scale); \
+      EQV2_CHECK_LAUNCH("eqv2_rotinv_reduce_fwd");                                                             \
+      return 0;                                                                                                \
+    }                                                                                                          \
     auto kfn = rotinv_reduce_fwd_kernel<L_, M_>;                                                                                    \
     EQV2_LAUNCH(kfn, dim3((unsigned)N, (Cv + CW - 1) / CW), dim3(NODE_THREADS), smem, stream, val, alpha, wig, rowptr_dst, perm_dst, out, Cv, CW, rows_used, val_estride, heads, scale); \
     EQV2_CHECK_LAUNCH("eqv2_rotinv_reduce_fwd");                                                               \
@@ -577,13 +800,8 @@ extern "C" int eqv2_rotinv_reduce_bwd(const float* dout, const float* val, const
 
 #ifndef EQV2_CPU_EMU
 // ---- producer-side operand planes: the same three kernels writing scaled fp16 hi/lo planes instead of fp32 ----------
-// the staged tile can exceed the 48 KB default of dynamic shared memory (lmax 6 / mmax 6: 49 rows x 256 columns x 4 B)
-static int plane_smem_attr(const void* kfn, size_t smem) {
-  if (smem <= 48 * 1024) return 0;
-  cudaError_t e = cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-  EQV2_REQUIRE(e == cudaSuccess, "plane kernels: cannot reserve %zu B of shared memory: %s", smem, cudaGetErrorString(e));
-  return 0;
-}
+// (the staged tile can exceed the 48 KB default of dynamic shared memory: lmax 6 / mmax 6 is 49 rows x 256 columns x 4 B;
+// plane_smem_attr above)
 
 static int check_planes(const char* who, const void* planes, long long plane, long long ld, long long cols,
                         const float* bound_a, const float* bound_out) {
