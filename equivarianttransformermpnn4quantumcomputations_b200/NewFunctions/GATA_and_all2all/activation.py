@@ -75,6 +75,16 @@ def _attend(q, k, values, counts, scale, dropout, bias_fn=None):
     that are mixed with the SAME attention weights; softmax over the atoms of the query's own structure (the reference
     masks cross-graph pairs of an [N_tot, N_tot] map or pads to [B, N_max]: identical weights).  bias_fn(g) -> [H, n, n]
     additive logit bias of structure g.  Returns the list of mixed values, [N, m, H*D] each."""
+    H, D = q.shape[1], q.shape[2]
+    if ops.pair_attention_available(H, D):
+        # one scores / softmax / mix launch for the whole batch on the ragged pair layout (csrc/pair_attn.cu)
+        blocks = None
+        if bias_fn is not None:
+            blocks = [bias_fn(g) for g in range(len(counts))]
+            if any(b is None for b in blocks):
+                assert all(b is None for b in blocks)
+                blocks = None
+        return ops.pair_attention(q, k, values, counts, scale, dropout, blocks)
     outs = [[] for _ in values]
     start = 0
     for g, n in enumerate(counts):

@@ -105,6 +105,11 @@ _PROTOS = {
     "eqv2_gata_value_fwd": [P, P, P, P, L, I, I, I, I, P],
     "eqv2_gata_value_bwd": [P, P, P, P, P, P, L, I, I, I, I, P],
     "eqv2_gata_value_bwd2": [P, P, P, P, P, P, P, P, P, L, I, I, I, I, P],
+    "eqv2_pair_scores": [P, P, P, P, P, P, L, I, I, I, F, P],
+    "eqv2_pair_mix": [P, P, P, P, P, P, L, I, I, I, I, I, P],
+    "eqv2_pair_softmax_fwd": [P, P, P, P, L, I, P],
+    "eqv2_pair_softmax_bwd": [P, P, P, P, P, L, I, P],
+    "eqv2_pair_softmax_bwd2": [P, P, P, P, P, P, P, L, I, P],
     "eqv2_opt_chunk_elems": [],
     "eqv2_grad_sqnorm": [P, P, P, I, F, P, P, P],
     "eqv2_adamw_ema_step": [P, P, P, I, P, F, F, F, I, F, P],

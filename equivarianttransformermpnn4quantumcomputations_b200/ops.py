@@ -2415,6 +2415,178 @@ class GataValueBwdFn(torch.autograd.Function):
         return d2comb, d2Xp, None, dg, None, None
 
 
+# ----------------------------------------------------------------------------------------------
+# all-pairs attention core of the global-attention classes (csrc/pair_attn.cu)
+# ----------------------------------------------------------------------------------------------
+class PairLayout:
+    """Ragged [P, H] layout of the per-structure attention maps: row i owns gcount[i] contiguous entries from rowptr[i]
+    (see include/eqv2_b200.h).  Built from the host-side structure sizes: no device read-back."""
+
+    _cache = {}
+
+    def __init__(self, counts, device):
+        counts = [int(n) for n in counts]
+        self.counts, self.N = counts, sum(counts)
+        self.max_count = max(counts) if counts else 0
+        self.P = sum(n * n for n in counts)
+        gs, gc, rp = [], [], [0]
+        start = 0
+        for n in counts:
+            for _ in range(n):
+                gs.append(start)
+                gc.append(n)
+                rp.append(rp[-1] + n)
+            start += n
+        self.gstart = torch.tensor(gs, dtype=torch.int32, device=device)
+        self.gcount = torch.tensor(gc, dtype=torch.int32, device=device)
+        self.rowptr = torch.tensor(rp, dtype=torch.int64, device=device)
+
+    @classmethod
+    def get(cls, counts, device):
+        key = (tuple(int(n) for n in counts), str(device))
+        hit = cls._cache.get(key)
+        if hit is None:
+            if len(cls._cache) > 64:
+                cls._cache.clear()
+            hit = cls._cache[key] = cls(counts, device)
+        return hit
+
+    def from_blocks(self, blocks):
+        """[H, n_g, n_g] per structure -> [P, H]."""
+        return torch.cat([b.permute(1, 2, 0).reshape(-1, b.shape[0]) for b in blocks], dim=0)
+
+
+def _pair_scores(a, b, lay, scale):
+    N, M, H, D = a.shape
+    S = torch.empty(lay.P, H, dtype=_F32, device=a.device)
+    _lib.call("eqv2_pair_scores", a.data_ptr(), b.data_ptr(), lay.gstart.data_ptr(), lay.gcount.data_ptr(),
+              lay.rowptr.data_ptr(), S.data_ptr(), N, M, H, D, float(scale), _lib.stream_ptr(),
+              work=(2.0 * lay.P * M * H * D, 4.0 * (2 * N * M * H * D + lay.P * H)))
+    return S
+
+
+def _pair_mix(W, b, lay, transpose):
+    N, M, H, D = b.shape
+    out = torch.empty_like(b)
+    _lib.call("eqv2_pair_mix", W.data_ptr(), b.data_ptr(), lay.gstart.data_ptr(), lay.gcount.data_ptr(),
+              lay.rowptr.data_ptr(), out.data_ptr(), N, M, H, D, lay.max_count, 1 if transpose else 0, _lib.stream_ptr(),
+              work=(2.0 * lay.P * M * H * D, 4.0 * (2 * N * M * H * D + lay.P * H)))
+    return out
+
+
+class PairScoresFn(torch.autograd.Function):
+    """S[pair(i,j), h] = scale <a_i, b_j>_h  (activation.py:1533 `einsum('bihd,bjhd->bhij')` per structure)."""
+
+    @staticmethod
+    def forward(ctx, a, b, lay, scale):
+        _lib.check_device(a, b)
+        a, b = a.contiguous(), b.contiguous()
+        ctx.save_for_backward(a, b)
+        ctx.lay, ctx.scale = lay, scale
+        return _pair_scores(a, b, lay, scale)
+
+    @staticmethod
+    def backward(ctx, gS):
+        a, b = ctx.saved_tensors
+        ga = gb = None
+        if gS is not None:
+            gS = gS.contiguous()
+            if ctx.needs_input_grad[0]:
+                ga = PairMixFn.apply(gS, b, ctx.lay, False) * ctx.scale
+            if ctx.needs_input_grad[1]:
+                gb = PairMixFn.apply(gS, a, ctx.lay, True) * ctx.scale
+        return ga, gb, None, None
+
+
+class PairMixFn(torch.autograd.Function):
+    """out_i = sum_j W[pair(i,j)] b_j  (activation.py:1545 `einsum('bhij,bjmhd->bimhd')`); transpose: out_j = sum_i W b_i."""
+
+    @staticmethod
+    def forward(ctx, W, b, lay, transpose):
+        _lib.check_device(W, b)
+        W, b = W.contiguous(), b.contiguous()
+        ctx.save_for_backward(W, b)
+        ctx.lay, ctx.transpose = lay, transpose
+        return _pair_mix(W, b, lay, transpose)
+
+    @staticmethod
+    def backward(ctx, gout):
+        W, b = ctx.saved_tensors
+        gW = gb = None
+        if gout is not None:
+            gout = gout.contiguous()
+            if ctx.needs_input_grad[0]:
+                gW = PairScoresFn.apply(b, gout, ctx.lay, 1.0) if ctx.transpose else PairScoresFn.apply(gout, b, ctx.lay, 1.0)
+            if ctx.needs_input_grad[1]:
+                gb = PairMixFn.apply(W, gout, ctx.lay, not ctx.transpose)
+        return gW, gb, None, None
+
+
+class PairSoftmaxFn(torch.autograd.Function):
+    """softmax over the atoms of the query's structure (the reference's masked / padded softmax, activation.py:1541)."""
+
+    @staticmethod
+    def forward(ctx, S, lay):
+        _lib.check_device(S)
+        S = S.contiguous()
+        Pw = torch.empty_like(S)
+        _lib.call("eqv2_pair_softmax_fwd", S.data_ptr(), lay.gcount.data_ptr(), lay.rowptr.data_ptr(), Pw.data_ptr(),
+                  lay.N, S.shape[1], _lib.stream_ptr(), work=(0.0, 8.0 * S.numel()))
+        ctx.save_for_backward(Pw)
+        ctx.lay = lay
+        return Pw
+
+    @staticmethod
+    def backward(ctx, gP):
+        (Pw,) = ctx.saved_tensors
+        return PairSoftmaxBwdFn.apply(Pw, gP, ctx.lay), None
+
+
+class PairSoftmaxBwdFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, Pw, gP, lay):
+        gP = gP.contiguous()
+        gS = torch.empty_like(Pw)
+        _lib.call("eqv2_pair_softmax_bwd", Pw.data_ptr(), gP.data_ptr(), lay.gcount.data_ptr(), lay.rowptr.data_ptr(),
+                  gS.data_ptr(), lay.N, Pw.shape[1], _lib.stream_ptr(), work=(0.0, 12.0 * Pw.numel()))
+        ctx.save_for_backward(Pw, gP)
+        ctx.lay = lay
+        return gS
+
+    @staticmethod
+    @torch.autograd.function.once_differentiable
+    def backward(ctx, u):
+        Pw, gP = ctx.saved_tensors
+        lay = ctx.lay
+        u = u.contiguous()
+        dP, dgP = torch.empty_like(Pw), torch.empty_like(Pw)
+        _lib.call("eqv2_pair_softmax_bwd2", Pw.data_ptr(), gP.data_ptr(), u.data_ptr(), lay.gcount.data_ptr(),
+                  lay.rowptr.data_ptr(), dP.data_ptr(), dgP.data_ptr(), lay.N, Pw.shape[1], _lib.stream_ptr(),
+                  work=(0.0, 20.0 * Pw.numel()))
+        return dP, dgP, None
+
+
+def pair_attention(q, k, values, counts, scale, dropout=None, bias_blocks=None):
+    """Per-structure multi-head attention for all structures at once: q, k [N, H, D]; values: list of [N, m, H, D] mixed
+    with the SAME weights; bias_blocks: list of [H, n_g, n_g] additive logit biases or None.  -> list of [N, m, H*D]."""
+    N, H, D = q.shape
+    lay = PairLayout.get(counts, q.device)
+    S = PairScoresFn.apply(q.reshape(N, 1, H, D), k.reshape(N, 1, H, D), lay, scale)
+    if bias_blocks is not None:
+        S = S + lay.from_blocks(bias_blocks)
+    Pw = PairSoftmaxFn.apply(S, lay)
+    if dropout is not None:
+        Pw = dropout(Pw)
+    sizes = [v.shape[1] for v in values]
+    V = values[0] if len(values) == 1 else torch.cat(values, dim=1)
+    out = PairMixFn.apply(Pw, V, lay, False)
+    return [o.reshape(N, m, H * D) for o, m in zip(torch.split(out, sizes, dim=1), sizes)]
+
+
+def pair_attention_available(H, D):
+    return D % 4 == 0 and ((D // 4) & (D // 4 - 1)) == 0 and D // 4 <= 32
+
+
 def gata_value(comb, Xp, rl, lmax, mmax):
     return GataValueFn.apply(comb.contiguous(), Xp.contiguous(), rl.contiguous(), lmax, mmax)
 

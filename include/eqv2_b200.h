@@ -331,6 +331,29 @@ int eqv2_gata_value_bwd2(const float* comb, const float* Xp, const float* rl, co
                          const float* v, float* dg, float* d2comb, float* d2Xp, long long E, int H, int lmax, int mmax,
                          int Kr, void* stream);
 
+/* ---- all-pairs attention core of the global-attention classes (NewFunctions/GATA_and_all2all/activation.py:419-1567:
+ * `attn = softmax(q k^T * scale + bias)` over the atoms of the query's own structure, `out_l = attn @ v_l`; the reference
+ * forms an [N_tot, N_tot] map and masks cross-structure pairs) -------------------------------------------------------
+ * Ragged pair tensors [P, H], P = sum_g n_g^2: row i (atom of structure g: first atom gstart[i], gcount[i] atoms) owns the
+ * contiguous entries rowptr[i] + (j - gstart[i]).  Node tensors a, b, out are [N, M, H, D] fp32, D = 4 x a power of two.
+ *   eqv2_pair_scores      : S[pair(i,j), h] = scale * sum_{m,d} a[i,m,h,d] b[j,m,h,d]
+ *   eqv2_pair_mix         : out[i,m,h,d] = sum_j W[pair(i,j), h] b[j,m,h,d]   (transpose != 0: out[j] = sum_i W[pair(i,j)] b[i]);
+ *                           max_count = largest structure (shared-memory sizing)
+ *   eqv2_pair_softmax_fwd : Pw = softmax over each row and head
+ *   eqv2_pair_softmax_bwd : gS = Pw (gP - sum_j Pw gP)
+ *   eqv2_pair_softmax_bwd2: for a cotangent u of gS: dgP = Pw (u - q), dP = u (gP - r) - gP q  (r = sum Pw gP, q = sum Pw u)
+ * scores / mix are each other's derivatives (csrc/pair_attn.cu), so the double backward of a force loss needs no more. */
+int eqv2_pair_scores(const float* a, const float* b, const int* gstart, const int* gcount, const long long* rowptr,
+                     float* S, long long N, int M, int H, int D, float scale, void* stream);
+int eqv2_pair_mix(const float* W, const float* b, const int* gstart, const int* gcount, const long long* rowptr, float* out,
+                  long long N, int M, int H, int D, int max_count, int transpose, void* stream);
+int eqv2_pair_softmax_fwd(const float* S, const int* gcount, const long long* rowptr, float* Pw, long long N, int H,
+                          void* stream);
+int eqv2_pair_softmax_bwd(const float* Pw, const float* gP, const int* gcount, const long long* rowptr, float* gS,
+                          long long N, int H, void* stream);
+int eqv2_pair_softmax_bwd2(const float* Pw, const float* gP, const float* u, const int* gcount, const long long* rowptr,
+                           float* dP, float* dgP, long long N, int H, void* stream);
+
 /* ---- optimizer-side step (train_oc20v2_parallel.py:95-126,177-186) -----------------------------------
  * Multi-tensor kernels over ONE device table of the model's parameter tensors, processed in chunks of
  * eqv2_opt_chunk_elems() elements: chunk c covers elements [chunk_index[c] * chunk, ...) of tensors[chunk_tensor[c]].
