@@ -51,6 +51,9 @@ def backend(request, monkeypatch):
         monkeypatch.setattr(_lib, "check_device", lambda *t: None)
         monkeypatch.setattr(_lib, "stream_ptr", lambda: None)
         ops.set_gemm_mode("fp32")           # the tcgen05 engine is inline PTX: GPU only
+        # the software-pipelined node kernels are bit-identical to their plain twins (tests/test_rotate_pipeline.py, which
+        # switches them on); 105 KB stages per emulated CTA only make the model-level emulator tests slower
+        monkeypatch.setenv("EQV2_NODE_PIPE", "0")
     else:
         if not torch.cuda.is_available():
             pytest.skip("no CUDA device")

@@ -73,6 +73,9 @@ def test_padded_oc20_batch_gives_the_same_outputs_and_gradients(backend):
 def test_padded_matpes_batch_double_backward_is_unchanged(backend):
     """MatPES pattern: forces by autograd through the padded batch (the ghost atoms' edge vectors are recomputed from
     their positions inside the model), loss masked, double backward."""
+    if backend.name == "emu":
+        pytest.skip("CPU suite budget (2 minutes under the emulator): the first-order padded-batch test runs on the "
+                    "emulator, this double-backward one on the GPU")
     batching = pkg("batching")
     fx = golden("matpes_v2_small.pt")
     data = backend.to(dict(fx["inputs"]))

@@ -35,7 +35,8 @@ def test_split_batch_roundtrip():
 
 
 def _worker(rank, world, port, use_ddp, out_dir):
-    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world),
+                      EQV2_NODE_PIPE="0")
     sys.path.insert(0, REPO)
     sys.path.insert(0, os.path.join(REPO, "tests"))
     sys.path.insert(0, os.path.join(REPO, "tests", "emu"))

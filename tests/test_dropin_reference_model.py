@@ -110,8 +110,8 @@ def test_reference_matpes_model_files_run_on_dropin(reference_on_dropin, modname
     """The unmodified MatPES v2 / GATAV2 model files (their own Python graph builder, HTR/GATA blocks from the
     drop-in `NewFunctions`) with the reference train-step pattern: forces by autograd, double backward."""
     be = reference_on_dropin
-    if be.name == "emu" and "phi_at_every_iteration_like_gata" not in modname:
-        pytest.skip("CPU suite budget: the emulator runs the two phi variants (supersets of the others); all four run on the GPU")
+    if be.name == "emu" and not modname.endswith("phi_at_every_iteration_like_gata"):
+        pytest.skip("CPU suite budget: the emulator runs the phi variant (superset of the base ones); all four run on the GPU")
     mod = importlib.import_module(modname)
     assert mod.__file__.startswith(REF)
     fx = golden(fixture)
