@@ -19,7 +19,7 @@
 //                 per K=16 slice  A_hi x [B_hi | B_lo] (one N=256 instruction -> D_hh | D_lo) and
 //                 A_lo x B_hi (N=128 -> D_lo): 2 instructions, 20 KB of shared-memory operand reads instead of the
 //                 24 KB of three separate products.
-//      warps 2-9  promotion + epilogue.  MEASURED on B200 (scripts/gemm_accuracy.py): every tcgen05.mma
+//      warps 2-17 promotion + epilogue.  MEASURED on B200 (scripts/gemm_accuracy.py): every tcgen05.mma
 //                 accumulation into TMEM truncates (~5e-8 relative per instruction, systematic), so the hi*hi
 //                 chain is kept to CHUNK_KB k-blocks (16 instructions) in one of two ping-pong accumulator
 //                 buffers; the workers add every finished chunk into fp32 registers (round to nearest) while the
@@ -39,11 +39,20 @@ constexpr int BM = 128, BN = 128, BK = 64;         // BK fp16 = 128 bytes = one 
 constexpr int STAGES = 3;
 constexpr int TILE_BYTES = BM * BK * 2;            // 16 KB per operand plane tile
 constexpr int STAGE_BYTES = 4 * TILE_BYTES;        // A_hi | A_lo | B_hi | B_lo
-constexpr int NUM_WORKER_WARPS = 8;                // warps 2-9 (TMEM lane quarter = warp & 3)
+#ifndef EQV2_GEMM_WORKERS
+#define EQV2_GEMM_WORKERS 16
+#endif
+// worker warps 2.. (TMEM lane quarter = warp & 3); each owns 32 rows x WCOLS columns of the tile.  16 workers (4 column
+// quarters): the per-tile promotion + epilogue chain of a warp is half as long and twice as many warps hide its latencies
+// (ncu r02: the workers ran at 6.2 cycles per instruction with 2 warps per scheduler, and their per-tile chain, not the
+// MMAs or the stores, bounded the K = 128 launches).
+constexpr int NUM_WORKER_WARPS = EQV2_GEMM_WORKERS;
+constexpr int WCOLS = BN / (NUM_WORKER_WARPS / 4);          // 64 or 32 accumulator columns per worker thread
+constexpr int PATCH_ROWS = 128 / NUM_WORKER_WARPS;          // 16 or 8 rows per transposition round
 constexpr int NUM_THREADS = (2 + NUM_WORKER_WARPS) * 32;
 constexpr int TMEM_COLS = 512;                     // buffer b: D_hh at b*256, D_lo at b*256 + 128
 constexpr int CHUNK_KB = 4;                        // k-blocks per promoted hi*hi chain (16 tcgen05.mma)
-constexpr int EPI_PATCH_BYTES = NUM_WORKER_WARPS * 16 * 36 * 4;   // per worker warp: a padded 16 x 32 fp32 transposition patch
+constexpr int EPI_PATCH_BYTES = NUM_WORKER_WARPS * PATCH_ROWS * 36 * 4;   // per worker warp: a padded PATCH_ROWS x 32 fp32 transposition patch
 constexpr size_t SMEM_BYTES = (size_t)STAGES * STAGE_BYTES + 1024 /*align*/ + 256 /*barriers*/ + EPI_PATCH_BYTES;
 
 struct alignas(64) HGroup {
@@ -306,8 +315,8 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) gemm_f16_kernel(const __grid_c
   } else {
     // ================= workers: promotion of finished chunks + epilogue =================
     const int q = warp & 3;                                // TMEM lane quarter this warp may access
-    const int half = (warp - 2) >> 2;                      // column half
-    const uint32_t lane_col = ((uint32_t)(q * 32) << 16) + (uint32_t)(half * 64);
+    const int half = (warp - 2) >> 2;                      // column block (WCOLS wide) of this warp
+    const uint32_t lane_col = ((uint32_t)(q * 32) << 16) + (uint32_t)(half * WCOLS);
     uint32_t c = 0;
     int scale_gi = -1;                                      // group whose 1/(s_A s_B) is cached in ia / ib
     float ia = 1.f, ib = 1.f;
@@ -322,31 +331,31 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) gemm_f16_kernel(const __grid_c
         scale_gi = W.gi;
       }
       const int nchunks = (W.nkb + CHUNK_KB - 1) / CHUNK_KB;
-      float acc[64];
+      float acc[WCOLS];
 #pragma unroll
-      for (int x = 0; x < 64; ++x) acc[x] = 0.f;
+      for (int x = 0; x < WCOLS; ++x) acc[x] = 0.f;
       for (int j = 0; j < nchunks; ++j, ++c) {
         const uint32_t b = c & 1u;
         mbar_wait(smem_u32(&acc_full[b]), (c >> 1) & 1u);
         tc_fence_after();
         const uint32_t d_hh = tmem_base + b * 256u + lane_col;
-        uint32_t r0[32], r1[32];
+        uint32_t r0[32], r1[WCOLS > 32 ? 32 : 1];
         tmem_ld32_nowait(d_hh, r0);
-        tmem_ld32_nowait(d_hh + 32u, r1);
+        if constexpr (WCOLS > 32) tmem_ld32_nowait(d_hh + 32u, r1);
         tmem_ld_wait();
 #pragma unroll
         for (int x = 0; x < 32; ++x) {
           acc[x] += __uint_as_float(r0[x]);
-          acc[32 + x] += __uint_as_float(r1[x]);
+          if constexpr (WCOLS > 32) acc[32 + x] += __uint_as_float(r1[x]);
         }
         if (PASSES != 1 && j >= nchunks - 2) {               // last chunk on this buffer: its D_lo is final
           tmem_ld32_nowait(d_hh + 128u, r0);
-          tmem_ld32_nowait(d_hh + 160u, r1);
+          if constexpr (WCOLS > 32) tmem_ld32_nowait(d_hh + 160u, r1);
           tmem_ld_wait();
 #pragma unroll
           for (int x = 0; x < 32; ++x) {
             acc[x] += __uint_as_float(r0[x]);
-            acc[32 + x] += __uint_as_float(r1[x]);
+            if constexpr (WCOLS > 32) acc[32 + x] += __uint_as_float(r1[x]);
           }
         }
         tc_fence_before();
@@ -367,17 +376,17 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) gemm_f16_kernel(const __grid_c
       const bool fast = (G.ldc & 3) == 0 && (G.c_bs & 3) == 0 && (G.N & 3) == 0 &&
                         (reinterpret_cast<uintptr_t>(G.C) & 15) == 0 && ((W.n0 & 3) == 0);
       if (fast) {
-        float* patch = epi_patch + (warp - 2) * (16 * 36);
-        const int r16 = lane & 15, c4 = (lane & 7) * 4, rsub = lane >> 3;
+        float* patch = epi_patch + (warp - 2) * (PATCH_ROWS * 36);
+        const int r16 = lane & (PATCH_ROWS - 1), c4 = (lane & 7) * 4, rsub = lane >> 3;
 #pragma unroll
-        for (int cc = 0; cc < 2; ++cc) {
-          const int col = W.n0 + half * 64 + cc * 32 + c4;
+        for (int cc = 0; cc < WCOLS / 32; ++cc) {
+          const int col = W.n0 + half * WCOLS + cc * 32 + c4;
           const bool col_ok = col < G.N;
           float4 bv = make_float4(0.f, 0.f, 0.f, 0.f);
           if (G.bias != nullptr && col_ok && W.ks == 0) bv = __ldg(reinterpret_cast<const float4*>(G.bias + col));
 #pragma unroll
-          for (int rh = 0; rh < 2; ++rh) {
-            if ((lane >> 4) == rh) {
+          for (int rh = 0; rh < 32 / PATCH_ROWS; ++rh) {
+            if ((lane / PATCH_ROWS) == rh) {
 #pragma unroll
               for (int j = 0; j < 8; ++j)
                 *reinterpret_cast<float4*>(patch + r16 * 36 + 4 * j) =
@@ -386,9 +395,9 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) gemm_f16_kernel(const __grid_c
             }
             __syncwarp();
 #pragma unroll
-            for (int i = 0; i < 4; ++i) {
+            for (int i = 0; i < PATCH_ROWS / 4; ++i) {
               const int rl = 4 * i + rsub;
-              const int grow = W.m0 + q * 32 + rh * 16 + rl;
+              const int grow = W.m0 + q * 32 + rh * PATCH_ROWS + rl;
               float4 o = *reinterpret_cast<const float4*>(patch + rl * 36 + c4);
               if (grow < G.M && col_ok) {
                 long long roff = (long long)grow * G.ldc;
@@ -415,16 +424,16 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) gemm_f16_kernel(const __grid_c
           }
         }
       } else if (row < G.M) {
-        const int col0 = half * 64;
+        const int col0 = half * WCOLS;
         long long roff = (long long)row * G.ldc;
         if (G.c_rpb != 0) {
           const int qd = row / G.c_rpb;
           roff = (long long)qd * G.c_bs + (long long)(row - qd * G.c_rpb) * G.ldc;
         }
         float* crow = G.C + roff + W.n0 + col0;
-        const int ncol = min(64, G.N - W.n0 - col0);
+        const int ncol = min(WCOLS, G.N - W.n0 - col0);
 #pragma unroll
-        for (int x = 0; x < 64; ++x) {
+        for (int x = 0; x < WCOLS; ++x) {
           if (x < ncol) {
             float o = acc[x] * sc;
             if (G.bias != nullptr && W.ks == 0) o += __ldg(G.bias + W.n0 + col0 + x);
