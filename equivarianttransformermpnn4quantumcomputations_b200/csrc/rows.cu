@@ -150,6 +150,41 @@ __global__ void planes_colsum_partial_kernel(const __half* __restrict__ hi, long
   for (; i < rows; i += S) a[0] += __half2float(hi[i * ld + c]) + __half2float(hi[i * ld + c + plane]);
   partial[(long long)s * C + c] = (a[0] + a[1]) + (a[2] + a[3]);
 }
+// 16-byte loads: thread (cx, ry) = (tid % 16, tid / 16) sums 8 adjacent columns over the rows s + (ry + 8 k) S of slice s;
+// the 8 row lanes meet in shared memory in fixed order (deterministic).  (The scalar version above read 2 bytes per thread
+// and load: 2.9 TB/s on the [E, 4608] radial-weight gradient, 1.1 ms per OC20 step.)
+__global__ void __launch_bounds__(128)
+planes_colsum_partial_vec_kernel(const __half* __restrict__ hi, long long plane, long long ld, long long rows, int C, int S,
+                                 float* __restrict__ partial) {
+  __shared__ float red[8][16][9];
+  const int s = blockIdx.y, cx = threadIdx.x & 15, ry = threadIdx.x >> 4;
+  const int c = blockIdx.x * 128 + cx * 8;
+  float a[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+  if (c < C) {
+    for (long long i = s + (long long)ry * S; i < rows; i += 8ll * S) {
+      const uint4 h = __ldg(reinterpret_cast<const uint4*>(hi + i * ld + c));
+      const uint4 l = __ldg(reinterpret_cast<const uint4*>(hi + i * ld + c + plane));
+      const __half2* hp = reinterpret_cast<const __half2*>(&h);
+      const __half2* lp = reinterpret_cast<const __half2*>(&l);
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const float2 x = __half22float2(hp[u]), y = __half22float2(lp[u]);
+        a[2 * u] += x.x + y.x;
+        a[2 * u + 1] += x.y + y.y;
+      }
+    }
+  }
+#pragma unroll
+  for (int u = 0; u < 8; ++u) red[ry][cx][u] = a[u];
+  __syncthreads();
+  const int col = threadIdx.x;              // 128 columns of this block
+  if (blockIdx.x * 128 + col < C) {
+    float t = 0.f;
+#pragma unroll
+    for (int q = 0; q < 8; ++q) t += red[q][col >> 3][col & 7];
+    partial[(long long)s * C + blockIdx.x * 128 + col] = t;
+  }
+}
 __global__ void planes_colsum_final_kernel(const float* __restrict__ partial, int C, int S, const float* __restrict__ bound,
                                            float* __restrict__ out) {
   __shared__ float red[8][33];
@@ -175,7 +210,11 @@ extern "C" int eqv2_planes_colsum(const void* planes, long long plane, long long
   EQV2_REQUIRE(S >= 1 && C >= 0 && planes && bound && partial && out, "eqv2_planes_colsum: bad arguments");
   if (C == 0) return 0;
   const __half* hi = reinterpret_cast<const __half*>(planes) + col_off;
-  EQV2_LAUNCH(planes_colsum_partial_kernel, dim3((C + 127) / 128, S), dim3(128), 0, stream, hi, plane, ld, rows, C, S, partial);
+  if (C % 8 == 0 && col_off % 8 == 0 && ld % 8 == 0 && plane % 8 == 0 && (reinterpret_cast<uintptr_t>(planes) & 15) == 0) {
+    EQV2_LAUNCH(planes_colsum_partial_vec_kernel, dim3((C + 127) / 128, S), dim3(128), 0, stream, hi, plane, ld, rows, C, S, partial);
+  } else {
+    EQV2_LAUNCH(planes_colsum_partial_kernel, dim3((C + 127) / 128, S), dim3(128), 0, stream, hi, plane, ld, rows, C, S, partial);
+  }
   EQV2_CHECK_LAUNCH("eqv2_planes_colsum (partial)");
   EQV2_LAUNCH(planes_colsum_final_kernel, dim3((C + 31) / 32), dim3(32, 8), 0, stream, partial, C, S, bound, out);
   EQV2_CHECK_LAUNCH("eqv2_planes_colsum (final)");

@@ -9,7 +9,7 @@ $CMD > $OUT/r02_ncu_plain.log 2>&1 || { echo "plain run failed"; tail -5 $OUT/r0
 ncu --metrics gpu__time_duration.sum --clock-control none -s 9000 -c 3400 --csv --log-file $OUT/r02_ncu_launches.csv $CMD > $OUT/r02_ncu_launches.log 2>&1
 echo "launch list rc=$?"
 $SHORT > $OUT/r02_ncu_plain_short.log 2>&1 || { echo "short plain run failed"; exit 1; }
-for spec in "gemm_f16_kernel:gemm:40:3" "gather_rotate_fwd_kernel:grfwd:3:1" "rotinv_reduce_bwd_kernel:rirbwd:2:1" "gather_rotate_dx_kernel:grdx:2:1" "rbf_linear_wgrad_partial_kernel:rbfw:2:1" "s2sep_bwd_kernel:s2bwd:2:1" "split_kernel:split:30:2"; do
+for spec in "gemm_f16_kernel:gemm:40:3" "gather_rotate_dx_pipe_kernel:grdx:2:1" "rotinv_reduce_fwd_pipe_kernel:rirfwd:2:1" ; do
   IFS=: read pat tag skip cnt <<< "$spec"
   ncu --set full --clock-control none --import-source on -k regex:$pat -s $skip -c $cnt -f -o $OUT/r02_ncu_$tag $SHORT > $OUT/r02_ncu_$tag.log 2>&1
   echo "$tag rc=$?"

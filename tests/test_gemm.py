@@ -5,6 +5,7 @@ import ctypes
 import pytest
 import torch
 
+from conftest import PKG
 from helpers import pkg
 
 
@@ -159,3 +160,25 @@ def test_f16x3_slab_linear_matches_ffma(lmax, N, Ci, Co):
         ops.set_gemm_mode(ops.DEFAULT_GEMM_MODE)
     for a, b_ in zip(res["f16x3"], res["fp32"]):
         assert float((a - b_).abs().max() / b_.abs().max()) < 3e-6
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("rows,cols,col_off,n", [(13489, 4608, 0, 4608), (1000, 2432, 576, 1024), (37, 200, 8, 120), (513, 70, 3, 9)])
+def test_planes_colsum_matches_fp32_column_sums(rows, cols, col_off, n):
+    """Bias gradients read from operand planes (eqv2_planes_colsum: vectorised 16-byte path and the scalar fallback)."""
+    import importlib
+    if not torch.cuda.is_available():
+        pytest.skip("no CUDA device")
+    ops = pkg("ops")
+    _lib = importlib.import_module(PKG + "._lib")
+    ops.set_gemm_mode(ops.DEFAULT_GEMM_MODE)
+    gen = torch.Generator().manual_seed(rows)
+    t = (torch.randn(rows, cols, generator=gen) * 3).cuda()
+    sp = ops._splits_for([ops.OperandSrc(t, rows, cols)])[(id(t), 0)]
+    S = max(1, min(rows // 16, -(-2368 // ((n + 127) // 128))))
+    partial = torch.empty(S * n, dtype=torch.float32, device="cuda")
+    out = torch.empty(n, dtype=torch.float32, device="cuda")
+    _lib.call("eqv2_planes_colsum", sp.buf.data_ptr(), sp.plane, sp.cols_pad, col_off, rows, n, S, sp.absmax.data_ptr(),
+              partial.data_ptr(), out.data_ptr(), _lib.stream_ptr(), n_kernels=2)
+    ref = t[:, col_off:col_off + n].double().sum(0)
+    assert float((out.double() - ref).abs().max()) <= 2e-6 * float(t.abs().max()) * rows ** 0.5 + 1e-4
