@@ -106,7 +106,7 @@ def parse():
     ap.add_argument("--no-dropout", action="store_true", help="alpha_drop = drop_path_rate = 0")
     ap.add_argument("--bucket", default=None, help="pad every batch to multiples ATOMS,EDGES (e.g. 64,512) with a masked "
                     "ghost structure so that one captured graph serves a whole bucket of batch sizes")
-    ap.add_argument("--grad-sync", default="overlap", choices=["overlap", "flat"],
+    ap.add_argument("--grad-sync", default="overlap", choices=["overlap", "captured", "flat"],
                     help="N > 1: 'overlap' = bucket all-reduces issued from inside the (captured) backward pass on a side "
                          "stream, gradients live in the flat buckets; 'flat' = copy / all-reduce / copy back after it")
     ap.add_argument("--optimizer", default="fused", choices=["fused", "torch"],
@@ -415,8 +415,9 @@ def run_b200(args):
         sync = None
         if world > 1:
             parallel = importlib.import_module(PKG + ".parallel")
-            if args.grad_sync == "overlap":
-                sync = parallel.OverlappedGradientAllReducer(model.parameters(), bucket_mb=32)
+            if args.grad_sync in ("overlap", "captured"):     # captured: inside the graph, but after the backward pass
+                sync = parallel.OverlappedGradientAllReducer(model.parameters(), bucket_mb=32,
+                                                             overlap=args.grad_sync == "overlap")
             else:
                 sync = parallel.GradientAllReducer(model.parameters(), bucket_mb=64).reduce
         bucket = tuple(int(v) for v in args.bucket.split(",")) if args.bucket else None
@@ -447,6 +448,9 @@ def run_b200(args):
         barrier()
         ms = torch.tensor([e0.elapsed_time(e1)], device=dev)
         if dist is not None:
+            every = [torch.zeros_like(ms) for _ in range(world)]
+            dist.all_gather(every, ms)
+            stats["rank_ms_per_step"] = [round(float(t.item()) / n, 3) for t in every]
             dist.all_reduce(ms, op=dist.ReduceOp.MAX)
         return float(ms.item())
 
@@ -459,6 +463,13 @@ def run_b200(args):
     _lib.reset_launch_count()
     ms_dev = timed(lambda: step(resident), args.steps)
     host_ms = stats["host_ms"]
+    rank_ms = stats.get("rank_ms_per_step")
+    rank_edges = None
+    if dist is not None:
+        mine = torch.tensor([E], device=dev)
+        every = [torch.zeros_like(mine) for _ in range(world)]
+        dist.all_gather(every, mine)
+        rank_edges = [int(t.item()) for t in every]
     launches = _lib.launch_count()
     ms_e2e = timed(step_e2e, args.steps)
     clocks = sampler.stop() if sampler is not None else None
@@ -509,6 +520,8 @@ def run_b200(args):
                 "e2e": {"value": e2e, "unit": UNIT, "ms_per_step": ms_e2e / args.steps, "h2d_bytes_per_step": h2d_bytes,
                         "d2h_bytes_per_step": 4},
                 "gpu_launches": launches, "host_enqueue_ms_per_step": host_ms,
+                "ranks": ({"ms_per_step": rank_ms, "edges": rank_edges, "grad_sync": args.grad_sync}
+                          if world > 1 else None),
                 "edge_msgs_per_s": E * world * blocks * args.steps / (ms_dev / 1e3),
                 "roofline": roof, "rooflines": rooflines, "kernel_time_shares": shares, "clocks": clocks,
                 "cpu_baseline": cpu}

@@ -154,9 +154,14 @@ class OverlappedGradientAllReducer:
     not waited for in the next one, so their bucket still goes out from inside the backward pass.
     Requirement (as for DDP): every rank runs the same model, so buckets complete in the same order everywhere."""
 
-    def __init__(self, parameters, bucket_mb=32, group=None):
+    def __init__(self, parameters, bucket_mb=32, group=None, overlap=True):
+        """overlap=False: same flat-bucket exchange (captured with the step, no copy back), but every bucket is sent from
+        finish(), after the backward pass -- for A/B measurements of what the concurrency costs the compute kernels (an
+        NCCL kernel occupies SMs for as long as its collective runs; the persistent GEMM kernels size their grid to all
+        148)."""
         self.params = [p for p in parameters if p.requires_grad]
         self.group = group
+        self.overlap = overlap
         limit = bucket_mb * (1 << 20)
         self.buckets, cur, size = [], [], 0
         for p in reversed(self.params):
@@ -207,7 +212,7 @@ class OverlappedGradientAllReducer:
             self.left[b] = -1
             return
         self.left[b] -= 1
-        if self.left[b] == 0:
+        if self.left[b] == 0 and self.overlap:
             self._send(b)
 
     def _send(self, b):
