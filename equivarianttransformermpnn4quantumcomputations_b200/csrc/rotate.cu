@@ -136,14 +136,19 @@ __device__ __forceinline__ void load_column(float (&v)[N], const float* __restri
 // ------------------------------------------------------------------------------------------
 // PL = true: the result goes out as scaled fp16 hi/lo planes (the A operand of the first SO(2) convolution's GEMM) instead
 // of fp32 (Eqv2PlaneArgs, common.cuh); bound = max |rad| * max |x| * sqrt(2 lmax + 1)  (|(W x)_row| <= ||x_l||_2).
-template <int L, int M, bool PL>
+// CT > 0: the channel count is the compile-time constant CT (the launcher checks C == CT): every row stride, the CTA width and
+// the staged tile's shape become immediates -- the 67 strided loads and 58 staged stores per thread lose their 64-bit address
+// arithmetic (SASS r02: 471 of 1 704 instructions of the CT = 0 instance were IADD3 / IMAD / LEA).
+template <int L, int M, bool PL, int CT = 0>
 __global__ void __launch_bounds__(256)
 gather_rotate_fwd_kernel(const float* __restrict__ x, const long long* __restrict__ src,
                          const long long* __restrict__ dst, const float* __restrict__ wig,
-                         const float* __restrict__ rad, float* __restrict__ out, int C, int Kr, int nrad,
+                         const float* __restrict__ rad, float* __restrict__ out, int C_rt, int Kr_rt, int nrad_rt,
                          float* __restrict__ absmax, const Eqv2PlaneArgs PA) {
   constexpr int K = Dim<L>::K, WS = Dim<L>::WS;
   constexpr int NS = nslots<L, M>();
+  const int C = CT ? CT : C_rt, Kr = CT ? mpos<L, M>(L, -M) + 1 : Kr_rt, nrad = CT ? NS * 2 * CT : nrad_rt;
+  const int T = CT ? (2 * CT < 256 ? 2 * CT : 256) : (int)blockDim.x;
   __shared__ __align__(16) float sw[wpad_off(L + 1)];
   const long long e = blockIdx.x;
   float pscale = 1.f;
@@ -156,7 +161,7 @@ gather_rotate_fwd_kernel(const float* __restrict__ x, const long long* __restric
   // the barrier then waits on one memory latency, not on wigner-then-x-then-rad in sequence (ncu r01: long_scoreboard
   // 12.5 and barrier 2.8 stall cycles per issue with one short-lived CTA per edge).
   float xc[K], rv[NS];
-  const int ch = blockIdx.y * blockDim.x + threadIdx.x;       // channel chunks of blockDim.x are a grid dimension
+  const int ch = blockIdx.y * T + threadIdx.x;       // channel chunks of T are a grid dimension
   if (ch < C2) {
     load_column<K>(xc, x + ((ch < C) ? ns_ : nd_) * (long long)K * C + ((ch < C) ? ch : ch - C), C);
     if (rad) load_column<NS>(rv, rad + e * (long long)nrad + ch, C2);
@@ -165,7 +170,7 @@ gather_rotate_fwd_kernel(const float* __restrict__ x, const long long* __restric
 #pragma unroll
     for (int i = 0; i < NS; ++i) rv[i] = 1.0f;
   }
-  stage_wigner<L>(sw, wig + e * WS, threadIdx.x, blockDim.x);
+  stage_wigner<L>(sw, wig + e * WS, threadIdx.x, T);
   __syncthreads();
   if (ch < C2) {
     float* op = out + e * (long long)Kr * C2 + ch;
@@ -176,13 +181,13 @@ gather_rotate_fwd_kernel(const float* __restrict__ x, const long long* __restric
         constexpr int m = decltype(mc)::value - mm;
         constexpr int p = mpos<L, M>(l, m), sl = rslot<L, M>(l, m < 0 ? -m : m);
         const float acc = row_dot<l>(sw, l + m, xc + l * l) * rv[sl];
-        if constexpr (PL) eqv2_plane_stage(stage, Kr, blockDim.x, p, threadIdx.x, acc, pscale);
+        if constexpr (PL) eqv2_plane_stage(stage, Kr, T, p, threadIdx.x, acc, pscale);
         else op[(long long)p * C2] = acc;
         amax = fmaxf(amax, fabsf(acc));
       });
     });
   }
-  if constexpr (PL) eqv2_plane_flush(PA, stage, Kr, blockDim.x, e * PA.ld + (long long)blockIdx.y * blockDim.x, C2);
+  if constexpr (PL) eqv2_plane_flush(PA, stage, Kr, T, e * PA.ld + (long long)blockIdx.y * T, C2);
   if (absmax != nullptr) eqv2_commit_absmax(amax, absmax);
 }
 
@@ -191,13 +196,15 @@ gather_rotate_fwd_kernel(const float* __restrict__ x, const long long* __restric
 // slot of  dA[e, row, ch] * (W_e x)[row, ch]   (so2_ops.py:170-175: rows +m and -m share one radial weight).
 // PL = true: drad goes out as fp16 hi/lo planes (operand of the radial MLP's backward GEMMs);
 // bound = 2 * max |dA| * max |x| * sqrt(2 lmax + 1)  (two rows share a slot).
-template <int L, int M, bool PL>
+template <int L, int M, bool PL, int CT = 0>
 __global__ void __launch_bounds__(256)
 gather_rotate_drad_kernel(const float* __restrict__ x, const long long* __restrict__ src,
                           const long long* __restrict__ dst, const float* __restrict__ wig,
-                          const float* __restrict__ dA, float* __restrict__ drad, int C, int Kr, int nrad,
+                          const float* __restrict__ dA, float* __restrict__ drad, int C_rt, int Kr_rt, int nrad_rt,
                           float* __restrict__ absmax, const Eqv2PlaneArgs PA) {
   constexpr int K = Dim<L>::K, WS = Dim<L>::WS;
+  const int C = CT ? CT : C_rt, Kr = CT ? mpos<L, M>(L, -M) + 1 : Kr_rt, nrad = CT ? nslots<L, M>() * 2 * CT : nrad_rt;
+  const int T = CT ? (2 * CT < 256 ? 2 * CT : 256) : (int)blockDim.x;
   __shared__ __align__(16) float sw[wpad_off(L + 1)];
   const long long e = blockIdx.x;
   float pscale = 1.f;
@@ -210,12 +217,12 @@ gather_rotate_drad_kernel(const float* __restrict__ x, const long long* __restri
   // x and dA columns first, Wigner staging + barrier second (see gather_rotate_fwd_kernel)
   constexpr int KR = mpos<L, M>(L, -M) + 1;      // Kr consecutive m-primary rows
   float xc[K], gv[KR];
-  const int ch = blockIdx.y * blockDim.x + threadIdx.x;
+  const int ch = blockIdx.y * T + threadIdx.x;
   if (ch < C2) {
     load_column<K>(xc, x + ((ch < C) ? ns_ : nd_) * (long long)K * C + ((ch < C) ? ch : ch - C), C);
     load_column<KR>(gv, dA + e * (long long)Kr * C2 + ch, C2);
   }
-  stage_wigner<L>(sw, wig + e * WS, threadIdx.x, blockDim.x);
+  stage_wigner<L>(sw, wig + e * WS, threadIdx.x, T);
   __syncthreads();
   if (ch < C2) {
     float* drp = drad + e * (long long)nrad + ch;
@@ -227,13 +234,13 @@ gather_rotate_drad_kernel(const float* __restrict__ x, const long long* __restri
         constexpr int pp = mpos<L, M>(l, m), pm = mpos<L, M>(l, -m), sl = rslot<L, M>(l, m);
         float d = gv[pp] * row_dot<l>(sw, l + m, xc + l * l);
         if constexpr (m > 0) d = fmaf(gv[pm], row_dot<l>(sw, l - m, xc + l * l), d);
-        if constexpr (PL) eqv2_plane_stage(stage, NSL, blockDim.x, sl, threadIdx.x, d, pscale);
+        if constexpr (PL) eqv2_plane_stage(stage, NSL, T, sl, threadIdx.x, d, pscale);
         else drp[(long long)sl * C2] = d;
         amax = fmaxf(amax, fabsf(d));
       });
     });
   }
-  if constexpr (PL) eqv2_plane_flush(PA, stage, NSL, blockDim.x, e * PA.ld + (long long)blockIdx.y * blockDim.x, C2);
+  if constexpr (PL) eqv2_plane_flush(PA, stage, NSL, T, e * PA.ld + (long long)blockIdx.y * T, C2);
   if (absmax != nullptr) eqv2_commit_absmax(amax, absmax);
 }
 
@@ -578,18 +585,20 @@ rotinv_reduce_fwd_kernel(const float* __restrict__ val, const float* __restrict_
 // ------------------------------------------------------------------------------------------
 // PL = true: d(value) goes out as fp16 hi/lo planes (operand of the second SO(2) convolution's backward GEMMs);
 // bound = max |dout| * alpha_bound * scale * sqrt((2 lmax + 1) * max(1, (2 lmax + 1) / (2 mmax + 1))).
-template <int L, int M, bool PL>
+template <int L, int M, bool PL, int CT = 0>
 __global__ void __launch_bounds__(256)
 rotinv_reduce_bwd_kernel(const float* __restrict__ dout, const float* __restrict__ val, const float* __restrict__ alpha,
                          const float* __restrict__ wig, const long long* __restrict__ dst, float* __restrict__ dval,
-                         float* __restrict__ dalpha, int Cv, int rows_used, long long val_estride, int heads, float scale,
+                         float* __restrict__ dalpha, int Cv_rt, int rows_used, long long val_estride, int heads, float scale,
                          float* __restrict__ absmax, const Eqv2PlaneArgs PA) {
   constexpr int K = Dim<L>::K, WS = Dim<L>::WS;
+  const int Cv = CT ? CT : Cv_rt;                       // CT > 0: the launcher checks Cv == CT == CTA width
+  const int T = CT ? CT : (int)blockDim.x;
   __shared__ __align__(16) float sw[wpad_off(L + 1)];
   float pscale = 1.f;
   if constexpr (PL) pscale = eqv2_plane_scale(PA, blockIdx.x == 0 && threadIdx.x == 0);
-  EQV2_DYN_SMEM(float, spart);   // [blockDim.x] partial d(alpha); PL: then hi[rows_used][T] | lo[rows_used][T]
-  __half* stage = reinterpret_cast<__half*>(spart + blockDim.x);
+  EQV2_DYN_SMEM(float, spart);   // [T] partial d(alpha); PL: then hi[rows_used][T] | lo[rows_used][T]
+  __half* stage = reinterpret_cast<__half*>(spart + T);
   constexpr int KR = mpos<L, M>(L, -M) + 1;
   const long long e = blockIdx.x;
   const int c = threadIdx.x;
@@ -615,7 +624,7 @@ rotinv_reduce_bwd_kernel(const float* __restrict__ dout, const float* __restrict
       for (int p = 0; p < KR; ++p) vv[p] = (p < rows_used) ? __ldg(vp + (long long)p * Cv) : 0.f;
     }
   }
-  stage_wigner<L>(sw, wig + e * WS, threadIdx.x, blockDim.x);
+  stage_wigner<L>(sw, wig + e * WS, threadIdx.x, T);
   __syncthreads();
   if (live) {
     float* dvp = dval + e * val_estride + c;
@@ -628,7 +637,7 @@ rotinv_reduce_bwd_kernel(const float* __restrict__ dout, const float* __restrict
         if (p < rows_used) {
           const float t = row_dot<l>(sw, l + m, g + l * l);
           if (alpha) da = fmaf(t, vv[p], da);
-          if constexpr (PL) eqv2_plane_stage(stage, rows_used, blockDim.x, p, c, t * a, pscale);
+          if constexpr (PL) eqv2_plane_stage(stage, rows_used, T, p, c, t * a, pscale);
           else dvp[(long long)p * Cv] = t * a;
           amax = fmaxf(amax, fabsf(t * a));
         }
@@ -644,7 +653,7 @@ rotinv_reduce_bwd_kernel(const float* __restrict__ dout, const float* __restrict
       dalpha[e * heads + threadIdx.x] = s;
     }
   }
-  if constexpr (PL) eqv2_plane_flush(PA, stage, rows_used, blockDim.x, e * PA.ld, Cv);
+  if constexpr (PL) eqv2_plane_flush(PA, stage, rows_used, T, e * PA.ld, Cv);
   if (absmax != nullptr) eqv2_commit_absmax(amax, absmax);
 }
 
@@ -803,6 +812,12 @@ extern "C" int eqv2_rotinv_reduce_bwd(const float* dout, const float* val, const
 // (the staged tile can exceed the 48 KB default of dynamic shared memory: lmax 6 / mmax 6 is 49 rows x 256 columns x 4 B;
 // plane_smem_attr above)
 
+// EQV2_ROT_CT=0 selects the run-time-channel-count instances (A/B measurements)
+static bool ct_enabled() {
+  const char* v = getenv("EQV2_ROT_CT");
+  return v == nullptr || v[0] != '0';
+}
+
 static int check_planes(const char* who, const void* planes, long long plane, long long ld, long long cols,
                         const float* bound_a, const float* bound_out) {
   EQV2_REQUIRE(planes != nullptr && bound_a != nullptr && bound_out != nullptr, "%s: null plane / bound pointer", who);
@@ -824,7 +839,8 @@ extern "C" int eqv2_gather_rotate_fwd_planes(const float* x, const long long* sr
   const int threads = min(256, round32(2 * C));
 #define X(L_, M_)                                                                                              \
   if (lmax == L_ && mmax == M_) {                                                                              \
-    auto kfn = gather_rotate_fwd_kernel<L_, M_, true>;                                                         \
+    auto kfn = (C == 128 && Kr == mpos<L_, M_>(L_, -M_) + 1 && nrad == nslots<L_, M_>() * 256 && ct_enabled())       \
+                   ? gather_rotate_fwd_kernel<L_, M_, true, 128> : gather_rotate_fwd_kernel<L_, M_, true>;     \
     const size_t smem = (size_t)Kr * threads * 4;                                                              \
     if (plane_smem_attr((const void*)kfn, smem)) return 1;                                                     \
     EQV2_LAUNCH(kfn, dim3((unsigned)E, (2 * C + threads - 1) / threads), dim3(threads), smem, stream, x, src, dst, wig, rad, (float*)nullptr, C, Kr, nrad, (float*)nullptr, PA); \
@@ -848,7 +864,8 @@ extern "C" int eqv2_gather_rotate_drad_planes(const float* x, const long long* s
   const int threads = min(256, round32(2 * C));
 #define X(L_, M_)                                                                                              \
   if (lmax == L_ && mmax == M_) {                                                                              \
-    auto kfn = gather_rotate_drad_kernel<L_, M_, true>;                                                        \
+    auto kfn = (C == 128 && Kr == mpos<L_, M_>(L_, -M_) + 1 && nrad == nslots<L_, M_>() * 256 && ct_enabled())       \
+                   ? gather_rotate_drad_kernel<L_, M_, true, 128> : gather_rotate_drad_kernel<L_, M_, true>;   \
     const size_t smem = (size_t)(nrad / (2 * C)) * threads * 4;                                                \
     if (plane_smem_attr((const void*)kfn, smem)) return 1;                                                     \
     EQV2_LAUNCH(kfn, dim3((unsigned)E, (2 * C + threads - 1) / threads), dim3(threads), smem, stream, x, src, dst, wig, dA, (float*)nullptr, C, Kr, nrad, (float*)nullptr, PA); \
@@ -876,7 +893,8 @@ extern "C" int eqv2_rotinv_reduce_bwd_planes(const float* dout, const float* val
   const int threads = round32(max(Cv, heads));
 #define X(L_, M_)                                                                                              \
   if (lmax == L_ && mmax == M_) {                                                                              \
-    auto kfn = rotinv_reduce_bwd_kernel<L_, M_, true>;                                                         \
+    auto kfn = (Cv == 128 && threads == 128 && ct_enabled()) ? rotinv_reduce_bwd_kernel<L_, M_, true, 128>      \
+                                                              : rotinv_reduce_bwd_kernel<L_, M_, true>;         \
     const size_t smem = threads * sizeof(float) + (size_t)rows_used * threads * 4;                             \
     if (plane_smem_attr((const void*)kfn, smem)) return 1;                                                     \
     EQV2_LAUNCH(kfn, dim3((unsigned)E), dim3(threads), smem, stream, dout, val, alpha, wig, dst, (float*)nullptr, dalpha, Cv, rows_used, val_estride, heads, scale, (float*)nullptr, PA); \
