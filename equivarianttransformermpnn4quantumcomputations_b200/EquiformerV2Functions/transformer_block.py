@@ -160,8 +160,11 @@ class SO2EquivariantGraphAttention(nn.Module):
             Zm = ops.s2_act(Y[:, extra:].reshape(plan.E, lay.Kr, self.hidden_channels), Y[:, ha:extra], mats)
             Zm = Zm.reshape(plan.E, lay.Kr * self.hidden_channels)
         else:
+            # f16 engine: the activation writes the second convolution's A operand as planes (no fp32 Z, no split pass)
+            z_planes = ops.s2_planes_available(Y, mats, self.hidden_channels, lay.Kr * self.num_heads * self.attn_value_channels,
+                                               self.num_heads * self.attn_value_channels, self.num_heads)
             Zm, alpha = ops.edge_act_alpha(Y, ln_w, ln_b, self.alpha_dot, plan, mats, self.num_heads,
-                                                 self.attn_alpha_channels, self.hidden_channels)
+                                                 self.attn_alpha_channels, self.hidden_channels, z_planes=z_planes)
         alpha_bound = 1.0
         if self.alpha_dropout is not None:
             if self.training:

@@ -105,6 +105,7 @@ _PROTOS = {
     "eqv2_gata_value_fwd": [P, P, P, P, L, I, I, I, I, P],
     "eqv2_gata_value_bwd": [P, P, P, P, P, P, L, I, I, I, I, P],
     "eqv2_gata_value_bwd2": [P, P, P, P, P, P, P, P, P, L, I, I, I, I, P],
+    "eqv2_s2sep_fwd_planes": [P, L, P, L, P, L, L, P, F, P, L, I, I, I, I, I, P],
     "eqv2_pair_scores": [P, P, P, P, P, P, L, I, I, I, F, P],
     "eqv2_pair_mix": [P, P, P, P, P, P, L, I, I, I, I, I, P],
     "eqv2_pair_softmax_fwd": [P, P, P, P, L, I, P],
@@ -116,7 +117,8 @@ _PROTOS = {
 }
 # entry points that only exist in the real (nvcc-built) library
 _OPTIONAL = {"eqv2_gemm_tc", "eqv2_split_f16", "eqv2_gemm_f16", "eqv2_gemm_f16_ex", "eqv2_gather_rotate_fwd_planes",
-             "eqv2_gather_rotate_drad_planes", "eqv2_rotinv_reduce_bwd_planes", "eqv2_planes_colsum"}   # inline-PTX kernels: not part of the CPU emulator build
+             "eqv2_gather_rotate_drad_planes", "eqv2_rotinv_reduce_bwd_planes", "eqv2_planes_colsum",
+             "eqv2_s2sep_fwd_planes"}   # inline-PTX kernels: not part of the CPU emulator build
 
 _state = {"lib": None, "launches": 0}
 

@@ -136,6 +136,81 @@ s2sep_fwd_kernel(const float* __restrict__ X, long long x_rs, const float* __res
   if (absmax != nullptr) eqv2_commit_absmax(amax, absmax);
 }
 
+#ifndef EQV2_CPU_EMU
+// The same forward with the result written as scaled fp16 hi/lo operand planes (the A operand of the second SO(2)
+// convolution's GEMM, common.cuh) instead of fp32: the [E, Kr*C] activation tensor and its operand-split pass disappear.
+// bound = max |Y| * max(1, ||F||_1 ||T||_inf)  (|SiLU(g)| <= |g| <= ||T||_inf max |x|; the gate row is |SiLU(gate)| <= |gate|),
+// a factor 25-80 above typical maxima: inside the 2^8 margin of the plane format.  A CTA-iteration covers 128 consecutive
+// (row, channel) pairs = 128 / C whole rows (C divides 128); their [Kr][C] blocks are contiguous in the plane rows and leave
+// through the bulk-copy engine, one copy per row and plane.
+template <int L, int M, bool MP>
+__global__ void __launch_bounds__(S2_THREADS)
+s2sep_fwd_planes_kernel(const float* __restrict__ X, long long x_rs, const float* __restrict__ gate, long long g_rs,
+                        long long R, int C, int slot, const Eqv2PlaneArgs PA) {
+  constexpr int Kr = KrOf<L, M>::value();
+  const S2Tables& T = g_tab[slot];
+  EQV2_DYN_SMEM(__half, stage);            // hi [128 / C rows][Kr][C] | lo [...]
+  const float pscale = eqv2_plane_scale(PA, blockIdx.x == 0 && threadIdx.x == 0);
+  const long long total = R * C;
+  const int r_local = threadIdx.x / C, c = threadIdx.x - r_local * C;
+  for (long long base = (long long)blockIdx.x * S2_THREADS; base < total; base += (long long)gridDim.x * S2_THREADS) {
+    const long long r0 = base / C;
+    const long long r = r0 + r_local;
+    if (r < R) {
+      float x[Kr], o[Kr];
+#pragma unroll
+      for (int p = 0; p < Kr; ++p) {
+        x[p] = __ldg(X + r * x_rs + (long long)p * C + c);
+        o[p] = 0.f;
+      }
+#pragma unroll 1
+      for (int b = 0; b < S2_RES; ++b) {
+        float up[M + 1], un[M + 1], vp[M + 1], vn[M + 1];
+        lat_fwd<L, M, MP>(x, T.Pt, b, up, un);
+#pragma unroll
+        for (int mi = 0; mi <= M; ++mi) vp[mi] = vn[mi] = 0.f;
+#pragma unroll
+        for (int a = 0; a < S2_RES; ++a) {
+          float g = up[0];
+#pragma unroll
+          for (int mi = 1; mi <= M; ++mi) g = fmaf(T.ct[a][mi], up[mi], fmaf(T.st[a][mi], un[mi], g));
+          const float sv = eqv2_silu(g);
+          vp[0] += sv;
+#pragma unroll
+          for (int mi = 1; mi <= M; ++mi) {
+            vp[mi] = fmaf(T.ct[a][mi], sv, vp[mi]);
+            vn[mi] = fmaf(T.st[a][mi], sv, vn[mi]);
+          }
+        }
+        lat_bwd<L, M, MP>(o, T.Pf, b, vp, vn);
+      }
+      if (gate != nullptr) o[0] = eqv2_silu(__ldg(gate + r * g_rs + c));
+      __half* sh = stage + r_local * (Kr * C) + c;
+#pragma unroll
+      for (int p = 0; p < Kr; ++p) {
+        const float v = o[p] * pscale;
+        const __half h = __float2half_rn(v);
+        sh[p * C] = h;
+        sh[Kr * S2_THREADS + p * C] = __float2half_rn(v - __half2float(h));
+      }
+    }
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      const long long rows_here = (R - r0) < (long long)(S2_THREADS / C) ? (R - r0) : (long long)(S2_THREADS / C);
+      __half* hp = reinterpret_cast<__half*>(PA.hi);
+      for (long long rl = 0; rl < rows_here; ++rl) {
+        eqv2_bulk_s2g(hp + (r0 + rl) * PA.ld, stage + rl * (Kr * C), (unsigned)(Kr * C * 2));
+        eqv2_bulk_s2g(hp + (r0 + rl) * PA.ld + PA.plane, stage + Kr * S2_THREADS + rl * (Kr * C), (unsigned)(Kr * C * 2));
+      }
+      asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+      asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");     // the staged tile is rewritten next iteration
+    }
+    __syncthreads();
+  }
+}
+#endif
+
 template <int L, int M, bool MP>
 __global__ void __launch_bounds__(S2_THREADS)
 s2sep_bwd_kernel(const float* __restrict__ X, long long x_rs, const float* __restrict__ gate, long long g_rs,
@@ -325,6 +400,36 @@ extern "C" int eqv2_s2sep_fwd(const float* Xp, long long x_rs, const float* gate
   eqv2_set_error("s2sep_fwd: (lmax, mmax) = (%d, %d) not instantiated", lmax, mmax);
   return 1;
 }
+
+#ifndef EQV2_CPU_EMU
+extern "C" int eqv2_s2sep_fwd_planes(const float* Xp, long long x_rs, const float* gate, long long g_rs, void* planes,
+                                     long long plane, long long ld, const float* bound_in, float bound_c, float* bound_out,
+                                     long long R, int C, int lmax, int mmax, int m_primary, int slot, void* stream) {
+  if (R == 0) return 0;
+  EQV2_REQUIRE(planes != nullptr && bound_in != nullptr && bound_out != nullptr && bound_c >= 1.0f,
+               "s2sep_fwd_planes: null plane / bound pointer or bound factor < 1");
+  EQV2_REQUIRE(C > 0 && C <= S2_THREADS && S2_THREADS % C == 0 && C % 8 == 0,
+               "s2sep_fwd_planes: C = %d must divide %d and be a multiple of 8", C, S2_THREADS);
+  EQV2_REQUIRE((ld % 8) == 0 && (plane % 8) == 0 && (((uintptr_t)planes) & 15) == 0,
+               "s2sep_fwd_planes: planes must be 16-byte aligned with ld %% 8 == 0");
+  const Eqv2PlaneArgs PA{planes, plane, ld, bound_in, nullptr, bound_c, bound_out};
+  const unsigned blocks = s2_grid_blocks(R * C);
+#define X(L_, M_)                                                                                                        \
+  if (lmax == L_ && mmax == M_) {                                                                                        \
+    auto kfn = m_primary ? s2sep_fwd_planes_kernel<L_, M_, true> : s2sep_fwd_planes_kernel<L_, M_, false>;               \
+    constexpr int kr_ = KrOf<L_, M_>::value();                                                                           \
+    const size_t smem = (size_t)2 * kr_ * S2_THREADS * sizeof(__half);                                                   \
+    EQV2_REQUIRE(ld >= (long long)kr_ * C, "s2sep_fwd_planes: ld smaller than Kr * C");                                  \
+    EQV2_LAUNCH(kfn, dim3(blocks), dim3(S2_THREADS), smem, stream, Xp, x_rs, gate, g_rs, R, C, slot, PA);                 \
+    EQV2_CHECK_LAUNCH("eqv2_s2sep_fwd_planes");                                                                          \
+    return 0;                                                                                                            \
+  }
+  EQV2_S2_CONFIGS(X)
+#undef X
+  eqv2_set_error("s2sep_fwd_planes: (lmax, mmax) = (%d, %d) not instantiated", lmax, mmax);
+  return 1;
+}
+#endif
 
 extern "C" int eqv2_s2sep_bwd(const float* Xp, long long x_rs, const float* gate, long long g_rs, const float* dO,
                               long long o_rs, float* dX, long long dx_rs, float* dgate, long long dg_rs, long long R, int C,

@@ -453,7 +453,7 @@ import os as _os
 
 # A/B switches for measurements (bench.py --disable ...): "planes" = producer kernels write operand planes,
 # "c_absmax" = the GEMM epilogue reduces max |C|.  Both on by default; EQV2_DISABLE=planes,c_absmax turns them off.
-_FEATURES = {k: k not in _os.environ.get("EQV2_DISABLE", "").split(",") for k in ("planes", "c_absmax")}
+_FEATURES = {k: k not in _os.environ.get("EQV2_DISABLE", "").split(",") for k in ("planes", "c_absmax", "s2_planes")}
 
 DEFAULT_GEMM_MODE = "f16x3"
 _GEMM_MODE = {"mode": DEFAULT_GEMM_MODE}
@@ -1449,20 +1449,26 @@ class ConvRotInvReduceFn(torch.autograd.Function):
     @staticmethod
     def forward(ctx, Zm, alpha, bias0, plan, wig, lmax, mmax, heads, alpha_bound, groups, *Ws):
         _lib.check_device(Zm, alpha, wig, bias0, *Ws)
-        assert Zm.is_contiguous() and alpha.is_contiguous() and all(w.is_contiguous() for w in Ws)
+        given = getattr(Zm, "_eqv2_planes", None)       # Z exists only as planes (edge_act_alpha(z_planes=True))
+        assert (given is not None or Zm.is_contiguous()) and alpha.is_contiguous() and all(w.is_contiguous() for w in Ws)
         lay = CoeffLayout.get(lmax, mmax)
         xs = tuple((a_off, k_g) for a_off, k_g, _, _ in groups)
         ys = tuple((c_off, n_g) for _, _, c_off, n_g in groups)
         width = sum(n for _, n in ys)
-        V, splits = _slice_mm(Zm, bias0, xs, ys, width, True, Ws)
+        if given is not None:
+            with split_scope([given]):
+                V, splits = _slice_mm(given[0], bias0, xs, ys, width, True, Ws)
+        else:
+            V, splits = _slice_mm(Zm, bias0, xs, ys, width, True, Ws)
         Cv = width // lay.Kr
         meta = (lmax, mmax, lay.Kr, heads, 1.0, Cv)
         out = _rir_fwd(V, alpha, plan, wig, *meta)
         planes_ok = (_FEATURES["planes"] and splits[0] is not None and width % 8 == 0 and Cv % 32 == 0 and heads <= Cv
                      and hasattr(_lib.lib(), "eqv2_rotinv_reduce_bwd_planes"))
+        assert planes_ok or given is None, "Z was written as planes only, but the backward pass would need it in fp32"
         if planes_ok:           # Z itself is not needed again: its planes serve the weight gradient
             ctx.save_for_backward(V, alpha, wig, *Ws)
-            ctx.zref = PlaneRef(Zm.shape[0], Zm.shape[1], Zm.device)
+            ctx.zref = given[0] if given is not None else PlaneRef(Zm.shape[0], Zm.shape[1], Zm.device)
             ctx.spZ = splits[0]
             ctx.spZ.version = 0
         else:
@@ -1526,7 +1532,9 @@ def gather_rotate_conv(x, h, W3, b3, bias0, plan, wig, lmax, mmax, groups, weigh
 
 
 def conv_rotinv_reduce(Zm, alpha, bias0, plan, wig, lmax, mmax, heads, alpha_bound, groups, weights):
-    return ConvRotInvReduceFn.apply(Zm.contiguous(), alpha.contiguous(), bias0, plan, wig, lmax, mmax, heads, alpha_bound,
+    if getattr(Zm, "_eqv2_planes", None) is None:
+        Zm = Zm.contiguous()
+    return ConvRotInvReduceFn.apply(Zm, alpha.contiguous(), bias0, plan, wig, lmax, mmax, heads, alpha_bound,
                                     groups, *[w.contiguous() for w in weights])
 
 
@@ -1559,7 +1567,11 @@ class GridMats:
         Fm = torch.zeros(G, KP, dtype=_F32, device=tg.device)
         T[:, :Kr], Fm[:, :Kr] = tg, fg
         factors = cls._factor_tables(to_grid, from_grid, lmax, mmax)
-        return cls(T.contiguous(), Fm.contiguous(), Kr, KP, G, lmax, mmax, order, factors)
+        mats = cls(T.contiguous(), Fm.contiguous(), Kr, KP, G, lmax, mmax, order, factors)
+        # operator-norm bound of the activation, for kernels that write its output as operand planes:
+        # |F silu(T x)|_inf <= ||F^t||_inf ||T||_inf |x|_inf  (|silu(g)| <= |g|);  >= 1 covers the gate row silu(gate)
+        mats.out_bound = 1.01 * max(1.0, float(tg.abs().sum(1).max()) * float(fg.abs().sum(0).max()))
+        return mats
 
     @staticmethod
     def _factor_tables(to_grid, from_grid, lmax, mmax):
@@ -1720,19 +1732,32 @@ class EdgeActAlphaFn(torch.autograd.Function):
     whose backward passes are differentiable."""
 
     @staticmethod
-    def forward(ctx, Y, ln_w, ln_b, alpha_dot, plan, mats, heads, ach, H):
+    def forward(ctx, Y, ln_w, ln_b, alpha_dot, plan, mats, heads, ach, H, z_planes=False):
         _lib.check_device(Y, ln_w, ln_b, alpha_dot)
         assert Y.is_contiguous()
         E, W = Y.shape
         extra = heads * ach + H
         Kr = mats.Kr
         assert W == extra + Kr * H
-        Z = torch.empty(E, Kr * H, dtype=_F32, device=Y.device)
         yp = Y.data_ptr()
-        # max |Z| is reduced while Z is written: the operand split of the second convolution skips its absmax pass
-        zslot = _s2_fwd(mats, yp + 4 * extra, W, yp + 4 * heads * ach, W, Z.data_ptr(), Kr * H, E, H, Y.device,
-                        absmax=_absmax_slot(Y.device))
-        _register_absmax(Z, zslot)
+        if z_planes:
+            # Z goes out as the operand planes of the second convolution (ConvRotInvReduceFn finds them through the
+            # `_eqv2_planes` attribute edge_act_alpha attaches); the tensor autograd sees is a stride-0 stand-in of Z's shape
+            by = _known_absmax(Y)
+            assert by is not None, "edge_act_alpha(z_planes=True) needs the registered maximum of Y"
+            ref, spZ = _planes_for(E, Kr * H, Y.device)
+            slot = _s2_bind_tables(mats, Y.device)
+            _lib.call("eqv2_s2sep_fwd_planes", yp + 4 * extra, W, yp + 4 * heads * ach, W, spZ.buf.data_ptr(), spZ.plane,
+                      spZ.cols_pad, by.data_ptr(), float(mats.out_bound), spZ.absmax.data_ptr(), E, H, mats.lmax, mats.mmax,
+                      int(mats.order == "m"), slot, _lib.stream_ptr(), work=_s2_work(mats, E, H, 2))
+            Z = Y.new_empty(1).expand(E, Kr * H)
+            EdgeActAlphaFn.last_planes = (ref, spZ)
+        else:
+            Z = torch.empty(E, Kr * H, dtype=_F32, device=Y.device)
+            # max |Z| is reduced while Z is written: the operand split of the second convolution skips its absmax pass
+            zslot = _s2_fwd(mats, yp + 4 * extra, W, yp + 4 * heads * ach, W, Z.data_ptr(), Kr * H, E, H, Y.device,
+                            absmax=_absmax_slot(Y.device))
+            _register_absmax(Z, zslot)
         logits = torch.empty(E, heads, dtype=_F32, device=Y.device)
         alpha = torch.empty(E, heads, dtype=_F32, device=Y.device)
         ln_w_c = ln_w.contiguous() if ln_w is not None else None
@@ -1775,7 +1800,7 @@ class EdgeActAlphaFn(torch.autograd.Function):
                   dlogits.data_ptr(), gp, W, _lib.ptr(g_lnw), _lib.ptr(g_lnb), g_dot.data_ptr(), E, plan.N, heads,
                   ach, 1e-5, _lib.ptr(gslot), _lib.stream_ptr(), n_kernels=2)
         _register_absmax(gY, gslot)
-        return gY, g_lnw, g_lnb, g_dot, None, None, None, None, None
+        return gY, g_lnw, g_lnb, g_dot, None, None, None, None, None, None
 
 
 # ----------------------------------------------------------------------------------------------
@@ -2608,8 +2633,24 @@ def attn_alpha(Ya, ln_w, ln_b, alpha_dot, plan, heads, ach):
     return AttnAlphaFn.apply(Ya.contiguous(), ln_w, ln_b, alpha_dot.contiguous(), plan, heads, ach)
 
 
-def edge_act_alpha(Y, ln_w, ln_b, alpha_dot, plan, mats, heads, ach, H):
-    return EdgeActAlphaFn.apply(Y.contiguous(), ln_w, ln_b, alpha_dot.contiguous(), plan, mats, heads, ach, H)
+def edge_act_alpha(Y, ln_w, ln_b, alpha_dot, plan, mats, heads, ach, H, z_planes=False):
+    """z_planes: Z is written as the operand planes of the second convolution; the returned Z is a stand-in that only
+    `conv_rotinv_reduce` can consume (see s2_planes_available)."""
+    Y = Y.contiguous()
+    Z, alpha = EdgeActAlphaFn.apply(Y, ln_w, ln_b, alpha_dot.contiguous(), plan, mats, heads, ach, H, z_planes)
+    if z_planes:
+        Z._eqv2_planes, EdgeActAlphaFn.last_planes = EdgeActAlphaFn.last_planes, None
+    return Z, alpha
+
+
+def s2_planes_available(Y, mats, H, width, Cv, heads):
+    """Can the S2 activation write the second convolution's A operand as planes?  f16 engine, the separable kernel, whole
+    rows per 128-thread tile, the maximum of Y known (GEMM epilogue), and the conditions under which ConvRotInvReduceFn keeps
+    Z as planes only."""
+    return (_FEATURES["planes"] and _FEATURES["s2_planes"] and _GEMM_MODE["mode"] in ("f16x3", "f16") and Y.is_cuda
+            and mats.factors is not None and 128 % H == 0 and H % 8 == 0 and (mats.Kr * H) % 8 == 0
+            and width % 8 == 0 and Cv % 32 == 0 and heads <= Cv and _known_absmax(Y.contiguous()) is not None
+            and hasattr(_lib.lib(), "eqv2_s2sep_fwd_planes") and hasattr(_lib.lib(), "eqv2_rotinv_reduce_bwd_planes"))
 
 
 def equiv_norm(x, w, b, norm_type, lmax, eps):

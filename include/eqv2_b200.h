@@ -179,6 +179,12 @@ int eqv2_s2sep_set_tables(const float* host_tables, int nfloats, int slot, void*
 int eqv2_s2sep_fwd(const float* X, long long x_rs, const float* gate, long long g_rs, float* O, long long o_rs,
                    long long R, int C, int lmax, int mmax, int m_primary, int slot,
                    float* absmax /*may be NULL; else 64 zeroed floats receiving max |O|*/, void* stream);
+/* eqv2_s2sep_fwd with the result written as scaled fp16 hi/lo operand planes [2][R][ld] (the A operand of the second SO(2)
+ * convolution, so2_ops.py:150-185) instead of fp32; bound_out[0] <- max(bound_in slots) * bound_c, bound_c >= the operator
+ * norm ||from_grid||_1 ||to_grid||_inf of the activation (and >= 1 for the gate row).  C must divide 128, C % 8 == 0. */
+int eqv2_s2sep_fwd_planes(const float* Xp, long long x_rs, const float* gate, long long g_rs, void* planes, long long plane,
+                          long long ld, const float* bound_in, float bound_c, float* bound_out, long long R, int C, int lmax,
+                          int mmax, int m_primary, int slot, void* stream);
 int eqv2_s2sep_bwd(const float* X, long long x_rs, const float* gate, long long g_rs, const float* dO, long long o_rs,
                    float* dX, long long dx_rs, float* dgate, long long dg_rs, long long R, int C, int lmax, int mmax,
                    int m_primary, int slot, float* absmax /*may be NULL; max |dX|, |dgate|*/, void* stream);

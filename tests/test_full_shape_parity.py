@@ -256,6 +256,8 @@ def test_cuda_path_matches_reference_at_baseline_shape(case, mode):
             if kind in ("oc20", "qm9"):     # ... fed by the producer kernels that write operand planes (no split pass)
                 assert prof.get("eqv2_gather_rotate_fwd_planes", {}).get("calls", 0) >= 1, sorted(prof)
                 assert prof.get("eqv2_rotinv_reduce_bwd_planes", {}).get("calls", 0) >= 1, sorted(prof)
+            if kind == "oc20":              # hidden width 64 divides the S2 kernel's 128-thread tile: Z as planes too
+                assert prof.get("eqv2_s2sep_fwd_planes", {}).get("calls", 0) >= 1, sorted(prof)
         worst = _check_grads(model, ref)
         print(f"PARITY {case} [{mode}]: energy {e_err:.2e} forces {f_err:.2e} (bound {f_tol:.1e}); worst gradient at "
               f"{worst:.2f} of its bound; gemm_f16 launches {prof.get('eqv2_gemm_f16', {}).get('calls', 0)}")

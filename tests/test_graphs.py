@@ -19,7 +19,10 @@ def _run(graphed, batches, mode=None):
                                    attn_alpha_channels=16, attn_value_channels=8, ffn_hidden_channels=32, lmax_list=[3],
                                    mmax_list=[2], edge_channels=32, alpha_drop=0.0, drop_path_rate=0.0, max_radius=8.0).cuda()
     opt = torch.optim.AdamW(model.parameters(), lr=1e-3, fused=True)
-    stepper = graphs.GraphedTrainStep(model, _loss, opt) if graphed else None
+    sync = None
+    if graphed == "captured_sync":      # the data-parallel exchange object, captured with the backward pass (world size 1:
+        sync = pkg("parallel").OverlappedGradientAllReducer(model.parameters(), bucket_mb=0.25)    # no collective issued)
+    stepper = graphs.GraphedTrainStep(model, _loss, opt, grad_sync=sync) if graphed else None
     torch.manual_seed(3)
     out = []
     for d in batches:
@@ -33,6 +36,10 @@ def _run(graphed, batches, mode=None):
             out.append(float(loss))
     if graphed:
         assert stepper.replays == len(batches) and len(stepper.graphs) == 2
+    if sync is not None:                # the gradients the optimizer read LIVE in the flat buckets, sent from inside backward
+        assert len(sync.buckets) >= 3
+        for p in model.parameters():
+            assert p.grad is not None and p.grad.data_ptr() == sync.view[id(p)].data_ptr()
     return out, [p.detach().clone() for p in model.parameters()]
 
 
@@ -50,6 +57,10 @@ def test_graphed_step_follows_eager_trajectory():
     assert max(abs(x - y) / abs(x) for x, y in zip(l0, l1)) < 1e-5, (l0, l1)
     worst = max(float((x - y).abs().max() / (x.abs().max() + 1e-12)) for x, y in zip(p0, p1))
     assert worst < 1e-4, worst
+    # with the bucketed gradient exchange captured inside the replayed backward pass (parallel.OverlappedGradientAllReducer)
+    l3, p3 = _run("captured_sync", batches)
+    assert max(abs(x - y) / abs(x) for x, y in zip(l0, l3)) < 1e-5, (l0, l3)
+    assert max(float((x - y).abs().max() / (x.abs().max() + 1e-12)) for x, y in zip(p0, p3)) < 1e-4
     # the same trajectory on the exact FFMA engine: catches host-side caches that go stale across optimizer updates
     # (fused AdamW does not bump Tensor._version) -- several steps, not just one
     try:
