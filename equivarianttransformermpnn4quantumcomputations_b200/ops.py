@@ -1016,7 +1016,9 @@ class SlabMm(torch.autograd.Function):
             if ctx.needs_input_grad[1] and _grad_wanted(W):
                 gW = SlabOuter.apply(gy, x) if transW else SlabOuter.apply(x, gy)
         if has_bias and ctx.needs_input_grad[2] and ctx.bias_wanted():
-            gb = gy[:, 0, :].sum(0)
+            # column sums of the l = 0 slab = the first C columns of gy read as [N, K*C] (the strided torch reduction took
+            # 16 us per launch, 37 launches per OC20 step)
+            gb = colsum(gy.view(gy.shape[0], -1), 0, gy.shape[2])
         return gx, gW, gb, None
 
 
