@@ -47,6 +47,12 @@ class GraphDropPath(nn.Module):
         # number of structures they were given (set_num_graphs), which is the same value without the synchronisation
         # (and keeps the block capturable in a CUDA graph); without the announcement the reference expression is used.
         num_graphs = _NUM_GRAPHS["n"] if _NUM_GRAPHS["n"] is not None else int(batch.max()) + 1
+        if self.training and self.drop_prob and x.is_cuda and x.dtype == torch.float32 and batch.dtype == torch.long:
+            # same draw as the reference (`torch.rand((num_graphs, 1, 1))` inside drop_path), then ONE kernel for
+            # ones.div(keep) * floor(keep + u), the gather by `batch` and the product (bit-identical)
+            from .. import ops
+            u = torch.rand((num_graphs,) + (1,) * (x.ndim - 1), dtype=x.dtype, device=x.device)
+            return ops.drop_path_scale(x, u, batch, 1.0 - self.drop_prob)
         ones = torch.ones((num_graphs,) + (1,) * (x.ndim - 1), dtype=x.dtype, device=x.device)
         return x * drop_path(ones, self.drop_prob, self.training)[batch]
 

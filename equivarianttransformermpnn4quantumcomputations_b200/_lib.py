@@ -106,6 +106,7 @@ _PROTOS = {
     "eqv2_gata_value_bwd": [P, P, P, P, P, P, L, I, I, I, I, P],
     "eqv2_gata_value_bwd2": [P, P, P, P, P, P, P, P, P, L, I, I, I, I, P],
     "eqv2_s2sep_fwd_planes": [P, L, P, L, P, L, L, P, F, P, L, I, I, I, I, I, P],
+    "eqv2_drop_path_scale": [P, P, P, F, P, L, L, P],
     "eqv2_pair_scores": [P, P, P, P, P, P, L, I, I, I, F, P],
     "eqv2_pair_mix": [P, P, P, P, P, P, L, I, I, I, I, I, P],
     "eqv2_pair_softmax_fwd": [P, P, P, P, L, I, P],

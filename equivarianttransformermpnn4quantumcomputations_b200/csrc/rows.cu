@@ -115,6 +115,35 @@ extern "C" int eqv2_embed_rows(const float* table, const long long* idx, float* 
   return 0;
 }
 
+// Per-graph stochastic depth (reference drop.py:16-27,49-68): out[n, :] = x[n, :] * scale[batch[n]],
+// scale[g] = floor(keep + u[g]) * (1 / keep) -- the reference's `ones.div(keep) * (keep + rand).floor_()` gathered by `batch`
+// and multiplied into the node tensor (seven element-wise launches per call), bit for bit; u is the reference's draw.
+namespace {
+__global__ void drop_path_scale_kernel(const float* __restrict__ x, const float* __restrict__ u,
+                                       const long long* __restrict__ batch, float keep, float* __restrict__ out,
+                                       long long N, long long row) {
+  const float inv = 1.0f / keep;
+  const long long total = N * row;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const long long n = i / row;
+    const float scale = inv * floorf(keep + __ldg(u + __ldg(batch + n)));
+    out[i] = x[i] * scale;
+  }
+}
+}  // namespace
+
+extern "C" int eqv2_drop_path_scale(const float* x, const float* u, const long long* batch, float keep, float* out,
+                                    long long N, long long row, void* stream) {
+  if (N == 0 || row == 0) return 0;
+  EQV2_REQUIRE(keep > 0.f && keep <= 1.f, "eqv2_drop_path_scale: keep probability %f out of (0, 1]", (double)keep);
+  const long long total = N * row;
+  const long long blocks = (total + 255) / 256;
+  EQV2_LAUNCH(drop_path_scale_kernel, dim3((unsigned)(blocks < 148 * 16 ? blocks : 148 * 16)), dim3(256), 0, stream, x, u, batch,
+              keep, out, N, row);
+  EQV2_CHECK_LAUNCH("eqv2_drop_path_scale");
+  return 0;
+}
+
 extern "C" int eqv2_seg_colsum(const float* src, long long ld, const int* rowptr, const int* perm, long long rows, int V,
                                int C, int S, float* partial, float* out, void* stream) {
   EQV2_REQUIRE(V >= 1 && S >= 1 && C >= 0, "eqv2_seg_colsum: bad V/S/C");

@@ -2614,6 +2614,32 @@ def pair_attention_available(H, D):
     return D % 4 == 0 and ((D // 4) & (D // 4 - 1)) == 0 and D // 4 <= 32
 
 
+class DropPathScaleFn(torch.autograd.Function):
+    """x * scale[batch], scale = floor(keep + u) / keep (GraphDropPath, drop.py:49-68): one kernel instead of the
+    reference's seven element-wise launches; linear in x, so the backward is the same kernel on the gradient."""
+
+    @staticmethod
+    def forward(ctx, x, u, batch, keep):
+        _lib.check_device(x, u, batch)
+        x = x.contiguous()
+        out = torch.empty_like(x)
+        N = int(x.shape[0])
+        _lib.call("eqv2_drop_path_scale", x.data_ptr(), u.data_ptr(), batch.data_ptr(), float(keep), out.data_ptr(), N,
+                  x.numel() // max(N, 1), _lib.stream_ptr(), work=(0.0, 8.0 * x.numel()))
+        ctx.save_for_backward(u, batch)
+        ctx.keep = keep
+        return out
+
+    @staticmethod
+    def backward(ctx, g):
+        u, batch = ctx.saved_tensors
+        return DropPathScaleFn.apply(g, u, batch, ctx.keep), None, None, None
+
+
+def drop_path_scale(x, u, batch, keep):
+    return DropPathScaleFn.apply(x, u.reshape(-1).contiguous(), batch.contiguous(), keep)
+
+
 def gata_value(comb, Xp, rl, lmax, mmax):
     return GataValueFn.apply(comb.contiguous(), Xp.contiguous(), rl.contiguous(), lmax, mmax)
 

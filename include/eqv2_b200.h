@@ -337,6 +337,11 @@ int eqv2_gata_value_bwd2(const float* comb, const float* Xp, const float* rl, co
                          const float* v, float* dg, float* d2comb, float* d2Xp, long long E, int H, int lmax, int mmax,
                          int Kr, void* stream);
 
+/* ---- per-graph stochastic depth (EquiformerV2Functions/drop.py:16-27,49-68 `GraphDropPath`) --------------------------
+ * out[n, 0:row] = x[n, 0:row] * (1 / keep) * floor(keep + u[batch[n]]);  u [num_graphs] is the reference's uniform draw. */
+int eqv2_drop_path_scale(const float* x, const float* u, const long long* batch, float keep, float* out, long long N,
+                         long long row, void* stream);
+
 /* ---- all-pairs attention core of the global-attention classes (NewFunctions/GATA_and_all2all/activation.py:419-1567:
  * `attn = softmax(q k^T * scale + bias)` over the atoms of the query's own structure, `out_l = attn @ v_l`; the reference
  * forms an [N_tot, N_tot] map and masks cross-structure pairs) -------------------------------------------------------

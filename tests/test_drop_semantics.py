@@ -143,3 +143,32 @@ def test_whole_model_train_mode_matches_reference_with_same_seed(backend):
         torch.manual_seed(78)
         e2, _ = model(data)
     assert rel_err(e2, e_ref) > 1e-4
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("p", [0.05, 0.5])
+def test_fused_graph_drop_path_kernel_is_bit_identical_to_the_reference_expression(p):
+    """eqv2_drop_path_scale (one launch) against the reference's expression `x * (ones.div(keep) * floor(keep + rand))[batch]`
+    (drop.py:16-27,49-68) with the same seed on the GPU: outputs and input gradients bit for bit."""
+    if not torch.cuda.is_available():
+        pytest.skip("no CUDA device")
+    mine = pkg("EquiformerV2Functions.drop")
+    pkg("_lib")._state["lib"] = None
+    batch = _batch().cuda()
+    x0 = torch.randn(len(batch), 9, 8, generator=torch.Generator().manual_seed(1)).cuda()
+    g0 = torch.randn(len(batch), 9, 8, generator=torch.Generator().manual_seed(2)).cuda()
+    mod = mine.GraphDropPath(p).train(True)
+    for seed in range(4):
+        xa, xb = x0.clone().requires_grad_(True), x0.clone().requires_grad_(True)
+        torch.manual_seed(seed)
+        ones = torch.ones((5, 1, 1), device="cuda")
+        ya = xa * mine.drop_path(ones, p, True)[batch]                 # the reference expression (torch ops)
+        torch.manual_seed(seed)
+        mine.set_num_graphs(5)
+        try:
+            yb = mod(xb, batch)                                        # the kernel
+        finally:
+            mine.set_num_graphs(None)
+        assert torch.equal(ya, yb)
+        ya.backward(g0), yb.backward(g0)
+        assert torch.equal(xa.grad, xb.grad)
