@@ -11,6 +11,8 @@
 // the host checks them against the module's to_grid/from_grid buffers before use.
 // One thread per (row, channel); x / o stay in registers; coefficient order (l- or m-primary) is a
 // compile-time index map.
+#include <stdlib.h>
+
 #include "common.cuh"
 
 namespace {
@@ -88,8 +90,12 @@ __device__ __forceinline__ void lat_bwd(float (&o)[KrOf<L, M>::value()], const f
   }
 }
 
-template <int L, int M, bool MP>
-__global__ void __launch_bounds__(S2_THREADS)
+// MB = minimum resident CTAs per SM the register allocation must allow.  Unconstrained (MB = 1) ptxas takes 197-255 registers
+// for these kernels -> 2 CTAs = 8 warps per SM; MB = 3 caps them at 168 (no spills at lmax 6 / mmax 2, 160 bytes at mmax 6)
+// -> 12 warps per SM: measured on one box (profiles/r02an_*) the OC20 step takes 65.33 (MB = 1) / 63.37 (3) / 64.15 ms (4:
+// 128 registers), the S2 backward 250 / 209 / 216 us per launch.  3 is the default.
+template <int L, int M, bool MP, int MB>
+__global__ void __launch_bounds__(S2_THREADS, MB)
 s2sep_fwd_kernel(const float* __restrict__ X, long long x_rs, const float* __restrict__ gate, long long g_rs,
                  float* __restrict__ O, long long o_rs, long long R, int C, int slot, float* __restrict__ absmax) {
   constexpr int Kr = KrOf<L, M>::value();
@@ -143,8 +149,8 @@ s2sep_fwd_kernel(const float* __restrict__ X, long long x_rs, const float* __res
 // a factor 25-80 above typical maxima: inside the 2^8 margin of the plane format.  A CTA-iteration covers 128 consecutive
 // (row, channel) pairs = 128 / C whole rows (C divides 128); their [Kr][C] blocks are contiguous in the plane rows and leave
 // through the bulk-copy engine, one copy per row and plane.
-template <int L, int M, bool MP>
-__global__ void __launch_bounds__(S2_THREADS)
+template <int L, int M, bool MP, int MB>
+__global__ void __launch_bounds__(S2_THREADS, MB)
 s2sep_fwd_planes_kernel(const float* __restrict__ X, long long x_rs, const float* __restrict__ gate, long long g_rs,
                         long long R, int C, int slot, const Eqv2PlaneArgs PA) {
   constexpr int Kr = KrOf<L, M>::value();
@@ -211,8 +217,8 @@ s2sep_fwd_planes_kernel(const float* __restrict__ X, long long x_rs, const float
 }
 #endif
 
-template <int L, int M, bool MP>
-__global__ void __launch_bounds__(S2_THREADS)
+template <int L, int M, bool MP, int MB>
+__global__ void __launch_bounds__(S2_THREADS, MB)
 s2sep_bwd_kernel(const float* __restrict__ X, long long x_rs, const float* __restrict__ gate, long long g_rs,
                  const float* __restrict__ dO, long long o_rs, float* __restrict__ dX, long long dx_rs,
                  float* __restrict__ dgate, long long dg_rs, long long R, int C, int slot, float* __restrict__ absmax) {
@@ -359,6 +365,15 @@ inline unsigned s2_grid_blocks(long long total) {
 
 }  // namespace
 
+// EQV2_S2_MB=1 selects the unconstrained-register instances of the forward / backward kernels (A/B measurements)
+static int s2_min_blocks() {
+  const char* v = getenv("EQV2_S2_MB");
+  return (v != nullptr && v[0] == '1') ? 1 : 3;
+}
+#define S2_PICK(K, L_, M_)                                                                                               \
+  (s2_min_blocks() == 3 ? (m_primary ? K<L_, M_, true, 3> : K<L_, M_, false, 3>)                                         \
+                        : (m_primary ? K<L_, M_, true, 1> : K<L_, M_, false, 1>))
+
 #define EQV2_S2_CONFIGS(X) X(2, 2) X(3, 2) X(3, 3) X(4, 2) X(4, 4) X(6, 2) X(6, 6) X(1, 1) X(2, 1) X(5, 2) X(5, 5)
 
 extern "C" int eqv2_s2sep_supported(int lmax, int mmax) {
@@ -390,7 +405,7 @@ extern "C" int eqv2_s2sep_fwd(const float* Xp, long long x_rs, const float* gate
   const unsigned blocks = s2_grid_blocks(R * C);
 #define X(L_, M_)                                                                                                        \
   if (lmax == L_ && mmax == M_) {                                                                                        \
-    auto kfn = m_primary ? s2sep_fwd_kernel<L_, M_, true> : s2sep_fwd_kernel<L_, M_, false>;                             \
+    auto kfn = S2_PICK(s2sep_fwd_kernel, L_, M_);                                                                        \
     EQV2_LAUNCH(kfn, dim3(blocks), dim3(S2_THREADS), 0, stream, Xp, x_rs, gate, g_rs, O, o_rs, R, C, slot, absmax);       \
     EQV2_CHECK_LAUNCH("eqv2_s2sep_fwd");                                                                                 \
     return 0;                                                                                                            \
@@ -416,7 +431,7 @@ extern "C" int eqv2_s2sep_fwd_planes(const float* Xp, long long x_rs, const floa
   const unsigned blocks = s2_grid_blocks(R * C);
 #define X(L_, M_)                                                                                                        \
   if (lmax == L_ && mmax == M_) {                                                                                        \
-    auto kfn = m_primary ? s2sep_fwd_planes_kernel<L_, M_, true> : s2sep_fwd_planes_kernel<L_, M_, false>;               \
+    auto kfn = S2_PICK(s2sep_fwd_planes_kernel, L_, M_);                                                                 \
     constexpr int kr_ = KrOf<L_, M_>::value();                                                                           \
     const size_t smem = (size_t)2 * kr_ * S2_THREADS * sizeof(__half);                                                   \
     EQV2_REQUIRE(ld >= (long long)kr_ * C, "s2sep_fwd_planes: ld smaller than Kr * C");                                  \
@@ -438,7 +453,7 @@ extern "C" int eqv2_s2sep_bwd(const float* Xp, long long x_rs, const float* gate
   const unsigned blocks = s2_grid_blocks(R * C);
 #define X(L_, M_)                                                                                                        \
   if (lmax == L_ && mmax == M_) {                                                                                        \
-    auto kfn = m_primary ? s2sep_bwd_kernel<L_, M_, true> : s2sep_bwd_kernel<L_, M_, false>;                             \
+    auto kfn = S2_PICK(s2sep_bwd_kernel, L_, M_);                                                                        \
     EQV2_LAUNCH(kfn, dim3(blocks), dim3(S2_THREADS), 0, stream, Xp, x_rs, gate, g_rs, dO, o_rs, dX, dx_rs, dgate, dg_rs, R, C, slot, absmax); \
     EQV2_CHECK_LAUNCH("eqv2_s2sep_bwd");                                                                                 \
     return 0;                                                                                                            \
