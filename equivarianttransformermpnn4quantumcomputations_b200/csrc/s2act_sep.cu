@@ -290,7 +290,7 @@ __device__ __forceinline__ float eqv2_d2silu(float z) {
 //   dS/dgo'  = F^t[ (T u) . SiLU'(T x) ]             dS/dgo_0 = w SiLU'(gate)      (gated)
 //   dS/dgate = w go_0 SiLU''(gate)
 template <int L, int M, bool MP>
-__global__ void __launch_bounds__(S2_THREADS)
+__global__ void __launch_bounds__(S2_THREADS, 3)
 s2sep_bwd2_kernel(const float* __restrict__ X, long long x_rs, const float* __restrict__ gate, long long g_rs,
                   const float* __restrict__ dO, long long o_rs, const float* __restrict__ U, long long u_rs,
                   const float* __restrict__ Wg, long long w_rs, float* __restrict__ d2X, long long d2x_rs,
