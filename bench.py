@@ -109,6 +109,7 @@ def parse():
     ap.add_argument("--grad-sync", default="overlap", choices=["overlap", "captured", "flat"],
                     help="N > 1: 'overlap' = bucket all-reduces issued from inside the (captured) backward pass on a side "
                          "stream, gradients live in the flat buckets; 'flat' = copy / all-reduce / copy back after it")
+    ap.add_argument("--sync-bucket-mb", type=float, default=32.0, help="N > 1: size of the gradient all-reduce buckets")
     ap.add_argument("--optimizer", default="fused", choices=["fused", "torch"],
                     help="fused: clip_grad_norm_ + AdamW + EMA as one multi-tensor pass (optim.FusedAdamW, the reference's "
                          "optimizer-side step); torch: torch.optim.AdamW(fused=True) alone (the round-1 step)")
@@ -416,7 +417,7 @@ def run_b200(args):
         if world > 1:
             parallel = importlib.import_module(PKG + ".parallel")
             if args.grad_sync in ("overlap", "captured"):     # captured: inside the graph, but after the backward pass
-                sync = parallel.OverlappedGradientAllReducer(model.parameters(), bucket_mb=32,
+                sync = parallel.OverlappedGradientAllReducer(model.parameters(), bucket_mb=args.sync_bucket_mb,
                                                              overlap=args.grad_sync == "overlap")
             else:
                 sync = parallel.GradientAllReducer(model.parameters(), bucket_mb=64).reduce
