@@ -40,8 +40,20 @@ void eqv2_set_error(const char* fmt, ...);
     }                                  \
   } while (0)
 
-// MUFU.EX2 + MUFU.RCP (2 ulp): the S2 grid evaluates 324 sigmoids per (edge, channel)
+// MUFU.EX2 + MUFU.RCP (2 ulp): the S2 grid evaluates 324 sigmoids per (edge, channel).  `__expf` wraps the EX2 in range
+// scaling for denormal results (FSETP + two predicated FMULs per call: 972 of the 8 400 instructions an S2-forward thread
+// executes, and that kernel is issue-bound); the flush-to-zero form needs none -- below 2^-126 the sigmoid is 1 to 38 digits
+// and an overflowing exponent still gives 1 / inf = 0.  Same bits as before everywhere else.
+#ifndef EQV2_CPU_EMU
+__device__ __forceinline__ float eqv2_sigmoid(float x) {
+  float e, r;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(-1.4426950408889634f * x));
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(1.0f + e));
+  return r;
+}
+#else
 __device__ __forceinline__ float eqv2_sigmoid(float x) { return __fdividef(1.0f, 1.0f + __expf(-x)); }
+#endif
 __device__ __forceinline__ float eqv2_silu(float x) { return x * eqv2_sigmoid(x); }
 // d/dx silu(x) = s (1 + x (1 - s))
 __device__ __forceinline__ float eqv2_dsilu(float x) {
