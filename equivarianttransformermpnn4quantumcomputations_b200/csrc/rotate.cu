@@ -355,14 +355,16 @@ __device__ __forceinline__ void stage_rows_async(float* __restrict__ sdst, const
   }
 }
 
-template <int L, int M, int S>
+// CT > 0: C = CW = CT at compile time (the launcher checks), as in the edge-centric kernels: strides and group shape immediate.
+template <int L, int M, int S, int CT = 0>
 __global__ void __launch_bounds__(NODE_THREADS, 2)
 gather_rotate_dx_pipe_kernel(const float* __restrict__ wig, const float* __restrict__ rad, const float* __restrict__ dA,
                              const int* __restrict__ rowptr_src, const int* __restrict__ perm_src,
                              const int* __restrict__ rowptr_dst, const int* __restrict__ perm_dst, float* __restrict__ dx,
-                             int C, int CW, int Kr, int nrad) {
+                             int C_rt, int CW_rt, int Kr_rt, int nrad_rt) {
   constexpr int K = Dim<L>::K, WS = Dim<L>::WS, WP = wpad_off(L + 1);
   constexpr int KR = mpos<L, M>(L, -M) + 1, NS = nslots<L, M>(), ROWS = KR + NS;
+  const int C = CT ? CT : C_rt, CW = CT ? CT : CW_rt, Kr = CT ? KR : Kr_rt, nrad = CT ? NS * 2 * CT : nrad_rt;
   EQV2_DYN_SMEM(float, smem);     // S stages of { columns [ROWS][NODE_THREADS] | Wigner [G][WP] }; reused as sred [K][CW]
   const long long node = blockIdx.x;
   const int G = NODE_THREADS / CW;
@@ -434,12 +436,13 @@ gather_rotate_dx_pipe_kernel(const float* __restrict__ wig, const float* __restr
   }
 }
 
-template <int L, int M, int S>
+template <int L, int M, int S, int CT = 0>
 __global__ void __launch_bounds__(NODE_THREADS, 2)
 rotinv_reduce_fwd_pipe_kernel(const float* __restrict__ val, const float* __restrict__ alpha, const float* __restrict__ wig,
                               const int* __restrict__ rowptr_dst, const int* __restrict__ perm_dst, float* __restrict__ out,
-                              int Cv, int CW, int rows_used, long long val_estride, int heads, float scale) {
+                              int Cv_rt, int CW_rt, int rows_used, long long val_estride, int heads, float scale) {
   constexpr int K = Dim<L>::K, WS = Dim<L>::WS, WP = wpad_off(L + 1);
+  const int Cv = CT ? CT : Cv_rt, CW = CT ? CT : CW_rt;
   constexpr int KR = mpos<L, M>(L, -M) + 1, ROWS = KR + 1;         // value rows + the attention weight
   EQV2_DYN_SMEM(float, smem);
   const long long node = blockIdx.x;
@@ -675,6 +678,10 @@ static int node_env_int(const char* name, int dflt) {
   const char* v = getenv(name);
   return (v != nullptr && v[0] != 0) ? atoi(v) : dflt;
 }
+static bool node_ct() {                                 // EQV2_NODE_CT=0: run-time channel count in the pipelined kernels
+  const char* v = getenv("EQV2_NODE_CT");
+  return v == nullptr || v[0] != '0';
+}
 static bool node_pipe_enabled() {
   const char* v = getenv("EQV2_NODE_PIPE");      // read per call: tests toggle it
   return v == nullptr || v[0] != '0';
@@ -722,7 +729,9 @@ extern "C" int eqv2_gather_rotate_dx(const float* wig, const float* rad, const f
     const int PCW = node_env_int("EQV2_NODE_CW", CW), PS = node_env_int("EQV2_NODE_STAGES", 2);                 \
     const size_t psmem = PS * ((size_t)ROWS_ * NODE_THREADS + (NODE_THREADS / PCW) * wpad_off(L_ + 1)) * sizeof(float); \
     if (aligned && node_pipe_enabled() && psmem <= (PS == 2 ? NODE_PIPE_SMEM_MAX : 224 * 1024)) {               \
-      auto pfn = PS == 3 ? gather_rotate_dx_pipe_kernel<L_, M_, 3> : gather_rotate_dx_pipe_kernel<L_, M_, 2>;  \
+      auto pfn = PS == 3 ? gather_rotate_dx_pipe_kernel<L_, M_, 3>                                             \
+                 : (C == 128 && PCW == 128 && Kr == mpos<L_, M_>(L_, -M_) + 1 && nrad == nslots<L_, M_>() * 256 && node_ct()) \
+                       ? gather_rotate_dx_pipe_kernel<L_, M_, 2, 128> : gather_rotate_dx_pipe_kernel<L_, M_, 2>; \
       if (plane_smem_attr((const void*)pfn, psmem)) return 1;                                                  \
       EQV2_LAUNCH(pfn, dim3((unsigned)N, (C + PCW - 1) / PCW), dim3(NODE_THREADS), psmem, stream, wig, rad, dA, rowptr_src, perm_src, rowptr_dst, perm_dst, dx, C, PCW, Kr, nrad); \
       EQV2_CHECK_LAUNCH("eqv2_gather_rotate_dx");                                                              \
@@ -772,7 +781,9 @@ extern "C" int eqv2_rotinv_reduce_fwd(const float* val, const float* alpha, cons
     const int PCW = node_env_int("EQV2_NODE_CW", CW), PS = node_env_int("EQV2_NODE_STAGES", 2);                 \
     const size_t psmem = PS * ((size_t)ROWS_ * NODE_THREADS + (NODE_THREADS / PCW) * wpad_off(L_ + 1)) * sizeof(float); \
     if (aligned && node_pipe_enabled() && psmem <= (PS == 2 ? NODE_PIPE_SMEM_MAX : 224 * 1024) && rows_used <= ROWS_ - 1) { \
-      auto pfn = PS == 3 ? rotinv_reduce_fwd_pipe_kernel<L_, M_, 3> : rotinv_reduce_fwd_pipe_kernel<L_, M_, 2>; \
+      auto pfn = PS == 3 ? rotinv_reduce_fwd_pipe_kernel<L_, M_, 3>                                            \
+                 : (Cv == 128 && PCW == 128 && node_ct()) ? rotinv_reduce_fwd_pipe_kernel<L_, M_, 2, 128>       \
+                                                          : rotinv_reduce_fwd_pipe_kernel<L_, M_, 2>;           \
       if (plane_smem_attr((const void*)pfn, psmem)) return 1;                                                  \
       EQV2_LAUNCH(pfn, dim3((unsigned)N, (Cv + PCW - 1) / PCW), dim3(NODE_THREADS), psmem, stream, val, alpha, wig, rowptr_dst, perm_dst, out, Cv, PCW, rows_used, val_estride, heads, scale); \
       EQV2_CHECK_LAUNCH("eqv2_rotinv_reduce_fwd");                                                             \
